@@ -1,0 +1,222 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ by running the UNMODIFIED
+reference (/root/reference) under the Bio.SeqIO shim in tests/_ref.
+
+Runs ONLY in the build container (the reference tree does not exist on the GPU
+box).  The fixtures it writes are committed; tests read only the fixtures.
+
+    python tests/golden/make_golden.py
+
+Outputs
+  extract_cases.json  - FASTA texts + KmerExtractor outputs (k{k}.txt lines in
+                        file order) + stdout lines, from
+                        kmerml/kmers/generate.py:21-91
+  stats_cases.json    - KmerFeatureExtractor CSV text for small k files, from
+                        kmerml/kmers/statistics.py:35-147
+  matrix_cases.json   - KmerFeatureBuilder matrices, from
+                        kmerml/ml/features.py:28-117
+  ref_timing.json     - single-core timings of the reference extractor here
+"""
+import base64
+import contextlib
+import io
+import json
+import os
+import random
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parent / "_ref"))      # the Bio shim
+sys.path.insert(1, "/root/reference")              # the unmodified reference
+
+from kmerml.kmers.generate import KmerExtractor              # noqa: E402
+from kmerml.kmers.statistics import KmerFeatureExtractor     # noqa: E402
+from kmerml.ml.features import KmerFeatureBuilder            # noqa: E402
+
+
+G0 = (">chr1 test contig\nAAAAAATCGGNACGTacgtAAAAAATC\nAAAC\n>short\nACGTA\n>chr2\nACGTRACGTACGT\n")
+
+
+def rand_fasta(rng, n_records, max_len, alphabet, width_choices, eol="\n", tail_newline=True,
+               junk_prefix="", weird_ws=False):
+    out = [junk_prefix]
+    for r in range(n_records):
+        out.append(f">rec{r} some description{eol}")
+        length = rng.choice([0, 1, 2, 3, 5, 7, 8, 11, 12, 13, rng.randint(0, max_len), rng.randint(0, max_len)])
+        seq = "".join(rng.choice(alphabet) for _ in range(length))
+        width = rng.choice(width_choices)
+        for i in range(0, len(seq), width):
+            line = seq[i:i + width]
+            if weird_ws and rng.random() < 0.2:
+                line = line + rng.choice([" ", "  ", "\t", " \t ", "\x0b", "\x0c"])
+            if weird_ws and rng.random() < 0.1 and len(line) > 2:
+                j = rng.randint(1, len(line) - 1)
+                line = line[:j] + rng.choice([" ", "\t", " \t"]) + line[j:]
+            out.append(line + eol)
+        if weird_ws and rng.random() < 0.3:
+            out.append(eol)
+    text = "".join(out)
+    if not tail_newline:
+        text = text.rstrip("\r\n")
+    return text
+
+
+def extract_cases():
+    rng = random.Random(20261018)
+    cases = [
+        ("G0", G0, [2, 8]),
+        ("G0_k1to6", G0, [1, 2, 3, 4, 5, 6]),
+        ("G0_unsorted_k", G0, [8, 2, 5]),
+        ("empty_file", "", [3]),
+        ("only_header", ">x\n", [3]),
+        ("no_header", "ACGTACGTACGT\nACGT\n", [3]),
+        ("junk_then_header", "; comment\nACGTACGT\n>r1\nACGTACGTAC\n", [2, 4]),
+        ("gt_midline", ">r1\nACGT>ACGTACGT\nAC>GT\n>r2\nGGGGCCCC\n", [2, 4]),
+        ("crlf", ">r1 x\r\nACGTACGTAC\r\nGTAC\r\n>r2\r\nTTTTGGGGCC\r\n", [3, 5]),
+        ("lone_cr", ">r1\rACGTACGTAC\rGTAC\r>r2\rTTTTGGGGCC", [3, 5]),
+        ("no_trailing_newline", ">r1\nACGTACGTACGTAAC", [4, 12]),
+        ("all_n", ">r1\nNNNNNNNNNNNNNNNNNNNN\n", [2, 5]),
+        ("lower", ">r1\nacgtnacgtacgtacgtttgaca\n", [1, 3, 12]),
+        ("exact_len", ">a\nACGTACGTACGT\n>b\nACGTACGTACG\n>c\nACGTACGTACGTA\n", [3, 12]),
+        ("header_only_records", ">a\n>b\n>c\nACGTAC\n>d\n", [2]),
+        ("blank_lines", ">a\n\nACGT\n\n\nACGT\n\n>b\n\n\nGGGTTTAAAC\n", [2, 8]),
+        ("spaces_tabs", ">a\nAC GT AC GT\nACGT\t\nAC\tGT\nAAAA \t \n", [2, 4]),
+        ("homopolymer", ">a\n" + "A" * 300 + "\n" + "A" * 123 + "\n", [1, 6, 12]),
+        ("single_line_long", ">a\n" + "".join(rng.choice("ACGT") for _ in range(5000)) + "\n", [7, 12]),
+    ]
+    for i in range(24):
+        alphabet = rng.choice(["ACGT", "ACGT", "ACGTN", "ACGTacgtNnRY-*", "ACGTacgt", "AC"])
+        text = rand_fasta(
+            rng,
+            n_records=rng.randint(1, 8),
+            max_len=rng.choice([40, 200, 1500]),
+            alphabet=alphabet,
+            width_choices=rng.choice([[60], [80], [70], [1, 2, 3], [5, 7, 11], [1000000]]),
+            eol=rng.choice(["\n", "\n", "\r\n"]),
+            tail_newline=rng.random() < 0.7,
+            junk_prefix=rng.choice(["", "", "", "junk line\n", "\n\n"]),
+            weird_ws=(i % 3 == 2),
+        )
+        ks = sorted(rng.sample(range(1, 13), rng.randint(1, 4)))
+        if i % 5 == 0:
+            rng.shuffle(ks)
+        cases.append((f"rand{i:02d}", text, ks))
+    # large-k (sparse path) cases
+    for i in range(6):
+        text = rand_fasta(rng, n_records=rng.randint(1, 5), max_len=600,
+                          alphabet=rng.choice(["ACGT", "ACGTN", "ACGTacgtNn"]),
+                          width_choices=[rng.choice([60, 80, 13])])
+        ks = sorted(rng.sample(range(13, 33), 2)) + ([rng.randint(2, 12)] if i % 2 else [])
+        cases.append((f"largek{i:02d}", text, ks))
+
+    out = []
+    for name, text, ks in cases:
+        with tempfile.TemporaryDirectory() as td:
+            fa = Path(td) / "GCF_900000001_1.fa"
+            # newline="" so that the bytes on disk are exactly `text`
+            with open(fa, "w", newline="") as f:
+                f.write(text)
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                ex = KmerExtractor(output_dir=Path(td) / "out", compress=False)
+                org = ex.extract_kmers_from_fasta(fa, list(ks))
+            files = {}
+            for k in dict.fromkeys(ks):
+                files[str(k)] = (Path(td) / "out" / org / f"k{k}.txt").read_text()
+            out.append({
+                "name": name,
+                "fasta_b64": base64.b64encode(text.encode("latin-1")).decode(),
+                "k_values": list(ks),
+                "organism_id": org,
+                "stdout": buf.getvalue().splitlines(),
+                "files": files,
+            })
+    return out
+
+
+def stats_and_matrix_cases(extract):
+    stats, matrices = [], []
+    picks = [c for c in extract if c["name"] in ("G0", "G0_k1to6", "rand00", "rand03", "rand07", "lower", "spaces_tabs")]
+    for feature_set in (None, ["gc_content", "base_counts"],
+                        ["gc_content", "base_counts", "entropy", "cpg_sites", "repeats"]):
+        for c in picks:
+            with tempfile.TemporaryDirectory() as td:
+                kdir = Path(td) / "kmers" / "GCF_900000001_1"
+                kdir.mkdir(parents=True)
+                paths = []
+                for k, txt in c["files"].items():
+                    p = kdir / f"k{k}.txt"
+                    p.write_text(txt)
+                    paths.append(p)
+                buf = io.StringIO()
+                with contextlib.redirect_stdout(buf):
+                    fx = KmerFeatureExtractor(input_paths=paths, output_dir=Path(td) / "features")
+                    res = fx.extract_features(required_features=feature_set)
+                csv_path = res["GCF_900000001_1"]
+                csv_text = csv_path.read_text() if csv_path else None
+                stats.append({"name": c["name"], "feature_set": feature_set,
+                              "k_order": list(c["files"].keys()), "csv": csv_text})
+    # feature matrices over several organisms
+    groups = [("G0", "rand00", "rand03"), ("G0_k1to6", "lower", "rand07")]
+    by_name = {c["name"]: c for c in extract}
+    for metric in ("count", "gc_percent"):
+        for grp in groups:
+            with tempfile.TemporaryDirectory() as td:
+                fdir = Path(td) / "features"
+                ids = []
+                for gi, nm in enumerate(grp):
+                    c = by_name[nm]
+                    org = f"GCF_90000000{gi}_1"
+                    kdir = Path(td) / "kmers" / org
+                    kdir.mkdir(parents=True)
+                    paths = []
+                    for k, txt in c["files"].items():
+                        p = kdir / f"k{k}.txt"
+                        p.write_text(txt)
+                        paths.append(p)
+                    with contextlib.redirect_stdout(io.StringIO()):
+                        KmerFeatureExtractor(input_paths=paths, output_dir=fdir).extract_features()
+                    ids.append(org)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    b = KmerFeatureBuilder(fdir)
+                    m = b.build_from_statistics_files(metric=metric)
+                matrices.append({
+                    "cases": list(grp), "metric": metric,
+                    "index": [str(x) for x in m.index], "columns": [str(x) for x in m.columns],
+                    "values": [[float(v) for v in row] for row in m.to_numpy()],
+                })
+    return stats, matrices
+
+
+def timing():
+    rng = random.Random(0)
+    seq = "".join(rng.choice("ACGT") for _ in range(200_000))
+    text = ">chr\n" + "\n".join(seq[i:i + 80] for i in range(0, len(seq), 80)) + "\n"
+    res = {"n_bases": len(seq), "cpu": os.cpu_count(), "rows": []}
+    with tempfile.TemporaryDirectory() as td:
+        fa = Path(td) / "t.fa"
+        fa.write_text(text)
+        for ks in ([6], [12], [8, 9, 10, 11, 12], list(range(1, 13))):
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                KmerExtractor(output_dir=Path(td) / "o", compress=False).extract_kmers_from_fasta(fa, ks)
+            dt = time.perf_counter() - t0
+            res["rows"].append({"k_values": ks, "seconds": dt, "mbp_per_s": len(seq) / dt / 1e6})
+    return res
+
+
+def main():
+    ext = extract_cases()
+    (HERE / "extract_cases.json").write_text(json.dumps(ext, indent=0))
+    st, mx = stats_and_matrix_cases(ext)
+    (HERE / "stats_cases.json").write_text(json.dumps(st, indent=0))
+    (HERE / "matrix_cases.json").write_text(json.dumps(mx, indent=0))
+    (HERE / "ref_timing.json").write_text(json.dumps(timing(), indent=1))
+    print(f"{len(ext)} extract cases, {len(st)} stats cases, {len(mx)} matrix cases")
+
+
+if __name__ == "__main__":
+    main()
