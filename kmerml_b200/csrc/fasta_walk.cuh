@@ -1,0 +1,282 @@
+// fasta_walk.cuh -- exact FASTA byte-stream semantics for carry-free k-mer walking.
+//
+// Shared between the sm_100a kernels (dense_kernels.cu, ...) and the CPU thread
+// emulator in tests/emu (same source compiled with g++), so the per-thread logic
+// that runs on the GPU is the logic the CPU tests exercise.
+//
+// Semantics restated (paths relative to the reference tree):
+//   * record / line structure of Bio.SeqIO.parse(..., "fasta") as used at
+//     kmerml/kmers/generate.py:39 -- text mode (\n, \r\n, \r end a line), a line
+//     whose first byte is '>' starts a record, everything before the first such
+//     line is ignored, sequence lines are rstrip()ed and ' ' removed;
+//   * upper-casing (generate.py:41) is folded into base_code (c & 0xDF);
+//   * a window is counted iff all k symbols are in ACGT (generate.py:55-56), never
+//     across records (:39), and only in records with len >= max(k_values) (:44-46).
+//
+// Design: every thread owns the windows that START in its 64-byte chunk and reads
+// up to k-1 symbols past the chunk end (the "overhang"), so no state is carried
+// between threads, warps, CTAs or GPUs.  Everything that needs context from
+// BEFORE the chunk (header lines, run ends, short records) is a rare event that
+// is resolved exactly by the byte walkers below, directly on global memory.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KM_HD __host__ __device__ __forceinline__
+#define KM_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define KM_HD inline
+#define KM_HD_NOINLINE inline
+#endif
+
+namespace km {
+
+constexpr int CHUNK = 64;            // bytes owned by one thread per tile
+constexpr int MAX_DENSE_K = 15;
+
+// One genome = one FASTA file's bytes [lo, hi) inside a batch buffer.  `lo` has
+// already been advanced to the first header line (or to hi when there is none).
+struct Genome {
+    const uint8_t* b;
+    uint64_t lo, hi;
+};
+
+enum : int { SYM_INV = 4, SYM_SKIP = 5, SYM_HDR = 6 };
+
+KM_HD bool is_term(uint32_t c) { return c == 10u || c == 13u; }
+KM_HD bool is_softws(uint32_t c) {
+    // what str.rstrip() strips besides ' ', '\n', '\r' (ASCII part of str.isspace())
+    return c == 9u || c == 11u || c == 12u || (c >= 0x1cu && c <= 0x1fu);
+}
+
+// 0..3 (A C G T, lexicographic) for a base of either case, -1 otherwise.
+KM_HD int base_code(uint32_t c) {
+    uint32_t u = c & 0xDFu;
+    uint32_t code = ((u >> 1) ^ (u >> 2)) & 3u;
+    uint32_t expect = (0x54474341u >> (8u * code)) & 0xFFu;   // "ACGT"[code]
+    return (u == expect) ? (int)code : -1;
+}
+
+// Kind of a non-base byte that lies in a sequence line.
+KM_HD_NOINLINE int classify_nonbase(const Genome& g, uint64_t pos, uint32_t c) {
+    if (c == 10u || c == 13u || c == 32u) return SYM_SKIP;
+    if (c == (uint32_t)'>') return (pos == g.lo || is_term(g.b[pos - 1])) ? SYM_HDR : SYM_INV;
+    if (is_softws(c)) {
+        // stripped only when nothing but whitespace follows on the line (rstrip)
+        uint64_t q = pos + 1;
+        while (q < g.hi && (is_softws(g.b[q]) || g.b[q] == 32u)) q++;
+        return (q == g.hi || is_term(g.b[q])) ? SYM_SKIP : SYM_INV;
+    }
+    return SYM_INV;
+}
+
+// Next symbol at or after r (r lies in a sequence line).  Returns 0..3, SYM_INV
+// (r advanced past it) or SYM_HDR (r stays on the '>' / at g.hi).
+KM_HD_NOINLINE int next_symbol(const Genome& g, uint64_t& r) {
+    while (r < g.hi) {
+        uint32_t c = g.b[r];
+        int code = base_code(c);
+        if (code >= 0) { r++; return code; }
+        int kind = classify_nonbase(g, r, c);
+        if (kind == SYM_HDR) return SYM_HDR;
+        r++;
+        if (kind == SYM_INV) return SYM_INV;
+    }
+    return SYM_HDR;
+}
+
+// Previous symbol strictly before q (q lies in a sequence line or on a line
+// start).  Returns 0..3 or SYM_INV with q moved onto that symbol, or SYM_HDR when
+// the record start (a header line, or g.lo) is reached.
+KM_HD_NOINLINE int prev_symbol(const Genome& g, uint64_t& q) {
+    while (q > g.lo) {
+        uint64_t p = q - 1;
+        uint32_t c = g.b[p];
+        if (is_term(c)) {
+            // the line that ends at p: is it a header line?
+            uint64_t ls = p;
+            while (ls > g.lo && !is_term(g.b[ls - 1])) ls--;
+            if (ls < p && g.b[ls] == (uint8_t)'>') { q = ls; return SYM_HDR; }
+            q = p;
+            continue;
+        }
+        q = p;
+        int code = base_code(c);
+        if (code >= 0) return code;
+        int kind = classify_nonbase(g, p, c);
+        if (kind == SYM_SKIP) continue;
+        if (kind == SYM_HDR) return SYM_HDR;       // only if the caller started inside a header line
+        return SYM_INV;
+    }
+    return SYM_HDR;
+}
+
+// Does the record that contains byte position p (in a sequence line) hold at
+// least `need` symbols?  (generate.py:44 -- len(sequence) < max(k_values))
+KM_HD_NOINLINE bool record_len_at_least(const Genome& g, uint64_t p, int need) {
+    int total = 0;
+    uint64_t q = p;
+    while (total < need) {
+        if (prev_symbol(g, q) == SYM_HDR) break;
+        total++;
+    }
+    uint64_t r = p;
+    while (total < need) {
+        if (next_symbol(g, r) == SYM_HDR) break;
+        total++;
+    }
+    return total >= need;
+}
+
+// Is byte position p (> g.lo) inside a header line?  If so *until is the first
+// position after the header's terminator... precisely: the header occupies
+// [line start, *until).  Used once per slice start.
+KM_HD_NOINLINE bool pos_in_header(const Genome& g, uint64_t p, uint64_t* until) {
+    if (p <= g.lo || p >= g.hi) return false;
+    uint64_t ls = p;
+    while (ls > g.lo && !is_term(g.b[ls - 1])) ls--;
+    if (ls == p || g.b[ls] != (uint8_t)'>') return false;
+    uint64_t e = p;
+    while (e < g.hi && !is_term(g.b[e])) e++;
+    *until = e + 1;
+    return true;
+}
+
+// First header line at or after `from` (used to skip text before the first record).
+KM_HD_NOINLINE uint64_t first_header(const uint8_t* b, uint64_t from, uint64_t hi) {
+    uint64_t p = from;
+    while (p < hi) {
+        if (b[p] == (uint8_t)'>' && (p == from || is_term(b[p - 1]))) return p;
+        p++;
+    }
+    return hi;
+}
+
+// ---------------------------------------------------------------------------
+// Dense walking
+// ---------------------------------------------------------------------------
+struct DenseParams {
+    int k;            // the counted level (largest dense k of the call)
+    uint32_t mask;    // 4^k - 1
+    int min_rec;      // records shorter than this are dropped (>= k)
+    int tails;        // emit run-end tails for levels 1..k-1 (needed by the cascade)
+};
+
+struct WalkState {
+    uint32_t kmer;
+    int run;          // valid bases since the last reset, counted from the chunk start
+    int in_hdr;
+    int pend;         // the previous symbol is a base inside my chunk
+    int rec_known;    // 0 unknown, 1 record is long enough, 2 record is too short
+};
+
+// A run of valid bases ended just before `pos` (pos = the invalid symbol, the '>'
+// of the next record, or g.hi).  Emits the last j-mer of the run for every
+// j < k with run >= j: the j-mers that have no (j+1)-mer extension, which the
+// marginalisation cascade cannot see.
+template <class Sink>
+KM_HD_NOINLINE void run_end_event(const Genome& g, uint64_t pos, const DenseParams& P, Sink& sink) {
+    uint64_t q = pos;
+    uint32_t code = 0;
+    int cnt = 0;
+    while (cnt < P.k - 1) {
+        int kind = prev_symbol(g, q);
+        if (kind > 3) break;
+        code |= (uint32_t)kind << (2 * cnt);
+        cnt++;
+    }
+    if (cnt == 0) return;
+    uint64_t inside = pos;
+    (void)prev_symbol(g, inside);                       // byte position of the run's last base
+    if (!record_len_at_least(g, inside, P.min_rec)) return;
+    for (int j = 1; j <= cnt; j++) sink.tail(j, code & ((1u << (2 * j)) - 1u));
+}
+
+template <class Sink>
+KM_HD void on_base(const Genome& g, uint64_t pos, int code, WalkState& s, const DenseParams& P, Sink& sink) {
+    s.kmer = (s.kmer << 2) | (uint32_t)code;
+    s.run++;
+    if (s.run >= P.k) {
+        if (P.min_rec > P.k) {                           // rare mode: k list mixes dense and larger k
+            if (s.rec_known == 0) s.rec_known = (s.run >= P.min_rec || record_len_at_least(g, pos, P.min_rec)) ? 1 : 2;
+            if (s.rec_known == 2) return;
+        }
+        sink.count(s.kmer & P.mask, pos);
+    }
+}
+
+// One byte of the thread's own chunk.
+template <class Sink>
+KM_HD void step_own(const Genome& g, uint64_t pos, uint32_t c, WalkState& s, const DenseParams& P, Sink& sink) {
+    int code = base_code(c);
+    if (code >= 0 && !s.in_hdr) {
+        s.pend = 1;
+        on_base(g, pos, code, s, P, sink);
+        return;
+    }
+    if (s.in_hdr) {
+        if (is_term(c)) s.in_hdr = 0;
+        return;
+    }
+    int kind = classify_nonbase(g, pos, c);
+    if (kind == SYM_SKIP) return;
+    if (s.pend && P.tails) run_end_event(g, pos, P, sink);
+    s.pend = 0;
+    s.run = 0;
+    if (kind == SYM_HDR) { s.in_hdr = 1; s.rec_known = 0; }
+}
+
+// After the own chunk: finish the windows that started in it (at most k-1 more
+// symbols) and detect a run end right at the chunk boundary.
+template <class Sink>
+KM_HD void walk_overhang(const Genome& g, uint64_t ce, WalkState& s, const DenseParams& P, Sink& sink) {
+    if (s.run == 0 || s.in_hdr) return;
+    uint64_t pos = ce;
+    int cnt = 0;
+    while (cnt < P.k - 1 || s.pend) {
+        if (pos >= g.hi) {
+            if (s.pend && P.tails) run_end_event(g, g.hi, P, sink);
+            return;
+        }
+        uint32_t c = g.b[pos];
+        int code = base_code(c);
+        if (code >= 0) {
+            s.pend = 0;                                  // my last base has a successor: not a run end
+            if (cnt >= P.k - 1) return;
+            cnt++;
+            on_base(g, pos, code, s, P, sink);
+            pos++;
+            continue;
+        }
+        int kind = classify_nonbase(g, pos, c);
+        if (kind == SYM_SKIP) { pos++; continue; }
+        if (s.pend && P.tails) run_end_event(g, pos, P, sink);
+        return;
+    }
+}
+
+// Walk one chunk [cs, ce) whose bytes are read through `at(pos)`.
+template <class Sink, class ByteAt>
+KM_HD void walk_chunk(const Genome& g, uint64_t cs, uint64_t ce, bool starts_in_header,
+                      const DenseParams& P, Sink& sink, ByteAt&& at) {
+    WalkState s;
+    s.kmer = 0; s.run = 0; s.in_hdr = starts_in_header ? 1 : 0; s.pend = 0; s.rec_known = 0;
+    for (uint64_t pos = cs; pos < ce; pos++) step_own(g, pos, at(pos), s, P, sink);
+    walk_overhang(g, ce, s, P, sink);
+}
+
+// Header lines that START in [cs, ce): callback(h, until) with the header
+// occupying [h, until) (until = one past its terminator, or > g.hi at EOF).
+template <class F>
+KM_HD void find_headers(const Genome& g, uint64_t cs, uint64_t ce, F&& on_header) {
+    for (uint64_t pos = cs; pos < ce; pos++) {
+        if (g.b[pos] != (uint8_t)'>') continue;
+        if (!(pos == g.lo || is_term(g.b[pos - 1]))) continue;
+        uint64_t e = pos + 1;
+        while (e < g.hi && !is_term(g.b[e])) e++;
+        on_header(pos, e + 1);
+        pos = e;                                         // nothing inside a header line starts a record
+    }
+}
+
+}  // namespace km

@@ -1,0 +1,115 @@
+// CPU emulation of the GPU thread decomposition of the dense counting path.
+// TEST INFRASTRUCTURE: compiles kmerml_b200/csrc/fasta_walk.cuh with g++ and
+// runs every "thread" of every tile sequentially, with the same slice / tile /
+// chunk / header-flag structure the kernels in dense_kernels.cu use.  It lets
+// the carry-free walking logic be fuzzed against the oracle without a GPU.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../kmerml_b200/csrc/fasta_walk.cuh"
+
+using namespace km;
+
+namespace {
+struct EmuSink {
+    std::vector<uint64_t>* top;
+    std::vector<std::vector<uint64_t>>* tails;
+    std::vector<uint64_t>* first;     // optional first-occurrence (min end offset)
+    uint64_t n_count = 0;
+    void count(uint32_t idx, uint64_t pos) {
+        (*top)[idx]++;
+        n_count++;
+        if (first && pos < (*first)[idx]) (*first)[idx] = pos;
+    }
+    void tail(int j, uint32_t idx) { (*tails)[j][idx]++; }
+};
+}  // namespace
+
+extern "C" {
+
+// bytes[0..n): one FASTA file placed at `base_off` inside a zero-padded buffer
+// (exercises unaligned genome starts).  Counts level kmax with the tile/slice
+// geometry given, then cascades to every level 1..kmax.  out_levels receives
+// levels 1..kmax concatenated (uint64).  Returns counted windows at kmax.
+int64_t emu_count_dense(const uint8_t* bytes, uint64_t n, uint64_t base_off, int kmax, int min_rec,
+                        int threads_per_tile, int tiles_per_slice, uint64_t* out_levels,
+                        uint64_t* out_first /* 4^kmax or NULL */) {
+    std::vector<uint8_t> buf(base_off + n + 256, 0);
+    if (n) memcpy(buf.data() + base_off, bytes, n);
+    Genome g;
+    g.b = buf.data();
+    g.hi = base_off + n;
+    g.lo = first_header(g.b, base_off, g.hi);
+
+    DenseParams P;
+    P.k = kmax;
+    P.mask = (kmax >= 16) ? 0xFFFFFFFFu : ((1u << (2 * kmax)) - 1u);
+    P.min_rec = min_rec;
+    P.tails = kmax > 1;
+
+    std::vector<uint64_t> top(1ull << (2 * kmax), 0);
+    std::vector<std::vector<uint64_t>> tails(kmax + 1);
+    for (int j = 1; j < kmax; j++) tails[j].assign(1ull << (2 * j), 0);
+    std::vector<uint64_t> first;
+    if (out_first) first.assign(1ull << (2 * kmax), UINT64_MAX);
+    EmuSink sink;
+    sink.top = &top;
+    sink.tails = &tails;
+    sink.first = out_first ? &first : nullptr;
+
+    const uint64_t tile_bytes = (uint64_t)threads_per_tile * CHUNK;
+    const uint64_t slice_bytes = tile_bytes * (uint64_t)tiles_per_slice;
+    // slices are aligned to absolute multiples of slice_bytes (as on the GPU)
+    uint64_t first_slice = g.lo / slice_bytes;
+    for (uint64_t sb = first_slice * slice_bytes; sb < g.hi; sb += slice_bytes) {
+        uint64_t hdr_carry = 0;
+        if (sb > g.lo) {
+            uint64_t until;
+            if (pos_in_header(g, sb, &until)) hdr_carry = until;
+        }
+        std::vector<uint8_t> flags(threads_per_tile);
+        for (uint64_t tb = sb; tb < std::min(sb + slice_bytes, g.hi); tb += tile_bytes) {
+            std::fill(flags.begin(), flags.end(), 0);
+            uint64_t next_carry = hdr_carry;
+            auto clip = [&](int t, uint64_t& cs, uint64_t& ce) {
+                cs = std::max<uint64_t>(tb + (uint64_t)t * CHUNK, g.lo);
+                ce = std::min<uint64_t>(tb + (uint64_t)(t + 1) * CHUNK, g.hi);
+                return cs < ce;
+            };
+            for (int t = 0; t < threads_per_tile; t++) {            // phase 1
+                uint64_t cs, ce;
+                if (!clip(t, cs, ce)) continue;
+                find_headers(g, cs, ce, [&](uint64_t h, uint64_t until) {
+                    (void)h;
+                    for (int j = t + 1; j < threads_per_tile && tb + (uint64_t)j * CHUNK < until; j++) flags[j] = 1;
+                    next_carry = std::max(next_carry, until);
+                });
+            }
+            for (int t = 0; t < threads_per_tile; t++) {            // phase 2
+                uint64_t cs, ce;
+                if (!clip(t, cs, ce)) continue;
+                bool in_hdr = flags[t] || cs < hdr_carry;
+                walk_chunk(g, cs, ce, in_hdr, P, sink, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
+            }
+            hdr_carry = next_carry;
+        }
+    }
+    // cascade: c_j[p] = sum_b c_{j+1}[4p+b] + tails_j[p]
+    std::vector<std::vector<uint64_t>> lv(kmax + 1);
+    lv[kmax] = top;
+    for (int j = kmax - 1; j >= 1; j--) {
+        lv[j].assign(1ull << (2 * j), 0);
+        for (uint64_t p = 0; p < lv[j].size(); p++)
+            lv[j][p] = lv[j + 1][4 * p] + lv[j + 1][4 * p + 1] + lv[j + 1][4 * p + 2] + lv[j + 1][4 * p + 3] + tails[j][p];
+    }
+    uint64_t off = 0;
+    for (int j = 1; j <= kmax; j++) {
+        memcpy(out_levels + off, lv[j].data(), lv[j].size() * sizeof(uint64_t));
+        off += lv[j].size();
+    }
+    if (out_first) memcpy(out_first, first.data(), first.size() * sizeof(uint64_t));
+    return (int64_t)sink.n_count;
+}
+}
