@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- k-mer count+feature throughput (Gbp/s) of the dense hot path.
+
+Workload (BASELINE.json configs[1], "C2"): 100 synthetic fungal-sized genomes
+(12-40 Mbp, 8-30 records, upper-case 80-column FASTA), k = 1..12 dense histograms
++ frequency rows, on each GPU (weak scaling: every rank counts its own 100 genomes,
+no data-path collective).
+
+One "step" = one pass of the hot path over the whole batch.  Printed JSON line:
+  value     whole-job Gbp/s with the FASTA bytes already resident in HBM
+  e2e       the same through the host-buffer C-ABI call (pinned host FASTA -> H2D ->
+            count -> D2H of counts + frequencies), copies inside the timed region
+  roofline  the dominant kernel (count_kernel) against the measured HBM copy peak
+  cpu_baseline  the oracle port timed on this box's host cores on a bounded sample
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_LIST = list(range(1, 13))
+METRIC = "kmer_count_feature_throughput"
+UNIT = "Gbp/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genomes", type=int, default=100, help="genomes per GPU")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink genome sizes (debug only)")
+    ap.add_argument("--k", default=None, help="comma-separated k list (default 1..12)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-genomes", type=int, default=None)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ workload
+def genome_shape(i, scale):
+    """Record lengths of C2 genome i (seeds 1000+i, 12-40 Mbp, 8..30 records)."""
+    from kmerml_b200 import synth
+    rng = np.random.default_rng(1000 + i)
+    total = int(rng.integers(12_000_000, 40_000_000) * scale)
+    nrec = int(rng.integers(8, 31))
+    return synth.split_lengths(max(total, nrec + 1), nrec, rng)
+
+
+def make_genome_gpu(i, scale, device, torch):
+    """FASTA bytes of genome i generated on the GPU (uniform ACGT, 80 columns)."""
+    lens = genome_shape(i, scale)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(1000 + i)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
+    nl = torch.tensor([10], dtype=torch.uint8, device=device)
+    parts = []
+    for r, L in enumerate(lens):
+        hdr = f">chr{r + 1} synthetic genome {i} record len={L}\n".encode()
+        parts.append(torch.tensor(list(hdr), dtype=torch.uint8, device=device))
+        seq = lut[torch.randint(0, 4, (L,), device=device, generator=gen)]
+        full = (L // 80) * 80
+        if full:
+            body = seq[:full].view(-1, 80)
+            parts.append(torch.cat([body, nl.expand(body.shape[0], 1)], dim=1).reshape(-1))
+        if L > full:
+            parts.append(seq[full:])
+            parts.append(nl)
+    return torch.cat(parts), sum(lens)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, cmax = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx.append(cmax)
+            if t0 - 0.05 <= ts <= t1 + 0.05:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:
+            sm = [float(x.split(",")[1]) for _, x in self.lines[-3:] if len(x.split(",")) > 2] or [0.0]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ CPU legs
+def oracle_seconds(data, ks):
+    import oracle
+    t0 = time.perf_counter()
+    oracle.count_dense_multi(data, ks)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port: the reference itself is
+    pure Python + biopython and cannot travel to the GPU box) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    from kmerml_b200 import synth
+    oracle.build()
+    ks = [int(x) for x in args.k.split(",")] if args.k else K_LIST
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    scale = 0.12 * args.scale                       # ~3 Mbp per genome: a few seconds per core per step
+    genomes = [synth.config2_genome(i, scale=scale) for i in range(cores)]
+    datas = [g.tobytes() for g in genomes]
+    nbases = sum(int(oracle.count_dense(d, 1).sum()) for d in datas)
+
+    def step():
+        with ThreadPoolExecutor(cores) as ex:
+            list(ex.map(lambda d: oracle.count_dense_multi(d, ks), datas))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = nbases / dt / 1e9
+    sample = (f"{cores} synthetic C2-shaped genomes of ~{nbases // cores / 1e6:.1f} Mbp, k={ks[0]}..{ks[-1]}, "
+              f"one genome per thread, {cores} threads (ctypes releases the GIL)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "C2 sample on host cores: " + sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle C port of kmerml/kmers/generate.py:36-58; the unmodified Python reference measured "
+                "0.034 Mbp/s on one core for k=1..12 in the build container (tests/golden/ref_timing.json)",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from kmerml_b200 import _lib, engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    ks = [int(x) for x in args.k.split(",")] if args.k else K_LIST
+    n_gen = args.genomes
+
+    # ---- synthetic batch, generated on the GPU, resident in HBM
+    parts, offs, nbases = [], [0], 0
+    for i in range(n_gen):
+        t, nb = make_genome_gpu(rank * 1000 + i, args.scale, device, torch)
+        parts.append(t)
+        offs.append(offs[-1] + t.numel())
+        nbases += nb
+    fasta = torch.cat(parts)
+    sizes = [p.numel() for p in parts]
+    del parts
+    torch.cuda.synchronize()
+    _, row_len = engine.row_layout(ks)
+    counts = torch.empty((n_gen, row_len), dtype=torch.int32, device=device)
+    freq = torch.empty((n_gen, row_len), dtype=torch.float32, device=device)
+    totals = torch.zeros((n_gen, len(ks)), dtype=torch.int64, device=device)
+    ctx = _lib.context(local)
+
+    def step():
+        engine.count_dense_device(fasta, offs, ks, out_counts=counts, out_freq=freq, out_totals=totals)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    barrier()
+    ctx.profile_enable(True)
+    ctx.profile_read(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    prof = ctx.profile_read(reset=True)
+    ctx.profile_enable(False)
+    clocks = sampler.stop(t0, t1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        nb_all = torch.tensor([nbases], dtype=torch.float64, device=device)
+        dist.all_reduce(nb_all, op=dist.ReduceOp.SUM)
+        total_bases = float(nb_all.item())
+    else:
+        total_bases = float(nbases)
+    ms_per_step = ms / args.steps
+    value = total_bases / (ms_per_step * 1e-3) / 1e9
+
+    # ---- parity gates on the measured outputs (oracle = checker only)
+    parity = {}
+    lay, _ = engine.row_layout(ks)
+    u64 = lambda t: t.to(torch.int64) & 0xFFFFFFFF
+    ok_tot = True
+    for ki, k in enumerate(ks):
+        off, n = lay[k]
+        s = torch.stack([u64(counts[g, off:off + n]).sum() for g in range(n_gen)])
+        ok_tot &= bool(torch.equal(s, totals[:, ki]))
+    parity["sum_counts_equals_windows"] = ok_tot
+    if 12 in ks and 11 in ks:
+        # marginal property: c11[p] >= sum_b c12[4p+b], equality except for run-end tails
+        o12, n12 = lay[12]
+        o11, n11 = lay[11]
+        m = u64(counts[0, o12:o12 + n12]).view(-1, 4).sum(dim=1)
+        d = u64(counts[0, o11:o11 + n11]) - m
+        parity["marginal_k12_to_k11_tails"] = int(d.sum().item())
+        ok_tot &= bool((d >= 0).all().item())
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu:
+        import oracle
+        oracle.build()
+        gi = int(np.argmin(sizes))
+        data = fasta[offs[gi]:offs[gi + 1]].cpu().numpy().tobytes()
+        t_cpu = time.perf_counter()
+        ref = oracle.count_dense_multi(data, ks)
+        t_cpu = time.perf_counter() - t_cpu
+        exact = True
+        for k in ks:
+            off, n = lay[k]
+            got = counts[gi, off:off + n].cpu().numpy().view(np.uint32).astype(np.uint64)
+            exact &= bool(np.array_equal(got, ref[k]))
+        parity["oracle_bit_exact_genome"] = gi
+        parity["oracle_bit_exact"] = exact
+        nb_g = int(ref[1].sum())
+        cpu_baseline = {"value": nb_g / t_cpu / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"smallest genome of the batch ({nb_g / 1e6:.1f} Mbp), k={ks[0]}..{ks[-1]}, "
+                                  f"oracle C port, 1 thread, {t_cpu:.1f} s"}
+        if not exact or not ok_tot:
+            print(json.dumps({"error": "parity gate failed", "parity": parity}))
+            raise SystemExit(3)
+
+    # ---- roofline of the dominant kernel (count_kernel), live CUDA-event timing
+    peak, peak_src = measured_peak()
+    kmax = max(ks)
+    n_count = max(int(prof["count_launches"]), 1)
+    # algorithmic bytes per count launch: one read of the genome's FASTA bytes + one write of
+    # the 4^kmax uint32 count vector it produces (F + 4^k * 4 for this kernel)
+    alg_bytes = float(fasta.numel()) / n_gen + (4 ** kmax) * 4.0
+    t_count = prof["ms_count"] * 1e-3 / n_count
+    achieved = alg_bytes / t_count / 1e9 if t_count > 0 else 0.0
+    step_alg = float(fasta.numel()) + n_gen * row_len * 8.0          # F + sum_k 4^k * (4 + 4) per genome
+    roofline = {
+        "bound": "hbm", "kernel": "count_kernel<global RED>" if kmax > 7 else "count_kernel<smem>",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "peak_source": peak_src,
+        "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": t_count * 1e3,
+        "kernel_share_of_step": prof["ms_count"] / ms if ms > 0 else None,
+        "step_frac": step_alg / (ms_per_step * 1e-3) / 1e9 / peak,
+        "step_alg_bytes": step_alg,
+        "ms": {k: prof[k] / args.steps for k in ("ms_count", "ms_cascade", "ms_finalize", "ms_other")},
+    }
+
+    # ---- end to end through the host-buffer C-ABI call
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = args.e2e_genomes or n_gen
+        try:
+            avail = 0
+            with open("/proc/meminfo") as f:
+                for line in f:
+                    if line.startswith("MemAvailable"):
+                        avail = int(line.split()[1]) * 1024
+            need = lambda n: sum(sizes[:n]) + n * row_len * 8
+            while n_e2e > 1 and need(n_e2e) * 3 > avail:
+                n_e2e //= 2
+            host_bufs = [torch.empty(sizes[i], dtype=torch.uint8, pin_memory=True) for i in range(n_e2e)]
+            for i in range(n_e2e):
+                host_bufs[i].copy_(fasta[offs[i]:offs[i + 1]])
+            hc = torch.empty((n_e2e, row_len), dtype=torch.int32, pin_memory=True)
+            hf = torch.empty((n_e2e, row_len), dtype=torch.float32, pin_memory=True)
+            ht = torch.zeros((n_e2e, len(ks)), dtype=torch.int64, pin_memory=True)
+            torch.cuda.synchronize()
+
+            def e2e_step():
+                engine.count_dense_host(host_bufs, ks, device=device, out_counts=hc, out_freq=hf, out_totals=ht)
+
+            e2e_step()                                        # warm-up (allocates the slots)
+            barrier()
+            t_a = time.perf_counter()
+            n_e2e_steps = max(1, min(args.steps, 2))
+            for _ in range(n_e2e_steps):
+                e2e_step()
+            torch.cuda.synchronize()
+            t_b = time.perf_counter()
+            dt = (t_b - t_a) / n_e2e_steps
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            nb_e2e = float(sum(int(x) for x in ht[:, 0].tolist()))        # k=1 windows = valid bases
+            if world > 1:
+                t = torch.tensor([nb_e2e], dtype=torch.float64, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                nb_e2e = float(t.item())
+            same = torch.equal(hc, counts[:n_e2e].cpu())
+            e2e = {"value": nb_e2e / dt / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": int(sum(sizes[:n_e2e])),
+                   "d2h_bytes_per_step": int(n_e2e * (row_len * 8 + len(ks) * 8)),
+                   "genomes": n_e2e, "ms_per_step": dt * 1e3, "matches_device_path": bool(same),
+                   "api": "kmerml_count_dense_host (pinned host FASTA -> H2D -> count -> D2H counts+freq+totals)"}
+        except Exception as exc:                                  # report, never fake
+            e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:300]}
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"C2: {n_gen} synthetic fungal-sized genomes per GPU (12-40 Mbp x {args.scale:g}), "
+                                   f"k={ks[0]}..{ks[-1]} dense histograms + frequency rows",
+                       "genomes_per_gpu": n_gen, "k_list": ks, "bases_per_gpu": nbases,
+                       "fasta_bytes_per_gpu": int(fasta.numel()),
+                       "l2_policy": "inputs (GBs) and outputs far exceed the 126 MB L2; no explicit flush"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": int(prof["launches"]), "clocks": clocks, "parity": parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,120 @@
+/*
+ * kmerml_b200.h -- C-ABI of libkmerml_b200.so: the B200 (sm_100a) implementation of
+ * kmer-ml's k-mer extraction -> counts -> feature-matrix hot path.
+ *
+ * The reference (Masthetheus/kmer-ml) is pure Python and has no FFI; this header is
+ * the boundary a maintainer would bind with ctypes.  Each entry
+ * point names the reference code it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - every function returns an int status: KMERML_OK or a negative KMERML_ERR_*;
+ *     nothing throws or aborts; kmerml_last_error() gives the thread-local message;
+ *   - plain pointers and sizes only; "d_" pointers are device memory of the context's
+ *     GPU (16-byte aligned), "h_" pointers are host memory (pinned for full speed);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *     device entry points are asynchronous on it, *_host entry points synchronise;
+ *   - k-mer index = lexicographic ACGT (A0 C1 G2 T3), first base most significant;
+ *     the on-disk digit code A0 T1 C2 G3 (kmerml/kmers/generate.py:71) is applied
+ *     only by the text writer;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef KMERML_B200_H
+#define KMERML_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMERML_OK 0
+#define KMERML_ERR_ARG (-1)     /* bad argument */
+#define KMERML_ERR_CUDA (-2)    /* CUDA runtime error (message has the details) */
+#define KMERML_ERR_NOMEM (-3)   /* host or device allocation failed */
+#define KMERML_ERR_RANGE (-4)   /* input too large for the 32-bit counters / offsets */
+
+#define KMERML_FLAG_CANONICAL 1u /* count min(kmer, revcomp) -- opt-in extension, not in the reference */
+
+#define KMERML_MAX_DENSE_K 14    /* dense 4^k histograms up to here; larger k -> kmerml_count_sparse */
+#define KMERML_MAX_K 32
+#define KMERML_N_STATIC_FEATURES 14
+
+typedef struct kmerml_ctx kmerml_ctx;
+
+int kmerml_version(void);
+const char *kmerml_last_error(void);
+
+/* One context per GPU per host thread.  Owns scratch/staging memory and streams. */
+int kmerml_ctx_create(int device, kmerml_ctx **out);
+int kmerml_ctx_destroy(kmerml_ctx *ctx);
+int kmerml_ctx_sm_count(const kmerml_ctx *ctx);
+
+/* Elements in one output row: sum over k_list of 4^k. */
+uint64_t kmerml_row_len(const int *k_list, int nk);
+
+/*
+ * Dense k-mer counting of a batch of genomes that is already resident in HBM.
+ * Replaces kmerml/kmers/generate.py:36-58 (KmerExtractor.extract_kmers_from_fasta:
+ * record loop :39, upper-casing :41, short-record skip :44-46, window loop :49-52,
+ * ACGT filter :55-56, count :58) for every k in k_list (all <= KMERML_MAX_DENSE_K),
+ * and adds the per-genome frequency row (count / windows) the reference only
+ * gestures at (tests/test_ml.py:8 normalize(method="frequency")).
+ *
+ *   d_fasta      raw FASTA file bytes of all genomes, concatenated back to back
+ *   h_offsets    n_genomes+1 byte offsets into d_fasta (genome g = [off[g], off[g+1]))
+ *   k_list       distinct k values, any order (output row follows this order)
+ *   min_record_len  records shorter than this contribute nothing (the reference uses
+ *                max(k_values) over ALL requested k, generate.py:44); 0 = max(k_list)
+ *   d_counts     [n_genomes][counts_stride] uint32, row g = concat_k counts_k[4^k]
+ *   d_freq       same shape in float32, or NULL
+ *   d_totals     [n_genomes][nk] uint64 counted windows per k, or NULL
+ */
+int kmerml_count_dense_batch(kmerml_ctx *ctx, const uint8_t *d_fasta, const uint64_t *h_offsets,
+                             int n_genomes, const int *k_list, int nk, int min_record_len,
+                             unsigned flags, uint32_t *d_counts, uint64_t counts_stride,
+                             float *d_freq, uint64_t freq_stride, uint64_t *d_totals,
+                             void *stream);
+
+/*
+ * The same path end to end from HOST buffers: per genome H2D copy -> counting ->
+ * D2H of counts (+ frequencies, totals), pipelined over three device slots.
+ * h_counts / h_freq / h_totals are laid out like their d_ counterparts.  This is
+ * the call the Python KmerExtractor makes for files on disk.  Synchronous.
+ */
+int kmerml_count_dense_host(kmerml_ctx *ctx, const uint8_t *const *h_fasta, const uint64_t *h_sizes,
+                            int n_genomes, const int *k_list, int nk, int min_record_len,
+                            unsigned flags, uint32_t *h_counts, uint64_t counts_stride,
+                            float *h_freq, uint64_t freq_stride, uint64_t *h_totals);
+
+/*
+ * Byte offset (within the genome) of the last base of the first window of every
+ * k-mer, UINT32_MAX where the k-mer never occurs: sorting the observed bins by
+ * this value gives dict insertion order, i.e. the line order of k{k}.txt
+ * (kmerml/kmers/generate.py:88).  One genome, one k (<= KMERML_MAX_DENSE_K),
+ * genome smaller than 4 GiB.  d_first: uint32[4^k].
+ */
+int kmerml_first_occurrence(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbytes, int k,
+                            int min_record_len, uint32_t *d_first, void *stream);
+
+/*
+ * Measurement hooks (bench.py): with profiling enabled every kernel the library
+ * launches is bracketed by CUDA events on the launching stream.  kmerml_profile_read
+ * synchronises those events and returns the accumulated device time per kernel family
+ * and the number of kernel launches since the last reset.
+ */
+typedef struct kmerml_profile {
+    uint64_t launches;        /* all kernels of this library (memsets excluded) */
+    uint64_t count_launches;  /* counting-kernel launches */
+    double ms_count;          /* device time inside the counting kernels */
+    double ms_cascade;        /* ... the marginalisation cascade */
+    double ms_finalize;       /* ... fold / normalise */
+    double ms_other;          /* prologue and the rest */
+} kmerml_profile;
+int kmerml_profile_enable(kmerml_ctx *ctx, int on);
+int kmerml_profile_read(kmerml_ctx *ctx, kmerml_profile *out, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMERML_B200_H */

@@ -1,0 +1,123 @@
+"""ctypes binding of libkmerml_b200.so (include/kmerml_b200.h).
+
+The product path fails loudly when the CUDA library is missing or no B200 is
+present: there is no CPU fallback anywhere in this package.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkmerml_b200.so")
+
+OK = 0
+FLAG_CANONICAL = 1
+MAX_DENSE_K = 14
+MAX_K = 32
+
+_lib = None
+
+
+class Profile(ctypes.Structure):
+    _fields_ = [("launches", ctypes.c_uint64), ("count_launches", ctypes.c_uint64),
+                ("ms_count", ctypes.c_double), ("ms_cascade", ctypes.c_double),
+                ("ms_finalize", ctypes.c_double), ("ms_other", ctypes.c_double)]
+
+
+class KmermlError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (no GPU needed for loading, only for calling)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m kmerml_b200.build` "
+            "(nvcc, sm_100a). kmerml_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, u32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_uint64
+    L.kmerml_version.restype = i32
+    L.kmerml_last_error.restype = ctypes.c_char_p
+    L.kmerml_ctx_create.argtypes = [i32, ctypes.POINTER(vp)]
+    L.kmerml_ctx_destroy.argtypes = [vp]
+    L.kmerml_ctx_sm_count.argtypes = [vp]
+    L.kmerml_row_len.restype = u64
+    L.kmerml_row_len.argtypes = [vp, i32]
+    L.kmerml_count_dense_batch.argtypes = [vp, vp, vp, i32, vp, i32, i32, u32, vp, u64, vp, u64, vp, vp]
+    L.kmerml_count_dense_host.argtypes = [vp, vp, vp, i32, vp, i32, i32, u32, vp, u64, vp, u64, vp]
+    L.kmerml_first_occurrence.argtypes = [vp, vp, u64, i32, i32, vp, vp]
+    L.kmerml_profile_enable.argtypes = [vp, i32]
+    L.kmerml_profile_read.argtypes = [vp, ctypes.POINTER(Profile), i32]
+    for name in EXPORTS:
+        fn = getattr(L, name)          # AttributeError here = header/library mismatch
+        if fn.restype is ctypes.c_int and name not in ("kmerml_version", "kmerml_ctx_sm_count"):
+            pass
+    _lib = L
+    return L
+
+
+# every symbol include/kmerml_b200.h declares (checked by tests/test_cabi.py)
+EXPORTS = [
+    "kmerml_version", "kmerml_last_error", "kmerml_ctx_create", "kmerml_ctx_destroy",
+    "kmerml_ctx_sm_count", "kmerml_row_len", "kmerml_count_dense_batch",
+    "kmerml_count_dense_host", "kmerml_first_occurrence", "kmerml_profile_enable",
+    "kmerml_profile_read",
+]
+
+
+def check(status):
+    if status != OK:
+        msg = load().kmerml_last_error()
+        raise KmermlError(f"kmerml_b200 error {status}: {msg.decode() if msg else '?'}")
+
+
+class Context:
+    """One per GPU (per host thread).  Wraps kmerml_ctx_create/destroy."""
+
+    def __init__(self, device=0):
+        self._lib = load()
+        self._h = ctypes.c_void_p()
+        check(self._lib.kmerml_ctx_create(int(device), ctypes.byref(self._h)))
+        self.device = int(device)
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise KmermlError("context already destroyed")
+        return self._h
+
+    @property
+    def sm_count(self):
+        return self._lib.kmerml_ctx_sm_count(self.handle)
+
+    def profile_enable(self, on=True):
+        check(self._lib.kmerml_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self, reset=True):
+        p = Profile()
+        check(self._lib.kmerml_profile_read(self.handle, ctypes.byref(p), 1 if reset else 0))
+        return {f: getattr(p, f) for f, _ in Profile._fields_}
+
+    def close(self):
+        if self._h:
+            self._lib.kmerml_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_contexts = {}
+
+
+def context(device=0):
+    """Process-wide context cache, one per device index."""
+    ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = _contexts[device] = Context(device)
+    return ctx

@@ -1,0 +1,541 @@
+// api.cu -- the C-ABI of libkmerml_b200.so (include/kmerml_b200.h) and the host
+// orchestration of the dense counting path.  No torch types, no CPU fallback.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+namespace km {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return KMERML_ERR_CUDA;
+}
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return KMERML_OK;
+        if (p) KM_CUDA(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(bytes, 256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            (void)cudaGetLastError();
+            return fail(KMERML_ERR_NOMEM, "device allocation of " + std::to_string(want) + " bytes failed");
+        }
+        cap = want;
+        return KMERML_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return KMERML_OK;
+        if (p) KM_CUDA(cudaFreeHost(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(bytes, 4096);
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            (void)cudaGetLastError();
+            return fail(KMERML_ERR_NOMEM, "pinned allocation of " + std::to_string(want) + " bytes failed");
+        }
+        cap = want;
+        return KMERML_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// Tables + scratch used by one in-flight counting call.
+struct Workspace {
+    DevBuf tables;      // offsets | GenomeDev | GenomeStats | Slice[]
+    DevBuf scratch;     // pass-through cascade levels
+    PinBuf staging;     // host image of offsets + slices
+    cudaEvent_t staging_free = nullptr;
+    // host-path slot buffers
+    DevBuf fasta, counts, freq, totals;
+    cudaStream_t stream = nullptr;
+    void release() {
+        tables.release(); scratch.release(); staging.release();
+        fasta.release(); counts.release(); freq.release(); totals.release();
+        if (staging_free) cudaEventDestroy(staging_free);
+        if (stream) cudaStreamDestroy(stream);
+        staging_free = nullptr;
+        stream = nullptr;
+    }
+};
+
+}  // namespace km
+
+struct ProfRec {
+    int kind;                 // 0 count, 1 cascade, 2 finalize, 3 other
+    cudaEvent_t a, b;
+};
+
+struct kmerml_ctx {
+    int device = 0;
+    int sm_count = 148;
+    km::Workspace ws[3];
+    // measurement hooks
+    bool profiling = false;
+    uint64_t launches = 0, count_launches = 0;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    double ms[4] = {0, 0, 0, 0};
+};
+
+namespace km {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Brackets a group of launches with events when profiling is on; always counts launches.
+struct Prof {
+    kmerml_ctx* ctx;
+    cudaStream_t s;
+    int kind;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Prof(kmerml_ctx* c, cudaStream_t st, int k, int n_launches) : ctx(c), s(st), kind(k) {
+        ctx->launches += (uint64_t)n_launches;
+        if (k == 0) ctx->count_launches += (uint64_t)n_launches;
+        if (!ctx->profiling) return;
+        a = take();
+        b = take();
+        if (a && b) cudaEventRecord(a, s);
+    }
+    cudaEvent_t take() {
+        cudaEvent_t e = nullptr;
+        if (!ctx->pool.empty()) { e = ctx->pool.back(); ctx->pool.pop_back(); return e; }
+        if (cudaEventCreate(&e) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+        return e;
+    }
+    ~Prof() {
+        if (!a || !b) return;
+        cudaEventRecord(b, s);
+        ctx->recs.push_back({kind, a, b});
+    }
+};
+
+static int build_row(const int* k_list, int nk, RowSpec* row, int* kmax, int* kmin) {
+    if (!k_list || nk < 1 || nk > 14) return fail(KMERML_ERR_ARG, "k_list must hold 1..14 values");
+    row->nk = nk;
+    unsigned long long off = 0;
+    *kmax = 0;
+    *kmin = 99;
+    for (int i = 0; i < nk; i++) {
+        int k = k_list[i];
+        if (k < 1 || k > KMERML_MAX_DENSE_K)
+            return fail(KMERML_ERR_ARG, "dense k must be in 1.." + std::to_string(KMERML_MAX_DENSE_K));
+        for (int j = 0; j < i; j++)
+            if (k_list[j] == k) return fail(KMERML_ERR_ARG, "k_list values must be distinct");
+        row->k[i] = k;
+        row->off[i] = off;
+        off += 1ull << (2 * k);
+        *kmax = std::max(*kmax, k);
+        *kmin = std::min(*kmin, k);
+    }
+    row->off[nk] = off;
+    return KMERML_OK;
+}
+
+// The dense path on device-resident bytes, using one workspace, asynchronous on `s`.
+static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fasta, const uint64_t* h_offsets,
+                            int n_genomes, const int* k_list, int nk, int min_record_len, unsigned flags,
+                            uint32_t* d_counts, uint64_t counts_stride, float* d_freq, uint64_t freq_stride,
+                            uint64_t* d_totals, cudaStream_t s) {
+    RowSpec row;
+    int kmax, kmin;
+    int rc = build_row(k_list, nk, &row, &kmax, &kmin);
+    if (rc) return rc;
+    if (n_genomes < 0) return fail(KMERML_ERR_ARG, "n_genomes < 0");
+    if (n_genomes == 0) return KMERML_OK;
+    if (!d_fasta || !h_offsets || !d_counts) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (((uintptr_t)d_fasta & 15) || ((uintptr_t)d_counts & 15) || (d_freq && ((uintptr_t)d_freq & 15)))
+        return fail(KMERML_ERR_ARG, "device pointers must be 16-byte aligned");
+    if (counts_stride < row.off[nk] || (counts_stride & 3))
+        return fail(KMERML_ERR_ARG, "counts_stride must be >= row length and a multiple of 4");
+    if (d_freq && (freq_stride < row.off[nk] || (freq_stride & 3)))
+        return fail(KMERML_ERR_ARG, "freq_stride must be >= row length and a multiple of 4");
+    int min_rec = min_record_len > 0 ? min_record_len : kmax;
+    if (min_rec < kmax) return fail(KMERML_ERR_ARG, "min_record_len must be >= max(k_list)");
+    for (int g = 0; g < n_genomes; g++) {
+        if (h_offsets[g + 1] < h_offsets[g]) return fail(KMERML_ERR_ARG, "offsets must be non-decreasing");
+        if (h_offsets[g + 1] - h_offsets[g] >= (1ull << 32))
+            return fail(KMERML_ERR_RANGE, "a genome of 4 GiB or more does not fit the 32-bit counters");
+    }
+    const bool use_smem = kmax <= SMEM_MAX_K;
+    const bool canonical = (flags & KMERML_FLAG_CANONICAL) != 0;
+
+    // ---- level map: requested levels live in the caller's row, the rest in scratch
+    LevelMap lm;
+    memset(&lm, 0, sizeof(lm));
+    unsigned long long scratch_stride = 0;
+    for (int j = kmin; j <= kmax; j++) {
+        int ki = -1;
+        for (int i = 0; i < nk; i++)
+            if (row.k[i] == j) ki = i;
+        if (ki >= 0) {
+            lm.off[j] = (long long)row.off[ki];
+        } else {
+            lm.off[j] = -1 - (long long)scratch_stride;
+            scratch_stride += 1ull << (2 * j);
+        }
+    }
+    lm.counts = d_counts;
+    lm.counts_stride = counts_stride;
+    lm.scratch_slots = use_smem ? (uint32_t)n_genomes : 1u;
+    lm.scratch_stride = scratch_stride;
+    if (scratch_stride) {
+        rc = ws.scratch.ensure((size_t)scratch_stride * lm.scratch_slots * 4);
+        if (rc) return rc;
+    }
+    lm.scratch = (uint32_t*)ws.scratch.p;
+
+    // ---- slices
+    const uint64_t total_bytes = h_offsets[n_genomes] - h_offsets[0];
+    const uint64_t target = (uint64_t)ctx->sm_count * 8;
+    std::vector<uint64_t> slice_bytes(n_genomes);
+    std::vector<uint32_t> first_slice(n_genomes + 1);
+    uint64_t n_slices = 0;
+    for (int g = 0; g < n_genomes; g++) {
+        uint64_t bytes = h_offsets[g + 1] - h_offsets[g];
+        uint64_t sb;
+        if (use_smem) {
+            if ((uint64_t)n_genomes >= target) sb = 1ull << 40;
+            else sb = align_up(std::max<uint64_t>(total_bytes / target, 4ull * TILE_BYTES), TILE_BYTES);
+        } else {
+            sb = align_up(std::min<uint64_t>(std::max<uint64_t>(bytes / target, TILE_BYTES), 64ull * TILE_BYTES), TILE_BYTES);
+        }
+        slice_bytes[g] = sb;
+        first_slice[g] = (uint32_t)n_slices;
+        if (bytes) {
+            uint64_t b0 = h_offsets[g] / sb, b1 = (h_offsets[g + 1] - 1) / sb;
+            n_slices += b1 - b0 + 1;
+        }
+        if (n_slices > 0x7fffffffull) return fail(KMERML_ERR_RANGE, "too many slices");
+    }
+    first_slice[n_genomes] = (uint32_t)n_slices;
+
+    // ---- tables: offsets | genomes | stats | slices
+    const size_t off_bytes = align_up((size_t)(n_genomes + 1) * 8, 256);
+    const size_t gen_bytes = align_up((size_t)n_genomes * sizeof(GenomeDev), 256);
+    const size_t st_bytes = align_up((size_t)n_genomes * sizeof(GenomeStats), 256);
+    const size_t sl_bytes = align_up((size_t)std::max<uint64_t>(n_slices, 1) * sizeof(Slice), 256);
+    rc = ws.tables.ensure(off_bytes + gen_bytes + st_bytes + sl_bytes);
+    if (rc) return rc;
+    rc = ws.staging.ensure(off_bytes + sl_bytes);
+    if (rc) return rc;
+    if (!ws.staging_free) KM_CUDA(cudaEventCreateWithFlags(&ws.staging_free, cudaEventDisableTiming));
+    KM_CUDA(cudaEventSynchronize(ws.staging_free));     // previous call's upload has left the staging buffer
+    uint8_t* base = (uint8_t*)ws.tables.p;
+    uint64_t* d_offsets = (uint64_t*)base;
+    GenomeDev* d_genomes = (GenomeDev*)(base + off_bytes);
+    GenomeStats* d_stats = (GenomeStats*)(base + off_bytes + gen_bytes);
+    Slice* d_slices = (Slice*)(base + off_bytes + gen_bytes + st_bytes);
+    uint8_t* hs = (uint8_t*)ws.staging.p;
+    memcpy(hs, h_offsets, (size_t)(n_genomes + 1) * 8);
+    Slice* h_slices = (Slice*)(hs + off_bytes);
+    {
+        uint64_t si = 0;
+        for (int g = 0; g < n_genomes; g++) {
+            if (h_offsets[g + 1] == h_offsets[g]) continue;
+            uint64_t sb = slice_bytes[g];
+            uint64_t b0 = h_offsets[g] / sb, b1 = (h_offsets[g + 1] - 1) / sb;
+            for (uint64_t b = b0; b <= b1; b++) {
+                h_slices[si].genome = (uint32_t)g;
+                h_slices[si].pad = 0;
+                h_slices[si].begin = b * sb;
+                h_slices[si].end = (b + 1) * sb;
+                si++;
+            }
+        }
+    }
+    KM_CUDA(cudaMemcpyAsync(d_offsets, hs, off_bytes, cudaMemcpyHostToDevice, s));
+    KM_CUDA(cudaMemcpyAsync(d_slices, h_slices, sl_bytes, cudaMemcpyHostToDevice, s));
+    KM_CUDA(cudaEventRecord(ws.staging_free, s));
+
+    {
+        Prof pr(ctx, s, 3, 1);
+        rc = launch_prologue(d_fasta, d_offsets, d_genomes, d_stats, n_genomes, s);
+    }
+    if (rc) return rc;
+    const int n_cascade = (kmax - kmin + 4) / 5;
+
+    const size_t row_bytes = (size_t)row.off[nk] * 4;
+    if (use_smem) {
+        KM_CUDA(cudaMemset2DAsync(d_counts, (size_t)counts_stride * 4, 0, row_bytes, (size_t)n_genomes, s));
+        if (scratch_stride) KM_CUDA(cudaMemsetAsync(lm.scratch, 0, (size_t)scratch_stride * n_genomes * 4, s));
+        {
+            Prof pr(ctx, s, 0, 1);
+            rc = launch_count(d_fasta, d_genomes, d_slices, (int)n_slices, kmax, min_rec, kmax > kmin, true, lm, d_stats, s);
+        }
+        if (rc) return rc;
+        for (int g0 = 0; g0 < n_genomes; g0 += 32768) {
+            int ng = std::min(32768, n_genomes - g0);
+            {
+                Prof pr(ctx, s, 1, n_cascade);
+                rc = launch_cascade(lm, kmax, kmin, (uint32_t)g0, ng, s);
+            }
+            if (rc) return rc;
+            {
+                Prof pr(ctx, s, 2, 1);
+                rc = launch_finalize(lm, row, kmax, canonical, d_stats, d_freq, freq_stride, d_totals, (uint32_t)g0, ng, s);
+            }
+            if (rc) return rc;
+        }
+    } else {
+        // one genome at a time so that its 4^k row stays resident in the 126 MB L2
+        for (int g = 0; g < n_genomes; g++) {
+            KM_CUDA(cudaMemsetAsync(d_counts + (size_t)g * counts_stride, 0, row_bytes, s));
+            if (scratch_stride) KM_CUDA(cudaMemsetAsync(lm.scratch, 0, (size_t)scratch_stride * 4, s));
+            int ns = (int)(first_slice[g + 1] - first_slice[g]);
+            {
+                Prof pr(ctx, s, 0, ns > 0 ? 1 : 0);
+                rc = launch_count(d_fasta, d_genomes, d_slices + first_slice[g], ns, kmax, min_rec, kmax > kmin, false, lm, d_stats, s);
+            }
+            if (rc) return rc;
+            {
+                Prof pr(ctx, s, 1, n_cascade);
+                rc = launch_cascade(lm, kmax, kmin, (uint32_t)g, 1, s);
+            }
+            if (rc) return rc;
+            {
+                Prof pr(ctx, s, 2, 1);
+                rc = launch_finalize(lm, row, kmax, canonical, d_stats, d_freq, freq_stride, d_totals, (uint32_t)g, 1, s);
+            }
+            if (rc) return rc;
+        }
+    }
+    return KMERML_OK;
+}
+
+}  // namespace km
+
+using namespace km;
+
+extern "C" {
+
+int kmerml_version(void) { return 100; }
+
+const char* kmerml_last_error(void) { return g_err.c_str(); }
+
+int kmerml_ctx_create(int device, kmerml_ctx** out) {
+    if (!out) return fail(KMERML_ERR_ARG, "out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return fail(KMERML_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(KMERML_ERR_ARG, "device index out of range");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    KM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(KMERML_ERR_CUDA, std::string("built for sm_100a (B200); device is ") + prop.name);
+    kmerml_ctx* ctx = new (std::nothrow) kmerml_ctx();
+    if (!ctx) return fail(KMERML_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    int rc = dense_setup_attributes();
+    if (rc) { delete ctx; return rc; }
+    *out = ctx;
+    return KMERML_OK;
+}
+
+int kmerml_ctx_destroy(kmerml_ctx* ctx) {
+    if (!ctx) return KMERML_OK;
+    DeviceGuard guard(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& w : ctx->ws) w.release();
+    for (auto& r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->pool) cudaEventDestroy(e);
+    delete ctx;
+    return KMERML_OK;
+}
+
+int kmerml_ctx_sm_count(const kmerml_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int kmerml_profile_enable(kmerml_ctx* ctx, int on) {
+    if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
+    ctx->profiling = on != 0;
+    return KMERML_OK;
+}
+
+int kmerml_profile_read(kmerml_ctx* ctx, kmerml_profile* out, int reset) {
+    if (!ctx || !out) return fail(KMERML_ERR_ARG, "null pointer argument");
+    DeviceGuard guard(ctx->device);
+    for (auto& r : ctx->recs) {
+        KM_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0;
+        KM_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        ctx->ms[r.kind] += ms;
+        ctx->pool.push_back(r.a);
+        ctx->pool.push_back(r.b);
+    }
+    ctx->recs.clear();
+    out->launches = ctx->launches;
+    out->count_launches = ctx->count_launches;
+    out->ms_count = ctx->ms[0];
+    out->ms_cascade = ctx->ms[1];
+    out->ms_finalize = ctx->ms[2];
+    out->ms_other = ctx->ms[3];
+    if (reset) {
+        ctx->launches = ctx->count_launches = 0;
+        for (double& m : ctx->ms) m = 0;
+    }
+    return KMERML_OK;
+}
+
+uint64_t kmerml_row_len(const int* k_list, int nk) {
+    uint64_t n = 0;
+    for (int i = 0; k_list && i < nk; i++)
+        if (k_list[i] >= 0 && k_list[i] <= 31) n += 1ull << (2 * k_list[i]);
+    return n;
+}
+
+int kmerml_count_dense_batch(kmerml_ctx* ctx, const uint8_t* d_fasta, const uint64_t* h_offsets, int n_genomes,
+                             const int* k_list, int nk, int min_record_len, unsigned flags, uint32_t* d_counts,
+                             uint64_t counts_stride, float* d_freq, uint64_t freq_stride, uint64_t* d_totals,
+                             void* stream) {
+    if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    return count_dense_core(ctx, ctx->ws[0], d_fasta, h_offsets, n_genomes, k_list, nk, min_record_len, flags,
+                            d_counts, counts_stride, d_freq, freq_stride, d_totals, (cudaStream_t)stream);
+}
+
+int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, const uint64_t* h_sizes, int n_genomes,
+                            const int* k_list, int nk, int min_record_len, unsigned flags, uint32_t* h_counts,
+                            uint64_t counts_stride, float* h_freq, uint64_t freq_stride, uint64_t* h_totals) {
+    if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
+    if (n_genomes < 0) return fail(KMERML_ERR_ARG, "n_genomes < 0");
+    if (n_genomes == 0) return KMERML_OK;
+    if (!h_fasta || !h_sizes || !h_counts) return fail(KMERML_ERR_ARG, "null pointer argument");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    RowSpec row;
+    int kmax, kmin;
+    int rc = build_row(k_list, nk, &row, &kmax, &kmin);
+    if (rc) return rc;
+    const size_t row_len = (size_t)row.off[nk];
+    const size_t row_stride = align_up(row_len, 4);
+    uint64_t max_bytes = 0;
+    for (int g = 0; g < n_genomes; g++) max_bytes = std::max(max_bytes, h_sizes[g]);
+    const int n_slots = std::min(3, n_genomes);
+    for (int i = 0; i < n_slots; i++) {
+        Workspace& w = ctx->ws[i];
+        if (!w.stream) KM_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+        if ((rc = w.fasta.ensure(align_up((size_t)max_bytes + 64, 256)))) return rc;
+        if ((rc = w.counts.ensure(row_stride * 4))) return rc;
+        if (h_freq && (rc = w.freq.ensure(row_stride * 4))) return rc;
+        if ((rc = w.totals.ensure((size_t)nk * 8))) return rc;
+    }
+    for (int g = 0; g < n_genomes; g++) {
+        Workspace& w = ctx->ws[g % n_slots];
+        cudaStream_t s = w.stream;
+        if (h_sizes[g]) KM_CUDA(cudaMemcpyAsync(w.fasta.p, h_fasta[g], (size_t)h_sizes[g], cudaMemcpyHostToDevice, s));
+        uint64_t offs[2] = {0, h_sizes[g]};
+        rc = count_dense_core(ctx, w, (const uint8_t*)w.fasta.p, offs, 1, k_list, nk, min_record_len, flags,
+                              (uint32_t*)w.counts.p, row_stride, h_freq ? (float*)w.freq.p : nullptr, row_stride,
+                              (uint64_t*)w.totals.p, s);
+        if (rc) return rc;
+        KM_CUDA(cudaMemcpyAsync(h_counts + (size_t)g * counts_stride, w.counts.p, row_len * 4, cudaMemcpyDeviceToHost, s));
+        if (h_freq)
+            KM_CUDA(cudaMemcpyAsync(h_freq + (size_t)g * freq_stride, w.freq.p, row_len * 4, cudaMemcpyDeviceToHost, s));
+        if (h_totals)
+            KM_CUDA(cudaMemcpyAsync(h_totals + (size_t)g * nk, w.totals.p, (size_t)nk * 8, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < n_slots; i++) KM_CUDA(cudaStreamSynchronize(ctx->ws[i].stream));
+    return KMERML_OK;
+}
+
+int kmerml_first_occurrence(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, int k, int min_record_len,
+                            uint32_t* d_first, void* stream) {
+    if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
+    if (k < 1 || k > KMERML_MAX_DENSE_K) return fail(KMERML_ERR_ARG, "k out of range");
+    if (!d_first || (nbytes && !d_fasta)) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (((uintptr_t)d_fasta & 15)) return fail(KMERML_ERR_ARG, "device pointers must be 16-byte aligned");
+    if (nbytes >= 0xFFFFFFFFull) return fail(KMERML_ERR_RANGE, "genome too large for 32-bit offsets");
+    int min_rec = min_record_len > 0 ? min_record_len : k;
+    if (min_rec < k) return fail(KMERML_ERR_ARG, "min_record_len must be >= k");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t s = (cudaStream_t)stream;
+    Workspace& ws = ctx->ws[0];
+    KM_CUDA(cudaMemsetAsync(d_first, 0xFF, (size_t)(1ull << (2 * k)) * 4, s));
+    if (!nbytes) return KMERML_OK;
+    const uint64_t sb = align_up(std::min<uint64_t>(std::max<uint64_t>(nbytes / ((uint64_t)ctx->sm_count * 8), TILE_BYTES),
+                                                    64ull * TILE_BYTES), TILE_BYTES);
+    const uint64_t n_slices = (nbytes - 1) / sb + 1;
+    const size_t off_bytes = 256, gen_bytes = 256, st_bytes = 256;
+    const size_t sl_bytes = align_up((size_t)n_slices * sizeof(Slice), 256);
+    int rc = ws.tables.ensure(off_bytes + gen_bytes + st_bytes + sl_bytes);
+    if (rc) return rc;
+    if ((rc = ws.staging.ensure(off_bytes + sl_bytes))) return rc;
+    if (!ws.staging_free) KM_CUDA(cudaEventCreateWithFlags(&ws.staging_free, cudaEventDisableTiming));
+    KM_CUDA(cudaEventSynchronize(ws.staging_free));
+    uint8_t* base = (uint8_t*)ws.tables.p;
+    uint8_t* hs = (uint8_t*)ws.staging.p;
+    uint64_t* ho = (uint64_t*)hs;
+    ho[0] = 0;
+    ho[1] = nbytes;
+    Slice* h_slices = (Slice*)(hs + off_bytes);
+    for (uint64_t b = 0; b < n_slices; b++) {
+        h_slices[b].genome = 0;
+        h_slices[b].pad = 0;
+        h_slices[b].begin = b * sb;
+        h_slices[b].end = (b + 1) * sb;
+    }
+    KM_CUDA(cudaMemcpyAsync(base, hs, off_bytes, cudaMemcpyHostToDevice, s));
+    KM_CUDA(cudaMemcpyAsync(base + off_bytes + gen_bytes + st_bytes, h_slices, sl_bytes, cudaMemcpyHostToDevice, s));
+    KM_CUDA(cudaEventRecord(ws.staging_free, s));
+    rc = launch_prologue(d_fasta, (const uint64_t*)base, (GenomeDev*)(base + off_bytes),
+                         (GenomeStats*)(base + off_bytes + gen_bytes), 1, s);
+    if (rc) return rc;
+    return launch_first_occurrence(d_fasta, (const GenomeDev*)(base + off_bytes),
+                                   (const Slice*)(base + off_bytes + gen_bytes + st_bytes), (int)n_slices, k, min_rec,
+                                   d_first, s);
+}
+
+}  // extern "C"

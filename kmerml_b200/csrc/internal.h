@@ -1,0 +1,82 @@
+// internal.h -- declarations shared by the translation units of libkmerml_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/kmerml_b200.h"
+
+namespace km {
+
+// ---- error plumbing (thread-local message, never throws across the C-ABI) ----
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+#define KM_CUDA(expr)                                        \
+    do {                                                     \
+        cudaError_t e__ = (expr);                            \
+        if (e__ != cudaSuccess) return ::km::cuda_fail(e__, #expr); \
+    } while (0)
+
+// ---- device-side descriptors --------------------------------------------------
+struct GenomeDev {            // one genome's byte range inside the batch buffer
+    uint64_t file_lo;         // start of the file
+    uint64_t lo;              // first header line (set by the prologue kernel)
+    uint64_t hi;              // end of the file
+};
+
+struct GenomeStats {          // per genome, zeroed by the prologue kernel
+    unsigned long long total_top;     // windows counted at the top (largest) level
+    unsigned long long n_tail[16];    // run-end tails per level
+};
+
+struct Slice {                // unit of work of one CTA: bytes [begin, end) of one genome
+    uint32_t genome;
+    uint32_t pad;
+    uint64_t begin, end;      // multiples of the tile size (absolute buffer offsets)
+};
+
+// Where level j (the 4^j histogram) of genome g lives: inside the caller's counts
+// row when k=j was requested, else in the context's scratch (cascade pass-through).
+struct LevelMap {
+    long long off[16];        // >= 0: element offset in the counts row; < 0: -(1 + offset) in scratch
+    uint32_t* counts;
+    uint64_t counts_stride;
+    uint32_t* scratch;
+    uint64_t scratch_stride;
+    uint32_t scratch_slots;
+#ifdef __CUDACC__
+    __host__ __device__ __forceinline__ uint32_t* ptr(uint32_t g, int j) const {
+        long long o = off[j];
+        return o >= 0 ? counts + (uint64_t)g * counts_stride + (uint64_t)o
+                      : scratch + (uint64_t)(g % scratch_slots) * scratch_stride + (uint64_t)(-1 - o);
+    }
+#endif
+};
+
+struct RowSpec {              // the caller's k_list, in row order
+    int nk;
+    int k[16];
+    unsigned long long off[17];   // element offset of each k inside a row; off[nk] = row length
+};
+
+// ---- launchers (dense.cu) -----------------------------------------------------
+constexpr int COUNT_THREADS = 256;                 // threads per CTA of the counting kernels
+constexpr int TILE_BYTES = COUNT_THREADS * 64;     // bytes per tile (64-byte chunk per thread)
+constexpr int SMEM_MAX_K = 7;                      // 4^7 * 4 B = 64 KB shared histogram
+
+int launch_prologue(const uint8_t* d_fasta, const uint64_t* d_offsets, GenomeDev* d_genomes,
+                    GenomeStats* d_stats, int n_genomes, cudaStream_t s);
+int launch_count(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices,
+                 int n_slices, int k, int min_rec, bool tails, bool use_smem, const LevelMap& lm,
+                 GenomeStats* d_stats, cudaStream_t s);
+int launch_cascade(const LevelMap& lm, int k_top, int k_bottom, uint32_t genome0, int n_genomes,
+                   cudaStream_t s);
+int launch_finalize(const LevelMap& lm, const RowSpec& row, int k_top, bool canonical,
+                    const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride,
+                    uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s);
+int launch_first_occurrence(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices,
+                            int n_slices, int k, int min_rec, uint32_t* d_first, cudaStream_t s);
+int dense_setup_attributes();
+
+}  // namespace km

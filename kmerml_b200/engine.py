@@ -1,0 +1,141 @@
+"""Host-side driver of the dense counting path: torch owns device memory and the
+stream, the work is done by libkmerml_b200.so through the C-ABI.
+
+Replaces (reference tree) kmerml/kmers/generate.py:36-58 for k <= 14 and adds the
+frequency rows the reference only gestures at (tests/test_ml.py:8).
+"""
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def row_layout(k_list):
+    """{k: (offset, length)} of the concatenated output row, in k_list order."""
+    out, off = {}, 0
+    for k in k_list:
+        out[k] = (off, 4 ** k)
+        off += 4 ** k
+    return out, off
+
+
+def _dedupe(k_values):
+    ks = list(dict.fromkeys(int(k) for k in k_values))
+    if not ks:
+        raise ValueError("k_values is empty")
+    return ks
+
+
+@dataclass
+class DenseResult:
+    k_list: list
+    counts: torch.Tensor      # [n_genomes, row_len] int32 storage of uint32 counts
+    freq: torch.Tensor        # [n_genomes, row_len] float32 or None
+    totals: torch.Tensor      # [n_genomes, nk] int64 (counted windows per k)
+
+    def counts_of(self, g, k):
+        lay, _ = row_layout(self.k_list)
+        off, n = lay[k]
+        return self.counts[g, off:off + n]
+
+    def freq_of(self, g, k):
+        lay, _ = row_layout(self.k_list)
+        off, n = lay[k]
+        return self.freq[g, off:off + n]
+
+    def counts_numpy(self, g, k):
+        return self.counts_of(g, k).cpu().numpy().view(np.uint32)
+
+
+def _device_index(device):
+    dev = torch.device(device if device is not None else "cuda")
+    if dev.type != "cuda":
+        raise _lib.KmermlError("kmerml_b200 runs on a CUDA device only (no CPU fallback)")
+    return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+def count_dense_device(fasta, offsets, k_values, *, min_record_len=None, canonical=False,
+                       want_freq=True, out_counts=None, out_freq=None, out_totals=None):
+    """Count k-mers of genomes already resident in HBM.
+
+    fasta    uint8 CUDA tensor holding the FASTA bytes of all genomes back to back
+    offsets  n_genomes+1 byte offsets (host ints)
+    """
+    if not torch.cuda.is_available():
+        raise _lib.KmermlError("no CUDA device: kmerml_b200 has no CPU fallback")
+    if not (fasta.is_cuda and fasta.dtype == torch.uint8 and fasta.is_contiguous()):
+        raise ValueError("fasta must be a contiguous uint8 CUDA tensor")
+    ks = _dedupe(k_values)
+    dev = fasta.device.index
+    ctx = _lib.context(dev)
+    L = _lib.load()
+    n = len(offsets) - 1
+    _, row_len = row_layout(ks)
+    counts = out_counts if out_counts is not None else torch.empty((n, row_len), dtype=torch.int32, device=fasta.device)
+    freq = None
+    if want_freq:
+        freq = out_freq if out_freq is not None else torch.empty((n, row_len), dtype=torch.float32, device=fasta.device)
+    totals = out_totals if out_totals is not None else torch.zeros((n, len(ks)), dtype=torch.int64, device=fasta.device)
+    offs = np.asarray(offsets, dtype=np.uint64)
+    karr = np.asarray(ks, dtype=np.int32)
+    stream = torch.cuda.current_stream(fasta.device).cuda_stream
+    _lib.check(L.kmerml_count_dense_batch(
+        ctx.handle, fasta.data_ptr(), offs.ctypes.data, n, karr.ctypes.data, len(ks),
+        int(min_record_len or 0), _lib.FLAG_CANONICAL if canonical else 0,
+        counts.data_ptr(), counts.stride(0), freq.data_ptr() if freq is not None else None,
+        freq.stride(0) if freq is not None else 0, totals.data_ptr(), ctypes.c_void_p(stream)))
+    return DenseResult(ks, counts, freq, totals)
+
+
+def count_dense_host(buffers, k_values, *, min_record_len=None, canonical=False, want_freq=True,
+                     device=None, out_counts=None, out_freq=None, out_totals=None):
+    """End to end from host byte buffers (numpy uint8 arrays / pinned torch tensors): H2D,
+    counting and D2H all inside libkmerml_b200.so.  Returns host (pinned) torch tensors."""
+    if not torch.cuda.is_available():
+        raise _lib.KmermlError("no CUDA device: kmerml_b200 has no CPU fallback")
+    ks = _dedupe(k_values)
+    dev = _device_index(device)
+    ctx = _lib.context(dev)
+    L = _lib.load()
+    n = len(buffers)
+    _, row_len = row_layout(ks)
+    ptrs = (ctypes.c_void_p * max(n, 1))()
+    sizes = np.zeros(max(n, 1), dtype=np.uint64)
+    keep = []
+    for i, b in enumerate(buffers):
+        if isinstance(b, torch.Tensor):
+            assert b.dtype == torch.uint8 and not b.is_cuda and b.is_contiguous()
+            ptrs[i] = b.data_ptr() if b.numel() else None
+            sizes[i] = b.numel()
+        else:
+            a = np.ascontiguousarray(np.frombuffer(b, dtype=np.uint8) if not isinstance(b, np.ndarray) else b)
+            keep.append(a)
+            ptrs[i] = a.ctypes.data if a.size else None
+            sizes[i] = a.size
+    pin = True
+    counts = out_counts if out_counts is not None else torch.empty((n, row_len), dtype=torch.int32, pin_memory=pin)
+    freq = None
+    if want_freq:
+        freq = out_freq if out_freq is not None else torch.empty((n, row_len), dtype=torch.float32, pin_memory=pin)
+    totals = out_totals if out_totals is not None else torch.zeros((n, len(ks)), dtype=torch.int64, pin_memory=pin)
+    karr = np.asarray(ks, dtype=np.int32)
+    _lib.check(L.kmerml_count_dense_host(
+        ctx.handle, ptrs, sizes.ctypes.data, n, karr.ctypes.data, len(ks), int(min_record_len or 0),
+        _lib.FLAG_CANONICAL if canonical else 0, counts.data_ptr(), counts.stride(0),
+        freq.data_ptr() if freq is not None else None, freq.stride(0) if freq is not None else 0,
+        totals.data_ptr()))
+    return DenseResult(ks, counts, freq, totals)
+
+
+def first_occurrence_device(fasta, k, *, min_record_len=None):
+    """uint32[4^k] (as int64 tensor view-safe int32 storage) end offset of each k-mer's first window."""
+    ctx = _lib.context(fasta.device.index)
+    L = _lib.load()
+    out = torch.empty(4 ** k, dtype=torch.int32, device=fasta.device)
+    stream = torch.cuda.current_stream(fasta.device).cuda_stream
+    _lib.check(L.kmerml_first_occurrence(ctx.handle, fasta.data_ptr(), fasta.numel(), int(k),
+                                         int(min_record_len or 0), out.data_ptr(), ctypes.c_void_p(stream)))
+    return out

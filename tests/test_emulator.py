@@ -1,0 +1,65 @@
+"""CPU emulation of the GPU thread decomposition (tests/emu/emu_dense.cpp compiles
+kmerml_b200/csrc/fasta_walk.cuh with g++) against the oracle.  No GPU."""
+import ctypes
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import fuzz_fasta, golden_extract_cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = os.path.join(HERE, "emu", "emu_dense.cpp")
+    so = os.path.join(HERE, "emu", "libemu_dense.so")
+    hdr = os.path.join(HERE, "..", "kmerml_b200", "csrc", "fasta_walk.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+    L = ctypes.CDLL(so)
+    L.emu_count_dense.restype = ctypes.c_int64
+    L.emu_count_dense.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    return L
+
+
+def run_emu(L, data, kmax, min_rec, tpt, tps, base_off):
+    a = np.frombuffer(data, np.uint8) if len(data) else np.zeros(0, np.uint8)
+    out = np.zeros(sum(4 ** j for j in range(1, kmax + 1)), np.uint64)
+    L.emu_count_dense(a.ctypes.data if a.size else None, a.size, base_off, kmax, min_rec, tpt, tps,
+                      out.ctypes.data, None)
+    res, off = {}, 0
+    for j in range(1, kmax + 1):
+        res[j] = out[off:off + 4 ** j]
+        off += 4 ** j
+    return res
+
+
+def check(L, data, kmax, min_rec, tpt, tps, base_off):
+    res = run_emu(L, data, kmax, min_rec, tpt, tps, base_off)
+    for j in range(1, kmax + 1):
+        ref = oracle.count_dense(data, j, min_rec)
+        assert np.array_equal(ref, res[j]), (j, kmax, min_rec, tpt, tps, base_off)
+
+
+def test_emulator_on_goldens(emu):
+    rng = random.Random(11)
+    for c in golden_extract_cases():
+        for kmax in (1, 3, 8):
+            check(emu, c["fasta"], kmax, kmax, rng.choice([1, 2, 4, 8]), rng.choice([1, 2, 5]),
+                  rng.choice([0, 1, 17, 63, 64, 100]))
+
+
+def test_emulator_fuzz(emu):
+    rng = random.Random(7)
+    for _ in range(400):
+        data = fuzz_fasta(rng)
+        kmax = rng.choice([1, 2, 3, 4, 6, 8, 9])
+        mr = kmax if rng.random() < 0.75 else kmax + rng.randint(1, 12)
+        check(emu, data, kmax, mr, rng.choice([1, 2, 3, 4, 8, 16]), rng.choice([1, 2, 3, 100]),
+              rng.choice([0, 0, 3, 31, 64, 77]))

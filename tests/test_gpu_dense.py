@@ -1,0 +1,141 @@
+"""GPU parity of the dense counting path (through the C-ABI) against the oracle and
+the golden fixtures of the unmodified reference.  Integer counts are bit-exact;
+frequencies are float32 within 1e-6 relative of the float64 restatement."""
+import random
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import fuzz_fasta, golden_extract_cases, parse_kmer_file
+
+pytestmark = pytest.mark.gpu
+
+FREQ_RTOL = 1e-6
+
+
+def torch_mod():
+    import torch
+    return torch
+
+
+def gpu_counts(datas, ks, **kw):
+    torch = torch_mod()
+    from kmerml_b200 import engine, synth
+    arrs = [np.frombuffer(d, np.uint8) if len(d) else np.zeros(0, np.uint8) for d in datas]
+    buf, offs = synth.pack(arrs)
+    dev = torch.from_numpy(np.concatenate([buf, np.zeros(64, np.uint8)])).cuda()
+    res = engine.count_dense_device(dev, offs, ks, **kw)
+    torch.cuda.synchronize()
+    return res
+
+
+def check_against_oracle(datas, ks, min_record_len=None, canonical=False):
+    res = gpu_counts(datas, ks, min_record_len=min_record_len, canonical=canonical)
+    ml = min_record_len or max(ks)
+    totals = res.totals.cpu().numpy()
+    for g, d in enumerate(datas):
+        for ki, k in enumerate(res.k_list):
+            ref = oracle.count_dense(d, k, ml)
+            if canonical:
+                ref = oracle.canonical_from_forward(ref, k)
+            got = res.counts_numpy(g, k).astype(np.uint64)
+            assert np.array_equal(ref, got), f"genome {g} k={k}: {np.nonzero(ref != got)[0][:5]}"
+            assert int(totals[g, ki]) == int(ref.sum())
+            f = res.freq_of(g, k).cpu().numpy().astype(np.float64)
+            want = oracle.frequencies(ref)
+            denom = np.maximum(np.abs(want), 1e-300)
+            assert np.all(np.abs(f - want) / denom <= FREQ_RTOL)
+
+
+def test_golden_files_from_gpu_counts():
+    """counts + first-occurrence order reproduce the reference's k{k}.txt lines exactly."""
+    torch = torch_mod()
+    from kmerml_b200 import engine
+    for c in golden_extract_cases():
+        ks = [k for k in dict.fromkeys(c["k_values"]) if k <= 12]
+        if not ks:
+            continue
+        ml = max(c["k_values"])
+        res = gpu_counts([c["fasta"]], ks, min_record_len=ml)
+        a = np.frombuffer(c["fasta"], np.uint8) if len(c["fasta"]) else np.zeros(0, np.uint8)
+        dev = torch.from_numpy(np.concatenate([a, np.zeros(64, np.uint8)])).cuda()[:a.size]
+        for k in ks:
+            counts = res.counts_numpy(0, k)
+            first = engine.first_occurrence_device(dev, k, min_record_len=ml).cpu().numpy().view(np.uint32)
+            nz = np.nonzero(counts)[0]
+            assert np.all(first[nz] != 0xFFFFFFFF) and np.all(first[counts == 0] == 0xFFFFFFFF)
+            order = nz[np.argsort(first[nz], kind="stable")]
+            got = [(oracle.file_digits(b, k), int(counts[b])) for b in order]
+            assert got == parse_kmer_file(c["files"][str(k)]), (c["name"], k)
+
+
+def test_golden_batch_all_cases_one_launch():
+    cases = golden_extract_cases()
+    check_against_oracle([c["fasta"] for c in cases], [1, 2, 3, 5, 7])
+    check_against_oracle([c["fasta"] for c in cases], [8, 4])
+    check_against_oracle([c["fasta"] for c in cases][:12], [12, 11, 3])
+
+
+def test_fuzz_small():
+    rng = random.Random(99)
+    for it in range(12):
+        datas = [fuzz_fasta(rng) for _ in range(rng.randint(1, 40))]
+        ks = sorted(rng.sample(range(1, 13), rng.randint(1, 4)), reverse=rng.random() < 0.3)
+        mr = None if rng.random() < 0.7 else max(ks) + rng.randint(1, 10)
+        check_against_oracle(datas, ks, min_record_len=mr)
+
+
+def test_canonical_opt_in():
+    rng = random.Random(5)
+    datas = [fuzz_fasta(rng, max_len=2000) for _ in range(6)]
+    check_against_oracle(datas, [4, 5, 6], canonical=True)
+    check_against_oracle(datas, [12, 9], canonical=True)
+
+
+def test_medium_genomes_multi_slice():
+    """1-3 Mbp genomes: many slices/tiles per genome, both the shared and the global path."""
+    from kmerml_b200 import synth
+    g1 = synth.fasta_bytes([700_000, 300_001, 11, 250_000], seed=42).tobytes()
+    g2 = synth.config3_genome(7, scale=0.3).tobytes()
+    # N runs and soft-masked lower case in a wrapped genome
+    rng = np.random.default_rng(8)
+    s = np.frombuffer(synth.fasta_bytes([400_000], seed=9).tobytes(), np.uint8).copy()
+    for _ in range(50):
+        i = int(rng.integers(100, len(s) - 5000))
+        n = int(rng.integers(1, 3000))
+        seg = s[i:i + n]
+        seg[seg != 10] = ord("N")
+    low = (s >= 65) & (s <= 90) & (rng.random(len(s)) < 0.3)
+    s[low] += 32
+    s[:s.tolist().index(10)] = np.frombuffer(b">chr1 synthetic record len=400000"[: s.tolist().index(10)], np.uint8)
+    g3 = s.tobytes()
+    check_against_oracle([g1, g2, g3], [6])
+    check_against_oracle([g1, g2, g3], [1, 2, 3, 4, 5, 6, 7])
+    check_against_oracle([g1, g2, g3], [8])
+    check_against_oracle([g1, g3], list(range(1, 13)))
+
+
+def test_host_api_matches_device_api():
+    torch = torch_mod()
+    from kmerml_b200 import engine
+    rng = random.Random(3)
+    datas = [fuzz_fasta(rng, max_len=3000) for _ in range(7)]
+    for ks in ([3, 6], [10, 2, 8]):
+        dres = gpu_counts(datas, ks)
+        hres = engine.count_dense_host(datas, ks)
+        assert torch.equal(dres.counts.cpu(), hres.counts)
+        assert torch.equal(dres.freq.cpu(), hres.freq)
+        assert torch.equal(dres.totals.cpu(), hres.totals)
+
+
+def test_argument_errors():
+    torch = torch_mod()
+    from kmerml_b200 import _lib, engine
+    dev = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    with pytest.raises(_lib.KmermlError):
+        engine.count_dense_device(dev, [0, 64], [15])
+    with pytest.raises(_lib.KmermlError):
+        engine.count_dense_device(dev, [0, 64], [5], min_record_len=3)
+    with pytest.raises(_lib.KmermlError):
+        engine.count_dense_device(dev, [64, 0], [5])

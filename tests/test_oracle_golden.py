@@ -1,0 +1,67 @@
+"""The CPU oracle against the fixtures produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  No GPU."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import golden_extract_cases
+
+CASES = golden_extract_cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_kmer_files_byte_identical(case):
+    ml = max(case["k_values"])
+    for k in dict.fromkeys(case["k_values"]):
+        assert oracle.kmer_file_text(case["fasta"], k, ml) == case["files"][str(k)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_record_messages(case):
+    """'Skipping <id>' / 'Processed <id>' lines of generate.py:45,60 follow from ids + lengths."""
+    ml = max(case["k_values"])
+    want = case["stdout"]
+    got = []
+    for rid, n in oracle.record_ids(case["fasta"]):
+        if n < ml:
+            got.append(f"Skipping {rid}: too short for k-mer extraction")
+        else:
+            got.append(f"Processed chromosome/contig: {rid}")
+    assert got == want
+
+
+def test_g0_survey_values():
+    """The worked example of SURVEY.md section 4 (G0)."""
+    g0 = next(c for c in CASES if c["name"] == "G0")
+    c2 = oracle.count_dense(g0["fasta"], 2, 8)
+    assert int(c2[oracle.kmer_to_code("AA")]) == 12
+    assert int(c2[oracle.kmer_to_code("AT")]) == 2
+    assert int(c2[oracle.kmer_to_code("CG")]) == 6
+    c8 = oracle.count_dense(g0["fasta"], 8, 8)
+    assert int(c8[oracle.kmer_to_code("ACGTACGT")]) == 2
+    assert int(c8.sum()) == 17
+
+
+def test_canonical_identity():
+    rng = np.random.default_rng(3)
+    seq = "".join("ACGT"[i] for i in rng.integers(0, 4, 500))
+    data = f">r\n{seq}\n".encode()
+    for k in (3, 4, 5, 6):
+        fwd = oracle.count_dense(data, k)
+        canon = oracle.canonical_from_forward(fwd, k)
+        assert canon.sum() == fwd.sum()
+        # direct canonical count with the reference's window rules
+        direct = np.zeros(4 ** k, np.uint64)
+        for i in range(len(seq) - k + 1):
+            c = oracle.kmer_to_code(seq[i:i + k])
+            direct[min(c, oracle.revcomp_code(c, k))] += 1
+        assert np.array_equal(direct, canon)
+
+
+def test_sparse_matches_dense():
+    g0 = next(c for c in CASES if c["name"] == "rand04")
+    for k in (3, 8, 12):
+        counts, order = oracle.count_dense(g0["fasta"], k, 12, want_order=True)
+        codes, cnts = oracle.count_sparse(g0["fasta"], k, 12)
+        assert list(codes) == list(order)
+        assert list(cnts) == [counts[b] for b in order]
