@@ -297,7 +297,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         rc = launch_prologue(d_fasta, d_offsets, d_genomes, d_stats, n_genomes, s);
     }
     if (rc) return rc;
-    const int n_cascade = (kmax - kmin + 4) / 5;
+    const int n_cascade = cascade_launches(kmax, kmin);
 
     const size_t row_bytes = (size_t)row.off[nk] * 4;
     if (use_smem) {
@@ -305,7 +305,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         if (scratch_stride) KM_CUDA(cudaMemsetAsync(lm.scratch, 0, (size_t)scratch_stride * n_genomes * 4, s));
         {
             Prof pr(ctx, s, 0, 1);
-            rc = launch_count(d_fasta, d_genomes, d_slices, (int)n_slices, kmax, min_rec, kmax > kmin, true, lm, d_stats, s);
+            rc = launch_count(d_fasta, d_genomes, d_slices, (int)n_slices, kmax, kmin, min_rec, true, lm, d_stats, s);
         }
         if (rc) return rc;
         for (int g0 = 0; g0 < n_genomes; g0 += 32768) {
@@ -329,7 +329,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
             int ns = (int)(first_slice[g + 1] - first_slice[g]);
             {
                 Prof pr(ctx, s, 0, ns > 0 ? 1 : 0);
-                rc = launch_count(d_fasta, d_genomes, d_slices + first_slice[g], ns, kmax, min_rec, kmax > kmin, false, lm, d_stats, s);
+                rc = launch_count(d_fasta, d_genomes, d_slices + first_slice[g], ns, kmax, kmin, min_rec, false, lm, d_stats, s);
             }
             if (rc) return rc;
             {

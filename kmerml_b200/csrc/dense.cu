@@ -199,26 +199,40 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
     if (tid == 0 && sh_total) atomicAdd(&stats[sl.genome].total_top, sh_total);
 }
 
-// Levels k_top-1 .. k_top-depth from level k_top (final) and the tails already
-// accumulated in the lower levels.  Block b owns top-level bins [1024 b, 1024 b + 1024).
+// Levels k_top-1 .. k_top-depth (depth <= 6) from level k_top (final) and the tails
+// already accumulated in the lower levels.  Block b owns top-level bins
+// [4096 b, 4096 b + 4096): each thread reads 16 of them (4 x 128-bit), produces its 4
+// bins of level k_top-1 and 1 bin of level k_top-2 in registers; deeper levels go
+// through a small shared-memory tree.
 __global__ void __launch_bounds__(256)
 cascade_kernel(LevelMap lm, int k_top, int depth, uint32_t genome0) {
     __shared__ uint32_t sh[256];
     const int tid = threadIdx.x;
     const uint32_t g = genome0 + blockIdx.y;
-    const uint64_t n1 = 1ull << (2 * (k_top - 1));
-    const uint64_t p = (uint64_t)blockIdx.x * 256 + tid;
-    uint32_t v = 0;
-    if (p < n1) {
-        const uint4 h = reinterpret_cast<const uint4*>(lm.ptr(g, k_top))[p];
-        uint32_t* lo = lm.ptr(g, k_top - 1);
-        v = h.x + h.y + h.z + h.w + lo[p];
-        lo[p] = v;
+    const uint64_t n2 = k_top >= 2 ? 1ull << (2 * (k_top - 2)) : 0;   // bins at level k_top-2
+    const uint64_t q2 = (uint64_t)blockIdx.x * 256 + tid;
+    uint32_t w = 0;
+    if (k_top >= 2 ? q2 < n2 : q2 == 0) {
+        const uint4* hi = reinterpret_cast<const uint4*>(lm.ptr(g, k_top)) + 4 * q2;
+        uint4 h0 = hi[0], h1 = hi[1], h2 = hi[2], h3 = hi[3];
+        uint4* lo1 = reinterpret_cast<uint4*>(lm.ptr(g, k_top - 1)) + q2;
+        uint4 t = *lo1;
+        t.x += h0.x + h0.y + h0.z + h0.w;
+        t.y += h1.x + h1.y + h1.z + h1.w;
+        t.z += h2.x + h2.y + h2.z + h2.w;
+        t.w += h3.x + h3.y + h3.z + h3.w;
+        *lo1 = t;
+        if (depth >= 2) {
+            uint32_t* lo2 = lm.ptr(g, k_top - 2);
+            w = t.x + t.y + t.z + t.w + lo2[q2];
+            lo2[q2] = w;
+        }
     }
-    sh[tid] = v;
+    if (depth < 3) return;
+    sh[tid] = w;
     __syncthreads();
     int width = 256;
-    for (int d = 2; d <= depth; d++) {
+    for (int d = 3; d <= depth; d++) {
         width >>= 2;
         const int level = k_top - d;
         uint32_t nv = 0;
@@ -242,21 +256,52 @@ __device__ __forceinline__ uint32_t revcomp_code(uint32_t x, int k) {
     return v >> (32 - 2 * k);
 }
 
-__global__ void __launch_bounds__(256)
-finalize_kernel(LevelMap lm, RowSpec row, int k_top, int canonical, const GenomeStats* __restrict__ stats,
-                float* freq, uint64_t freq_stride, uint64_t* totals, uint32_t genome0) {
-    __shared__ unsigned long long tot[16];
+__device__ __forceinline__ void level_totals(const RowSpec& row, int k_top, const GenomeStats* stats, uint32_t g,
+                                             unsigned long long* tot, uint64_t* totals, bool write) {
     const int tid = threadIdx.x;
-    const uint32_t g = genome0 + blockIdx.y;
     if (tid < row.nk) {
         const int j = row.k[tid];
         unsigned long long t = stats[g].total_top;
         for (int i = j; i < k_top; i++) t += stats[g].n_tail[i];
         tot[tid] = t;
-        if (totals && blockIdx.x == 0) totals[(uint64_t)g * row.nk + tid] = t;
+        if (totals && write) totals[(uint64_t)g * row.nk + tid] = t;
     }
     __syncthreads();
-    if (!freq && !canonical) return;
+}
+
+// Frequency rows (count / windows) and window totals; 4 bins per thread, 128-bit I/O.
+__global__ void __launch_bounds__(256)
+finalize_kernel(LevelMap lm, RowSpec row, int k_top, const GenomeStats* __restrict__ stats,
+                float* freq, uint64_t freq_stride, uint64_t* totals, uint32_t genome0) {
+    __shared__ unsigned long long tot[16];
+    const uint32_t g = genome0 + blockIdx.y;
+    level_totals(row, k_top, stats, g, tot, totals, blockIdx.x == 0);
+    if (!freq) return;
+    const unsigned long long n4 = row.off[row.nk] >> 2;
+    const unsigned long long v = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+    if (v >= n4) return;
+    const unsigned long long e = v << 2;
+    int ki = 0;
+    while (ki + 1 < row.nk && e >= row.off[ki + 1]) ki++;
+    const uint4 c = *reinterpret_cast<const uint4*>(lm.counts + (uint64_t)g * lm.counts_stride + e);
+    const double inv = tot[ki] ? 1.0 / (double)tot[ki] : 0.0;
+    float4 f;
+    f.x = (float)((double)c.x * inv);
+    f.y = (float)((double)c.y * inv);
+    f.z = (float)((double)c.z * inv);
+    f.w = (float)((double)c.w * inv);
+    *reinterpret_cast<float4*>(freq + (uint64_t)g * freq_stride + e) = f;
+}
+
+// Canonical mode: fold every requested level onto min(kmer, revcomp) in place, then
+// normalise.  The thread of the smaller index of each {x, rc(x)} pair owns both bins.
+__global__ void __launch_bounds__(256)
+finalize_canonical_kernel(LevelMap lm, RowSpec row, int k_top, const GenomeStats* __restrict__ stats,
+                          float* freq, uint64_t freq_stride, uint64_t* totals, uint32_t genome0) {
+    __shared__ unsigned long long tot[16];
+    const int tid = threadIdx.x;
+    const uint32_t g = genome0 + blockIdx.y;
+    level_totals(row, k_top, stats, g, tot, totals, blockIdx.x == 0);
     const unsigned long long n = row.off[row.nk];
     for (unsigned long long e = (unsigned long long)blockIdx.x * 256 + tid; e < n;
          e += (unsigned long long)gridDim.x * 256) {
@@ -267,18 +312,14 @@ finalize_kernel(LevelMap lm, RowSpec row, int k_top, int canonical, const Genome
         uint32_t* c = lm.ptr(g, j);
         float* f = freq ? freq + (uint64_t)g * freq_stride + row.off[ki] : nullptr;
         const double inv = tot[ki] ? 1.0 / (double)tot[ki] : 0.0;
-        if (!canonical) {
-            f[x] = (float)((double)c[x] * inv);
-        } else {
-            const uint32_t rc = revcomp_code(x, j);
-            if (x < rc) {
-                const uint32_t a = c[x] + c[rc];
-                c[x] = a;
-                c[rc] = 0;
-                if (f) { f[x] = (float)((double)a * inv); f[rc] = 0.0f; }
-            } else if (x == rc) {
-                if (f) f[x] = (float)((double)c[x] * inv);
-            }
+        const uint32_t rc = revcomp_code(x, j);
+        if (x < rc) {
+            const uint32_t a = c[x] + c[rc];
+            c[x] = a;
+            c[rc] = 0;
+            if (f) { f[x] = (float)((double)a * inv); f[rc] = 0.0f; }
+        } else if (x == rc) {
+            if (f) f[x] = (float)((double)c[x] * inv);
         }
     }
 }
@@ -298,20 +339,21 @@ int launch_prologue(const uint8_t* d_fasta, const uint64_t* d_offsets, GenomeDev
     return KMERML_OK;
 }
 
-static DenseParams make_params(int k, int min_rec, bool tails) {
+static DenseParams make_params(int k, int min_rec, bool tails, int tail_lo) {
     DenseParams P;
     P.k = k;
     P.mask = k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
     P.min_rec = min_rec;
     P.tails = tails ? 1 : 0;
+    P.tail_lo = tail_lo;
     return P;
 }
 
 int launch_count(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices, int n_slices,
-                 int k, int min_rec, bool tails, bool use_smem, const LevelMap& lm, GenomeStats* d_stats,
+                 int k, int k_bottom, int min_rec, bool use_smem, const LevelMap& lm, GenomeStats* d_stats,
                  cudaStream_t s) {
     if (n_slices <= 0) return KMERML_OK;
-    DenseParams P = make_params(k, min_rec, tails);
+    DenseParams P = make_params(k, min_rec, k > k_bottom, k_bottom);
     if (use_smem) {
         size_t smem = (size_t)(1u << (2 * k)) * 4;
         count_kernel<1><<<n_slices, COUNT_THREADS, smem, s>>>(d_fasta, d_genomes, d_slices, P, lm, d_stats, nullptr);
@@ -325,7 +367,7 @@ int launch_count(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice
 int launch_first_occurrence(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices,
                             int n_slices, int k, int min_rec, uint32_t* d_first, cudaStream_t s) {
     if (n_slices <= 0) return KMERML_OK;
-    DenseParams P = make_params(k, min_rec, false);
+    DenseParams P = make_params(k, min_rec, false, k);
     LevelMap lm = {};
     count_kernel<2><<<n_slices, COUNT_THREADS, 0, s>>>(d_fasta, d_genomes, d_slices, P, lm, nullptr, d_first);
     KM_CUDA(cudaGetLastError());
@@ -336,9 +378,9 @@ int launch_cascade(const LevelMap& lm, int k_top, int k_bottom, uint32_t genome0
                    cudaStream_t s) {
     int top = k_top;
     while (top > k_bottom) {
-        int depth = top - k_bottom < 5 ? top - k_bottom : 5;
-        uint64_t n1 = 1ull << (2 * (top - 1));
-        dim3 grid((unsigned)((n1 + 255) / 256), (unsigned)n_genomes);
+        int depth = top - k_bottom < 6 ? top - k_bottom : 6;
+        uint64_t n2 = top >= 2 ? 1ull << (2 * (top - 2)) : 1;
+        dim3 grid((unsigned)((n2 + 255) / 256), (unsigned)n_genomes);
         cascade_kernel<<<grid, 256, 0, s>>>(lm, top, depth, genome0);
         KM_CUDA(cudaGetLastError());
         top -= depth;
@@ -346,17 +388,24 @@ int launch_cascade(const LevelMap& lm, int k_top, int k_bottom, uint32_t genome0
     return KMERML_OK;
 }
 
+int cascade_launches(int k_top, int k_bottom) { return (k_top - k_bottom + 5) / 6; }
+
 int launch_finalize(const LevelMap& lm, const RowSpec& row, int k_top, bool canonical,
                     const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride, uint64_t* d_totals,
                     uint32_t genome0, int n_genomes, cudaStream_t s) {
     if (n_genomes <= 0) return KMERML_OK;
     unsigned long long n = row.off[row.nk];
-    unsigned gx = (unsigned)((n + 256ull * 8 - 1) / (256ull * 8));
-    if (gx < 1) gx = 1;
-    if (gx > 148u * 16u) gx = 148u * 16u;
-    dim3 grid(gx, (unsigned)n_genomes);
-    finalize_kernel<<<grid, 256, 0, s>>>(lm, row, k_top, canonical ? 1 : 0, d_stats, d_freq, freq_stride,
-                                         d_totals, genome0);
+    if (canonical) {
+        unsigned gx = (unsigned)((n + 256ull * 8 - 1) / (256ull * 8));
+        if (gx < 1) gx = 1;
+        if (gx > 148u * 16u) gx = 148u * 16u;
+        dim3 grid(gx, (unsigned)n_genomes);
+        finalize_canonical_kernel<<<grid, 256, 0, s>>>(lm, row, k_top, d_stats, d_freq, freq_stride, d_totals, genome0);
+    } else {
+        unsigned gx = d_freq ? (unsigned)(((n >> 2) + 255) / 256) : 1u;
+        dim3 grid(gx, (unsigned)n_genomes);
+        finalize_kernel<<<grid, 256, 0, s>>>(lm, row, k_top, d_stats, d_freq, freq_stride, d_totals, genome0);
+    }
     KM_CUDA(cudaGetLastError());
     return KMERML_OK;
 }

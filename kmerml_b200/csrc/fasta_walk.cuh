@@ -159,7 +159,8 @@ struct DenseParams {
     int k;            // the counted level (largest dense k of the call)
     uint32_t mask;    // 4^k - 1
     int min_rec;      // records shorter than this are dropped (>= k)
-    int tails;        // emit run-end tails for levels 1..k-1 (needed by the cascade)
+    int tails;        // emit run-end tails for levels tail_lo..k-1 (needed by the cascade)
+    int tail_lo;      // lowest level the cascade descends to
 };
 
 struct WalkState {
@@ -185,11 +186,11 @@ KM_HD_NOINLINE void run_end_event(const Genome& g, uint64_t pos, const DensePara
         code |= (uint32_t)kind << (2 * cnt);
         cnt++;
     }
-    if (cnt == 0) return;
+    if (cnt == 0 || cnt < P.tail_lo) return;
     uint64_t inside = pos;
     (void)prev_symbol(g, inside);                       // byte position of the run's last base
     if (!record_len_at_least(g, inside, P.min_rec)) return;
-    for (int j = 1; j <= cnt; j++) sink.tail(j, code & ((1u << (2 * j)) - 1u));
+    for (int j = P.tail_lo > 1 ? P.tail_lo : 1; j <= cnt; j++) sink.tail(j, code & ((1u << (2 * j)) - 1u));
 }
 
 template <class Sink>

@@ -68,10 +68,11 @@ constexpr int SMEM_MAX_K = 7;                      // 4^7 * 4 B = 64 KB shared h
 int launch_prologue(const uint8_t* d_fasta, const uint64_t* d_offsets, GenomeDev* d_genomes,
                     GenomeStats* d_stats, int n_genomes, cudaStream_t s);
 int launch_count(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices,
-                 int n_slices, int k, int min_rec, bool tails, bool use_smem, const LevelMap& lm,
+                 int n_slices, int k, int k_bottom, int min_rec, bool use_smem, const LevelMap& lm,
                  GenomeStats* d_stats, cudaStream_t s);
 int launch_cascade(const LevelMap& lm, int k_top, int k_bottom, uint32_t genome0, int n_genomes,
                    cudaStream_t s);
+int cascade_launches(int k_top, int k_bottom);
 int launch_finalize(const LevelMap& lm, const RowSpec& row, int k_top, bool canonical,
                     const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride,
                     uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s);

@@ -48,6 +48,7 @@ int64_t emu_count_dense(const uint8_t* bytes, uint64_t n, uint64_t base_off, int
     P.mask = (kmax >= 16) ? 0xFFFFFFFFu : ((1u << (2 * kmax)) - 1u);
     P.min_rec = min_rec;
     P.tails = kmax > 1;
+    P.tail_lo = 1;
 
     std::vector<uint64_t> top(1ull << (2 * kmax), 0);
     std::vector<std::vector<uint64_t>> tails(kmax + 1);
