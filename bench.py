@@ -311,25 +311,44 @@ def run_ours(args):
             print(json.dumps({"error": "parity gate failed", "parity": parity}))
             raise SystemExit(3)
 
-    # ---- roofline of the dominant kernel (count_kernel), live CUDA-event timing
+    # ---- roofline of the dominant kernel, live CUDA-event timing (kmerml_profile_read)
     peak, peak_src = measured_peak()
     kmax = max(ks)
-    n_count = max(int(prof["count_launches"]), 1)
-    # algorithmic bytes per count launch: one read of the genome's FASTA bytes + one write of
-    # the 4^kmax uint32 count vector it produces (F + 4^k * 4 for this kernel)
-    alg_bytes = float(fasta.numel()) / n_gen + (4 ** kmax) * 4.0
-    t_count = prof["ms_count"] * 1e-3 / n_count
-    achieved = alg_bytes / t_count / 1e9 if t_count > 0 else 0.0
-    step_alg = float(fasta.numel()) + n_gen * row_len * 8.0          # F + sum_k 4^k * (4 + 4) per genome
+    F = float(fasta.numel())
+    out_bytes = n_gen * row_len * 8.0                          # sum_k 4^k * (4 + 4) per genome
+    step_alg = F + out_bytes                                   # B_alg per step
+    per_step = {k: prof[k] / args.steps for k in prof if k.startswith("ms_")}
+    # algorithmic bytes each kernel family is responsible for, per step
+    if per_step.get("ms_partition", 0) > 0:
+        alg = {"ms_partition": F,                               # one read of the FASTA bytes
+               "ms_bucket": n_gen * sum(4 ** k for k in ks if k >= max(kmax - 7, min(ks))) * 8.0,
+               "ms_cascade": n_gen * sum(4 ** k for k in ks if k < max(kmax - 7, min(ks))) * 4.0,
+               "ms_finalize": n_gen * sum(4 ** k for k in ks if k < max(kmax - 7, min(ks))) * 4.0}
+        names = {"ms_partition": "partition_kernel", "ms_bucket": "bucket_kernel",
+                 "ms_cascade": "cascade_kernel", "ms_finalize": "finalize_low_kernel"}
+    else:
+        alg = {"ms_count": F + n_gen * (4 ** kmax) * 4.0,       # FASTA read + the top-level count vector
+               "ms_cascade": n_gen * sum(4 ** k for k in ks if k < kmax) * 4.0,
+               "ms_finalize": n_gen * row_len * 4.0}
+        names = {"ms_count": "count_kernel", "ms_cascade": "cascade_kernel", "ms_finalize": "finalize_kernel"}
+    kernels = []
+    for key, nm in names.items():
+        t = per_step.get(key, 0.0) * 1e-3
+        if t > 0:
+            kernels.append({"kernel": nm, "ms_per_step": t * 1e3, "alg_bytes_per_step": alg[key],
+                            "achieved": alg[key] / t / 1e9, "frac": alg[key] / t / 1e9 / peak,
+                            "share_of_step": t * 1e3 / ms_per_step})
+    dom = max(kernels, key=lambda d: d["ms_per_step"]) if kernels else None
+    n_dom_launch = max(int(prof["count_launches"]) // max(args.steps, 1), 1) if dom and dom["kernel"] in ("partition_kernel", "count_kernel") else 1
     roofline = {
-        "bound": "hbm", "kernel": "count_kernel<global RED>" if kmax > 7 else "count_kernel<smem>",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src,
-        "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": t_count * 1e3,
-        "kernel_share_of_step": prof["ms_count"] / ms if ms > 0 else None,
-        "step_frac": step_alg / (ms_per_step * 1e-3) / 1e9 / peak,
-        "step_alg_bytes": step_alg,
-        "ms": {k: prof[k] / args.steps for k in ("ms_count", "ms_cascade", "ms_finalize", "ms_other")},
+        "bound": "hbm", "kernel": dom["kernel"] if dom else None,
+        "achieved": dom["achieved"] if dom else 0.0, "peak": peak, "unit": "GB/s",
+        "frac": dom["frac"] if dom else 0.0, "traffic": None, "peak_source": peak_src,
+        "alg_bytes_per_launch": (dom["alg_bytes_per_step"] / n_dom_launch) if dom else None,
+        "avg_launch_ms": (dom["ms_per_step"] / n_dom_launch) if dom else None,
+        "kernel_share_of_step": dom["share_of_step"] if dom else None,
+        "step_frac": step_alg / (ms_per_step * 1e-3) / 1e9 / peak, "step_alg_bytes": step_alg,
+        "kernels": kernels,
     }
 
     # ---- end to end through the host-buffer C-ABI call

@@ -35,6 +35,7 @@ extern "C" {
 #define KMERML_ERR_RANGE (-4)   /* input too large for the 32-bit counters / offsets */
 
 #define KMERML_FLAG_CANONICAL 1u /* count min(kmer, revcomp) -- opt-in extension, not in the reference */
+#define KMERML_FLAG_NO_PARTITION 2u /* k = 9..12: use the global-atomic kernel instead of the partition path */
 
 #define KMERML_MAX_DENSE_K 14    /* dense 4^k histograms up to here; larger k -> kmerml_count_sparse */
 #define KMERML_MAX_K 32
@@ -110,6 +111,8 @@ typedef struct kmerml_profile {
     double ms_cascade;        /* ... the marginalisation cascade */
     double ms_finalize;       /* ... fold / normalise */
     double ms_other;          /* prologue and the rest */
+    double ms_partition;      /* ... the partition kernel (k = 9..12) */
+    double ms_bucket;         /* ... the bucket histogram + in-bucket cascade kernel */
 } kmerml_profile;
 int kmerml_profile_enable(kmerml_ctx *ctx, int on);
 int kmerml_profile_read(kmerml_ctx *ctx, kmerml_profile *out, int reset);

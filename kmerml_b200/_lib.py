@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libkmerml_b200.so")
 
 OK = 0
 FLAG_CANONICAL = 1
+FLAG_NO_PARTITION = 2
 MAX_DENSE_K = 14
 MAX_K = 32
 
@@ -20,7 +21,8 @@ _lib = None
 class Profile(ctypes.Structure):
     _fields_ = [("launches", ctypes.c_uint64), ("count_launches", ctypes.c_uint64),
                 ("ms_count", ctypes.c_double), ("ms_cascade", ctypes.c_double),
-                ("ms_finalize", ctypes.c_double), ("ms_other", ctypes.c_double)]
+                ("ms_finalize", ctypes.c_double), ("ms_other", ctypes.c_double),
+                ("ms_partition", ctypes.c_double), ("ms_bucket", ctypes.c_double)]
 
 
 class KmermlError(RuntimeError):

@@ -76,13 +76,14 @@ struct PinBuf {
 struct Workspace {
     DevBuf tables;      // offsets | GenomeDev | GenomeStats | Slice[]
     DevBuf scratch;     // pass-through cascade levels
+    DevBuf part;        // partition path: bucket-sorted payloads + per-tile offset tables
     PinBuf staging;     // host image of offsets + slices
     cudaEvent_t staging_free = nullptr;
     // host-path slot buffers
     DevBuf fasta, counts, freq, totals;
     cudaStream_t stream = nullptr;
     void release() {
-        tables.release(); scratch.release(); staging.release();
+        tables.release(); scratch.release(); part.release(); staging.release();
         fasta.release(); counts.release(); freq.release(); totals.release();
         if (staging_free) cudaEventDestroy(staging_free);
         if (stream) cudaStreamDestroy(stream);
@@ -94,7 +95,7 @@ struct Workspace {
 }  // namespace km
 
 struct ProfRec {
-    int kind;                 // 0 count, 1 cascade, 2 finalize, 3 other
+    int kind;                 // 0 count, 1 cascade, 2 finalize, 3 other, 4 partition, 5 bucket
     cudaEvent_t a, b;
 };
 
@@ -107,7 +108,7 @@ struct kmerml_ctx {
     uint64_t launches = 0, count_launches = 0;
     std::vector<ProfRec> recs;
     std::vector<cudaEvent_t> pool;
-    double ms[4] = {0, 0, 0, 0};
+    double ms[6] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace km {
@@ -135,7 +136,7 @@ struct Prof {
     cudaEvent_t a = nullptr, b = nullptr;
     Prof(kmerml_ctx* c, cudaStream_t st, int k, int n_launches) : ctx(c), s(st), kind(k) {
         ctx->launches += (uint64_t)n_launches;
-        if (k == 0) ctx->count_launches += (uint64_t)n_launches;
+        if (k == 0 || k == 4) ctx->count_launches += (uint64_t)n_launches;
         if (!ctx->profiling) return;
         a = take();
         b = take();
@@ -202,6 +203,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
             return fail(KMERML_ERR_RANGE, "a genome of 4 GiB or more does not fit the 32-bit counters");
     }
     const bool use_smem = kmax <= SMEM_MAX_K;
+    const bool use_part = kmax >= PART_MIN_K && kmax <= PART_MAX_K && !(flags & KMERML_FLAG_NO_PARTITION);
     const bool canonical = (flags & KMERML_FLAG_CANONICAL) != 0;
 
     // ---- level map: requested levels live in the caller's row, the rest in scratch
@@ -221,7 +223,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     }
     lm.counts = d_counts;
     lm.counts_stride = counts_stride;
-    lm.scratch_slots = use_smem ? (uint32_t)n_genomes : 1u;
+    lm.scratch_slots = (use_smem || use_part) ? (uint32_t)n_genomes : 1u;
     lm.scratch_stride = scratch_stride;
     if (scratch_stride) {
         rc = ws.scratch.ensure((size_t)scratch_stride * lm.scratch_slots * 4);
@@ -238,7 +240,9 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     for (int g = 0; g < n_genomes; g++) {
         uint64_t bytes = h_offsets[g + 1] - h_offsets[g];
         uint64_t sb;
-        if (use_smem) {
+        if (use_part) {
+            sb = TILE_BYTES;                                  // one tile per CTA
+        } else if (use_smem) {
             if ((uint64_t)n_genomes >= target) sb = 1ull << 40;
             else sb = align_up(std::max<uint64_t>(total_bytes / target, 4ull * TILE_BYTES), TILE_BYTES);
         } else {
@@ -259,9 +263,10 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     const size_t gen_bytes = align_up((size_t)n_genomes * sizeof(GenomeDev), 256);
     const size_t st_bytes = align_up((size_t)n_genomes * sizeof(GenomeStats), 256);
     const size_t sl_bytes = align_up((size_t)std::max<uint64_t>(n_slices, 1) * sizeof(Slice), 256);
-    rc = ws.tables.ensure(off_bytes + gen_bytes + st_bytes + sl_bytes);
+    const size_t gt_bytes = align_up((size_t)n_genomes * 8, 256);
+    rc = ws.tables.ensure(off_bytes + gen_bytes + st_bytes + sl_bytes + gt_bytes);
     if (rc) return rc;
-    rc = ws.staging.ensure(off_bytes + sl_bytes);
+    rc = ws.staging.ensure(off_bytes + sl_bytes + gt_bytes);
     if (rc) return rc;
     if (!ws.staging_free) KM_CUDA(cudaEventCreateWithFlags(&ws.staging_free, cudaEventDisableTiming));
     KM_CUDA(cudaEventSynchronize(ws.staging_free));     // previous call's upload has left the staging buffer
@@ -288,8 +293,30 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
             }
         }
     }
+    // partition path: genomes are processed in groups whose payload workspace is bounded
+    uint32_t* d_gtiles = (uint32_t*)(base + off_bytes + gen_bytes + st_bytes + sl_bytes);
+    uint32_t* h_gtiles = (uint32_t*)(hs + off_bytes + sl_bytes);
+    std::vector<int> group_end;                              // exclusive genome index per group
+    if (use_part) {
+        const uint64_t max_tiles = (6ull << 30) / ((uint64_t)TILE_BYTES * 2);
+        uint64_t in_group = 0;
+        uint32_t group_tile0 = 0;
+        for (int g = 0; g < n_genomes; g++) {
+            uint32_t nt = first_slice[g + 1] - first_slice[g];
+            if (in_group && in_group + nt > max_tiles) {
+                group_end.push_back(g);
+                in_group = 0;
+                group_tile0 = first_slice[g];
+            }
+            h_gtiles[2 * g] = first_slice[g] - group_tile0;
+            h_gtiles[2 * g + 1] = nt;
+            in_group += nt;
+        }
+        group_end.push_back(n_genomes);
+    }
     KM_CUDA(cudaMemcpyAsync(d_offsets, hs, off_bytes, cudaMemcpyHostToDevice, s));
     KM_CUDA(cudaMemcpyAsync(d_slices, h_slices, sl_bytes, cudaMemcpyHostToDevice, s));
+    if (use_part) KM_CUDA(cudaMemcpyAsync(d_gtiles, h_gtiles, gt_bytes, cudaMemcpyHostToDevice, s));
     KM_CUDA(cudaEventRecord(ws.staging_free, s));
 
     {
@@ -300,7 +327,58 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     const int n_cascade = cascade_launches(kmax, kmin);
 
     const size_t row_bytes = (size_t)row.off[nk] * 4;
-    if (use_smem) {
+    if (use_part) {
+        const int nb = 1 << (2 * (kmax - PART_LOW_BASES));
+        const int k_stop = std::max(kmax - PART_LOW_BASES, kmin);
+        uint64_t max_group_tiles = 0;
+        for (size_t gi = 0, g0 = 0; gi < group_end.size(); g0 = group_end[gi], gi++)
+            max_group_tiles = std::max<uint64_t>(max_group_tiles, first_slice[group_end[gi]] - first_slice[g0]);
+        const size_t payload_bytes = align_up((size_t)max_group_tiles * TILE_BYTES * 2, 256);
+        const size_t table_bytes = align_up((size_t)max_group_tiles * (size_t)(nb + 1) * 2 + 64, 256);
+        rc = ws.part.ensure(payload_bytes + table_bytes);
+        if (rc) return rc;
+        uint16_t* d_payload = (uint16_t*)ws.part.p;
+        uint16_t* d_table = (uint16_t*)((uint8_t*)ws.part.p + payload_bytes);
+        // only the levels below kmax collect run-end tails and must start from zero;
+        // the top-level row is written in full by the bucket kernel
+        for (int i = 0; i < nk; i++)
+            if (row.k[i] < kmax)
+                KM_CUDA(cudaMemset2DAsync(d_counts + row.off[i], (size_t)counts_stride * 4, 0,
+                                          (size_t)(1ull << (2 * row.k[i])) * 4, (size_t)n_genomes, s));
+        if (scratch_stride) KM_CUDA(cudaMemsetAsync(lm.scratch, 0, (size_t)scratch_stride * n_genomes * 4, s));
+        int g0 = 0;
+        for (size_t gi = 0; gi < group_end.size(); gi++) {
+            const int g1 = group_end[gi], ng = g1 - g0;
+            const int nt = (int)(first_slice[g1] - first_slice[g0]);
+            {
+                Prof pr(ctx, s, 4, nt > 0 ? 1 : 0);
+                rc = launch_partition(d_fasta, d_genomes, d_slices + first_slice[g0], nt, kmax, kmin, min_rec, lm,
+                                      d_stats, d_payload, d_table, s);
+            }
+            if (rc) return rc;
+            {
+                Prof pr(ctx, s, 5, 1);
+                rc = launch_bucket(lm, row, kmax, kmin, d_gtiles, d_payload, d_table, d_stats,
+                                   canonical ? nullptr : d_freq, freq_stride, d_totals, (uint32_t)g0, ng, s);
+            }
+            if (rc) return rc;
+            for (int h0 = g0; h0 < g1; h0 += 32768) {
+                const int nh = std::min(32768, g1 - h0);
+                if (k_stop > kmin) {
+                    Prof pr(ctx, s, 1, cascade_launches(k_stop, kmin));
+                    rc = launch_cascade(lm, k_stop, kmin, (uint32_t)h0, nh, s);
+                    if (rc) return rc;
+                }
+                Prof pr(ctx, s, 2, 1);
+                if (canonical)
+                    rc = launch_finalize(lm, row, kmax, true, d_stats, d_freq, freq_stride, d_totals, (uint32_t)h0, nh, s);
+                else
+                    rc = launch_finalize_low(lm, row, kmax, k_stop, d_stats, d_freq, freq_stride, (uint32_t)h0, nh, s);
+                if (rc) return rc;
+            }
+            g0 = g1;
+        }
+    } else if (use_smem) {
         KM_CUDA(cudaMemset2DAsync(d_counts, (size_t)counts_stride * 4, 0, row_bytes, (size_t)n_genomes, s));
         if (scratch_stride) KM_CUDA(cudaMemsetAsync(lm.scratch, 0, (size_t)scratch_stride * n_genomes * 4, s));
         {
@@ -420,6 +498,8 @@ int kmerml_profile_read(kmerml_ctx* ctx, kmerml_profile* out, int reset) {
     out->ms_cascade = ctx->ms[1];
     out->ms_finalize = ctx->ms[2];
     out->ms_other = ctx->ms[3];
+    out->ms_partition = ctx->ms[4];
+    out->ms_bucket = ctx->ms[5];
     if (reset) {
         ctx->launches = ctx->count_launches = 0;
         for (double& m : ctx->ms) m = 0;

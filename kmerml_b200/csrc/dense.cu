@@ -12,6 +12,8 @@
 // Work decomposition: a CTA owns a slice (a few tiles) of one genome; a thread owns
 // the windows that START in its 64-byte chunk of the tile (fasta_walk.cuh), so there
 // is no carry between threads and no compaction pass: the FASTA bytes are read once.
+#include <algorithm>
+
 #include "fasta_walk.cuh"
 #include "internal.h"
 
@@ -62,28 +64,72 @@ struct FirstSink {
 };
 
 // ------------------------------------------------------------------ helpers
-__device__ __forceinline__ bool any_byte_eq(const uint32_t (&w)[16], uint32_t pattern) {
-    uint32_t acc = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        uint32_t x = w[i] ^ pattern;
-        acc |= (x - 0x01010101u) & ~x & 0x80808080u;   // a zero byte in x
+__device__ __forceinline__ void level_totals(const RowSpec& row, int k_top, const GenomeStats* stats, uint32_t g,
+                                             unsigned long long* tot, uint64_t* totals, bool write);
+
+struct TileCtx {                      // shared-memory state of the tile loop
+    uint8_t* flags;                   // [COUNT_THREADS] chunk starts inside a header line
+    unsigned long long* carry;        // [2] end of a header line that runs into later tiles
+};
+
+// The tile loop every counting kernel shares: 128-bit loads of the thread's 64-byte
+// chunk, header-line detection (phase 1), then the carry-free walk (phase 2).
+template <class Sink>
+__device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, const Genome& g, const Slice& sl,
+                                           const DenseParams& P, Sink& sink, const TileCtx& tc) {
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        unsigned long long c = 0;
+        uint64_t until;
+        if (sl.begin > g.lo && pos_in_header(g, sl.begin, &until)) c = until;
+        tc.carry[0] = c;
+        tc.carry[1] = c;
     }
-    return acc != 0;
+    const uint64_t end = sl.end < g.hi ? sl.end : g.hi;
+    for (uint64_t tb = sl.begin; tb < end; tb += TILE_BYTES) {
+        tc.flags[tid] = 0;
+        __syncthreads();                                    // flags cleared, carry[0] visible
+        const uint64_t cb = tb + (uint64_t)tid * CHUNK;
+        const uint64_t cs = cb > g.lo ? cb : g.lo;
+        const uint64_t ce = cb + CHUNK < g.hi ? cb + CHUNK : g.hi;
+        const bool has = cs < ce;
+        const bool full = has && (ce - cs == CHUNK);
+        uint32_t w[16];
+        bool gt = true;
+        if (full) {
+            const uint4* src = reinterpret_cast<const uint4*>(buf + cb);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint4 v = __ldg(src + i);
+                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+            gt = any_byte_eq16(w, 0x3E3E3E3Eu);
+        }
+        // phase 1: header lines that start in my chunk shadow the chunks after it
+        if (has && gt) {
+            find_headers(g, cs, ce, [&](uint64_t, uint64_t until) {
+                for (int j = tid + 1; j < COUNT_THREADS && tb + (uint64_t)j * CHUNK < until; j++) tc.flags[j] = 1;
+                atomicMax(&tc.carry[1], (unsigned long long)until);
+            });
+        }
+        __syncthreads();
+        // phase 2: walk
+        if (has) {
+            const bool in_hdr = tc.flags[tid] || cs < tc.carry[0];
+            if (full && !gt && !in_hdr && P.min_rec == P.k) walk_chunk_fast(g, cs, w, P, sink);
+            else walk_chunk(g, cs, ce, in_hdr, P, sink, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
+        }
+        __syncthreads();
+        if (tid == 0) tc.carry[0] = tc.carry[1];
+    }
 }
 
-template <class Sink>
-__device__ __forceinline__ void walk_chunk_regs(const Genome& g, uint64_t cs, const uint32_t (&w)[16],
-                                                bool in_hdr, const DenseParams& P, Sink& sink) {
-    WalkState s;
-    s.kmer = 0; s.run = 0; s.in_hdr = in_hdr ? 1 : 0; s.pend = 0; s.rec_known = 0;
+__device__ __forceinline__ unsigned long long block_sum_u32(unsigned n, unsigned long long* sh_total) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            step_own(g, cs + (uint64_t)(4 * i + j), (w[i] >> (8 * j)) & 0xFFu, s, P, sink);
-    }
-    walk_overhang(g, cs + CHUNK, s, P, sink);
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(sh_total, (unsigned long long)n);
+    __syncthreads();
+    return *sh_total;
 }
 
 // ------------------------------------------------------------------ kernels
@@ -117,77 +163,35 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
     g.b = buf;
     g.lo = gd.lo;
     g.hi = gd.hi;
+    TileCtx tc;
+    tc.flags = flags;
+    tc.carry = carry;
 
     if (MODE == 1) {
         const int nb = 1 << (2 * P.k);
         for (int i = tid; i < nb; i += COUNT_THREADS) sh_hist[i] = 0;
     }
-    if (tid == 0) {
-        sh_total = 0;
-        unsigned long long c = 0;
-        uint64_t until;
-        if (sl.begin > g.lo && pos_in_header(g, sl.begin, &until)) c = until;
-        carry[0] = c;
-        carry[1] = c;
+    if (tid == 0) sh_total = 0;
+
+    unsigned n = 0;
+    if (MODE == 0) {
+        GlobalSink sink;
+        sink.top = lm.ptr(sl.genome, P.k); sink.lm = &lm; sink.st = stats + sl.genome; sink.genome = sl.genome; sink.n = 0;
+        walk_slice(buf, g, sl, P, sink, tc);
+        n = sink.n;
+    } else if (MODE == 1) {
+        SmemSink sink;
+        sink.sbase = (uint32_t)__cvta_generic_to_shared(sh_hist); sink.lm = &lm; sink.st = stats + sl.genome;
+        sink.genome = sl.genome; sink.n = 0;
+        walk_slice(buf, g, sl, P, sink, tc);
+        n = sink.n;
+    } else {
+        FirstSink sink;
+        sink.first = first; sink.file_lo = gd.file_lo; sink.n = 0;
+        walk_slice(buf, g, sl, P, sink, tc);
+        return;
     }
-
-    GlobalSink gs;
-    SmemSink ss;
-    FirstSink fs;
-    if (MODE == 0) { gs.top = lm.ptr(sl.genome, P.k); gs.lm = &lm; gs.st = stats + sl.genome; gs.genome = sl.genome; gs.n = 0; }
-    if (MODE == 1) { ss.sbase = (uint32_t)__cvta_generic_to_shared(sh_hist); ss.lm = &lm; ss.st = stats + sl.genome; ss.genome = sl.genome; ss.n = 0; }
-    if (MODE == 2) { fs.first = first; fs.file_lo = gd.file_lo; fs.n = 0; }
-
-    const uint64_t end = sl.end < g.hi ? sl.end : g.hi;
-    for (uint64_t tb = sl.begin; tb < end; tb += TILE_BYTES) {
-        flags[tid] = 0;
-        __syncthreads();                                    // flags cleared, carry[0] visible
-        const uint64_t cb = tb + (uint64_t)tid * CHUNK;
-        const uint64_t cs = cb > g.lo ? cb : g.lo;
-        const uint64_t ce = cb + CHUNK < g.hi ? cb + CHUNK : g.hi;
-        const bool has = cs < ce;
-        const bool full = has && (ce - cs == CHUNK);
-        uint32_t w[16];
-        if (full) {
-            const uint4* src = reinterpret_cast<const uint4*>(buf + cb);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                uint4 v = __ldg(src + i);
-                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-            }
-        }
-        // phase 1: header lines that start in my chunk shadow the chunks after it
-        if (has && (!full || any_byte_eq(w, 0x3E3E3E3Eu))) {
-            find_headers(g, cs, ce, [&](uint64_t, uint64_t until) {
-                for (int j = tid + 1; j < COUNT_THREADS && tb + (uint64_t)j * CHUNK < until; j++) flags[j] = 1;
-                atomicMax(&carry[1], (unsigned long long)until);
-            });
-        }
-        __syncthreads();
-        // phase 2: walk
-        if (has) {
-            const bool in_hdr = flags[tid] || cs < carry[0];
-            if (MODE == 0) {
-                if (full) walk_chunk_regs(g, cs, w, in_hdr, P, gs);
-                else walk_chunk(g, cs, ce, in_hdr, P, gs, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
-            } else if (MODE == 1) {
-                if (full) walk_chunk_regs(g, cs, w, in_hdr, P, ss);
-                else walk_chunk(g, cs, ce, in_hdr, P, ss, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
-            } else {
-                if (full) walk_chunk_regs(g, cs, w, in_hdr, P, fs);
-                else walk_chunk(g, cs, ce, in_hdr, P, fs, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
-            }
-        }
-        __syncthreads();
-        if (tid == 0) carry[0] = carry[1];
-    }
-
-    if (MODE == 2) return;
-    unsigned n = MODE == 0 ? gs.n : ss.n;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-    if ((tid & 31) == 0 && n) atomicAdd(&sh_total, (unsigned long long)n);
-    __syncthreads();
+    const unsigned long long total = block_sum_u32(n, &sh_total);
     if (MODE == 1) {
         uint32_t* top = lm.ptr(sl.genome, P.k);
         const int nb = 1 << (2 * P.k);
@@ -196,7 +200,254 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
             if (v) atomicAdd(top + i, v);
         }
     }
-    if (tid == 0 && sh_total) atomicAdd(&stats[sl.genome].total_top, sh_total);
+    if (tid == 0 && total) atomicAdd(&stats[sl.genome].total_top, total);
+}
+
+// ---------------------------------------------------------------- partition path
+// k = 9..12: the 4^k histogram (up to 64 MB) is too big for shared memory and L2
+// atomics top out near 190 G/s (and thrash the L2 next to the streamed input), so the
+// windows are first partitioned by their leading k-7 bases:
+//   partition_kernel  one CTA per 16 KB tile: walk, counting-sort the tile's windows by
+//                     bucket in shared memory, write them bucket-sorted as 14-bit
+//                     payloads (uint16) plus the tile's bucket offsets
+//   bucket_kernel     one CTA per bucket: gather its segment from every tile into a
+//                     16384-bin shared histogram, then write that 64 KB slice of the
+//                     count row, its frequencies, and the bucket's whole cascade subtree
+// Only shared-memory atomics (2.5 T/s on B200) are used; every global access is a
+// coalesced stream.
+constexpr int PART_LOW = 7;
+constexpr int PART_BINS = 1 << (2 * PART_LOW);        // 16384 bins per bucket
+constexpr int PART_MAX_BUCKETS = 1024;                // k <= 12
+constexpr int TILE_WINDOWS = TILE_BYTES;              // a tile owns at most one window per byte
+
+struct PartSink {
+    uint32_t raw_base;                 // shared address of raw[]: raw[n * COUNT_THREADS + tid]
+    uint32_t cnt_base;                 // shared address of cnt[]
+    uint32_t n_local;
+    const LevelMap* lm;
+    GenomeStats* st;
+    uint32_t genome;
+    __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(raw_base + (n_local * COUNT_THREADS + threadIdx.x) * 4u), "r"(idx) : "memory");
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt_base + (idx >> (2 * PART_LOW)) * 4u) : "memory");
+        n_local++;
+    }
+    __device__ __noinline__ void tail(int j, uint32_t idx) {
+        atomicAdd(lm->ptr(genome, j) + idx, 1u);
+        atomicAdd(&st->n_tail[j], 1ull);
+    }
+};
+
+struct PartSmem {
+    uint32_t raw[TILE_WINDOWS];                 // 64 KB: the tile's windows, thread-interleaved
+    uint16_t staged[TILE_WINDOWS];              // 32 KB: payloads sorted by bucket
+    uint32_t cnt[PART_MAX_BUCKETS + 4];         // per-bucket count, then cursor
+    uint32_t off[PART_MAX_BUCKETS + 4];         // exclusive offsets
+    uint32_t warp_tot[COUNT_THREADS / 32];
+    unsigned long long carry[2];
+    unsigned long long sh_total;
+    uint8_t flags[COUNT_THREADS];
+};
+
+__global__ void __launch_bounds__(COUNT_THREADS, 2)
+partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
+                 const Slice* __restrict__ tiles, DenseParams P, LevelMap lm, GenomeStats* stats,
+                 uint16_t* __restrict__ payload, uint16_t* __restrict__ table, int nb) {
+    extern __shared__ __align__(16) unsigned char part_smem_raw[];
+    PartSmem& sm = *reinterpret_cast<PartSmem*>(part_smem_raw);
+    const int tid = threadIdx.x;
+    const Slice sl = tiles[blockIdx.x];
+    const GenomeDev gd = gds[sl.genome];
+    Genome g;
+    g.b = buf;
+    g.lo = gd.lo;
+    g.hi = gd.hi;
+    TileCtx tc;
+    tc.flags = sm.flags;
+    tc.carry = sm.carry;
+    for (int i = tid; i < nb; i += COUNT_THREADS) sm.cnt[i] = 0;
+    if (tid == 0) sm.sh_total = 0;
+
+    PartSink sink;
+    sink.raw_base = (uint32_t)__cvta_generic_to_shared(sm.raw);
+    sink.cnt_base = (uint32_t)__cvta_generic_to_shared(sm.cnt);
+    sink.n_local = 0;
+    sink.lm = &lm; sink.st = stats + sl.genome; sink.genome = sl.genome;
+    walk_slice(buf, g, sl, P, sink, tc);            // slice == one tile; ends with __syncthreads
+
+    // exclusive scan of cnt[0..nb) (4 buckets per thread)
+    uint32_t v[4], s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int b = 4 * tid + i;
+        v[i] = b < nb ? sm.cnt[b] : 0u;
+        s += v[i];
+    }
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((tid & 31) >= o) inc += t;
+    }
+    if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int wdx = 0; wdx < (tid >> 5); wdx++) base += sm.warp_tot[wdx];
+    uint32_t ex = base + inc - s;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int b = 4 * tid + i;
+        if (b < nb) { sm.off[b] = ex; sm.cnt[b] = ex; }     // cnt becomes the scatter cursor
+        ex += v[i];
+    }
+    if (tid == COUNT_THREADS - 1) sm.off[nb] = ex;
+    __syncthreads();
+    const uint32_t total = sm.off[nb];
+    // the tile's row of the offset table
+    uint16_t* trow = table + (size_t)blockIdx.x * (size_t)(nb + 1);
+    for (int i = tid; i <= nb; i += COUNT_THREADS) trow[i] = (uint16_t)sm.off[i];
+    // scatter payloads into bucket order
+    const uint32_t cnt_base = sink.cnt_base;
+    for (uint32_t n = 0; n < sink.n_local; n++) {
+        const uint32_t idx = sm.raw[n * COUNT_THREADS + tid];
+        uint32_t pos;
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cnt_base + (idx >> (2 * PART_LOW)) * 4u) : "memory");
+        sm.staged[pos] = (uint16_t)(idx & (PART_BINS - 1));
+    }
+    __syncthreads();
+    // coalesced copy of the sorted tile
+    uint4* dst = reinterpret_cast<uint4*>(payload + (size_t)blockIdx.x * TILE_WINDOWS);
+    const uint4* src = reinterpret_cast<const uint4*>(sm.staged);
+    const uint32_t nvec = (total + 7) >> 3;
+    for (uint32_t i = tid; i < nvec; i += COUNT_THREADS) dst[i] = src[i];
+    if (tid == 0 && total) atomicAdd(&stats[sl.genome].total_top, (unsigned long long)total);
+}
+
+struct GenomeTiles {                   // tiles of one genome inside the group's tile list
+    uint32_t tile0, n_tiles;
+};
+
+struct LevelInfo {                     // per level: index into the caller's k_list (-1: pass-through)
+    int ki[16];
+};
+
+constexpr int BUCKET_THREADS = 512;
+constexpr int BUCKET_BATCH = 2048;     // tile segments staged per round
+
+struct BucketSmem {
+    uint32_t hist[PART_BINS];          // 64 KB
+    uint32_t lvl[PART_BINS / 4];       // 16 KB ping-pong buffer of the in-bucket cascade
+    uint32_t seg[BUCKET_BATCH];        // (start | end << 16) of this bucket's segment in each tile
+    unsigned long long tot[16];
+};
+
+__global__ void __launch_bounds__(BUCKET_THREADS)
+bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const GenomeTiles* __restrict__ gts,
+              const uint16_t* __restrict__ payload, const uint16_t* __restrict__ table, int nb,
+              const GenomeStats* __restrict__ stats, float* freq, uint64_t freq_stride, uint64_t* totals,
+              uint32_t genome0) {
+    extern __shared__ __align__(16) unsigned char bucket_smem_raw[];
+    BucketSmem& sm = *reinterpret_cast<BucketSmem*>(bucket_smem_raw);
+    const int tid = threadIdx.x;
+    const uint32_t b = blockIdx.x;
+    const uint32_t g = genome0 + blockIdx.y;
+    const GenomeTiles gt = gts[g];
+    for (int i = tid; i < PART_BINS; i += BUCKET_THREADS) sm.hist[i] = 0;
+    if (tid < row.nk) {
+        const int j = row.k[tid];
+        unsigned long long t = stats[g].total_top;
+        for (int i = j; i < k; i++) t += stats[g].n_tail[i];
+        sm.tot[tid] = t;
+        if (totals && b == 0) totals[(uint64_t)g * row.nk + tid] = t;
+    }
+    const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sm.hist);
+    const int half = tid >> 4, hl = tid & 15;               // 32 half-warps, 16 lanes each
+    for (uint32_t t0 = 0; t0 < gt.n_tiles; t0 += BUCKET_BATCH) {
+        const uint32_t nt = min((uint32_t)BUCKET_BATCH, gt.n_tiles - t0);
+        __syncthreads();
+        for (uint32_t i = tid; i < nt; i += BUCKET_THREADS) {
+            const uint16_t* trow = table + (size_t)(gt.tile0 + t0 + i) * (size_t)(nb + 1) + b;
+            sm.seg[i] = (uint32_t)trow[0] | ((uint32_t)trow[1] << 16);
+        }
+        __syncthreads();
+        for (uint32_t i = half; i < nt; i += BUCKET_THREADS / 16) {
+            const uint32_t se = sm.seg[i];
+            const uint32_t s0 = se & 0xFFFFu, s1 = se >> 16;
+            const uint16_t* src = payload + (size_t)(gt.tile0 + t0 + i) * TILE_WINDOWS;
+            for (uint32_t q = s0 + hl; q < s1; q += 16) {
+                const uint32_t p = src[q];
+                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + p * 4u) : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    // level k: this bucket's 16384 bins, and level k-1 on the way
+    {
+        const int ki = li.ki[k];
+        uint32_t* ck = lm.ptr(g, k) + (size_t)b * PART_BINS;
+        float* fk = (freq && ki >= 0) ? freq + (uint64_t)g * freq_stride + row.off[ki] + (size_t)b * PART_BINS : nullptr;
+        const double inv = (ki >= 0 && sm.tot[ki]) ? 1.0 / (double)sm.tot[ki] : 0.0;
+        const bool down = k - 1 >= k_stop;
+        uint32_t* c1 = down ? lm.ptr(g, k - 1) + (size_t)b * (PART_BINS / 4) : nullptr;
+        const int ki1 = down ? li.ki[k - 1] : -1;
+        float* f1 = (freq && ki1 >= 0) ? freq + (uint64_t)g * freq_stride + row.off[ki1] + (size_t)b * (PART_BINS / 4) : nullptr;
+        const double inv1 = (ki1 >= 0 && sm.tot[ki1]) ? 1.0 / (double)sm.tot[ki1] : 0.0;
+        for (int i = tid; i < PART_BINS / 4; i += BUCKET_THREADS) {
+            const uint4 c = reinterpret_cast<const uint4*>(sm.hist)[i];
+            reinterpret_cast<uint4*>(ck)[i] = c;
+            if (fk) {
+                float4 f;
+                f.x = (float)((double)c.x * inv); f.y = (float)((double)c.y * inv);
+                f.z = (float)((double)c.z * inv); f.w = (float)((double)c.w * inv);
+                reinterpret_cast<float4*>(fk)[i] = f;
+            }
+            if (down) {
+                const uint32_t v = c.x + c.y + c.z + c.w + c1[i];     // + run-end tails of level k-1
+                c1[i] = v;
+                if (f1) f1[i] = (float)((double)v * inv1);
+                sm.lvl[i] = v;
+            }
+        }
+    }
+    // deeper levels of the bucket's subtree, ping-pong between lvl[] and hist[]
+    uint32_t* cur = sm.lvl;
+    uint32_t* nxt = sm.hist;
+    int n_cur = PART_BINS / 4;
+    for (int level = k - 2; level >= k_stop; level--) {
+        __syncthreads();
+        const int n_next = n_cur >> 2;
+        uint32_t* cl = lm.ptr(g, level) + (size_t)b * n_next;
+        const int kil = li.ki[level];
+        float* fl = (freq && kil >= 0) ? freq + (uint64_t)g * freq_stride + row.off[kil] + (size_t)b * n_next : nullptr;
+        const double invl = (kil >= 0 && sm.tot[kil]) ? 1.0 / (double)sm.tot[kil] : 0.0;
+        for (int i = tid; i < n_next; i += BUCKET_THREADS) {
+            const uint32_t v = cur[4 * i] + cur[4 * i + 1] + cur[4 * i + 2] + cur[4 * i + 3] + cl[i];
+            cl[i] = v;
+            if (fl) fl[i] = (float)((double)v * invl);
+            nxt[i] = v;
+        }
+        uint32_t* t = cur; cur = nxt; nxt = t;
+        n_cur = n_next;
+    }
+}
+
+// Frequencies of the requested levels below `level_limit` (the few levels the bucket
+// kernel's subtrees do not reach); one block per genome.
+__global__ void __launch_bounds__(256)
+finalize_low_kernel(LevelMap lm, RowSpec row, int k_top, int level_limit, const GenomeStats* __restrict__ stats,
+                    float* freq, uint64_t freq_stride, uint32_t genome0) {
+    __shared__ unsigned long long tot[16];
+    const uint32_t g = genome0 + blockIdx.x;
+    level_totals(row, k_top, stats, g, tot, nullptr, false);
+    if (!freq) return;
+    for (int ki = 0; ki < row.nk; ki++) {
+        const int j = row.k[ki];
+        if (j >= level_limit) continue;
+        const uint32_t* c = lm.ptr(g, j);
+        float* f = freq + (uint64_t)g * freq_stride + row.off[ki];
+        const double inv = tot[ki] ? 1.0 / (double)tot[ki] : 0.0;
+        for (uint32_t x = threadIdx.x; x < (1u << (2 * j)); x += 256) f[x] = (float)((double)c[x] * inv);
+    }
 }
 
 // Levels k_top-1 .. k_top-depth (depth <= 6) from level k_top (final) and the tails
@@ -328,6 +579,8 @@ finalize_canonical_kernel(LevelMap lm, RowSpec row, int k_top, const GenomeStats
 int dense_setup_attributes() {
     KM_CUDA(cudaFuncSetAttribute(count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (1 << (2 * SMEM_MAX_K)) * 4));
+    KM_CUDA(cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
+    KM_CUDA(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
     return KMERML_OK;
 }
 
@@ -360,6 +613,46 @@ int launch_count(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice
     } else {
         count_kernel<0><<<n_slices, COUNT_THREADS, 0, s>>>(d_fasta, d_genomes, d_slices, P, lm, d_stats, nullptr);
     }
+    KM_CUDA(cudaGetLastError());
+    return KMERML_OK;
+}
+
+int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles,
+                     int k, int k_bottom, int min_rec, const LevelMap& lm, GenomeStats* d_stats,
+                     uint16_t* d_payload, uint16_t* d_table, cudaStream_t s) {
+    if (n_tiles <= 0) return KMERML_OK;
+    DenseParams P = make_params(k, min_rec, k > k_bottom, k_bottom);
+    const int nb = 1 << (2 * (k - PART_LOW));
+    partition_kernel<<<n_tiles, COUNT_THREADS, sizeof(PartSmem), s>>>(d_fasta, d_genomes, d_tiles, P, lm, d_stats,
+                                                                     d_payload, d_table, nb);
+    KM_CUDA(cudaGetLastError());
+    return KMERML_OK;
+}
+
+int launch_bucket(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, const void* d_genome_tiles,
+                  const uint16_t* d_payload, const uint16_t* d_table, const GenomeStats* d_stats, float* d_freq,
+                  uint64_t freq_stride, uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s) {
+    if (n_genomes <= 0) return KMERML_OK;
+    const int nb = 1 << (2 * (k - PART_LOW));
+    LevelInfo li;
+    for (int j = 0; j < 16; j++) {
+        li.ki[j] = -1;
+        for (int i = 0; i < row.nk; i++)
+            if (row.k[i] == j) li.ki[j] = i;
+    }
+    const int k_stop = std::max(k - PART_LOW, k_bottom);
+    dim3 grid((unsigned)nb, (unsigned)n_genomes);
+    bucket_kernel<<<grid, BUCKET_THREADS, sizeof(BucketSmem), s>>>(lm, row, li, k, k_stop,
+        (const GenomeTiles*)d_genome_tiles, d_payload, d_table, nb, d_stats, d_freq, freq_stride, d_totals, genome0);
+    KM_CUDA(cudaGetLastError());
+    return KMERML_OK;
+}
+
+int launch_finalize_low(const LevelMap& lm, const RowSpec& row, int k_top, int level_limit,
+                        const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride, uint32_t genome0,
+                        int n_genomes, cudaStream_t s) {
+    if (n_genomes <= 0 || !d_freq) return KMERML_OK;
+    finalize_low_kernel<<<n_genomes, 256, 0, s>>>(lm, row, k_top, level_limit, d_stats, d_freq, freq_stride, genome0);
     KM_CUDA(cudaGetLastError());
     return KMERML_OK;
 }

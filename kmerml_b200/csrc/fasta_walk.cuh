@@ -266,6 +266,80 @@ KM_HD void walk_chunk(const Genome& g, uint64_t cs, uint64_t ce, bool starts_in_
     walk_overhang(g, ce, s, P, sink);
 }
 
+// 4-entry byte LUT: byte i of the result = byte (sel nibble i) of `lut` (PRMT on the GPU).
+KM_HD uint32_t prmt4(uint32_t lut, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(lut, 0u, sel);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= ((lut >> (8 * ((sel >> (4 * i)) & 3u))) & 0xFFu) << (8 * i);
+    return r;
+#endif
+}
+
+// Per 32-bit word of FASTA bytes: 2-bit codes in bits [1:0] of every byte (y) and a
+// 0x80 flag in every byte that is not one of AaCcGgTt (bad).  13 integer ops per 4 bases.
+KM_HD void classify_word(uint32_t x, uint32_t& y, uint32_t& bad) {
+    const uint32_t u = x & 0xDFDFDFDFu;                       // upper-case (generate.py:41)
+    y = ((u >> 1) ^ (u >> 2)) & 0x03030303u;                   // A0 C1 G2 T3
+    const uint32_t t = y | (y >> 4);
+    const uint32_t sel = (t & 0xFFu) | ((t >> 8) & 0xFF00u);   // the 4 codes as PRMT selector nibbles
+    const uint32_t d = prmt4(0x54474341u, sel) ^ u;            // "ACGT"[code] == byte ?
+    bad = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+}
+
+// Fast walk of a chunk that (a) lies completely inside the genome, (b) does not start
+// inside a header line, (c) holds no '>' byte, with (d) min_rec == k.  Everything else
+// goes through walk_chunk.  `w` = the chunk's 16 little-endian words.
+template <class Sink>
+KM_HD void walk_chunk_fast(const Genome& g, uint64_t cs, const uint32_t* w, const DenseParams& P, Sink& sink) {
+    uint32_t kmer = 0;
+    int run = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < CHUNK / 4; i++) {
+        const uint32_t x = w[i];
+        uint32_t y, bad;
+        classify_word(x, y, bad);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; j++) {
+            if (!(bad & (0x80u << (8 * j)))) {
+                kmer = (kmer << 2) | ((y >> (8 * j)) & 3u);
+                run++;
+                if (run >= P.k) sink.count(kmer & P.mask, cs + (uint64_t)(4 * i + j));
+            } else {
+                const uint32_t c = (x >> (8 * j)) & 0xFFu;
+                if (c != 10u) {
+                    const uint64_t pos = cs + (uint64_t)(4 * i + j);
+                    if (classify_nonbase(g, pos, c) != SYM_SKIP) {
+                        if (run > 0 && P.tails) run_end_event(g, pos, P, sink);
+                        run = 0;
+                    }
+                }
+            }
+        }
+    }
+    WalkState s;
+    s.kmer = kmer; s.run = run; s.in_hdr = 0; s.pend = run > 0 ? 1 : 0; s.rec_known = 0;
+    walk_overhang(g, cs + CHUNK, s, P, sink);
+}
+
+// Does any byte of the 16 words equal the byte replicated in `pattern`?
+KM_HD bool any_byte_eq16(const uint32_t* w, uint32_t pattern) {
+    uint32_t acc = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < CHUNK / 4; i++) {
+        const uint32_t x = w[i] ^ pattern;
+        acc |= (x - 0x01010101u) & ~x & 0x80808080u;           // a zero byte in x
+    }
+    return acc != 0;
+}
+
 // Header lines that START in [cs, ce): callback(h, until) with the header
 // occupying [h, until) (until = one past its terminator, or > g.hi at EOF).
 template <class F>

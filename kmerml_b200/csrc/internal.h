@@ -76,6 +76,17 @@ int cascade_launches(int k_top, int k_bottom);
 int launch_finalize(const LevelMap& lm, const RowSpec& row, int k_top, bool canonical,
                     const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride,
                     uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s);
+// partition path (k = 9..12)
+constexpr int PART_MIN_K = 9, PART_MAX_K = 12, PART_LOW_BASES = 7;
+int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles,
+                     int k, int k_bottom, int min_rec, const LevelMap& lm, GenomeStats* d_stats,
+                     uint16_t* d_payload, uint16_t* d_table, cudaStream_t s);
+int launch_bucket(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, const void* d_genome_tiles,
+                  const uint16_t* d_payload, const uint16_t* d_table, const GenomeStats* d_stats, float* d_freq,
+                  uint64_t freq_stride, uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s);
+int launch_finalize_low(const LevelMap& lm, const RowSpec& row, int k_top, int level_limit,
+                        const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride, uint32_t genome0,
+                        int n_genomes, cudaStream_t s);
 int launch_first_occurrence(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices,
                             int n_slices, int k, int min_rec, uint32_t* d_first, cudaStream_t s);
 int dense_setup_attributes();

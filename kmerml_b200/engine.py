@@ -57,8 +57,12 @@ def _device_index(device):
     return dev.index if dev.index is not None else torch.cuda.current_device()
 
 
+def _flags(canonical, partition):
+    return (_lib.FLAG_CANONICAL if canonical else 0) | (0 if partition else _lib.FLAG_NO_PARTITION)
+
+
 def count_dense_device(fasta, offsets, k_values, *, min_record_len=None, canonical=False,
-                       want_freq=True, out_counts=None, out_freq=None, out_totals=None):
+                       want_freq=True, out_counts=None, out_freq=None, out_totals=None, partition=True):
     """Count k-mers of genomes already resident in HBM.
 
     fasta    uint8 CUDA tensor holding the FASTA bytes of all genomes back to back
@@ -84,14 +88,14 @@ def count_dense_device(fasta, offsets, k_values, *, min_record_len=None, canonic
     stream = torch.cuda.current_stream(fasta.device).cuda_stream
     _lib.check(L.kmerml_count_dense_batch(
         ctx.handle, fasta.data_ptr(), offs.ctypes.data, n, karr.ctypes.data, len(ks),
-        int(min_record_len or 0), _lib.FLAG_CANONICAL if canonical else 0,
+        int(min_record_len or 0), _flags(canonical, partition),
         counts.data_ptr(), counts.stride(0), freq.data_ptr() if freq is not None else None,
         freq.stride(0) if freq is not None else 0, totals.data_ptr(), ctypes.c_void_p(stream)))
     return DenseResult(ks, counts, freq, totals)
 
 
 def count_dense_host(buffers, k_values, *, min_record_len=None, canonical=False, want_freq=True,
-                     device=None, out_counts=None, out_freq=None, out_totals=None):
+                     device=None, out_counts=None, out_freq=None, out_totals=None, partition=True):
     """End to end from host byte buffers (numpy uint8 arrays / pinned torch tensors): H2D,
     counting and D2H all inside libkmerml_b200.so.  Returns host (pinned) torch tensors."""
     if not torch.cuda.is_available():
@@ -124,7 +128,7 @@ def count_dense_host(buffers, k_values, *, min_record_len=None, canonical=False,
     karr = np.asarray(ks, dtype=np.int32)
     _lib.check(L.kmerml_count_dense_host(
         ctx.handle, ptrs, sizes.ctypes.data, n, karr.ctypes.data, len(ks), int(min_record_len or 0),
-        _lib.FLAG_CANONICAL if canonical else 0, counts.data_ptr(), counts.stride(0),
+        _flags(canonical, partition), counts.data_ptr(), counts.stride(0),
         freq.data_ptr() if freq is not None else None, freq.stride(0) if freq is not None else 0,
         totals.data_ptr()))
     return DenseResult(ks, counts, freq, totals)

@@ -92,7 +92,13 @@ int64_t emu_count_dense(const uint8_t* bytes, uint64_t n, uint64_t base_off, int
                 uint64_t cs, ce;
                 if (!clip(t, cs, ce)) continue;
                 bool in_hdr = flags[t] || cs < hdr_carry;
-                walk_chunk(g, cs, ce, in_hdr, P, sink, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
+                bool full = (ce - cs == CHUNK) && (cs % 4 == 0);
+                uint32_t w[CHUNK / 4];
+                if (full) memcpy(w, g.b + cs, CHUNK);
+                if (full && !in_hdr && P.min_rec == P.k && !any_byte_eq16(w, 0x3E3E3E3Eu))
+                    walk_chunk_fast(g, cs, w, P, sink);           // the path nearly every GPU thread takes
+                else
+                    walk_chunk(g, cs, ce, in_hdr, P, sink, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
             }
             hdr_carry = next_carry;
         }

@@ -30,8 +30,8 @@ def gpu_counts(datas, ks, **kw):
     return res
 
 
-def check_against_oracle(datas, ks, min_record_len=None, canonical=False):
-    res = gpu_counts(datas, ks, min_record_len=min_record_len, canonical=canonical)
+def check_against_oracle(datas, ks, min_record_len=None, canonical=False, partition=True):
+    res = gpu_counts(datas, ks, min_record_len=min_record_len, canonical=canonical, partition=partition)
     ml = min_record_len or max(ks)
     totals = res.totals.cpu().numpy()
     for g, d in enumerate(datas):
@@ -75,6 +75,9 @@ def test_golden_batch_all_cases_one_launch():
     check_against_oracle([c["fasta"] for c in cases], [1, 2, 3, 5, 7])
     check_against_oracle([c["fasta"] for c in cases], [8, 4])
     check_against_oracle([c["fasta"] for c in cases][:12], [12, 11, 3])
+    check_against_oracle([c["fasta"] for c in cases][:12], [12, 11, 3], partition=False)
+    check_against_oracle([c["fasta"] for c in cases], [9])
+    check_against_oracle([c["fasta"] for c in cases], [10, 6, 1])
 
 
 def test_fuzz_small():
@@ -83,7 +86,7 @@ def test_fuzz_small():
         datas = [fuzz_fasta(rng) for _ in range(rng.randint(1, 40))]
         ks = sorted(rng.sample(range(1, 13), rng.randint(1, 4)), reverse=rng.random() < 0.3)
         mr = None if rng.random() < 0.7 else max(ks) + rng.randint(1, 10)
-        check_against_oracle(datas, ks, min_record_len=mr)
+        check_against_oracle(datas, ks, min_record_len=mr, partition=(it % 3 != 0))
 
 
 def test_canonical_opt_in():
@@ -91,6 +94,7 @@ def test_canonical_opt_in():
     datas = [fuzz_fasta(rng, max_len=2000) for _ in range(6)]
     check_against_oracle(datas, [4, 5, 6], canonical=True)
     check_against_oracle(datas, [12, 9], canonical=True)
+    check_against_oracle(datas, [12, 9], canonical=True, partition=False)
 
 
 def test_medium_genomes_multi_slice():
@@ -114,6 +118,10 @@ def test_medium_genomes_multi_slice():
     check_against_oracle([g1, g2, g3], [1, 2, 3, 4, 5, 6, 7])
     check_against_oracle([g1, g2, g3], [8])
     check_against_oracle([g1, g3], list(range(1, 13)))
+    check_against_oracle([g1, g3], list(range(1, 13)), partition=False)
+    check_against_oracle([g1, g2, g3], [11, 9])
+    check_against_oracle([g2, g3], [10])
+    check_against_oracle([g1, g2], [13])
 
 
 def test_host_api_matches_device_api():
