@@ -298,7 +298,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     uint32_t* h_gtiles = (uint32_t*)(hs + off_bytes + sl_bytes);
     std::vector<int> group_end;                              // exclusive genome index per group
     if (use_part) {
-        const uint64_t max_tiles = (6ull << 30) / ((uint64_t)TILE_BYTES * 2);
+        const uint64_t max_tiles = (6ull << 30) / ((uint64_t)PART_TILE_CAP * 2);
         uint64_t in_group = 0;
         uint32_t group_tile0 = 0;
         for (int g = 0; g < n_genomes; g++) {
@@ -333,7 +333,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         uint64_t max_group_tiles = 0;
         for (size_t gi = 0, g0 = 0; gi < group_end.size(); g0 = group_end[gi], gi++)
             max_group_tiles = std::max<uint64_t>(max_group_tiles, first_slice[group_end[gi]] - first_slice[g0]);
-        const size_t payload_bytes = align_up((size_t)max_group_tiles * TILE_BYTES * 2, 256);
+        const size_t payload_bytes = align_up((size_t)max_group_tiles * PART_TILE_CAP * 2, 256);
         const size_t table_bytes = align_up((size_t)max_group_tiles * (size_t)(nb + 1) * 2 + 64, 256);
         rc = ws.part.ensure(payload_bytes + table_bytes);
         if (rc) return rc;

@@ -20,47 +20,47 @@
 namespace km {
 
 // --------------------------------------------------------------------- sinks
-struct GlobalSink {
-    uint32_t* top;
+// The hot sinks hold only what count() touches so that they live in registers; the
+// rare run-end tails go through DevTails (passed by reference to non-inlined code).
+struct DevTails {
     const LevelMap* lm;
     GenomeStats* st;
     uint32_t genome;
+    __device__ __noinline__ void tail(int j, uint32_t idx) const {
+        atomicAdd(lm->ptr(genome, j) + idx, 1u);
+        atomicAdd(&st->n_tail[j], 1ull);
+    }
+};
+
+struct NoTails {
+    __device__ __forceinline__ void tail(int, uint32_t) const {}
+};
+
+struct GlobalSink {
+    uint32_t* top;
     unsigned n;
     __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
         // no return value: a REDG.ADD executed by the L2 slice that owns the bin
         asm volatile("red.global.add.u32 [%0], 1;" ::"l"(__cvta_generic_to_global(top + idx)) : "memory");
         n++;
     }
-    __device__ __noinline__ void tail(int j, uint32_t idx) {
-        atomicAdd(lm->ptr(genome, j) + idx, 1u);
-        atomicAdd(&st->n_tail[j], 1ull);
-    }
 };
 
 struct SmemSink {
     uint32_t sbase;                    // shared-window address of the CTA's histogram
-    const LevelMap* lm;
-    GenomeStats* st;
-    uint32_t genome;
     unsigned n;
     __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(sbase + idx * 4u) : "memory");
         n++;
-    }
-    __device__ __noinline__ void tail(int j, uint32_t idx) {
-        atomicAdd(lm->ptr(genome, j) + idx, 1u);
-        atomicAdd(&st->n_tail[j], 1ull);
     }
 };
 
 struct FirstSink {
     uint32_t* first;
     uint64_t file_lo;
-    unsigned n;
     __device__ __forceinline__ void count(uint32_t idx, uint64_t pos) {
         atomicMin(first + idx, (uint32_t)(pos - file_lo));
     }
-    __device__ __forceinline__ void tail(int, uint32_t) {}
 };
 
 // ------------------------------------------------------------------ helpers
@@ -73,10 +73,11 @@ struct TileCtx {                      // shared-memory state of the tile loop
 };
 
 // The tile loop every counting kernel shares: 128-bit loads of the thread's 64-byte
-// chunk, header-line detection (phase 1), then the carry-free walk (phase 2).
-template <class Sink>
+// chunk, SWAR classification + header-line detection (phase 1), then the carry-free
+// walk (phase 2).
+template <class Sink, class Tails>
 __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, const Genome& g, const Slice& sl,
-                                           const DenseParams& P, Sink& sink, const TileCtx& tc) {
+                                           const DenseParams& P, Sink& sink, const Tails& tails, const TileCtx& tc) {
     const int tid = threadIdx.x;
     if (tid == 0) {
         unsigned long long c = 0;
@@ -94,19 +95,25 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
         const uint64_t ce = cb + CHUNK < g.hi ? cb + CHUNK : g.hi;
         const bool has = cs < ce;
         const bool full = has && (ce - cs == CHUNK);
-        uint32_t w[16];
-        bool gt = true;
+        uint32_t y[16], bad[16];
+        bool weird = true;
         if (full) {
+            uint32_t w[16];
             const uint4* src = reinterpret_cast<const uint4*>(buf + cb);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 uint4 v = __ldg(src + i);
                 w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
             }
-            gt = any_byte_eq16(w, 0x3E3E3E3Eu);
-        }
-        // phase 1: header lines that start in my chunk shadow the chunks after it
-        if (has && gt) {
+            weird = classify_chunk(w, y, bad) != 0;         // anything besides bases and '\n' ?
+            // phase 1: only chunks that hold a '>' can start a header line
+            if (weird && any_byte_eq16(w, 0x3E3E3E3Eu)) {
+                find_headers(g, cs, ce, [&](uint64_t, uint64_t until) {
+                    for (int j = tid + 1; j < COUNT_THREADS && tb + (uint64_t)j * CHUNK < until; j++) tc.flags[j] = 1;
+                    atomicMax(&tc.carry[1], (unsigned long long)until);
+                });
+            }
+        } else if (has) {
             find_headers(g, cs, ce, [&](uint64_t, uint64_t until) {
                 for (int j = tid + 1; j < COUNT_THREADS && tb + (uint64_t)j * CHUNK < until; j++) tc.flags[j] = 1;
                 atomicMax(&tc.carry[1], (unsigned long long)until);
@@ -116,8 +123,8 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
         // phase 2: walk
         if (has) {
             const bool in_hdr = tc.flags[tid] || cs < tc.carry[0];
-            if (full && !gt && !in_hdr && P.min_rec == P.k) walk_chunk_fast(g, cs, w, P, sink);
-            else walk_chunk(g, cs, ce, in_hdr, P, sink, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
+            if (full && !weird && !in_hdr && P.min_rec == P.k) walk_classified(g, cs, y, bad, P, sink, tails);
+            else walk_chunk(g, cs, ce, in_hdr, P, sink, tails, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
         }
         __syncthreads();
         if (tid == 0) tc.carry[0] = tc.carry[1];
@@ -174,22 +181,25 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
     if (tid == 0) sh_total = 0;
 
     unsigned n = 0;
+    if (MODE == 2) {
+        FirstSink sink;
+        sink.first = first; sink.file_lo = gd.file_lo;
+        NoTails nt;
+        walk_slice(buf, g, sl, P, sink, nt, tc);
+        return;
+    }
+    DevTails tails;
+    tails.lm = &lm; tails.st = stats + sl.genome; tails.genome = sl.genome;
     if (MODE == 0) {
         GlobalSink sink;
-        sink.top = lm.ptr(sl.genome, P.k); sink.lm = &lm; sink.st = stats + sl.genome; sink.genome = sl.genome; sink.n = 0;
-        walk_slice(buf, g, sl, P, sink, tc);
-        n = sink.n;
-    } else if (MODE == 1) {
-        SmemSink sink;
-        sink.sbase = (uint32_t)__cvta_generic_to_shared(sh_hist); sink.lm = &lm; sink.st = stats + sl.genome;
-        sink.genome = sl.genome; sink.n = 0;
-        walk_slice(buf, g, sl, P, sink, tc);
+        sink.top = lm.ptr(sl.genome, P.k); sink.n = 0;
+        walk_slice(buf, g, sl, P, sink, tails, tc);
         n = sink.n;
     } else {
-        FirstSink sink;
-        sink.first = first; sink.file_lo = gd.file_lo; sink.n = 0;
-        walk_slice(buf, g, sl, P, sink, tc);
-        return;
+        SmemSink sink;
+        sink.sbase = (uint32_t)__cvta_generic_to_shared(sh_hist); sink.n = 0;
+        walk_slice(buf, g, sl, P, sink, tails, tc);
+        n = sink.n;
     }
     const unsigned long long total = block_sum_u32(n, &sh_total);
     if (MODE == 1) {
@@ -204,48 +214,46 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
 }
 
 // ---------------------------------------------------------------- partition path
-// k = 9..12: the 4^k histogram (up to 64 MB) is too big for shared memory and L2
-// atomics top out near 190 G/s (and thrash the L2 next to the streamed input), so the
-// windows are first partitioned by their leading k-7 bases:
+// k = 9..12: the 4^k histogram (up to 64 MB) is too big for shared memory, and L2
+// atomics top out near 190 G/s (measured) and thrash the L2 next to the streamed
+// input, so the windows are first partitioned by their leading k-7 bases:
 //   partition_kernel  one CTA per 16 KB tile: walk, counting-sort the tile's windows by
 //                     bucket in shared memory, write them bucket-sorted as 14-bit
-//                     payloads (uint16) plus the tile's bucket offsets
+//                     payloads (uint16; every bucket segment padded to 8 bytes with
+//                     0xFFFF) plus the tile's bucket offsets
 //   bucket_kernel     one CTA per bucket: gather its segment from every tile into a
 //                     16384-bin shared histogram, then write that 64 KB slice of the
 //                     count row, its frequencies, and the bucket's whole cascade subtree
-// Only shared-memory atomics (2.5 T/s on B200) are used; every global access is a
-// coalesced stream.
+// Only shared-memory atomics (2.5 T/s measured on B200) are used; every global access
+// is a coalesced or 8-byte-aligned vector stream.
 constexpr int PART_LOW = 7;
 constexpr int PART_BINS = 1 << (2 * PART_LOW);        // 16384 bins per bucket
 constexpr int PART_MAX_BUCKETS = 1024;                // k <= 12
 constexpr int TILE_WINDOWS = TILE_BYTES;              // a tile owns at most one window per byte
+constexpr int SEG_ALIGN = 4;                          // entries: bucket segments start on 8-byte boundaries
+constexpr int TILE_CAP = TILE_WINDOWS + (SEG_ALIGN - 1) * PART_MAX_BUCKETS;   // padded entries per tile
+constexpr uint32_t PAD_ENTRY = 0xFFFFu;
 
 struct PartSink {
-    uint32_t raw_base;                 // shared address of raw[]: raw[n * COUNT_THREADS + tid]
+    uint32_t raw_addr;                 // shared address of raw[n_local * COUNT_THREADS + tid]
     uint32_t cnt_base;                 // shared address of cnt[]
     uint32_t n_local;
-    const LevelMap* lm;
-    GenomeStats* st;
-    uint32_t genome;
     __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(raw_base + (n_local * COUNT_THREADS + threadIdx.x) * 4u), "r"(idx) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(raw_addr), "r"(idx) : "memory");
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt_base + (idx >> (2 * PART_LOW)) * 4u) : "memory");
+        raw_addr += COUNT_THREADS * 4u;
         n_local++;
-    }
-    __device__ __noinline__ void tail(int j, uint32_t idx) {
-        atomicAdd(lm->ptr(genome, j) + idx, 1u);
-        atomicAdd(&st->n_tail[j], 1ull);
     }
 };
 
 struct PartSmem {
     uint32_t raw[TILE_WINDOWS];                 // 64 KB: the tile's windows, thread-interleaved
-    uint16_t staged[TILE_WINDOWS];              // 32 KB: payloads sorted by bucket
-    uint32_t cnt[PART_MAX_BUCKETS + 4];         // per-bucket count, then cursor
-    uint32_t off[PART_MAX_BUCKETS + 4];         // exclusive offsets
+    uint16_t staged[TILE_CAP];                  // 38 KB: payloads sorted by bucket, segments padded
+    uint32_t cnt[PART_MAX_BUCKETS];             // per-bucket count, then scatter cursor
+    uint32_t off[PART_MAX_BUCKETS + 4];         // exclusive (padded) offsets
     uint32_t warp_tot[COUNT_THREADS / 32];
+    uint32_t warp_cnt[COUNT_THREADS / 32];
     unsigned long long carry[2];
-    unsigned long long sh_total;
     uint8_t flags[COUNT_THREADS];
 };
 
@@ -266,30 +274,32 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     tc.flags = sm.flags;
     tc.carry = sm.carry;
     for (int i = tid; i < nb; i += COUNT_THREADS) sm.cnt[i] = 0;
-    if (tid == 0) sm.sh_total = 0;
 
     PartSink sink;
-    sink.raw_base = (uint32_t)__cvta_generic_to_shared(sm.raw);
+    sink.raw_addr = (uint32_t)__cvta_generic_to_shared(sm.raw) + tid * 4u;
     sink.cnt_base = (uint32_t)__cvta_generic_to_shared(sm.cnt);
     sink.n_local = 0;
-    sink.lm = &lm; sink.st = stats + sl.genome; sink.genome = sl.genome;
-    walk_slice(buf, g, sl, P, sink, tc);            // slice == one tile; ends with __syncthreads
+    DevTails tails;
+    tails.lm = &lm; tails.st = stats + sl.genome; tails.genome = sl.genome;
+    walk_slice(buf, g, sl, P, sink, tails, tc);     // slice == one tile; ends with __syncthreads
 
-    // exclusive scan of cnt[0..nb) (4 buckets per thread)
-    uint32_t v[4], s = 0;
+    // exclusive scan of the padded bucket counts (4 buckets per thread)
+    uint32_t v[4], s = 0, sv = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int b = 4 * tid + i;
         v[i] = b < nb ? sm.cnt[b] : 0u;
-        s += v[i];
+        s += (v[i] + (SEG_ALIGN - 1)) & ~(uint32_t)(SEG_ALIGN - 1);
+        sv += v[i];
     }
-    uint32_t inc = s;
+    uint32_t inc = s, incv = sv;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if ((tid & 31) >= o) inc += t;
+        uint32_t u = __shfl_up_sync(0xffffffffu, incv, o);
+        if ((tid & 31) >= o) { inc += t; incv += u; }
     }
-    if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = inc;
+    if ((tid & 31) == 31) { sm.warp_tot[tid >> 5] = inc; sm.warp_cnt[tid >> 5] = incv; }
     __syncthreads();
     uint32_t base = 0;
     for (int wdx = 0; wdx < (tid >> 5); wdx++) base += sm.warp_tot[wdx];
@@ -297,30 +307,53 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int b = 4 * tid + i;
-        if (b < nb) { sm.off[b] = ex; sm.cnt[b] = ex; }     // cnt becomes the scatter cursor
-        ex += v[i];
+        const uint32_t padded = (v[i] + (SEG_ALIGN - 1)) & ~(uint32_t)(SEG_ALIGN - 1);
+        if (b < nb) {
+            sm.off[b] = ex;
+            sm.cnt[b] = ex;                                    // cnt becomes the scatter cursor
+            for (uint32_t q = ex + v[i]; q < ex + padded; q++) sm.staged[q] = (uint16_t)PAD_ENTRY;
+        }
+        ex += padded;
     }
     if (tid == COUNT_THREADS - 1) sm.off[nb] = ex;
     __syncthreads();
-    const uint32_t total = sm.off[nb];
-    // the tile's row of the offset table
+    const uint32_t total_padded = sm.off[nb];
+    // the tile's row of the offset table (in units of SEG_ALIGN entries)
     uint16_t* trow = table + (size_t)blockIdx.x * (size_t)(nb + 1);
-    for (int i = tid; i <= nb; i += COUNT_THREADS) trow[i] = (uint16_t)sm.off[i];
+    for (int i = tid; i <= nb; i += COUNT_THREADS) trow[i] = (uint16_t)(sm.off[i] / SEG_ALIGN);
     // scatter payloads into bucket order
     const uint32_t cnt_base = sink.cnt_base;
-    for (uint32_t n = 0; n < sink.n_local; n++) {
-        const uint32_t idx = sm.raw[n * COUNT_THREADS + tid];
+    const uint32_t staged_base = (uint32_t)__cvta_generic_to_shared(sm.staged);
+    const uint32_t* rp = sm.raw + tid;
+    uint32_t n = 0;
+    for (; n + 4 <= sink.n_local; n += 4) {
+        uint32_t idx[4], pos[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) idx[u] = rp[(n + u) * COUNT_THREADS];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos[u]) : "r"(cnt_base + (idx[u] >> (2 * PART_LOW)) * 4u) : "memory");
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(staged_base + pos[u] * 2u), "h"((uint16_t)(idx[u] & (PART_BINS - 1))) : "memory");
+    }
+    for (; n < sink.n_local; n++) {
+        const uint32_t idx = rp[n * COUNT_THREADS];
         uint32_t pos;
         asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cnt_base + (idx >> (2 * PART_LOW)) * 4u) : "memory");
         sm.staged[pos] = (uint16_t)(idx & (PART_BINS - 1));
     }
     __syncthreads();
     // coalesced copy of the sorted tile
-    uint4* dst = reinterpret_cast<uint4*>(payload + (size_t)blockIdx.x * TILE_WINDOWS);
+    uint4* dst = reinterpret_cast<uint4*>(payload + (size_t)blockIdx.x * TILE_CAP);
     const uint4* src = reinterpret_cast<const uint4*>(sm.staged);
-    const uint32_t nvec = (total + 7) >> 3;
+    const uint32_t nvec = (total_padded + 7) >> 3;
     for (uint32_t i = tid; i < nvec; i += COUNT_THREADS) dst[i] = src[i];
-    if (tid == 0 && total) atomicAdd(&stats[sl.genome].total_top, (unsigned long long)total);
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int wdx = 0; wdx < COUNT_THREADS / 32; wdx++) total += sm.warp_cnt[wdx];
+        if (total) atomicAdd(&stats[sl.genome].total_top, (unsigned long long)total);
+    }
 }
 
 struct GenomeTiles {                   // tiles of one genome inside the group's tile list
@@ -332,7 +365,7 @@ struct LevelInfo {                     // per level: index into the caller's k_l
 };
 
 constexpr int BUCKET_THREADS = 512;
-constexpr int BUCKET_BATCH = 2048;     // tile segments staged per round
+constexpr int BUCKET_BATCH = 4096;     // tile segments staged per round
 
 struct BucketSmem {
     uint32_t hist[PART_BINS];          // 64 KB
@@ -340,6 +373,12 @@ struct BucketSmem {
     uint32_t seg[BUCKET_BATCH];        // (start | end << 16) of this bucket's segment in each tile
     unsigned long long tot[16];
 };
+
+__device__ __forceinline__ void hist_add2(uint32_t hbase, uint32_t two) {
+    const uint32_t lo = two & 0xFFFFu, hi = two >> 16;
+    if (lo != PAD_ENTRY) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + lo * 4u) : "memory");
+    if (hi != PAD_ENTRY) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + hi * 4u) : "memory");
+}
 
 __global__ void __launch_bounds__(BUCKET_THREADS)
 bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const GenomeTiles* __restrict__ gts,
@@ -352,7 +391,10 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
     const uint32_t b = blockIdx.x;
     const uint32_t g = genome0 + blockIdx.y;
     const GenomeTiles gt = gts[g];
-    for (int i = tid; i < PART_BINS; i += BUCKET_THREADS) sm.hist[i] = 0;
+    {
+        uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
+        for (int i = tid; i < PART_BINS / 4; i += BUCKET_THREADS) h4[i] = make_uint4(0, 0, 0, 0);
+    }
     if (tid < row.nk) {
         const int j = row.k[tid];
         unsigned long long t = stats[g].total_top;
@@ -361,7 +403,6 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
         if (totals && b == 0) totals[(uint64_t)g * row.nk + tid] = t;
     }
     const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sm.hist);
-    const int half = tid >> 4, hl = tid & 15;               // 32 half-warps, 16 lanes each
     for (uint32_t t0 = 0; t0 < gt.n_tiles; t0 += BUCKET_BATCH) {
         const uint32_t nt = min((uint32_t)BUCKET_BATCH, gt.n_tiles - t0);
         __syncthreads();
@@ -370,13 +411,20 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
             sm.seg[i] = (uint32_t)trow[0] | ((uint32_t)trow[1] << 16);
         }
         __syncthreads();
-        for (uint32_t i = half; i < nt; i += BUCKET_THREADS / 16) {
+        // one thread per (tile, bucket) segment: 8-byte vectors, first four loads in flight together
+        for (uint32_t i = tid; i < nt; i += BUCKET_THREADS) {
             const uint32_t se = sm.seg[i];
-            const uint32_t s0 = se & 0xFFFFu, s1 = se >> 16;
-            const uint16_t* src = payload + (size_t)(gt.tile0 + t0 + i) * TILE_WINDOWS;
-            for (uint32_t q = s0 + hl; q < s1; q += 16) {
-                const uint32_t p = src[q];
-                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + p * 4u) : "memory");
+            const uint32_t v0 = se & 0xFFFFu, v1 = se >> 16;
+            const uint2* src = reinterpret_cast<const uint2*>(payload + (size_t)(gt.tile0 + t0 + i) * TILE_CAP);
+            uint2 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) x[u] = (v0 + u < v1) ? __ldg(src + v0 + u) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+#pragma unroll
+            for (int u = 0; u < 4; u++) { hist_add2(hbase, x[u].x); hist_add2(hbase, x[u].y); }
+            for (uint32_t q = v0 + 4; q < v1; q++) {
+                const uint2 xx = __ldg(src + q);
+                hist_add2(hbase, xx.x);
+                hist_add2(hbase, xx.y);
             }
         }
     }

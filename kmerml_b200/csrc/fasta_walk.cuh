@@ -174,9 +174,10 @@ struct WalkState {
 // A run of valid bases ended just before `pos` (pos = the invalid symbol, the '>'
 // of the next record, or g.hi).  Emits the last j-mer of the run for every
 // j < k with run >= j: the j-mers that have no (j+1)-mer extension, which the
-// marginalisation cascade cannot see.
-template <class Sink>
-KM_HD_NOINLINE void run_end_event(const Genome& g, uint64_t pos, const DenseParams& P, Sink& sink) {
+// marginalisation cascade cannot see.  `tails` is kept apart from the hot sink so
+// that the sink's counters stay in registers (this function is never inlined).
+template <class Tails>
+KM_HD_NOINLINE void run_end_event(const Genome& g, uint64_t pos, const DenseParams& P, const Tails& tails) {
     uint64_t q = pos;
     uint32_t code = 0;
     int cnt = 0;
@@ -190,7 +191,7 @@ KM_HD_NOINLINE void run_end_event(const Genome& g, uint64_t pos, const DensePara
     uint64_t inside = pos;
     (void)prev_symbol(g, inside);                       // byte position of the run's last base
     if (!record_len_at_least(g, inside, P.min_rec)) return;
-    for (int j = P.tail_lo > 1 ? P.tail_lo : 1; j <= cnt; j++) sink.tail(j, code & ((1u << (2 * j)) - 1u));
+    for (int j = P.tail_lo > 1 ? P.tail_lo : 1; j <= cnt; j++) tails.tail(j, code & ((1u << (2 * j)) - 1u));
 }
 
 template <class Sink>
@@ -206,9 +207,10 @@ KM_HD void on_base(const Genome& g, uint64_t pos, int code, WalkState& s, const 
     }
 }
 
-// One byte of the thread's own chunk.
-template <class Sink>
-KM_HD void step_own(const Genome& g, uint64_t pos, uint32_t c, WalkState& s, const DenseParams& P, Sink& sink) {
+// One byte of the thread's own chunk (generic path).
+template <class Sink, class Tails>
+KM_HD void step_own(const Genome& g, uint64_t pos, uint32_t c, WalkState& s, const DenseParams& P, Sink& sink,
+                    const Tails& tails) {
     int code = base_code(c);
     if (code >= 0 && !s.in_hdr) {
         s.pend = 1;
@@ -221,22 +223,22 @@ KM_HD void step_own(const Genome& g, uint64_t pos, uint32_t c, WalkState& s, con
     }
     int kind = classify_nonbase(g, pos, c);
     if (kind == SYM_SKIP) return;
-    if (s.pend && P.tails) run_end_event(g, pos, P, sink);
+    if (s.pend && P.tails) run_end_event(g, pos, P, tails);
     s.pend = 0;
     s.run = 0;
     if (kind == SYM_HDR) { s.in_hdr = 1; s.rec_known = 0; }
 }
 
 // After the own chunk: finish the windows that started in it (at most k-1 more
-// symbols) and detect a run end right at the chunk boundary.
-template <class Sink>
-KM_HD void walk_overhang(const Genome& g, uint64_t ce, WalkState& s, const DenseParams& P, Sink& sink) {
+// symbols, `cnt` of which were already consumed) and detect a run end right at
+// the chunk boundary.  Generic byte-by-byte version starting at `pos`.
+template <class Sink, class Tails>
+KM_HD_NOINLINE void walk_overhang(const Genome& g, uint64_t pos, int cnt, WalkState& s, const DenseParams& P,
+                                  Sink& sink, const Tails& tails) {
     if (s.run == 0 || s.in_hdr) return;
-    uint64_t pos = ce;
-    int cnt = 0;
     while (cnt < P.k - 1 || s.pend) {
         if (pos >= g.hi) {
-            if (s.pend && P.tails) run_end_event(g, g.hi, P, sink);
+            if (s.pend && P.tails) run_end_event(g, g.hi, P, tails);
             return;
         }
         uint32_t c = g.b[pos];
@@ -251,19 +253,19 @@ KM_HD void walk_overhang(const Genome& g, uint64_t ce, WalkState& s, const Dense
         }
         int kind = classify_nonbase(g, pos, c);
         if (kind == SYM_SKIP) { pos++; continue; }
-        if (s.pend && P.tails) run_end_event(g, pos, P, sink);
+        if (s.pend && P.tails) run_end_event(g, pos, P, tails);
         return;
     }
 }
 
-// Walk one chunk [cs, ce) whose bytes are read through `at(pos)`.
-template <class Sink, class ByteAt>
+// Walk one chunk [cs, ce) whose bytes are read through `at(pos)` (generic path).
+template <class Sink, class Tails, class ByteAt>
 KM_HD void walk_chunk(const Genome& g, uint64_t cs, uint64_t ce, bool starts_in_header,
-                      const DenseParams& P, Sink& sink, ByteAt&& at) {
+                      const DenseParams& P, Sink& sink, const Tails& tails, ByteAt&& at) {
     WalkState s;
     s.kmer = 0; s.run = 0; s.in_hdr = starts_in_header ? 1 : 0; s.pend = 0; s.rec_known = 0;
-    for (uint64_t pos = cs; pos < ce; pos++) step_own(g, pos, at(pos), s, P, sink);
-    walk_overhang(g, ce, s, P, sink);
+    for (uint64_t pos = cs; pos < ce; pos++) step_own(g, pos, at(pos), s, P, sink, tails);
+    walk_overhang(g, ce, 0, s, P, sink, tails);
 }
 
 // 4-entry byte LUT: byte i of the result = byte (sel nibble i) of `lut` (PRMT on the GPU).
@@ -277,54 +279,118 @@ KM_HD uint32_t prmt4(uint32_t lut, uint32_t sel) {
 #endif
 }
 
-// Per 32-bit word of FASTA bytes: 2-bit codes in bits [1:0] of every byte (y) and a
-// 0x80 flag in every byte that is not one of AaCcGgTt (bad).  13 integer ops per 4 bases.
-KM_HD void classify_word(uint32_t x, uint32_t& y, uint32_t& bad) {
+// Per 32-bit word of FASTA bytes: 2-bit codes in bits [1:0] of every byte (y), a 0x80
+// flag in every byte that is not one of AaCcGgTt (bad), and a non-zero `weird` when
+// one of those is anything but '\n'.  ~18 integer ops per 4 bases, no table lookups.
+KM_HD void classify_word(uint32_t x, uint32_t& y, uint32_t& bad, uint32_t& weird) {
     const uint32_t u = x & 0xDFDFDFDFu;                       // upper-case (generate.py:41)
     y = ((u >> 1) ^ (u >> 2)) & 0x03030303u;                   // A0 C1 G2 T3
     const uint32_t t = y | (y >> 4);
     const uint32_t sel = (t & 0xFFu) | ((t >> 8) & 0xFF00u);   // the 4 codes as PRMT selector nibbles
     const uint32_t d = prmt4(0x54474341u, sel) ^ u;            // "ACGT"[code] == byte ?
     bad = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+    const uint32_t n = x ^ 0x0A0A0A0Au;
+    const uint32_t not_nl = (((n & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | n) & 0x80808080u;
+    weird = bad & not_nl;
 }
 
-// Fast walk of a chunk that (a) lies completely inside the genome, (b) does not start
-// inside a header line, (c) holds no '>' byte, with (d) min_rec == k.  Everything else
-// goes through walk_chunk.  `w` = the chunk's 16 little-endian words.
-template <class Sink>
-KM_HD void walk_chunk_fast(const Genome& g, uint64_t cs, const uint32_t* w, const DenseParams& P, Sink& sink) {
+// Classify the 16 words of a chunk; returns non-zero when the chunk holds a byte that
+// is neither a base nor '\n' (N runs, IUPAC codes, '>', '\r', blanks ...).
+KM_HD uint32_t classify_chunk(const uint32_t* w, uint32_t* y, uint32_t* bad) {
+    uint32_t weird = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < CHUNK / 4; i++) {
+        uint32_t wd;
+        classify_word(w[i], y[i], bad[i], wd);
+        weird |= wd;
+    }
+    return weird;
+}
+
+// Branch-free walk of a classified chunk that (a) lies completely inside the genome,
+// (b) does not start inside a header line, (c) holds nothing but bases and '\n'
+// (classify_chunk returned 0), with (d) min_rec == k.  Everything else takes the
+// generic walk_chunk.
+template <class Sink, class Tails>
+KM_HD void walk_classified(const Genome& g, uint64_t cs, const uint32_t* y, const uint32_t* bad,
+                           const DenseParams& P, Sink& sink, const Tails& tails) {
     uint32_t kmer = 0;
     int run = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int i = 0; i < CHUNK / 4; i++) {
-        const uint32_t x = w[i];
-        uint32_t y, bad;
-        classify_word(x, y, bad);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int j = 0; j < 4; j++) {
-            if (!(bad & (0x80u << (8 * j)))) {
-                kmer = (kmer << 2) | ((y >> (8 * j)) & 3u);
+            if (!(bad[i] & (0x80u << (8 * j)))) {              // every other byte here is '\n': no state change
+                kmer = (kmer << 2) | ((y[i] >> (8 * j)) & 3u);
                 run++;
                 if (run >= P.k) sink.count(kmer & P.mask, cs + (uint64_t)(4 * i + j));
-            } else {
-                const uint32_t c = (x >> (8 * j)) & 0xFFu;
-                if (c != 10u) {
-                    const uint64_t pos = cs + (uint64_t)(4 * i + j);
-                    if (classify_nonbase(g, pos, c) != SYM_SKIP) {
-                        if (run > 0 && P.tails) run_end_event(g, pos, P, sink);
-                        run = 0;
-                    }
-                }
             }
         }
     }
+    if (run == 0) return;
+    // overhang: up to k-1 more bases finish the windows that started in this chunk
+    uint64_t pos = cs + CHUNK;
+    int cnt = 0;
+    if (pos + 16 <= g.hi) {
+        uint32_t oy[4], ob[4];
+        uint32_t ow = 0;
+#if defined(__CUDA_ARCH__)
+        const uint4 v = *reinterpret_cast<const uint4*>(g.b + pos);
+        const uint32_t o[4] = {v.x, v.y, v.z, v.w};
+#else
+        uint32_t o[4];
+        for (int i = 0; i < 4; i++)
+            o[i] = (uint32_t)g.b[pos + 4 * i] | ((uint32_t)g.b[pos + 4 * i + 1] << 8) |
+                   ((uint32_t)g.b[pos + 4 * i + 2] << 16) | ((uint32_t)g.b[pos + 4 * i + 3] << 24);
+#endif
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < 4; i++) {
+            uint32_t wd;
+            classify_word(o[i], oy[i], ob[i], wd);
+            ow |= wd;
+        }
+        if (!ow) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int i = 0; i < 4; i++) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int j = 0; j < 4; j++) {
+                    if (!(ob[i] & (0x80u << (8 * j))) && cnt < P.k - 1) {
+                        kmer = (kmer << 2) | ((oy[i] >> (8 * j)) & 3u);
+                        run++;
+                        cnt++;
+                        if (run >= P.k) sink.count(kmer & P.mask, pos + (uint64_t)(4 * i + j));
+                    }
+                }
+            }
+            if (cnt >= P.k - 1) return;
+            pos += 16;                                         // mostly line ends in there: keep going below
+        }
+    }
     WalkState s;
-    s.kmer = kmer; s.run = run; s.in_hdr = 0; s.pend = run > 0 ? 1 : 0; s.rec_known = 0;
-    walk_overhang(g, cs + CHUNK, s, P, sink);
+    s.kmer = kmer; s.run = run; s.in_hdr = 0; s.pend = cnt == 0 ? 1 : 0; s.rec_known = 0;
+    walk_overhang(g, pos, cnt, s, P, sink, tails);
+}
+
+// classify + walk; false (nothing emitted) when the chunk needs the generic path.
+template <class Sink, class Tails>
+KM_HD bool walk_chunk_fast(const Genome& g, uint64_t cs, const uint32_t* w, const DenseParams& P, Sink& sink,
+                           const Tails& tails) {
+    uint32_t y[CHUNK / 4], bad[CHUNK / 4];
+    if (classify_chunk(w, y, bad)) return false;
+    walk_classified(g, cs, y, bad, P, sink, tails);
+    return true;
 }
 
 // Does any byte of the 16 words equal the byte replicated in `pattern`?

@@ -78,6 +78,7 @@ int launch_finalize(const LevelMap& lm, const RowSpec& row, int k_top, bool cano
                     uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s);
 // partition path (k = 9..12)
 constexpr int PART_MIN_K = 9, PART_MAX_K = 12, PART_LOW_BASES = 7;
+constexpr int PART_TILE_CAP = TILE_BYTES + 3 * 1024;    // padded payload entries per tile (dense.cu TILE_CAP)
 int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles,
                      int k, int k_bottom, int min_rec, const LevelMap& lm, GenomeStats* d_stats,
                      uint16_t* d_payload, uint16_t* d_table, cudaStream_t s);

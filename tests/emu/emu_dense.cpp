@@ -23,7 +23,7 @@ struct EmuSink {
         n_count++;
         if (first && pos < (*first)[idx]) (*first)[idx] = pos;
     }
-    void tail(int j, uint32_t idx) { (*tails)[j][idx]++; }
+    void tail(int j, uint32_t idx) const { (*tails)[j][idx]++; }
 };
 }  // namespace
 
@@ -95,10 +95,10 @@ int64_t emu_count_dense(const uint8_t* bytes, uint64_t n, uint64_t base_off, int
                 bool full = (ce - cs == CHUNK) && (cs % 4 == 0);
                 uint32_t w[CHUNK / 4];
                 if (full) memcpy(w, g.b + cs, CHUNK);
-                if (full && !in_hdr && P.min_rec == P.k && !any_byte_eq16(w, 0x3E3E3E3Eu))
-                    walk_chunk_fast(g, cs, w, P, sink);           // the path nearly every GPU thread takes
-                else
-                    walk_chunk(g, cs, ce, in_hdr, P, sink, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
+                // the fast path is what nearly every GPU thread takes; it declines (before
+                // emitting anything) chunks that hold more than bases and line feeds
+                if (!(full && !in_hdr && P.min_rec == P.k && walk_chunk_fast(g, cs, w, P, sink, sink)))
+                    walk_chunk(g, cs, ce, in_hdr, P, sink, sink, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
             }
             hdr_carry = next_carry;
         }
