@@ -289,6 +289,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
                 h_slices[si].pad = 0;
                 h_slices[si].begin = b * sb;
                 h_slices[si].end = (b + 1) * sb;
+                h_slices[si].hdr_until = 0;
                 si++;
             }
         }
@@ -320,8 +321,9 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     KM_CUDA(cudaEventRecord(ws.staging_free, s));
 
     {
-        Prof pr(ctx, s, 3, 1);
+        Prof pr(ctx, s, 3, 2);
         rc = launch_prologue(d_fasta, d_offsets, d_genomes, d_stats, n_genomes, s);
+        if (!rc) rc = launch_slice_headers(d_fasta, d_genomes, d_slices, (int)n_slices, s);
     }
     if (rc) return rc;
     const int n_cascade = cascade_launches(kmax, kmin);
@@ -606,12 +608,16 @@ int kmerml_first_occurrence(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nb
         h_slices[b].pad = 0;
         h_slices[b].begin = b * sb;
         h_slices[b].end = (b + 1) * sb;
+        h_slices[b].hdr_until = 0;
     }
     KM_CUDA(cudaMemcpyAsync(base, hs, off_bytes, cudaMemcpyHostToDevice, s));
     KM_CUDA(cudaMemcpyAsync(base + off_bytes + gen_bytes + st_bytes, h_slices, sl_bytes, cudaMemcpyHostToDevice, s));
     KM_CUDA(cudaEventRecord(ws.staging_free, s));
     rc = launch_prologue(d_fasta, (const uint64_t*)base, (GenomeDev*)(base + off_bytes),
                          (GenomeStats*)(base + off_bytes + gen_bytes), 1, s);
+    if (rc) return rc;
+    rc = launch_slice_headers(d_fasta, (const GenomeDev*)(base + off_bytes),
+                              (Slice*)(base + off_bytes + gen_bytes + st_bytes), (int)n_slices, s);
     if (rc) return rc;
     return launch_first_occurrence(d_fasta, (const GenomeDev*)(base + off_bytes),
                                    (const Slice*)(base + off_bytes + gen_bytes + st_bytes), (int)n_slices, k, min_rec,

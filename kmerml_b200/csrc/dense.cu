@@ -10,7 +10,7 @@
 //   finalize_kernel   optional canonical fold, frequency row, window totals
 //
 // Work decomposition: a CTA owns a slice (a few tiles) of one genome; a thread owns
-// the windows that START in its 64-byte chunk of the tile (fasta_walk.cuh), so there
+// the windows that START in its 32-byte chunk of the tile (fasta_walk.cuh), so there
 // is no carry between threads and no compaction pass: the FASTA bytes are read once.
 #include <algorithm>
 
@@ -69,64 +69,95 @@ __device__ __forceinline__ void level_totals(const RowSpec& row, int k_top, cons
 
 struct TileCtx {                      // shared-memory state of the tile loop
     uint8_t* flags;                   // [COUNT_THREADS] chunk starts inside a header line
+    uint8_t* clean;                   // [COUNT_THREADS] chunk is clean (bases + at most one '\n')
+    uint32_t* last16;                 // [COUNT_THREADS] last 16 bases of a clean chunk
     unsigned long long* carry;        // [2] end of a header line that runs into later tiles
+    uint32_t* prev_tile;              // [2] {ok, last16} of the previous tile's last chunk
 };
 
-// The tile loop every counting kernel shares: 128-bit loads of the thread's 64-byte
-// chunk, SWAR classification + header-line detection (phase 1), then the carry-free
-// walk (phase 2).
+#define KM_TILE_SMEM(prefix)                                   \
+    __shared__ uint8_t prefix##_flags[COUNT_THREADS];          \
+    __shared__ uint8_t prefix##_clean[COUNT_THREADS];          \
+    __shared__ uint32_t prefix##_last16[COUNT_THREADS];        \
+    __shared__ unsigned long long prefix##_carry[2];           \
+    __shared__ uint32_t prefix##_prev[2];                      \
+    TileCtx tc;                                                \
+    tc.flags = prefix##_flags; tc.clean = prefix##_clean; tc.last16 = prefix##_last16; \
+    tc.carry = prefix##_carry; tc.prev_tile = prefix##_prev;
+
+// The tile loop every counting kernel shares.  Per tile and thread: two 128-bit loads
+// of the 32-byte chunk, SWAR classification, bit-compaction of clean chunks and
+// header-line detection (phase 1); then either the funnel-shift emission of a clean
+// chunk whose left neighbour is clean too, or the generic byte walker (phase 2).
 template <class Sink, class Tails>
 __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, const Genome& g, const Slice& sl,
                                            const DenseParams& P, Sink& sink, const Tails& tails, const TileCtx& tc) {
     const int tid = threadIdx.x;
     if (tid == 0) {
-        unsigned long long c = 0;
-        uint64_t until;
-        if (sl.begin > g.lo && pos_in_header(g, sl.begin, &until)) c = until;
-        tc.carry[0] = c;
-        tc.carry[1] = c;
+        tc.carry[0] = sl.hdr_until;                         // resolved per slice by slice_header_kernel
+        tc.carry[1] = sl.hdr_until;
+        tc.prev_tile[0] = 0;                                // the chunk before the slice is someone else's
+        tc.prev_tile[1] = 0;
     }
     const uint64_t end = sl.end < g.hi ? sl.end : g.hi;
     for (uint64_t tb = sl.begin; tb < end; tb += TILE_BYTES) {
         tc.flags[tid] = 0;
-        __syncthreads();                                    // flags cleared, carry[0] visible
+        __syncthreads();                                    // flags cleared, carry / prev_tile visible
         const uint64_t cb = tb + (uint64_t)tid * CHUNK;
         const uint64_t cs = cb > g.lo ? cb : g.lo;
         const uint64_t ce = cb + CHUNK < g.hi ? cb + CHUNK : g.hi;
         const bool has = cs < ce;
         const bool full = has && (ce - cs == CHUNK);
-        uint32_t y[16], bad[16];
-        bool weird = true;
+        CleanChunk cc;
+        cc.hi = cc.lo = 0; cc.n = 0; cc.nl = 32; cc.last16 = 0;
+        bool clean = false;
+        auto on_header = [&](uint64_t, uint64_t until) {
+            for (int j = tid + 1; j < COUNT_THREADS && tb + (uint64_t)j * CHUNK < until; j++) tc.flags[j] = 1;
+            atomicMax(&tc.carry[1], (unsigned long long)until);
+        };
         if (full) {
-            uint32_t w[16];
+            uint32_t w[CHUNK / 4], y[CHUNK / 4], bad[CHUNK / 4];
             const uint4* src = reinterpret_cast<const uint4*>(buf + cb);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < CHUNK / 16; i++) {
                 uint4 v = __ldg(src + i);
                 w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
             }
-            weird = classify_chunk(w, y, bad) != 0;         // anything besides bases and '\n' ?
-            // phase 1: only chunks that hold a '>' can start a header line
-            if (weird && any_byte_eq16(w, 0x3E3E3E3Eu)) {
-                find_headers(g, cs, ce, [&](uint64_t, uint64_t until) {
-                    for (int j = tid + 1; j < COUNT_THREADS && tb + (uint64_t)j * CHUNK < until; j++) tc.flags[j] = 1;
-                    atomicMax(&tc.carry[1], (unsigned long long)until);
-                });
-            }
+            const bool weird = classify_chunk(w, y, bad) != 0;      // anything besides bases and '\n' ?
+            clean = !weird && pack_clean(y, bad, cc);
+            // only chunks that hold a '>' can start a header line
+            if (weird && any_byte_eq_chunk(w, 0x3E3E3E3Eu)) find_headers(g, cs, ce, on_header);
         } else if (has) {
-            find_headers(g, cs, ce, [&](uint64_t, uint64_t until) {
-                for (int j = tid + 1; j < COUNT_THREADS && tb + (uint64_t)j * CHUNK < until; j++) tc.flags[j] = 1;
-                atomicMax(&tc.carry[1], (unsigned long long)until);
-            });
+            find_headers(g, cs, ce, on_header);
         }
+        tc.clean[tid] = clean ? 1 : 0;
+        tc.last16[tid] = cc.last16;
         __syncthreads();
-        // phase 2: walk
+        // phase 2
+        const unsigned long long hc = tc.carry[0];
+        const bool in_hdr = tc.flags[tid] || cs < hc;
+        bool prev_ok;
+        uint32_t carry16;
+        if (tid > 0) {
+            prev_ok = tc.clean[tid - 1] && !tc.flags[tid - 1] && !(cb - CHUNK < hc);
+            carry16 = tc.last16[tid - 1];
+        } else {
+            prev_ok = tc.prev_tile[0] != 0;
+            carry16 = tc.prev_tile[1];
+        }
         if (has) {
-            const bool in_hdr = tc.flags[tid] || cs < tc.carry[0];
-            if (full && !weird && !in_hdr && P.min_rec == P.k) walk_classified(g, cs, y, bad, P, sink, tails);
-            else walk_chunk(g, cs, ce, in_hdr, P, sink, tails, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
+            if (clean && !in_hdr && prev_ok && P.min_rec == P.k) {
+                emit_clean(cc, carry16, cs, P, sink);
+                if (ce == g.hi && P.tails) run_end_event(g, g.hi, P, tails);
+            } else {
+                walk_chunk(g, cs, ce, in_hdr, P, sink, tails, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
+            }
         }
         __syncthreads();
+        if (tid == COUNT_THREADS - 1) {
+            tc.prev_tile[0] = (has && clean && !in_hdr) ? 1u : 0u;
+            tc.prev_tile[1] = cc.last16;
+        }
         if (tid == 0) tc.carry[0] = tc.carry[1];
     }
 }
@@ -152,6 +183,23 @@ __global__ void prologue_kernel(const uint8_t* __restrict__ buf, const uint64_t*
     for (int j = 0; j < 16; j++) st[g].n_tail[j] = 0;
 }
 
+// Per slice: does its first byte lie inside a header line that started earlier?  (One
+// thread per slice, so the serial backward scans overlap instead of stalling a CTA.)
+__global__ void slice_header_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
+                                    Slice* slices, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Slice sl = slices[i];
+    const GenomeDev gd = gds[sl.genome];
+    Genome g;
+    g.b = buf;
+    g.lo = gd.lo;
+    g.hi = gd.hi;
+    uint64_t until = 0;
+    if (!(sl.begin > g.lo && pos_in_header(g, sl.begin, &until))) until = 0;
+    slices[i].hdr_until = until;
+}
+
 // MODE 0: global histogram, 1: shared histogram, 2: first occurrence
 template <int MODE>
 __global__ void __launch_bounds__(COUNT_THREADS)
@@ -159,8 +207,7 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
              const Slice* __restrict__ slices, DenseParams P, LevelMap lm, GenomeStats* stats,
              uint32_t* first) {
     extern __shared__ __align__(16) uint32_t sh_hist[];
-    __shared__ uint8_t flags[COUNT_THREADS];
-    __shared__ unsigned long long carry[2];
+    KM_TILE_SMEM(ck)
     __shared__ unsigned long long sh_total;
 
     const int tid = threadIdx.x;
@@ -170,9 +217,6 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
     g.b = buf;
     g.lo = gd.lo;
     g.hi = gd.hi;
-    TileCtx tc;
-    tc.flags = flags;
-    tc.carry = carry;
 
     if (MODE == 1) {
         const int nb = 1 << (2 * P.k);
@@ -237,12 +281,10 @@ constexpr uint32_t PAD_ENTRY = 0xFFFFu;
 struct PartSink {
     uint32_t raw_addr;                 // shared address of raw[n_local * COUNT_THREADS + tid]
     uint32_t cnt_base;                 // shared address of cnt[]
-    uint32_t n_local;
     __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(raw_addr), "r"(idx) : "memory");
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt_base + (idx >> (2 * PART_LOW)) * 4u) : "memory");
         raw_addr += COUNT_THREADS * 4u;
-        n_local++;
     }
 };
 
@@ -253,8 +295,11 @@ struct PartSmem {
     uint32_t off[PART_MAX_BUCKETS + 4];         // exclusive (padded) offsets
     uint32_t warp_tot[COUNT_THREADS / 32];
     uint32_t warp_cnt[COUNT_THREADS / 32];
+    uint32_t last16[COUNT_THREADS];
     unsigned long long carry[2];
+    uint32_t prev_tile[2];
     uint8_t flags[COUNT_THREADS];
+    uint8_t clean[COUNT_THREADS];
 };
 
 __global__ void __launch_bounds__(COUNT_THREADS, 2)
@@ -271,23 +316,24 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     g.lo = gd.lo;
     g.hi = gd.hi;
     TileCtx tc;
-    tc.flags = sm.flags;
-    tc.carry = sm.carry;
+    tc.flags = sm.flags; tc.clean = sm.clean; tc.last16 = sm.last16;
+    tc.carry = sm.carry; tc.prev_tile = sm.prev_tile;
     for (int i = tid; i < nb; i += COUNT_THREADS) sm.cnt[i] = 0;
 
     PartSink sink;
-    sink.raw_addr = (uint32_t)__cvta_generic_to_shared(sm.raw) + tid * 4u;
+    const uint32_t raw0 = (uint32_t)__cvta_generic_to_shared(sm.raw) + tid * 4u;
+    sink.raw_addr = raw0;
     sink.cnt_base = (uint32_t)__cvta_generic_to_shared(sm.cnt);
-    sink.n_local = 0;
     DevTails tails;
     tails.lm = &lm; tails.st = stats + sl.genome; tails.genome = sl.genome;
     walk_slice(buf, g, sl, P, sink, tails, tc);     // slice == one tile; ends with __syncthreads
 
-    // exclusive scan of the padded bucket counts (4 buckets per thread)
-    uint32_t v[4], s = 0, sv = 0;
+    // exclusive scan of the padded bucket counts (SCAN_PER buckets per thread)
+    constexpr int SCAN_PER = PART_MAX_BUCKETS / COUNT_THREADS;
+    uint32_t v[SCAN_PER], s = 0, sv = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int b = 4 * tid + i;
+    for (int i = 0; i < SCAN_PER; i++) {
+        const int b = SCAN_PER * tid + i;
         v[i] = b < nb ? sm.cnt[b] : 0u;
         s += (v[i] + (SEG_ALIGN - 1)) & ~(uint32_t)(SEG_ALIGN - 1);
         sv += v[i];
@@ -305,8 +351,8 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     for (int wdx = 0; wdx < (tid >> 5); wdx++) base += sm.warp_tot[wdx];
     uint32_t ex = base + inc - s;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int b = 4 * tid + i;
+    for (int i = 0; i < SCAN_PER; i++) {
+        const int b = SCAN_PER * tid + i;
         const uint32_t padded = (v[i] + (SEG_ALIGN - 1)) & ~(uint32_t)(SEG_ALIGN - 1);
         if (b < nb) {
             sm.off[b] = ex;
@@ -325,8 +371,9 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     const uint32_t cnt_base = sink.cnt_base;
     const uint32_t staged_base = (uint32_t)__cvta_generic_to_shared(sm.staged);
     const uint32_t* rp = sm.raw + tid;
+    const uint32_t n_local = (sink.raw_addr - raw0) / (COUNT_THREADS * 4u);
     uint32_t n = 0;
-    for (; n + 4 <= sink.n_local; n += 4) {
+    for (; n + 4 <= n_local; n += 4) {
         uint32_t idx[4], pos[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) idx[u] = rp[(n + u) * COUNT_THREADS];
@@ -337,7 +384,7 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
         for (int u = 0; u < 4; u++)
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(staged_base + pos[u] * 2u), "h"((uint16_t)(idx[u] & (PART_BINS - 1))) : "memory");
     }
-    for (; n < sink.n_local; n++) {
+    for (; n < n_local; n++) {
         const uint32_t idx = rp[n * COUNT_THREADS];
         uint32_t pos;
         asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cnt_base + (idx >> (2 * PART_LOW)) * 4u) : "memory");
@@ -372,6 +419,9 @@ struct BucketSmem {
     uint32_t lvl[PART_BINS / 4];       // 16 KB ping-pong buffer of the in-bucket cascade
     uint32_t seg[BUCKET_BATCH];        // (start | end << 16) of this bucket's segment in each tile
     unsigned long long tot[16];
+    uint32_t* lvl_counts[16];          // per level: this bucket's slice of the count row
+    float* lvl_freq[16];               //            ... of the frequency row (nullptr: not requested)
+    double lvl_inv[16];                //            1 / windows of that level
 };
 
 __device__ __forceinline__ void hist_add2(uint32_t hbase, uint32_t two) {
@@ -379,6 +429,9 @@ __device__ __forceinline__ void hist_add2(uint32_t hbase, uint32_t two) {
     if (lo != PAD_ENTRY) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + lo * 4u) : "memory");
     if (hi != PAD_ENTRY) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + hi * 4u) : "memory");
 }
+
+constexpr int GATHER_SEGS = 4;         // (tile, bucket) segments a thread keeps in flight
+constexpr int GATHER_VECS = 3;         // 8-byte vectors loaded up front per segment (12 entries)
 
 __global__ void __launch_bounds__(BUCKET_THREADS)
 bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const GenomeTiles* __restrict__ gts,
@@ -402,6 +455,25 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
         sm.tot[tid] = t;
         if (totals && b == 0) totals[(uint64_t)g * row.nk + tid] = t;
     }
+    __syncthreads();
+    if (tid >= 32 && tid < 48) {                                  // per-level pointers, once
+        const int level = tid - 32;
+        uint32_t* cp = nullptr;
+        float* fp = nullptr;
+        double inv = 0.0;
+        if (level >= k_stop && level <= k) {
+            const size_t n_level = (size_t)PART_BINS >> (2 * (k - level));
+            cp = lm.ptr(g, level) + (size_t)b * n_level;
+            const int ki = li.ki[level];
+            if (ki >= 0) {
+                if (freq) fp = freq + (uint64_t)g * freq_stride + row.off[ki] + (size_t)b * n_level;
+                inv = sm.tot[ki] ? 1.0 / (double)sm.tot[ki] : 0.0;
+            }
+        }
+        sm.lvl_counts[level] = cp;
+        sm.lvl_freq[level] = fp;
+        sm.lvl_inv[level] = inv;
+    }
     const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sm.hist);
     for (uint32_t t0 = 0; t0 < gt.n_tiles; t0 += BUCKET_BATCH) {
         const uint32_t nt = min((uint32_t)BUCKET_BATCH, gt.n_tiles - t0);
@@ -411,36 +483,55 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
             sm.seg[i] = (uint32_t)trow[0] | ((uint32_t)trow[1] << 16);
         }
         __syncthreads();
-        // one thread per (tile, bucket) segment: 8-byte vectors, first four loads in flight together
-        for (uint32_t i = tid; i < nt; i += BUCKET_THREADS) {
-            const uint32_t se = sm.seg[i];
-            const uint32_t v0 = se & 0xFFFFu, v1 = se >> 16;
-            const uint2* src = reinterpret_cast<const uint2*>(payload + (size_t)(gt.tile0 + t0 + i) * TILE_CAP);
-            uint2 x[4];
+        // a thread owns GATHER_SEGS (tile, bucket) segments per round; their first
+        // GATHER_VECS 8-byte vectors are all loaded before any is consumed
+        for (uint32_t i0 = tid; i0 < nt; i0 += BUCKET_THREADS * GATHER_SEGS) {
+            uint2 x[GATHER_SEGS][GATHER_VECS];
+            uint32_t v0[GATHER_SEGS], v1[GATHER_SEGS];
 #pragma unroll
-            for (int u = 0; u < 4; u++) x[u] = (v0 + u < v1) ? __ldg(src + v0 + u) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+            for (int sgi = 0; sgi < GATHER_SEGS; sgi++) {
+                const uint32_t i = i0 + sgi * BUCKET_THREADS;
+                const uint32_t se = i < nt ? sm.seg[i] : 0u;
+                v0[sgi] = se & 0xFFFFu;
+                v1[sgi] = se >> 16;
+                const uint2* src = reinterpret_cast<const uint2*>(payload + (size_t)(gt.tile0 + t0 + i) * TILE_CAP);
 #pragma unroll
-            for (int u = 0; u < 4; u++) { hist_add2(hbase, x[u].x); hist_add2(hbase, x[u].y); }
-            for (uint32_t q = v0 + 4; q < v1; q++) {
-                const uint2 xx = __ldg(src + q);
-                hist_add2(hbase, xx.x);
-                hist_add2(hbase, xx.y);
+                for (int u = 0; u < GATHER_VECS; u++)
+                    x[sgi][u] = (v0[sgi] + u < v1[sgi]) ? __ldg(src + v0[sgi] + u) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+            }
+#pragma unroll
+            for (int sgi = 0; sgi < GATHER_SEGS; sgi++) {
+#pragma unroll
+                for (int u = 0; u < GATHER_VECS; u++) { hist_add2(hbase, x[sgi][u].x); hist_add2(hbase, x[sgi][u].y); }
+                if (v0[sgi] + GATHER_VECS < v1[sgi]) {                // longer than 12 entries: the rest
+                    const uint32_t i = i0 + sgi * BUCKET_THREADS;
+                    const uint2* src = reinterpret_cast<const uint2*>(payload + (size_t)(gt.tile0 + t0 + i) * TILE_CAP);
+                    for (uint32_t q = v0[sgi] + GATHER_VECS; q < v1[sgi]; q++) {
+                        const uint2 xx = __ldg(src + q);
+                        hist_add2(hbase, xx.x);
+                        hist_add2(hbase, xx.y);
+                    }
+                }
             }
         }
     }
     __syncthreads();
     // level k: this bucket's 16384 bins, and level k-1 on the way
     {
-        const int ki = li.ki[k];
-        uint32_t* ck = lm.ptr(g, k) + (size_t)b * PART_BINS;
-        float* fk = (freq && ki >= 0) ? freq + (uint64_t)g * freq_stride + row.off[ki] + (size_t)b * PART_BINS : nullptr;
-        const double inv = (ki >= 0 && sm.tot[ki]) ? 1.0 / (double)sm.tot[ki] : 0.0;
+        uint32_t* ck = sm.lvl_counts[k];
+        float* fk = sm.lvl_freq[k];
+        const double inv = sm.lvl_inv[k];
         const bool down = k - 1 >= k_stop;
-        uint32_t* c1 = down ? lm.ptr(g, k - 1) + (size_t)b * (PART_BINS / 4) : nullptr;
-        const int ki1 = down ? li.ki[k - 1] : -1;
-        float* f1 = (freq && ki1 >= 0) ? freq + (uint64_t)g * freq_stride + row.off[ki1] + (size_t)b * (PART_BINS / 4) : nullptr;
-        const double inv1 = (ki1 >= 0 && sm.tot[ki1]) ? 1.0 / (double)sm.tot[ki1] : 0.0;
-        for (int i = tid; i < PART_BINS / 4; i += BUCKET_THREADS) {
+        uint32_t* c1 = down ? sm.lvl_counts[k - 1] : nullptr;
+        float* f1 = down ? sm.lvl_freq[k - 1] : nullptr;
+        const double inv1 = down ? sm.lvl_inv[k - 1] : 0.0;
+        constexpr int PER = PART_BINS / 4 / BUCKET_THREADS;          // 8 level-(k-1) bins per thread
+        uint32_t tails1[PER];
+#pragma unroll
+        for (int u = 0; u < PER; u++) tails1[u] = down ? c1[tid + u * BUCKET_THREADS] : 0u;   // run-end tails of level k-1
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const int i = tid + u * BUCKET_THREADS;
             const uint4 c = reinterpret_cast<const uint4*>(sm.hist)[i];
             reinterpret_cast<uint4*>(ck)[i] = c;
             if (fk) {
@@ -450,30 +541,51 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
                 reinterpret_cast<float4*>(fk)[i] = f;
             }
             if (down) {
-                const uint32_t v = c.x + c.y + c.z + c.w + c1[i];     // + run-end tails of level k-1
+                const uint32_t v = c.x + c.y + c.z + c.w + tails1[u];
                 c1[i] = v;
                 if (f1) f1[i] = (float)((double)v * inv1);
                 sm.lvl[i] = v;
             }
         }
     }
-    // deeper levels of the bucket's subtree, ping-pong between lvl[] and hist[]
+    // deeper levels of the bucket's subtree, ping-pong between lvl[] and hist[]; the first
+    // (1024 bins) by the whole CTA, the small rest by warp 0 alone
     uint32_t* cur = sm.lvl;
     uint32_t* nxt = sm.hist;
     int n_cur = PART_BINS / 4;
-    for (int level = k - 2; level >= k_stop; level--) {
+    int level = k - 2;
+    if (level >= k_stop) {
         __syncthreads();
         const int n_next = n_cur >> 2;
-        uint32_t* cl = lm.ptr(g, level) + (size_t)b * n_next;
-        const int kil = li.ki[level];
-        float* fl = (freq && kil >= 0) ? freq + (uint64_t)g * freq_stride + row.off[kil] + (size_t)b * n_next : nullptr;
-        const double invl = (kil >= 0 && sm.tot[kil]) ? 1.0 / (double)sm.tot[kil] : 0.0;
+        uint32_t* cl = sm.lvl_counts[level];
+        float* fl = sm.lvl_freq[level];
+        const double invl = sm.lvl_inv[level];
         for (int i = tid; i < n_next; i += BUCKET_THREADS) {
-            const uint32_t v = cur[4 * i] + cur[4 * i + 1] + cur[4 * i + 2] + cur[4 * i + 3] + cl[i];
+            const uint4 c = reinterpret_cast<const uint4*>(cur)[i];
+            const uint32_t v = c.x + c.y + c.z + c.w + cl[i];
             cl[i] = v;
             if (fl) fl[i] = (float)((double)v * invl);
             nxt[i] = v;
         }
+        uint32_t* t = cur; cur = nxt; nxt = t;
+        n_cur = n_next;
+        level--;
+    }
+    __syncthreads();
+    if (tid >= 32) return;
+    for (; level >= k_stop; level--) {
+        const int n_next = n_cur >> 2;
+        uint32_t* cl = sm.lvl_counts[level];
+        float* fl = sm.lvl_freq[level];
+        const double invl = sm.lvl_inv[level];
+        for (int i = tid; i < n_next; i += 32) {
+            const uint4 c = reinterpret_cast<const uint4*>(cur)[i];
+            const uint32_t v = c.x + c.y + c.z + c.w + cl[i];
+            cl[i] = v;
+            if (fl) fl[i] = (float)((double)v * invl);
+            nxt[i] = v;
+        }
+        __syncwarp();
         uint32_t* t = cur; cur = nxt; nxt = t;
         n_cur = n_next;
     }
@@ -648,6 +760,14 @@ static DenseParams make_params(int k, int min_rec, bool tails, int tail_lo) {
     P.tails = tails ? 1 : 0;
     P.tail_lo = tail_lo;
     return P;
+}
+
+int launch_slice_headers(const uint8_t* d_fasta, const GenomeDev* d_genomes, Slice* d_slices, int n_slices,
+                         cudaStream_t s) {
+    if (n_slices <= 0) return KMERML_OK;
+    slice_header_kernel<<<(n_slices + 127) / 128, 128, 0, s>>>(d_fasta, d_genomes, d_slices, n_slices);
+    KM_CUDA(cudaGetLastError());
+    return KMERML_OK;
 }
 
 int launch_count(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices, int n_slices,

@@ -13,11 +13,15 @@
 //   * a window is counted iff all k symbols are in ACGT (generate.py:55-56), never
 //     across records (:39), and only in records with len >= max(k_values) (:44-46).
 //
-// Design: every thread owns the windows that START in its 64-byte chunk and reads
-// up to k-1 symbols past the chunk end (the "overhang"), so no state is carried
-// between threads, warps, CTAs or GPUs.  Everything that needs context from
-// BEFORE the chunk (header lines, run ends, short records) is a rare event that
-// is resolved exactly by the byte walkers below, directly on global memory.
+// Design: every thread owns the windows whose LAST base lies in its 32-byte chunk.
+//   * clean chunk (only bases and at most one '\n') right after a clean chunk: the
+//     chunk is bit-compacted into one 64-bit register, the k-1 bases before it come
+//     from the neighbour thread's register, and every window is one funnel shift --
+//     no per-byte state machine at all (pack_clean / emit_clean);
+//   * anything else (header lines, N runs, IUPAC codes, '\r', blanks, the first
+//     chunk of a slice ...): generic byte walker whose start state is recovered by
+//     walking BACKWARDS over global memory (lookback), so no state is ever carried
+//     between threads, warps, CTAs or GPUs.
 #pragma once
 #include <stdint.h>
 
@@ -31,7 +35,7 @@
 
 namespace km {
 
-constexpr int CHUNK = 64;            // bytes owned by one thread per tile
+constexpr int CHUNK = 32;            // bytes owned by one thread per tile
 constexpr int MAX_DENSE_K = 15;
 
 // One genome = one FASTA file's bytes [lo, hi) inside a batch buffer.  `lo` has
@@ -165,9 +169,8 @@ struct DenseParams {
 
 struct WalkState {
     uint32_t kmer;
-    int run;          // valid bases since the last reset, counted from the chunk start
+    int run;          // valid bases right before the current position (capped lookback + own bases)
     int in_hdr;
-    int pend;         // the previous symbol is a base inside my chunk
     int rec_known;    // 0 unknown, 1 record is long enough, 2 record is too short
 };
 
@@ -207,13 +210,13 @@ KM_HD void on_base(const Genome& g, uint64_t pos, int code, WalkState& s, const 
     }
 }
 
-// One byte of the thread's own chunk (generic path).
+// One byte of the thread's own chunk (generic path).  run > 0 <=> the previous symbol
+// is a valid base, so a non-base symbol ends a run exactly when run > 0.
 template <class Sink, class Tails>
 KM_HD void step_own(const Genome& g, uint64_t pos, uint32_t c, WalkState& s, const DenseParams& P, Sink& sink,
                     const Tails& tails) {
     int code = base_code(c);
     if (code >= 0 && !s.in_hdr) {
-        s.pend = 1;
         on_base(g, pos, code, s, P, sink);
         return;
     }
@@ -223,49 +226,39 @@ KM_HD void step_own(const Genome& g, uint64_t pos, uint32_t c, WalkState& s, con
     }
     int kind = classify_nonbase(g, pos, c);
     if (kind == SYM_SKIP) return;
-    if (s.pend && P.tails) run_end_event(g, pos, P, tails);
-    s.pend = 0;
+    if (s.run > 0 && P.tails) run_end_event(g, pos, P, tails);
     s.run = 0;
     if (kind == SYM_HDR) { s.in_hdr = 1; s.rec_known = 0; }
 }
 
-// After the own chunk: finish the windows that started in it (at most k-1 more
-// symbols, `cnt` of which were already consumed) and detect a run end right at
-// the chunk boundary.  Generic byte-by-byte version starting at `pos`.
-template <class Sink, class Tails>
-KM_HD_NOINLINE void walk_overhang(const Genome& g, uint64_t pos, int cnt, WalkState& s, const DenseParams& P,
-                                  Sink& sink, const Tails& tails) {
-    if (s.run == 0 || s.in_hdr) return;
-    while (cnt < P.k - 1 || s.pend) {
-        if (pos >= g.hi) {
-            if (s.pend && P.tails) run_end_event(g, g.hi, P, tails);
-            return;
-        }
-        uint32_t c = g.b[pos];
-        int code = base_code(c);
-        if (code >= 0) {
-            s.pend = 0;                                  // my last base has a successor: not a run end
-            if (cnt >= P.k - 1) return;
-            cnt++;
-            on_base(g, pos, code, s, P, sink);
-            pos++;
-            continue;
-        }
-        int kind = classify_nonbase(g, pos, c);
-        if (kind == SYM_SKIP) { pos++; continue; }
-        if (s.pend && P.tails) run_end_event(g, pos, P, tails);
-        return;
+// Start state of a chunk that begins at cs (not inside a header line): the up to k-1
+// valid bases that immediately precede it (run is capped at k-1, which is all the
+// window test `run >= k` and the run-end test `run > 0` need).
+KM_HD_NOINLINE void lookback(const Genome& g, uint64_t cs, const DenseParams& P, WalkState& s) {
+    uint64_t q = cs;
+    uint32_t code = 0;
+    int cnt = 0;
+    while (cnt < P.k - 1) {
+        int kind = prev_symbol(g, q);
+        if (kind > 3) break;
+        code |= (uint32_t)kind << (2 * cnt);
+        cnt++;
     }
+    s.kmer = code;
+    s.run = cnt;
 }
 
-// Walk one chunk [cs, ce) whose bytes are read through `at(pos)` (generic path).
+// Generic walk of one chunk [cs, ce): the windows that END in it.  Bytes are read
+// through `at(pos)`.
 template <class Sink, class Tails, class ByteAt>
 KM_HD void walk_chunk(const Genome& g, uint64_t cs, uint64_t ce, bool starts_in_header,
                       const DenseParams& P, Sink& sink, const Tails& tails, ByteAt&& at) {
     WalkState s;
-    s.kmer = 0; s.run = 0; s.in_hdr = starts_in_header ? 1 : 0; s.pend = 0; s.rec_known = 0;
+    s.kmer = 0; s.run = 0; s.in_hdr = starts_in_header ? 1 : 0; s.rec_known = 0;
+    if (!starts_in_header && cs > g.lo) lookback(g, cs, P, s);
     for (uint64_t pos = cs; pos < ce; pos++) step_own(g, pos, at(pos), s, P, sink, tails);
-    walk_overhang(g, ce, 0, s, P, sink, tails);
+    // the genome ends with this chunk: a run that is still open ends here
+    if (ce == g.hi && s.run > 0 && !s.in_hdr && P.tails) run_end_event(g, g.hi, P, tails);
 }
 
 // 4-entry byte LUT: byte i of the result = byte (sel nibble i) of `lut` (PRMT on the GPU).
@@ -294,7 +287,7 @@ KM_HD void classify_word(uint32_t x, uint32_t& y, uint32_t& bad, uint32_t& weird
     weird = bad & not_nl;
 }
 
-// Classify the 16 words of a chunk; returns non-zero when the chunk holds a byte that
+// Classify the words of a chunk; returns non-zero when the chunk holds a byte that
 // is neither a base nor '\n' (N runs, IUPAC codes, '>', '\r', blanks ...).
 KM_HD uint32_t classify_chunk(const uint32_t* w, uint32_t* y, uint32_t* bad) {
     uint32_t weird = 0;
@@ -309,92 +302,80 @@ KM_HD uint32_t classify_chunk(const uint32_t* w, uint32_t* y, uint32_t* bad) {
     return weird;
 }
 
-// Branch-free walk of a classified chunk that (a) lies completely inside the genome,
-// (b) does not start inside a header line, (c) holds nothing but bases and '\n'
-// (classify_chunk returned 0), with (d) min_rec == k.  Everything else takes the
-// generic walk_chunk.
-template <class Sink, class Tails>
-KM_HD void walk_classified(const Genome& g, uint64_t cs, const uint32_t* y, const uint32_t* bad,
-                           const DenseParams& P, Sink& sink, const Tails& tails) {
-    uint32_t kmer = 0;
-    int run = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < CHUNK / 4; i++) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = 0; j < 4; j++) {
-            if (!(bad[i] & (0x80u << (8 * j)))) {              // every other byte here is '\n': no state change
-                kmer = (kmer << 2) | ((y[i] >> (8 * j)) & 3u);
-                run++;
-                if (run >= P.k) sink.count(kmer & P.mask, cs + (uint64_t)(4 * i + j));
-            }
-        }
-    }
-    if (run == 0) return;
-    // overhang: up to k-1 more bases finish the windows that started in this chunk
-    uint64_t pos = cs + CHUNK;
-    int cnt = 0;
-    if (pos + 16 <= g.hi) {
-        uint32_t oy[4], ob[4];
-        uint32_t ow = 0;
-#if defined(__CUDA_ARCH__)
-        const uint4 v = *reinterpret_cast<const uint4*>(g.b + pos);
-        const uint32_t o[4] = {v.x, v.y, v.z, v.w};
-#else
-        uint32_t o[4];
-        for (int i = 0; i < 4; i++)
-            o[i] = (uint32_t)g.b[pos + 4 * i] | ((uint32_t)g.b[pos + 4 * i + 1] << 8) |
-                   ((uint32_t)g.b[pos + 4 * i + 2] << 16) | ((uint32_t)g.b[pos + 4 * i + 3] << 24);
-#endif
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int i = 0; i < 4; i++) {
-            uint32_t wd;
-            classify_word(o[i], oy[i], ob[i], wd);
-            ow |= wd;
-        }
-        if (!ow) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int i = 0; i < 4; i++) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                for (int j = 0; j < 4; j++) {
-                    if (!(ob[i] & (0x80u << (8 * j))) && cnt < P.k - 1) {
-                        kmer = (kmer << 2) | ((oy[i] >> (8 * j)) & 3u);
-                        run++;
-                        cnt++;
-                        if (run >= P.k) sink.count(kmer & P.mask, pos + (uint64_t)(4 * i + j));
-                    }
-                }
-            }
-            if (cnt >= P.k - 1) return;
-            pos += 16;                                         // mostly line ends in there: keep going below
-        }
-    }
-    WalkState s;
-    s.kmer = kmer; s.run = run; s.in_hdr = 0; s.pend = cnt == 0 ? 1 : 0; s.rec_known = 0;
-    walk_overhang(g, pos, cnt, s, P, sink, tails);
-}
+// A clean chunk: its 31 or 32 bases as one top-aligned 64-bit string (base 0 in bits
+// 63:62 of hi:lo), the '\n' (if any) squeezed out.
+struct CleanChunk {
+    uint32_t hi, lo;      // top-aligned 2-bit codes
+    int n;                // 31 or 32 bases
+    int nl;               // byte index of the removed '\n', 32 if none
+    uint32_t last16;      // the last 16 bases, right-aligned: the carry of the next chunk
+};
 
-// classify + walk; false (nothing emitted) when the chunk needs the generic path.
-template <class Sink, class Tails>
-KM_HD bool walk_chunk_fast(const Genome& g, uint64_t cs, const uint32_t* w, const DenseParams& P, Sink& sink,
-                           const Tails& tails) {
-    uint32_t y[CHUNK / 4], bad[CHUNK / 4];
-    if (classify_chunk(w, y, bad)) return false;
-    walk_classified(g, cs, y, bad, P, sink, tails);
+// Compact a classified chunk (classify_chunk returned 0) -- false when it holds more
+// than one '\n' (lines shorter than 32 columns): the caller takes the generic path.
+KM_HD bool pack_clean(const uint32_t* y, const uint32_t* bad, CleanChunk& c) {
+    static_assert(CHUNK == 32, "pack_clean packs 32 bases into 64 bits");
+    uint32_t pk[8], m = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 8; i++) {
+        pk[i] = (y[i] * 0x40100401u) >> 24;                               // 4 codes -> 8 bits, first base on top
+        m |= ((((bad[i] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * i);   // bit b <=> byte b is the '\n'
+    }
+    uint64_t B = ((uint64_t)((pk[0] << 24) | (pk[1] << 16) | (pk[2] << 8) | pk[3]) << 32) |
+                 (uint64_t)((pk[4] << 24) | (pk[5] << 16) | (pk[6] << 8) | pk[7]);
+    if (m & (m - 1)) return false;                                        // two or more line feeds
+    if (m == 0) {
+        c.n = 32;
+        c.nl = 32;
+        c.last16 = (uint32_t)B;
+    } else {
+        int p = 0;
+#if defined(__CUDA_ARCH__)
+        p = __ffs((int)m) - 1;
+#else
+        while (!((m >> p) & 1u)) p++;
+#endif
+        const uint64_t upper = p ? (B >> (64 - 2 * p)) : 0ull;                            // bases 0 .. p-1
+        const uint64_t lower = p == 31 ? 0ull : (B & ((1ull << (62 - 2 * p)) - 1ull));     // bases p+1 .. 31
+        const uint64_t V = p == 31 ? upper : ((upper << (62 - 2 * p)) | lower);           // 31 bases, right-aligned
+        c.n = 31;
+        c.nl = p;
+        c.last16 = (uint32_t)V;
+        B = V << 2;
+    }
+    c.hi = (uint32_t)(B >> 32);
+    c.lo = (uint32_t)B;
     return true;
 }
 
-// Does any byte of the 16 words equal the byte replicated in `pattern`?
-KM_HD bool any_byte_eq16(const uint32_t* w, uint32_t pattern) {
+KM_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int s) {                 // bits [s, s+32) of hi:lo, 0 <= s < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, (unsigned)s);
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> s);
+#endif
+}
+
+// Every window that ends in a clean chunk whose predecessor chunk is clean too:
+// carry16 = the predecessor's last 16 bases (k <= 16).  Two integer ops per window.
+template <class Sink>
+KM_HD void emit_clean(const CleanChunk& c, uint32_t carry16, uint64_t cs, const DenseParams& P, Sink& sink) {
+    const uint32_t mask = P.mask;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 31; j++) {                                         // a clean chunk has >= 31 bases
+        const int sft = 62 - 2 * j;                                        // bit position of base j in hi:lo
+        const uint32_t w = sft >= 32 ? funnel_r(c.hi, carry16, sft - 32) : funnel_r(c.lo, c.hi, sft);
+        sink.count(w & mask, cs + (uint64_t)(j + (j >= c.nl ? 1 : 0)));
+    }
+    if (c.n == 32) sink.count(c.lo & mask, cs + 31);
+}
+
+// Does any byte of the chunk's words equal the byte replicated in `pattern`?
+KM_HD bool any_byte_eq_chunk(const uint32_t* w, uint32_t pattern) {
     uint32_t acc = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll

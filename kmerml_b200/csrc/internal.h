@@ -34,6 +34,7 @@ struct Slice {                // unit of work of one CTA: bytes [begin, end) of 
     uint32_t genome;
     uint32_t pad;
     uint64_t begin, end;      // multiples of the tile size (absolute buffer offsets)
+    uint64_t hdr_until;       // slice_header_kernel: `begin` lies in a header line that ends here (else 0)
 };
 
 // Where level j (the 4^j histogram) of genome g lives: inside the caller's counts
@@ -61,12 +62,14 @@ struct RowSpec {              // the caller's k_list, in row order
 };
 
 // ---- launchers (dense.cu) -----------------------------------------------------
-constexpr int COUNT_THREADS = 256;                 // threads per CTA of the counting kernels
-constexpr int TILE_BYTES = COUNT_THREADS * 64;     // bytes per tile (64-byte chunk per thread)
+constexpr int COUNT_THREADS = 512;                 // threads per CTA of the counting kernels
+constexpr int TILE_BYTES = COUNT_THREADS * 32;     // bytes per tile (32-byte chunk per thread)
 constexpr int SMEM_MAX_K = 7;                      // 4^7 * 4 B = 64 KB shared histogram
 
 int launch_prologue(const uint8_t* d_fasta, const uint64_t* d_offsets, GenomeDev* d_genomes,
                     GenomeStats* d_stats, int n_genomes, cudaStream_t s);
+int launch_slice_headers(const uint8_t* d_fasta, const GenomeDev* d_genomes, Slice* d_slices, int n_slices,
+                         cudaStream_t s);
 int launch_count(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices,
                  int n_slices, int k, int k_bottom, int min_rec, bool use_smem, const LevelMap& lm,
                  GenomeStats* d_stats, cudaStream_t s);

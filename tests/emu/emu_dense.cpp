@@ -70,36 +70,67 @@ int64_t emu_count_dense(const uint8_t* bytes, uint64_t n, uint64_t base_off, int
             uint64_t until;
             if (pos_in_header(g, sb, &until)) hdr_carry = until;
         }
-        std::vector<uint8_t> flags(threads_per_tile);
+        std::vector<uint8_t> flags(threads_per_tile), clean(threads_per_tile);
+        std::vector<CleanChunk> cc(threads_per_tile);
+        bool prev_tile_ok = false;                 // last chunk of the previous tile was a clean, in-sequence chunk
+        uint32_t prev_tile_last16 = 0;
         for (uint64_t tb = sb; tb < std::min(sb + slice_bytes, g.hi); tb += tile_bytes) {
             std::fill(flags.begin(), flags.end(), 0);
+            std::fill(clean.begin(), clean.end(), 0);
             uint64_t next_carry = hdr_carry;
             auto clip = [&](int t, uint64_t& cs, uint64_t& ce) {
                 cs = std::max<uint64_t>(tb + (uint64_t)t * CHUNK, g.lo);
                 ce = std::min<uint64_t>(tb + (uint64_t)(t + 1) * CHUNK, g.hi);
                 return cs < ce;
             };
-            for (int t = 0; t < threads_per_tile; t++) {            // phase 1
+            for (int t = 0; t < threads_per_tile; t++) {            // phase 1: classify, pack, find header lines
                 uint64_t cs, ce;
                 if (!clip(t, cs, ce)) continue;
-                find_headers(g, cs, ce, [&](uint64_t h, uint64_t until) {
+                auto on_header = [&](uint64_t h, uint64_t until) {
                     (void)h;
                     for (int j = t + 1; j < threads_per_tile && tb + (uint64_t)j * CHUNK < until; j++) flags[j] = 1;
                     next_carry = std::max(next_carry, until);
-                });
+                };
+                if (ce - cs == CHUNK) {
+                    uint32_t w[CHUNK / 4], y[CHUNK / 4], bad[CHUNK / 4];
+                    memcpy(w, g.b + cs, CHUNK);
+                    const bool weird = classify_chunk(w, y, bad) != 0;
+                    clean[t] = !weird && pack_clean(y, bad, cc[t]);
+                    if (weird && any_byte_eq_chunk(w, 0x3E3E3E3Eu)) find_headers(g, cs, ce, on_header);
+                } else {
+                    find_headers(g, cs, ce, on_header);
+                }
             }
-            for (int t = 0; t < threads_per_tile; t++) {            // phase 2
+            bool last_ok = false;
+            uint32_t last_l16 = 0;
+            for (int t = 0; t < threads_per_tile; t++) {            // phase 2: walk
                 uint64_t cs, ce;
-                if (!clip(t, cs, ce)) continue;
-                bool in_hdr = flags[t] || cs < hdr_carry;
-                bool full = (ce - cs == CHUNK) && (cs % 4 == 0);
-                uint32_t w[CHUNK / 4];
-                if (full) memcpy(w, g.b + cs, CHUNK);
-                // the fast path is what nearly every GPU thread takes; it declines (before
-                // emitting anything) chunks that hold more than bases and line feeds
-                if (!(full && !in_hdr && P.min_rec == P.k && walk_chunk_fast(g, cs, w, P, sink, sink)))
-                    walk_chunk(g, cs, ce, in_hdr, P, sink, sink, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
+                const bool has = clip(t, cs, ce);
+                const bool in_hdr = flags[t] || cs < hdr_carry;
+                bool prev_ok;
+                uint32_t carry;
+                if (t > 0) {
+                    prev_ok = clean[t - 1] && !flags[t - 1] && !(tb + (uint64_t)(t - 1) * CHUNK < hdr_carry);
+                    carry = cc[t - 1].last16;
+                } else {
+                    prev_ok = prev_tile_ok;
+                    carry = prev_tile_last16;
+                }
+                if (has) {
+                    if (clean[t] && !in_hdr && prev_ok && P.min_rec == P.k) {
+                        emit_clean(cc[t], carry, cs, P, sink);       // the path nearly every GPU thread takes
+                        if (ce == g.hi && P.tails) run_end_event(g, g.hi, P, sink);
+                    } else {
+                        walk_chunk(g, cs, ce, in_hdr, P, sink, sink, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
+                    }
+                }
+                if (t == threads_per_tile - 1) {
+                    last_ok = has && clean[t] && !in_hdr;
+                    last_l16 = cc[t].last16;
+                }
             }
+            prev_tile_ok = last_ok;
+            prev_tile_last16 = last_l16;
             hdr_carry = next_carry;
         }
     }
