@@ -286,6 +286,8 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
             uint64_t b0 = h_offsets[g] / sb, b1 = (h_offsets[g + 1] - 1) / sb;
             for (uint64_t b = b0; b <= b1; b++) {
                 h_slices[si].genome = (uint32_t)g;
+                h_slices[si].prev_ok = 0;
+                h_slices[si].prev16 = 0;
                 h_slices[si].pad = 0;
                 h_slices[si].begin = b * sb;
                 h_slices[si].end = (b + 1) * sb;
@@ -605,6 +607,8 @@ int kmerml_first_occurrence(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nb
     Slice* h_slices = (Slice*)(hs + off_bytes);
     for (uint64_t b = 0; b < n_slices; b++) {
         h_slices[b].genome = 0;
+        h_slices[b].prev_ok = 0;
+        h_slices[b].prev16 = 0;
         h_slices[b].pad = 0;
         h_slices[b].begin = b * sb;
         h_slices[b].end = (b + 1) * sb;

@@ -96,8 +96,8 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
     if (tid == 0) {
         tc.carry[0] = sl.hdr_until;                         // resolved per slice by slice_header_kernel
         tc.carry[1] = sl.hdr_until;
-        tc.prev_tile[0] = 0;                                // the chunk before the slice is someone else's
-        tc.prev_tile[1] = 0;
+        tc.prev_tile[0] = sl.prev_ok;                       // the chunk before the slice (another CTA's)
+        tc.prev_tile[1] = sl.prev16;
     }
     const uint64_t end = sl.end < g.hi ? sl.end : g.hi;
     for (uint64_t tb = sl.begin; tb < end; tb += TILE_BYTES) {
@@ -198,6 +198,26 @@ __global__ void slice_header_kernel(const uint8_t* __restrict__ buf, const Genom
     uint64_t until = 0;
     if (!(sl.begin > g.lo && pos_in_header(g, sl.begin, &until))) until = 0;
     slices[i].hdr_until = until;
+    // the chunk right before the slice: pack it once so that the slice's first chunk can take
+    // the clean path like every other chunk (it must be sequence, not header text)
+    uint32_t ok = 0, l16 = 0;
+    if (sl.begin >= g.lo + CHUNK && sl.begin < g.hi) {
+        uint32_t w[CHUNK / 4], y[CHUNK / 4], bad[CHUNK / 4];
+        const uint4* src = reinterpret_cast<const uint4*>(buf + sl.begin - CHUNK);
+#pragma unroll
+        for (int j = 0; j < CHUNK / 16; j++) {
+            uint4 v = __ldg(src + j);
+            w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+        }
+        CleanChunk pc;
+        uint64_t dummy;
+        if (classify_chunk(w, y, bad) == 0 && pack_clean(y, bad, pc) && !pos_in_header(g, sl.begin - CHUNK, &dummy)) {
+            ok = 1;
+            l16 = pc.last16;
+        }
+    }
+    slices[i].prev_ok = ok;
+    slices[i].prev16 = l16;
 }
 
 // MODE 0: global histogram, 1: shared histogram, 2: first occurrence

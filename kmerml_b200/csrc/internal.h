@@ -32,9 +32,11 @@ struct GenomeStats {          // per genome, zeroed by the prologue kernel
 
 struct Slice {                // unit of work of one CTA: bytes [begin, end) of one genome
     uint32_t genome;
-    uint32_t pad;
+    uint32_t prev_ok;         // slice_header_kernel: the 32-byte chunk before `begin` is a clean sequence chunk
     uint64_t begin, end;      // multiples of the tile size (absolute buffer offsets)
     uint64_t hdr_until;       // slice_header_kernel: `begin` lies in a header line that ends here (else 0)
+    uint32_t prev16;          // ... and these are its last 16 bases (the carry of the slice's first chunk)
+    uint32_t pad;
 };
 
 // Where level j (the 4^j histogram) of genome g lives: inside the caller's counts

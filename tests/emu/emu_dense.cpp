@@ -72,8 +72,20 @@ int64_t emu_count_dense(const uint8_t* bytes, uint64_t n, uint64_t base_off, int
         }
         std::vector<uint8_t> flags(threads_per_tile), clean(threads_per_tile);
         std::vector<CleanChunk> cc(threads_per_tile);
-        bool prev_tile_ok = false;                 // last chunk of the previous tile was a clean, in-sequence chunk
+        // last chunk before the current tile: clean and in sequence?  For the slice's first tile
+        // the chunk belongs to another CTA and is packed once more by thread 0.
+        bool prev_tile_ok = false;
         uint32_t prev_tile_last16 = 0;
+        if (sb >= g.lo + CHUNK && sb < g.hi) {
+            uint32_t w[CHUNK / 4], y[CHUNK / 4], bad[CHUNK / 4];
+            memcpy(w, g.b + sb - CHUNK, CHUNK);
+            CleanChunk pc;
+            uint64_t dummy;
+            if (classify_chunk(w, y, bad) == 0 && pack_clean(y, bad, pc) && !pos_in_header(g, sb - CHUNK, &dummy)) {
+                prev_tile_ok = true;
+                prev_tile_last16 = pc.last16;
+            }
+        }
         for (uint64_t tb = sb; tb < std::min(sb + slice_bytes, g.hi); tb += tile_bytes) {
             std::fill(flags.begin(), flags.end(), 0);
             std::fill(clean.begin(), clean.end(), 0);

@@ -63,3 +63,15 @@ def test_emulator_fuzz(emu):
         mr = kmax if rng.random() < 0.75 else kmax + rng.randint(1, 12)
         check(emu, data, kmax, mr, rng.choice([1, 2, 3, 4, 8, 16]), rng.choice([1, 2, 3, 100]),
               rng.choice([0, 0, 3, 31, 64, 77]))
+
+
+def test_header_text_that_looks_like_sequence(emu):
+    """A header line made of ACGT letters whose line feed closes the 32-byte chunk right before a
+    tile / slice start must not leak into the next record's first windows."""
+    for tpt in (1, 2, 4):
+        for base_off in (0, 32, 64):
+            for hdrlen in range(20, 110, 3):
+                hdr = (">" + "ACGT" * 40)[:hdrlen]
+                data = (">r0\n" + "ACGTTGCA" * 12 + "\n" + hdr + "\n" + "GATTACAGATTACAGGATCC" * 8 + "\n").encode()
+                for k in (3, 12):
+                    check(emu, data, k, k, tpt, 1, base_off)
