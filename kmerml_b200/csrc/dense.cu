@@ -308,19 +308,26 @@ struct PartSink {
     }
 };
 
+struct PartWalkSmem {                           // only live during the walk ...
+    uint32_t last16[COUNT_THREADS];
+    uint8_t flags[COUNT_THREADS];
+    uint8_t clean[COUNT_THREADS];
+};
+
 struct PartSmem {
     uint32_t raw[TILE_WINDOWS];                 // 64 KB: the tile's windows, thread-interleaved
-    uint16_t staged[TILE_CAP];                  // 38 KB: payloads sorted by bucket, segments padded
+    union {
+        uint16_t staged[TILE_CAP];              // 38 KB: payloads sorted by bucket, segments padded
+        PartWalkSmem walk;                      // ... so it shares the staging buffer's space
+    };
     uint32_t cnt[PART_MAX_BUCKETS];             // per-bucket count, then scatter cursor
     uint32_t off[PART_MAX_BUCKETS + 4];         // exclusive (padded) offsets
     uint32_t warp_tot[COUNT_THREADS / 32];
     uint32_t warp_cnt[COUNT_THREADS / 32];
-    uint32_t last16[COUNT_THREADS];
     unsigned long long carry[2];
     uint32_t prev_tile[2];
-    uint8_t flags[COUNT_THREADS];
-    uint8_t clean[COUNT_THREADS];
 };
+static_assert(sizeof(PartSmem) <= 113 * 1024, "two partition CTAs must fit in one SM's shared memory");
 
 __global__ void __launch_bounds__(COUNT_THREADS, 2)
 partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
@@ -336,7 +343,7 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     g.lo = gd.lo;
     g.hi = gd.hi;
     TileCtx tc;
-    tc.flags = sm.flags; tc.clean = sm.clean; tc.last16 = sm.last16;
+    tc.flags = sm.walk.flags; tc.clean = sm.walk.clean; tc.last16 = sm.walk.last16;
     tc.carry = sm.carry; tc.prev_tile = sm.prev_tile;
     for (int i = tid; i < nb; i += COUNT_THREADS) sm.cnt[i] = 0;
 
@@ -432,17 +439,19 @@ struct LevelInfo {                     // per level: index into the caller's k_l
 };
 
 constexpr int BUCKET_THREADS = 512;
-constexpr int BUCKET_BATCH = 4096;     // tile segments staged per round
+constexpr int BUCKET_BATCH = 2048;     // tile segments staged per round
+constexpr int SMALL_LEVEL_BINS = 341;  // 256 + 64 + 16 + 4 + 1: levels k-3 .. k-7 of one bucket
 
 struct BucketSmem {
-    uint32_t hist[PART_BINS];          // 64 KB
-    uint32_t lvl[PART_BINS / 4];       // 16 KB ping-pong buffer of the in-bucket cascade
+    uint32_t hist[PART_BINS];          // 64 KB; reused in place by the in-bucket cascade
     uint32_t seg[BUCKET_BATCH];        // (start | end << 16) of this bucket's segment in each tile
+    uint32_t small_tails[SMALL_LEVEL_BINS + 3];   // run-end tails of the small levels, prefetched
     unsigned long long tot[16];
     uint32_t* lvl_counts[16];          // per level: this bucket's slice of the count row
     float* lvl_freq[16];               //            ... of the frequency row (nullptr: not requested)
     double lvl_inv[16];                //            1 / windows of that level
 };
+static_assert(sizeof(BucketSmem) <= 74 * 1024, "three bucket CTAs must fit in one SM's shared memory");
 
 __device__ __forceinline__ void hist_add2(uint32_t hbase, uint32_t two) {
     const uint32_t lo = two & 0xFFFFu, hi = two >> 16;
@@ -450,10 +459,10 @@ __device__ __forceinline__ void hist_add2(uint32_t hbase, uint32_t two) {
     if (hi != PAD_ENTRY) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + hi * 4u) : "memory");
 }
 
-constexpr int GATHER_SEGS = 4;         // (tile, bucket) segments a thread keeps in flight
+constexpr int GATHER_SEGS = 2;         // (tile, bucket) segments a thread keeps in flight
 constexpr int GATHER_VECS = 3;         // 8-byte vectors loaded up front per segment (12 entries)
 
-__global__ void __launch_bounds__(BUCKET_THREADS)
+__global__ void __launch_bounds__(BUCKET_THREADS, 3)
 bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const GenomeTiles* __restrict__ gts,
               const uint16_t* __restrict__ payload, const uint16_t* __restrict__ table, int nb,
               const GenomeStats* __restrict__ stats, float* freq, uint64_t freq_stride, uint64_t* totals,
@@ -493,6 +502,24 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
         sm.lvl_counts[level] = cp;
         sm.lvl_freq[level] = fp;
         sm.lvl_inv[level] = inv;
+    }
+    // run-end tails of every lower level of this bucket's subtree: issue the loads now, they
+    // arrive while the histogram is being gathered
+    constexpr int PER1 = PART_BINS / 4 / BUCKET_THREADS;          // 8 level-(k-1) bins per thread
+    constexpr int PER2 = PART_BINS / 16 / BUCKET_THREADS;         // 2 level-(k-2) bins per thread
+    uint32_t tails1[PER1], tails2[PER2];
+    {
+        const uint32_t* c1 = (k - 1 >= k_stop) ? lm.ptr(g, k - 1) + (size_t)b * (PART_BINS / 4) : nullptr;
+        const uint32_t* c2 = (k - 2 >= k_stop) ? lm.ptr(g, k - 2) + (size_t)b * (PART_BINS / 16) : nullptr;
+#pragma unroll
+        for (int u = 0; u < PER1; u++) tails1[u] = c1 ? c1[tid + u * BUCKET_THREADS] : 0u;
+#pragma unroll
+        for (int u = 0; u < PER2; u++) tails2[u] = c2 ? c2[tid + u * BUCKET_THREADS] : 0u;
+        if (tid < SMALL_LEVEL_BINS) {                             // levels k-3 (256 bins) .. k-7 (1 bin)
+            int level = k - 3, base = 0, n = 256;
+            while (tid >= base + n) { base += n; n >>= 2; level--; }
+            sm.small_tails[tid] = level >= k_stop ? lm.ptr(g, level)[(size_t)b * n + (tid - base)] : 0u;
+        }
     }
     const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sm.hist);
     for (uint32_t t0 = 0; t0 < gt.n_tiles; t0 += BUCKET_BATCH) {
@@ -536,7 +563,8 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
         }
     }
     __syncthreads();
-    // level k: this bucket's 16384 bins, and level k-1 on the way
+    // level k: this bucket's 16384 bins, and level k-1 on the way (kept in registers)
+    uint32_t v1r[PER1];
     {
         uint32_t* ck = sm.lvl_counts[k];
         float* fk = sm.lvl_freq[k];
@@ -545,12 +573,8 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
         uint32_t* c1 = down ? sm.lvl_counts[k - 1] : nullptr;
         float* f1 = down ? sm.lvl_freq[k - 1] : nullptr;
         const double inv1 = down ? sm.lvl_inv[k - 1] : 0.0;
-        constexpr int PER = PART_BINS / 4 / BUCKET_THREADS;          // 8 level-(k-1) bins per thread
-        uint32_t tails1[PER];
 #pragma unroll
-        for (int u = 0; u < PER; u++) tails1[u] = down ? c1[tid + u * BUCKET_THREADS] : 0u;   // run-end tails of level k-1
-#pragma unroll
-        for (int u = 0; u < PER; u++) {
+        for (int u = 0; u < PER1; u++) {
             const int i = tid + u * BUCKET_THREADS;
             const uint4 c = reinterpret_cast<const uint4*>(sm.hist)[i];
             reinterpret_cast<uint4*>(ck)[i] = c;
@@ -560,53 +584,53 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
                 f.z = (float)((double)c.z * inv); f.w = (float)((double)c.w * inv);
                 reinterpret_cast<float4*>(fk)[i] = f;
             }
+            v1r[u] = c.x + c.y + c.z + c.w + tails1[u];               // + run-end tails of level k-1
             if (down) {
-                const uint32_t v = c.x + c.y + c.z + c.w + tails1[u];
-                c1[i] = v;
-                if (f1) f1[i] = (float)((double)v * inv1);
-                sm.lvl[i] = v;
+                c1[i] = v1r[u];
+                if (f1) f1[i] = (float)((double)v1r[u] * inv1);
             }
         }
     }
-    // deeper levels of the bucket's subtree, ping-pong between lvl[] and hist[]; the first
-    // (1024 bins) by the whole CTA, the small rest by warp 0 alone
-    uint32_t* cur = sm.lvl;
-    uint32_t* nxt = sm.hist;
-    int n_cur = PART_BINS / 4;
-    int level = k - 2;
-    if (level >= k_stop) {
-        __syncthreads();
-        const int n_next = n_cur >> 2;
-        uint32_t* cl = sm.lvl_counts[level];
-        float* fl = sm.lvl_freq[level];
-        const double invl = sm.lvl_inv[level];
-        for (int i = tid; i < n_next; i += BUCKET_THREADS) {
-            const uint4 c = reinterpret_cast<const uint4*>(cur)[i];
-            const uint32_t v = c.x + c.y + c.z + c.w + cl[i];
+    if (k - 2 < k_stop) return;
+    __syncthreads();                                                  // everybody is done reading hist[]
+#pragma unroll
+    for (int u = 0; u < PER1; u++) sm.hist[tid + u * BUCKET_THREADS] = v1r[u];   // level k-1, in place
+    __syncthreads();
+    {   // level k-2: 1024 bins, whole CTA; results to hist[4096 ..)
+        uint32_t* cl = sm.lvl_counts[k - 2];
+        float* fl = sm.lvl_freq[k - 2];
+        const double invl = sm.lvl_inv[k - 2];
+#pragma unroll
+        for (int u = 0; u < PER2; u++) {
+            const int i = tid + u * BUCKET_THREADS;
+            const uint4 c = reinterpret_cast<const uint4*>(sm.hist)[i];
+            const uint32_t v = c.x + c.y + c.z + c.w + tails2[u];
             cl[i] = v;
             if (fl) fl[i] = (float)((double)v * invl);
-            nxt[i] = v;
+            sm.hist[4096 + i] = v;
         }
-        uint32_t* t = cur; cur = nxt; nxt = t;
-        n_cur = n_next;
-        level--;
     }
     __syncthreads();
     if (tid >= 32) return;
-    for (; level >= k_stop; level--) {
+    // the small rest (256, 64, 16, 4, 1 bins) by warp 0, ping-pong inside hist[]
+    uint32_t* cur = sm.hist + 4096;
+    uint32_t* nxt = sm.hist + 8192;
+    int n_cur = 1024, tbase = 0;
+    for (int level = k - 3; level >= k_stop; level--) {
         const int n_next = n_cur >> 2;
         uint32_t* cl = sm.lvl_counts[level];
         float* fl = sm.lvl_freq[level];
         const double invl = sm.lvl_inv[level];
         for (int i = tid; i < n_next; i += 32) {
             const uint4 c = reinterpret_cast<const uint4*>(cur)[i];
-            const uint32_t v = c.x + c.y + c.z + c.w + cl[i];
+            const uint32_t v = c.x + c.y + c.z + c.w + sm.small_tails[tbase + i];
             cl[i] = v;
             if (fl) fl[i] = (float)((double)v * invl);
             nxt[i] = v;
         }
         __syncwarp();
         uint32_t* t = cur; cur = nxt; nxt = t;
+        tbase += n_next;
         n_cur = n_next;
     }
 }
