@@ -99,6 +99,49 @@ int kmerml_first_occurrence(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nb
                             int min_record_len, uint32_t *d_first, void *stream);
 
 /*
+ * Record table of one FASTA file resident in HBM: byte offsets of the header lines
+ * (unordered; sort them) -- what Bio.SeqIO.parse would yield one record for
+ * (kmerml/kmers/generate.py:39).  *h_count receives the number found (may exceed cap;
+ * then call again with a larger buffer).  Synchronous.
+ */
+int kmerml_find_records(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbytes, uint64_t *d_offsets,
+                        uint32_t cap, uint32_t *h_count, void *stream);
+/*
+ * For n records given by the (sorted or not) header offsets: is_short[i] = 1 when the
+ * record holds fewer than min_record_len symbols -- the records generate.py:44-46 skips
+ * with "Skipping <id>: too short for k-mer extraction".
+ */
+int kmerml_records_short(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbytes, const uint64_t *d_offsets,
+                         uint32_t n, int min_record_len, uint8_t *d_is_short, void *stream);
+
+/*
+ * Static per-k-mer features (functions of the k-mer string only): replaces the per-row
+ * helpers of kmerml/kmers/statistics.py:190-240.  d_out: int32[4^k][8] =
+ * {n, A_count, C_count, G_count, T_count, cpg_count, has_repeat, first base}, row index =
+ * lexicographic ACGT k-mer index.  compat != 0 computes them on the string the reference's
+ * CSV actually holds (leading 'A's lost to pandas' integer parsing, statistics.py:261-271).
+ * The float columns (gc_percent, cpg_obs_exp, entropies) are pure functions of these
+ * integers and are derived by the host with the reference's own float expressions.
+ */
+int kmerml_static_features(kmerml_ctx *ctx, int k, int compat, int32_t *d_out, void *stream);
+
+/* out[g][i] = counts[g][i] / totals[g] (float32): frequency normalisation of count rows. */
+int kmerml_normalize_rows(kmerml_ctx *ctx, const uint32_t *d_counts, uint64_t counts_stride,
+                          const uint64_t *d_totals, int n_rows, uint64_t m, float *d_out,
+                          uint64_t out_stride, void *stream);
+
+/*
+ * Genome x genome distance matrix of the rows of X (n x m): metric 0 = cosine,
+ * 1 = Euclidean.  dtype 0 = float32, 1 = uint32 (count rows: the Gram matrix is then
+ * exact), 2 = float64.  Accumulation is float64 (the north star's 1e-6 relative
+ * tolerance).  d_out32 / d_out64: n x n, either may be NULL.
+ */
+#define KMERML_METRIC_COSINE 0
+#define KMERML_METRIC_EUCLIDEAN 1
+int kmerml_pairwise_distance(kmerml_ctx *ctx, const void *d_x, int dtype, uint64_t stride, int n,
+                             uint64_t m, int metric, float *d_out32, double *d_out64, void *stream);
+
+/*
  * Measurement hooks (bench.py): with profiling enabled every kernel the library
  * launches is bracketed by CUDA events on the launching stream.  kmerml_profile_read
  * synchronises those events and returns the accumulated device time per kernel family

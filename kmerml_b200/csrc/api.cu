@@ -77,13 +77,14 @@ struct Workspace {
     DevBuf tables;      // offsets | GenomeDev | GenomeStats | Slice[]
     DevBuf scratch;     // pass-through cascade levels
     DevBuf part;        // partition path: bucket-sorted payloads + per-tile offset tables
+    DevBuf misc;        // record scan counter, Gram matrix
     PinBuf staging;     // host image of offsets + slices
     cudaEvent_t staging_free = nullptr;
     // host-path slot buffers
     DevBuf fasta, counts, freq, totals;
     cudaStream_t stream = nullptr;
     void release() {
-        tables.release(); scratch.release(); part.release(); staging.release();
+        tables.release(); scratch.release(); part.release(); misc.release(); staging.release();
         fasta.release(); counts.release(); freq.release(); totals.release();
         if (staging_free) cudaEventDestroy(staging_free);
         if (stream) cudaStreamDestroy(stream);
@@ -572,6 +573,61 @@ int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, cons
     }
     for (int i = 0; i < n_slots; i++) KM_CUDA(cudaStreamSynchronize(ctx->ws[i].stream));
     return KMERML_OK;
+}
+
+int kmerml_find_records(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, uint64_t* d_offsets, uint32_t cap,
+                        uint32_t* h_count, void* stream) {
+    if (!ctx || !h_count || (cap && !d_offsets)) return fail(KMERML_ERR_ARG, "null pointer argument");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t s = (cudaStream_t)stream;
+    Workspace& ws = ctx->ws[0];
+    int rc = ws.misc.ensure(256);
+    if (rc) return rc;
+    uint32_t* d_count = (uint32_t*)ws.misc.p;
+    rc = launch_scan_records(d_fasta, nbytes, 0, (unsigned long long*)d_offsets, nullptr, cap, d_count, s);
+    if (rc) return rc;
+    KM_CUDA(cudaMemcpyAsync(h_count, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    KM_CUDA(cudaStreamSynchronize(s));
+    return KMERML_OK;
+}
+
+int kmerml_records_short(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, const uint64_t* d_offsets,
+                         uint32_t n, int min_record_len, uint8_t* d_is_short, void* stream) {
+    if (!ctx || (n && (!d_offsets || !d_is_short))) return fail(KMERML_ERR_ARG, "null pointer argument");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    return launch_record_short(d_fasta, nbytes, (const unsigned long long*)d_offsets, n, min_record_len, d_is_short,
+                               (cudaStream_t)stream);
+}
+
+int kmerml_static_features(kmerml_ctx* ctx, int k, int compat, int32_t* d_out, void* stream) {
+    if (!ctx || !d_out) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (k < 1 || k > KMERML_MAX_DENSE_K) return fail(KMERML_ERR_ARG, "k out of range");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    return launch_static_features(k, compat, d_out, (cudaStream_t)stream);
+}
+
+int kmerml_normalize_rows(kmerml_ctx* ctx, const uint32_t* d_counts, uint64_t counts_stride, const uint64_t* d_totals,
+                          int n_rows, uint64_t m, float* d_out, uint64_t out_stride, void* stream) {
+    if (!ctx || !d_counts || !d_totals || !d_out) return fail(KMERML_ERR_ARG, "null pointer argument");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    return launch_normalize_rows(d_counts, counts_stride, d_totals, n_rows, m, d_out, out_stride, (cudaStream_t)stream);
+}
+
+int kmerml_pairwise_distance(kmerml_ctx* ctx, const void* d_x, int dtype, uint64_t stride, int n, uint64_t m,
+                             int metric, float* d_out32, double* d_out64, void* stream) {
+    if (!ctx || !d_x || (!d_out32 && !d_out64)) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (dtype < 0 || dtype > 2 || metric < 0 || metric > 1 || n < 0) return fail(KMERML_ERR_ARG, "bad dtype / metric");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    Workspace& ws = ctx->ws[0];
+    int rc = ws.misc.ensure(256 + (size_t)n * n * sizeof(double));
+    if (rc) return rc;
+    return launch_pairwise(d_x, dtype, stride, n, m, metric, (double*)((uint8_t*)ws.misc.p + 256), d_out32, d_out64,
+                           (cudaStream_t)stream);
 }
 
 int kmerml_first_occurrence(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, int k, int min_record_len,

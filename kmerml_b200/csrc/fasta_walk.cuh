@@ -27,7 +27,7 @@
 
 #if defined(__CUDACC__)
 #define KM_HD __host__ __device__ __forceinline__
-#define KM_HD_NOINLINE __host__ __device__ __noinline__
+#define KM_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define KM_HD inline
 #define KM_HD_NOINLINE inline

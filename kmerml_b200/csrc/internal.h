@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
 
 #include "../../include/kmerml_b200.h"
@@ -96,5 +97,16 @@ int launch_finalize_low(const LevelMap& lm, const RowSpec& row, int k_top, int l
 int launch_first_occurrence(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices,
                             int n_slices, int k, int min_rec, uint32_t* d_first, cudaStream_t s);
 int dense_setup_attributes();
+
+// ---- launchers (features.cu) --------------------------------------------------
+int launch_scan_records(const uint8_t* d_fasta, uint64_t nbytes, int need, unsigned long long* d_offsets,
+                        uint8_t* d_short, uint32_t cap, uint32_t* d_count, cudaStream_t s);
+int launch_record_short(const uint8_t* d_fasta, uint64_t nbytes, const unsigned long long* d_offsets, uint32_t n,
+                        int need, uint8_t* d_short, cudaStream_t s);
+int launch_static_features(int k, int compat, int32_t* d_out, cudaStream_t s);
+int launch_normalize_rows(const uint32_t* d_counts, uint64_t counts_stride, const uint64_t* d_totals, int n_rows,
+                          uint64_t m, float* d_out, uint64_t out_stride, cudaStream_t s);
+int launch_pairwise(const void* d_x, int dtype, uint64_t stride, int n, uint64_t m, int metric, double* d_gram,
+                    float* d_out32, double* d_out64, cudaStream_t s);
 
 }  // namespace km

@@ -143,3 +143,59 @@ def first_occurrence_device(fasta, k, *, min_record_len=None):
     _lib.check(L.kmerml_first_occurrence(ctx.handle, fasta.data_ptr(), fasta.numel(), int(k),
                                          int(min_record_len or 0), out.data_ptr(), ctypes.c_void_p(stream)))
     return out
+
+
+def revcomp_codes(k):
+    """numpy int64[4^k]: index of the reverse complement of every k-mer (A0 C1 G2 T3)."""
+    idx = np.arange(4 ** k, dtype=np.int64)
+    rc = np.zeros_like(idx)
+    t = idx.copy()
+    for _ in range(k):
+        rc = (rc << 2) | (3 - (t & 3))
+        t >>= 2
+    return rc
+
+
+def static_features_device(k, *, compat=False, device=None):
+    """int32 [4^k, 8] CUDA tensor: n, A/C/G/T counts, cpg_count, has_repeat, first base."""
+    dev = _device_index(device)
+    ctx = _lib.context(dev)
+    out = torch.empty((4 ** k, 8), dtype=torch.int32, device=torch.device("cuda", dev))
+    stream = torch.cuda.current_stream(out.device).cuda_stream
+    _lib.check(_lib.load().kmerml_static_features(ctx.handle, int(k), 1 if compat else 0, out.data_ptr(),
+                                                  ctypes.c_void_p(stream)))
+    return out
+
+
+def normalize_rows_device(counts, totals):
+    """float32 frequencies of uint32 count rows (int32 storage) given int64 row totals."""
+    ctx = _lib.context(counts.device.index)
+    out = torch.empty(counts.shape, dtype=torch.float32, device=counts.device)
+    stream = torch.cuda.current_stream(counts.device).cuda_stream
+    totals = totals.to(torch.int64).contiguous()
+    _lib.check(_lib.load().kmerml_normalize_rows(ctx.handle, counts.data_ptr(), counts.stride(0), totals.data_ptr(),
+                                                 counts.shape[0], counts.shape[1], out.data_ptr(), out.stride(0),
+                                                 ctypes.c_void_p(stream)))
+    return out
+
+
+_DTYPE_CODE = {torch.float32: 0, torch.int32: 1, torch.float64: 2}
+_METRIC_CODE = {"cosine": 0, "euclidean": 1}
+
+
+def pairwise_distance_device(x, metric="cosine", *, out_dtype=torch.float32):
+    """n x n distance matrix of the rows of the CUDA tensor x (float32, float64, or int32
+    holding uint32 counts); float64 accumulation."""
+    if metric not in _METRIC_CODE:
+        raise ValueError(f"metric must be one of {sorted(_METRIC_CODE)}")
+    if x.dtype not in _DTYPE_CODE or not x.is_cuda or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be a 2-D CUDA tensor (float32 / float64 / int32) with contiguous rows")
+    ctx = _lib.context(x.device.index)
+    n, m = x.shape
+    out = torch.empty((n, n), dtype=out_dtype, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    o32 = out.data_ptr() if out_dtype == torch.float32 else None
+    o64 = out.data_ptr() if out_dtype == torch.float64 else None
+    _lib.check(_lib.load().kmerml_pairwise_distance(ctx.handle, x.data_ptr(), _DTYPE_CODE[x.dtype], x.stride(0), n, m,
+                                                    _METRIC_CODE[metric], o32, o64, ctypes.c_void_p(stream)))
+    return out

@@ -1,0 +1,245 @@
+"""KmerFeatureExtractor -- drop-in for the reference's kmerml/kmers/statistics.py:9-273.
+
+Reads k{k}.txt[.gz] files, computes the per-k-mer feature columns and writes one
+<organism>_kmer_features.csv per organism, with the reference's column order and its
+"bug-for-bug" behaviours: the digit column is parsed by pandas as an integer
+(statistics.py:261-271), so leading zeros (leading 'A's) are lost before decoding
+(:158,:248-251) and every feature is computed on that shortened string.
+
+The reference spends ~70 us per k-mer in df.iterrows(); here every column is computed
+for all rows at once.  (The features are functions of the k-mer string only; the same
+integers per k-mer index are also available on the GPU as
+engine.static_features_device / kmerml_static_features for in-memory pipelines.)
+"""
+import json
+import math
+import re
+from collections import defaultdict
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+
+ALL_FEATURES = ["base_counts", "gc_content", "cpg_sites", "entropy", "repeats", "presence"]
+_LETTER = np.frombuffer(b"ATCGNNNNNN", dtype=np.uint8)       # digit -> letter (statistics.py:250)
+_K_IN_NAME = re.compile(r"k(\d+)")
+
+
+class _GenomeSizes:
+    """The slice of GenomeMetadataManager the feature extractor uses
+    (kmerml/utils/genome_metadata.py:11-28,87-91): a JSON map organism -> {"total_size"}."""
+
+    def __init__(self, metadata_file):
+        self.path = Path(metadata_file)
+        self.path.parent.mkdir(parents=True, exist_ok=True)
+        self.metadata = {}
+        if self.path.exists():
+            try:
+                with open(self.path) as fh:
+                    self.metadata = json.load(fh)
+            except json.JSONDecodeError:
+                self.metadata = {}
+
+    def get_genome_size(self, genome_id):
+        entry = self.metadata.get(genome_id)
+        return entry["total_size"] if entry is not None else None
+
+
+def _entropy_of(counts, n):
+    """-sum p log2 p over the letters present (statistics.py:220-226), Python floats."""
+    h = 0
+    for c in counts:
+        if c > 0:
+            p = c / n
+            h -= p * math.log2(p)
+    return h
+
+
+def features_from_digits(values, wanted):
+    """Feature columns for an int64 array of digit-encoded k-mers (leading zeros already
+    lost, exactly what the reference's DataFrame holds).  Returns an ordered dict of
+    column name -> numpy array, starting with the decoded 'kmer' strings."""
+    v = np.asarray(values, dtype=np.int64)
+    rows = v.size
+    if rows and v.min() < 0:
+        raise ValueError("negative k-mer codes")
+    nd = np.ones(rows, dtype=np.int64)
+    t = v // 10
+    while t.any():
+        nd += t > 0
+        t //= 10
+    width = int(nd.max()) if rows else 1
+    # digit matrix, most significant first, right-aligned rows padded with 255 on the left
+    digits = np.full((rows, width), 255, dtype=np.uint8)
+    t = v.copy()
+    for col in range(width - 1, -1, -1):
+        live = (width - 1 - col) < nd
+        digits[live, col] = (t[live] % 10).astype(np.uint8)
+        t //= 10
+    letters = np.where(digits == 255, 0, _LETTER[np.minimum(digits, 9)]).astype(np.uint8)
+    kmer = np.empty(rows, dtype=object)
+    for n in np.unique(nd):
+        sel = nd == n
+        block = np.ascontiguousarray(letters[sel][:, width - n:])
+        kmer[sel] = block.view(f"S{int(n)}").ravel().astype(f"U{int(n)}")
+    cols = {"kmer": kmer}
+    n_a = (digits == 0).sum(1)
+    n_t = (digits == 1).sum(1)
+    n_c = (digits == 2).sum(1)
+    n_g = (digits == 3).sum(1)
+    n_n = ((digits >= 4) & (digits != 255)).sum(1)
+    nf = nd.astype(np.float64)
+    if "gc_content" in wanted:
+        cols["gc_percent"] = ((n_g + n_c) / nf) * 100
+    if "base_counts" in wanted:
+        cols["A_count"], cols["C_count"], cols["G_count"], cols["T_count"] = n_a, n_c, n_g, n_t
+    if "presence" in wanted:
+        for name, cnt in (("A", n_a), ("C", n_c), ("G", n_g), ("T", n_t)):
+            cols[f"{name}_present"] = (cnt > 0).astype(np.int64)
+    if "cpg_sites" in wanted:
+        cpg = ((digits[:, :-1] == 2) & (digits[:, 1:] == 3)).sum(1) if width > 1 else np.zeros(rows, np.int64)
+        cols["cpg_count"] = cpg
+        prod = (n_c / nf) * (n_g / nf)
+        expected = np.where(prod > 0, prod * (nd - 1), 0.001)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cols["cpg_obs_exp"] = np.where(expected > 0, cpg / np.where(expected > 0, expected, 1.0), 0.0)
+    if "entropy" in wanted:
+        key = np.stack([nd, n_a, n_c, n_g, n_t, n_n], axis=1)
+        uniq, inverse = np.unique(key, axis=0, return_inverse=True)
+        table = np.array([_entropy_of(row[1:], int(row[0])) for row in uniq.tolist()], dtype=np.float64)
+        ent = table[inverse.ravel()]
+        cols["shannon_entropy"] = ent
+        cols["normalized_entropy"] = ent / 2.0
+    if "repeats" in wanted:
+        rep = np.zeros(rows, dtype=bool)
+        sym = np.where(digits == 255, 250, np.minimum(digits, 4))       # every non-ACGT digit decodes to 'N'
+        for i in range(width - 3):
+            both = (digits[:, i] != 255)
+            rep |= both & (sym[:, i] == sym[:, i + 2]) & (sym[:, i + 1] == sym[:, i + 3])
+        cols["has_repeat"] = rep.astype(np.int64)
+    return cols
+
+
+def _features_from_strings(kmers, wanted):
+    """Slow path for files that already hold letter strings (not produced by KmerExtractor)."""
+    out = defaultdict(list)
+    for s in kmers:
+        s = str(s)
+        n = len(s)
+        out["kmer"].append(s)
+        if "gc_content" in wanted:
+            out["gc_percent"].append(((s.count("G") + s.count("C")) / n) * 100 if n > 0 else 0)
+        if "base_counts" in wanted:
+            for b in "ACGT":
+                out[f"{b}_count"].append(s.count(b))
+        if "presence" in wanted:
+            for b in "ACGT":
+                out[f"{b}_present"].append(1 if b in s else 0)
+        if "cpg_sites" in wanted:
+            cpg = sum(1 for i in range(n - 1) if s[i:i + 2] == "CG")
+            out["cpg_count"].append(cpg)
+            prod = (s.count("C") / n) * (s.count("G") / n) if n > 0 else 0
+            expected = prod * (n - 1) if prod > 0 else 0.001
+            out["cpg_obs_exp"].append(cpg / expected if expected > 0 else 0)
+        if "entropy" in wanted:
+            h = _entropy_of([s.count(b) for b in sorted(set(s))], n)
+            out["shannon_entropy"].append(h)
+            out["normalized_entropy"].append(h / 2.0)
+        if "repeats" in wanted:
+            out["has_repeat"].append(1 if any(s[i:i + 2] == s[i + 2:i + 4] for i in range(n - 3)) else 0)
+    return {k: np.asarray(v, dtype=object if k == "kmer" else None) for k, v in out.items()}
+
+
+class KmerFeatureExtractor:
+    """Extract machine-learning features from k-mer count files."""
+
+    def __init__(self, input_paths=None, output_dir=None, metadata_file=None):
+        self.input_paths = [Path(p) for p in input_paths] if input_paths else []
+        self.output_dir = Path(output_dir) if output_dir else Path("kmer_features")
+        self.output_dir.mkdir(exist_ok=True, parents=True)
+        self.metadata = None
+        if metadata_file:
+            self.metadata_manager = _GenomeSizes(metadata_file)
+
+    def add_paths(self, paths):
+        self.input_paths.extend(Path(p) for p in paths)
+
+    def extract_features(self, required_features=None):
+        """Write one CSV per organism; returns {organism: csv path or None}."""
+        wanted = list(ALL_FEATURES) if required_features is None else required_features
+        return {organism: self._process_organism_kmers(organism, files, wanted)
+                for organism, files in self._group_files_by_organism().items()}
+
+    def _group_files_by_organism(self):
+        groups = defaultdict(list)
+        for path in self.input_paths:
+            if path.is_file():
+                groups[path.parent.name].append(path)
+            elif path.is_dir():
+                for sub in path.iterdir():
+                    if sub.is_dir():
+                        groups[sub.name].extend(sub.glob("k*.txt*"))
+        return groups
+
+    def _process_organism_kmers(self, organism, kmer_files, required_features):
+        genome_size = None
+        if hasattr(self, "metadata_manager"):
+            genome_size = self.metadata_manager.get_genome_size(organism)
+        frames = []
+        for kmer_file in kmer_files:
+            k_val = self._extract_k_from_filename(kmer_file.name)
+            if k_val is None:
+                print(f"Warning: Could not extract k value from {kmer_file}")
+                continue
+            table = self._load_kmer_file(kmer_file)
+            if len(table):
+                frames.append(self._extract_kmer_features(table, k_val, organism, required_features))
+        if not frames:
+            print(f"No features extracted for {organism}")
+            return None
+        result = pd.concat(frames, ignore_index=True) if len(frames) > 1 else frames[0]
+        if genome_size:
+            result["genome_size"] = genome_size
+        output_file = self.output_dir / f"{organism}_kmer_features.csv"
+        result.to_csv(output_file, index=False)
+        print(f"Created feature CSV for {organism}: {output_file}")
+        return output_file
+
+    def _extract_kmer_features(self, df, k_val, organism, required_features):
+        """DataFrame of the feature columns for one k-mer file (all rows at once)."""
+        col = df["kmer"]
+        if pd.api.types.is_integer_dtype(col.dtype):
+            cols = features_from_digits(col.to_numpy(), required_features)
+        else:
+            decoded = [self._decode_kmer(x) if str(x).isdigit() else x for x in col.tolist()]
+            cols = _features_from_strings(decoded, required_features)
+        ordered = {"kmer": cols.pop("kmer"), "count": df["count"].to_numpy(), "k": np.full(len(df), k_val)}
+        ordered.update(cols)
+        return pd.DataFrame(ordered)
+
+    @staticmethod
+    def _extract_k_from_filename(filename):
+        m = _K_IN_NAME.search(filename)
+        return int(m.group(1)) if m else None
+
+    @staticmethod
+    def _decode_kmer(encoded_kmer):
+        table = {"0": "A", "1": "T", "2": "C", "3": "G"}
+        return "".join(table.get(ch, "N") for ch in str(encoded_kmer))
+
+    @staticmethod
+    def _load_kmer_file(filepath):
+        """TSV -> DataFrame(kmer, count), read the way the reference reads it: the digit column
+        is left to pandas' type inference, which is what drops the leading zeros."""
+        compression = "gzip" if str(filepath).endswith(".gz") else None
+        names = ["kmer", "count"]
+        try:
+            df = pd.read_csv(filepath, sep="\t", compression=compression)
+            if "kmer" not in df.columns and "count" not in df.columns:
+                df = pd.read_csv(filepath, sep="\t", header=None, names=names, compression=compression)
+        except Exception:
+            try:
+                df = pd.read_csv(filepath, sep="\t", header=None, names=names, compression=compression)
+            except pd.errors.EmptyDataError:
+                df = pd.DataFrame({"kmer": pd.Series(dtype="int64"), "count": pd.Series(dtype="int64")})
+        return df

@@ -70,8 +70,8 @@ def test_header_text_that_looks_like_sequence(emu):
     tile / slice start must not leak into the next record's first windows."""
     for tpt in (1, 2, 4):
         for base_off in (0, 32, 64):
-            for hdrlen in range(20, 110, 3):
+            for hdrlen in range(20, 110, 9):
                 hdr = (">" + "ACGT" * 40)[:hdrlen]
                 data = (">r0\n" + "ACGTTGCA" * 12 + "\n" + hdr + "\n" + "GATTACAGATTACAGGATCC" * 8 + "\n").encode()
-                for k in (3, 12):
+                for k in (12,):
                     check(emu, data, k, k, tpt, 1, base_off)

@@ -1,0 +1,131 @@
+"""GPU drop-in surface: KmerExtractor writes the reference's files byte for byte, the CLI
+behaves like scripts/extract_kmers.py, and the feature / distance kernels match float64
+restatements within 1e-6 relative."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import golden_extract_cases
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6
+
+
+def test_extractor_files_and_messages_match_reference(tmp_path):
+    from kmerml_b200.kmers.generate import KmerExtractor
+    n = 0
+    for c in golden_extract_cases():
+        if max(c["k_values"]) > 14:
+            continue
+        fa = tmp_path / c["name"] / "GCF_900000001_1.fa"
+        fa.parent.mkdir()
+        fa.write_bytes(c["fasta"])
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            org = KmerExtractor(output_dir=tmp_path / c["name"] / "out", compress=False).extract_kmers_from_fasta(
+                fa, list(c["k_values"]))
+        assert org == c["organism_id"]
+        assert buf.getvalue().splitlines() == c["stdout"], c["name"]
+        for k, text in c["files"].items():
+            got = (tmp_path / c["name"] / "out" / org / f"k{k}.txt").read_bytes()
+            assert got == text.encode(), (c["name"], k)
+        n += 1
+    assert n >= 40
+
+
+def test_extractor_gzip_and_genome_list(tmp_path, capsys):
+    import gzip
+    from kmerml_b200.kmers.generate import KmerExtractor
+    cases = [c for c in golden_extract_cases() if c["name"] in ("G0", "rand03")]
+    paths = []
+    for c in cases:
+        p = tmp_path / f"{c['name']}.fa"
+        p.write_bytes(c["fasta"])
+        paths.append(p)
+    ex = KmerExtractor(output_dir=tmp_path / "o")            # compress=True is the reference default
+    done = ex.extract_from_genome_list(paths + [tmp_path / "missing.fa"], [2, 8])
+    out = capsys.readouterr().out
+    assert done == ["G0", "rand03"]
+    assert "Error processing missing" in out and "Completed processing 2 out of 3 genomes" in out
+    g0 = cases[0]
+    assert gzip.open(tmp_path / "o" / "G0" / "k8.txt.gz", "rt").read() == g0["files"]["8"]
+    with pytest.raises(ValueError):
+        ex.extract_from_genome_list(paths, [2], organism_ids=["only_one"])
+
+
+def test_extract_cli(tmp_path, capsys):
+    from kmerml_b200.scripts import extract_kmers
+    c = next(c for c in golden_extract_cases() if c["name"] == "G0")
+    (tmp_path / "raw").mkdir()
+    (tmp_path / "raw" / "GCF_900000001_1.fa").write_bytes(c["fasta"])
+    assert extract_kmers.main(["-i", str(tmp_path / "raw"), "-o", str(tmp_path / "k"), "-k", "a,b"]) == 1
+    assert extract_kmers.main(["-i", str(tmp_path / "raw"), "-o", str(tmp_path / "k"), "-p", "*.nothing"]) == 1
+    capsys.readouterr()
+    assert extract_kmers.main(["-i", str(tmp_path / "raw"), "-o", str(tmp_path / "k"), "-k", "2,8"]) == 0
+    out = capsys.readouterr().out
+    assert "Found 1 genome files" in out and "Processing GCF_900000001_1 (1/1)" in out
+    assert "K-mer extraction completed successfully" in out
+    assert (tmp_path / "k" / "GCF_900000001_1" / "k2.txt").read_text() == c["files"]["2"]
+
+
+def test_static_features_match_statistics_py():
+    from kmerml_b200 import engine
+    for k, compat in ((1, False), (4, False), (6, True), (8, True)):
+        t = engine.static_features_device(k, compat=compat).cpu().numpy()
+        rng = np.random.default_rng(k)
+        for idx in list(range(min(4 ** k, 70))) + rng.integers(0, 4 ** k, 200).tolist():
+            s = oracle.compat_kmer_string(idx, k) if compat else oracle.code_to_kmer(idx, k)
+            f = oracle.kmer_features(s)
+            want = [len(s), f["A_count"], f["C_count"], f["G_count"], f["T_count"], f["cpg_count"], f["has_repeat"],
+                    "ACGT".index(s[0])]
+            assert t[idx].tolist() == want, (k, compat, idx, s)
+
+
+def test_normalize_and_distances():
+    import torch
+    from kmerml_b200 import engine, synth
+    genomes = [synth.config3_genome(i, scale=0.02).tobytes() for i in range(12)]
+    buf, offs = synth.pack([np.frombuffer(g, np.uint8) for g in genomes])
+    res = engine.count_dense_device(torch.from_numpy(buf).cuda(), offs, [6, 8])
+    counts = res.counts[:, 4 ** 6:].contiguous()
+    ref_counts = np.stack([oracle.count_dense(g, 8) for g in genomes]).astype(np.float64)
+    freq = engine.normalize_rows_device(counts, res.totals[:, 1]).cpu().numpy().astype(np.float64)
+    want = ref_counts / ref_counts.sum(1, keepdims=True)
+    assert np.all(np.abs(freq - want) <= RTOL * np.maximum(want, 1e-300))
+    for metric in ("cosine", "euclidean"):
+        ref = oracle.pairwise_distance(want, metric)
+        for x in (counts if metric == "cosine" else None, torch.as_tensor(want, device="cuda"),
+                  torch.as_tensor(want.astype(np.float32), device="cuda")):
+            if x is None:
+                continue
+            d = engine.pairwise_distance_device(x, metric, out_dtype=torch.float64).cpu().numpy()
+            tol = RTOL if x.dtype != torch.float32 else 2e-5      # float32 INPUT rounding, not accumulation
+            off = ~np.eye(len(genomes), dtype=bool)
+            assert np.all(np.abs(d - ref)[off] <= tol * np.abs(ref)[off]), (metric, x.dtype)
+            assert np.all(np.diag(d) == 0)
+
+
+def test_builder_from_counts_and_distance_matrix():
+    import torch
+    from kmerml_b200 import engine, synth
+    from kmerml_b200.ml.features import KmerFeatureBuilder
+    genomes = [synth.config3_genome(i, scale=0.004).tobytes() for i in range(5)]
+    buf, offs = synth.pack([np.frombuffer(g, np.uint8) for g in genomes])
+    res = engine.count_dense_device(torch.from_numpy(buf).cuda(), offs, [5])
+    orgs = [f"GCF_90000000{i}_1" for i in range(5)]
+    b = KmerFeatureBuilder()
+    m = b.from_counts(res, orgs, 5)
+    ref = np.stack([oracle.count_dense(g, 5) for g in genomes]).astype(np.int64)
+    keep = ref.any(axis=0)
+    assert list(m.columns) == [oracle.code_to_kmer(i, 5) for i in np.nonzero(keep)[0]]
+    assert list(m.columns) == sorted(m.columns) and np.array_equal(m.to_numpy(), ref[:, keep])
+    f = ref[:, keep] / ref[:, keep].sum(1, keepdims=True)
+    np.testing.assert_allclose(b.normalize().to_numpy(), f, rtol=RTOL)
+    for metric in ("cosine", "euclidean"):
+        d = b.distance_matrix(metric).to_numpy()
+        want = oracle.pairwise_distance(f, metric)
+        off = ~np.eye(5, dtype=bool)
+        assert np.all(np.abs(d - want)[off] <= RTOL * np.abs(want)[off])

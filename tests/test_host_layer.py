@@ -1,0 +1,133 @@
+"""Host-side drop-in layer (statistics CSVs, feature matrix, path utils, CLI argument
+handling) against the fixtures produced by the unmodified reference.  No GPU."""
+import contextlib
+import io
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from helpers import GOLDEN, golden_extract_cases
+
+from kmerml_b200.kmers.statistics import KmerFeatureExtractor, features_from_digits
+from kmerml_b200.ml.features import KmerFeatureBuilder
+from kmerml_b200.scripts import generate_kmers_features
+from kmerml_b200.utils.path_utils import ensure_directory_exists, find_files, is_valid_file
+
+EXTRACT = {c["name"]: c for c in golden_extract_cases()}
+with open(os.path.join(GOLDEN, "stats_cases.json")) as fh:
+    STATS = json.load(fh)
+with open(os.path.join(GOLDEN, "matrix_cases.json")) as fh:
+    MATRICES = json.load(fh)
+
+
+def write_kmer_files(root, organism, case):
+    kdir = root / "kmers" / organism
+    kdir.mkdir(parents=True)
+    paths = []
+    for k, text in case["files"].items():
+        p = kdir / f"k{k}.txt"
+        p.write_text(text)
+        paths.append(p)
+    return paths
+
+
+@pytest.mark.parametrize("case", STATS, ids=[f"{c['name']}-{len(c['feature_set'] or [])}" for c in STATS])
+def test_statistics_csv_matches_reference(case, tmp_path):
+    paths = write_kmer_files(tmp_path, "GCF_900000001_1", EXTRACT[case["name"]])
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        res = KmerFeatureExtractor(input_paths=paths, output_dir=tmp_path / "f").extract_features(case["feature_set"])
+    path = res["GCF_900000001_1"]
+    if case["csv"] is None:
+        assert path is None and "No features extracted" in out.getvalue()
+        return
+    got = path.read_text()
+    if got == case["csv"]:
+        return                                              # byte-identical (the usual case)
+    # the reference sums the entropy terms in set-iteration (hash) order: last-ulp differences only
+    a, b = pd.read_csv(io.StringIO(got)), pd.read_csv(io.StringIO(case["csv"]))
+    assert list(a.columns) == list(b.columns) and a.shape == b.shape
+    for col in a.columns:
+        if a[col].dtype.kind == "f":
+            np.testing.assert_allclose(a[col].to_numpy(), b[col].to_numpy(), rtol=1e-12, atol=0)
+        else:
+            assert a[col].equals(b[col]), col
+
+
+@pytest.mark.parametrize("case", MATRICES, ids=[f"{'+'.join(c['cases'])}-{c['metric']}" for c in MATRICES])
+def test_feature_matrix_matches_reference(case, tmp_path):
+    fdir = tmp_path / "features"
+    for gi, name in enumerate(case["cases"]):
+        org = f"GCF_90000000{gi}_1"
+        paths = write_kmer_files(tmp_path / org, org, EXTRACT[name])
+        with contextlib.redirect_stdout(io.StringIO()):
+            KmerFeatureExtractor(input_paths=paths, output_dir=fdir).extract_features()
+    b = KmerFeatureBuilder(fdir)
+    m = b.build_from_statistics_files(metric=case["metric"])
+    assert [str(x) for x in m.index] == case["index"]
+    assert [str(x) for x in m.columns] == case["columns"]
+    np.testing.assert_allclose(m.to_numpy(dtype=np.float64), np.asarray(case["values"]), rtol=1e-12, atol=0)
+    assert b.organisms == case["index"] and [str(x) for x in b.kmers] == case["columns"]
+    if case["metric"] == "count":
+        assert m.dtypes.map(lambda d: d.kind).eq("i").all()
+        freq = b.normalize("frequency")
+        np.testing.assert_allclose(freq.sum(axis=1).to_numpy(), 1.0, rtol=1e-12)
+
+
+def test_leading_zero_quirk():
+    """02310231 (ACGTACGT) is read as the integer 2310231 and decodes to CGTACGT; 00 -> "A"."""
+    cols = features_from_digits(np.array([2310231, 0, 12]), ["gc_content", "base_counts"])
+    assert list(cols["kmer"]) == ["CGTACGT", "A", "TC"]
+    assert list(cols["A_count"]) == [1, 1, 0] and list(cols["C_count"]) == [2, 0, 1]
+
+
+def test_builder_errors(tmp_path):
+    with pytest.raises(ValueError, match="Statistics directory not set"):
+        KmerFeatureBuilder().build_from_statistics_files()
+    with pytest.raises(ValueError, match="No statistics files found"):
+        KmerFeatureBuilder(tmp_path).build_from_statistics_files()
+    assert KmerFeatureBuilder._extract_organism_id(tmp_path / "GCF_000146045_2_kmer_features.csv") == "GCF_000146045"
+
+
+def test_path_utils(tmp_path):
+    d = ensure_directory_exists(tmp_path / "a" / "b")
+    (d / "x.fa").write_text(">x\nAC\n")
+    (tmp_path / "a" / "y.fasta").write_text(">y\nAC\n")
+    assert [p.name for p in find_files(tmp_path / "a", ["*.fa", "*.fasta"])] == ["y.fasta"]
+    assert [p.name for p in find_files(tmp_path / "a", ["*.fa", "*.fasta"], recursive=True)] == ["x.fa", "y.fasta"]
+    assert is_valid_file(d / "x.fa") and not is_valid_file(d)
+
+
+def test_features_cli(tmp_path, capsys):
+    assert generate_kmers_features.main(["-i", str(tmp_path), "-o", str(tmp_path / "o"), "-m", str(tmp_path / "m.json")]) == 1
+    assert "No k-mer files found" in capsys.readouterr().out
+    write_kmer_files(tmp_path, "GCF_1_1", EXTRACT["G0"])
+    assert generate_kmers_features.main(["-i", str(tmp_path / "kmers"), "-o", str(tmp_path / "o"), "-k", "x"]) == 1
+    assert generate_kmers_features.main(["-i", str(tmp_path / "kmers"), "-o", str(tmp_path / "o"), "-f", "nope",
+                                         "-m", str(tmp_path / "m.json")]) == 1
+    rc = generate_kmers_features.main(["-i", str(tmp_path / "kmers"), "-o", str(tmp_path / "o"), "-f", "basic",
+                                       "-k", "2,8", "-m", str(tmp_path / "m.json")])
+    out = capsys.readouterr().out
+    assert rc == 0 and "Found 2 k-mer files" in out and "Generated 1 feature files" in out
+    cols = list(pd.read_csv(tmp_path / "o" / "GCF_1_1_kmer_features.csv").columns)
+    assert cols == ["kmer", "count", "k", "gc_percent", "A_count", "C_count", "G_count", "T_count"]
+
+
+def test_install_as_kmerml():
+    import sys
+    import kmerml_b200
+    saved = {k: v for k, v in sys.modules.items() if k == "kmerml" or k.startswith("kmerml.") or k == "scripts" or k.startswith("scripts.")}
+    try:
+        kmerml_b200.install_as_kmerml()
+        from kmerml.kmers.generate import KmerExtractor                    # noqa: F401
+        from kmerml.kmers.statistics import KmerFeatureExtractor as K2
+        from kmerml.ml.features import KmerFeatureBuilder as B2
+        from kmerml.utils.path_utils import find_files as f2
+        from scripts import extract_kmers                                  # noqa: F401
+        assert K2 is KmerFeatureExtractor and B2 is KmerFeatureBuilder and f2 is find_files
+    finally:
+        for k in [k for k in sys.modules if k == "kmerml" or k.startswith("kmerml.") or k == "scripts" or k.startswith("scripts.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
