@@ -189,7 +189,8 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     if (rc) return rc;
     if (n_genomes < 0) return fail(KMERML_ERR_ARG, "n_genomes < 0");
     if (n_genomes == 0) return KMERML_OK;
-    if (!d_fasta || !h_offsets || !d_counts) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (!h_offsets || !d_counts) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (!d_fasta && h_offsets[n_genomes] > h_offsets[0]) return fail(KMERML_ERR_ARG, "d_fasta is null");
     if (((uintptr_t)d_fasta & 15) || ((uintptr_t)d_counts & 15) || (d_freq && ((uintptr_t)d_freq & 15)))
         return fail(KMERML_ERR_ARG, "device pointers must be 16-byte aligned");
     if (counts_stride < row.off[nk] || (counts_stride & 3))
