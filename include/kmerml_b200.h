@@ -78,6 +78,20 @@ int kmerml_count_dense_batch(kmerml_ctx *ctx, const uint8_t *d_fasta, const uint
                              void *stream);
 
 /*
+ * One genome, only the windows whose LAST base lies in bytes [range_begin, range_end) of the
+ * file: the unit of intra-genome parallelism.  Ranges that tile the file give partial count
+ * rows (all requested k, cascade included) and partial window totals whose SUM over the ranges
+ * is exactly the whole-genome result -- across GPUs that sum is one NCCL all-reduce of
+ * uint32[row_len].  The k-1 bases before range_begin are read from the file itself,
+ * so no overlap bookkeeping is needed.  range_begin must be a multiple of 16384; no frequencies
+ * are written (normalise after the reduction with kmerml_normalize_rows).
+ */
+int kmerml_count_dense_range(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbytes,
+                             uint64_t range_begin, uint64_t range_end, const int *k_list, int nk,
+                             int min_record_len, unsigned flags, uint32_t *d_counts,
+                             uint64_t *d_totals, void *stream);
+
+/*
  * The same path end to end from HOST buffers: per genome H2D copy -> counting ->
  * D2H of counts (+ frequencies, totals), pipelined over three device slots.
  * h_counts / h_freq / h_totals are laid out like their d_ counterparts.  This is

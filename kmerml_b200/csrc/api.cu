@@ -182,7 +182,7 @@ static int build_row(const int* k_list, int nk, RowSpec* row, int* kmax, int* km
 static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fasta, const uint64_t* h_offsets,
                             int n_genomes, const int* k_list, int nk, int min_record_len, unsigned flags,
                             uint32_t* d_counts, uint64_t counts_stride, float* d_freq, uint64_t freq_stride,
-                            uint64_t* d_totals, cudaStream_t s) {
+                            uint64_t* d_totals, cudaStream_t s, uint64_t range_begin = 0, uint64_t range_end = 0) {
     RowSpec row;
     int kmax, kmin;
     int rc = build_row(k_list, nk, &row, &kmax, &kmin);
@@ -252,8 +252,10 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         }
         slice_bytes[g] = sb;
         first_slice[g] = (uint32_t)n_slices;
-        if (bytes) {
-            uint64_t b0 = h_offsets[g] / sb, b1 = (h_offsets[g + 1] - 1) / sb;
+        uint64_t lo = h_offsets[g], hi = h_offsets[g + 1];
+        if (range_end) { lo = std::max(lo, range_begin); hi = std::min(hi, range_end); }
+        if (lo < hi) {
+            uint64_t b0 = lo / sb, b1 = (hi - 1) / sb;
             n_slices += b1 - b0 + 1;
         }
         if (n_slices > 0x7fffffffull) return fail(KMERML_ERR_RANGE, "too many slices");
@@ -283,16 +285,19 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     {
         uint64_t si = 0;
         for (int g = 0; g < n_genomes; g++) {
-            if (h_offsets[g + 1] == h_offsets[g]) continue;
+            uint64_t lo = h_offsets[g], hi = h_offsets[g + 1];
+            if (range_end) { lo = std::max(lo, range_begin); hi = std::min(hi, range_end); }
+            if (lo >= hi) continue;
             uint64_t sb = slice_bytes[g];
-            uint64_t b0 = h_offsets[g] / sb, b1 = (h_offsets[g + 1] - 1) / sb;
+            uint64_t b0 = lo / sb, b1 = (hi - 1) / sb;
             for (uint64_t b = b0; b <= b1; b++) {
                 h_slices[si].genome = (uint32_t)g;
                 h_slices[si].prev_ok = 0;
                 h_slices[si].prev16 = 0;
                 h_slices[si].pad = 0;
-                h_slices[si].begin = b * sb;
-                h_slices[si].end = (b + 1) * sb;
+                // a range cuts whole tiles: clip the slice to it (range_begin is tile-aligned)
+                h_slices[si].begin = range_end ? std::max(b * sb, range_begin) : b * sb;
+                h_slices[si].end = range_end ? std::min((b + 1) * sb, range_end) : (b + 1) * sb;
                 h_slices[si].hdr_until = 0;
                 si++;
             }
@@ -529,6 +534,29 @@ int kmerml_count_dense_batch(kmerml_ctx* ctx, const uint8_t* d_fasta, const uint
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     return count_dense_core(ctx, ctx->ws[0], d_fasta, h_offsets, n_genomes, k_list, nk, min_record_len, flags,
                             d_counts, counts_stride, d_freq, freq_stride, d_totals, (cudaStream_t)stream);
+}
+
+int kmerml_count_dense_range(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin,
+                             uint64_t range_end, const int* k_list, int nk, int min_record_len, unsigned flags,
+                             uint32_t* d_counts, uint64_t* d_totals, void* stream) {
+    if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
+    if (range_begin % TILE_BYTES) return fail(KMERML_ERR_ARG, "range_begin must be a multiple of 16384");
+    if (range_end > nbytes) range_end = nbytes;
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    uint64_t offs[2] = {0, nbytes};
+    RowSpec row;
+    int kmax, kmin;
+    int rc = build_row(k_list, nk, &row, &kmax, &kmin);
+    if (rc) return rc;
+    if (range_begin >= range_end) {                       // empty range: an all-zero contribution
+        KM_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)row.off[nk] * 4, (cudaStream_t)stream));
+        if (d_totals) KM_CUDA(cudaMemsetAsync(d_totals, 0, (size_t)nk * 8, (cudaStream_t)stream));
+        return KMERML_OK;
+    }
+    return count_dense_core(ctx, ctx->ws[0], d_fasta, offs, 1, k_list, nk, min_record_len, flags, d_counts,
+                            align_up((size_t)row.off[nk], 4), nullptr, 0, d_totals, (cudaStream_t)stream, range_begin,
+                            range_end);
 }
 
 int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, const uint64_t* h_sizes, int n_genomes,

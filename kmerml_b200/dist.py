@@ -1,0 +1,145 @@
+"""Multi-GPU layer: one process per GPU (torchrun), torch.distributed for the plumbing.
+
+Two levels, as in SURVEY 8e:
+  * whole genomes are independent units -> sharded across ranks (longest-processing-time
+    first on file size), no data-path collective; rows are gathered only when asked for;
+  * one large genome is cut into byte ranges of whole 16 KB tiles; every rank counts the
+    windows that END in its range (kmerml_count_dense_range reads the k-1 bases before the
+    range from the file itself) and the dense uint32 rows are summed with ONE all-reduce
+    (NCCL over NVLink on GPUs).  Integer sums are order-independent, so the result is
+    bit-identical to the single-GPU one.
+"""
+import numpy as np
+
+TILE_BYTES = 16384
+
+
+def shard_genomes(sizes, world_size):
+    """Longest-processing-time-first assignment of genomes (by byte size) to ranks.
+    Returns a list of index lists, one per rank; deterministic for equal inputs."""
+    order = sorted(range(len(sizes)), key=lambda i: (-int(sizes[i]), i))
+    load = [0] * world_size
+    shards = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda j: (load[j], j))
+        shards[r].append(i)
+        load[r] += int(sizes[i])
+    for s in shards:
+        s.sort()
+    return shards
+
+
+def chunk_ranges(nbytes, world_size, tile=TILE_BYTES):
+    """world_size contiguous byte ranges [begin, end) that tile [0, nbytes); every begin is a
+    multiple of the tile size (the kernels' slice granularity)."""
+    tiles = (int(nbytes) + tile - 1) // tile
+    out = []
+    for r in range(world_size):
+        t0 = tiles * r // world_size
+        t1 = tiles * (r + 1) // world_size
+        out.append((min(t0 * tile, int(nbytes)), min(t1 * tile, int(nbytes))))
+    return out
+
+
+def _world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def allreduce_counts(counts, totals=None):
+    """In-place SUM all-reduce of partial count rows (int32 storage of uint32: the wrap-around
+    sum is the uint32 sum) and of the window totals."""
+    import torch.distributed as dist
+    _, world = _world()
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        if totals is not None:
+            dist.all_reduce(totals, op=dist.ReduceOp.SUM)
+    return counts, totals
+
+
+def count_genome_chunked(fasta, k_values, *, min_record_len=None, canonical=False, want_freq=True,
+                         count_range=None):
+    """Dense counts of ONE genome resident on every rank's device, computed cooperatively:
+    rank r counts byte range r, then one all-reduce.  Every rank returns the full result.
+
+    `count_range(fasta, begin, end, ks, min_record_len, canonical) -> (counts, totals)` can be
+    injected (the CPU tests use the thread emulator); by default it is the CUDA entry point.
+    """
+    import torch
+    from . import engine
+    rank, world = _world()
+    ks = list(dict.fromkeys(int(k) for k in k_values))
+    begin, end = chunk_ranges(int(fasta.numel()), world)[rank]
+    fn = count_range if count_range is not None else engine.count_dense_range_device
+    counts, totals = fn(fasta, begin, end, ks, min_record_len, canonical)
+    allreduce_counts(counts, totals)
+    freq = None
+    if want_freq:
+        if counts.is_cuda:
+            lay, _ = engine.row_layout(ks)
+            freq = torch.empty(counts.shape, dtype=torch.float32, device=counts.device)
+            for ki, k in enumerate(ks):
+                off, n = lay[k]
+                freq[off:off + n] = engine.normalize_rows_device(counts[off:off + n].unsqueeze(0).contiguous(),
+                                                                 totals[ki:ki + 1])[0]
+        else:
+            lay, _ = engine.row_layout(ks)
+            c = counts.numpy().view(np.uint32).astype(np.float64)
+            f = np.zeros_like(c)
+            for ki, k in enumerate(ks):
+                off, n = lay[k]
+                t = float(totals[ki])
+                f[off:off + n] = c[off:off + n] / t if t else 0.0
+            freq = torch.from_numpy(f.astype(np.float32))
+    return counts, freq, totals
+
+
+def count_genomes_sharded(fasta_list, k_values, *, min_record_len=None, canonical=False, gather=True, count_batch=None):
+    """Dense counts of many genomes: this rank counts its LPT shard; with gather=True the rows
+    of all ranks are assembled (in input order) on every rank with one all_gather per tensor.
+
+    fasta_list: per-genome uint8 tensors (only this rank's shard needs to be on its device).
+    Returns (indices of the rows held, counts [n, row_len], totals [n, nk])."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    rank, world = _world()
+    ks = list(dict.fromkeys(int(k) for k in k_values))
+    sizes = [int(t.numel()) for t in fasta_list]
+    shards = shard_genomes(sizes, world)
+    mine = shards[rank]
+    _, row_len = engine.row_layout(ks)
+    if count_batch is not None:
+        counts, totals = count_batch([fasta_list[i] for i in mine], ks, min_record_len, canonical)
+    elif mine:
+        dev = fasta_list[mine[0]].device
+        buf = torch.cat([fasta_list[i].to(dev) for i in mine])
+        offs = np.concatenate(([0], np.cumsum([sizes[i] for i in mine]))).tolist()
+        res = engine.count_dense_device(buf, offs, ks, min_record_len=min_record_len, canonical=canonical,
+                                        want_freq=False)
+        counts, totals = res.counts, res.totals
+    else:
+        dev = fasta_list[0].device if fasta_list else torch.device("cpu")
+        counts = torch.zeros((0, row_len), dtype=torch.int32, device=dev)
+        totals = torch.zeros((0, len(ks)), dtype=torch.int64, device=dev)
+    if not gather or world == 1:
+        return mine, counts, totals
+    n_max = max(len(s) for s in shards)
+    pad_c = torch.zeros((n_max, row_len), dtype=torch.int32, device=counts.device)
+    pad_t = torch.zeros((n_max, len(ks)), dtype=torch.int64, device=counts.device)
+    pad_c[:len(mine)] = counts
+    pad_t[:len(mine)] = totals
+    all_c = [torch.empty_like(pad_c) for _ in range(world)]
+    all_t = [torch.empty_like(pad_t) for _ in range(world)]
+    dist.all_gather(all_c, pad_c)
+    dist.all_gather(all_t, pad_t)
+    out_c = torch.empty((len(sizes), row_len), dtype=torch.int32, device=counts.device)
+    out_t = torch.empty((len(sizes), len(ks)), dtype=torch.int64, device=counts.device)
+    for r, idxs in enumerate(shards):
+        for j, i in enumerate(idxs):
+            out_c[i] = all_c[r][j]
+            out_t[i] = all_t[r][j]
+    return list(range(len(sizes))), out_c, out_t

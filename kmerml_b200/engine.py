@@ -199,3 +199,20 @@ def pairwise_distance_device(x, metric="cosine", *, out_dtype=torch.float32):
     _lib.check(_lib.load().kmerml_pairwise_distance(ctx.handle, x.data_ptr(), _DTYPE_CODE[x.dtype], x.stride(0), n, m,
                                                     _METRIC_CODE[metric], o32, o64, ctypes.c_void_p(stream)))
     return out
+
+
+def count_dense_range_device(fasta, begin, end, k_values, min_record_len=None, canonical=False, partition=True):
+    """(counts int32[row_len], totals int64[nk]) of the windows of ONE genome whose last base
+    lies in bytes [begin, end): the additive unit of intra-genome / multi-GPU parallelism."""
+    ks = _dedupe(k_values)
+    ctx = _lib.context(fasta.device.index)
+    _, row_len = row_layout(ks)
+    counts = torch.empty(row_len, dtype=torch.int32, device=fasta.device)
+    totals = torch.zeros(len(ks), dtype=torch.int64, device=fasta.device)
+    karr = np.asarray(ks, dtype=np.int32)
+    stream = torch.cuda.current_stream(fasta.device).cuda_stream
+    _lib.check(_lib.load().kmerml_count_dense_range(
+        ctx.handle, fasta.data_ptr(), fasta.numel(), int(begin), int(end), karr.ctypes.data, len(ks),
+        int(min_record_len or 0), _flags(canonical, partition), counts.data_ptr(), totals.data_ptr(),
+        ctypes.c_void_p(stream)))
+    return counts, totals

@@ -33,9 +33,9 @@ extern "C" {
 // (exercises unaligned genome starts).  Counts level kmax with the tile/slice
 // geometry given, then cascades to every level 1..kmax.  out_levels receives
 // levels 1..kmax concatenated (uint64).  Returns counted windows at kmax.
-int64_t emu_count_dense(const uint8_t* bytes, uint64_t n, uint64_t base_off, int kmax, int min_rec,
+static int64_t emu_core(const uint8_t* bytes, uint64_t n, uint64_t base_off, int kmax, int min_rec,
                         int threads_per_tile, int tiles_per_slice, uint64_t* out_levels,
-                        uint64_t* out_first /* 4^kmax or NULL */) {
+                        uint64_t* out_first /* 4^kmax or NULL */, uint64_t range_begin, uint64_t range_end) {
     std::vector<uint8_t> buf(base_off + n + 256, 0);
     if (n) memcpy(buf.data() + base_off, bytes, n);
     Genome g;
@@ -65,6 +65,8 @@ int64_t emu_count_dense(const uint8_t* bytes, uint64_t n, uint64_t base_off, int
     // slices are aligned to absolute multiples of slice_bytes (as on the GPU)
     uint64_t first_slice = g.lo / slice_bytes;
     for (uint64_t sb = first_slice * slice_bytes; sb < g.hi; sb += slice_bytes) {
+        // a byte range (relative to the file start) selects whole slices: the multi-GPU unit
+        if (range_end && (sb + slice_bytes <= base_off + range_begin || sb >= base_off + range_end)) continue;
         uint64_t hdr_carry = 0;
         if (sb > g.lo) {
             uint64_t until;
@@ -161,5 +163,17 @@ int64_t emu_count_dense(const uint8_t* bytes, uint64_t n, uint64_t base_off, int
     }
     if (out_first) memcpy(out_first, first.data(), first.size() * sizeof(uint64_t));
     return (int64_t)sink.n_count;
+}
+
+int64_t emu_count_dense(const uint8_t* bytes, uint64_t n, uint64_t base_off, int kmax, int min_rec,
+                        int threads_per_tile, int tiles_per_slice, uint64_t* out_levels, uint64_t* out_first) {
+    return emu_core(bytes, n, base_off, kmax, min_rec, threads_per_tile, tiles_per_slice, out_levels, out_first, 0, 0);
+}
+
+// Only the slices inside [range_begin, range_end) (multiples of the slice size, base_off = 0).
+int64_t emu_count_dense_range(const uint8_t* bytes, uint64_t n, int kmax, int min_rec, int threads_per_tile,
+                              int tiles_per_slice, uint64_t range_begin, uint64_t range_end, uint64_t* out_levels) {
+    return emu_core(bytes, n, 0, kmax, min_rec, threads_per_tile, tiles_per_slice, out_levels, nullptr, range_begin,
+                    range_end);
 }
 }

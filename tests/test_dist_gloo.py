@@ -1,0 +1,143 @@
+"""Multi-rank host logic on CPU: world_size-2 gloo runs of kmerml_b200.dist with the CUDA entry
+points replaced by the CPU thread emulator (tests/emu), checked against the oracle.  No GPU."""
+import ctypes
+import os
+import socket
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from kmerml_b200 import dist as kdist
+from kmerml_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _emu():
+    src = os.path.join(HERE, "emu", "emu_dense.cpp")
+    so = os.path.join(HERE, "emu", "libemu_dense.so")
+    hdr = os.path.join(HERE, "..", "kmerml_b200", "csrc", "fasta_walk.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+    L = ctypes.CDLL(so)
+    L.emu_count_dense_range.restype = ctypes.c_int64
+    L.emu_count_dense_range.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+    return L
+
+
+def emu_count_range(fasta, begin, end, ks, min_record_len, canonical):
+    """Stand-in for engine.count_dense_range_device with the same contract (CPU emulator)."""
+    a = fasta.numpy()
+    kmax = max(ks)
+    levels = np.zeros(sum(4 ** j for j in range(1, kmax + 1)), np.uint64)
+    if begin < end:
+        _emu().emu_count_dense_range(a.ctypes.data, a.size, kmax, min_record_len or kmax, 512, 1, begin, end,
+                                     levels.ctypes.data)
+    offs = np.concatenate(([0], np.cumsum([4 ** j for j in range(1, kmax + 1)])))
+    row = np.concatenate([levels[offs[k - 1]:offs[k]] for k in ks])
+    totals = np.array([levels[offs[k - 1]:offs[k]].sum() for k in ks], dtype=np.int64)
+    return torch.from_numpy(row.astype(np.uint32).view(np.int32).copy()), torch.from_numpy(totals)
+
+
+def emu_count_batch(fastas, ks, min_record_len, canonical):
+    rows, tots = [], []
+    for f in fastas:
+        c, t = emu_count_range(f, 0, int(f.numel()), ks, min_record_len, canonical)
+        rows.append(c)
+        tots.append(t)
+    _, row_len = __import__("kmerml_b200.engine", fromlist=["row_layout"]).row_layout(ks)
+    if not rows:
+        return torch.zeros((0, row_len), dtype=torch.int32), torch.zeros((0, len(ks)), dtype=torch.int64)
+    return torch.stack(rows), torch.stack(tots)
+
+
+def _worker(rank, world, port, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ks = [3, 8]
+        # (1) one genome cut into byte ranges + all-reduce
+        genome = synth.fasta_bytes([30_000, 7, 21_000], seed=5)
+        genome[40_000:40_300] = ord("N")
+        data = torch.from_numpy(genome.copy())
+        counts, freq, totals = kdist.count_genome_chunked(data, ks, count_range=emu_count_range)
+        ok = True
+        off = 0
+        for ki, k in enumerate(ks):
+            ref = oracle.count_dense(genome.tobytes(), k, max(ks))
+            got = counts[off:off + 4 ** k].numpy().view(np.uint32).astype(np.uint64)
+            ok &= bool(np.array_equal(ref, got)) and int(totals[ki]) == int(ref.sum())
+            f = freq[off:off + 4 ** k].numpy().astype(np.float64)
+            ok &= bool(np.all(np.abs(f - oracle.frequencies(ref)) <= 1e-6 * np.maximum(oracle.frequencies(ref), 1e-300)))
+            off += 4 ** k
+        # (2) genomes sharded across ranks + gather
+        gs = [synth.fasta_bytes([3000 + 700 * i, 1500], seed=20 + i) for i in range(5)]
+        idx, c2, t2 = kdist.count_genomes_sharded([torch.from_numpy(g.copy()) for g in gs], ks, count_batch=emu_count_batch)
+        ok &= idx == list(range(5))
+        for i, g in enumerate(gs):
+            off = 0
+            for ki, k in enumerate(ks):
+                ref = oracle.count_dense(g.tobytes(), k, max(ks))
+                ok &= bool(np.array_equal(ref, c2[i, off:off + 4 ** k].numpy().view(np.uint32).astype(np.uint64)))
+                ok &= int(t2[i, ki]) == int(ref.sum())
+                off += 4 ** k
+        results[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_rank_gloo_chunked_and_sharded():
+    _emu()
+    oracle.build()
+    world = 2
+    with mp.Manager() as mgr:
+        results = mgr.dict()
+        mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+        assert dict(results) == {0: True, 1: True}
+
+
+def test_shard_genomes_lpt():
+    sizes = [40, 12, 33, 25, 18, 30, 12]
+    shards = kdist.shard_genomes(sizes, 3)
+    assert sorted(i for s in shards for i in s) == list(range(7))
+    loads = [sum(sizes[i] for i in s) for s in shards]
+    assert max(loads) - min(loads) <= max(sizes)
+    assert shards == kdist.shard_genomes(sizes, 3)
+    assert kdist.shard_genomes([5, 5], 4) == [[0], [1], [], []]
+
+
+def test_chunk_ranges_tile_aligned():
+    for n in (0, 1, 16384, 16385, 1_000_000, 3_100_000_123):
+        for w in (1, 2, 4, 8):
+            r = kdist.chunk_ranges(n, w)
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert all(b % kdist.TILE_BYTES == 0 for b, _ in r if b < n)
+
+
+def test_single_process_additivity_over_ranges():
+    """Counts of byte ranges that tile the file add up to the whole (the multi-GPU invariant)."""
+    genome = synth.fasta_bytes([50_000, 12_345], seed=9)
+    data = torch.from_numpy(genome.copy())
+    for world in (2, 3, 5):
+        total = None
+        for b, e in kdist.chunk_ranges(genome.size, world):
+            c, _ = emu_count_range(data, b, e, [2, 9], 9, False)
+            total = c.numpy().view(np.uint32).astype(np.uint64) if total is None else total + c.numpy().view(np.uint32)
+        ref = np.concatenate([oracle.count_dense(genome.tobytes(), k, 9) for k in (2, 9)])
+        assert np.array_equal(total, ref), world

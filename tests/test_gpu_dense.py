@@ -147,3 +147,27 @@ def test_argument_errors():
         engine.count_dense_device(dev, [0, 64], [5], min_record_len=3)
     with pytest.raises(_lib.KmermlError):
         engine.count_dense_device(dev, [64, 0], [5])
+
+
+def test_byte_ranges_are_additive():
+    """kmerml_count_dense_range over ranges that tile the file sums to the whole-genome rows
+    (the multi-GPU all-reduce invariant), on both the partition and the global-atomic path."""
+    torch = torch_mod()
+    from kmerml_b200 import dist as kdist
+    from kmerml_b200 import engine, synth
+    g = synth.fasta_bytes([400_000, 30, 250_000], seed=77)
+    g[100_000:100_900] = ord("N")
+    dev = torch.from_numpy(g).cuda()
+    for ks, part in (([12, 5], True), ([10], True), ([12, 11], False), ([6, 2], True), ([8], True)):
+        whole = engine.count_dense_device(dev, [0, g.size], ks, want_freq=False, partition=part)
+        for world in (2, 5):
+            acc = torch.zeros_like(whole.counts[0], dtype=torch.int64)
+            tot = torch.zeros_like(whole.totals[0])
+            for b, e in kdist.chunk_ranges(g.size, world):
+                c, t = engine.count_dense_range_device(dev, b, e, ks, partition=part)
+                acc += c.to(torch.int64) & 0xFFFFFFFF
+                tot += t
+            assert torch.equal(acc, whole.counts[0].to(torch.int64) & 0xFFFFFFFF), (ks, part, world)
+            assert torch.equal(tot, whole.totals[0])
+        for k in ks:
+            assert np.array_equal(whole.counts_numpy(0, k).astype(np.uint64), oracle.count_dense(g.tobytes(), k, max(ks)))
