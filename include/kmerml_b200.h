@@ -103,6 +103,18 @@ int kmerml_count_dense_host(kmerml_ctx *ctx, const uint8_t *const *h_fasta, cons
                             float *h_freq, uint64_t freq_stride, uint64_t *h_totals);
 
 /*
+ * Sparse counting for 15 <= k <= 32 (any k >= 1 is accepted): the distinct k-mers of ONE genome as
+ * sorted 2-bit packed keys (A0 C1 G2 T3, first base most significant), their counts, and the byte
+ * offset of the last base of each k-mer's first window (sort by it for dict insertion order,
+ * generate.py:88).  Same window rules as the dense path.  Synchronous.  *h_unique receives the
+ * number of distinct k-mers; when it exceeds out_cap nothing is written: call again with larger
+ * outputs.  Genome < 4 GiB.  d_first may be NULL.
+ */
+int kmerml_count_sparse(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbytes, int k, int min_record_len,
+                        unsigned flags, uint64_t *d_keys, uint32_t *d_counts, uint32_t *d_first,
+                        uint64_t out_cap, uint64_t *h_unique, uint64_t *h_windows, void *stream);
+
+/*
  * Byte offset (within the genome) of the last base of the first window of every
  * k-mer, UINT32_MAX where the k-mer never occurs: sorting the observed bins by
  * this value gives dict insertion order, i.e. the line order of k{k}.txt

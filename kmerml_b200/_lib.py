@@ -50,6 +50,8 @@ def load():
     L.kmerml_count_dense_batch.argtypes = [vp, vp, vp, i32, vp, i32, i32, u32, vp, u64, vp, u64, vp, vp]
     L.kmerml_count_dense_host.argtypes = [vp, vp, vp, i32, vp, i32, i32, u32, vp, u64, vp, u64, vp]
     L.kmerml_count_dense_range.argtypes = [vp, vp, u64, u64, u64, vp, i32, i32, u32, vp, vp, vp]
+    L.kmerml_count_sparse.argtypes = [vp, vp, u64, i32, i32, u32, vp, vp, vp, u64, ctypes.POINTER(ctypes.c_uint64),
+                                      ctypes.POINTER(ctypes.c_uint64), vp]
     L.kmerml_first_occurrence.argtypes = [vp, vp, u64, i32, i32, vp, vp]
     L.kmerml_find_records.argtypes = [vp, vp, u64, vp, u32, ctypes.POINTER(ctypes.c_uint32), vp]
     L.kmerml_records_short.argtypes = [vp, vp, u64, vp, u32, i32, vp, vp]
@@ -73,6 +75,7 @@ EXPORTS = [
     "kmerml_count_dense_host", "kmerml_first_occurrence", "kmerml_profile_enable",
     "kmerml_profile_read", "kmerml_find_records", "kmerml_records_short", "kmerml_static_features",
     "kmerml_normalize_rows", "kmerml_pairwise_distance", "kmerml_count_dense_range",
+    "kmerml_count_sparse",
 ]
 
 

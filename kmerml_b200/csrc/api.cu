@@ -659,6 +659,26 @@ int kmerml_pairwise_distance(kmerml_ctx* ctx, const void* d_x, int dtype, uint64
                            (cudaStream_t)stream);
 }
 
+int kmerml_count_sparse(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, int k, int min_record_len,
+                        unsigned flags, uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_first, uint64_t out_cap,
+                        uint64_t* h_unique, uint64_t* h_windows, void* stream) {
+    if (!ctx || !h_unique || !h_windows) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (k < 1 || k > KMERML_MAX_K) return fail(KMERML_ERR_ARG, "k must be in 1..32");
+    if (nbytes && !d_fasta) return fail(KMERML_ERR_ARG, "d_fasta is null");
+    if (out_cap && (!d_keys || !d_counts)) return fail(KMERML_ERR_ARG, "null output pointer");
+    if (nbytes >= 0xFFFFFFFFull) return fail(KMERML_ERR_RANGE, "genome too large for 32-bit offsets");
+    int min_rec = min_record_len > 0 ? min_record_len : k;
+    if (min_rec < k) return fail(KMERML_ERR_ARG, "min_record_len must be >= k");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    Workspace& ws = ctx->ws[0];
+    const uint64_t cap = std::max<uint64_t>(nbytes, 1);           // at most one window ends at every byte
+    int rc = ws.part.ensure(sparse_workspace_bytes(cap));
+    if (rc) return rc;
+    return run_sparse_in(ws.part.p, d_fasta, nbytes, k, min_rec, (flags & KMERML_FLAG_CANONICAL) != 0, cap, d_keys,
+                         d_counts, d_first, out_cap, h_unique, h_windows, (cudaStream_t)stream);
+}
+
 int kmerml_first_occurrence(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, int k, int min_record_len,
                             uint32_t* d_first, void* stream) {
     if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");

@@ -98,6 +98,13 @@ int launch_first_occurrence(const uint8_t* d_fasta, const GenomeDev* d_genomes, 
                             int n_slices, int k, int min_rec, uint32_t* d_first, cudaStream_t s);
 int dense_setup_attributes();
 
+// ---- sparse path (sparse.cu) ---------------------------------------------------
+struct SparseWork;
+size_t sparse_workspace_bytes(uint64_t cap);
+int run_sparse_in(void* workspace, const uint8_t* d_fasta, uint64_t nbytes, int k, int min_rec, bool canonical,
+                  uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
+                  uint64_t* h_unique, uint64_t* h_windows, cudaStream_t s);
+
 // ---- launchers (features.cu) --------------------------------------------------
 int launch_scan_records(const uint8_t* d_fasta, uint64_t nbytes, int need, unsigned long long* d_offsets,
                         uint8_t* d_short, uint32_t cap, uint32_t* d_count, cudaStream_t s);

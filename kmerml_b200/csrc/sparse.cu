@@ -1,0 +1,219 @@
+// sparse.cu -- k = 15..32: 4^k bins no longer fit a dense histogram, so the windows are emitted as
+// 2-bit packed 64-bit keys (+ the byte offset of their last base), radix-sorted and run-length
+// reduced into (k-mer, count, first occurrence).  Same window semantics as the dense path
+// (kmerml/kmers/generate.py:39-58 of the reference); canonical = min(k-mer, reverse complement).
+//
+// Round 1: the sort and the segmented reductions are CUB library calls (the toolkit's own headers);
+// the emitter is the shared carry-free walker with 64-bit state.
+#include <cub/cub.cuh>
+
+#include "fasta_walk.cuh"
+#include "internal.h"
+
+namespace km {
+
+struct SparseParams {
+    int k;
+    int min_rec;
+    int canonical;
+    uint64_t mask;       // 4^k - 1 (all ones for k = 32)
+};
+
+__device__ __forceinline__ void sparse_push(uint64_t fwd, uint64_t rc, const SparseParams& P, uint64_t pos,
+                                            uint64_t* keys, uint32_t* ends, unsigned long long* cursor, uint64_t cap) {
+    const uint64_t key = P.canonical ? (fwd < rc ? fwd : rc) : fwd;
+    // one reservation per warp instead of one per window
+    const unsigned active = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(active) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(active));
+    base = __shfl_sync(active, base, leader);
+    const unsigned long long slot = base + __popc(active & ((1u << lane) - 1u));
+    if (slot < cap) {
+        keys[slot] = key;
+        ends[slot] = (uint32_t)pos;
+    }
+}
+
+// One thread per 32-byte chunk, owning the windows whose last base lies in it; the start state
+// comes from a backward walk over global memory (same rules as fasta_walk.cuh's generic path).
+__global__ void __launch_bounds__(256)
+sparse_emit_kernel(const uint8_t* __restrict__ buf, uint64_t nbytes, SparseParams P, uint64_t* keys, uint32_t* ends,
+                   unsigned long long* cursor, uint64_t cap) {
+    Genome g;
+    g.b = buf;
+    g.hi = nbytes;
+    g.lo = 0;
+    // text before the first header line is ignored: every thread needs the same g.lo
+    __shared__ uint64_t s_lo;
+    if (threadIdx.x == 0) s_lo = first_header(buf, 0, nbytes);
+    __syncthreads();
+    g.lo = s_lo;
+    const uint64_t cb = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * CHUNK;
+    const uint64_t cs = cb > g.lo ? cb : g.lo;
+    const uint64_t ce = cb + CHUNK < g.hi ? cb + CHUNK : g.hi;
+    if (cs >= ce) return;
+    uint64_t until = 0;
+    int in_hdr = (cs > g.lo && pos_in_header(g, cs, &until)) ? 1 : 0;
+    uint64_t fwd = 0, rc = 0;
+    int run = 0, rec_known = 0;
+    const int rcshift = 2 * (P.k - 1);
+    if (!in_hdr && cs > g.lo) {
+        // the up to k-1 valid bases right before the chunk, oldest first
+        uint64_t q = cs;
+        uint32_t codes[32];
+        int cnt = 0;
+        while (cnt < P.k - 1) {
+            int kind = prev_symbol(g, q);
+            if (kind > 3) break;
+            codes[cnt++] = (uint32_t)kind;
+        }
+        for (int i = cnt - 1; i >= 0; i--) {
+            fwd = ((fwd << 2) | codes[i]) & P.mask;
+            rc = (rc >> 2) | ((uint64_t)(3u - codes[i]) << rcshift);
+        }
+        run = cnt;
+    }
+    for (uint64_t pos = cs; pos < ce; pos++) {
+        const uint32_t c = buf[pos];
+        const int code = base_code(c);
+        if (code >= 0 && !in_hdr) {
+            fwd = ((fwd << 2) | (uint64_t)code) & P.mask;
+            rc = (rc >> 2) | ((uint64_t)(3 - code) << rcshift);
+            run++;
+            if (run >= P.k) {
+                if (P.min_rec > P.k) {
+                    if (rec_known == 0) rec_known = (run >= P.min_rec || record_len_at_least(g, pos, P.min_rec)) ? 1 : 2;
+                    if (rec_known == 2) continue;
+                }
+                sparse_push(fwd, rc, P, pos, keys, ends, cursor, cap);
+            }
+            continue;
+        }
+        if (in_hdr) {
+            if (is_term(c)) in_hdr = 0;
+            continue;
+        }
+        const int kind = classify_nonbase(g, pos, c);
+        if (kind == SYM_SKIP) continue;
+        run = 0;
+        fwd = rc = 0;
+        if (kind == SYM_HDR) { in_hdr = 1; rec_known = 0; }
+    }
+}
+
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ src, uint32_t* dst, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+struct SparseWork {
+    uint64_t* keys_a;
+    uint64_t* keys_b;
+    uint32_t* ends_a;
+    uint32_t* ends_b;
+    unsigned long long* cursor;
+    unsigned long long* n_runs;
+    void* temp;
+    size_t temp_bytes;
+};
+
+// Layout of the workspace for `cap` windows; returns the total number of bytes.
+size_t sparse_workspace(uint64_t cap, SparseWork* w, uint8_t* base) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        uint8_t* p = base ? base + off : nullptr;
+        off += (bytes + 255) / 256 * 256;
+        return p;
+    };
+    SparseWork local;
+    local.keys_a = (uint64_t*)take(cap * 8);
+    local.keys_b = (uint64_t*)take(cap * 8);
+    local.ends_a = (uint32_t*)take(cap * 4);
+    local.ends_b = (uint32_t*)take(cap * 4);
+    local.cursor = (unsigned long long*)take(256);
+    local.n_runs = (unsigned long long*)take(256);
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
+    cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, dk, dv, (uint64_t)cap, 0, 64);
+    cub::DeviceRunLengthEncode::Encode(nullptr, t2, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
+                                       (unsigned long long*)nullptr, (uint64_t)cap);
+    cub::DeviceReduce::ReduceByKey(nullptr, t3, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
+                                   (uint32_t*)nullptr, (unsigned long long*)nullptr, cub::Min(), (uint64_t)cap);
+    local.temp_bytes = std::max(t1, std::max(t2, t3));
+    local.temp = take(local.temp_bytes);
+    if (w) *w = local;
+    return off;
+}
+
+// Emits, sorts and reduces.  On return (after a stream sync) *h_windows / *h_unique are valid; when
+// *h_unique > out_cap nothing was written to the outputs.
+int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, int k, int min_rec, bool canonical, const SparseWork& w,
+               uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
+               uint64_t* h_unique, uint64_t* h_windows, cudaStream_t s) {
+    SparseParams P;
+    P.k = k;
+    P.min_rec = min_rec;
+    P.canonical = canonical ? 1 : 0;
+    P.mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    KM_CUDA(cudaMemsetAsync(w.cursor, 0, 8, s));
+    KM_CUDA(cudaMemsetAsync(w.n_runs, 0, 8, s));
+    *h_unique = 0;
+    *h_windows = 0;
+    if (!nbytes) return KMERML_OK;
+    const uint64_t chunks = (nbytes + CHUNK - 1) / CHUNK;
+    sparse_emit_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(d_fasta, nbytes, P, w.keys_a, w.ends_a,
+                                                                       w.cursor, cap);
+    KM_CUDA(cudaGetLastError());
+    unsigned long long n = 0;
+    KM_CUDA(cudaMemcpyAsync(&n, w.cursor, 8, cudaMemcpyDeviceToHost, s));
+    KM_CUDA(cudaStreamSynchronize(s));
+    *h_windows = n;
+    if (n > cap) {
+        set_error("internal: sparse window capacity exceeded");
+        return KMERML_ERR_RANGE;
+    }
+    if (!n) return KMERML_OK;
+    cub::DoubleBuffer<uint64_t> dk(w.keys_a, w.keys_b);
+    cub::DoubleBuffer<uint32_t> dv(w.ends_a, w.ends_b);
+    size_t tb = w.temp_bytes;
+    // radix sort is stable and the emission order is arbitrary, so the first occurrence is the
+    // MIN end offset of each run, not its first element
+    KM_CUDA(cub::DeviceRadixSort::SortPairs(w.temp, tb, dk, dv, (uint64_t)n, 0, 2 * k, s));
+    uint64_t* sorted_keys = dk.Current();
+    uint32_t* sorted_ends = dv.Current();
+    uint64_t* uniq = dk.Alternate();                 // scratch for the unique keys
+    uint32_t* runs = dv.Alternate();                 // scratch for counts, then first offsets
+    tb = w.temp_bytes;
+    KM_CUDA(cub::DeviceRunLengthEncode::Encode(w.temp, tb, sorted_keys, uniq, runs, w.n_runs, (uint64_t)n, s));
+    unsigned long long nu = 0;
+    KM_CUDA(cudaMemcpyAsync(&nu, w.n_runs, 8, cudaMemcpyDeviceToHost, s));
+    KM_CUDA(cudaStreamSynchronize(s));
+    *h_unique = nu;
+    if (nu > out_cap) return KMERML_OK;             // caller re-sizes and calls again
+    KM_CUDA(cudaMemcpyAsync(d_keys_out, uniq, nu * 8, cudaMemcpyDeviceToDevice, s));
+    gather_u32_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, s>>>(runs, d_counts_out, nu);
+    KM_CUDA(cudaGetLastError());
+    if (d_first_out) {
+        tb = w.temp_bytes;
+        KM_CUDA(cub::DeviceReduce::ReduceByKey(w.temp, tb, sorted_keys, uniq, sorted_ends, d_first_out, w.n_runs,
+                                               cub::Min(), (uint64_t)n, s));
+    }
+    KM_CUDA(cudaStreamSynchronize(s));
+    return KMERML_OK;
+}
+
+size_t sparse_workspace_bytes(uint64_t cap) { return sparse_workspace(cap, nullptr, nullptr); }
+
+int run_sparse_in(void* workspace, const uint8_t* d_fasta, uint64_t nbytes, int k, int min_rec, bool canonical,
+                  uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
+                  uint64_t* h_unique, uint64_t* h_windows, cudaStream_t s) {
+    SparseWork w;
+    sparse_workspace(cap, &w, (uint8_t*)workspace);
+    return run_sparse(d_fasta, nbytes, k, min_rec, canonical, w, cap, d_keys_out, d_counts_out, d_first_out, out_cap,
+                      h_unique, h_windows, s);
+}
+
+}  // namespace km

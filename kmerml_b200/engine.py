@@ -216,3 +216,25 @@ def count_dense_range_device(fasta, begin, end, k_values, min_record_len=None, c
         int(min_record_len or 0), _flags(canonical, partition), counts.data_ptr(), totals.data_ptr(),
         ctypes.c_void_p(stream)))
     return counts, totals
+
+
+def count_sparse_device(fasta, k, *, min_record_len=None, canonical=False, want_first=True):
+    """Distinct k-mers of ONE genome for any k <= 32 (meant for k > 14): returns
+    (keys int64[n] -- uint64 2-bit packed, sorted --, counts int32[n], first int32[n] or None, windows)."""
+    ctx = _lib.context(fasta.device.index)
+    L = _lib.load()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(fasta.device).cuda_stream)
+    cap = max(1024, min(int(fasta.numel()), 1 << 22))
+    while True:
+        keys = torch.empty(cap, dtype=torch.int64, device=fasta.device)
+        counts = torch.empty(cap, dtype=torch.int32, device=fasta.device)
+        first = torch.empty(cap, dtype=torch.int32, device=fasta.device) if want_first else None
+        nu, nw = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _lib.check(L.kmerml_count_sparse(ctx.handle, fasta.data_ptr() if fasta.numel() else None, fasta.numel(), int(k),
+                                         int(min_record_len or 0), _lib.FLAG_CANONICAL if canonical else 0,
+                                         keys.data_ptr(), counts.data_ptr(), first.data_ptr() if want_first else None,
+                                         cap, ctypes.byref(nu), ctypes.byref(nw), stream))
+        if nu.value <= cap:
+            n = int(nu.value)
+            return keys[:n], counts[:n], (first[:n] if want_first else None), int(nw.value)
+        cap = int(nu.value)

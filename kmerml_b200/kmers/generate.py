@@ -100,8 +100,8 @@ class KmerExtractor:
             organism_id = Path(fasta_file).stem
         ks = list(dict.fromkeys(int(k) for k in k_values))
         max_k = max(ks)
-        if max_k > _lib.MAX_DENSE_K:
-            raise _lib.KmermlError(f"k={max_k}: k > {_lib.MAX_DENSE_K} needs the sparse path, which this build lacks")
+        if max_k > _lib.MAX_K or min(ks) < 1:
+            raise _lib.KmermlError(f"k must be in 1..{_lib.MAX_K}")
         device = self._device()
         host = np.fromfile(str(fasta_file), dtype=np.uint8)
         dev = torch.from_numpy(host).to(device) if host.size else torch.zeros(0, dtype=torch.uint8, device=device)
@@ -112,9 +112,16 @@ class KmerExtractor:
             else:
                 print(f"Processed chromosome/contig: {rid}")
 
-        res = engine.count_dense_device(dev, [0, int(dev.numel())], ks, min_record_len=max_k,
-                                        canonical=self.canonical, want_freq=False)
+        dense = [k for k in ks if k <= _lib.MAX_DENSE_K]
+        res = engine.count_dense_device(dev, [0, int(dev.numel())], dense, min_record_len=max_k,
+                                        canonical=self.canonical, want_freq=False) if dense else None
         for k in ks:
+            if k > _lib.MAX_DENSE_K:                     # sparse path: distinct k-mers, sorted by first occurrence
+                keys, cnts, first, _ = engine.count_sparse_device(dev, k, min_record_len=max_k, canonical=self.canonical)
+                order = torch.argsort(first.to(torch.int64) & 0xFFFFFFFF, stable=True)
+                codes = keys[order].cpu().numpy().view(np.uint64)
+                self._write_lines(organism_id, k, format_kmer_lines(codes, cnts[order].cpu().numpy().view(np.uint32), k))
+                continue
             counts = res.counts_numpy(0, k)
             observed = np.nonzero(counts)[0]
             if observed.size:
