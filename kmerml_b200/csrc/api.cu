@@ -308,7 +308,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     uint32_t* h_gtiles = (uint32_t*)(hs + off_bytes + sl_bytes);
     std::vector<int> group_end;                              // exclusive genome index per group
     if (use_part) {
-        const uint64_t max_tiles = (6ull << 30) / ((uint64_t)PART_TILE_CAP * 2);
+        const uint64_t max_tiles = (12ull << 30) / ((uint64_t)PART_STAGE_ENTRIES * 2);
         uint64_t in_group = 0;
         uint32_t group_tile0 = 0;
         for (int g = 0; g < n_genomes; g++) {
@@ -339,17 +339,22 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
 
     const size_t row_bytes = (size_t)row.off[nk] * 4;
     if (use_part) {
-        const int nb = 1 << (2 * (kmax - PART_LOW_BASES));
         const int k_stop = std::max(kmax - PART_LOW_BASES, kmin);
-        uint64_t max_group_tiles = 0;
-        for (size_t gi = 0, g0 = 0; gi < group_end.size(); g0 = group_end[gi], gi++)
+        uint64_t max_group_tiles = 0, max_group_bytes = 0;
+        for (size_t gi = 0, g0 = 0; gi < group_end.size(); g0 = group_end[gi], gi++) {
             max_group_tiles = std::max<uint64_t>(max_group_tiles, first_slice[group_end[gi]] - first_slice[g0]);
-        const size_t payload_bytes = align_up((size_t)max_group_tiles * PART_TILE_CAP * 2, 256);
-        const size_t table_bytes = align_up((size_t)max_group_tiles * (size_t)(nb + 1) * 2 + 64, 256);
-        rc = ws.part.ensure(payload_bytes + table_bytes);
+            max_group_bytes = std::max<uint64_t>(max_group_bytes, h_offsets[group_end[gi]] - h_offsets[g0]);
+        }
+        // workspace: bucket-major payload slots | overflow lists (one entry per FASTA byte at most) | counters
+        const size_t payload_bytes = align_up((size_t)max_group_tiles * PART_STAGE_ENTRIES * 2, 256);
+        const size_t ov_bytes = align_up((size_t)max_group_bytes * 4 + 64, 256);
+        const size_t ovc_bytes = align_up((size_t)n_genomes * 4, 256);
+        rc = ws.part.ensure(payload_bytes + ov_bytes + ovc_bytes);
         if (rc) return rc;
         uint16_t* d_payload = (uint16_t*)ws.part.p;
-        uint16_t* d_table = (uint16_t*)((uint8_t*)ws.part.p + payload_bytes);
+        uint32_t* d_overflow = (uint32_t*)((uint8_t*)ws.part.p + payload_bytes);
+        unsigned int* d_ov_counts = (unsigned int*)((uint8_t*)ws.part.p + payload_bytes + ov_bytes);
+        KM_CUDA(cudaMemsetAsync(d_ov_counts, 0, (size_t)n_genomes * 4, s));
         // only the levels below kmax collect run-end tails and must start from zero;
         // the top-level row is written in full by the bucket kernel
         for (int i = 0; i < nk; i++)
@@ -361,20 +366,27 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         for (size_t gi = 0; gi < group_end.size(); gi++) {
             const int g1 = group_end[gi], ng = g1 - g0;
             const int nt = (int)(first_slice[g1] - first_slice[g0]);
+            const uint64_t batch_lo = h_offsets[g0];
             {
                 Prof pr(ctx, s, 4, nt > 0 ? 1 : 0);
-                rc = launch_partition(d_fasta, d_genomes, d_slices + first_slice[g0], nt, kmax, kmin, min_rec, lm,
-                                      d_stats, d_payload, d_table, s);
+                rc = launch_partition(d_fasta, d_genomes, d_slices + first_slice[g0], nt, d_gtiles, kmax, kmin, min_rec,
+                                      lm, d_stats, d_payload, d_overflow, d_ov_counts, batch_lo, s);
             }
             if (rc) return rc;
             {
                 Prof pr(ctx, s, 5, 1);
-                rc = launch_bucket(lm, row, kmax, kmin, d_gtiles, d_payload, d_table, d_stats,
-                                   canonical ? nullptr : d_freq, freq_stride, d_totals, (uint32_t)g0, ng, s);
+                rc = launch_bucket(lm, row, kmax, kmin, d_gtiles, d_payload, d_stats, canonical ? nullptr : d_freq,
+                                   freq_stride, d_totals, (uint32_t)g0, ng, s);
             }
             if (rc) return rc;
             for (int h0 = g0; h0 < g1; h0 += 32768) {
                 const int nh = std::min(32768, g1 - h0);
+                {
+                    Prof pr(ctx, s, 3, canonical || !d_freq ? 1 : 2);
+                    rc = launch_overflow(lm, row, kmax, kmin, d_genomes, d_overflow, d_ov_counts, batch_lo, d_stats,
+                                         canonical ? nullptr : d_freq, freq_stride, (uint32_t)h0, nh, s);
+                    if (rc) return rc;
+                }
                 if (k_stop > kmin) {
                     Prof pr(ctx, s, 1, cascade_launches(k_stop, kmin));
                     rc = launch_cascade(lm, k_stop, kmin, (uint32_t)h0, nh, s);

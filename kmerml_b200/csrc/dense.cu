@@ -278,33 +278,43 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
 }
 
 // ---------------------------------------------------------------- partition path
-// k = 9..12: the 4^k histogram (up to 64 MB) is too big for shared memory, and L2
-// atomics top out near 190 G/s (measured) and thrash the L2 next to the streamed
-// input, so the windows are first partitioned by their leading k-7 bases:
-//   partition_kernel  one CTA per 16 KB tile: walk, counting-sort the tile's windows by
-//                     bucket in shared memory, write them bucket-sorted as 14-bit
-//                     payloads (uint16; every bucket segment padded to 8 bytes with
-//                     0xFFFF) plus the tile's bucket offsets
-//   bucket_kernel     one CTA per bucket: gather its segment from every tile into a
-//                     16384-bin shared histogram, then write that 64 KB slice of the
-//                     count row, its frequencies, and the bucket's whole cascade subtree
-// Only shared-memory atomics (2.5 T/s measured on B200) are used; every global access
-// is a coalesced or 8-byte-aligned vector stream.
+// k = 9..12: the 4^k histogram (up to 64 MB) is too big for shared memory, and L2 atomics top out
+// near 190 G/s (measured) and thrash the L2 next to the streamed input, so the windows are first
+// partitioned by their leading k-7 bases into nb = 4^(k-7) buckets of 16384 bins:
+//   partition_kernel  one CTA per 16 KB tile: every window is placed with ONE returning shared
+//                     atomic into its bucket's fixed-size slot of a 64 KB staging buffer
+//                     (slot = 32768/nb uint16: entry 0 = fill count, then 14-bit payloads); the
+//                     slots are then written bucket-major: [genome][bucket][tile][slot]
+//   bucket_kernel     one CTA per (bucket, genome): STREAMS its n_tiles contiguous slots with
+//                     coalesced 128-bit loads into a 16384-bin shared histogram, then writes that
+//                     64 KB slice of the count row, its frequencies and the bucket's whole
+//                     cascade subtree (levels k .. k-7)
+//   overflow_kernel   the rare windows that found their slot full (slot = 2 x the mean fill;
+//                     skewed genomes) are kept as plain k-mer indices and added afterwards
+// Only shared-memory atomics (2.5 T/s measured on B200) sit on the hot path and every global
+// access is a full-sector vector stream.
 constexpr int PART_LOW = 7;
 constexpr int PART_BINS = 1 << (2 * PART_LOW);        // 16384 bins per bucket
 constexpr int PART_MAX_BUCKETS = 1024;                // k <= 12
-constexpr int TILE_WINDOWS = TILE_BYTES;              // a tile owns at most one window per byte
-constexpr int SEG_ALIGN = 4;                          // entries: bucket segments start on 8-byte boundaries
-constexpr int TILE_CAP = TILE_WINDOWS + (SEG_ALIGN - 1) * PART_MAX_BUCKETS;   // padded entries per tile
-constexpr uint32_t PAD_ENTRY = 0xFFFFu;
+constexpr int STAGE_ENTRIES = 32768;                  // uint16 entries staged per tile = nb * slot
 
-struct PartSink {
-    uint32_t raw_addr;                 // shared address of raw[n_local * COUNT_THREADS + tid]
-    uint32_t cnt_base;                 // shared address of cnt[]
+struct SlotSink {
+    uint32_t cnt_base;                 // shared address of cnt[nb]
+    uint32_t stage_base;               // shared address of staged[]
+    uint32_t slot_shift;               // log2(slot entries)
+    uint32_t slot_cap;                 // slot entries - 1 (entry 0 holds the count)
+    uint32_t* ov;                      // this genome's overflow list
+    unsigned int* ov_count;
     __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(raw_addr), "r"(idx) : "memory");
-        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt_base + (idx >> (2 * PART_LOW)) * 4u) : "memory");
-        raw_addr += COUNT_THREADS * 4u;
+        const uint32_t b = idx >> (2 * PART_LOW);
+        uint32_t pos;
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cnt_base + b * 4u) : "memory");
+        if (pos < slot_cap) {
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(stage_base + (((b << slot_shift) + 1u + pos) << 1)),
+                         "h"((uint16_t)(idx & (PART_BINS - 1))) : "memory");
+        } else {
+            ov[atomicAdd(ov_count, 1u)] = idx;        // rare: the slot is full
+        }
     }
 };
 
@@ -315,29 +325,30 @@ struct PartWalkSmem {                           // only live during the walk ...
 };
 
 struct PartSmem {
-    uint32_t raw[TILE_WINDOWS];                 // 64 KB: the tile's windows, thread-interleaved
-    union {
-        uint16_t staged[TILE_CAP];              // 38 KB: payloads sorted by bucket, segments padded
-        PartWalkSmem walk;                      // ... so it shares the staging buffer's space
-    };
-    uint32_t cnt[PART_MAX_BUCKETS];             // per-bucket count, then scatter cursor
-    uint32_t off[PART_MAX_BUCKETS + 4];         // exclusive (padded) offsets
-    uint32_t warp_tot[COUNT_THREADS / 32];
-    uint32_t warp_cnt[COUNT_THREADS / 32];
+    uint16_t staged[STAGE_ENTRIES];             // 64 KB: nb slots
+    uint32_t cnt[PART_MAX_BUCKETS];             // windows per bucket in this tile
+    PartWalkSmem walk;
     unsigned long long carry[2];
     uint32_t prev_tile[2];
+    unsigned long long sh_total;
 };
-static_assert(sizeof(PartSmem) <= 113 * 1024, "two partition CTAs must fit in one SM's shared memory");
+static_assert(sizeof(PartSmem) <= 74 * 1024, "three partition CTAs must fit in one SM's shared memory");
+
+struct GenomeTiles {                   // tiles of one genome inside the group's tile list
+    uint32_t tile0, n_tiles;
+};
 
 __global__ void __launch_bounds__(COUNT_THREADS, 2)
 partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
-                 const Slice* __restrict__ tiles, DenseParams P, LevelMap lm, GenomeStats* stats,
-                 uint16_t* __restrict__ payload, uint16_t* __restrict__ table, int nb) {
+                 const Slice* __restrict__ tiles, const GenomeTiles* __restrict__ gts, DenseParams P, LevelMap lm,
+                 GenomeStats* stats, uint16_t* __restrict__ payload, uint32_t* __restrict__ overflow,
+                 unsigned int* __restrict__ ov_counts, uint64_t batch_lo, int nb, int slot_shift) {
     extern __shared__ __align__(16) unsigned char part_smem_raw[];
     PartSmem& sm = *reinterpret_cast<PartSmem*>(part_smem_raw);
     const int tid = threadIdx.x;
     const Slice sl = tiles[blockIdx.x];
     const GenomeDev gd = gds[sl.genome];
+    const GenomeTiles gt = gts[sl.genome];
     Genome g;
     g.b = buf;
     g.lo = gd.lo;
@@ -346,105 +357,50 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     tc.flags = sm.walk.flags; tc.clean = sm.walk.clean; tc.last16 = sm.walk.last16;
     tc.carry = sm.carry; tc.prev_tile = sm.prev_tile;
     for (int i = tid; i < nb; i += COUNT_THREADS) sm.cnt[i] = 0;
+    if (tid == 0) sm.sh_total = 0;
 
-    PartSink sink;
-    const uint32_t raw0 = (uint32_t)__cvta_generic_to_shared(sm.raw) + tid * 4u;
-    sink.raw_addr = raw0;
+    SlotSink sink;
     sink.cnt_base = (uint32_t)__cvta_generic_to_shared(sm.cnt);
+    sink.stage_base = (uint32_t)__cvta_generic_to_shared(sm.staged);
+    sink.slot_shift = (uint32_t)slot_shift;
+    sink.slot_cap = (1u << slot_shift) - 1u;
+    sink.ov = overflow + (gd.file_lo - batch_lo);      // one possible window per byte of the genome
+    sink.ov_count = ov_counts + sl.genome;
     DevTails tails;
     tails.lm = &lm; tails.st = stats + sl.genome; tails.genome = sl.genome;
-    walk_slice(buf, g, sl, P, sink, tails, tc);     // slice == one tile; ends with __syncthreads
+    walk_slice(buf, g, sl, P, sink, tails, tc);         // slice == one tile; ends with __syncthreads
 
-    // exclusive scan of the padded bucket counts (SCAN_PER buckets per thread)
-    constexpr int SCAN_PER = PART_MAX_BUCKETS / COUNT_THREADS;
-    uint32_t v[SCAN_PER], s = 0, sv = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_PER; i++) {
-        const int b = SCAN_PER * tid + i;
-        v[i] = b < nb ? sm.cnt[b] : 0u;
-        s += (v[i] + (SEG_ALIGN - 1)) & ~(uint32_t)(SEG_ALIGN - 1);
-        sv += v[i];
+    // fill counts into entry 0 of every slot; windows of the tile
+    unsigned n = 0;
+    for (int b = tid; b < nb; b += COUNT_THREADS) {
+        const uint32_t c = sm.cnt[b];
+        n += c;
+        sm.staged[b << slot_shift] = (uint16_t)(c < sink.slot_cap ? c : sink.slot_cap);
     }
-    uint32_t inc = s, incv = sv;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        uint32_t u = __shfl_up_sync(0xffffffffu, incv, o);
-        if ((tid & 31) >= o) { inc += t; incv += u; }
-    }
-    if ((tid & 31) == 31) { sm.warp_tot[tid >> 5] = inc; sm.warp_cnt[tid >> 5] = incv; }
-    __syncthreads();
-    uint32_t base = 0;
-    for (int wdx = 0; wdx < (tid >> 5); wdx++) base += sm.warp_tot[wdx];
-    uint32_t ex = base + inc - s;
-#pragma unroll
-    for (int i = 0; i < SCAN_PER; i++) {
-        const int b = SCAN_PER * tid + i;
-        const uint32_t padded = (v[i] + (SEG_ALIGN - 1)) & ~(uint32_t)(SEG_ALIGN - 1);
-        if (b < nb) {
-            sm.off[b] = ex;
-            sm.cnt[b] = ex;                                    // cnt becomes the scatter cursor
-            for (uint32_t q = ex + v[i]; q < ex + padded; q++) sm.staged[q] = (uint16_t)PAD_ENTRY;
-        }
-        ex += padded;
-    }
-    if (tid == COUNT_THREADS - 1) sm.off[nb] = ex;
-    __syncthreads();
-    const uint32_t total_padded = sm.off[nb];
-    // the tile's row of the offset table (in units of SEG_ALIGN entries)
-    uint16_t* trow = table + (size_t)blockIdx.x * (size_t)(nb + 1);
-    for (int i = tid; i <= nb; i += COUNT_THREADS) trow[i] = (uint16_t)(sm.off[i] / SEG_ALIGN);
-    // scatter payloads into bucket order
-    const uint32_t cnt_base = sink.cnt_base;
-    const uint32_t staged_base = (uint32_t)__cvta_generic_to_shared(sm.staged);
-    const uint32_t* rp = sm.raw + tid;
-    const uint32_t n_local = (sink.raw_addr - raw0) / (COUNT_THREADS * 4u);
-    uint32_t n = 0;
-    for (; n + 4 <= n_local; n += 4) {
-        uint32_t idx[4], pos[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) idx[u] = rp[(n + u) * COUNT_THREADS];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos[u]) : "r"(cnt_base + (idx[u] >> (2 * PART_LOW)) * 4u) : "memory");
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(staged_base + pos[u] * 2u), "h"((uint16_t)(idx[u] & (PART_BINS - 1))) : "memory");
-    }
-    for (; n < n_local; n++) {
-        const uint32_t idx = rp[n * COUNT_THREADS];
-        uint32_t pos;
-        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cnt_base + (idx >> (2 * PART_LOW)) * 4u) : "memory");
-        sm.staged[pos] = (uint16_t)(idx & (PART_BINS - 1));
-    }
-    __syncthreads();
-    // coalesced copy of the sorted tile
-    uint4* dst = reinterpret_cast<uint4*>(payload + (size_t)blockIdx.x * TILE_CAP);
+    const unsigned long long total = block_sum_u32(n, &sm.sh_total);       // includes a __syncthreads
+    // bucket-major write: slot (b, t) of this genome at ((b * n_tiles + t) << slot_shift)
+    const uint32_t t_local = blockIdx.x - gt.tile0;
+    uint16_t* pg = payload + (size_t)gt.tile0 * STAGE_ENTRIES;
+    const int vec_shift = slot_shift - 3;                                   // uint4 vectors per slot
     const uint4* src = reinterpret_cast<const uint4*>(sm.staged);
-    const uint32_t nvec = (total_padded + 7) >> 3;
-    for (uint32_t i = tid; i < nvec; i += COUNT_THREADS) dst[i] = src[i];
-    if (tid == 0) {
-        uint32_t total = 0;
-        for (int wdx = 0; wdx < COUNT_THREADS / 32; wdx++) total += sm.warp_cnt[wdx];
-        if (total) atomicAdd(&stats[sl.genome].total_top, (unsigned long long)total);
+    for (int v = tid; v < STAGE_ENTRIES / 8; v += COUNT_THREADS) {
+        const uint32_t b = (uint32_t)v >> vec_shift;
+        const uint32_t o = (uint32_t)v & ((1u << vec_shift) - 1u);
+        uint4* dst = reinterpret_cast<uint4*>(pg + (((size_t)b * gt.n_tiles + t_local) << slot_shift)) + o;
+        *dst = src[v];
     }
+    if (tid == 0 && total) atomicAdd(&stats[sl.genome].total_top, total);
 }
-
-struct GenomeTiles {                   // tiles of one genome inside the group's tile list
-    uint32_t tile0, n_tiles;
-};
 
 struct LevelInfo {                     // per level: index into the caller's k_list (-1: pass-through)
     int ki[16];
 };
 
 constexpr int BUCKET_THREADS = 512;
-constexpr int BUCKET_BATCH = 2048;     // tile segments staged per round
 constexpr int SMALL_LEVEL_BINS = 341;  // 256 + 64 + 16 + 4 + 1: levels k-3 .. k-7 of one bucket
 
 struct BucketSmem {
     uint32_t hist[PART_BINS];          // 64 KB; reused in place by the in-bucket cascade
-    uint32_t seg[BUCKET_BATCH];        // (start | end << 16) of this bucket's segment in each tile
     uint32_t small_tails[SMALL_LEVEL_BINS + 3];   // run-end tails of the small levels, prefetched
     unsigned long long tot[16];
     uint32_t* lvl_counts[16];          // per level: this bucket's slice of the count row
@@ -453,18 +409,20 @@ struct BucketSmem {
 };
 static_assert(sizeof(BucketSmem) <= 74 * 1024, "three bucket CTAs must fit in one SM's shared memory");
 
-__device__ __forceinline__ void hist_add2(uint32_t hbase, uint32_t two) {
-    const uint32_t lo = two & 0xFFFFu, hi = two >> 16;
-    if (lo != PAD_ENTRY) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + lo * 4u) : "memory");
-    if (hi != PAD_ENTRY) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + hi * 4u) : "memory");
+// 8 payload entries of one 128-bit vector: entry e of the slot is valid iff 1 <= e <= cnt
+__device__ __forceinline__ void hist_add8(uint32_t hbase, const uint4& x, uint32_t e0, uint32_t cnt) {
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t ea = e0 + 2 * i, eb = ea + 1;
+        if (ea - 1u < cnt) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + (w[i] & 0xFFFFu) * 4u) : "memory");
+        if (eb - 1u < cnt) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + (w[i] >> 16) * 4u) : "memory");
+    }
 }
-
-constexpr int GATHER_SEGS = 2;         // (tile, bucket) segments a thread keeps in flight
-constexpr int GATHER_VECS = 3;         // 8-byte vectors loaded up front per segment (12 entries)
 
 __global__ void __launch_bounds__(BUCKET_THREADS, 3)
 bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const GenomeTiles* __restrict__ gts,
-              const uint16_t* __restrict__ payload, const uint16_t* __restrict__ table, int nb,
+              const uint16_t* __restrict__ payload, int slot_shift,
               const GenomeStats* __restrict__ stats, float* freq, uint64_t freq_stride, uint64_t* totals,
               uint32_t genome0) {
     extern __shared__ __align__(16) unsigned char bucket_smem_raw[];
@@ -504,7 +462,7 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
         sm.lvl_inv[level] = inv;
     }
     // run-end tails of every lower level of this bucket's subtree: issue the loads now, they
-    // arrive while the histogram is being gathered
+    // arrive while the histogram is being built
     constexpr int PER1 = PART_BINS / 4 / BUCKET_THREADS;          // 8 level-(k-1) bins per thread
     constexpr int PER2 = PART_BINS / 16 / BUCKET_THREADS;         // 2 level-(k-2) bins per thread
     uint32_t tails1[PER1], tails2[PER2];
@@ -521,45 +479,31 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
             sm.small_tails[tid] = level >= k_stop ? lm.ptr(g, level)[(size_t)b * n + (tid - base)] : 0u;
         }
     }
+    // stream this bucket's slots: n_tiles * slot entries, contiguous, 128-bit coalesced loads
     const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sm.hist);
-    for (uint32_t t0 = 0; t0 < gt.n_tiles; t0 += BUCKET_BATCH) {
-        const uint32_t nt = min((uint32_t)BUCKET_BATCH, gt.n_tiles - t0);
-        __syncthreads();
-        for (uint32_t i = tid; i < nt; i += BUCKET_THREADS) {
-            const uint16_t* trow = table + (size_t)(gt.tile0 + t0 + i) * (size_t)(nb + 1) + b;
-            sm.seg[i] = (uint32_t)trow[0] | ((uint32_t)trow[1] << 16);
+    const uint16_t* bp = payload + (size_t)gt.tile0 * STAGE_ENTRIES + (((size_t)b * gt.n_tiles) << slot_shift);
+    const uint4* bp4 = reinterpret_cast<const uint4*>(bp);
+    const int vec_shift = slot_shift - 3;
+    const uint32_t vmask = (1u << vec_shift) - 1u;
+    const uint64_t n_vec = (uint64_t)gt.n_tiles << vec_shift;
+    constexpr int UNROLL = 4;
+    for (uint64_t v0 = tid; v0 < n_vec; v0 += (uint64_t)BUCKET_THREADS * UNROLL) {
+        uint4 x[UNROLL];
+        uint32_t cnt[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const uint64_t v = v0 + (uint64_t)u * BUCKET_THREADS;
+            if (v < n_vec) {
+                x[u] = __ldg(bp4 + v);
+                cnt[u] = __ldg(bp + ((v >> vec_shift) << slot_shift));      // the slot's fill count (entry 0)
+            } else {
+                cnt[u] = 0;
+            }
         }
-        __syncthreads();
-        // a thread owns GATHER_SEGS (tile, bucket) segments per round; their first
-        // GATHER_VECS 8-byte vectors are all loaded before any is consumed
-        for (uint32_t i0 = tid; i0 < nt; i0 += BUCKET_THREADS * GATHER_SEGS) {
-            uint2 x[GATHER_SEGS][GATHER_VECS];
-            uint32_t v0[GATHER_SEGS], v1[GATHER_SEGS];
 #pragma unroll
-            for (int sgi = 0; sgi < GATHER_SEGS; sgi++) {
-                const uint32_t i = i0 + sgi * BUCKET_THREADS;
-                const uint32_t se = i < nt ? sm.seg[i] : 0u;
-                v0[sgi] = se & 0xFFFFu;
-                v1[sgi] = se >> 16;
-                const uint2* src = reinterpret_cast<const uint2*>(payload + (size_t)(gt.tile0 + t0 + i) * TILE_CAP);
-#pragma unroll
-                for (int u = 0; u < GATHER_VECS; u++)
-                    x[sgi][u] = (v0[sgi] + u < v1[sgi]) ? __ldg(src + v0[sgi] + u) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-            }
-#pragma unroll
-            for (int sgi = 0; sgi < GATHER_SEGS; sgi++) {
-#pragma unroll
-                for (int u = 0; u < GATHER_VECS; u++) { hist_add2(hbase, x[sgi][u].x); hist_add2(hbase, x[sgi][u].y); }
-                if (v0[sgi] + GATHER_VECS < v1[sgi]) {                // longer than 12 entries: the rest
-                    const uint32_t i = i0 + sgi * BUCKET_THREADS;
-                    const uint2* src = reinterpret_cast<const uint2*>(payload + (size_t)(gt.tile0 + t0 + i) * TILE_CAP);
-                    for (uint32_t q = v0[sgi] + GATHER_VECS; q < v1[sgi]; q++) {
-                        const uint2 xx = __ldg(src + q);
-                        hist_add2(hbase, xx.x);
-                        hist_add2(hbase, xx.y);
-                    }
-                }
-            }
+        for (int u = 0; u < UNROLL; u++) {
+            const uint64_t v = v0 + (uint64_t)u * BUCKET_THREADS;
+            if (cnt[u]) hist_add8(hbase, x[u], ((uint32_t)v & vmask) * 8u, cnt[u]);
         }
     }
     __syncthreads();
@@ -632,6 +576,34 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
         uint32_t* t = cur; cur = nxt; nxt = t;
         tbase += n_next;
         n_cur = n_next;
+    }
+}
+
+// The windows that found their slot full: add them to level k and to every level of the bucket
+// subtrees (the cascade below k_stop runs after this kernel), then refresh the touched
+// frequencies from the final counts (idempotent, so concurrent duplicates are harmless).
+__global__ void __launch_bounds__(256)
+overflow_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const GenomeDev* __restrict__ gds,
+                const uint32_t* __restrict__ overflow, const unsigned int* __restrict__ ov_counts, uint64_t batch_lo,
+                const GenomeStats* __restrict__ stats, float* freq, uint64_t freq_stride, uint32_t genome0, int pass) {
+    const uint32_t g = genome0 + blockIdx.y;
+    const unsigned int n = ov_counts[g];
+    if (!n) return;
+    const uint32_t* ov = overflow + (gds[g].file_lo - batch_lo);
+    for (unsigned int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const uint32_t idx = ov[i];
+        for (int level = k; level >= k_stop; level--) {
+            const uint32_t x = idx >> (2 * (k - level));
+            uint32_t* c = lm.ptr(g, level);
+            if (pass == 0) {
+                atomicAdd(c + x, 1u);
+            } else if (freq && li.ki[level] >= 0) {
+                const int ki = li.ki[level];
+                unsigned long long t = stats[g].total_top;
+                for (int q = level; q < k; q++) t += stats[g].n_tail[q];
+                freq[(uint64_t)g * freq_stride + row.off[ki] + x] = t ? (float)((double)c[x] * (1.0 / (double)t)) : 0.0f;
+            }
+        }
     }
 }
 
@@ -829,34 +801,61 @@ int launch_count(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice
     return KMERML_OK;
 }
 
+int part_slot_shift(int k) {                  // log2 of the slot size: 32768 / 4^(k-7) entries
+    return 15 - 2 * (k - PART_LOW);
+}
+
 int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles,
-                     int k, int k_bottom, int min_rec, const LevelMap& lm, GenomeStats* d_stats,
-                     uint16_t* d_payload, uint16_t* d_table, cudaStream_t s) {
+                     const void* d_genome_tiles, int k, int k_bottom, int min_rec, const LevelMap& lm,
+                     GenomeStats* d_stats, uint16_t* d_payload, uint32_t* d_overflow, unsigned int* d_ov_counts,
+                     uint64_t batch_lo, cudaStream_t s) {
     if (n_tiles <= 0) return KMERML_OK;
     DenseParams P = make_params(k, min_rec, k > k_bottom, k_bottom);
     const int nb = 1 << (2 * (k - PART_LOW));
-    partition_kernel<<<n_tiles, COUNT_THREADS, sizeof(PartSmem), s>>>(d_fasta, d_genomes, d_tiles, P, lm, d_stats,
-                                                                     d_payload, d_table, nb);
+    partition_kernel<<<n_tiles, COUNT_THREADS, sizeof(PartSmem), s>>>(
+        d_fasta, d_genomes, d_tiles, (const GenomeTiles*)d_genome_tiles, P, lm, d_stats, d_payload, d_overflow,
+        d_ov_counts, batch_lo, nb, part_slot_shift(k));
     KM_CUDA(cudaGetLastError());
     return KMERML_OK;
 }
 
-int launch_bucket(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, const void* d_genome_tiles,
-                  const uint16_t* d_payload, const uint16_t* d_table, const GenomeStats* d_stats, float* d_freq,
-                  uint64_t freq_stride, uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s) {
-    if (n_genomes <= 0) return KMERML_OK;
-    const int nb = 1 << (2 * (k - PART_LOW));
+static LevelInfo make_level_info(const RowSpec& row) {
     LevelInfo li;
     for (int j = 0; j < 16; j++) {
         li.ki[j] = -1;
         for (int i = 0; i < row.nk; i++)
             if (row.k[i] == j) li.ki[j] = i;
     }
+    return li;
+}
+
+int launch_bucket(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, const void* d_genome_tiles,
+                  const uint16_t* d_payload, const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride,
+                  uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s) {
+    if (n_genomes <= 0) return KMERML_OK;
+    const int nb = 1 << (2 * (k - PART_LOW));
+    const LevelInfo li = make_level_info(row);
     const int k_stop = std::max(k - PART_LOW, k_bottom);
     dim3 grid((unsigned)nb, (unsigned)n_genomes);
     bucket_kernel<<<grid, BUCKET_THREADS, sizeof(BucketSmem), s>>>(lm, row, li, k, k_stop,
-        (const GenomeTiles*)d_genome_tiles, d_payload, d_table, nb, d_stats, d_freq, freq_stride, d_totals, genome0);
+        (const GenomeTiles*)d_genome_tiles, d_payload, part_slot_shift(k), d_stats, d_freq, freq_stride, d_totals, genome0);
     KM_CUDA(cudaGetLastError());
+    return KMERML_OK;
+}
+
+int launch_overflow(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, const GenomeDev* d_genomes,
+                    const uint32_t* d_overflow, const unsigned int* d_ov_counts, uint64_t batch_lo,
+                    const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride, uint32_t genome0, int n_genomes,
+                    cudaStream_t s) {
+    if (n_genomes <= 0) return KMERML_OK;
+    const LevelInfo li = make_level_info(row);
+    const int k_stop = std::max(k - PART_LOW, k_bottom);
+    dim3 grid(32, (unsigned)n_genomes);
+    for (int pass = 0; pass < (d_freq ? 2 : 1); pass++) {
+        overflow_kernel<<<grid, 256, 0, s>>>(lm, row, li, k, k_stop, d_genomes, d_overflow, d_ov_counts, batch_lo,
+                                             d_stats, d_freq, freq_stride, genome0, pass);
+        KM_CUDA(cudaGetLastError());
+    }
     return KMERML_OK;
 }
 

@@ -84,13 +84,18 @@ int launch_finalize(const LevelMap& lm, const RowSpec& row, int k_top, bool cano
                     uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s);
 // partition path (k = 9..12)
 constexpr int PART_MIN_K = 9, PART_MAX_K = 12, PART_LOW_BASES = 7;
-constexpr int PART_TILE_CAP = TILE_BYTES + 3 * 1024;    // padded payload entries per tile (dense.cu TILE_CAP)
+constexpr int PART_STAGE_ENTRIES = 32768;               // uint16 payload entries written per tile (64 KB)
 int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles,
-                     int k, int k_bottom, int min_rec, const LevelMap& lm, GenomeStats* d_stats,
-                     uint16_t* d_payload, uint16_t* d_table, cudaStream_t s);
+                     const void* d_genome_tiles, int k, int k_bottom, int min_rec, const LevelMap& lm,
+                     GenomeStats* d_stats, uint16_t* d_payload, uint32_t* d_overflow, unsigned int* d_ov_counts,
+                     uint64_t batch_lo, cudaStream_t s);
 int launch_bucket(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, const void* d_genome_tiles,
-                  const uint16_t* d_payload, const uint16_t* d_table, const GenomeStats* d_stats, float* d_freq,
-                  uint64_t freq_stride, uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s);
+                  const uint16_t* d_payload, const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride,
+                  uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s);
+int launch_overflow(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, const GenomeDev* d_genomes,
+                    const uint32_t* d_overflow, const unsigned int* d_ov_counts, uint64_t batch_lo,
+                    const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride, uint32_t genome0, int n_genomes,
+                    cudaStream_t s);
 int launch_finalize_low(const LevelMap& lm, const RowSpec& row, int k_top, int level_limit,
                         const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride, uint32_t genome0,
                         int n_genomes, cudaStream_t s);
