@@ -310,7 +310,10 @@ struct SlotSink {
         uint32_t pos;
         asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cnt_base + b * 4u) : "memory");
         if (pos < slot_cap) {
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(stage_base + (((b << slot_shift) + 1u + pos) << 1)),
+            // entry e of bucket b lives at position (e + 2b) mod slot: the order inside a slot is
+            // irrelevant, and the rotation spreads the random buckets over all 32 banks
+            const uint32_t phys = (1u + pos + 2u * b) & slot_cap;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(stage_base + (((b << slot_shift) + phys) << 1)),
                          "h"((uint16_t)(idx & (PART_BINS - 1))) : "memory");
         } else {
             ov[atomicAdd(ov_count, 1u)] = idx;        // rare: the slot is full
@@ -375,7 +378,7 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     for (int b = tid; b < nb; b += COUNT_THREADS) {
         const uint32_t c = sm.cnt[b];
         n += c;
-        sm.staged[b << slot_shift] = (uint16_t)(c < sink.slot_cap ? c : sink.slot_cap);
+        sm.staged[(b << slot_shift) + ((2u * b) & sink.slot_cap)] = (uint16_t)(c < sink.slot_cap ? c : sink.slot_cap);
     }
     const unsigned long long total = block_sum_u32(n, &sm.sh_total);       // includes a __syncthreads
     // bucket-major write: slot (b, t) of this genome at ((b * n_tiles + t) << slot_shift)
@@ -409,12 +412,12 @@ struct BucketSmem {
 };
 static_assert(sizeof(BucketSmem) <= 74 * 1024, "three bucket CTAs must fit in one SM's shared memory");
 
-// 8 payload entries of one 128-bit vector: entry e of the slot is valid iff 1 <= e <= cnt
-__device__ __forceinline__ void hist_add8(uint32_t hbase, const uint4& x, uint32_t e0, uint32_t cnt) {
+// 8 payload entries of one 128-bit vector: (rotated) entry e of the slot is valid iff 1 <= e <= cnt
+__device__ __forceinline__ void hist_add8(uint32_t hbase, const uint4& x, uint32_t e0, uint32_t cnt, uint32_t smask) {
     const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const uint32_t ea = e0 + 2 * i, eb = ea + 1;
+        const uint32_t ea = (e0 + 2 * i) & smask, eb = (e0 + 2 * i + 1) & smask;
         if (ea - 1u < cnt) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + (w[i] & 0xFFFFu) * 4u) : "memory");
         if (eb - 1u < cnt) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + (w[i] >> 16) * 4u) : "memory");
     }
@@ -486,6 +489,8 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
     const int vec_shift = slot_shift - 3;
     const uint32_t vmask = (1u << vec_shift) - 1u;
     const uint64_t n_vec = (uint64_t)gt.n_tiles << vec_shift;
+    const uint32_t smask = (1u << slot_shift) - 1u;
+    const uint32_t rot = (2u * b) & smask;                       // partition_kernel's per-bucket rotation
     constexpr int UNROLL = 4;
     for (uint64_t v0 = tid; v0 < n_vec; v0 += (uint64_t)BUCKET_THREADS * UNROLL) {
         uint4 x[UNROLL];
@@ -495,7 +500,7 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
             const uint64_t v = v0 + (uint64_t)u * BUCKET_THREADS;
             if (v < n_vec) {
                 x[u] = __ldg(bp4 + v);
-                cnt[u] = __ldg(bp + ((v >> vec_shift) << slot_shift));      // the slot's fill count (entry 0)
+                cnt[u] = __ldg(bp + ((v >> vec_shift) << slot_shift) + rot);   // the slot's fill count (entry 0)
             } else {
                 cnt[u] = 0;
             }
@@ -503,7 +508,7 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const uint64_t v = v0 + (uint64_t)u * BUCKET_THREADS;
-            if (cnt[u]) hist_add8(hbase, x[u], ((uint32_t)v & vmask) * 8u, cnt[u]);
+            if (cnt[u]) hist_add8(hbase, x[u], ((uint32_t)v & vmask) * 8u - rot, cnt[u], smask);
         }
     }
     __syncthreads();
