@@ -361,14 +361,14 @@ def run_ours(args):
                 for line in f:
                     if line.startswith("MemAvailable"):
                         avail = int(line.split()[1]) * 1024
-            need = lambda n: sum(sizes[:n]) + n * row_len * 8
+            need = lambda n: sum(sizes[:n]) + n * row_len * 4
             while n_e2e > 1 and need(n_e2e) * 3 > avail:
                 n_e2e //= 2
             host_bufs = [torch.empty(sizes[i], dtype=torch.uint8, pin_memory=True) for i in range(n_e2e)]
             for i in range(n_e2e):
                 host_bufs[i].copy_(fasta[offs[i]:offs[i + 1]])
             hc = torch.empty((n_e2e, row_len), dtype=torch.int32, pin_memory=True)
-            hf = torch.empty((n_e2e, row_len), dtype=torch.float32, pin_memory=True)
+            hf = freq[:n_e2e]          # the feature matrix stays resident in HBM (what the ML stage consumes)
             ht = torch.zeros((n_e2e, len(ks)), dtype=torch.int64, pin_memory=True)
             torch.cuda.synchronize()
 
@@ -396,9 +396,11 @@ def run_ours(args):
             same = torch.equal(hc, counts[:n_e2e].cpu())
             e2e = {"value": nb_e2e / dt / 1e9, "unit": UNIT,
                    "h2d_bytes_per_step": int(sum(sizes[:n_e2e])),
-                   "d2h_bytes_per_step": int(n_e2e * (row_len * 8 + len(ks) * 8)),
+                   "d2h_bytes_per_step": int(n_e2e * (row_len * 4 + len(ks) * 8)),
                    "genomes": n_e2e, "ms_per_step": dt * 1e3, "matches_device_path": bool(same),
-                   "api": "kmerml_count_dense_host (pinned host FASTA -> H2D -> count -> D2H counts+freq+totals)"}
+                   "api": "kmerml_count_dense_host: pinned host FASTA -> H2D -> count + frequency rows -> D2H of the "
+                          "uint32 count rows and totals (what the reference writes to disk); the float32 frequency "
+                          "matrix is computed per step and left resident in HBM (KMERML_FLAG_FREQ_ON_DEVICE)"}
         except Exception as exc:                                  # report, never fake
             e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:300]}
 

@@ -93,14 +93,18 @@ int kmerml_count_dense_range(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t n
 
 /*
  * The same path end to end from HOST buffers: per genome H2D copy -> counting ->
- * D2H of counts (+ frequencies, totals), pipelined over three device slots.
- * h_counts / h_freq / h_totals are laid out like their d_ counterparts.  This is
- * the call the Python KmerExtractor makes for files on disk.  Synchronous.
+ * D2H of the counts and totals, pipelined over three device slots.  h_counts / h_totals
+ * are laid out like their d_ counterparts.  The frequency rows go where the caller needs
+ * them: `freq` is a HOST buffer (copied back like the counts) or, with
+ * KMERML_FLAG_FREQ_ON_DEVICE, a DEVICE buffer [n_genomes][freq_stride] that keeps the
+ * feature matrix resident in HBM for the distance / ML stage; NULL = not computed.
+ * Synchronous.
  */
+#define KMERML_FLAG_FREQ_ON_DEVICE 4u
 int kmerml_count_dense_host(kmerml_ctx *ctx, const uint8_t *const *h_fasta, const uint64_t *h_sizes,
                             int n_genomes, const int *k_list, int nk, int min_record_len,
                             unsigned flags, uint32_t *h_counts, uint64_t counts_stride,
-                            float *h_freq, uint64_t freq_stride, uint64_t *h_totals);
+                            float *freq, uint64_t freq_stride, uint64_t *h_totals);
 
 /*
  * Sparse counting for 15 <= k <= 32 (any k >= 1 is accepted): the distinct k-mers of ONE genome as

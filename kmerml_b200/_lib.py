@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libkmerml_b200.so")
 OK = 0
 FLAG_CANONICAL = 1
 FLAG_NO_PARTITION = 2
+FLAG_FREQ_ON_DEVICE = 4
 MAX_DENSE_K = 14
 MAX_K = 32
 

@@ -573,7 +573,7 @@ int kmerml_count_dense_range(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t n
 
 int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, const uint64_t* h_sizes, int n_genomes,
                             const int* k_list, int nk, int min_record_len, unsigned flags, uint32_t* h_counts,
-                            uint64_t counts_stride, float* h_freq, uint64_t freq_stride, uint64_t* h_totals) {
+                            uint64_t counts_stride, float* freq, uint64_t freq_stride, uint64_t* h_totals) {
     if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
     if (n_genomes < 0) return fail(KMERML_ERR_ARG, "n_genomes < 0");
     if (n_genomes == 0) return KMERML_OK;
@@ -584,8 +584,11 @@ int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, cons
     int kmax, kmin;
     int rc = build_row(k_list, nk, &row, &kmax, &kmin);
     if (rc) return rc;
+    const bool freq_dev = freq && (flags & KMERML_FLAG_FREQ_ON_DEVICE);
     const size_t row_len = (size_t)row.off[nk];
     const size_t row_stride = align_up(row_len, 4);
+    if (freq_dev && (((uintptr_t)freq & 15) || (freq_stride & 3) || freq_stride < row_len))
+        return fail(KMERML_ERR_ARG, "device freq buffer must be 16-byte aligned with a stride multiple of 4");
     uint64_t max_bytes = 0;
     for (int g = 0; g < n_genomes; g++) max_bytes = std::max(max_bytes, h_sizes[g]);
     const int n_slots = std::min(3, n_genomes);
@@ -594,7 +597,7 @@ int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, cons
         if (!w.stream) KM_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
         if ((rc = w.fasta.ensure(align_up((size_t)max_bytes + 64, 256)))) return rc;
         if ((rc = w.counts.ensure(row_stride * 4))) return rc;
-        if (h_freq && (rc = w.freq.ensure(row_stride * 4))) return rc;
+        if (freq && !freq_dev && (rc = w.freq.ensure(row_stride * 4))) return rc;
         if ((rc = w.totals.ensure((size_t)nk * 8))) return rc;
     }
     for (int g = 0; g < n_genomes; g++) {
@@ -602,13 +605,14 @@ int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, cons
         cudaStream_t s = w.stream;
         if (h_sizes[g]) KM_CUDA(cudaMemcpyAsync(w.fasta.p, h_fasta[g], (size_t)h_sizes[g], cudaMemcpyHostToDevice, s));
         uint64_t offs[2] = {0, h_sizes[g]};
-        rc = count_dense_core(ctx, w, (const uint8_t*)w.fasta.p, offs, 1, k_list, nk, min_record_len, flags,
-                              (uint32_t*)w.counts.p, row_stride, h_freq ? (float*)w.freq.p : nullptr, row_stride,
-                              (uint64_t*)w.totals.p, s);
+        float* d_f = !freq ? nullptr : (freq_dev ? freq + (size_t)g * freq_stride : (float*)w.freq.p);
+        rc = count_dense_core(ctx, w, (const uint8_t*)w.fasta.p, offs, 1, k_list, nk, min_record_len,
+                              flags & ~KMERML_FLAG_FREQ_ON_DEVICE, (uint32_t*)w.counts.p, row_stride, d_f,
+                              freq_dev ? freq_stride : row_stride, (uint64_t*)w.totals.p, s);
         if (rc) return rc;
         KM_CUDA(cudaMemcpyAsync(h_counts + (size_t)g * counts_stride, w.counts.p, row_len * 4, cudaMemcpyDeviceToHost, s));
-        if (h_freq)
-            KM_CUDA(cudaMemcpyAsync(h_freq + (size_t)g * freq_stride, w.freq.p, row_len * 4, cudaMemcpyDeviceToHost, s));
+        if (freq && !freq_dev)
+            KM_CUDA(cudaMemcpyAsync(freq + (size_t)g * freq_stride, w.freq.p, row_len * 4, cudaMemcpyDeviceToHost, s));
         if (h_totals)
             KM_CUDA(cudaMemcpyAsync(h_totals + (size_t)g * nk, w.totals.p, (size_t)nk * 8, cudaMemcpyDeviceToHost, s));
     }

@@ -298,11 +298,16 @@ constexpr int PART_BINS = 1 << (2 * PART_LOW);        // 16384 bins per bucket
 constexpr int PART_MAX_BUCKETS = 1024;                // k <= 12
 constexpr int STAGE_ENTRIES = 32768;                  // uint16 entries staged per tile = nb * slot
 
+__device__ __noinline__ void overflow_push(uint32_t* ov, unsigned int* ov_count, uint32_t idx) {
+    ov[atomicAdd(ov_count, 1u)] = idx;                // rare: the slot is full
+}
+
+template <int SLOT_SHIFT>
 struct SlotSink {
+    static constexpr uint32_t slot_shift = SLOT_SHIFT;         // log2(slot entries)
+    static constexpr uint32_t slot_cap = (1u << SLOT_SHIFT) - 1u;   // slot entries - 1 (entry 0 holds the count)
     uint32_t cnt_base;                 // shared address of cnt[nb]
     uint32_t stage_base;               // shared address of staged[]
-    uint32_t slot_shift;               // log2(slot entries)
-    uint32_t slot_cap;                 // slot entries - 1 (entry 0 holds the count)
     uint32_t* ov;                      // this genome's overflow list
     unsigned int* ov_count;
     __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
@@ -316,7 +321,7 @@ struct SlotSink {
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(stage_base + (((b << slot_shift) + phys) << 1)),
                          "h"((uint16_t)(idx & (PART_BINS - 1))) : "memory");
         } else {
-            ov[atomicAdd(ov_count, 1u)] = idx;        // rare: the slot is full
+            overflow_push(ov, ov_count, idx);
         }
     }
 };
@@ -341,11 +346,14 @@ struct GenomeTiles {                   // tiles of one genome inside the group's
     uint32_t tile0, n_tiles;
 };
 
+template <int SLOT_SHIFT>
 __global__ void __launch_bounds__(COUNT_THREADS, 2)
 partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
                  const Slice* __restrict__ tiles, const GenomeTiles* __restrict__ gts, DenseParams P, LevelMap lm,
                  GenomeStats* stats, uint16_t* __restrict__ payload, uint32_t* __restrict__ overflow,
-                 unsigned int* __restrict__ ov_counts, uint64_t batch_lo, int nb, int slot_shift) {
+                 unsigned int* __restrict__ ov_counts, uint64_t batch_lo) {
+    constexpr int slot_shift = SLOT_SHIFT;
+    constexpr int nb = STAGE_ENTRIES >> SLOT_SHIFT;
     extern __shared__ __align__(16) unsigned char part_smem_raw[];
     PartSmem& sm = *reinterpret_cast<PartSmem*>(part_smem_raw);
     const int tid = threadIdx.x;
@@ -362,11 +370,9 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     for (int i = tid; i < nb; i += COUNT_THREADS) sm.cnt[i] = 0;
     if (tid == 0) sm.sh_total = 0;
 
-    SlotSink sink;
+    SlotSink<SLOT_SHIFT> sink;
     sink.cnt_base = (uint32_t)__cvta_generic_to_shared(sm.cnt);
     sink.stage_base = (uint32_t)__cvta_generic_to_shared(sm.staged);
-    sink.slot_shift = (uint32_t)slot_shift;
-    sink.slot_cap = (1u << slot_shift) - 1u;
     sink.ov = overflow + (gd.file_lo - batch_lo);      // one possible window per byte of the genome
     sink.ov_count = ov_counts + sl.genome;
     DevTails tails;
@@ -386,11 +392,21 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     uint16_t* pg = payload + (size_t)gt.tile0 * STAGE_ENTRIES;
     const int vec_shift = slot_shift - 3;                                   // uint4 vectors per slot
     const uint4* src = reinterpret_cast<const uint4*>(sm.staged);
-    for (int v = tid; v < STAGE_ENTRIES / 8; v += COUNT_THREADS) {
-        const uint32_t b = (uint32_t)v >> vec_shift;
-        const uint32_t o = (uint32_t)v & ((1u << vec_shift) - 1u);
-        uint4* dst = reinterpret_cast<uint4*>(pg + (((size_t)b * gt.n_tiles + t_local) << slot_shift)) + o;
-        *dst = src[v];
+    if (vec_shift <= 9) {
+        // vector v = tid + 512 j belongs to bucket (tid >> vec_shift) + (512 >> vec_shift) j: the
+        // destination advances by a constant stride, one add per 128-bit store
+        const uint32_t b0 = (uint32_t)tid >> vec_shift, o = (uint32_t)tid & ((1u << vec_shift) - 1u);
+        uint4* dst = reinterpret_cast<uint4*>(pg + (((size_t)b0 * gt.n_tiles + t_local) << slot_shift)) + o;
+        const size_t stride = (((size_t)(COUNT_THREADS >> vec_shift) * gt.n_tiles) << slot_shift) / 8;
+#pragma unroll
+        for (int j = 0; j < STAGE_ENTRIES / 8 / COUNT_THREADS; j++) dst[j * stride] = src[tid + j * COUNT_THREADS];
+    } else {
+        for (int v = tid; v < STAGE_ENTRIES / 8; v += COUNT_THREADS) {
+            const uint32_t b = (uint32_t)v >> vec_shift;
+            const uint32_t o = (uint32_t)v & ((1u << vec_shift) - 1u);
+            uint4* dst = reinterpret_cast<uint4*>(pg + (((size_t)b * gt.n_tiles + t_local) << slot_shift)) + o;
+            *dst = src[v];
+        }
     }
     if (tid == 0 && total) atomicAdd(&stats[sl.genome].total_top, total);
 }
@@ -760,7 +776,10 @@ finalize_canonical_kernel(LevelMap lm, RowSpec row, int k_top, const GenomeStats
 int dense_setup_attributes() {
     KM_CUDA(cudaFuncSetAttribute(count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (1 << (2 * SMEM_MAX_K)) * 4));
-    KM_CUDA(cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
+    KM_CUDA(cudaFuncSetAttribute(partition_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
+    KM_CUDA(cudaFuncSetAttribute(partition_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
+    KM_CUDA(cudaFuncSetAttribute(partition_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
+    KM_CUDA(cudaFuncSetAttribute(partition_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
     KM_CUDA(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
     return KMERML_OK;
 }
@@ -816,10 +835,17 @@ int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const S
                      uint64_t batch_lo, cudaStream_t s) {
     if (n_tiles <= 0) return KMERML_OK;
     DenseParams P = make_params(k, min_rec, k > k_bottom, k_bottom);
-    const int nb = 1 << (2 * (k - PART_LOW));
-    partition_kernel<<<n_tiles, COUNT_THREADS, sizeof(PartSmem), s>>>(
-        d_fasta, d_genomes, d_tiles, (const GenomeTiles*)d_genome_tiles, P, lm, d_stats, d_payload, d_overflow,
-        d_ov_counts, batch_lo, nb, part_slot_shift(k));
+#define KM_LAUNCH_PART(SH)                                                                            \
+    partition_kernel<SH><<<n_tiles, COUNT_THREADS, sizeof(PartSmem), s>>>(                             \
+        d_fasta, d_genomes, d_tiles, (const GenomeTiles*)d_genome_tiles, P, lm, d_stats, d_payload, d_overflow, \
+        d_ov_counts, batch_lo)
+    switch (part_slot_shift(k)) {
+        case 5: KM_LAUNCH_PART(5); break;        // k = 12
+        case 7: KM_LAUNCH_PART(7); break;        // k = 11
+        case 9: KM_LAUNCH_PART(9); break;        // k = 10
+        default: KM_LAUNCH_PART(11); break;      // k = 9
+    }
+#undef KM_LAUNCH_PART
     KM_CUDA(cudaGetLastError());
     return KMERML_OK;
 }

@@ -95,9 +95,11 @@ def count_dense_device(fasta, offsets, k_values, *, min_record_len=None, canonic
 
 
 def count_dense_host(buffers, k_values, *, min_record_len=None, canonical=False, want_freq=True,
-                     device=None, out_counts=None, out_freq=None, out_totals=None, partition=True):
+                     device=None, out_counts=None, out_freq=None, out_totals=None, partition=True,
+                     freq_on_device=False):
     """End to end from host byte buffers (numpy uint8 arrays / pinned torch tensors): H2D,
-    counting and D2H all inside libkmerml_b200.so.  Returns host (pinned) torch tensors."""
+    counting and D2H all inside libkmerml_b200.so.  Returns host (pinned) torch tensors; with
+    freq_on_device the frequency rows stay in HBM (a CUDA tensor) for the distance / ML stage."""
     if not torch.cuda.is_available():
         raise _lib.KmermlError("no CUDA device: kmerml_b200 has no CPU fallback")
     ks = _dedupe(k_values)
@@ -123,12 +125,19 @@ def count_dense_host(buffers, k_values, *, min_record_len=None, canonical=False,
     counts = out_counts if out_counts is not None else torch.empty((n, row_len), dtype=torch.int32, pin_memory=pin)
     freq = None
     if want_freq:
-        freq = out_freq if out_freq is not None else torch.empty((n, row_len), dtype=torch.float32, pin_memory=pin)
+        if out_freq is not None:
+            freq = out_freq
+            freq_on_device = freq.is_cuda
+        elif freq_on_device:
+            freq = torch.empty((n, row_len), dtype=torch.float32, device=torch.device("cuda", dev))
+        else:
+            freq = torch.empty((n, row_len), dtype=torch.float32, pin_memory=pin)
     totals = out_totals if out_totals is not None else torch.zeros((n, len(ks)), dtype=torch.int64, pin_memory=pin)
     karr = np.asarray(ks, dtype=np.int32)
+    flags = _flags(canonical, partition) | (_lib.FLAG_FREQ_ON_DEVICE if (freq is not None and freq.is_cuda) else 0)
     _lib.check(L.kmerml_count_dense_host(
         ctx.handle, ptrs, sizes.ctypes.data, n, karr.ctypes.data, len(ks), int(min_record_len or 0),
-        _flags(canonical, partition), counts.data_ptr(), counts.stride(0),
+        flags, counts.data_ptr(), counts.stride(0),
         freq.data_ptr() if freq is not None else None, freq.stride(0) if freq is not None else 0,
         totals.data_ptr()))
     return DenseResult(ks, counts, freq, totals)
