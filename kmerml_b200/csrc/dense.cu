@@ -486,8 +486,10 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
     constexpr int PER2 = PART_BINS / 16 / BUCKET_THREADS;         // 2 level-(k-2) bins per thread
     uint32_t tails1[PER1], tails2[PER2];
     {
-        const uint32_t* c1 = (k - 1 >= k_stop) ? lm.ptr(g, k - 1) + (size_t)b * (PART_BINS / 4) : nullptr;
-        const uint32_t* c2 = (k - 2 >= k_stop) ? lm.ptr(g, k - 2) + (size_t)b * (PART_BINS / 16) : nullptr;
+        // (a level without a single run-end tail is all zeros: nothing to read)
+        const GenomeStats& gs = stats[g];
+        const uint32_t* c1 = (k - 1 >= k_stop && gs.n_tail[k - 1]) ? lm.ptr(g, k - 1) + (size_t)b * (PART_BINS / 4) : nullptr;
+        const uint32_t* c2 = (k - 2 >= k_stop && gs.n_tail[k - 2]) ? lm.ptr(g, k - 2) + (size_t)b * (PART_BINS / 16) : nullptr;
 #pragma unroll
         for (int u = 0; u < PER1; u++) tails1[u] = c1 ? c1[tid + u * BUCKET_THREADS] : 0u;
 #pragma unroll
@@ -495,7 +497,7 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
         if (tid < SMALL_LEVEL_BINS) {                             // levels k-3 (256 bins) .. k-7 (1 bin)
             int level = k - 3, base = 0, n = 256;
             while (tid >= base + n) { base += n; n >>= 2; level--; }
-            sm.small_tails[tid] = level >= k_stop ? lm.ptr(g, level)[(size_t)b * n + (tid - base)] : 0u;
+            sm.small_tails[tid] = (level >= k_stop && gs.n_tail[level]) ? lm.ptr(g, level)[(size_t)b * n + (tid - base)] : 0u;
         }
     }
     // stream this bucket's slots: n_tiles * slot entries, contiguous, 128-bit coalesced loads
