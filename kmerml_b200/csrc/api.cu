@@ -243,7 +243,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         uint64_t bytes = h_offsets[g + 1] - h_offsets[g];
         uint64_t sb;
         if (use_part) {
-            sb = TILE_BYTES;                                  // one tile per CTA
+            sb = (uint64_t)TILE_BYTES * PART_TILES_PER_SLICE;   // a CTA walks a run of consecutive tiles
         } else if (use_smem) {
             if ((uint64_t)n_genomes >= target) sb = 1ull << 40;
             else sb = align_up(std::max<uint64_t>(total_bytes / target, 4ull * TILE_BYTES), TILE_BYTES);
@@ -261,6 +261,19 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         if (n_slices > 0x7fffffffull) return fail(KMERML_ERR_RANGE, "too many slices");
     }
     first_slice[n_genomes] = (uint32_t)n_slices;
+    // tiles of every genome (partition path: payload slots are addressed by tile)
+    std::vector<uint64_t> first_tile_abs(n_genomes, 0), tile_start(n_genomes + 1, 0);
+    for (int g = 0; g < n_genomes; g++) {
+        uint64_t lo = h_offsets[g], hi = h_offsets[g + 1];
+        if (range_end) { lo = std::max(lo, range_begin); hi = std::min(hi, range_end); }
+        uint64_t nt = 0;
+        if (lo < hi) {
+            first_tile_abs[g] = lo / TILE_BYTES;
+            nt = (hi - 1) / TILE_BYTES - first_tile_abs[g] + 1;
+        }
+        tile_start[g + 1] = tile_start[g] + nt;
+    }
+    if (use_part && tile_start[n_genomes] > 0x7fffffffull) return fail(KMERML_ERR_RANGE, "too many tiles");
 
     // ---- tables: offsets | genomes | stats | slices
     const size_t off_bytes = align_up((size_t)(n_genomes + 1) * 8, 256);
@@ -294,10 +307,12 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
                 h_slices[si].genome = (uint32_t)g;
                 h_slices[si].prev_ok = 0;
                 h_slices[si].prev16 = 0;
-                h_slices[si].pad = 0;
                 // a range cuts whole tiles: clip the slice to it (range_begin is tile-aligned)
                 h_slices[si].begin = range_end ? std::max(b * sb, range_begin) : b * sb;
                 h_slices[si].end = range_end ? std::min((b + 1) * sb, range_end) : (b + 1) * sb;
+                if (use_part)     // skip the empty tiles before the genome's first byte: tiles are numbered from there
+                    h_slices[si].begin = std::max<uint64_t>(h_slices[si].begin, first_tile_abs[g] * TILE_BYTES);
+                h_slices[si].tile0 = (uint32_t)(tile_start[g] + (h_slices[si].begin / TILE_BYTES - first_tile_abs[g]));
                 h_slices[si].hdr_until = 0;
                 si++;
             }
@@ -310,17 +325,19 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     if (use_part) {
         const uint64_t max_tiles = (12ull << 30) / ((uint64_t)PART_STAGE_ENTRIES * 2);
         uint64_t in_group = 0;
-        uint32_t group_tile0 = 0;
+        uint64_t group_tile0 = 0;
         for (int g = 0; g < n_genomes; g++) {
-            uint32_t nt = first_slice[g + 1] - first_slice[g];
+            const uint64_t nt = tile_start[g + 1] - tile_start[g];
             if (in_group && in_group + nt > max_tiles) {
                 group_end.push_back(g);
                 in_group = 0;
-                group_tile0 = first_slice[g];
+                group_tile0 = tile_start[g];
             }
-            h_gtiles[2 * g] = first_slice[g] - group_tile0;
-            h_gtiles[2 * g + 1] = nt;
+            h_gtiles[2 * g] = (uint32_t)(tile_start[g] - group_tile0);
+            h_gtiles[2 * g + 1] = (uint32_t)nt;
             in_group += nt;
+            // tile numbers inside slices are relative to the group's first tile
+            for (uint32_t si = first_slice[g]; si < first_slice[g + 1]; si++) h_slices[si].tile0 -= (uint32_t)group_tile0;
         }
         group_end.push_back(n_genomes);
     }
@@ -342,7 +359,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         const int k_stop = std::max(kmax - PART_LOW_BASES, kmin);
         uint64_t max_group_tiles = 0, max_group_bytes = 0;
         for (size_t gi = 0, g0 = 0; gi < group_end.size(); g0 = group_end[gi], gi++) {
-            max_group_tiles = std::max<uint64_t>(max_group_tiles, first_slice[group_end[gi]] - first_slice[g0]);
+            max_group_tiles = std::max<uint64_t>(max_group_tiles, tile_start[group_end[gi]] - tile_start[g0]);
             max_group_bytes = std::max<uint64_t>(max_group_bytes, h_offsets[group_end[gi]] - h_offsets[g0]);
         }
         // workspace: bucket-major payload slots | overflow lists (one entry per FASTA byte at most) | counters
@@ -730,7 +747,7 @@ int kmerml_first_occurrence(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nb
         h_slices[b].genome = 0;
         h_slices[b].prev_ok = 0;
         h_slices[b].prev16 = 0;
-        h_slices[b].pad = 0;
+        h_slices[b].tile0 = 0;
         h_slices[b].begin = b * sb;
         h_slices[b].end = (b + 1) * sb;
         h_slices[b].hdr_until = 0;

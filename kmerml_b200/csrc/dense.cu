@@ -44,6 +44,10 @@ struct GlobalSink {
         asm volatile("red.global.add.u32 [%0], 1;" ::"l"(__cvta_generic_to_global(top + idx)) : "memory");
         n++;
     }
+    __device__ __forceinline__ void count4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pa, uint64_t pb,
+                                           uint64_t pc, uint64_t pd) {
+        count(a, pa); count(b, pb); count(c, pc); count(d, pd);
+    }
 };
 
 struct SmemSink {
@@ -53,6 +57,10 @@ struct SmemSink {
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(sbase + idx * 4u) : "memory");
         n++;
     }
+    __device__ __forceinline__ void count4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pa, uint64_t pb,
+                                           uint64_t pc, uint64_t pd) {
+        count(a, pa); count(b, pb); count(c, pc); count(d, pd);
+    }
 };
 
 struct FirstSink {
@@ -60,6 +68,10 @@ struct FirstSink {
     uint64_t file_lo;
     __device__ __forceinline__ void count(uint32_t idx, uint64_t pos) {
         atomicMin(first + idx, (uint32_t)(pos - file_lo));
+    }
+    __device__ __forceinline__ void count4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pa, uint64_t pb,
+                                           uint64_t pc, uint64_t pd) {
+        count(a, pa); count(b, pb); count(c, pc); count(d, pd);
     }
 };
 
@@ -89,9 +101,10 @@ struct TileCtx {                      // shared-memory state of the tile loop
 // of the 32-byte chunk, SWAR classification, bit-compaction of clean chunks and
 // header-line detection (phase 1); then either the funnel-shift emission of a clean
 // chunk whose left neighbour is clean too, or the generic byte walker (phase 2).
-template <class Sink, class Tails>
+template <class Sink, class Tails, class PerTile>
 __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, const Genome& g, const Slice& sl,
-                                           const DenseParams& P, Sink& sink, const Tails& tails, const TileCtx& tc) {
+                                           const DenseParams& P, Sink& sink, const Tails& tails, const TileCtx& tc,
+                                           PerTile&& per_tile) {
     const int tid = threadIdx.x;
     if (tid == 0) {
         tc.carry[0] = sl.hdr_until;                         // resolved per slice by slice_header_kernel
@@ -100,14 +113,29 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
         tc.prev_tile[1] = sl.prev16;
     }
     const uint64_t end = sl.end < g.hi ? sl.end : g.hi;
-    for (uint64_t tb = sl.begin; tb < end; tb += TILE_BYTES) {
+    // software pipeline: the chunk of tile i+1 is loaded while tile i is processed
+    auto load_chunk = [&](uint64_t tbx, uint32_t* w) -> bool {
+        const uint64_t cbx = tbx + (uint64_t)tid * CHUNK;
+        if (!(cbx >= g.lo && cbx + CHUNK <= g.hi && tbx < end)) return false;
+        const uint4* src = reinterpret_cast<const uint4*>(buf + cbx);
+#pragma unroll
+        for (int i = 0; i < CHUNK / 16; i++) {
+            uint4 v = __ldg(src + i);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+        return true;
+    };
+    uint32_t w[CHUNK / 4], wn[CHUNK / 4];
+    bool full = load_chunk(sl.begin, w);
+    uint32_t tile_no = 0;
+    for (uint64_t tb = sl.begin; tb < end; tb += TILE_BYTES, tile_no++) {
         tc.flags[tid] = 0;
         __syncthreads();                                    // flags cleared, carry / prev_tile visible
+        const bool full_next = load_chunk(tb + TILE_BYTES, wn);
         const uint64_t cb = tb + (uint64_t)tid * CHUNK;
         const uint64_t cs = cb > g.lo ? cb : g.lo;
         const uint64_t ce = cb + CHUNK < g.hi ? cb + CHUNK : g.hi;
         const bool has = cs < ce;
-        const bool full = has && (ce - cs == CHUNK);
         CleanChunk cc;
         cc.hi = cc.lo = 0; cc.n = 0; cc.nl = 32; cc.last16 = 0;
         bool clean = false;
@@ -116,13 +144,7 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
             atomicMax(&tc.carry[1], (unsigned long long)until);
         };
         if (full) {
-            uint32_t w[CHUNK / 4], y[CHUNK / 4], bad[CHUNK / 4];
-            const uint4* src = reinterpret_cast<const uint4*>(buf + cb);
-#pragma unroll
-            for (int i = 0; i < CHUNK / 16; i++) {
-                uint4 v = __ldg(src + i);
-                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-            }
+            uint32_t y[CHUNK / 4], bad[CHUNK / 4];
             const bool weird = classify_chunk(w, y, bad) != 0;      // anything besides bases and '\n' ?
             clean = !weird && pack_clean(y, bad, cc);
             // only chunks that hold a '>' can start a header line
@@ -159,6 +181,10 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
             tc.prev_tile[1] = cc.last16;
         }
         if (tid == 0) tc.carry[0] = tc.carry[1];
+        per_tile(tile_no);
+        full = full_next;
+#pragma unroll
+        for (int i = 0; i < CHUNK / 4; i++) w[i] = wn[i];
     }
 }
 
@@ -249,7 +275,7 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
         FirstSink sink;
         sink.first = first; sink.file_lo = gd.file_lo;
         NoTails nt;
-        walk_slice(buf, g, sl, P, sink, nt, tc);
+        walk_slice(buf, g, sl, P, sink, nt, tc, [](uint32_t) {});
         return;
     }
     DevTails tails;
@@ -257,12 +283,12 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
     if (MODE == 0) {
         GlobalSink sink;
         sink.top = lm.ptr(sl.genome, P.k); sink.n = 0;
-        walk_slice(buf, g, sl, P, sink, tails, tc);
+        walk_slice(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
         n = sink.n;
     } else {
         SmemSink sink;
         sink.sbase = (uint32_t)__cvta_generic_to_shared(sh_hist); sink.n = 0;
-        walk_slice(buf, g, sl, P, sink, tails, tc);
+        walk_slice(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
         n = sink.n;
     }
     const unsigned long long total = block_sum_u32(n, &sh_total);
@@ -306,22 +332,41 @@ template <int SLOT_SHIFT>
 struct SlotSink {
     static constexpr uint32_t slot_shift = SLOT_SHIFT;         // log2(slot entries)
     static constexpr uint32_t slot_cap = (1u << SLOT_SHIFT) - 1u;   // slot entries - 1 (entry 0 holds the count)
-    uint32_t cnt_base;                 // shared address of cnt[nb]
-    uint32_t stage_base;               // shared address of staged[]
+    // typed shared-memory pointers (not inline asm): the compiler can then keep several windows'
+    // atomics in flight before the first returned position is consumed
+    uint32_t* __restrict__ cnt;        // cnt[nb]
+    uint16_t* __restrict__ staged;     // staged[nb << slot_shift]
     uint32_t* ov;                      // this genome's overflow list
     unsigned int* ov_count;
     __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
         const uint32_t b = idx >> (2 * PART_LOW);
-        uint32_t pos;
-        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cnt_base + b * 4u) : "memory");
+        const uint32_t pos = atomicAdd(cnt + b, 1u);
         if (pos < slot_cap) {
             // entry e of bucket b lives at position (e + 2b) mod slot: the order inside a slot is
             // irrelevant, and the rotation spreads the random buckets over all 32 banks
             const uint32_t phys = (1u + pos + 2u * b) & slot_cap;
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(stage_base + (((b << slot_shift) + phys) << 1)),
-                         "h"((uint16_t)(idx & (PART_BINS - 1))) : "memory");
+            staged[(b << slot_shift) + phys] = (uint16_t)(idx & (PART_BINS - 1));
         } else {
             overflow_push(ov, ov_count, idx);
+        }
+    }
+    // four windows: all four atomics are issued before the first returned position is needed
+    __device__ __forceinline__ void count4(uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3, uint64_t, uint64_t,
+                                           uint64_t, uint64_t) {
+        const uint32_t idx[4] = {i0, i1, i2, i3};
+        uint32_t b[4], pos[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) b[u] = idx[u] >> (2 * PART_LOW);
+#pragma unroll
+        for (int u = 0; u < 4; u++) pos[u] = atomicAdd(cnt + b[u], 1u);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (pos[u] < slot_cap)
+                staged[(b[u] << slot_shift) + ((1u + pos[u] + 2u * b[u]) & slot_cap)] = (uint16_t)(idx[u] & (PART_BINS - 1));
+        if (max(max(pos[0], pos[1]), max(pos[2], pos[3])) >= slot_cap) {       // rare: some slot is full
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (pos[u] >= slot_cap) overflow_push(ov, ov_count, idx[u]);
         }
     }
 };
@@ -347,7 +392,7 @@ struct GenomeTiles {                   // tiles of one genome inside the group's
 };
 
 template <int SLOT_SHIFT>
-__global__ void __launch_bounds__(COUNT_THREADS, 2)
+__global__ void __launch_bounds__(COUNT_THREADS, 3)
 partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
                  const Slice* __restrict__ tiles, const GenomeTiles* __restrict__ gts, DenseParams P, LevelMap lm,
                  GenomeStats* stats, uint16_t* __restrict__ payload, uint32_t* __restrict__ overflow,
@@ -371,43 +416,48 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     if (tid == 0) sm.sh_total = 0;
 
     SlotSink<SLOT_SHIFT> sink;
-    sink.cnt_base = (uint32_t)__cvta_generic_to_shared(sm.cnt);
-    sink.stage_base = (uint32_t)__cvta_generic_to_shared(sm.staged);
+    sink.cnt = sm.cnt;
+    sink.staged = sm.staged;
     sink.ov = overflow + (gd.file_lo - batch_lo);      // one possible window per byte of the genome
     sink.ov_count = ov_counts + sl.genome;
     DevTails tails;
     tails.lm = &lm; tails.st = stats + sl.genome; tails.genome = sl.genome;
-    walk_slice(buf, g, sl, P, sink, tails, tc);         // slice == one tile; ends with __syncthreads
-
-    // fill counts into entry 0 of every slot; windows of the tile
-    unsigned n = 0;
-    for (int b = tid; b < nb; b += COUNT_THREADS) {
-        const uint32_t c = sm.cnt[b];
-        n += c;
-        sm.staged[(b << slot_shift) + ((2u * b) & sink.slot_cap)] = (uint16_t)(c < sink.slot_cap ? c : sink.slot_cap);
-    }
-    const unsigned long long total = block_sum_u32(n, &sm.sh_total);       // includes a __syncthreads
-    // bucket-major write: slot (b, t) of this genome at ((b * n_tiles + t) << slot_shift)
-    const uint32_t t_local = blockIdx.x - gt.tile0;
+    // a slice is a run of consecutive tiles of one genome: the CTA walks them one after the other,
+    // and after each tile writes its 64 KB of slots bucket-major: slot (b, t) of this genome at
+    // ((b * n_tiles + t) << slot_shift)
+    constexpr int vec_shift = slot_shift - 3;                               // uint4 vectors per slot
     uint16_t* pg = payload + (size_t)gt.tile0 * STAGE_ENTRIES;
-    const int vec_shift = slot_shift - 3;                                   // uint4 vectors per slot
     const uint4* src = reinterpret_cast<const uint4*>(sm.staged);
-    if (vec_shift <= 9) {
-        // vector v = tid + 512 j belongs to bucket (tid >> vec_shift) + (512 >> vec_shift) j: the
-        // destination advances by a constant stride, one add per 128-bit store
-        const uint32_t b0 = (uint32_t)tid >> vec_shift, o = (uint32_t)tid & ((1u << vec_shift) - 1u);
-        uint4* dst = reinterpret_cast<uint4*>(pg + (((size_t)b0 * gt.n_tiles + t_local) << slot_shift)) + o;
-        const size_t stride = (((size_t)(COUNT_THREADS >> vec_shift) * gt.n_tiles) << slot_shift) / 8;
-#pragma unroll
-        for (int j = 0; j < STAGE_ENTRIES / 8 / COUNT_THREADS; j++) dst[j * stride] = src[tid + j * COUNT_THREADS];
-    } else {
-        for (int v = tid; v < STAGE_ENTRIES / 8; v += COUNT_THREADS) {
-            const uint32_t b = (uint32_t)v >> vec_shift;
-            const uint32_t o = (uint32_t)v & ((1u << vec_shift) - 1u);
-            uint4* dst = reinterpret_cast<uint4*>(pg + (((size_t)b * gt.n_tiles + t_local) << slot_shift)) + o;
-            *dst = src[v];
+    const uint32_t b0 = (uint32_t)tid >> vec_shift, o = (uint32_t)tid & ((1u << vec_shift) - 1u);
+    const size_t stride = (((size_t)(COUNT_THREADS >> vec_shift) * gt.n_tiles) << slot_shift) / 8;
+    unsigned n = 0;
+    walk_slice(buf, g, sl, P, sink, tails, tc, [&](uint32_t tile_no) {
+        // (the walk of the tile ended with a __syncthreads)
+        for (int b = tid; b < nb; b += COUNT_THREADS) {
+            const uint32_t c = sm.cnt[b];
+            n += c;
+            sm.staged[(b << slot_shift) + ((2u * b) & sink.slot_cap)] = (uint16_t)(c < sink.slot_cap ? c : sink.slot_cap);
+            sm.cnt[b] = 0;
         }
-    }
+        __syncthreads();
+        const uint32_t t_local = sl.tile0 + tile_no - gt.tile0;
+        if (vec_shift <= 9) {
+            // vector v = tid + 512 j belongs to bucket (tid >> vec_shift) + (512 >> vec_shift) j: the
+            // destination advances by a constant stride, one add per 128-bit store
+            uint4* dst = reinterpret_cast<uint4*>(pg + (((size_t)b0 * gt.n_tiles + t_local) << slot_shift)) + o;
+#pragma unroll
+            for (int j = 0; j < STAGE_ENTRIES / 8 / COUNT_THREADS; j++) dst[j * stride] = src[tid + j * COUNT_THREADS];
+        } else {
+            for (int v = tid; v < STAGE_ENTRIES / 8; v += COUNT_THREADS) {
+                const uint32_t b = (uint32_t)v >> vec_shift;
+                const uint32_t oo = (uint32_t)v & ((1u << vec_shift) - 1u);
+                uint4* dst = reinterpret_cast<uint4*>(pg + (((size_t)b * gt.n_tiles + t_local) << slot_shift)) + oo;
+                *dst = src[v];
+            }
+        }
+        // (the next tile's walk starts with a __syncthreads before anything touches staged / cnt)
+    });
+    const unsigned long long total = block_sum_u32(n, &sm.sh_total);
     if (tid == 0 && total) atomicAdd(&stats[sl.genome].total_top, total);
 }
 

@@ -363,14 +363,21 @@ KM_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int s) {                 // bi
 template <class Sink>
 KM_HD void emit_clean(const CleanChunk& c, uint32_t carry16, uint64_t cs, const DenseParams& P, Sink& sink) {
     const uint32_t mask = P.mask;
+    auto window = [&](int j) -> uint32_t {
+        const int sft = 62 - 2 * j;                                        // bit position of base j in hi:lo
+        return (sft >= 32 ? funnel_r(c.hi, carry16, sft - 32) : funnel_r(c.lo, c.hi, sft)) & mask;
+    };
+    auto at = [&](int j) -> uint64_t { return cs + (uint64_t)(j + (j >= c.nl ? 1 : 0)); };   // byte of base j
+    // a clean chunk has >= 31 bases; windows go to the sink four at a time so that a sink with
+    // returning atomics (the partition path) can keep four of them in flight
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int j = 0; j < 31; j++) {                                         // a clean chunk has >= 31 bases
-        const int sft = 62 - 2 * j;                                        // bit position of base j in hi:lo
-        const uint32_t w = sft >= 32 ? funnel_r(c.hi, carry16, sft - 32) : funnel_r(c.lo, c.hi, sft);
-        sink.count(w & mask, cs + (uint64_t)(j + (j >= c.nl ? 1 : 0)));
-    }
+    for (int j = 0; j < 28; j += 4)
+        sink.count4(window(j), window(j + 1), window(j + 2), window(j + 3), at(j), at(j + 1), at(j + 2), at(j + 3));
+    sink.count(window(28), at(28));
+    sink.count(window(29), at(29));
+    sink.count(window(30), at(30));
     if (c.n == 32) sink.count(c.lo & mask, cs + 31);
 }
 

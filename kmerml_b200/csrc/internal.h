@@ -37,7 +37,7 @@ struct Slice {                // unit of work of one CTA: bytes [begin, end) of 
     uint64_t begin, end;      // multiples of the tile size (absolute buffer offsets)
     uint64_t hdr_until;       // slice_header_kernel: `begin` lies in a header line that ends here (else 0)
     uint32_t prev16;          // ... and these are its last 16 bases (the carry of the slice's first chunk)
-    uint32_t pad;
+    uint32_t tile0;           // partition path: index of the slice's first tile in the group's tile list
 };
 
 // Where level j (the 4^j histogram) of genome g lives: inside the caller's counts
@@ -85,6 +85,7 @@ int launch_finalize(const LevelMap& lm, const RowSpec& row, int k_top, bool cano
 // partition path (k = 9..12)
 constexpr int PART_MIN_K = 9, PART_MAX_K = 12, PART_LOW_BASES = 7;
 constexpr int PART_STAGE_ENTRIES = 32768;               // uint16 payload entries written per tile (64 KB)
+constexpr int PART_TILES_PER_SLICE = 8;                 // consecutive tiles one partition CTA walks
 int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles,
                      const void* d_genome_tiles, int k, int k_bottom, int min_rec, const LevelMap& lm,
                      GenomeStats* d_stats, uint16_t* d_payload, uint32_t* d_overflow, unsigned int* d_ov_counts,

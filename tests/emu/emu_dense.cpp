@@ -23,6 +23,9 @@ struct EmuSink {
         n_count++;
         if (first && pos < (*first)[idx]) (*first)[idx] = pos;
     }
+    void count4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pa, uint64_t pb, uint64_t pc, uint64_t pd) {
+        count(a, pa); count(b, pb); count(c, pc); count(d, pd);
+    }
     void tail(int j, uint32_t idx) const { (*tails)[j][idx]++; }
 };
 }  // namespace
