@@ -48,6 +48,10 @@ struct GlobalSink {
                                            uint64_t pc, uint64_t pd) {
         count(a, pa); count(b, pb); count(c, pc); count(d, pd);
     }
+    __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t* p) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) count(w[i], p[i]);
+    }
 };
 
 struct SmemSink {
@@ -61,6 +65,10 @@ struct SmemSink {
                                            uint64_t pc, uint64_t pd) {
         count(a, pa); count(b, pb); count(c, pc); count(d, pd);
     }
+    __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t* p) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) count(w[i], p[i]);
+    }
 };
 
 struct FirstSink {
@@ -72,6 +80,10 @@ struct FirstSink {
     __device__ __forceinline__ void count4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pa, uint64_t pb,
                                            uint64_t pc, uint64_t pd) {
         count(a, pa); count(b, pb); count(c, pc); count(d, pd);
+    }
+    __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t* p) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) count(w[i], p[i]);
     }
 };
 
@@ -354,18 +366,25 @@ struct SlotSink {
     __device__ __forceinline__ void count4(uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3, uint64_t, uint64_t,
                                            uint64_t, uint64_t) {
         const uint32_t idx[4] = {i0, i1, i2, i3};
-        uint32_t b[4], pos[4];
+        place<4>(idx);
+    }
+    __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t*) { place<8>(w); }
+    template <int N>
+    __device__ __forceinline__ void place(const uint32_t* idx) {
+        uint32_t b[N], pos[N], worst = 0;
 #pragma unroll
-        for (int u = 0; u < 4; u++) b[u] = idx[u] >> (2 * PART_LOW);
+        for (int u = 0; u < N; u++) b[u] = idx[u] >> (2 * PART_LOW);
 #pragma unroll
-        for (int u = 0; u < 4; u++) pos[u] = atomicAdd(cnt + b[u], 1u);
+        for (int u = 0; u < N; u++) pos[u] = atomicAdd(cnt + b[u], 1u);
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int u = 0; u < N; u++) {
+            worst = max(worst, pos[u]);
             if (pos[u] < slot_cap)
                 staged[(b[u] << slot_shift) + ((1u + pos[u] + 2u * b[u]) & slot_cap)] = (uint16_t)(idx[u] & (PART_BINS - 1));
-        if (max(max(pos[0], pos[1]), max(pos[2], pos[3])) >= slot_cap) {       // rare: some slot is full
+        }
+        if (worst >= slot_cap) {                                                // rare: some slot is full
 #pragma unroll
-            for (int u = 0; u < 4; u++)
+            for (int u = 0; u < N; u++)
                 if (pos[u] >= slot_cap) overflow_push(ov, ov_count, idx[u]);
         }
     }

@@ -373,8 +373,13 @@ KM_HD void emit_clean(const CleanChunk& c, uint32_t carry16, uint64_t cs, const 
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int j = 0; j < 28; j += 4)
-        sink.count4(window(j), window(j + 1), window(j + 2), window(j + 3), at(j), at(j + 1), at(j + 2), at(j + 3));
+    for (int j = 0; j < 24; j += 8) {
+        const uint32_t wv[8] = {window(j), window(j + 1), window(j + 2), window(j + 3),
+                                window(j + 4), window(j + 5), window(j + 6), window(j + 7)};
+        const uint64_t pv[8] = {at(j), at(j + 1), at(j + 2), at(j + 3), at(j + 4), at(j + 5), at(j + 6), at(j + 7)};
+        sink.count8(wv, pv);
+    }
+    sink.count4(window(24), window(25), window(26), window(27), at(24), at(25), at(26), at(27));
     sink.count(window(28), at(28));
     sink.count(window(29), at(29));
     sink.count(window(30), at(30));

@@ -26,6 +26,7 @@ struct EmuSink {
     void count4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pa, uint64_t pb, uint64_t pc, uint64_t pd) {
         count(a, pa); count(b, pb); count(c, pc); count(d, pd);
     }
+    void count8(const uint32_t* w, const uint64_t* p) { for (int i = 0; i < 8; i++) count(w[i], p[i]); }
     void tail(int j, uint32_t idx) const { (*tails)[j][idx]++; }
 };
 }  // namespace
