@@ -497,14 +497,16 @@ struct BucketSmem {
 };
 static_assert(sizeof(BucketSmem) <= 74 * 1024, "three bucket CTAs must fit in one SM's shared memory");
 
-// 8 payload entries of one 128-bit vector: (rotated) entry e of the slot is valid iff 1 <= e <= cnt
-__device__ __forceinline__ void hist_add8(uint32_t hbase, const uint4& x, uint32_t e0, uint32_t cnt, uint32_t smask) {
+// 8 payload entries of one 128-bit vector.  `valid` has bit i set when entry i of the vector is one of
+// the slot's cnt live entries (see the rotation in SlotSink): one predicate test per entry.
+__device__ __forceinline__ void hist_add8(uint32_t hbase, const uint4& x, uint32_t valid) {
     const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const uint32_t ea = (e0 + 2 * i) & smask, eb = (e0 + 2 * i + 1) & smask;
-        if (ea - 1u < cnt) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + (w[i] & 0xFFFFu) * 4u) : "memory");
-        if (eb - 1u < cnt) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + (w[i] >> 16) * 4u) : "memory");
+        if (valid & (1u << (2 * i)))
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + ((w[i] & 0xFFFFu) << 2)) : "memory");
+        if (valid & (2u << (2 * i)))
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + ((w[i] >> 16) << 2)) : "memory");
     }
 }
 
@@ -595,7 +597,21 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const uint64_t v = v0 + (uint64_t)u * BUCKET_THREADS;
-            if (cnt[u]) hist_add8(hbase, x[u], ((uint32_t)v & vmask) * 8u - rot, cnt[u], smask);
+            if (cnt[u]) {
+                // logical entries 1..cnt are live; entry e sits at position (e + rot) mod slot, so the
+                // live positions are a cyclic interval: build its bit mask once per vector
+                const uint32_t first = (((uint32_t)v & vmask) * 8u - rot) & smask;     // logical index of entry 0 of the vector
+                uint32_t valid;
+                if (slot_shift == 5) {
+                    const uint32_t live = (cnt[u] >= 31u ? 0xFFFFFFFFu : ((2u << cnt[u]) - 1u)) & ~1u;    // bits 1..cnt
+                    valid = __funnelshift_r(live, live, first) & 0xFFu;
+                } else {
+                    valid = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) valid |= ((((first + i) & smask) - 1u) < cnt[u] ? 1u : 0u) << i;
+                }
+                hist_add8(hbase, x[u], valid);
+            }
         }
     }
     __syncthreads();
