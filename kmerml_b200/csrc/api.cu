@@ -204,15 +204,21 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         if (h_offsets[g + 1] - h_offsets[g] >= (1ull << 32))
             return fail(KMERML_ERR_RANGE, "a genome of 4 GiB or more does not fit the 32-bit counters");
     }
-    const bool use_smem = kmax <= SMEM_MAX_K;
-    const bool use_part = kmax >= PART_MIN_K && kmax <= PART_MAX_K && !(flags & KMERML_FLAG_NO_PARTITION);
+    // the level that is actually counted; every lower level comes from the cascade.  k = 8 does not
+    // fit the shared histogram of count_kernel<1> (256 KB), so it is counted as 9-mers through the
+    // partition path (level 9 is a pass-through scratch level) instead of with global atomics
+    const bool part_ok = !(flags & KMERML_FLAG_NO_PARTITION);
+    const bool big = h_offsets[n_genomes] - h_offsets[0] >= (64ull << 20);   // small inputs: fixed costs dominate
+    const int kcount = (kmax == SMEM_MAX_K + 1 && part_ok && big) ? PART_MIN_K : kmax;
+    const bool use_smem = kcount <= SMEM_MAX_K;
+    const bool use_part = kcount >= PART_MIN_K && kcount <= PART_MAX_K && part_ok;
     const bool canonical = (flags & KMERML_FLAG_CANONICAL) != 0;
 
     // ---- level map: requested levels live in the caller's row, the rest in scratch
     LevelMap lm;
     memset(&lm, 0, sizeof(lm));
     unsigned long long scratch_stride = 0;
-    for (int j = kmin; j <= kmax; j++) {
+    for (int j = kmin; j <= kcount; j++) {
         int ki = -1;
         for (int i = 0; i < nk; i++)
             if (row.k[i] == j) ki = i;
@@ -352,11 +358,11 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         if (!rc) rc = launch_slice_headers(d_fasta, d_genomes, d_slices, (int)n_slices, s);
     }
     if (rc) return rc;
-    const int n_cascade = cascade_launches(kmax, kmin);
+    const int n_cascade = cascade_launches(kcount, kmin);
 
     const size_t row_bytes = (size_t)row.off[nk] * 4;
     if (use_part) {
-        const int k_stop = std::max(kmax - PART_LOW_BASES, kmin);
+        const int k_stop = std::max(kcount - PART_LOW_BASES, kmin);
         uint64_t max_group_tiles = 0, max_group_bytes = 0;
         for (size_t gi = 0, g0 = 0; gi < group_end.size(); g0 = group_end[gi], gi++) {
             max_group_tiles = std::max<uint64_t>(max_group_tiles, tile_start[group_end[gi]] - tile_start[g0]);
@@ -375,7 +381,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         // only the levels below kmax collect run-end tails and must start from zero;
         // the top-level row is written in full by the bucket kernel
         for (int i = 0; i < nk; i++)
-            if (row.k[i] < kmax)
+            if (row.k[i] < kcount)
                 KM_CUDA(cudaMemset2DAsync(d_counts + row.off[i], (size_t)counts_stride * 4, 0,
                                           (size_t)(1ull << (2 * row.k[i])) * 4, (size_t)n_genomes, s));
         if (scratch_stride) KM_CUDA(cudaMemsetAsync(lm.scratch, 0, (size_t)scratch_stride * n_genomes * 4, s));
@@ -386,13 +392,13 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
             const uint64_t batch_lo = h_offsets[g0];
             {
                 Prof pr(ctx, s, 4, nt > 0 ? 1 : 0);
-                rc = launch_partition(d_fasta, d_genomes, d_slices + first_slice[g0], nt, d_gtiles, kmax, kmin, min_rec,
+                rc = launch_partition(d_fasta, d_genomes, d_slices + first_slice[g0], nt, d_gtiles, kcount, kmin, min_rec,
                                       lm, d_stats, d_payload, d_overflow, d_ov_counts, batch_lo, s);
             }
             if (rc) return rc;
             {
                 Prof pr(ctx, s, 5, 1);
-                rc = launch_bucket(lm, row, kmax, kmin, d_gtiles, d_payload, d_stats, canonical ? nullptr : d_freq,
+                rc = launch_bucket(lm, row, kcount, kmin, d_gtiles, d_payload, d_stats, canonical ? nullptr : d_freq,
                                    freq_stride, d_totals, (uint32_t)g0, ng, s);
             }
             if (rc) return rc;
@@ -400,7 +406,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
                 const int nh = std::min(32768, g1 - h0);
                 {
                     Prof pr(ctx, s, 3, canonical || !d_freq ? 1 : 2);
-                    rc = launch_overflow(lm, row, kmax, kmin, d_genomes, d_overflow, d_ov_counts, batch_lo, d_stats,
+                    rc = launch_overflow(lm, row, kcount, kmin, d_genomes, d_overflow, d_ov_counts, batch_lo, d_stats,
                                          canonical ? nullptr : d_freq, freq_stride, (uint32_t)h0, nh, s);
                     if (rc) return rc;
                 }
@@ -411,9 +417,9 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
                 }
                 Prof pr(ctx, s, 2, 1);
                 if (canonical)
-                    rc = launch_finalize(lm, row, kmax, true, d_stats, d_freq, freq_stride, d_totals, (uint32_t)h0, nh, s);
+                    rc = launch_finalize(lm, row, kcount, true, d_stats, d_freq, freq_stride, d_totals, (uint32_t)h0, nh, s);
                 else
-                    rc = launch_finalize_low(lm, row, kmax, k_stop, d_stats, d_freq, freq_stride, (uint32_t)h0, nh, s);
+                    rc = launch_finalize_low(lm, row, kcount, k_stop, d_stats, d_freq, freq_stride, (uint32_t)h0, nh, s);
                 if (rc) return rc;
             }
             g0 = g1;
@@ -423,19 +429,19 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         if (scratch_stride) KM_CUDA(cudaMemsetAsync(lm.scratch, 0, (size_t)scratch_stride * n_genomes * 4, s));
         {
             Prof pr(ctx, s, 0, 1);
-            rc = launch_count(d_fasta, d_genomes, d_slices, (int)n_slices, kmax, kmin, min_rec, true, lm, d_stats, s);
+            rc = launch_count(d_fasta, d_genomes, d_slices, (int)n_slices, kcount, kmin, min_rec, true, lm, d_stats, s);
         }
         if (rc) return rc;
         for (int g0 = 0; g0 < n_genomes; g0 += 32768) {
             int ng = std::min(32768, n_genomes - g0);
             {
                 Prof pr(ctx, s, 1, n_cascade);
-                rc = launch_cascade(lm, kmax, kmin, (uint32_t)g0, ng, s);
+                rc = launch_cascade(lm, kcount, kmin, (uint32_t)g0, ng, s);
             }
             if (rc) return rc;
             {
                 Prof pr(ctx, s, 2, 1);
-                rc = launch_finalize(lm, row, kmax, canonical, d_stats, d_freq, freq_stride, d_totals, (uint32_t)g0, ng, s);
+                rc = launch_finalize(lm, row, kcount, canonical, d_stats, d_freq, freq_stride, d_totals, (uint32_t)g0, ng, s);
             }
             if (rc) return rc;
         }
@@ -447,17 +453,17 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
             int ns = (int)(first_slice[g + 1] - first_slice[g]);
             {
                 Prof pr(ctx, s, 0, ns > 0 ? 1 : 0);
-                rc = launch_count(d_fasta, d_genomes, d_slices + first_slice[g], ns, kmax, kmin, min_rec, false, lm, d_stats, s);
+                rc = launch_count(d_fasta, d_genomes, d_slices + first_slice[g], ns, kcount, kmin, min_rec, false, lm, d_stats, s);
             }
             if (rc) return rc;
             {
                 Prof pr(ctx, s, 1, n_cascade);
-                rc = launch_cascade(lm, kmax, kmin, (uint32_t)g, 1, s);
+                rc = launch_cascade(lm, kcount, kmin, (uint32_t)g, 1, s);
             }
             if (rc) return rc;
             {
                 Prof pr(ctx, s, 2, 1);
-                rc = launch_finalize(lm, row, kmax, canonical, d_stats, d_freq, freq_stride, d_totals, (uint32_t)g, 1, s);
+                rc = launch_finalize(lm, row, kcount, canonical, d_stats, d_freq, freq_stride, d_totals, (uint32_t)g, 1, s);
             }
             if (rc) return rc;
         }

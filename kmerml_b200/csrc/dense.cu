@@ -180,7 +180,7 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
             carry16 = tc.prev_tile[1];
         }
         if (has) {
-            if (clean && !in_hdr && prev_ok && P.min_rec == P.k) {
+            if (clean && !in_hdr && prev_ok && P.min_rec <= P.k) {
                 emit_clean(cc, carry16, cs, P, sink);
                 if (ce == g.hi && P.tails) run_end_event(g, g.hi, P, tails);
             } else {

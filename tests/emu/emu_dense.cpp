@@ -135,7 +135,7 @@ static int64_t emu_core(const uint8_t* bytes, uint64_t n, uint64_t base_off, int
                     carry = prev_tile_last16;
                 }
                 if (has) {
-                    if (clean[t] && !in_hdr && prev_ok && P.min_rec == P.k) {
+                    if (clean[t] && !in_hdr && prev_ok && P.min_rec <= P.k) {
                         emit_clean(cc[t], carry, cs, P, sink);       // the path nearly every GPU thread takes
                         if (ce == g.hi && P.tails) run_end_event(g, g.hi, P, sink);
                     } else {

@@ -75,3 +75,15 @@ def test_header_text_that_looks_like_sequence(emu):
                 data = (">r0\n" + "ACGTTGCA" * 12 + "\n" + hdr + "\n" + "GATTACAGATTACAGGATCC" * 8 + "\n").encode()
                 for k in (12,):
                     check(emu, data, k, k, tpt, 1, base_off)
+
+
+def test_counting_one_level_above_the_largest_k(emu):
+    """k = 8 is counted as 9-mers (min_rec stays 8) and cascaded down: every level <= 8 must still be
+    exactly the reference's count with max(k_values) = 8."""
+    rng = random.Random(21)
+    for _ in range(120):
+        data = fuzz_fasta(rng)
+        res = run_emu(emu, data, 9, 8, rng.choice([1, 2, 4, 16]), rng.choice([1, 3]), rng.choice([0, 31, 64]))
+        for j in range(1, 9):
+            assert np.array_equal(oracle.count_dense(data, j, 8), res[j]), j
+        assert np.array_equal(oracle.count_dense(data, 9, 9), res[9])
