@@ -2,6 +2,7 @@
 // orchestration of the dense counting path.  No torch types, no CPU fallback.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -155,6 +156,11 @@ struct Prof {
         ctx->recs.push_back({kind, a, b});
     }
 };
+
+static bool flags_no_tc() {                    // KMERML_NO_TC=1: fp64 CUDA-core Gram kernel instead (debugging)
+    const char* e = getenv("KMERML_NO_TC");
+    return e && e[0] == '1';
+}
 
 static int build_row(const int* k_list, int nk, RowSpec* row, int* kmax, int* kmin) {
     if (!k_list || nk < 1 || nk > 14) return fail(KMERML_ERR_ARG, "k_list must hold 1..14 values");
@@ -694,8 +700,16 @@ int kmerml_pairwise_distance(kmerml_ctx* ctx, const void* d_x, int dtype, uint64
     Workspace& ws = ctx->ws[0];
     int rc = ws.misc.ensure(256 + (size_t)n * n * sizeof(double));
     if (rc) return rc;
-    return launch_pairwise(d_x, dtype, stride, n, m, metric, (double*)((uint8_t*)ws.misc.p + 256), d_out32, d_out64,
-                           (cudaStream_t)stream);
+    double* d_gram = (double*)((uint8_t*)ws.misc.p + 256);
+    // uint32 count rows: exact integer Gram matrix on the tensor cores (tcgen05 kind::i8)
+    if (dtype == 1 && n > 0 && m >= 64 && m % 64 == 0 && !(flags_no_tc())) {
+        rc = ws.part.ensure(gram_tc_workspace(n, m));
+        if (rc) return rc;
+        rc = launch_gram_tc((const uint32_t*)d_x, stride, n, m, ws.part.p, d_gram, (cudaStream_t)stream);
+        if (rc) return rc;
+        return launch_distance_from_gram(d_gram, n, metric, d_out32, d_out64, (cudaStream_t)stream);
+    }
+    return launch_pairwise(d_x, dtype, stride, n, m, metric, d_gram, d_out32, d_out64, (cudaStream_t)stream);
 }
 
 int kmerml_count_sparse(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, int k, int min_record_len,

@@ -215,6 +215,14 @@ __global__ void distance_from_gram_kernel(const double* __restrict__ G, int n, i
     if (D64) D64[idx] = d;
 }
 
+int launch_distance_from_gram(const double* d_gram, int n, int metric, float* d_out32, double* d_out64, cudaStream_t s) {
+    const uint64_t nn = (uint64_t)n * n;
+    if (!nn) return KMERML_OK;
+    distance_from_gram_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(d_gram, n, metric, d_out32, d_out64);
+    KM_CUDA(cudaGetLastError());
+    return KMERML_OK;
+}
+
 int launch_pairwise(const void* d_x, int dtype, uint64_t stride, int n, uint64_t m, int metric, double* d_gram,
                     float* d_out32, double* d_out64, cudaStream_t s) {
     if (n <= 0) return KMERML_OK;

@@ -119,6 +119,10 @@ int launch_record_short(const uint8_t* d_fasta, uint64_t nbytes, const unsigned 
 int launch_static_features(int k, int compat, int32_t* d_out, cudaStream_t s);
 int launch_normalize_rows(const uint32_t* d_counts, uint64_t counts_stride, const uint64_t* d_totals, int n_rows,
                           uint64_t m, float* d_out, uint64_t out_stride, cudaStream_t s);
+size_t gram_tc_workspace(int n, uint64_t m);
+int launch_gram_tc(const uint32_t* d_counts, uint64_t stride, int n, uint64_t m, void* workspace, double* d_gram,
+                   cudaStream_t s);
+int launch_distance_from_gram(const double* d_gram, int n, int metric, float* d_out32, double* d_out64, cudaStream_t s);
 int launch_pairwise(const void* d_x, int dtype, uint64_t stride, int n, uint64_t m, int metric, double* d_gram,
                     float* d_out32, double* d_out64, cudaStream_t s);
 
