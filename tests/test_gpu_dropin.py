@@ -151,3 +151,31 @@ def test_sparse_counts_match_oracle():
         if not canonical:                                  # first-occurrence order = dict insertion order
             order = np.argsort(first.cpu().numpy().view(np.uint32), kind="stable")
             assert keys.cpu().numpy().view(np.uint64)[order].tolist() == ref_codes.tolist()
+
+
+def test_tensor_core_gram_is_exact():
+    """tcgen05 kind::i8 Gram of count rows (uint8 digit planes): distances equal the int64/float64
+    reference to the last bit of the final float64 arithmetic, also with 2- and 3-byte counts and ragged
+    n; the float64 CUDA-core path (float input) agrees within 1e-12."""
+    import torch
+    from kmerml_b200 import engine
+    rng = np.random.default_rng(5)
+    for n, m, hi in ((3, 64, 255), (129, 1024, 256), (77, 4096, 70_000), (260, 16384, 1000)):
+        c = rng.integers(0, hi, size=(n, m), dtype=np.int64)
+        c[rng.integers(0, n)] = 0                                     # an all-zero row -> nan cosine distances
+        x = torch.from_numpy(c.astype(np.uint32).view(np.int32)).cuda()
+        g = (c @ c.T).astype(np.float64)
+        nrm = np.sqrt(np.diag(g))
+        for metric in ("cosine", "euclidean"):
+            got = engine.pairwise_distance_device(x, metric, out_dtype=torch.float64).cpu().numpy()
+            with np.errstate(divide="ignore", invalid="ignore"):
+                if metric == "cosine":
+                    ref = 1.0 - g / (nrm[:, None] * nrm[None, :])
+                else:
+                    ref = np.sqrt(np.maximum(np.diag(g)[:, None] + np.diag(g)[None, :] - 2 * g, 0))
+            np.fill_diagonal(ref, 0.0)
+            ok = np.isclose(got, ref, rtol=1e-13, atol=0, equal_nan=True)
+            assert ok.all(), (n, m, hi, metric, np.abs(got - ref)[~ok][:3])
+            alt = engine.pairwise_distance_device(torch.as_tensor(c.astype(np.float64), device="cuda"), metric,
+                                                  out_dtype=torch.float64).cpu().numpy()
+            assert np.allclose(got, alt, rtol=1e-12, atol=1e-12, equal_nan=True)
