@@ -340,10 +340,21 @@ def run_ours(args):
                             "share_of_step": t * 1e3 / ms_per_step})
     dom = max(kernels, key=lambda d: d["ms_per_step"]) if kernels else None
     n_dom_launch = max(int(prof["count_launches"]) // max(args.steps, 1), 1) if dom and dom["kernel"] in ("partition_kernel", "count_kernel") else 1
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        if dom and dom["kernel"] in tj:
+            # measured DRAM bytes per algorithmic byte (one ncu --set full capture on a 6-genome subset of this
+            # workload), scaled to this launch
+            traffic = tj[dom["kernel"]]["ratio"] * dom["alg_bytes_per_step"] / n_dom_launch
+            traffic_src = tj["source"]
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": dom["kernel"] if dom else None,
         "achieved": dom["achieved"] if dom else 0.0, "peak": peak, "unit": "GB/s",
-        "frac": dom["frac"] if dom else 0.0, "traffic": None, "peak_source": peak_src,
+        "frac": dom["frac"] if dom else 0.0, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "alg_bytes_per_launch": (dom["alg_bytes_per_step"] / n_dom_launch) if dom else None,
         "avg_launch_ms": (dom["ms_per_step"] / n_dom_launch) if dom else None,
         "kernel_share_of_step": dom["share_of_step"] if dom else None,
