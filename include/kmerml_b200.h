@@ -35,6 +35,7 @@ extern "C" {
 #define KMERML_ERR_RANGE (-4)   /* input too large for the 32-bit counters / offsets */
 
 #define KMERML_FLAG_CANONICAL 1u /* count min(kmer, revcomp) -- opt-in extension, not in the reference */
+#define KMERML_FLAG_K8_AS_9 8u      /* k = 8: count 9-mers through the partition path instead of the packed shared histogram */
 #define KMERML_FLAG_NO_PARTITION 2u /* k = 9..12: use the global-atomic kernel instead of the partition path */
 
 #define KMERML_MAX_DENSE_K 14    /* dense 4^k histograms up to here; larger k -> kmerml_count_sparse */

@@ -13,6 +13,7 @@ OK = 0
 FLAG_CANONICAL = 1
 FLAG_NO_PARTITION = 2
 FLAG_FREQ_ON_DEVICE = 4
+FLAG_K8_AS_9 = 8
 MAX_DENSE_K = 14
 MAX_K = 32
 

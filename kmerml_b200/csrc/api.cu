@@ -214,9 +214,10 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     // fit the shared histogram of count_kernel<1> (256 KB), so it is counted as 9-mers through the
     // partition path (level 9 is a pass-through scratch level) instead of with global atomics
     const bool part_ok = !(flags & KMERML_FLAG_NO_PARTITION);
-    const bool big = h_offsets[n_genomes] - h_offsets[0] >= (64ull << 20);   // small inputs: fixed costs dominate
-    const int kcount = (kmax == SMEM_MAX_K + 1 && part_ok && big) ? PART_MIN_K : kmax;
-    const bool use_smem = kcount <= SMEM_MAX_K;
+    // k = 8: packed 16-bit shared histogram (count_kernel<3>); KMERML_FLAG_K8_AS_9 counts 9-mers through
+    // the partition path instead (kept for comparison)
+    const int kcount = (kmax == SMEM_MAX_K + 1 && part_ok && (flags & KMERML_FLAG_K8_AS_9)) ? PART_MIN_K : kmax;
+    const bool use_smem = kcount <= SMEM_MAX_K + 1;
     const bool use_part = kcount >= PART_MIN_K && kcount <= PART_MAX_K && part_ok;
     const bool canonical = (flags & KMERML_FLAG_CANONICAL) != 0;
 

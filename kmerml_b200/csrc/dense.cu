@@ -71,6 +71,44 @@ struct SmemSink {
     }
 };
 
+// k = 8: 65536 bins as packed 16-bit halves of 32768 shared words (128 KB).  A bin that reaches
+// 0x4000 is spilled (0x4000 moved to the global row) by the thread that saw it cross; because the
+// CTA synchronises after every tile (<= 16384 windows) a half can never exceed 0x7FFF, so there is
+// no carry into its neighbour and the counts stay exact for any input.
+struct Packed16Sink {
+    uint32_t* __restrict__ hist;       // shared, 32768 words
+    uint32_t* __restrict__ row;        // this genome's level-8 count row (global)
+    unsigned n;
+    __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
+        const uint32_t sh = (idx & 1u) << 4;
+        const uint32_t old = atomicAdd(hist + (idx >> 1), 1u << sh);
+        n++;
+        if (((old >> sh) & 0xFFFFu) == 0x3FFFu) spill(idx, sh);
+    }
+    __device__ __noinline__ void spill(uint32_t idx, uint32_t sh) {
+        atomicAdd(row + idx, 0x4000u);
+        atomicAdd(hist + (idx >> 1), 0u - (0x4000u << sh));
+    }
+    __device__ __forceinline__ void count4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t, uint64_t, uint64_t,
+                                           uint64_t) {
+        const uint32_t w[4] = {a, b, c, d};
+        place<4>(w);
+    }
+    __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t*) { place<8>(w); }
+    template <int N>
+    __device__ __forceinline__ void place(const uint32_t* idx) {
+        uint32_t old[N];
+#pragma unroll
+        for (int u = 0; u < N; u++) old[u] = atomicAdd(hist + (idx[u] >> 1), 1u << ((idx[u] & 1u) << 4));
+        n += N;
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            const uint32_t sh = (idx[u] & 1u) << 4;
+            if (((old[u] >> sh) & 0xFFFFu) == 0x3FFFu) spill(idx[u], sh);
+        }
+    }
+};
+
 struct FirstSink {
     uint32_t* first;
     uint64_t file_lo;
@@ -258,7 +296,7 @@ __global__ void slice_header_kernel(const uint8_t* __restrict__ buf, const Genom
     slices[i].prev16 = l16;
 }
 
-// MODE 0: global histogram, 1: shared histogram, 2: first occurrence
+// MODE 0: global histogram, 1: shared histogram, 2: first occurrence, 3: packed 16-bit shared histogram (k = 8)
 template <int MODE>
 __global__ void __launch_bounds__(COUNT_THREADS)
 count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
@@ -297,6 +335,12 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
         sink.top = lm.ptr(sl.genome, P.k); sink.n = 0;
         walk_slice(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
         n = sink.n;
+    } else if (MODE == 3) {
+        for (int i = tid; i < 32768; i += COUNT_THREADS) sh_hist[i] = 0;
+        Packed16Sink sink;
+        sink.hist = sh_hist; sink.row = lm.ptr(sl.genome, 8); sink.n = 0;
+        walk_slice(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
+        n = sink.n;
     } else {
         SmemSink sink;
         sink.sbase = (uint32_t)__cvta_generic_to_shared(sh_hist); sink.n = 0;
@@ -310,6 +354,14 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
         for (int i = tid; i < nb; i += COUNT_THREADS) {
             uint32_t v = sh_hist[i];
             if (v) atomicAdd(top + i, v);
+        }
+    }
+    if (MODE == 3) {
+        uint32_t* top = lm.ptr(sl.genome, 8);
+        for (int i = tid; i < 32768; i += COUNT_THREADS) {
+            const uint32_t v = sh_hist[i];
+            if (v & 0xFFFFu) atomicAdd(top + 2 * i, v & 0xFFFFu);
+            if (v >> 16) atomicAdd(top + 2 * i + 1, v >> 16);
         }
     }
     if (tid == 0 && total) atomicAdd(&stats[sl.genome].total_top, total);
@@ -863,6 +915,7 @@ finalize_canonical_kernel(LevelMap lm, RowSpec row, int k_top, const GenomeStats
 int dense_setup_attributes() {
     KM_CUDA(cudaFuncSetAttribute(count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (1 << (2 * SMEM_MAX_K)) * 4));
+    KM_CUDA(cudaFuncSetAttribute(count_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
     KM_CUDA(cudaFuncSetAttribute(partition_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
     KM_CUDA(cudaFuncSetAttribute(partition_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
     KM_CUDA(cudaFuncSetAttribute(partition_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
@@ -902,7 +955,9 @@ int launch_count(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice
                  cudaStream_t s) {
     if (n_slices <= 0) return KMERML_OK;
     DenseParams P = make_params(k, min_rec, k > k_bottom, k_bottom);
-    if (use_smem) {
+    if (use_smem && k == 8) {
+        count_kernel<3><<<n_slices, COUNT_THREADS, 32768 * 4, s>>>(d_fasta, d_genomes, d_slices, P, lm, d_stats, nullptr);
+    } else if (use_smem) {
         size_t smem = (size_t)(1u << (2 * k)) * 4;
         count_kernel<1><<<n_slices, COUNT_THREADS, smem, s>>>(d_fasta, d_genomes, d_slices, P, lm, d_stats, nullptr);
     } else {

@@ -58,7 +58,12 @@ def _device_index(device):
 
 
 def _flags(canonical, partition):
-    return (_lib.FLAG_CANONICAL if canonical else 0) | (0 if partition else _lib.FLAG_NO_PARTITION)
+    """partition: True (default paths), False (global atomics for k = 9..12), "k8as9" (k = 8 counted as
+    9-mers through the partition path instead of the packed shared histogram)."""
+    f = _lib.FLAG_CANONICAL if canonical else 0
+    if partition == "k8as9":
+        return f | _lib.FLAG_K8_AS_9
+    return f | (0 if partition else _lib.FLAG_NO_PARTITION)
 
 
 def count_dense_device(fasta, offsets, k_values, *, min_record_len=None, canonical=False,

@@ -117,6 +117,10 @@ def test_medium_genomes_multi_slice():
     check_against_oracle([g1, g2, g3], [6])
     check_against_oracle([g1, g2, g3], [1, 2, 3, 4, 5, 6, 7])
     check_against_oracle([g1, g2, g3], [8])
+    check_against_oracle([g1, g2, g3], [8, 3], partition="k8as9")
+    # k = 8 packed 16-bit histogram: a homopolymer drives one bin far past 16 bits
+    poly = (">p\n" + ("A" * 80 + "\n") * 4000 + "ACGTTGCA" * 50 + "\n").encode()
+    check_against_oracle([poly, g3], [8, 5])
     check_against_oracle([g1, g3], list(range(1, 13)))
     check_against_oracle([g1, g3], list(range(1, 13)), partition=False)
     check_against_oracle([g1, g2, g3], [11, 9])

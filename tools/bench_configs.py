@@ -37,9 +37,9 @@ def main():
     buf, offs = synth.pack(gs)
     dev = torch.from_numpy(buf).cuda()
     nb3 = n3 * 5_000_000
-    for ks, part in (([8], True), ([7], True), ([9], True)):
+    for ks, part in (([8], True), ([8], "k8as9"), ([7], True), ([9], True)):
         ms = timed(lambda: engine.count_dense_device(dev, offs, ks, partition=part), reps=3)
-        print(f"C3 {n3} x 5 Mbp k={ks}: {ms:.2f} ms  {nb3 / ms / 1e6:.1f} Gbp/s")
+        print(f"C3 {n3} x 5 Mbp k={ks} ({part}): {ms:.2f} ms  {nb3 / ms / 1e6:.1f} Gbp/s")
     res = engine.count_dense_device(dev, offs, [8])
     ms = timed(lambda: engine.pairwise_distance_device(res.counts, "cosine"), reps=3)
     print(f"C3 cosine distance {n3} x {n3} over 65536 features (fp64 Gram): {ms:.2f} ms")
