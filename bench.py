@@ -95,7 +95,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -236,14 +236,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled under load: from the first warm-up step to the end of the timed region
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    t_load = time.time()
     for _ in range(max(args.warmup, 0)):
         step()
     barrier()
     ctx.profile_enable(True)
     ctx.profile_read(reset=True)
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.25)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.time()
@@ -256,7 +258,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     prof = ctx.profile_read(reset=True)
     ctx.profile_enable(False)
-    clocks = sampler.stop(t0, t1)
+    clocks = sampler.stop(t_load, t1)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
