@@ -146,6 +146,13 @@ int kmerml_records_short(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbyte
                          uint32_t n, int min_record_len, uint8_t *d_is_short, void *stream);
 
 /*
+ * Genome tallies of one FASTA file resident in HBM, as kmerml/utils/genome_metadata.py:55-85 computes
+ * them: d_out[0] contigs (records), [1] total_size (symbols of all records), [2] G+C count,
+ * [3] N count (either case).  Asynchronous on `stream`; d_out: uint64[4] device memory.
+ */
+int kmerml_genome_stats(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbytes, uint64_t *d_out, void *stream);
+
+/*
  * Static per-k-mer features (functions of the k-mer string only): replaces the per-row
  * helpers of kmerml/kmers/statistics.py:190-240.  d_out: int32[4^k][8] =
  * {n, A_count, C_count, G_count, T_count, cpg_count, has_repeat, first base}, row index =

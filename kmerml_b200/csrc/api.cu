@@ -676,6 +676,13 @@ int kmerml_records_short(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbyte
                                (cudaStream_t)stream);
 }
 
+int kmerml_genome_stats(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, uint64_t* d_out, void* stream) {
+    if (!ctx || !d_out || (nbytes && !d_fasta)) return fail(KMERML_ERR_ARG, "null pointer argument");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    return launch_genome_stats(d_fasta, nbytes, (unsigned long long*)d_out, (cudaStream_t)stream);
+}
+
 int kmerml_static_features(kmerml_ctx* ctx, int k, int compat, int32_t* d_out, void* stream) {
     if (!ctx || !d_out) return fail(KMERML_ERR_ARG, "null pointer argument");
     if (k < 1 || k > KMERML_MAX_DENSE_K) return fail(KMERML_ERR_ARG, "k out of range");

@@ -72,6 +72,68 @@ int launch_record_short(const uint8_t* d_fasta, uint64_t nbytes, const unsigned 
     return KMERML_OK;
 }
 
+// ----------------------------------------------------------- genome stats
+// contigs / total_size / G+C / N tallies as kmerml/utils/genome_metadata.py:55-85 computes them
+// (upper-cased sequence of every record; len(sequence) counts every symbol, valid base or not).
+// out[0] contigs, out[1] total_size, out[2] gc_count, out[3] n_count.  One thread per 64-byte chunk.
+__global__ void genome_stats_kernel(const uint8_t* __restrict__ buf, uint64_t nbytes, unsigned long long* out) {
+    __shared__ uint64_t s_lo;
+    if (threadIdx.x == 0) s_lo = first_header(buf, 0, nbytes);
+    __syncthreads();
+    Genome g;
+    g.b = buf;
+    g.lo = s_lo;
+    g.hi = nbytes;
+    const uint64_t cb = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 64;
+    const uint64_t cs = cb > g.lo ? cb : g.lo;
+    const uint64_t ce = cb + 64 < g.hi ? cb + 64 : g.hi;
+    unsigned contigs = 0, total = 0, gc = 0, nn = 0;
+    if (cs < ce) {
+        uint64_t until = 0;
+        int in_hdr = (cs > g.lo && pos_in_header(g, cs, &until)) ? 1 : 0;
+        for (uint64_t pos = cs; pos < ce; pos++) {
+            const uint32_t c = buf[pos];
+            if (in_hdr) {
+                if (is_term(c)) in_hdr = 0;
+                continue;
+            }
+            const int code = base_code(c);
+            if (code >= 0) {
+                total++;
+                gc += (code == 1 || code == 2);
+                continue;
+            }
+            const int kind = classify_nonbase(g, pos, c);
+            if (kind == SYM_SKIP) continue;
+            if (kind == SYM_HDR) { contigs++; in_hdr = 1; continue; }
+            total++;
+            nn += ((c & 0xDFu) == (uint32_t)'N');
+        }
+    }
+    // warp then global reduction
+    for (int o = 16; o > 0; o >>= 1) {
+        contigs += __shfl_xor_sync(0xffffffffu, contigs, o);
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+        gc += __shfl_xor_sync(0xffffffffu, gc, o);
+        nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (contigs) atomicAdd(out + 0, (unsigned long long)contigs);
+        if (total) atomicAdd(out + 1, (unsigned long long)total);
+        if (gc) atomicAdd(out + 2, (unsigned long long)gc);
+        if (nn) atomicAdd(out + 3, (unsigned long long)nn);
+    }
+}
+
+int launch_genome_stats(const uint8_t* d_fasta, uint64_t nbytes, unsigned long long* d_out, cudaStream_t s) {
+    KM_CUDA(cudaMemsetAsync(d_out, 0, 4 * sizeof(unsigned long long), s));
+    if (!nbytes) return KMERML_OK;
+    const uint64_t threads = (nbytes + 63) / 64;
+    genome_stats_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(d_fasta, nbytes, d_out);
+    KM_CUDA(cudaGetLastError());
+    return KMERML_OK;
+}
+
 // --------------------------------------------------------- static features
 // out[idx * 8 + f] (int32), idx = lexicographic ACGT index of the k-mer:
 //   0 n (length of the string the features are computed on)   4 T_count

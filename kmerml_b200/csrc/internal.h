@@ -116,6 +116,7 @@ int launch_scan_records(const uint8_t* d_fasta, uint64_t nbytes, int need, unsig
                         uint8_t* d_short, uint32_t cap, uint32_t* d_count, cudaStream_t s);
 int launch_record_short(const uint8_t* d_fasta, uint64_t nbytes, const unsigned long long* d_offsets, uint32_t n,
                         int need, uint8_t* d_short, cudaStream_t s);
+int launch_genome_stats(const uint8_t* d_fasta, uint64_t nbytes, unsigned long long* d_out, cudaStream_t s);
 int launch_static_features(int k, int compat, int32_t* d_out, cudaStream_t s);
 int launch_normalize_rows(const uint32_t* d_counts, uint64_t counts_stride, const uint64_t* d_totals, int n_rows,
                           uint64_t m, float* d_out, uint64_t out_stride, cudaStream_t s);

@@ -252,3 +252,33 @@ def count_sparse_device(fasta, k, *, min_record_len=None, canonical=False, want_
             n = int(nu.value)
             return keys[:n], counts[:n], (first[:n] if want_first else None), int(nw.value)
         cap = int(nu.value)
+
+
+def genome_stats_device(fasta):
+    """{"contigs", "total_size", "gc_content", "n_count"} of one FASTA file on the GPU
+    (the tallies of kmerml/utils/genome_metadata.py:55-85)."""
+    ctx = _lib.context(fasta.device.index)
+    out = torch.zeros(4, dtype=torch.int64, device=fasta.device)
+    stream = torch.cuda.current_stream(fasta.device).cuda_stream
+    _lib.check(_lib.load().kmerml_genome_stats(ctx.handle, fasta.data_ptr() if fasta.numel() else None, fasta.numel(),
+                                               out.data_ptr(), ctypes.c_void_p(stream)))
+    contigs, total, gc, nn = (int(v) for v in out.cpu().tolist())
+    return {"contigs": contigs, "total_size": total, "n_count": nn,
+            "gc_content": (gc / total) * 100 if total > 0 else 0}
+
+
+def kmer_count_stats_device(counts_row, k):
+    """Summary of one k's count vector (int32 storage of uint32) as kmerml/utils/kmer_metadata.py:59-78 reports
+    it for a k{k}.txt file: totals over the OBSERVED k-mers."""
+    c = counts_row.to(torch.int64) & 0xFFFFFFFF
+    obs = c[c > 0]
+    if obs.numel() == 0:
+        return {"k_value": k, "total_kmers": 0, "unique_kmers": 0, "max_count": 0, "min_count": 0,
+                "mean_count": float("nan"), "median_count": float("nan"), "estimated_genome_size": k - 1}
+    srt = torch.sort(obs).values
+    n = srt.numel()
+    median = float(srt[n // 2].item()) if n % 2 else (float(srt[n // 2 - 1].item()) + float(srt[n // 2].item())) / 2.0
+    total = int(obs.sum().item())
+    return {"k_value": k, "total_kmers": total, "unique_kmers": int(n), "max_count": int(srt[-1].item()),
+            "min_count": int(srt[0].item()), "mean_count": total / n, "median_count": median,
+            "estimated_genome_size": total + k - 1}

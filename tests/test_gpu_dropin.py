@@ -179,3 +179,27 @@ def test_tensor_core_gram_is_exact():
             alt = engine.pairwise_distance_device(torch.as_tensor(c.astype(np.float64), device="cuda"), metric,
                                                   out_dtype=torch.float64).cpu().numpy()
             assert np.allclose(got, alt, rtol=1e-12, atol=1e-12, equal_nan=True)
+
+
+def test_genome_and_kmer_metadata():
+    """Genome tallies (genome_metadata.py:55-85) and k-mer file summaries (kmer_metadata.py:59-78) from the GPU."""
+    import torch
+    from kmerml_b200 import engine
+    for c in golden_extract_cases():
+        a = np.frombuffer(c["fasta"], np.uint8) if len(c["fasta"]) else np.zeros(0, np.uint8)
+        dev = torch.from_numpy(a.copy()).cuda() if a.size else torch.zeros(0, dtype=torch.uint8, device="cuda")
+        got = engine.genome_stats_device(dev)
+        want = oracle.genome_stats(c["fasta"])
+        assert got["contigs"] == want["contigs"] and got["total_size"] == want["total_size"], c["name"]
+        assert got["n_count"] == want["n_count"] and got["gc_content"] == want["gc_content"], c["name"]
+    g0 = next(c for c in golden_extract_cases() if c["name"] == "rand07")
+    ks = [k for k in g0["k_values"] if k <= 12]
+    dev = torch.from_numpy(np.frombuffer(g0["fasta"], np.uint8).copy()).cuda()
+    res = engine.count_dense_device(dev, [0, dev.numel()], ks, min_record_len=max(g0["k_values"]), want_freq=False)
+    for k in ks:
+        counts = np.array([int(line.split("\t")[1]) for line in g0["files"][str(k)].splitlines()])
+        s = engine.kmer_count_stats_device(res.counts_of(0, k), k)
+        assert s["total_kmers"] == counts.sum() and s["unique_kmers"] == counts.size
+        assert s["max_count"] == counts.max() and s["min_count"] == counts.min()
+        assert s["mean_count"] == float(counts.mean()) and s["median_count"] == float(np.median(counts))
+        assert s["estimated_genome_size"] == counts.sum() + k - 1
