@@ -292,7 +292,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     const size_t off_bytes = align_up((size_t)(n_genomes + 1) * 8, 256);
     const size_t gen_bytes = align_up((size_t)n_genomes * sizeof(GenomeDev), 256);
     const size_t st_bytes = align_up((size_t)n_genomes * sizeof(GenomeStats), 256);
-    const size_t sl_bytes = align_up((size_t)std::max<uint64_t>(n_slices, 1) * sizeof(Slice), 256);
+    const size_t sl_bytes = align_up((size_t)(n_slices + 1) * sizeof(Slice), 256);   // + 1 scratch entry
     const size_t gt_bytes = align_up((size_t)n_genomes * 8, 256);
     rc = ws.tables.ensure(off_bytes + gen_bytes + st_bytes + sl_bytes + gt_bytes);
     if (rc) return rc;
@@ -330,6 +330,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
                 si++;
             }
         }
+        h_slices[n_slices].genome = 0;                      // scratch entry of launch_slice_headers
     }
     // partition path: genomes are processed in groups whose payload workspace is bounded
     uint32_t* d_gtiles = (uint32_t*)(base + off_bytes + gen_bytes + st_bytes + sl_bytes);
@@ -759,7 +760,7 @@ int kmerml_first_occurrence(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nb
                                                     64ull * TILE_BYTES), TILE_BYTES);
     const uint64_t n_slices = (nbytes - 1) / sb + 1;
     const size_t off_bytes = 256, gen_bytes = 256, st_bytes = 256;
-    const size_t sl_bytes = align_up((size_t)n_slices * sizeof(Slice), 256);
+    const size_t sl_bytes = align_up((size_t)(n_slices + 1) * sizeof(Slice), 256);   // + 1 scratch entry
     int rc = ws.tables.ensure(off_bytes + gen_bytes + st_bytes + sl_bytes);
     if (rc) return rc;
     if ((rc = ws.staging.ensure(off_bytes + sl_bytes))) return rc;
@@ -780,6 +781,7 @@ int kmerml_first_occurrence(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nb
         h_slices[b].end = (b + 1) * sb;
         h_slices[b].hdr_until = 0;
     }
+    h_slices[n_slices].genome = 0;                          // scratch entry of launch_slice_headers
     KM_CUDA(cudaMemcpyAsync(base, hs, off_bytes, cudaMemcpyHostToDevice, s));
     KM_CUDA(cudaMemcpyAsync(base + off_bytes + gen_bytes + st_bytes, h_slices, sl_bytes, cudaMemcpyHostToDevice, s));
     KM_CUDA(cudaEventRecord(ws.staging_free, s));

@@ -271,29 +271,105 @@ __global__ void slice_header_kernel(const uint8_t* __restrict__ buf, const Genom
     g.b = buf;
     g.lo = gd.lo;
     g.hi = gd.hi;
-    uint64_t until = 0;
-    if (!(sl.begin > g.lo && pos_in_header(g, sl.begin, &until))) until = 0;
-    slices[i].hdr_until = until;
-    // the chunk right before the slice: pack it once so that the slice's first chunk can take
-    // the clean path like every other chunk (it must be sequence, not header text)
-    uint32_t ok = 0, l16 = 0;
-    if (sl.begin >= g.lo + CHUNK && sl.begin < g.hi) {
-        uint32_t w[CHUNK / 4], y[CHUNK / 4], bad[CHUNK / 4];
-        const uint4* src = reinterpret_cast<const uint4*>(buf + sl.begin - CHUNK);
+    SliceHead h;
+    slice_head_quick(g, sl.begin, LINE_SCAN_LIMIT, &h);
+    slices[i].hdr_until = h.hdr_until;
+    slices[i].prev_ok = h.prev_ok;
+    slices[i].prev16 = h.prev16;
+    slices[i].line_start = h.line_start;
+    slices[i].scan_last = LS_UNRESOLVED;
+    if (h.line_start == LS_UNRESOLVED) slices[n].genome = 1;     // scratch entry: the long-line passes have work
+}
+
+// Long lines (unwrapped FASTA): a slice whose bounded look-back found no line terminator scans the
+// bytes between the previous slice's start and its own, cooperatively and backwards, for the last one.
+__global__ void __launch_bounds__(256)
+slice_long_scan_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds, Slice* slices, int n) {
+    if (slices[n].genome == 0) return;
+    const int i = blockIdx.x;
+    const Slice sl = slices[i];
+    if (sl.line_start != LS_UNRESOLVED) return;
+    const GenomeDev gd = gds[sl.genome];
+    uint64_t lo = gd.lo;
+    if (i > 0 && slices[i - 1].genome == sl.genome && slices[i - 1].begin > lo) lo = slices[i - 1].begin;
+    __shared__ unsigned long long s_best;                 // 1 + position of the last terminator seen, 0 = none
+    if (threadIdx.x == 0) s_best = 0;
+    __syncthreads();
+    constexpr uint64_t WINDOW = 256 * 64;
+    for (uint64_t wend = sl.begin; wend > lo; wend = wend > WINDOW ? wend - WINDOW : 0) {
+        const uint64_t hi = wend - (uint64_t)threadIdx.x * 64 > wend ? 0 : wend - (uint64_t)threadIdx.x * 64;
+        unsigned long long best = 0;
+        if (hi >= 64 && hi > lo) {                        // the thread's 64 bytes [hi - 64, hi)
+            const uint4* src = reinterpret_cast<const uint4*>(buf + hi - 64);
+            uint4 v[4];
 #pragma unroll
-        for (int j = 0; j < CHUNK / 16; j++) {
-            uint4 v = __ldg(src + j);
-            w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+            for (int j = 0; j < 4; j++) v[j] = __ldg(src + j);
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(v);
+#pragma unroll
+            for (int j = 15; j >= 0; j--) {
+                const uint32_t x = w[j];
+                const uint32_t a = x ^ 0x0A0A0A0Au, c = x ^ 0x0D0D0D0Du;
+                const uint32_t z = (((a - 0x01010101u) & ~a) | ((c - 0x01010101u) & ~c)) & 0x80808080u;
+                if (z && !best) {
+                    // exact test per byte, highest first (the zero-byte trick can flag the byte above a match)
+                    for (int bb = 3; bb >= 0 && !best; bb--) {
+                        const uint32_t ch = (x >> (8 * bb)) & 0xFFu;
+                        const uint64_t pos = hi - 64 + 4 * (uint64_t)j + (uint64_t)bb;
+                        if (is_term(ch) && pos >= lo) best = pos + 1;
+                    }
+                }
+            }
         }
-        CleanChunk pc;
-        uint64_t dummy;
-        if (classify_chunk(w, y, bad) == 0 && pack_clean(y, bad, pc) && !pos_in_header(g, sl.begin - CHUNK, &dummy)) {
-            ok = 1;
-            l16 = pc.last16;
-        }
+        if (best) atomicMax(&s_best, best);
+        if (__syncthreads_or(best != 0)) break;
     }
-    slices[i].prev_ok = ok;
-    slices[i].prev16 = l16;
+    if (threadIdx.x == 0) slices[i].scan_last = s_best ? (uint64_t)s_best : (lo == gd.lo ? gd.lo : LS_UNRESOLVED);
+}
+
+// ... and the line start of every open slice is the running maximum of the line starts known so far
+// (the table is in buffer order).  One CTA scans the table; open slices then get their header verdict.
+__global__ void __launch_bounds__(1024)
+slice_long_resolve_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds, Slice* slices, int n) {
+    if (slices[n].genome == 0) return;
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        unsigned long long v = 0;
+        Slice sl;
+        if (i < n) {
+            sl = slices[i];
+            const uint64_t cand = sl.line_start != LS_UNRESOLVED ? sl.line_start : sl.scan_last;
+            v = cand == LS_UNRESOLVED ? 0ull : (unsigned long long)cand;
+        }
+        // inclusive prefix maximum over the block, then over the chunks seen so far
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o && u > v) v = u;
+        }
+        if (lane == 31) s_warp[wid] = v;
+        __syncthreads();
+        unsigned long long before = s_carry;
+        for (int w = 0; w < wid; w++) before = s_warp[w] > before ? s_warp[w] : before;
+        if (before > v) v = before;
+        __syncthreads();
+        if (tid == 1023) s_carry = v;
+        if (i < n && sl.line_start == LS_UNRESOLVED) {
+            const GenomeDev gd = gds[sl.genome];
+            Genome g;
+            g.b = buf;
+            g.lo = gd.lo;
+            g.hi = gd.hi;
+            const uint64_t ls = v > gd.lo ? (uint64_t)v : gd.lo;
+            const uint64_t until = header_until_from(g, sl.begin, ls);
+            slices[i].hdr_until = until;
+            if (until) slices[i].prev_ok = 0;
+        }
+        __syncthreads();
+    }
 }
 
 // MODE 0: global histogram, 1: shared histogram, 2: first occurrence, 3: packed 16-bit shared histogram (k = 8)
@@ -946,6 +1022,8 @@ int launch_slice_headers(const uint8_t* d_fasta, const GenomeDev* d_genomes, Sli
                          cudaStream_t s) {
     if (n_slices <= 0) return KMERML_OK;
     slice_header_kernel<<<(n_slices + 127) / 128, 128, 0, s>>>(d_fasta, d_genomes, d_slices, n_slices);
+    slice_long_scan_kernel<<<n_slices, 256, 0, s>>>(d_fasta, d_genomes, d_slices, n_slices);
+    slice_long_resolve_kernel<<<1, 1024, 0, s>>>(d_fasta, d_genomes, d_slices, n_slices);
     KM_CUDA(cudaGetLastError());
     return KMERML_OK;
 }

@@ -146,6 +146,38 @@ KM_HD_NOINLINE bool pos_in_header(const Genome& g, uint64_t p, uint64_t* until) 
     return true;
 }
 
+// ---- slice starts: is the first byte of a slice inside a header line? ----------------------------
+// Looking back for the start of the line costs the line's length, and an unwrapped FASTA file holds a
+// whole chromosome on one line.  So the look-back is bounded; slices it leaves open are settled by a
+// cooperative scan of the preceding slice plus a prefix maximum over the slice table (dense.cu).
+constexpr uint64_t LS_UNRESOLVED = ~0ull;
+constexpr uint32_t LINE_SCAN_LIMIT = 1024;
+
+struct SliceHead {
+    uint64_t hdr_until;      // p lies in a header line that ends here (0: it does not / not known yet)
+    uint64_t line_start;     // start of p's line, LS_UNRESOLVED when the bounded look-back gave up
+    uint32_t prev_ok;        // the 32-byte chunk before p is a clean sequence chunk ...
+    uint32_t prev16;         // ... and these are its last 16 bases
+};
+
+// Start of the line that holds p (g.lo < p < g.hi), looking back at most `limit` bytes.
+KM_HD_NOINLINE bool line_start_bounded(const Genome& g, uint64_t p, uint64_t limit, uint64_t* out) {
+    const uint64_t stop = (p - g.lo > limit) ? p - limit : g.lo;
+    uint64_t ls = p;
+    while (ls > stop && !is_term(g.b[ls - 1])) ls--;
+    if (ls > g.lo && !is_term(g.b[ls - 1])) return false;
+    *out = ls;
+    return true;
+}
+
+// p's line starts at ls: 0 when that is a sequence line (or p is its first byte), else the header's end.
+KM_HD_NOINLINE uint64_t header_until_from(const Genome& g, uint64_t p, uint64_t ls) {
+    if (ls >= p || g.b[ls] != (uint8_t)'>') return 0;
+    uint64_t e = p;
+    while (e < g.hi && !is_term(g.b[e])) e++;
+    return e + 1;
+}
+
 // First header line at or after `from` (used to skip text before the first record).
 KM_HD_NOINLINE uint64_t first_header(const uint8_t* b, uint64_t from, uint64_t hi) {
     uint64_t p = from;
@@ -410,6 +442,45 @@ KM_HD void find_headers(const Genome& g, uint64_t cs, uint64_t ce, F&& on_header
         while (e < g.hi && !is_term(g.b[e])) e++;
         on_header(pos, e + 1);
         pos = e;                                         // nothing inside a header line starts a record
+    }
+}
+
+// First pass over one slice start p (one thread per slice).
+KM_HD_NOINLINE void slice_head_quick(const Genome& g, uint64_t p, uint64_t limit, SliceHead* h) {
+    h->hdr_until = 0;
+    h->prev_ok = 0;
+    h->prev16 = 0;
+    h->line_start = g.lo;                 // nothing of the genome lies before p: by convention
+    if (p <= g.lo || p >= g.hi) return;
+    uint64_t ls = 0;
+    const bool known = line_start_bounded(g, p, limit, &ls);
+    h->line_start = known ? ls : LS_UNRESOLVED;
+    if (known) h->hdr_until = header_until_from(g, p, ls);
+    if (p < g.lo + CHUNK) return;
+    // the chunk right before the slice: packed once so that the slice's first chunk can take the clean
+    // path like every other chunk (it must be sequence, not header text made of base letters)
+    uint32_t w[CHUNK / 4], y[CHUNK / 4], bad[CHUNK / 4];
+    const uint64_t pp = p - CHUNK;
+    for (int j = 0; j < CHUNK / 4; j++) {
+        const uint8_t* q = g.b + pp + 4 * j;
+        w[j] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+    }
+    CleanChunk pc;
+    if (classify_chunk(w, y, bad) != 0 || !pack_clean(y, bad, pc)) return;
+    bool in_hdr;
+    if (!known) {
+        in_hdr = false;                   // same line as p (limit >= CHUNK): the table pass clears prev_ok if it is a header
+    } else if (ls <= pp) {
+        in_hdr = ls < pp && g.b[ls] == (uint8_t)'>';
+    } else {                              // a line ends inside the chunk: pp belongs to the line before
+        uint64_t ls2 = 0;
+        if (pp <= g.lo) in_hdr = false;
+        else if (!line_start_bounded(g, pp, limit, &ls2)) in_hdr = true;        // give up: generic path
+        else in_hdr = ls2 < pp && g.b[ls2] == (uint8_t)'>';
+    }
+    if (!in_hdr) {
+        h->prev_ok = 1;
+        h->prev16 = pc.last16;
     }
 }
 

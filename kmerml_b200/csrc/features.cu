@@ -76,6 +76,9 @@ int launch_record_short(const uint8_t* d_fasta, uint64_t nbytes, const unsigned 
 // contigs / total_size / G+C / N tallies as kmerml/utils/genome_metadata.py:55-85 computes them
 // (upper-cased sequence of every record; len(sequence) counts every symbol, valid base or not).
 // out[0] contigs, out[1] total_size, out[2] gc_count, out[3] n_count.  One thread per 64-byte chunk.
+// No thread needs to know whether its chunk starts inside a header line: every byte is tallied as if
+// it were sequence, and the thread that meets a header start ('>' at a line start) walks that one line
+// and takes its bytes' tallies back out.  The sums wrap mod 2^64, so the order does not matter.
 __global__ void genome_stats_kernel(const uint8_t* __restrict__ buf, uint64_t nbytes, unsigned long long* out) {
     __shared__ uint64_t s_lo;
     if (threadIdx.x == 0) s_lo = first_header(buf, 0, nbytes);
@@ -87,28 +90,26 @@ __global__ void genome_stats_kernel(const uint8_t* __restrict__ buf, uint64_t nb
     const uint64_t cb = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 64;
     const uint64_t cs = cb > g.lo ? cb : g.lo;
     const uint64_t ce = cb + 64 < g.hi ? cb + 64 : g.hi;
-    unsigned contigs = 0, total = 0, gc = 0, nn = 0;
-    if (cs < ce) {
-        uint64_t until = 0;
-        int in_hdr = (cs > g.lo && pos_in_header(g, cs, &until)) ? 1 : 0;
-        for (uint64_t pos = cs; pos < ce; pos++) {
-            const uint32_t c = buf[pos];
-            if (in_hdr) {
-                if (is_term(c)) in_hdr = 0;
-                continue;
-            }
-            const int code = base_code(c);
-            if (code >= 0) {
-                total++;
-                gc += (code == 1 || code == 2);
-                continue;
-            }
-            const int kind = classify_nonbase(g, pos, c);
-            if (kind == SYM_SKIP) continue;
-            if (kind == SYM_HDR) { contigs++; in_hdr = 1; continue; }
-            total++;
-            nn += ((c & 0xDFu) == (uint32_t)'N');
+    unsigned contigs = 0, total = 0, gc = 0, nn = 0;     // wrap-around arithmetic (see above)
+    auto tally = [&](uint64_t pos, unsigned sign) -> bool {          // true: a header line starts at pos
+        const uint32_t c = buf[pos];
+        const int code = base_code(c);
+        if (code >= 0) {
+            total += sign;
+            gc += (code == 1 || code == 2) ? sign : 0u;
+            return false;
         }
+        const int kind = classify_nonbase(g, pos, c);
+        if (kind == SYM_SKIP) return false;
+        if (kind == SYM_HDR) return true;
+        total += sign;
+        nn += ((c & 0xDFu) == (uint32_t)'N') ? sign : 0u;
+        return false;
+    };
+    for (uint64_t pos = cs; pos < ce; pos++) {
+        if (!tally(pos, 1u)) continue;
+        contigs++;
+        for (uint64_t q = pos + 1; q < g.hi && !is_term(buf[q]); q++) tally(q, 0u - 1u);
     }
     // warp then global reduction
     for (int o = 16; o > 0; o >>= 1) {

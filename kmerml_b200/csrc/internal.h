@@ -38,6 +38,8 @@ struct Slice {                // unit of work of one CTA: bytes [begin, end) of 
     uint64_t hdr_until;       // slice_header_kernel: `begin` lies in a header line that ends here (else 0)
     uint32_t prev16;          // ... and these are its last 16 bases (the carry of the slice's first chunk)
     uint32_t tile0;           // partition path: index of the slice's first tile in the group's tile list
+    uint64_t line_start;      // slice_header_kernel: start of the line holding `begin` (LS_UNRESOLVED: long line)
+    uint64_t scan_last;       // slice_long_scan_kernel: last line start inside the slice before (long lines only)
 };
 
 // Where level j (the 4^j histogram) of genome g lives: inside the caller's counts
@@ -71,6 +73,7 @@ constexpr int SMEM_MAX_K = 7;                      // 4^7 * 4 B = 64 KB shared h
 
 int launch_prologue(const uint8_t* d_fasta, const uint64_t* d_offsets, GenomeDev* d_genomes,
                     GenomeStats* d_stats, int n_genomes, cudaStream_t s);
+// d_slices holds n_slices + 1 entries: the last one is scratch (its `genome` field must be 0 on entry).
 int launch_slice_headers(const uint8_t* d_fasta, const GenomeDev* d_genomes, Slice* d_slices, int n_slices,
                          cudaStream_t s);
 int launch_count(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices,

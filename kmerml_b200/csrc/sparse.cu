@@ -36,70 +36,108 @@ __device__ __forceinline__ void sparse_push(uint64_t fwd, uint64_t rc, const Spa
     }
 }
 
-// One thread per 32-byte chunk, owning the windows whose last base lies in it; the start state
-// comes from a backward walk over global memory (same rules as fasta_walk.cuh's generic path).
-__global__ void __launch_bounds__(256)
-sparse_emit_kernel(const uint8_t* __restrict__ buf, uint64_t nbytes, SparseParams P, uint64_t* keys, uint32_t* ends,
-                   unsigned long long* cursor, uint64_t cap) {
+constexpr int SPARSE_THREADS = 256;
+constexpr int SPARSE_TILE = SPARSE_THREADS * CHUNK;          // 8 KB
+constexpr int SPARSE_TILES_PER_SLICE = 16;                   // one CTA walks 128 KB
+
+__global__ void sparse_setup_kernel(const uint8_t* __restrict__ buf, uint64_t nbytes, GenomeDev* gd, Slice* slices,
+                                    int n_slices) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        gd->file_lo = 0;
+        gd->lo = first_header(buf, 0, nbytes);       // text before the first header line is ignored
+        gd->hi = nbytes;
+    }
+    if (i <= n_slices) {                             // entry n_slices = scratch of launch_slice_headers
+        Slice sl;
+        sl.genome = 0; sl.prev_ok = 0; sl.prev16 = 0; sl.tile0 = 0; sl.hdr_until = 0;
+        sl.begin = (uint64_t)i * SPARSE_TILE * SPARSE_TILES_PER_SLICE;
+        sl.end = sl.begin + (uint64_t)SPARSE_TILE * SPARSE_TILES_PER_SLICE;
+        sl.line_start = 0; sl.scan_last = 0;
+        slices[i] = sl;
+    }
+}
+
+// One thread per 32-byte chunk, owning the windows whose last base lies in it; the k-1 bases before
+// the chunk come from a backward walk over global memory (same rules as fasta_walk.cuh's generic
+// path).  Whether a chunk starts inside a header line is settled per tile: the slice table says so for
+// the slice's first byte, and header lines that start inside the tile flag the chunks they cover.
+__global__ void __launch_bounds__(SPARSE_THREADS)
+sparse_emit_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds, const Slice* __restrict__ slices,
+                   SparseParams P, uint64_t* keys, uint32_t* ends, unsigned long long* cursor, uint64_t cap) {
+    __shared__ uint8_t s_flags[SPARSE_THREADS];
+    __shared__ unsigned long long s_carry[2];
+    const int tid = threadIdx.x;
+    const Slice sl = slices[blockIdx.x];
+    const GenomeDev gd = gds[0];
     Genome g;
     g.b = buf;
-    g.hi = nbytes;
-    g.lo = 0;
-    // text before the first header line is ignored: every thread needs the same g.lo
-    __shared__ uint64_t s_lo;
-    if (threadIdx.x == 0) s_lo = first_header(buf, 0, nbytes);
-    __syncthreads();
-    g.lo = s_lo;
-    const uint64_t cb = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * CHUNK;
-    const uint64_t cs = cb > g.lo ? cb : g.lo;
-    const uint64_t ce = cb + CHUNK < g.hi ? cb + CHUNK : g.hi;
-    if (cs >= ce) return;
-    uint64_t until = 0;
-    int in_hdr = (cs > g.lo && pos_in_header(g, cs, &until)) ? 1 : 0;
-    uint64_t fwd = 0, rc = 0;
-    int run = 0, rec_known = 0;
+    g.lo = gd.lo;
+    g.hi = gd.hi;
+    if (tid == 0) s_carry[0] = s_carry[1] = sl.hdr_until;
     const int rcshift = 2 * (P.k - 1);
-    if (!in_hdr && cs > g.lo) {
-        // the up to k-1 valid bases right before the chunk, oldest first
-        uint64_t q = cs;
-        uint32_t codes[32];
-        int cnt = 0;
-        while (cnt < P.k - 1) {
-            int kind = prev_symbol(g, q);
-            if (kind > 3) break;
-            codes[cnt++] = (uint32_t)kind;
+    const uint64_t end = sl.end < g.hi ? sl.end : g.hi;
+    for (uint64_t tb = sl.begin; tb < end; tb += SPARSE_TILE) {
+        s_flags[tid] = 0;
+        __syncthreads();
+        const uint64_t cb = tb + (uint64_t)tid * CHUNK;
+        const uint64_t cs = cb > g.lo ? cb : g.lo;
+        const uint64_t ce = cb + CHUNK < g.hi ? cb + CHUNK : g.hi;
+        const bool has = cs < ce;
+        if (has) {
+            find_headers(g, cs, ce, [&](uint64_t, uint64_t until) {
+                for (int j = tid + 1; j < SPARSE_THREADS && tb + (uint64_t)j * CHUNK < until; j++) s_flags[j] = 1;
+                atomicMax(&s_carry[1], (unsigned long long)until);
+            });
         }
-        for (int i = cnt - 1; i >= 0; i--) {
-            fwd = ((fwd << 2) | codes[i]) & P.mask;
-            rc = (rc >> 2) | ((uint64_t)(3u - codes[i]) << rcshift);
-        }
-        run = cnt;
-    }
-    for (uint64_t pos = cs; pos < ce; pos++) {
-        const uint32_t c = buf[pos];
-        const int code = base_code(c);
-        if (code >= 0 && !in_hdr) {
-            fwd = ((fwd << 2) | (uint64_t)code) & P.mask;
-            rc = (rc >> 2) | ((uint64_t)(3 - code) << rcshift);
-            run++;
-            if (run >= P.k) {
-                if (P.min_rec > P.k) {
-                    if (rec_known == 0) rec_known = (run >= P.min_rec || record_len_at_least(g, pos, P.min_rec)) ? 1 : 2;
-                    if (rec_known == 2) continue;
-                }
-                sparse_push(fwd, rc, P, pos, keys, ends, cursor, cap);
+        __syncthreads();
+        int in_hdr = (s_flags[tid] || cs < s_carry[0]) ? 1 : 0;
+        uint64_t fwd = 0, rc = 0;
+        int run = 0, rec_known = 0;
+        if (has && !in_hdr && cs > g.lo) {
+            // the up to k-1 valid bases right before the chunk, oldest first
+            uint64_t q = cs;
+            uint32_t codes[32];
+            int cnt = 0;
+            while (cnt < P.k - 1) {
+                int kind = prev_symbol(g, q);
+                if (kind > 3) break;
+                codes[cnt++] = (uint32_t)kind;
             }
-            continue;
+            for (int i = cnt - 1; i >= 0; i--) {
+                fwd = ((fwd << 2) | codes[i]) & P.mask;
+                rc = (rc >> 2) | ((uint64_t)(3u - codes[i]) << rcshift);
+            }
+            run = cnt;
         }
-        if (in_hdr) {
-            if (is_term(c)) in_hdr = 0;
-            continue;
+        for (uint64_t pos = cs; pos < ce; pos++) {
+            const uint32_t c = buf[pos];
+            const int code = base_code(c);
+            if (code >= 0 && !in_hdr) {
+                fwd = ((fwd << 2) | (uint64_t)code) & P.mask;
+                rc = (rc >> 2) | ((uint64_t)(3 - code) << rcshift);
+                run++;
+                if (run >= P.k) {
+                    if (P.min_rec > P.k) {
+                        if (rec_known == 0) rec_known = (run >= P.min_rec || record_len_at_least(g, pos, P.min_rec)) ? 1 : 2;
+                        if (rec_known == 2) continue;
+                    }
+                    sparse_push(fwd, rc, P, pos, keys, ends, cursor, cap);
+                }
+                continue;
+            }
+            if (in_hdr) {
+                if (is_term(c)) in_hdr = 0;
+                continue;
+            }
+            const int kind = classify_nonbase(g, pos, c);
+            if (kind == SYM_SKIP) continue;
+            run = 0;
+            fwd = rc = 0;
+            if (kind == SYM_HDR) { in_hdr = 1; rec_known = 0; }
         }
-        const int kind = classify_nonbase(g, pos, c);
-        if (kind == SYM_SKIP) continue;
-        run = 0;
-        fwd = rc = 0;
-        if (kind == SYM_HDR) { in_hdr = 1; rec_known = 0; }
+        __syncthreads();
+        if (tid == 0) s_carry[0] = s_carry[1];
     }
 }
 
@@ -115,6 +153,8 @@ struct SparseWork {
     uint32_t* ends_b;
     unsigned long long* cursor;
     unsigned long long* n_runs;
+    GenomeDev* genome;
+    Slice* slices;
     void* temp;
     size_t temp_bytes;
 };
@@ -134,6 +174,9 @@ size_t sparse_workspace(uint64_t cap, SparseWork* w, uint8_t* base) {
     local.ends_b = (uint32_t*)take(cap * 4);
     local.cursor = (unsigned long long*)take(256);
     local.n_runs = (unsigned long long*)take(256);
+    local.genome = (GenomeDev*)take(256);
+    // cap bounds the number of FASTA bytes (callers size it so); one slice entry per 128 KB + scratch
+    local.slices = (Slice*)take((cap / ((uint64_t)SPARSE_TILE * SPARSE_TILES_PER_SLICE) + 3) * sizeof(Slice));
     size_t t1 = 0, t2 = 0, t3 = 0;
     cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
     cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
@@ -163,9 +206,17 @@ int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, int k, int min_rec, bool
     *h_unique = 0;
     *h_windows = 0;
     if (!nbytes) return KMERML_OK;
-    const uint64_t chunks = (nbytes + CHUNK - 1) / CHUNK;
-    sparse_emit_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(d_fasta, nbytes, P, w.keys_a, w.ends_a,
-                                                                       w.cursor, cap);
+    const uint64_t slice_bytes = (uint64_t)SPARSE_TILE * SPARSE_TILES_PER_SLICE;
+    const int n_slices = (int)((nbytes + slice_bytes - 1) / slice_bytes);
+    if ((uint64_t)n_slices > cap / slice_bytes + 2) {
+        set_error("internal: sparse slice table too small");
+        return KMERML_ERR_RANGE;
+    }
+    sparse_setup_kernel<<<(n_slices + 1 + 127) / 128, 128, 0, s>>>(d_fasta, nbytes, w.genome, w.slices, n_slices);
+    KM_CUDA(cudaGetLastError());
+    if (int rc = launch_slice_headers(d_fasta, w.genome, w.slices, n_slices, s)) return rc;
+    sparse_emit_kernel<<<n_slices, SPARSE_THREADS, 0, s>>>(d_fasta, w.genome, w.slices, P, w.keys_a, w.ends_a, w.cursor,
+                                                           cap);
     KM_CUDA(cudaGetLastError());
     unsigned long long n = 0;
     KM_CUDA(cudaMemcpyAsync(&n, w.cursor, 8, cudaMemcpyDeviceToHost, s));

@@ -31,6 +31,8 @@ struct EmuSink {
 };
 }  // namespace
 
+static uint64_t g_line_limit = km::LINE_SCAN_LIMIT;
+extern "C" void emu_set_line_limit(uint64_t v) { g_line_limit = v ? v : km::LINE_SCAN_LIMIT; }
 extern "C" {
 
 // bytes[0..n): one FASTA file placed at `base_off` inside a zero-padded buffer
@@ -68,30 +70,46 @@ static int64_t emu_core(const uint8_t* bytes, uint64_t n, uint64_t base_off, int
     const uint64_t slice_bytes = tile_bytes * (uint64_t)tiles_per_slice;
     // slices are aligned to absolute multiples of slice_bytes (as on the GPU)
     uint64_t first_slice = g.lo / slice_bytes;
+    // slice table passes (slice_header_kernel, slice_long_scan_kernel, slice_long_resolve_kernel)
+    std::vector<uint64_t> starts;
     for (uint64_t sb = first_slice * slice_bytes; sb < g.hi; sb += slice_bytes) {
         // a byte range (relative to the file start) selects whole slices: the multi-GPU unit
         if (range_end && (sb + slice_bytes <= base_off + range_begin || sb >= base_off + range_end)) continue;
-        uint64_t hdr_carry = 0;
-        if (sb > g.lo) {
-            uint64_t until;
-            if (pos_in_header(g, sb, &until)) hdr_carry = until;
+        starts.push_back(sb);
+    }
+    std::vector<SliceHead> heads(starts.size());
+    std::vector<uint64_t> scan_last(starts.size(), LS_UNRESOLVED);
+    for (size_t i = 0; i < starts.size(); i++) slice_head_quick(g, starts[i], g_line_limit, &heads[i]);
+    for (size_t i = 0; i < starts.size(); i++) {
+        if (heads[i].line_start != LS_UNRESOLVED) continue;
+        uint64_t lo = g.lo;
+        if (i > 0 && starts[i - 1] > lo) lo = starts[i - 1];
+        uint64_t best = 0;
+        for (uint64_t pos = starts[i]; pos > lo; pos--)
+            if (is_term(g.b[pos - 1])) { best = pos; break; }
+        scan_last[i] = best ? best : (lo == g.lo ? g.lo : LS_UNRESOLVED);
+    }
+    {
+        uint64_t run_max = 0;
+        for (size_t i = 0; i < starts.size(); i++) {
+            uint64_t cand = heads[i].line_start != LS_UNRESOLVED ? heads[i].line_start : scan_last[i];
+            if (cand != LS_UNRESOLVED && cand > run_max) run_max = cand;
+            if (heads[i].line_start == LS_UNRESOLVED) {
+                uint64_t ls = std::max(run_max, g.lo);
+                heads[i].hdr_until = header_until_from(g, starts[i], ls);
+                if (heads[i].hdr_until) heads[i].prev_ok = 0;
+            }
         }
+    }
+    for (size_t si = 0; si < starts.size(); si++) {
+        const uint64_t sb = starts[si];
+        uint64_t hdr_carry = heads[si].hdr_until;
         std::vector<uint8_t> flags(threads_per_tile), clean(threads_per_tile);
         std::vector<CleanChunk> cc(threads_per_tile);
         // last chunk before the current tile: clean and in sequence?  For the slice's first tile
-        // the chunk belongs to another CTA and is packed once more by thread 0.
-        bool prev_tile_ok = false;
-        uint32_t prev_tile_last16 = 0;
-        if (sb >= g.lo + CHUNK && sb < g.hi) {
-            uint32_t w[CHUNK / 4], y[CHUNK / 4], bad[CHUNK / 4];
-            memcpy(w, g.b + sb - CHUNK, CHUNK);
-            CleanChunk pc;
-            uint64_t dummy;
-            if (classify_chunk(w, y, bad) == 0 && pack_clean(y, bad, pc) && !pos_in_header(g, sb - CHUNK, &dummy)) {
-                prev_tile_ok = true;
-                prev_tile_last16 = pc.last16;
-            }
-        }
+        // the chunk belongs to another CTA (slice table).
+        bool prev_tile_ok = heads[si].prev_ok != 0;
+        uint32_t prev_tile_last16 = heads[si].prev16;
         for (uint64_t tb = sb; tb < std::min(sb + slice_bytes, g.hi); tb += tile_bytes) {
             std::fill(flags.begin(), flags.end(), 0);
             std::fill(clean.begin(), clean.end(), 0);

@@ -87,3 +87,34 @@ def test_counting_one_level_above_the_largest_k(emu):
         for j in range(1, 9):
             assert np.array_equal(oracle.count_dense(data, j, 8), res[j]), j
         assert np.array_equal(oracle.count_dense(data, 9, 9), res[9])
+
+
+def test_long_lines_and_bounded_lookback(emu):
+    """Unwrapped FASTA: slice starts whose bounded look-back finds no line terminator are settled by the
+    slice-table passes.  A tiny limit forces that route on ordinary inputs, too."""
+    emu.emu_set_line_limit.argtypes = [ctypes.c_uint64]
+    rng = random.Random(33)
+    try:
+        for limit in (32, 40, 64):
+            emu.emu_set_line_limit(limit)
+            for _ in range(120):
+                data = fuzz_fasta(rng)
+                kmax = rng.choice([1, 3, 6, 9])
+                check(emu, data, kmax, kmax, rng.choice([1, 2, 3, 4]), rng.choice([1, 2, 3]), rng.choice([0, 3, 31, 64]))
+            for c in golden_extract_cases():
+                check(emu, c["fasta"], 8, 8, rng.choice([1, 2, 4]), rng.choice([1, 2]), rng.choice([0, 17, 64]))
+            # long sequence lines, long header lines (some made of base letters), CRLF
+            for _ in range(40):
+                parts = []
+                for r in range(rng.randint(1, 4)):
+                    hl = rng.choice([3, 30, 200, 700])
+                    alphabet = "ACGT" if rng.random() < 0.5 else "ACGTxyz _|"
+                    parts.append(">" + "".join(rng.choice(alphabet) for _ in range(hl)))
+                    for _line in range(rng.randint(0, 3)):
+                        parts.append("".join(rng.choice("ACGTACGTACGTN") for _ in range(rng.choice([0, 5, 60, 400, 1500]))))
+                nl = rng.choice(["\n", "\r\n"])
+                data = (nl.join(parts) + (nl if rng.random() < 0.8 else "")).encode()
+                kmax = rng.choice([2, 7, 9])
+                check(emu, data, kmax, kmax, rng.choice([1, 2, 4]), rng.choice([1, 2, 3]), rng.choice([0, 5, 32, 64]))
+    finally:
+        emu.emu_set_line_limit(0)

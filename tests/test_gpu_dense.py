@@ -175,3 +175,39 @@ def test_byte_ranges_are_additive():
             assert torch.equal(tot, whole.totals[0])
         for k in ks:
             assert np.array_equal(whole.counts_numpy(0, k).astype(np.uint64), oracle.count_dense(g.tobytes(), k, max(ks)))
+
+
+@pytest.mark.gpu
+def test_unwrapped_fasta_long_lines():
+    """Whole chromosomes on one line (and a very long header line): the slice-table passes settle what the
+    bounded look-back leaves open.  Dense (shared / packed / partition paths), sparse and first occurrence."""
+    import torch
+    from kmerml_b200 import engine
+    rng = np.random.default_rng(17)
+    def seq(n):
+        return np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].tobytes()
+    g1 = b">chr1 one line\n" + seq(700_001) + b"\n>chr2\n" + seq(300_000) + b"N" + seq(5_000) + b"\n"
+    g2 = b">" + seq(400_000) + b" header made of bases\n" + seq(200_003) + b"\r\n>x\r\n" + seq(150_000)
+    wrapped = seq(240_000)
+    g3 = b">w\n" + b"\n".join(wrapped[i:i + 70] for i in range(0, len(wrapped), 70)) + b"\n"
+    files = [g1, g2, g3]
+    data = b"".join(files)
+    offs = np.cumsum([0] + [len(f) for f in files]).tolist()
+    dev = torch.from_numpy(np.frombuffer(data, np.uint8).copy()).cuda()
+    for ks in ([3, 6], [8], [5, 10], [12]):
+        res = engine.count_dense_device(dev, offs, ks, want_freq=False)
+        for gi, f in enumerate(files):
+            for k in ks:
+                got = res.counts_of(gi, k).cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+                want = oracle.count_dense(f, k, max(ks))
+                assert np.array_equal(got, want.astype(np.int64)), (gi, k, ks)
+    for f in (g1, g2):
+        d1 = torch.from_numpy(np.frombuffer(f, np.uint8).copy()).cuda()
+        keys, counts, first, windows = engine.count_sparse_device(d1, 17)
+        wk, wc = oracle.count_sparse(f, 17)
+        order = np.argsort(wk)
+        assert np.array_equal(keys.cpu().numpy().view(np.uint64), wk[order])
+        assert np.array_equal(counts.cpu().numpy().astype(np.int64), wc[order].astype(np.int64))
+        fo = engine.first_occurrence_device(d1, 9)
+        dense = oracle.count_dense(f, 9)
+        assert np.array_equal(fo.cpu().numpy() >= 0, dense > 0)
