@@ -371,28 +371,35 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     const size_t row_bytes = (size_t)row.off[nk] * 4;
     if (use_part) {
         const int k_stop = std::max(kcount - PART_LOW_BASES, kmin);
-        uint64_t max_group_tiles = 0, max_group_bytes = 0;
+        uint64_t max_group_tiles = 0, max_group_bytes = 0, max_group_genomes = 0;
         for (size_t gi = 0, g0 = 0; gi < group_end.size(); g0 = group_end[gi], gi++) {
             max_group_tiles = std::max<uint64_t>(max_group_tiles, tile_start[group_end[gi]] - tile_start[g0]);
             max_group_bytes = std::max<uint64_t>(max_group_bytes, h_offsets[group_end[gi]] - h_offsets[g0]);
+            max_group_genomes = std::max<uint64_t>(max_group_genomes, group_end[gi] - g0);
         }
         // workspace: bucket-major payload slots | overflow lists (one entry per FASTA byte at most) | counters
         const size_t payload_bytes = align_up((size_t)max_group_tiles * PART_STAGE_ENTRIES * 2, 256);
         const size_t ov_bytes = align_up((size_t)max_group_bytes * 4 + 64, 256);
-        const size_t ovc_bytes = align_up((size_t)n_genomes * 4, 256);
-        rc = ws.part.ensure(payload_bytes + ov_bytes + ovc_bytes);
+        // ... | run-end tail lists (one entry per 64 FASTA bytes + 1024 per genome) | counters (overflow, tails)
+        const size_t ovc_bytes = align_up((size_t)n_genomes * 8 + 8, 256);
+        const size_t tl_bytes = align_up((size_t)((max_group_bytes >> 6) + 1024 * (max_group_genomes + 1)) * 8, 256);
+        rc = ws.part.ensure(payload_bytes + ov_bytes + tl_bytes + ovc_bytes);
         if (rc) return rc;
         uint16_t* d_payload = (uint16_t*)ws.part.p;
         uint32_t* d_overflow = (uint32_t*)((uint8_t*)ws.part.p + payload_bytes);
-        unsigned int* d_ov_counts = (unsigned int*)((uint8_t*)ws.part.p + payload_bytes + ov_bytes);
-        KM_CUDA(cudaMemsetAsync(d_ov_counts, 0, (size_t)n_genomes * 4, s));
-        // only the levels below kmax collect run-end tails and must start from zero;
-        // the top-level row is written in full by the bucket kernel
+        unsigned long long* d_tail_list = (unsigned long long*)((uint8_t*)ws.part.p + payload_bytes + ov_bytes);
+        unsigned int* d_ov_counts = (unsigned int*)((uint8_t*)ws.part.p + payload_bytes + ov_bytes + tl_bytes);
+        unsigned int* d_tail_counts = d_ov_counts + n_genomes;
+        unsigned int* d_tail_any = d_tail_counts + n_genomes;
+        KM_CUDA(cudaMemsetAsync(d_ov_counts, 0, (size_t)n_genomes * 8 + 8, s));
+        // the bucket kernel stores every row from level k_stop upwards in full; only the few small
+        // levels below it collect run-end tails directly and must start from zero
         for (int i = 0; i < nk; i++)
-            if (row.k[i] < kcount)
+            if (row.k[i] < k_stop)
                 KM_CUDA(cudaMemset2DAsync(d_counts + row.off[i], (size_t)counts_stride * 4, 0,
                                           (size_t)(1ull << (2 * row.k[i])) * 4, (size_t)n_genomes, s));
-        if (scratch_stride) KM_CUDA(cudaMemsetAsync(lm.scratch, 0, (size_t)scratch_stride * n_genomes * 4, s));
+        if (scratch_stride && k_stop > kmin)
+            KM_CUDA(cudaMemsetAsync(lm.scratch, 0, (size_t)scratch_stride * n_genomes * 4, s));
         int g0 = 0;
         for (size_t gi = 0; gi < group_end.size(); gi++) {
             const int g1 = group_end[gi], ng = g1 - g0;
@@ -401,7 +408,8 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
             {
                 Prof pr(ctx, s, 4, nt > 0 ? 1 : 0);
                 rc = launch_partition(d_fasta, d_genomes, d_slices + first_slice[g0], nt, d_gtiles, kcount, kmin, min_rec,
-                                      lm, d_stats, d_payload, d_overflow, d_ov_counts, batch_lo, s);
+                                      lm, d_stats, d_payload, d_overflow, d_ov_counts, batch_lo, d_tail_list, d_tail_counts,
+                                      d_tail_any, (uint32_t)g0, s);
             }
             if (rc) return rc;
             {
@@ -410,6 +418,13 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
                                    freq_stride, d_totals, (uint32_t)g0, ng, s);
             }
             if (rc) return rc;
+            if (kcount > kmin) {
+                Prof pr(ctx, s, 3, canonical || !d_freq ? 2 : 4);
+                rc = launch_tails(d_fasta, lm, row, kcount, kmin, min_rec, d_genomes, d_slices + first_slice[g0], nt,
+                                  d_tail_list, d_tail_counts, d_tail_any, batch_lo, d_stats, canonical ? nullptr : d_freq, freq_stride,
+                                  (uint32_t)g0, ng, s);
+                if (rc) return rc;
+            }
             for (int h0 = g0; h0 < g1; h0 += 32768) {
                 const int nh = std::min(32768, g1 - h0);
                 {

@@ -36,6 +36,43 @@ struct NoTails {
     __device__ __forceinline__ void tail(int, uint32_t) const {}
 };
 
+// Partition path: the levels the bucket kernel writes (>= k_stop) are never zeroed and never read back,
+// so their run-end tails are kept in a per-genome list (level << 32 | index) and added after the
+// bucket kernel has stored the rows.  A list that runs full is dropped as a whole: the genome's run
+// ends are then walked a second time (tails_rescan_kernel).
+struct TailList {
+    unsigned long long* list;          // all genomes of the group, see tail_list_of()
+    unsigned int* counts;              // per genome (global index): entries pushed, may exceed the capacity
+    unsigned int* any_full;            // set when some genome's list ran full
+    uint64_t batch_lo;                 // buffer offset of the group's first genome
+    uint32_t genome0;                  // ... and its index
+};
+__device__ __forceinline__ unsigned long long* tail_list_of(const TailList& tl, const GenomeDev& gd, uint32_t g,
+                                                            uint32_t* cap) {
+    *cap = (uint32_t)((gd.hi - gd.file_lo) >> 6) + 1024u;
+    return tl.list + ((gd.file_lo - tl.batch_lo) >> 6) + 1024ull * (g - tl.genome0);
+}
+struct ListTails {
+    const LevelMap* lm;
+    GenomeStats* st;
+    uint32_t genome;
+    int k_stop;
+    unsigned long long* list;
+    unsigned int* count;
+    unsigned int* any_full;
+    uint32_t cap;
+    __device__ __noinline__ void tail(int j, uint32_t idx) const {
+        atomicAdd(&st->n_tail[j], 1ull);
+        if (j < k_stop) {                                   // the few small levels below the bucket subtrees
+            atomicAdd(lm->ptr(genome, j) + idx, 1u);
+            return;
+        }
+        const unsigned int slot = atomicAdd(count, 1u);
+        if (slot < cap) list[slot] = ((unsigned long long)j << 32) | idx;
+        else *any_full = 1u;
+    }
+};
+
 struct GlobalSink {
     uint32_t* top;
     unsigned n;
@@ -543,7 +580,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, 3)
 partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
                  const Slice* __restrict__ tiles, const GenomeTiles* __restrict__ gts, DenseParams P, LevelMap lm,
                  GenomeStats* stats, uint16_t* __restrict__ payload, uint32_t* __restrict__ overflow,
-                 unsigned int* __restrict__ ov_counts, uint64_t batch_lo) {
+                 unsigned int* __restrict__ ov_counts, uint64_t batch_lo, TailList tl, int k_stop) {
     constexpr int slot_shift = SLOT_SHIFT;
     constexpr int nb = STAGE_ENTRIES >> SLOT_SHIFT;
     extern __shared__ __align__(16) unsigned char part_smem_raw[];
@@ -567,8 +604,11 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     sink.staged = sm.staged;
     sink.ov = overflow + (gd.file_lo - batch_lo);      // one possible window per byte of the genome
     sink.ov_count = ov_counts + sl.genome;
-    DevTails tails;
-    tails.lm = &lm; tails.st = stats + sl.genome; tails.genome = sl.genome;
+    ListTails tails;
+    tails.lm = &lm; tails.st = stats + sl.genome; tails.genome = sl.genome; tails.k_stop = k_stop;
+    tails.list = tail_list_of(tl, gd, sl.genome, &tails.cap);
+    tails.count = tl.counts + sl.genome;
+    tails.any_full = tl.any_full;
     // a slice is a run of consecutive tiles of one genome: the CTA walks them one after the other,
     // and after each tile writes its 64 KB of slots bucket-major: slot (b, t) of this genome at
     // ((b * n_tiles + t) << slot_shift)
@@ -613,11 +653,9 @@ struct LevelInfo {                     // per level: index into the caller's k_l
 };
 
 constexpr int BUCKET_THREADS = 512;
-constexpr int SMALL_LEVEL_BINS = 341;  // 256 + 64 + 16 + 4 + 1: levels k-3 .. k-7 of one bucket
 
 struct BucketSmem {
     uint32_t hist[PART_BINS];          // 64 KB; reused in place by the in-bucket cascade
-    uint32_t small_tails[SMALL_LEVEL_BINS + 3];   // run-end tails of the small levels, prefetched
     unsigned long long tot[16];
     uint32_t* lvl_counts[16];          // per level: this bucket's slice of the count row
     float* lvl_freq[16];               //            ... of the frequency row (nullptr: not requested)
@@ -679,26 +717,9 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
         sm.lvl_freq[level] = fp;
         sm.lvl_inv[level] = inv;
     }
-    // run-end tails of every lower level of this bucket's subtree: issue the loads now, they
-    // arrive while the histogram is being built
     constexpr int PER1 = PART_BINS / 4 / BUCKET_THREADS;          // 8 level-(k-1) bins per thread
     constexpr int PER2 = PART_BINS / 16 / BUCKET_THREADS;         // 2 level-(k-2) bins per thread
-    uint32_t tails1[PER1], tails2[PER2];
-    {
-        // (a level without a single run-end tail is all zeros: nothing to read)
-        const GenomeStats& gs = stats[g];
-        const uint32_t* c1 = (k - 1 >= k_stop && gs.n_tail[k - 1]) ? lm.ptr(g, k - 1) + (size_t)b * (PART_BINS / 4) : nullptr;
-        const uint32_t* c2 = (k - 2 >= k_stop && gs.n_tail[k - 2]) ? lm.ptr(g, k - 2) + (size_t)b * (PART_BINS / 16) : nullptr;
-#pragma unroll
-        for (int u = 0; u < PER1; u++) tails1[u] = c1 ? c1[tid + u * BUCKET_THREADS] : 0u;
-#pragma unroll
-        for (int u = 0; u < PER2; u++) tails2[u] = c2 ? c2[tid + u * BUCKET_THREADS] : 0u;
-        if (tid < SMALL_LEVEL_BINS) {                             // levels k-3 (256 bins) .. k-7 (1 bin)
-            int level = k - 3, base = 0, n = 256;
-            while (tid >= base + n) { base += n; n >>= 2; level--; }
-            sm.small_tails[tid] = (level >= k_stop && gs.n_tail[level]) ? lm.ptr(g, level)[(size_t)b * n + (tid - base)] : 0u;
-        }
-    }
+    // (run-end tails of these levels are added afterwards from the genome's tail list)
     // stream this bucket's slots: n_tiles * slot entries, contiguous, 128-bit coalesced loads
     const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sm.hist);
     const uint16_t* bp = payload + (size_t)gt.tile0 * STAGE_ENTRIES + (((size_t)b * gt.n_tiles) << slot_shift);
@@ -764,7 +785,7 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
                 f.z = (float)((double)c.z * inv); f.w = (float)((double)c.w * inv);
                 reinterpret_cast<float4*>(fk)[i] = f;
             }
-            v1r[u] = c.x + c.y + c.z + c.w + tails1[u];               // + run-end tails of level k-1
+            v1r[u] = c.x + c.y + c.z + c.w;
             if (down) {
                 c1[i] = v1r[u];
                 if (f1) f1[i] = (float)((double)v1r[u] * inv1);
@@ -784,7 +805,7 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
         for (int u = 0; u < PER2; u++) {
             const int i = tid + u * BUCKET_THREADS;
             const uint4 c = reinterpret_cast<const uint4*>(sm.hist)[i];
-            const uint32_t v = c.x + c.y + c.z + c.w + tails2[u];
+            const uint32_t v = c.x + c.y + c.z + c.w;
             cl[i] = v;
             if (fl) fl[i] = (float)((double)v * invl);
             sm.hist[4096 + i] = v;
@@ -795,7 +816,7 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
     // the small rest (256, 64, 16, 4, 1 bins) by warp 0, ping-pong inside hist[]
     uint32_t* cur = sm.hist + 4096;
     uint32_t* nxt = sm.hist + 8192;
-    int n_cur = 1024, tbase = 0;
+    int n_cur = 1024;
     for (int level = k - 3; level >= k_stop; level--) {
         const int n_next = n_cur >> 2;
         uint32_t* cl = sm.lvl_counts[level];
@@ -803,14 +824,13 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
         const double invl = sm.lvl_inv[level];
         for (int i = tid; i < n_next; i += 32) {
             const uint4 c = reinterpret_cast<const uint4*>(cur)[i];
-            const uint32_t v = c.x + c.y + c.z + c.w + sm.small_tails[tbase + i];
+            const uint32_t v = c.x + c.y + c.z + c.w;
             cl[i] = v;
             if (fl) fl[i] = (float)((double)v * invl);
             nxt[i] = v;
         }
         __syncwarp();
         uint32_t* t = cur; cur = nxt; nxt = t;
-        tbase += n_next;
         n_cur = n_next;
     }
 }
@@ -840,6 +860,85 @@ overflow_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const
                 freq[(uint64_t)g * freq_stride + row.off[ki] + x] = t ? (float)((double)c[x] * (1.0 / (double)t)) : 0.0f;
             }
         }
+    }
+}
+
+// One run-end tail of level j (>= k_stop) counts at level j and, through the marginal sums, at every
+// level below it down to k_stop (the cascade below k_stop runs later).  pass 0 adds, pass 1 refreshes
+// the touched frequencies from the final counts.
+struct TailApply {
+    LevelMap lm;
+    RowSpec row;
+    LevelInfo li;
+    int k, k_stop, pass;
+    const GenomeStats* stats;
+    float* freq;
+    uint64_t freq_stride;
+    __device__ __forceinline__ void apply(uint32_t g, int j, uint32_t idx) const {
+        for (int level = j; level >= k_stop; level--) {
+            const uint32_t x = idx >> (2 * (j - level));
+            uint32_t* c = lm.ptr(g, level);
+            if (pass == 0) {
+                atomicAdd(c + x, 1u);
+            } else if (freq && li.ki[level] >= 0) {
+                const int ki = li.ki[level];
+                unsigned long long t = stats[g].total_top;
+                for (int q = level; q < k; q++) t += stats[g].n_tail[q];
+                freq[(uint64_t)g * freq_stride + row.off[ki] + x] = t ? (float)((double)c[x] * (1.0 / (double)t)) : 0.0f;
+            }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(256)
+tails_apply_kernel(TailApply ap, const GenomeDev* __restrict__ gds, TailList tl, uint32_t genome0) {
+    const uint32_t g = genome0 + blockIdx.y;
+    const unsigned int n = tl.counts[g];
+    if (!n) return;
+    uint32_t cap;
+    const unsigned long long* list = tail_list_of(tl, gds[g], g, &cap);
+    if (n > cap) return;                                    // dropped: tails_rescan_kernel does this genome
+    for (unsigned int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const unsigned long long e = list[i];
+        ap.apply(g, (int)(e >> 32), (uint32_t)e);
+    }
+}
+
+struct NullSink {
+    __device__ __forceinline__ void count(uint32_t, uint64_t) {}
+    __device__ __forceinline__ void count4(uint32_t, uint32_t, uint32_t, uint32_t, uint64_t, uint64_t, uint64_t, uint64_t) {}
+    __device__ __forceinline__ void count8(const uint32_t*, const uint64_t*) {}
+};
+struct RescanTails {
+    const TailApply* ap;
+    uint32_t genome;
+    __device__ __noinline__ void tail(int j, uint32_t idx) const {
+        if (j >= ap->k_stop) ap->apply(genome, j, idx);
+    }
+};
+
+// Genomes whose tail list ran full (a run end every few bytes): walk the run ends again.  A small
+// persistent grid, so that the usual case (no list ran full) costs one wave of CTAs that exit at once.
+__global__ void __launch_bounds__(COUNT_THREADS)
+tails_rescan_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds, const Slice* __restrict__ slices,
+                    int n_slices, DenseParams P, TailApply ap, TailList tl) {
+    if (*tl.any_full == 0) return;
+    KM_TILE_SMEM(rs)
+    for (int i = blockIdx.x; i < n_slices; i += gridDim.x) {
+        const Slice sl = slices[i];
+        const GenomeDev gd = gds[sl.genome];
+        uint32_t cap;
+        (void)tail_list_of(tl, gd, sl.genome, &cap);
+        if (tl.counts[sl.genome] <= cap) continue;
+        Genome g;
+        g.b = buf;
+        g.lo = gd.lo;
+        g.hi = gd.hi;
+        NullSink sink;
+        RescanTails tails;
+        tails.ap = &ap; tails.genome = sl.genome;
+        walk_slice(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
+        __syncthreads();
     }
 }
 
@@ -1052,13 +1151,18 @@ int part_slot_shift(int k) {                  // log2 of the slot size: 32768 / 
 int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles,
                      const void* d_genome_tiles, int k, int k_bottom, int min_rec, const LevelMap& lm,
                      GenomeStats* d_stats, uint16_t* d_payload, uint32_t* d_overflow, unsigned int* d_ov_counts,
-                     uint64_t batch_lo, cudaStream_t s) {
+                     uint64_t batch_lo, unsigned long long* d_tail_list, unsigned int* d_tail_counts, unsigned int* d_tail_any,
+                     uint32_t genome0, cudaStream_t s) {
     if (n_tiles <= 0) return KMERML_OK;
     DenseParams P = make_params(k, min_rec, k > k_bottom, k_bottom);
+    const int k_stop = std::max(k - PART_LOW, k_bottom);
+    TailList tl;
+    tl.list = d_tail_list; tl.counts = d_tail_counts; tl.batch_lo = batch_lo; tl.genome0 = genome0;
+    tl.any_full = d_tail_any;
 #define KM_LAUNCH_PART(SH)                                                                            \
     partition_kernel<SH><<<n_tiles, COUNT_THREADS, sizeof(PartSmem), s>>>(                             \
         d_fasta, d_genomes, d_tiles, (const GenomeTiles*)d_genome_tiles, P, lm, d_stats, d_payload, d_overflow, \
-        d_ov_counts, batch_lo)
+        d_ov_counts, batch_lo, tl, k_stop)
     switch (part_slot_shift(k)) {
         case 5: KM_LAUNCH_PART(5); break;        // k = 12
         case 7: KM_LAUNCH_PART(7); break;        // k = 11
@@ -1105,6 +1209,35 @@ int launch_overflow(const LevelMap& lm, const RowSpec& row, int k, int k_bottom,
     for (int pass = 0; pass < (d_freq ? 2 : 1); pass++) {
         overflow_kernel<<<grid, 256, 0, s>>>(lm, row, li, k, k_stop, d_genomes, d_overflow, d_ov_counts, batch_lo,
                                              d_stats, d_freq, freq_stride, genome0, pass);
+        KM_CUDA(cudaGetLastError());
+    }
+    return KMERML_OK;
+}
+
+// Adds the run-end tails the partition kernel listed (levels >= k_stop) to the rows the bucket kernel
+// stored; `pass` as in launch_overflow.  Two launches per pass: the lists, and the rescan of genomes
+// whose list ran full (its CTAs exit at once otherwise).
+int launch_tails(const uint8_t* d_fasta, const LevelMap& lm, const RowSpec& row, int k, int k_bottom, int min_rec,
+                 const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles, unsigned long long* d_tail_list,
+                 unsigned int* d_tail_counts, unsigned int* d_tail_any, uint64_t batch_lo, const GenomeStats* d_stats,
+                 float* d_freq, uint64_t freq_stride, uint32_t genome0, int n_genomes, cudaStream_t s) {
+    if (n_genomes <= 0 || k <= k_bottom) return KMERML_OK;
+    TailApply ap;
+    ap.lm = lm; ap.row = row; ap.li = make_level_info(row);
+    ap.k = k; ap.k_stop = std::max(k - PART_LOW, k_bottom);
+    ap.stats = d_stats; ap.freq = d_freq; ap.freq_stride = freq_stride;
+    TailList tl;
+    tl.list = d_tail_list; tl.counts = d_tail_counts; tl.batch_lo = batch_lo; tl.genome0 = genome0;
+    tl.any_full = d_tail_any;
+    DenseParams P = make_params(k, min_rec, true, ap.k_stop);
+    for (int pass = 0; pass < (d_freq ? 2 : 1); pass++) {
+        ap.pass = pass;
+        for (int h0 = 0; h0 < n_genomes; h0 += 32768) {
+            dim3 grid(8, (unsigned)std::min(32768, n_genomes - h0));
+            tails_apply_kernel<<<grid, 256, 0, s>>>(ap, d_genomes, tl, genome0 + (uint32_t)h0);
+        }
+        if (n_tiles > 0)
+            tails_rescan_kernel<<<std::min(n_tiles, 4 * 148), COUNT_THREADS, 0, s>>>(d_fasta, d_genomes, d_tiles, n_tiles, P, ap, tl);
         KM_CUDA(cudaGetLastError());
     }
     return KMERML_OK;

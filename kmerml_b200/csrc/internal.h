@@ -92,7 +92,12 @@ constexpr int PART_TILES_PER_SLICE = 8;                 // consecutive tiles one
 int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles,
                      const void* d_genome_tiles, int k, int k_bottom, int min_rec, const LevelMap& lm,
                      GenomeStats* d_stats, uint16_t* d_payload, uint32_t* d_overflow, unsigned int* d_ov_counts,
-                     uint64_t batch_lo, cudaStream_t s);
+                     uint64_t batch_lo, unsigned long long* d_tail_list, unsigned int* d_tail_counts,
+                     unsigned int* d_tail_any, uint32_t genome0, cudaStream_t s);
+int launch_tails(const uint8_t* d_fasta, const LevelMap& lm, const RowSpec& row, int k, int k_bottom, int min_rec,
+                 const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles, unsigned long long* d_tail_list,
+                 unsigned int* d_tail_counts, unsigned int* d_tail_any, uint64_t batch_lo, const GenomeStats* d_stats,
+                 float* d_freq, uint64_t freq_stride, uint32_t genome0, int n_genomes, cudaStream_t s);
 int launch_bucket(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, const void* d_genome_tiles,
                   const uint16_t* d_payload, const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride,
                   uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s);

@@ -211,3 +211,28 @@ def test_unwrapped_fasta_long_lines():
         fo = engine.first_occurrence_device(d1, 9)
         dense = oracle.count_dense(f, 9)
         assert np.array_equal(fo.cpu().numpy() >= 0, dense > 0)
+
+
+def test_run_end_tail_list_overflow_rescans():
+    """A run end every dozen bytes overflows the partition path's per-genome tail list; the genome's run
+    ends are then walked again.  One such genome sits between two ordinary ones."""
+    rng = random.Random(91)
+    def seq(n):
+        return "".join(rng.choice("ACGT") for _ in range(n))
+    parts = []
+    for r in range(60):
+        parts.append(f">r{r}")
+        line = []
+        for _ in range(rng.randint(20, 60)):
+            line.append(seq(rng.randint(9, 30)))
+        parts.append("N".join(line))
+        for _ in range(rng.randint(0, 30)):
+            parts.append(seq(rng.randint(8, 14)) + rng.choice(["", "N", "x"]) + seq(rng.randint(0, 13)))
+    busy = ("\n".join(parts) + "\n").encode()
+    calm1 = (">a\n" + "\n".join(seq(70) for _ in range(300)) + "\n").encode()
+    calm2 = (">b\n" + seq(40_000) + "\n>c\n" + seq(33) + "\n").encode()
+    assert busy.count(b"N") * 6 > len(busy) // 64 + 1024       # really overflows
+    for ks in ([9, 10, 11, 12], [5, 12], [1, 2, 3, 4, 5, 6, 7, 8, 9], [10], [8, 11]):
+        check_against_oracle([calm1, busy, calm2], ks)
+    check_against_oracle([calm1, busy, calm2], [9, 12], canonical=True)
+    check_against_oracle([busy], [7, 12], min_record_len=40)
