@@ -167,7 +167,7 @@ __device__ __forceinline__ void level_totals(const RowSpec& row, int k_top, cons
                                              unsigned long long* tot, uint64_t* totals, bool write);
 
 struct TileCtx {                      // shared-memory state of the tile loop
-    uint8_t* flags;                   // [COUNT_THREADS] chunk starts inside a header line
+    uint8_t* flags;                   // [2][COUNT_THREADS] chunk starts inside a header line (by tile parity)
     uint8_t* clean;                   // [COUNT_THREADS] chunk is clean (bases + at most one '\n')
     uint32_t* last16;                 // [COUNT_THREADS] last 16 bases of a clean chunk
     unsigned long long* carry;        // [2] end of a header line that runs into later tiles
@@ -175,7 +175,7 @@ struct TileCtx {                      // shared-memory state of the tile loop
 };
 
 #define KM_TILE_SMEM(prefix)                                   \
-    __shared__ uint8_t prefix##_flags[COUNT_THREADS];          \
+    __shared__ uint8_t prefix##_flags[2 * COUNT_THREADS];      \
     __shared__ uint8_t prefix##_clean[COUNT_THREADS];          \
     __shared__ uint32_t prefix##_last16[COUNT_THREADS];        \
     __shared__ unsigned long long prefix##_carry[2];           \
@@ -192,15 +192,25 @@ template <class Sink, class Tails, class PerTile>
 __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, const Genome& g, const Slice& sl,
                                            const DenseParams& P, Sink& sink, const Tails& tails, const TileCtx& tc,
                                            PerTile&& per_tile) {
+    // Two barriers per tile.  What makes that safe:
+    //  * flags[] is double-buffered by tile parity; a thread clears its entry of the OTHER buffer during
+    //    phase 2, i.e. after that buffer's last readers (phase 2 of the tile before) passed a barrier and
+    //    before its next writers (phase 1 of the next tile) can start;
+    //  * carry[parity] only ever grows (atomicMax of header ends); every thread folds it into its own
+    //    running maximum `hc` after the barrier that closes phase 1;
+    //  * clean[] / last16[] are written in phase 1 and read by the right neighbour in phase 2.
     const int tid = threadIdx.x;
+    tc.flags[tid] = 0;
+    tc.flags[COUNT_THREADS + tid] = 0;
     if (tid == 0) {
-        tc.carry[0] = sl.hdr_until;                         // resolved per slice by slice_header_kernel
-        tc.carry[1] = sl.hdr_until;
+        tc.carry[0] = 0;
+        tc.carry[1] = 0;
         tc.prev_tile[0] = sl.prev_ok;                       // the chunk before the slice (another CTA's)
         tc.prev_tile[1] = sl.prev16;
     }
+    __syncthreads();
+    unsigned long long hc = sl.hdr_until;                   // resolved per slice by slice_header_kernel
     const uint64_t end = sl.end < g.hi ? sl.end : g.hi;
-    // software pipeline: the chunk of tile i+1 is loaded while tile i is processed
     auto load_chunk = [&](uint64_t tbx, uint32_t* w) -> bool {
         const uint64_t cbx = tbx + (uint64_t)tid * CHUNK;
         if (!(cbx >= g.lo && cbx + CHUNK <= g.hi && tbx < end)) return false;
@@ -212,13 +222,11 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
         }
         return true;
     };
-    uint32_t w[CHUNK / 4], wn[CHUNK / 4];
+    uint32_t w[CHUNK / 4];
     bool full = load_chunk(sl.begin, w);
     uint32_t tile_no = 0;
     for (uint64_t tb = sl.begin; tb < end; tb += TILE_BYTES, tile_no++) {
-        tc.flags[tid] = 0;
-        __syncthreads();                                    // flags cleared, carry / prev_tile visible
-        const bool full_next = load_chunk(tb + TILE_BYTES, wn);
+        uint8_t* flags = tc.flags + (tile_no & 1u) * COUNT_THREADS;
         const uint64_t cb = tb + (uint64_t)tid * CHUNK;
         const uint64_t cs = cb > g.lo ? cb : g.lo;
         const uint64_t ce = cb + CHUNK < g.hi ? cb + CHUNK : g.hi;
@@ -227,8 +235,8 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
         cc.hi = cc.lo = 0; cc.n = 0; cc.nl = 32; cc.last16 = 0;
         bool clean = false;
         auto on_header = [&](uint64_t, uint64_t until) {
-            for (int j = tid + 1; j < COUNT_THREADS && tb + (uint64_t)j * CHUNK < until; j++) tc.flags[j] = 1;
-            atomicMax(&tc.carry[1], (unsigned long long)until);
+            for (int j = tid + 1; j < COUNT_THREADS && tb + (uint64_t)j * CHUNK < until; j++) flags[j] = 1;
+            atomicMax(&tc.carry[tile_no & 1u], (unsigned long long)until);
         };
         if (full) {
             uint32_t y[CHUNK / 4], bad[CHUNK / 4];
@@ -243,17 +251,21 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
         tc.last16[tid] = cc.last16;
         __syncthreads();
         // phase 2
-        const unsigned long long hc = tc.carry[0];
-        const bool in_hdr = tc.flags[tid] || cs < hc;
+        const bool in_hdr = flags[tid] || cs < hc;
         bool prev_ok;
         uint32_t carry16;
         if (tid > 0) {
-            prev_ok = tc.clean[tid - 1] && !tc.flags[tid - 1] && !(cb - CHUNK < hc);
+            prev_ok = tc.clean[tid - 1] && !flags[tid - 1] && !(cb - CHUNK < hc);
             carry16 = tc.last16[tid - 1];
         } else {
             prev_ok = tc.prev_tile[0] != 0;
             carry16 = tc.prev_tile[1];
         }
+        {
+            const unsigned long long seen = tc.carry[tile_no & 1u];
+            hc = seen > hc ? seen : hc;                     // header lines that run into later tiles
+        }
+        tc.flags[((tile_no & 1u) ^ 1u) * COUNT_THREADS + tid] = 0;
         if (has) {
             if (clean && !in_hdr && prev_ok && P.min_rec <= P.k) {
                 emit_clean(cc, carry16, cs, P, sink);
@@ -262,16 +274,14 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
                 walk_chunk(g, cs, ce, in_hdr, P, sink, tails, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
             }
         }
+        // the next tile's chunk: in flight while the CTA waits at the barrier and runs the per-tile hook
+        full = load_chunk(tb + TILE_BYTES, w);
         __syncthreads();
         if (tid == COUNT_THREADS - 1) {
             tc.prev_tile[0] = (has && clean && !in_hdr) ? 1u : 0u;
             tc.prev_tile[1] = cc.last16;
         }
-        if (tid == 0) tc.carry[0] = tc.carry[1];
         per_tile(tile_no);
-        full = full_next;
-#pragma unroll
-        for (int i = 0; i < CHUNK / 4; i++) w[i] = wn[i];
     }
 }
 
@@ -557,7 +567,7 @@ struct SlotSink {
 
 struct PartWalkSmem {                           // only live during the walk ...
     uint32_t last16[COUNT_THREADS];
-    uint8_t flags[COUNT_THREADS];
+    uint8_t flags[2 * COUNT_THREADS];
     uint8_t clean[COUNT_THREADS];
 };
 
@@ -576,7 +586,7 @@ struct GenomeTiles {                   // tiles of one genome inside the group's
 };
 
 template <int SLOT_SHIFT>
-__global__ void __launch_bounds__(COUNT_THREADS, 3)
+__global__ void __launch_bounds__(COUNT_THREADS, 2)
 partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
                  const Slice* __restrict__ tiles, const GenomeTiles* __restrict__ gts, DenseParams P, LevelMap lm,
                  GenomeStats* stats, uint16_t* __restrict__ payload, uint32_t* __restrict__ overflow,
@@ -619,30 +629,31 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     const size_t stride = (((size_t)(COUNT_THREADS >> vec_shift) * gt.n_tiles) << slot_shift) / 8;
     unsigned n = 0;
     walk_slice(buf, g, sl, P, sink, tails, tc, [&](uint32_t tile_no) {
-        // (the walk of the tile ended with a __syncthreads)
-        for (int b = tid; b < nb; b += COUNT_THREADS) {
-            const uint32_t c = sm.cnt[b];
-            n += c;
-            sm.staged[(b << slot_shift) + ((2u * b) & sink.slot_cap)] = (uint16_t)(c < sink.slot_cap ? c : sink.slot_cap);
-            sm.cnt[b] = 0;
-        }
-        __syncthreads();
+        // (the walk of the tile ended with a __syncthreads; the next tile's placements start after
+        // another one.)  Vector v = tid + 512 j belongs to bucket (tid >> vec_shift) + (512 >> vec_shift) j:
+        // the destination advances by a constant stride, one add per 128-bit store.  The vector that
+        // holds the slot's entry 0 (at the bucket's rotation) gets the fill count patched in on the way
+        // out; its thread is the only one that reads and clears the bucket's counter.
         const uint32_t t_local = sl.tile0 + tile_no - gt.tile0;
-        if (vec_shift <= 9) {
-            // vector v = tid + 512 j belongs to bucket (tid >> vec_shift) + (512 >> vec_shift) j: the
-            // destination advances by a constant stride, one add per 128-bit store
-            uint4* dst = reinterpret_cast<uint4*>(pg + (((size_t)b0 * gt.n_tiles + t_local) << slot_shift)) + o;
+        uint4* dst = reinterpret_cast<uint4*>(pg + (((size_t)b0 * gt.n_tiles + t_local) << slot_shift)) + o;
 #pragma unroll
-            for (int j = 0; j < STAGE_ENTRIES / 8 / COUNT_THREADS; j++) dst[j * stride] = src[tid + j * COUNT_THREADS];
-        } else {
-            for (int v = tid; v < STAGE_ENTRIES / 8; v += COUNT_THREADS) {
-                const uint32_t b = (uint32_t)v >> vec_shift;
-                const uint32_t oo = (uint32_t)v & ((1u << vec_shift) - 1u);
-                uint4* dst = reinterpret_cast<uint4*>(pg + (((size_t)b * gt.n_tiles + t_local) << slot_shift)) + oo;
-                *dst = src[v];
+        for (int j = 0; j < STAGE_ENTRIES / 8 / COUNT_THREADS; j++) {
+            uint4 x = src[tid + j * COUNT_THREADS];
+            const uint32_t b = b0 + (uint32_t)j * (COUNT_THREADS >> vec_shift);
+            const uint32_t rot = (2u * b) & sink.slot_cap;
+            if (o == (rot >> 3)) {
+                const uint32_t c = sm.cnt[b];
+                sm.cnt[b] = 0;
+                n += c;
+                const uint32_t e0 = c < sink.slot_cap ? c : sink.slot_cap;
+                const uint32_t wsel = (rot & 7u) >> 1;                  // rot is even: low half of this word
+                x.x = wsel == 0 ? (x.x & 0xFFFF0000u) | e0 : x.x;
+                x.y = wsel == 1 ? (x.y & 0xFFFF0000u) | e0 : x.y;
+                x.z = wsel == 2 ? (x.z & 0xFFFF0000u) | e0 : x.z;
+                x.w = wsel == 3 ? (x.w & 0xFFFF0000u) | e0 : x.w;
             }
+            dst[j * stride] = x;
         }
-        // (the next tile's walk starts with a __syncthreads before anything touches staged / cnt)
     });
     const unsigned long long total = block_sum_u32(n, &sm.sh_total);
     if (tid == 0 && total) atomicAdd(&stats[sl.genome].total_top, total);
@@ -687,10 +698,6 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
     const uint32_t b = blockIdx.x;
     const uint32_t g = genome0 + blockIdx.y;
     const GenomeTiles gt = gts[g];
-    {
-        uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
-        for (int i = tid; i < PART_BINS / 4; i += BUCKET_THREADS) h4[i] = make_uint4(0, 0, 0, 0);
-    }
     if (tid < row.nk) {
         const int j = row.k[tid];
         unsigned long long t = stats[g].total_top;
@@ -729,39 +736,66 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
     const uint64_t n_vec = (uint64_t)gt.n_tiles << vec_shift;
     const uint32_t smask = (1u << slot_shift) - 1u;
     const uint32_t rot = (2u * b) & smask;                       // partition_kernel's per-bucket rotation
-    constexpr int UNROLL = 4;
-    for (uint64_t v0 = tid; v0 < n_vec; v0 += (uint64_t)BUCKET_THREADS * UNROLL) {
-        uint4 x[UNROLL];
-        uint32_t cnt[UNROLL];
+    // Software pipeline: round r + 1 is in flight while round r goes into the histogram (round 0 was
+    // issued before the histogram was cleared).  Every thread runs every round, so that the 4 (16) lanes
+    // that hold one slot's vectors can pass the slot's fill count around with a shuffle instead of a
+    // second load; slots wider than a warp's 32 vectors still load it.
+    constexpr int UNROLL = 2;
+    const uint32_t n_rounds = (uint32_t)((n_vec + (uint64_t)BUCKET_THREADS * UNROLL - 1) / ((uint64_t)BUCKET_THREADS * UNROLL));
+    const bool by_shuffle = vec_shift <= 5;
+    const uint32_t owner_vec = rot >> 3;                          // which vector of a slot holds entry 0 ...
+    const uint32_t owner_half = rot & 7u;                         // ... and where in it (even: low half of a word)
+    auto load_round = [&](uint32_t r, uint4* x, uint32_t* cnt) {
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
-            const uint64_t v = v0 + (uint64_t)u * BUCKET_THREADS;
+            const uint64_t v = (uint64_t)r * (BUCKET_THREADS * UNROLL) + (uint64_t)u * BUCKET_THREADS + tid;
             if (v < n_vec) {
                 x[u] = __ldg(bp4 + v);
-                cnt[u] = __ldg(bp + ((v >> vec_shift) << slot_shift) + rot);   // the slot's fill count (entry 0)
+                cnt[u] = by_shuffle ? 0u : (uint32_t)__ldg(bp + ((v >> vec_shift) << slot_shift) + rot);
             } else {
+                x[u] = make_uint4(0, 0, 0, 0);
                 cnt[u] = 0;
             }
         }
+    };
+    uint4 x[UNROLL], xn[UNROLL];
+    uint32_t cnt[UNROLL], cntn[UNROLL];
+    if (n_rounds) load_round(0, x, cnt);
+    {
+        uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
+        for (int i = tid; i < PART_BINS / 4; i += BUCKET_THREADS) h4[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    for (uint32_t r = 0; r < n_rounds; r++) {
+        if (r + 1 < n_rounds) load_round(r + 1, xn, cntn);
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
-            const uint64_t v = v0 + (uint64_t)u * BUCKET_THREADS;
-            if (cnt[u]) {
+            const uint32_t v = r * (BUCKET_THREADS * UNROLL) + (uint32_t)u * BUCKET_THREADS + tid;   // low bits are all we need
+            uint32_t c = cnt[u];
+            if (by_shuffle) {
+                const uint32_t wsel = owner_half >> 1;
+                const uint32_t word = wsel == 0 ? x[u].x : wsel == 1 ? x[u].y : wsel == 2 ? x[u].z : x[u].w;
+                const int lane = tid & 31;
+                c = __shfl_sync(0xffffffffu, word & 0xFFFFu, (lane & ~(int)vmask) | (int)owner_vec);
+            }
+            if (c) {
                 // logical entries 1..cnt are live; entry e sits at position (e + rot) mod slot, so the
                 // live positions are a cyclic interval: build its bit mask once per vector
-                const uint32_t first = (((uint32_t)v & vmask) * 8u - rot) & smask;     // logical index of entry 0 of the vector
+                const uint32_t first = ((v & vmask) * 8u - rot) & smask;     // logical index of entry 0 of the vector
                 uint32_t valid;
                 if (slot_shift == 5) {
-                    const uint32_t live = (cnt[u] >= 31u ? 0xFFFFFFFFu : ((2u << cnt[u]) - 1u)) & ~1u;    // bits 1..cnt
+                    const uint32_t live = (c >= 31u ? 0xFFFFFFFFu : ((2u << c) - 1u)) & ~1u;    // bits 1..cnt
                     valid = __funnelshift_r(live, live, first) & 0xFFu;
                 } else {
                     valid = 0;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) valid |= ((((first + i) & smask) - 1u) < cnt[u] ? 1u : 0u) << i;
+                    for (int i = 0; i < 8; i++) valid |= ((((first + i) & smask) - 1u) < c ? 1u : 0u) << i;
                 }
                 hist_add8(hbase, x[u], valid);
             }
         }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) { x[u] = xn[u]; cnt[u] = cntn[u]; }
     }
     __syncthreads();
     // level k: this bucket's 16384 bins, and level k-1 on the way (kept in registers)
