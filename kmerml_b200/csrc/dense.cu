@@ -518,7 +518,8 @@ __device__ __noinline__ void overflow_push(uint32_t* ov, unsigned int* ov_count,
 template <int SLOT_SHIFT>
 struct SlotSink {
     static constexpr uint32_t slot_shift = SLOT_SHIFT;         // log2(slot entries)
-    static constexpr uint32_t slot_cap = (1u << SLOT_SHIFT) - 1u;   // slot entries - 1 (entry 0 holds the count)
+    static constexpr uint32_t slot_cap = (1u << SLOT_SHIFT) - 1u;   // slot entries - 1 (a mask)
+    static constexpr uint32_t slot_size = 1u << SLOT_SHIFT;
     // typed shared-memory pointers (not inline asm): the compiler can then keep several windows'
     // atomics in flight before the first returned position is consumed
     uint32_t* __restrict__ cnt;        // cnt[nb]
@@ -528,10 +529,10 @@ struct SlotSink {
     __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
         const uint32_t b = idx >> (2 * PART_LOW);
         const uint32_t pos = atomicAdd(cnt + b, 1u);
-        if (pos < slot_cap) {
+        if (pos < slot_size) {
             // entry e of bucket b lives at position (e + 2b) mod slot: the order inside a slot is
             // irrelevant, and the rotation spreads the random buckets over all 32 banks
-            const uint32_t phys = (1u + pos + 2u * b) & slot_cap;
+            const uint32_t phys = (pos + 2u * b) & slot_cap;
             staged[(b << slot_shift) + phys] = (uint16_t)(idx & (PART_BINS - 1));
         } else {
             overflow_push(ov, ov_count, idx);
@@ -554,13 +555,13 @@ struct SlotSink {
 #pragma unroll
         for (int u = 0; u < N; u++) {
             worst = max(worst, pos[u]);
-            if (pos[u] < slot_cap)
-                staged[(b[u] << slot_shift) + ((1u + pos[u] + 2u * b[u]) & slot_cap)] = (uint16_t)(idx[u] & (PART_BINS - 1));
+            if (pos[u] < slot_size)
+                staged[(b[u] << slot_shift) + ((pos[u] + 2u * b[u]) & slot_cap)] = (uint16_t)(idx[u] & (PART_BINS - 1));
         }
-        if (worst >= slot_cap) {                                                // rare: some slot is full
+        if (worst >= slot_size) {                                                // rare: some slot is full
 #pragma unroll
             for (int u = 0; u < N; u++)
-                if (pos[u] >= slot_cap) overflow_push(ov, ov_count, idx[u]);
+                if (pos[u] >= slot_size) overflow_push(ov, ov_count, idx[u]);
         }
     }
 };
@@ -624,34 +625,42 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     // ((b * n_tiles + t) << slot_shift)
     constexpr int vec_shift = slot_shift - 3;                               // uint4 vectors per slot
     uint16_t* pg = payload + (size_t)gt.tile0 * STAGE_ENTRIES;
-    const uint4* src = reinterpret_cast<const uint4*>(sm.staged);
     const uint32_t b0 = (uint32_t)tid >> vec_shift, o = (uint32_t)tid & ((1u << vec_shift) - 1u);
     const size_t stride = (((size_t)(COUNT_THREADS >> vec_shift) * gt.n_tiles) << slot_shift) / 8;
     unsigned n = 0;
+    // Unused slot entries hold a padding value >= PART_BINS that the bucket kernel counts into a dummy
+    // bin, so it needs neither fill counts nor validity tests.  The padding of (tile t, vector o of the
+    // slot, entry e) is PART_BINS + ((t * vectors_per_slot + o) & 31) + 32 e: the 32 lanes of a bucket-
+    // kernel warp read 32 consecutive vectors, and for every e their dummy bins fall into 32 banks.
+    auto padding = [&](uint32_t t_local) -> uint4 {
+        const uint32_t L = ((t_local << vec_shift) + o) & 31u;
+        const uint32_t w0 = ((uint32_t)PART_BINS | ((uint32_t)(PART_BINS + 32) << 16)) + L * 0x00010001u;
+        return make_uint4(w0, w0 + 0x00400040u, w0 + 0x00800080u, w0 + 0x00C000C0u);
+    };
+    {
+        const uint4 pad = padding(sl.tile0 - gt.tile0);
+        uint4* st = reinterpret_cast<uint4*>(sm.staged);
+#pragma unroll
+        for (int j = 0; j < STAGE_ENTRIES / 8 / COUNT_THREADS; j++) st[tid + j * COUNT_THREADS] = pad;
+        // (walk_slice starts with a __syncthreads)
+    }
     walk_slice(buf, g, sl, P, sink, tails, tc, [&](uint32_t tile_no) {
         // (the walk of the tile ended with a __syncthreads; the next tile's placements start after
         // another one.)  Vector v = tid + 512 j belongs to bucket (tid >> vec_shift) + (512 >> vec_shift) j:
-        // the destination advances by a constant stride, one add per 128-bit store.  The vector that
-        // holds the slot's entry 0 (at the bucket's rotation) gets the fill count patched in on the way
-        // out; its thread is the only one that reads and clears the bucket's counter.
+        // the destination advances by a constant stride, one add per 128-bit store.  Each vector is
+        // replaced by the next tile's padding as soon as it has been read.
+        for (int b = tid; b < nb; b += COUNT_THREADS) {
+            n += sm.cnt[b];                                  // every window, also those that found the slot full
+            sm.cnt[b] = 0;
+        }
         const uint32_t t_local = sl.tile0 + tile_no - gt.tile0;
+        const uint4 pad = padding(t_local + 1);
+        uint4* st = reinterpret_cast<uint4*>(sm.staged);
         uint4* dst = reinterpret_cast<uint4*>(pg + (((size_t)b0 * gt.n_tiles + t_local) << slot_shift)) + o;
 #pragma unroll
         for (int j = 0; j < STAGE_ENTRIES / 8 / COUNT_THREADS; j++) {
-            uint4 x = src[tid + j * COUNT_THREADS];
-            const uint32_t b = b0 + (uint32_t)j * (COUNT_THREADS >> vec_shift);
-            const uint32_t rot = (2u * b) & sink.slot_cap;
-            if (o == (rot >> 3)) {
-                const uint32_t c = sm.cnt[b];
-                sm.cnt[b] = 0;
-                n += c;
-                const uint32_t e0 = c < sink.slot_cap ? c : sink.slot_cap;
-                const uint32_t wsel = (rot & 7u) >> 1;                  // rot is even: low half of this word
-                x.x = wsel == 0 ? (x.x & 0xFFFF0000u) | e0 : x.x;
-                x.y = wsel == 1 ? (x.y & 0xFFFF0000u) | e0 : x.y;
-                x.z = wsel == 2 ? (x.z & 0xFFFF0000u) | e0 : x.z;
-                x.w = wsel == 3 ? (x.w & 0xFFFF0000u) | e0 : x.w;
-            }
+            const uint4 x = st[tid + j * COUNT_THREADS];
+            st[tid + j * COUNT_THREADS] = pad;
             dst[j * stride] = x;
         }
     });
@@ -666,7 +675,7 @@ struct LevelInfo {                     // per level: index into the caller's k_l
 constexpr int BUCKET_THREADS = 512;
 
 struct BucketSmem {
-    uint32_t hist[PART_BINS];          // 64 KB; reused in place by the in-bucket cascade
+    uint32_t hist[PART_BINS + 256];    // 64 KB (reused in place by the in-bucket cascade) + the padding's dummy bins
     unsigned long long tot[16];
     uint32_t* lvl_counts[16];          // per level: this bucket's slice of the count row
     float* lvl_freq[16];               //            ... of the frequency row (nullptr: not requested)
@@ -674,16 +683,14 @@ struct BucketSmem {
 };
 static_assert(sizeof(BucketSmem) <= 74 * 1024, "three bucket CTAs must fit in one SM's shared memory");
 
-// 8 payload entries of one 128-bit vector.  `valid` has bit i set when entry i of the vector is one of
-// the slot's cnt live entries (see the rotation in SlotSink): one predicate test per entry.
-__device__ __forceinline__ void hist_add8(uint32_t hbase, const uint4& x, uint32_t valid) {
+// 8 payload entries of one 128-bit vector: live ones are bins of the bucket, padding goes to the
+// dummy bins behind them (see partition_kernel).
+__device__ __forceinline__ void hist_add8(uint32_t hbase, const uint4& x) {
     const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        if (valid & (1u << (2 * i)))
-            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + ((w[i] & 0xFFFFu) << 2)) : "memory");
-        if (valid & (2u << (2 * i)))
-            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + ((w[i] >> 16) << 2)) : "memory");
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + ((w[i] & 0xFFFFu) << 2)) : "memory");
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + ((w[i] >> 16) << 2)) : "memory");
     }
 }
 
@@ -732,70 +739,32 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
     const uint16_t* bp = payload + (size_t)gt.tile0 * STAGE_ENTRIES + (((size_t)b * gt.n_tiles) << slot_shift);
     const uint4* bp4 = reinterpret_cast<const uint4*>(bp);
     const int vec_shift = slot_shift - 3;
-    const uint32_t vmask = (1u << vec_shift) - 1u;
     const uint64_t n_vec = (uint64_t)gt.n_tiles << vec_shift;
-    const uint32_t smask = (1u << slot_shift) - 1u;
-    const uint32_t rot = (2u * b) & smask;                       // partition_kernel's per-bucket rotation
-    // Software pipeline: round r + 1 is in flight while round r goes into the histogram (round 0 was
-    // issued before the histogram was cleared).  Every thread runs every round, so that the 4 (16) lanes
-    // that hold one slot's vectors can pass the slot's fill count around with a shuffle instead of a
-    // second load; slots wider than a warp's 32 vectors still load it.
-    constexpr int UNROLL = 2;
+    // Software pipeline: round r + 1 is in flight while round r goes into the histogram (round 0 is
+    // issued before the histogram is cleared).
+    constexpr int UNROLL = 4;
     const uint32_t n_rounds = (uint32_t)((n_vec + (uint64_t)BUCKET_THREADS * UNROLL - 1) / ((uint64_t)BUCKET_THREADS * UNROLL));
-    const bool by_shuffle = vec_shift <= 5;
-    const uint32_t owner_vec = rot >> 3;                          // which vector of a slot holds entry 0 ...
-    const uint32_t owner_half = rot & 7u;                         // ... and where in it (even: low half of a word)
-    auto load_round = [&](uint32_t r, uint4* x, uint32_t* cnt) {
+    auto load_round = [&](uint32_t r, uint4* x) {
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const uint64_t v = (uint64_t)r * (BUCKET_THREADS * UNROLL) + (uint64_t)u * BUCKET_THREADS + tid;
-            if (v < n_vec) {
-                x[u] = __ldg(bp4 + v);
-                cnt[u] = by_shuffle ? 0u : (uint32_t)__ldg(bp + ((v >> vec_shift) << slot_shift) + rot);
-            } else {
-                x[u] = make_uint4(0, 0, 0, 0);
-                cnt[u] = 0;
-            }
+            // (beyond the end: eight times dummy bin 0)
+            x[u] = v < n_vec ? __ldg(bp4 + v) : make_uint4(0x40004000u, 0x40004000u, 0x40004000u, 0x40004000u);
         }
     };
     uint4 x[UNROLL], xn[UNROLL];
-    uint32_t cnt[UNROLL], cntn[UNROLL];
-    if (n_rounds) load_round(0, x, cnt);
+    if (n_rounds) load_round(0, x);
     {
         uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
         for (int i = tid; i < PART_BINS / 4; i += BUCKET_THREADS) h4[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     for (uint32_t r = 0; r < n_rounds; r++) {
-        if (r + 1 < n_rounds) load_round(r + 1, xn, cntn);
+        if (r + 1 < n_rounds) load_round(r + 1, xn);
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            const uint32_t v = r * (BUCKET_THREADS * UNROLL) + (uint32_t)u * BUCKET_THREADS + tid;   // low bits are all we need
-            uint32_t c = cnt[u];
-            if (by_shuffle) {
-                const uint32_t wsel = owner_half >> 1;
-                const uint32_t word = wsel == 0 ? x[u].x : wsel == 1 ? x[u].y : wsel == 2 ? x[u].z : x[u].w;
-                const int lane = tid & 31;
-                c = __shfl_sync(0xffffffffu, word & 0xFFFFu, (lane & ~(int)vmask) | (int)owner_vec);
-            }
-            if (c) {
-                // logical entries 1..cnt are live; entry e sits at position (e + rot) mod slot, so the
-                // live positions are a cyclic interval: build its bit mask once per vector
-                const uint32_t first = ((v & vmask) * 8u - rot) & smask;     // logical index of entry 0 of the vector
-                uint32_t valid;
-                if (slot_shift == 5) {
-                    const uint32_t live = (c >= 31u ? 0xFFFFFFFFu : ((2u << c) - 1u)) & ~1u;    // bits 1..cnt
-                    valid = __funnelshift_r(live, live, first) & 0xFFu;
-                } else {
-                    valid = 0;
+        for (int u = 0; u < UNROLL; u++) hist_add8(hbase, x[u]);
 #pragma unroll
-                    for (int i = 0; i < 8; i++) valid |= ((((first + i) & smask) - 1u) < c ? 1u : 0u) << i;
-                }
-                hist_add8(hbase, x[u], valid);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) { x[u] = xn[u]; cnt[u] = cntn[u]; }
+        for (int u = 0; u < UNROLL; u++) x[u] = xn[u];
     }
     __syncthreads();
     // level k: this bucket's 16384 bins, and level k-1 on the way (kept in registers)
