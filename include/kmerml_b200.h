@@ -130,6 +130,26 @@ int kmerml_first_occurrence(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nb
                             int min_record_len, uint32_t *d_first, void *stream);
 
 /*
+ * Text of a k{k}.txt file from a dense count row: one line "<digits>\t<count>\n" per observed k-mer
+ * (digits A0 T1 C2 G3), lines in order of first occurrence -- the writer of
+ * kmerml/kmers/generate.py:68-91.  d_counts: uint32[4^k], one genome's row of one k
+ * (kmerml_count_dense_batch); d_first: kmerml_first_occurrence's output for the same genome, k and
+ * min_record_len.  KMERML_FLAG_CANONICAL: d_counts is a canonical row.  max_lines bounds the observed
+ * k-mers and text_cap the bytes of d_text; *h_lines / *h_text_len always receive the real numbers, and
+ * when one exceeds its bound nothing is written: re-size and call again.  Synchronises `stream`.
+ */
+int kmerml_format_kmer_file(kmerml_ctx *ctx, int k, const uint32_t *d_counts, const uint32_t *d_first,
+                            unsigned flags, uint64_t max_lines, uint8_t *d_text, uint64_t text_cap,
+                            uint64_t *h_text_len, uint64_t *h_lines, void *stream);
+
+/*
+ * The same text from k-mers that are already in line order (kmerml_count_sparse's output sorted by
+ * first occurrence): d_codes uint64[n] 2-bit packed (A0 C1 G2 T3), d_counts uint32[n], k <= 32.
+ */
+int kmerml_format_kmer_lines(kmerml_ctx *ctx, int k, const uint64_t *d_codes, const uint32_t *d_counts,
+                             uint64_t n, uint8_t *d_text, uint64_t text_cap, uint64_t *h_text_len, void *stream);
+
+/*
  * Record table of one FASTA file resident in HBM: byte offsets of the header lines
  * (unordered; sort them) -- what Bio.SeqIO.parse would yield one record for
  * (kmerml/kmers/generate.py:39).  *h_count receives the number found (may exceed cap;

@@ -58,6 +58,9 @@ def load():
     L.kmerml_find_records.argtypes = [vp, vp, u64, vp, u32, ctypes.POINTER(ctypes.c_uint32), vp]
     L.kmerml_records_short.argtypes = [vp, vp, u64, vp, u32, i32, vp, vp]
     L.kmerml_genome_stats.argtypes = [vp, vp, u64, vp, vp]
+    p64 = ctypes.POINTER(ctypes.c_uint64)
+    L.kmerml_format_kmer_file.argtypes = [vp, i32, vp, vp, u32, u64, vp, u64, p64, p64, vp]
+    L.kmerml_format_kmer_lines.argtypes = [vp, i32, vp, vp, u64, vp, u64, p64, vp]
     L.kmerml_static_features.argtypes = [vp, i32, i32, vp, vp]
     L.kmerml_normalize_rows.argtypes = [vp, vp, u64, vp, i32, u64, vp, u64, vp]
     L.kmerml_pairwise_distance.argtypes = [vp, vp, i32, u64, i32, u64, i32, vp, vp, vp]
@@ -78,7 +81,7 @@ EXPORTS = [
     "kmerml_count_dense_host", "kmerml_first_occurrence", "kmerml_profile_enable",
     "kmerml_profile_read", "kmerml_find_records", "kmerml_records_short", "kmerml_static_features",
     "kmerml_normalize_rows", "kmerml_pairwise_distance", "kmerml_count_dense_range",
-    "kmerml_count_sparse", "kmerml_genome_stats",
+    "kmerml_count_sparse", "kmerml_genome_stats", "kmerml_format_kmer_file", "kmerml_format_kmer_lines",
 ]
 
 

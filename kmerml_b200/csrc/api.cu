@@ -692,6 +692,36 @@ int kmerml_records_short(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbyte
                                (cudaStream_t)stream);
 }
 
+int kmerml_format_kmer_file(kmerml_ctx* ctx, int k, const uint32_t* d_counts, const uint32_t* d_first, unsigned flags,
+                            uint64_t max_lines, uint8_t* d_text, uint64_t text_cap, uint64_t* h_text_len,
+                            uint64_t* h_lines, void* stream) {
+    if (!ctx || !d_counts || !d_first || !h_text_len || !h_lines) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (k < 1 || k > KMERML_MAX_DENSE_K) return fail(KMERML_ERR_ARG, "k out of range");
+    if (text_cap && !d_text) return fail(KMERML_ERR_ARG, "d_text is null");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    Workspace& ws = ctx->ws[0];
+    max_lines = std::max<uint64_t>(max_lines, 1);
+    int rc = ws.part.ensure(format_workspace_bytes(1ull << (2 * k), max_lines));
+    if (rc) return rc;
+    return run_format_dense(ws.part.p, k, d_counts, d_first, (flags & KMERML_FLAG_CANONICAL) != 0, max_lines, d_text,
+                            text_cap, h_text_len, h_lines, (cudaStream_t)stream);
+}
+
+int kmerml_format_kmer_lines(kmerml_ctx* ctx, int k, const uint64_t* d_codes, const uint32_t* d_counts, uint64_t n,
+                             uint8_t* d_text, uint64_t text_cap, uint64_t* h_text_len, void* stream) {
+    if (!ctx || !h_text_len) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (k < 1 || k > KMERML_MAX_K) return fail(KMERML_ERR_ARG, "k must be in 1..32");
+    if (n && (!d_codes || !d_counts)) return fail(KMERML_ERR_ARG, "null input pointer");
+    if (text_cap && !d_text) return fail(KMERML_ERR_ARG, "d_text is null");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    Workspace& ws = ctx->ws[0];
+    int rc = ws.part.ensure(format_workspace_bytes(1, std::max<uint64_t>(n, 1)));
+    if (rc) return rc;
+    return run_format_lines(ws.part.p, k, d_codes, d_counts, n, d_text, text_cap, h_text_len, (cudaStream_t)stream);
+}
+
 int kmerml_genome_stats(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, uint64_t* d_out, void* stream) {
     if (!ctx || !d_out || (nbytes && !d_fasta)) return fail(KMERML_ERR_ARG, "null pointer argument");
     DeviceGuard guard(ctx->device);

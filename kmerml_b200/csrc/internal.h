@@ -119,6 +119,14 @@ int run_sparse_in(void* workspace, const uint8_t* d_fasta, uint64_t nbytes, int 
                   uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
                   uint64_t* h_unique, uint64_t* h_windows, cudaStream_t s);
 
+// ---- k{k}.txt text (format.cu) --------------------------------------------------
+size_t format_workspace_bytes(uint64_t n_bins, uint64_t max_lines);
+int run_format_dense(void* workspace, int k, const uint32_t* d_counts, const uint32_t* d_first, bool canonical,
+                     uint64_t max_lines, uint8_t* d_text, uint64_t text_cap, uint64_t* h_len, uint64_t* h_lines,
+                     cudaStream_t s);
+int run_format_lines(void* workspace, int k, const uint64_t* d_codes, const uint32_t* d_counts, uint64_t n,
+                     uint8_t* d_text, uint64_t text_cap, uint64_t* h_len, cudaStream_t s);
+
 // ---- launchers (features.cu) --------------------------------------------------
 int launch_scan_records(const uint8_t* d_fasta, uint64_t nbytes, int need, unsigned long long* d_offsets,
                         uint8_t* d_short, uint32_t cap, uint32_t* d_count, cudaStream_t s);

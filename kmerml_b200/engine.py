@@ -282,3 +282,43 @@ def kmer_count_stats_device(counts_row, k):
     return {"k_value": k, "total_kmers": total, "unique_kmers": int(n), "max_count": int(srt[-1].item()),
             "min_count": int(srt[0].item()), "mean_count": total / n, "median_count": median,
             "estimated_genome_size": total + k - 1}
+
+
+def format_kmer_file_device(counts_row, first, k, *, canonical=False):
+    """uint8 tensor: the text of the reference's k{k}.txt for one genome (kmerml/kmers/generate.py:68-91) from
+    its dense count row (int32 storage of uint32, 4^k) and first-occurrence offsets; lines in dict insertion order."""
+    ctx = _lib.context(counts_row.device.index)
+    L = _lib.load()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(counts_row.device).cuda_stream)
+    max_lines = int(torch.count_nonzero(counts_row).item())
+    text = torch.empty(max(max_lines * (k + 4), 16), dtype=torch.uint8, device=counts_row.device)
+    while True:
+        nlen, nlines = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _lib.check(L.kmerml_format_kmer_file(ctx.handle, int(k), counts_row.data_ptr(), first.data_ptr(),
+                                             _lib.FLAG_CANONICAL if canonical else 0, max(max_lines, 1), text.data_ptr(),
+                                             text.numel(), ctypes.byref(nlen), ctypes.byref(nlines), stream))
+        if nlines.value > max_lines:
+            max_lines = int(nlines.value)
+            continue
+        if nlen.value > text.numel():                    # counts with many digits: exact size is known now
+            text = torch.empty(int(nlen.value), dtype=torch.uint8, device=counts_row.device)
+            continue
+        return text[:int(nlen.value)]
+
+
+def format_kmer_lines_device(codes, counts, k):
+    """uint8 tensor: the same text from k-mers already in line order (int64 storage of uint64 codes, int32 counts)."""
+    ctx = _lib.context(codes.device.index)
+    L = _lib.load()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(codes.device).cuda_stream)
+    n = int(codes.numel())
+    text = torch.empty(max(n * (k + 4), 16), dtype=torch.uint8, device=codes.device)
+    while True:
+        nlen = ctypes.c_uint64(0)
+        _lib.check(L.kmerml_format_kmer_lines(ctx.handle, int(k), codes.data_ptr() if n else None,
+                                              counts.data_ptr() if n else None, n, text.data_ptr(), text.numel(),
+                                              ctypes.byref(nlen), stream))
+        if nlen.value > text.numel():
+            text = torch.empty(int(nlen.value), dtype=torch.uint8, device=codes.device)
+            continue
+        return text[:int(nlen.value)]

@@ -119,19 +119,12 @@ class KmerExtractor:
             if k > _lib.MAX_DENSE_K:                     # sparse path: distinct k-mers, sorted by first occurrence
                 keys, cnts, first, _ = engine.count_sparse_device(dev, k, min_record_len=max_k, canonical=self.canonical)
                 order = torch.argsort(first.to(torch.int64) & 0xFFFFFFFF, stable=True)
-                codes = keys[order].cpu().numpy().view(np.uint64)
-                self._write_lines(organism_id, k, format_kmer_lines(codes, cnts[order].cpu().numpy().view(np.uint32), k))
-                continue
-            counts = res.counts_numpy(0, k)
-            observed = np.nonzero(counts)[0]
-            if observed.size:
-                first = engine.first_occurrence_device(dev, k, min_record_len=max_k).cpu().numpy().view(np.uint32)
-                if self.canonical:
-                    # a canonical bin first appears where either strand's k-mer first does
-                    from ..engine import revcomp_codes
-                    first = np.minimum(first, first[revcomp_codes(k)])
-                observed = observed[np.argsort(first[observed], kind="stable")]
-            self._write_lines(organism_id, k, format_kmer_lines(observed, counts[observed], k))
+                text = engine.format_kmer_lines_device(keys[order].contiguous(), cnts[order].contiguous(), k)
+            else:                                        # dense row + first-occurrence offsets -> text, on the GPU
+                row = res.counts_of(0, k)
+                first = engine.first_occurrence_device(dev, k, min_record_len=max_k)
+                text = engine.format_kmer_file_device(row, first, k, canonical=self.canonical)
+            self._write_lines(organism_id, k, text.cpu().numpy())
         return organism_id
 
     # ------------------------------------------------------------- file output

@@ -203,3 +203,44 @@ def test_genome_and_kmer_metadata():
         assert s["max_count"] == counts.max() and s["min_count"] == counts.min()
         assert s["mean_count"] == float(counts.mean()) and s["median_count"] == float(np.median(counts))
         assert s["estimated_genome_size"] == counts.sum() + k - 1
+
+
+def test_gpu_formatter_matches_golden_text():
+    """kmerml_format_kmer_file / _lines: the k{k}.txt text straight from the GPU, byte-identical to the files the
+    unmodified reference wrote (tests/golden) -- dense rows, canonical rows and the sparse path."""
+    import torch
+    from kmerml_b200 import engine
+    from kmerml_b200.kmers.generate import format_kmer_lines
+    for c in golden_extract_cases():
+        if not len(c["fasta"]):
+            continue
+        dev = torch.from_numpy(np.frombuffer(c["fasta"], np.uint8).copy()).cuda()
+        max_k = max(c["k_values"])
+        ks = [k for k in dict.fromkeys(c["k_values"]) if k <= 12]
+        if ks:
+            res = engine.count_dense_device(dev, [0, dev.numel()], ks, min_record_len=max_k, want_freq=False)
+            for k in ks:
+                first = engine.first_occurrence_device(dev, k, min_record_len=max_k)
+                text = engine.format_kmer_file_device(res.counts_of(0, k), first, k).cpu().numpy().tobytes()
+                assert text == c["files"][str(k)].encode(), (c["name"], k)
+        for k in [k for k in dict.fromkeys(c["k_values"]) if k > 14][:1]:
+            keys, cnts, first, _ = engine.count_sparse_device(dev, k, min_record_len=max_k)
+            order = torch.argsort(first.to(torch.int64) & 0xFFFFFFFF, stable=True)
+            text = engine.format_kmer_lines_device(keys[order].contiguous(), cnts[order].contiguous(), k)
+            assert text.cpu().numpy().tobytes() == c["files"][str(k)].encode(), (c["name"], k)
+    # canonical rows and counts with several digits against the host formatter
+    rng = np.random.default_rng(8)
+    data = b">r\n" + np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 300_000)].tobytes() + b"\n>s\n" + b"A" * 5000 + b"\n"
+    dev = torch.from_numpy(np.frombuffer(data, np.uint8).copy()).cuda()
+    for canonical in (False, True):
+        res = engine.count_dense_device(dev, [0, dev.numel()], [3, 7], canonical=canonical, want_freq=False)
+        for k in (3, 7):
+            first = engine.first_occurrence_device(dev, k, min_record_len=7)
+            got = engine.format_kmer_file_device(res.counts_of(0, k), first, k, canonical=canonical).cpu().numpy().tobytes()
+            counts = res.counts_numpy(0, k)
+            f = first.cpu().numpy().view(np.uint32)
+            if canonical:
+                f = np.minimum(f, f[engine.revcomp_codes(k)])
+            obs = np.nonzero(counts)[0]
+            obs = obs[np.argsort(f[obs], kind="stable")]
+            assert got == bytes(format_kmer_lines(obs, counts[obs], k)), (canonical, k)
