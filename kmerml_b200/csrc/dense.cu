@@ -89,6 +89,11 @@ struct GlobalSink {
 #pragma unroll
         for (int i = 0; i < 8; i++) count(w[i], p[i]);
     }
+    __device__ __forceinline__ void count8_tail(const uint32_t* w, const uint64_t* p, bool last) {
+#pragma unroll
+        for (int i = 0; i < 7; i++) count(w[i], p[i]);
+        if (last) count(w[7], p[7]);
+    }
 };
 
 struct SmemSink {
@@ -105,6 +110,11 @@ struct SmemSink {
     __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t* p) {
 #pragma unroll
         for (int i = 0; i < 8; i++) count(w[i], p[i]);
+    }
+    __device__ __forceinline__ void count8_tail(const uint32_t* w, const uint64_t* p, bool last) {
+#pragma unroll
+        for (int i = 0; i < 7; i++) count(w[i], p[i]);
+        if (last) count(w[7], p[7]);
     }
 };
 
@@ -132,6 +142,10 @@ struct Packed16Sink {
         place<4>(w);
     }
     __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t*) { place<8>(w); }
+    __device__ __forceinline__ void count8_tail(const uint32_t* w, const uint64_t*, bool last) {
+        place<7>(w);
+        if (last) count(w[7], 0);
+    }
     template <int N>
     __device__ __forceinline__ void place(const uint32_t* idx) {
         uint32_t old[N];
@@ -159,6 +173,11 @@ struct FirstSink {
     __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t* p) {
 #pragma unroll
         for (int i = 0; i < 8; i++) count(w[i], p[i]);
+    }
+    __device__ __forceinline__ void count8_tail(const uint32_t* w, const uint64_t* p, bool last) {
+#pragma unroll
+        for (int i = 0; i < 7; i++) count(w[i], p[i]);
+        if (last) count(w[7], p[7]);
     }
 };
 
@@ -188,7 +207,11 @@ struct TileCtx {                      // shared-memory state of the tile loop
 // of the 32-byte chunk, SWAR classification, bit-compaction of clean chunks and
 // header-line detection (phase 1); then either the funnel-shift emission of a clean
 // chunk whose left neighbour is clean too, or the generic byte walker (phase 2).
-template <class Sink, class Tails, class PerTile>
+// EARLY_LOAD: when the next tile's chunk is requested -- at the start of the current tile (a true
+// prefetch; needs 8 registers across the whole tile: the histogram kernels have them) or right before
+// the tile's closing barrier (the partition kernel, whose placement code needs every register: there
+// the early prefetch was spilled to local memory at once, measured).
+template <bool EARLY_LOAD, class Sink, class Tails, class PerTile>
 __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, const Genome& g, const Slice& sl,
                                            const DenseParams& P, Sink& sink, const Tails& tails, const TileCtx& tc,
                                            PerTile&& per_tile) {
@@ -222,11 +245,13 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
         }
         return true;
     };
-    uint32_t w[CHUNK / 4];
+    uint32_t w[CHUNK / 4], wn[CHUNK / 4];
     bool full = load_chunk(sl.begin, w);
     uint32_t tile_no = 0;
     for (uint64_t tb = sl.begin; tb < end; tb += TILE_BYTES, tile_no++) {
         uint8_t* flags = tc.flags + (tile_no & 1u) * COUNT_THREADS;
+        bool full_next = false;
+        if (EARLY_LOAD) full_next = load_chunk(tb + TILE_BYTES, wn);
         const uint64_t cb = tb + (uint64_t)tid * CHUNK;
         const uint64_t cs = cb > g.lo ? cb : g.lo;
         const uint64_t ce = cb + CHUNK < g.hi ? cb + CHUNK : g.hi;
@@ -274,14 +299,16 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
                 walk_chunk(g, cs, ce, in_hdr, P, sink, tails, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
             }
         }
-        // the next tile's chunk: in flight while the CTA waits at the barrier and runs the per-tile hook
-        full = load_chunk(tb + TILE_BYTES, w);
+        if (!EARLY_LOAD) full_next = load_chunk(tb + TILE_BYTES, wn);    // in flight during the barrier and the hook
         __syncthreads();
         if (tid == COUNT_THREADS - 1) {
             tc.prev_tile[0] = (has && clean && !in_hdr) ? 1u : 0u;
             tc.prev_tile[1] = cc.last16;
         }
         per_tile(tile_no);
+        full = full_next;
+#pragma unroll
+        for (int i = 0; i < CHUNK / 4; i++) w[i] = wn[i];
     }
 }
 
@@ -448,7 +475,7 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
         FirstSink sink;
         sink.first = first; sink.file_lo = gd.file_lo;
         NoTails nt;
-        walk_slice(buf, g, sl, P, sink, nt, tc, [](uint32_t) {});
+        walk_slice<true>(buf, g, sl, P, sink, nt, tc, [](uint32_t) {});
         return;
     }
     DevTails tails;
@@ -456,18 +483,18 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
     if (MODE == 0) {
         GlobalSink sink;
         sink.top = lm.ptr(sl.genome, P.k); sink.n = 0;
-        walk_slice(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
+        walk_slice<true>(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
         n = sink.n;
     } else if (MODE == 3) {
         for (int i = tid; i < 32768; i += COUNT_THREADS) sh_hist[i] = 0;
         Packed16Sink sink;
         sink.hist = sh_hist; sink.row = lm.ptr(sl.genome, 8); sink.n = 0;
-        walk_slice(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
+        walk_slice<true>(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
         n = sink.n;
     } else {
         SmemSink sink;
         sink.sbase = (uint32_t)__cvta_generic_to_shared(sh_hist); sink.n = 0;
-        walk_slice(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
+        walk_slice<true>(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
         n = sink.n;
     }
     const unsigned long long total = block_sum_u32(n, &sh_total);
@@ -544,18 +571,21 @@ struct SlotSink {
         const uint32_t idx[4] = {i0, i1, i2, i3};
         place<4>(idx);
     }
-    __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t*) { place<8>(w); }
+    __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t*) { place<8>(w, true); }
+    __device__ __forceinline__ void count8_tail(const uint32_t* w, const uint64_t*, bool last) { place<8>(w, last); }
+    // `last_live` = false: the N-th window does not exist (a chunk of 31 bases); its atomic is skipped
+    // and its returned position reads as 0 with the store predicated off
     template <int N>
-    __device__ __forceinline__ void place(const uint32_t* idx) {
+    __device__ __forceinline__ void place(const uint32_t* idx, bool last_live = true) {
         uint32_t b[N], pos[N], worst = 0;
 #pragma unroll
         for (int u = 0; u < N; u++) b[u] = idx[u] >> (2 * PART_LOW);
 #pragma unroll
-        for (int u = 0; u < N; u++) pos[u] = atomicAdd(cnt + b[u], 1u);
+        for (int u = 0; u < N; u++) pos[u] = (u < N - 1 || last_live) ? atomicAdd(cnt + b[u], 1u) : 0u;
 #pragma unroll
         for (int u = 0; u < N; u++) {
             worst = max(worst, pos[u]);
-            if (pos[u] < slot_size)
+            if (pos[u] < slot_size && (u < N - 1 || last_live))
                 staged[(b[u] << slot_shift) + ((pos[u] + 2u * b[u]) & slot_cap)] = (uint16_t)(idx[u] & (PART_BINS - 1));
         }
         if (worst >= slot_size) {                                                // rare: some slot is full
@@ -644,7 +674,7 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
         for (int j = 0; j < STAGE_ENTRIES / 8 / COUNT_THREADS; j++) st[tid + j * COUNT_THREADS] = pad;
         // (walk_slice starts with a __syncthreads)
     }
-    walk_slice(buf, g, sl, P, sink, tails, tc, [&](uint32_t tile_no) {
+    walk_slice<false>(buf, g, sl, P, sink, tails, tc, [&](uint32_t tile_no) {
         // (the walk of the tile ended with a __syncthreads; the next tile's placements start after
         // another one.)  Vector v = tid + 512 j belongs to bucket (tid >> vec_shift) + (512 >> vec_shift) j:
         // the destination advances by a constant stride, one add per 128-bit store.  Each vector is
@@ -911,6 +941,7 @@ struct NullSink {
     __device__ __forceinline__ void count(uint32_t, uint64_t) {}
     __device__ __forceinline__ void count4(uint32_t, uint32_t, uint32_t, uint32_t, uint64_t, uint64_t, uint64_t, uint64_t) {}
     __device__ __forceinline__ void count8(const uint32_t*, const uint64_t*) {}
+    __device__ __forceinline__ void count8_tail(const uint32_t*, const uint64_t*, bool) {}
 };
 struct RescanTails {
     const TailApply* ap;
@@ -940,7 +971,7 @@ tails_rescan_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict
         NullSink sink;
         RescanTails tails;
         tails.ap = &ap; tails.genome = sl.genome;
-        walk_slice(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
+        walk_slice<true>(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
         __syncthreads();
     }
 }

@@ -400,8 +400,8 @@ KM_HD void emit_clean(const CleanChunk& c, uint32_t carry16, uint64_t cs, const 
         return (sft >= 32 ? funnel_r(c.hi, carry16, sft - 32) : funnel_r(c.lo, c.hi, sft)) & mask;
     };
     auto at = [&](int j) -> uint64_t { return cs + (uint64_t)(j + (j >= c.nl ? 1 : 0)); };   // byte of base j
-    // a clean chunk has >= 31 bases; windows go to the sink four at a time so that a sink with
-    // returning atomics (the partition path) can keep four of them in flight
+    // a clean chunk has >= 31 bases; windows go to the sink eight at a time so that a sink with
+    // returning atomics (the partition path) can keep eight of them in flight
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -411,11 +411,12 @@ KM_HD void emit_clean(const CleanChunk& c, uint32_t carry16, uint64_t cs, const 
         const uint64_t pv[8] = {at(j), at(j + 1), at(j + 2), at(j + 3), at(j + 4), at(j + 5), at(j + 6), at(j + 7)};
         sink.count8(wv, pv);
     }
-    sink.count4(window(24), window(25), window(26), window(27), at(24), at(25), at(26), at(27));
-    sink.count(window(28), at(28));
-    sink.count(window(29), at(29));
-    sink.count(window(30), at(30));
-    if (c.n == 32) sink.count(c.lo & mask, cs + 31);
+    {   // windows 24..30 and, when the chunk holds 32 bases, the 32nd: one more batch of eight
+        const uint32_t wv[8] = {window(24), window(25), window(26), window(27), window(28), window(29), window(30),
+                                c.lo & mask};
+        const uint64_t pv[8] = {at(24), at(25), at(26), at(27), at(28), at(29), at(30), cs + 31};
+        sink.count8_tail(wv, pv, c.n == 32);
+    }
 }
 
 // Does any byte of the chunk's words equal the byte replicated in `pattern`?

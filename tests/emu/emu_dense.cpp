@@ -27,6 +27,7 @@ struct EmuSink {
         count(a, pa); count(b, pb); count(c, pc); count(d, pd);
     }
     void count8(const uint32_t* w, const uint64_t* p) { for (int i = 0; i < 8; i++) count(w[i], p[i]); }
+    void count8_tail(const uint32_t* w, const uint64_t* p, bool last) { for (int i = 0; i < (last ? 8 : 7); i++) count(w[i], p[i]); }
     void tail(int j, uint32_t idx) const { (*tails)[j][idx]++; }
 };
 }  // namespace
