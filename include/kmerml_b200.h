@@ -120,6 +120,30 @@ int kmerml_count_sparse(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbytes
                         uint64_t out_cap, uint64_t *h_unique, uint64_t *h_windows, void *stream);
 
 /*
+ * Multi-GPU unit of the sparse path ("one large genome, sparse k"): the same as
+ * kmerml_count_sparse for the windows whose last base lies in the byte range [range_begin, range_end) of
+ * the file -- begin a multiple of KMERML_SPARSE_RANGE_ALIGN, end too or == nbytes.  The k-1 bases before
+ * the range are read from the file itself, so the ranges of all ranks tile the genome without overlap
+ * bookkeeping; first offsets are relative to the file, not to the range.
+ */
+#define KMERML_SPARSE_RANGE_ALIGN 131072
+int kmerml_count_sparse_range(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbytes, uint64_t range_begin,
+                              uint64_t range_end, int k, int min_record_len, unsigned flags, uint64_t *d_keys,
+                              uint32_t *d_counts, uint32_t *d_first, uint64_t out_cap, uint64_t *h_unique,
+                              uint64_t *h_windows, void *stream);
+
+/*
+ * Merge of partial sparse results (what a rank holds after the all-to-all that routes every k-mer to
+ * the rank owning its key range): n (k-mer, count, first) triples in any order, duplicates allowed ->
+ * distinct k-mers ascending, counts added, smallest first offset kept.  d_first / d_first_out may be
+ * NULL.  *h_unique always receives the number of distinct k-mers; when it exceeds out_cap nothing is
+ * written.  Synchronises `stream`.
+ */
+int kmerml_merge_sparse(kmerml_ctx *ctx, int k, const uint64_t *d_keys, const uint32_t *d_counts,
+                        const uint32_t *d_first, uint64_t n, uint64_t *d_keys_out, uint32_t *d_counts_out,
+                        uint32_t *d_first_out, uint64_t out_cap, uint64_t *h_unique, void *stream);
+
+/*
  * Byte offset (within the genome) of the last base of the first window of every
  * k-mer, UINT32_MAX where the k-mer never occurs: sorting the observed bins by
  * this value gives dict insertion order, i.e. the line order of k{k}.txt

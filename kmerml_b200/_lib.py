@@ -54,6 +54,9 @@ def load():
     L.kmerml_count_dense_range.argtypes = [vp, vp, u64, u64, u64, vp, i32, i32, u32, vp, vp, vp]
     L.kmerml_count_sparse.argtypes = [vp, vp, u64, i32, i32, u32, vp, vp, vp, u64, ctypes.POINTER(ctypes.c_uint64),
                                       ctypes.POINTER(ctypes.c_uint64), vp]
+    L.kmerml_count_sparse_range.argtypes = [vp, vp, u64, u64, u64, i32, i32, u32, vp, vp, vp, u64,
+                                            ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), vp]
+    L.kmerml_merge_sparse.argtypes = [vp, i32, vp, vp, vp, u64, vp, vp, vp, u64, ctypes.POINTER(ctypes.c_uint64), vp]
     L.kmerml_first_occurrence.argtypes = [vp, vp, u64, i32, i32, vp, vp]
     L.kmerml_find_records.argtypes = [vp, vp, u64, vp, u32, ctypes.POINTER(ctypes.c_uint32), vp]
     L.kmerml_records_short.argtypes = [vp, vp, u64, vp, u32, i32, vp, vp]
@@ -82,6 +85,7 @@ EXPORTS = [
     "kmerml_profile_read", "kmerml_find_records", "kmerml_records_short", "kmerml_static_features",
     "kmerml_normalize_rows", "kmerml_pairwise_distance", "kmerml_count_dense_range",
     "kmerml_count_sparse", "kmerml_genome_stats", "kmerml_format_kmer_file", "kmerml_format_kmer_lines",
+    "kmerml_count_sparse_range", "kmerml_merge_sparse",
 ]
 
 

@@ -766,24 +766,61 @@ int kmerml_pairwise_distance(kmerml_ctx* ctx, const void* d_x, int dtype, uint64
     return launch_pairwise(d_x, dtype, stride, n, m, metric, d_gram, d_out32, d_out64, (cudaStream_t)stream);
 }
 
-int kmerml_count_sparse(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, int k, int min_record_len,
-                        unsigned flags, uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_first, uint64_t out_cap,
-                        uint64_t* h_unique, uint64_t* h_windows, void* stream) {
+static int count_sparse_core(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin,
+                             uint64_t range_end, int k, int min_record_len, unsigned flags, uint64_t* d_keys,
+                             uint32_t* d_counts, uint32_t* d_first, uint64_t out_cap, uint64_t* h_unique,
+                             uint64_t* h_windows, void* stream) {
     if (!ctx || !h_unique || !h_windows) return fail(KMERML_ERR_ARG, "null pointer argument");
     if (k < 1 || k > KMERML_MAX_K) return fail(KMERML_ERR_ARG, "k must be in 1..32");
     if (nbytes && !d_fasta) return fail(KMERML_ERR_ARG, "d_fasta is null");
     if (out_cap && (!d_keys || !d_counts)) return fail(KMERML_ERR_ARG, "null output pointer");
     if (nbytes >= 0xFFFFFFFFull) return fail(KMERML_ERR_RANGE, "genome too large for 32-bit offsets");
+    if (range_begin > range_end || range_end > nbytes) return fail(KMERML_ERR_ARG, "byte range outside the file");
+    if (range_begin % KMERML_SPARSE_RANGE_ALIGN || (range_end % KMERML_SPARSE_RANGE_ALIGN && range_end != nbytes))
+        return fail(KMERML_ERR_ARG, "byte range must be aligned to KMERML_SPARSE_RANGE_ALIGN");
     int min_rec = min_record_len > 0 ? min_record_len : k;
     if (min_rec < k) return fail(KMERML_ERR_ARG, "min_record_len must be >= k");
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     Workspace& ws = ctx->ws[0];
-    const uint64_t cap = std::max<uint64_t>(nbytes, 1);           // at most one window ends at every byte
-    int rc = ws.part.ensure(sparse_workspace_bytes(cap));
+    // at most one window ends at every byte of the range; the slice table covers the whole file
+    const uint64_t cap = std::max<uint64_t>(range_end - range_begin, 1);
+    int rc = ws.part.ensure(sparse_workspace_bytes(cap, nbytes));
     if (rc) return rc;
-    return run_sparse_in(ws.part.p, d_fasta, nbytes, k, min_rec, (flags & KMERML_FLAG_CANONICAL) != 0, cap, d_keys,
-                         d_counts, d_first, out_cap, h_unique, h_windows, (cudaStream_t)stream);
+    return run_sparse_in(ws.part.p, d_fasta, nbytes, range_begin, range_end, k, min_rec,
+                         (flags & KMERML_FLAG_CANONICAL) != 0, cap, d_keys, d_counts, d_first, out_cap, h_unique,
+                         h_windows, (cudaStream_t)stream);
+}
+
+int kmerml_count_sparse(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, int k, int min_record_len,
+                        unsigned flags, uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_first, uint64_t out_cap,
+                        uint64_t* h_unique, uint64_t* h_windows, void* stream) {
+    return count_sparse_core(ctx, d_fasta, nbytes, 0, nbytes, k, min_record_len, flags, d_keys, d_counts, d_first, out_cap,
+                             h_unique, h_windows, stream);
+}
+
+int kmerml_count_sparse_range(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin,
+                              uint64_t range_end, int k, int min_record_len, unsigned flags, uint64_t* d_keys,
+                              uint32_t* d_counts, uint32_t* d_first, uint64_t out_cap, uint64_t* h_unique,
+                              uint64_t* h_windows, void* stream) {
+    return count_sparse_core(ctx, d_fasta, nbytes, range_begin, range_end, k, min_record_len, flags, d_keys, d_counts,
+                             d_first, out_cap, h_unique, h_windows, stream);
+}
+
+int kmerml_merge_sparse(kmerml_ctx* ctx, int k, const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_first,
+                        uint64_t n, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
+                        uint64_t* h_unique, void* stream) {
+    if (!ctx || !h_unique) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (k < 1 || k > KMERML_MAX_K) return fail(KMERML_ERR_ARG, "k must be in 1..32");
+    if (n && (!d_keys || !d_counts)) return fail(KMERML_ERR_ARG, "null input pointer");
+    if (out_cap && (!d_keys_out || !d_counts_out)) return fail(KMERML_ERR_ARG, "null output pointer");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    Workspace& ws = ctx->ws[0];
+    int rc = ws.part.ensure(merge_workspace_bytes(std::max<uint64_t>(n, 1)));
+    if (rc) return rc;
+    return run_merge_sparse(ws.part.p, k, d_keys, d_counts, d_first, n, d_keys_out, d_counts_out, d_first_out, out_cap,
+                            h_unique, (cudaStream_t)stream);
 }
 
 int kmerml_first_occurrence(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, int k, int min_record_len,

@@ -114,10 +114,15 @@ int dense_setup_attributes();
 
 // ---- sparse path (sparse.cu) ---------------------------------------------------
 struct SparseWork;
-size_t sparse_workspace_bytes(uint64_t cap);
-int run_sparse_in(void* workspace, const uint8_t* d_fasta, uint64_t nbytes, int k, int min_rec, bool canonical,
-                  uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
+size_t sparse_workspace_bytes(uint64_t cap, uint64_t nbytes);
+int run_sparse_in(void* workspace, const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, uint64_t range_end,
+                  int k, int min_rec, bool canonical, uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
                   uint64_t* h_unique, uint64_t* h_windows, cudaStream_t s);
+
+size_t merge_workspace_bytes(uint64_t n);
+int run_merge_sparse(void* workspace, int k, const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_first,
+                     uint64_t n, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
+                     uint64_t* h_unique, cudaStream_t s);
 
 // ---- k{k}.txt text (format.cu) --------------------------------------------------
 size_t format_workspace_bytes(uint64_t n_bins, uint64_t max_lines);

@@ -160,7 +160,7 @@ struct SparseWork {
 };
 
 // Layout of the workspace for `cap` windows; returns the total number of bytes.
-size_t sparse_workspace(uint64_t cap, SparseWork* w, uint8_t* base) {
+size_t sparse_workspace(uint64_t cap, uint64_t nbytes, SparseWork* w, uint8_t* base) {
     size_t off = 0;
     auto take = [&](size_t bytes) {
         uint8_t* p = base ? base + off : nullptr;
@@ -175,8 +175,8 @@ size_t sparse_workspace(uint64_t cap, SparseWork* w, uint8_t* base) {
     local.cursor = (unsigned long long*)take(256);
     local.n_runs = (unsigned long long*)take(256);
     local.genome = (GenomeDev*)take(256);
-    // cap bounds the number of FASTA bytes (callers size it so); one slice entry per 128 KB + scratch
-    local.slices = (Slice*)take((cap / ((uint64_t)SPARSE_TILE * SPARSE_TILES_PER_SLICE) + 3) * sizeof(Slice));
+    // one slice entry per 128 KB of the whole file + scratch
+    local.slices = (Slice*)take((nbytes / ((uint64_t)SPARSE_TILE * SPARSE_TILES_PER_SLICE) + 3) * sizeof(Slice));
     size_t t1 = 0, t2 = 0, t3 = 0;
     cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
     cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
@@ -193,8 +193,8 @@ size_t sparse_workspace(uint64_t cap, SparseWork* w, uint8_t* base) {
 
 // Emits, sorts and reduces.  On return (after a stream sync) *h_windows / *h_unique are valid; when
 // *h_unique > out_cap nothing was written to the outputs.
-int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, int k, int min_rec, bool canonical, const SparseWork& w,
-               uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
+int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, uint64_t range_end, int k, int min_rec,
+               bool canonical, const SparseWork& w, uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
                uint64_t* h_unique, uint64_t* h_windows, cudaStream_t s) {
     SparseParams P;
     P.k = k;
@@ -208,16 +208,18 @@ int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, int k, int min_rec, bool
     if (!nbytes) return KMERML_OK;
     const uint64_t slice_bytes = (uint64_t)SPARSE_TILE * SPARSE_TILES_PER_SLICE;
     const int n_slices = (int)((nbytes + slice_bytes - 1) / slice_bytes);
-    if ((uint64_t)n_slices > cap / slice_bytes + 2) {
-        set_error("internal: sparse slice table too small");
-        return KMERML_ERR_RANGE;
-    }
     sparse_setup_kernel<<<(n_slices + 1 + 127) / 128, 128, 0, s>>>(d_fasta, nbytes, w.genome, w.slices, n_slices);
     KM_CUDA(cudaGetLastError());
     if (int rc = launch_slice_headers(d_fasta, w.genome, w.slices, n_slices, s)) return rc;
-    sparse_emit_kernel<<<n_slices, SPARSE_THREADS, 0, s>>>(d_fasta, w.genome, w.slices, P, w.keys_a, w.ends_a, w.cursor,
-                                                           cap);
-    KM_CUDA(cudaGetLastError());
+    // the header state of every slice start is settled over the whole file; only the slices of the
+    // requested byte range (whole slices: the multi-GPU unit) emit their windows
+    const int s0 = (int)std::min<uint64_t>(range_begin / slice_bytes, (uint64_t)n_slices);
+    const int s1 = (int)std::min<uint64_t>((range_end + slice_bytes - 1) / slice_bytes, (uint64_t)n_slices);
+    if (s1 > s0) {
+        sparse_emit_kernel<<<s1 - s0, SPARSE_THREADS, 0, s>>>(d_fasta, w.genome, w.slices + s0, P, w.keys_a, w.ends_a,
+                                                              w.cursor, cap);
+        KM_CUDA(cudaGetLastError());
+    }
     unsigned long long n = 0;
     KM_CUDA(cudaMemcpyAsync(&n, w.cursor, 8, cudaMemcpyDeviceToHost, s));
     KM_CUDA(cudaStreamSynchronize(s));
@@ -256,15 +258,106 @@ int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, int k, int min_rec, bool
     return KMERML_OK;
 }
 
-size_t sparse_workspace_bytes(uint64_t cap) { return sparse_workspace(cap, nullptr, nullptr); }
+size_t sparse_workspace_bytes(uint64_t cap, uint64_t nbytes) { return sparse_workspace(cap, nbytes, nullptr, nullptr); }
 
-int run_sparse_in(void* workspace, const uint8_t* d_fasta, uint64_t nbytes, int k, int min_rec, bool canonical,
-                  uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
+int run_sparse_in(void* workspace, const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, uint64_t range_end,
+                  int k, int min_rec, bool canonical, uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
                   uint64_t* h_unique, uint64_t* h_windows, cudaStream_t s) {
     SparseWork w;
-    sparse_workspace(cap, &w, (uint8_t*)workspace);
-    return run_sparse(d_fasta, nbytes, k, min_rec, canonical, w, cap, d_keys_out, d_counts_out, d_first_out, out_cap,
+    sparse_workspace(cap, nbytes, &w, (uint8_t*)workspace);
+    return run_sparse(d_fasta, nbytes, range_begin, range_end, k, min_rec, canonical, w, cap, d_keys_out, d_counts_out, d_first_out, out_cap,
                       h_unique, h_windows, s);
+}
+
+// ---- merge of partial results (multi-GPU: every rank receives the (k-mer, count, first) triples of its
+// key range from all ranks): sort by k-mer, add the counts, keep the smallest first offset.
+struct CountFirst {               // count in the high word, first offset in the low word
+    __host__ __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const {
+        const unsigned long long cnt = (a >> 32) + (b >> 32);
+        const unsigned long long fa = a & 0xFFFFFFFFull, fb = b & 0xFFFFFFFFull;
+        return (cnt << 32) | (fa < fb ? fa : fb);
+    }
+};
+
+__global__ void pack_count_first_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ first,
+                                        uint64_t n, unsigned long long* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ((unsigned long long)counts[i] << 32) | (first ? first[i] : 0xFFFFFFFFu);
+}
+
+__global__ void unpack_count_first_kernel(const unsigned long long* __restrict__ in, uint64_t n, uint32_t* counts,
+                                          uint32_t* first) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    counts[i] = (uint32_t)(in[i] >> 32);
+    if (first) first[i] = (uint32_t)in[i];
+}
+
+struct MergeWork {
+    uint64_t* keys_a;
+    uint64_t* keys_b;
+    unsigned long long* vals_a;
+    unsigned long long* vals_b;
+    unsigned long long* n_runs;
+    void* temp;
+    size_t temp_bytes;
+};
+
+static size_t merge_layout(uint64_t n, MergeWork* w, uint8_t* base) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        uint8_t* p = base ? base + off : nullptr;
+        off += (bytes + 255) / 256 * 256;
+        return p;
+    };
+    MergeWork l;
+    l.keys_a = (uint64_t*)take(n * 8);
+    l.keys_b = (uint64_t*)take(n * 8);
+    l.vals_a = (unsigned long long*)take(n * 8);
+    l.vals_b = (unsigned long long*)take(n * 8);
+    l.n_runs = (unsigned long long*)take(256);
+    size_t t1 = 0, t2 = 0;
+    cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
+    cub::DoubleBuffer<unsigned long long> dv(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, dk, dv, (uint64_t)n, 0, 64);
+    cub::DeviceReduce::ReduceByKey(nullptr, t2, (uint64_t*)nullptr, (uint64_t*)nullptr, (unsigned long long*)nullptr,
+                                   (unsigned long long*)nullptr, (unsigned long long*)nullptr, CountFirst(), (uint64_t)n);
+    l.temp_bytes = std::max(t1, t2);
+    l.temp = take(l.temp_bytes);
+    if (w) *w = l;
+    return off;
+}
+
+size_t merge_workspace_bytes(uint64_t n) { return merge_layout(n, nullptr, nullptr); }
+
+int run_merge_sparse(void* workspace, int k, const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_first,
+                     uint64_t n, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
+                     uint64_t* h_unique, cudaStream_t s) {
+    *h_unique = 0;
+    if (!n) return KMERML_OK;
+    MergeWork w;
+    merge_layout(n, &w, (uint8_t*)workspace);
+    KM_CUDA(cudaMemcpyAsync(w.keys_a, d_keys, n * 8, cudaMemcpyDeviceToDevice, s));
+    pack_count_first_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_counts, d_first, n, w.vals_a);
+    KM_CUDA(cudaGetLastError());
+    cub::DoubleBuffer<uint64_t> dk(w.keys_a, w.keys_b);
+    cub::DoubleBuffer<unsigned long long> dv(w.vals_a, w.vals_b);
+    size_t tb = w.temp_bytes;
+    KM_CUDA(cub::DeviceRadixSort::SortPairs(w.temp, tb, dk, dv, (uint64_t)n, 0, 2 * k, s));
+    tb = w.temp_bytes;
+    KM_CUDA(cudaMemsetAsync(w.n_runs, 0, 8, s));
+    KM_CUDA(cub::DeviceReduce::ReduceByKey(w.temp, tb, dk.Current(), dk.Alternate(), dv.Current(), dv.Alternate(),
+                                           w.n_runs, CountFirst(), (uint64_t)n, s));
+    unsigned long long nu = 0;
+    KM_CUDA(cudaMemcpyAsync(&nu, w.n_runs, 8, cudaMemcpyDeviceToHost, s));
+    KM_CUDA(cudaStreamSynchronize(s));
+    *h_unique = nu;
+    if (nu > out_cap) return KMERML_OK;                 // caller re-sizes and calls again
+    KM_CUDA(cudaMemcpyAsync(d_keys_out, dk.Alternate(), nu * 8, cudaMemcpyDeviceToDevice, s));
+    unpack_count_first_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, s>>>(dv.Alternate(), nu, d_counts_out, d_first_out);
+    KM_CUDA(cudaGetLastError());
+    KM_CUDA(cudaStreamSynchronize(s));
+    return KMERML_OK;
 }
 
 }  // namespace km

@@ -7,7 +7,11 @@ Two levels, as in SURVEY 8e:
     windows that END in its range (kmerml_count_dense_range reads the k-1 bases before the
     range from the file itself) and the dense uint32 rows are summed with ONE all-reduce
     (NCCL over NVLink on GPUs).  Integer sums are order-independent, so the result is
-    bit-identical to the single-GPU one.
+    bit-identical to the single-GPU one;
+  * one large genome, sparse k (15..32): every rank sort-reduces the windows of its byte range,
+    routes each distinct k-mer to the rank that owns its key range with ONE all-to-all
+    (k-mer, count, first offset), and merges what it receives.  The result stays sharded by key
+    range, ascending across ranks.
 """
 import numpy as np
 
@@ -143,3 +147,60 @@ def count_genomes_sharded(fasta_list, k_values, *, min_record_len=None, canonica
             out_c[i] = all_c[r][j]
             out_t[i] = all_t[r][j]
     return list(range(len(sizes))), out_c, out_t
+
+
+SPARSE_RANGE_ALIGN = 131072
+
+
+def key_owner_splits(keys, k, world_size):
+    """keys: int64 tensor holding ascending uint64 2-bit packed k-mers.  Rank r owns the k-mers whose top
+    16 bits t satisfy (t * world_size) >> 16 == r, so owners are ascending along `keys`; returns the number
+    of keys per owner (list of world_size ints)."""
+    import torch
+    bits = 2 * int(k)
+    if keys.numel() == 0:
+        return [0] * world_size
+    if bits >= 16:
+        top = (keys >> (bits - 16)) & 0xFFFF
+    else:
+        top = (keys << (16 - bits)) & 0xFFFF
+    owner = (top * world_size) >> 16
+    return torch.bincount(owner, minlength=world_size).cpu().tolist()
+
+
+def count_sparse_sharded(fasta, k, *, min_record_len=None, canonical=False, count_range=None, merge=None):
+    """Distinct k-mers (k <= 32) of ONE genome resident on every rank's device, counted cooperatively.
+    Rank r counts byte range r, the partial results are exchanged with one all-to-all per tensor, and rank r
+    returns the k-mers of key range r: (keys, counts, first, windows of the whole genome).  Concatenating the
+    ranks' results in rank order gives exactly the single-GPU result.
+
+    `count_range(fasta, begin, end, k, min_record_len, canonical) -> (keys, counts, first, windows)` and
+    `merge(keys, counts, first, k) -> (keys, counts, first)` can be injected (CPU tests); by default they are
+    the CUDA entry points."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    rank, world = _world()
+    begin, end = chunk_ranges(int(fasta.numel()), world, tile=SPARSE_RANGE_ALIGN)[rank]
+    if count_range is None:
+        count_range = lambda f, b, e, kk, ml, c: engine.count_sparse_range_device(f, b, e, kk, min_record_len=ml, canonical=c)
+    if merge is None:
+        merge = engine.merge_sparse_device
+    keys, counts, first, windows = count_range(fasta, begin, end, int(k), min_record_len, canonical)
+    if world == 1:
+        return keys, counts, first, windows
+    send = key_owner_splits(keys, k, world)
+    send_t = torch.tensor(send, dtype=torch.int64, device=keys.device)
+    recv_t = torch.empty_like(send_t)
+    dist.all_to_all_single(recv_t, send_t)
+    recv = recv_t.cpu().tolist()
+    total = int(sum(recv))
+    out = []
+    for t in (keys, counts, first):
+        r = torch.empty(total, dtype=t.dtype, device=t.device)
+        dist.all_to_all_single(r, t.contiguous(), output_split_sizes=recv, input_split_sizes=send)
+        out.append(r)
+    w = torch.tensor([windows], dtype=torch.int64, device=keys.device)
+    dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    mk, mc, mf = merge(out[0], out[1], out[2], int(k))
+    return mk, mc, mf, int(w.item())

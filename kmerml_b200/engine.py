@@ -254,6 +254,51 @@ def count_sparse_device(fasta, k, *, min_record_len=None, canonical=False, want_
         cap = int(nu.value)
 
 
+SPARSE_RANGE_ALIGN = 131072
+
+
+def count_sparse_range_device(fasta, begin, end, k, *, min_record_len=None, canonical=False):
+    """count_sparse_device for the windows ending in the byte range [begin, end) (multiples of SPARSE_RANGE_ALIGN,
+    or end == file size): the multi-GPU unit.  First offsets are relative to the file."""
+    ctx = _lib.context(fasta.device.index)
+    L = _lib.load()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(fasta.device).cuda_stream)
+    cap = max(1024, min(int(end) - int(begin), 1 << 22))
+    while True:
+        keys = torch.empty(cap, dtype=torch.int64, device=fasta.device)
+        counts = torch.empty(cap, dtype=torch.int32, device=fasta.device)
+        first = torch.empty(cap, dtype=torch.int32, device=fasta.device)
+        nu, nw = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _lib.check(L.kmerml_count_sparse_range(ctx.handle, fasta.data_ptr() if fasta.numel() else None, fasta.numel(),
+                                               int(begin), int(end), int(k), int(min_record_len or 0),
+                                               _lib.FLAG_CANONICAL if canonical else 0, keys.data_ptr(), counts.data_ptr(),
+                                               first.data_ptr(), cap, ctypes.byref(nu), ctypes.byref(nw), stream))
+        if nu.value <= cap:
+            n = int(nu.value)
+            return keys[:n], counts[:n], first[:n], int(nw.value)
+        cap = int(nu.value)
+
+
+def merge_sparse_device(keys, counts, first, k):
+    """(k-mer, count, first) triples in any order, duplicates allowed -> distinct k-mers ascending, counts added,
+    smallest first offset kept (int64 / int32 / int32 storage of uint64 / uint32 / uint32)."""
+    ctx = _lib.context(keys.device.index)
+    L = _lib.load()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(keys.device).cuda_stream)
+    n = int(keys.numel())
+    if n == 0:
+        return keys, counts, first
+    keys, counts, first = keys.contiguous(), counts.contiguous(), first.contiguous()
+    ok = torch.empty(n, dtype=torch.int64, device=keys.device)
+    oc = torch.empty(n, dtype=torch.int32, device=keys.device)
+    of = torch.empty(n, dtype=torch.int32, device=keys.device)
+    nu = ctypes.c_uint64(0)
+    _lib.check(L.kmerml_merge_sparse(ctx.handle, int(k), keys.data_ptr(), counts.data_ptr(), first.data_ptr(), n,
+                                     ok.data_ptr(), oc.data_ptr(), of.data_ptr(), n, ctypes.byref(nu), stream))
+    m = int(nu.value)
+    return ok[:m], oc[:m], of[:m]
+
+
 def genome_stats_device(fasta):
     """{"contigs", "total_size", "gc_content", "n_count"} of one FASTA file on the GPU
     (the tallies of kmerml/utils/genome_metadata.py:55-85)."""

@@ -56,3 +56,54 @@ def fuzz_fasta(rng: random.Random, max_records=6, max_len=400):
 
 def as_u8(data):
     return np.frombuffer(bytes(data), dtype=np.uint8)
+
+
+def unwrapped_fasta_with_windows(seqs, k, canonical=False):
+    """FASTA bytes with one unwrapped line per record, plus every valid k-window as (2-bit packed code uint64,
+    byte offset of its last base) -- a numpy restatement of the window rules (generate.py:49-58) for this simple
+    layout, used to check the byte-range / merge units of the multi-GPU sparse path."""
+    parts, spans, pos = [], [], 0
+    for i, s in enumerate(seqs):
+        h = f">r{i}\n".encode()
+        parts += [h, s, b"\n"]
+        spans.append((pos + len(h), pos + len(h) + len(s)))
+        pos += len(h) + len(s) + 1
+    data = b"".join(parts)
+    a = np.frombuffer(data, np.uint8)
+    lut = np.full(256, 255, np.uint8)
+    for j, ch in enumerate(b"ACGT"):
+        lut[ch] = j
+        lut[ch + 32] = j
+    keys, ends = [], []
+    for s0, s1 in spans:
+        if s1 - s0 < k:
+            continue
+        c = lut[a[s0:s1]]
+        bad = (c == 255).astype(np.int64)
+        cs = np.concatenate(([0], np.cumsum(bad)))
+        n = s1 - s0 - k + 1
+        ok = (cs[k:k + n] - cs[:n]) == 0
+        code = np.zeros(n, np.uint64)
+        rc = np.zeros(n, np.uint64)
+        cc = np.where(c == 255, 0, c).astype(np.uint64)
+        for j in range(k):
+            code = (code << np.uint64(2)) | cc[j:j + n]
+            rc = rc | ((np.uint64(3) - cc[j:j + n]) << np.uint64(2 * j))
+        key = np.minimum(code, rc) if canonical else code
+        keys.append(key[ok])
+        ends.append((np.arange(n) + s0 + k - 1)[ok])
+    keys = np.concatenate(keys) if keys else np.zeros(0, np.uint64)
+    ends = np.concatenate(ends) if ends else np.zeros(0, np.int64)
+    return data, keys, ends.astype(np.int64)
+
+
+def reduce_windows(keys, ends, begin=0, end=None):
+    """(distinct keys ascending, counts, smallest end offset) of the windows whose end lies in [begin, end)."""
+    sel = ends >= begin
+    if end is not None:
+        sel &= ends < end
+    k, e = keys[sel], ends[sel]
+    order = np.lexsort((e, k))
+    k, e = k[order], e[order]
+    uniq, idx, cnt = np.unique(k, return_index=True, return_counts=True)
+    return uniq, cnt.astype(np.int64), e[idx]

@@ -58,6 +58,36 @@ def main():
     if rank == 0:
         print(f"sharded 11 genomes over {world} ranks + all_gather: identical to single GPU = {ok}")
     assert ok
+    # one genome with N runs, sparse k = 21 canonical (BASELINE config 5 in miniature): byte ranges -> all-to-all
+    # by key range -> merge; the ranks' shards, concatenated in rank order, must equal the single-GPU result
+    g5 = genome.copy()
+    for a in range(3_000_000, g5.size - 100_000, 9_000_000):
+        seg = g5[a:a + 40_000]
+        seg[(seg != 10) & (seg != 62)] = ord("N")
+    fasta5 = torch.from_numpy(g5).to(dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    mk, mc, mf, windows = kdist.count_sparse_sharded(fasta5, 21, canonical=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    wk, wc, wf, ww = engine.count_sparse_device(fasta5, 21, canonical=True)
+    if world > 1:
+        n_mine = torch.tensor([mk.numel()], dtype=torch.int64, device=dev)
+        sizes = [torch.empty_like(n_mine) for _ in range(world)]
+        dist.all_gather(sizes, n_mine)
+        lo = int(sum(int(x.item()) for x in sizes[:rank]))
+        total = int(sum(int(x.item()) for x in sizes))
+    else:
+        lo, total = 0, mk.numel()
+    ok5 = (total == wk.numel() and windows == ww and torch.equal(mk, wk[lo:lo + mk.numel()])
+           and torch.equal(mc, wc[lo:lo + mk.numel()]) and torch.equal(mf, wf[lo:lo + mk.numel()]))
+    flag = torch.tensor([1 if ok5 else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"sparse k=21 canonical, {mbp:.0f} Mbp with N runs, world={world}: {total} distinct k-mers, shards identical to "
+              f"single GPU = {bool(flag.item())}  ({dt * 1e3:.1f} ms incl. all-to-all)")
+    assert flag.item() == 1
     if world > 1:
         dist.destroy_process_group()
 

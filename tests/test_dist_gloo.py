@@ -88,6 +88,37 @@ def _worker(rank, world, port, results):
                 ok &= bool(np.array_equal(ref, c2[i, off:off + 4 ** k].numpy().view(np.uint32).astype(np.uint64)))
                 ok &= int(t2[i, ki]) == int(ref.sum())
                 off += 4 ** k
+        # (3) one genome, sparse k: byte ranges -> all-to-all by key range -> merge
+        from helpers import reduce_windows, unwrapped_fasta_with_windows
+        rng = np.random.default_rng(77)
+        seqs = [np.frombuffer(b"ACGTN", np.uint8)[rng.choice(5, n, p=[.24, .25, .25, .24, .02])].tobytes()
+                for n in (300_000, 10, 150_000)]
+        for k, canonical in ((17, False), (9, True)):
+            fa, wk, we = unwrapped_fasta_with_windows(seqs, k, canonical)
+
+            def np_count_range(fasta, begin, end, kk, ml, c):
+                u, cnt, fst = reduce_windows(wk, we, begin, end)
+                return (torch.from_numpy(u.view(np.int64).copy()), torch.from_numpy(cnt.astype(np.int32)),
+                        torch.from_numpy(fst.astype(np.int32)), int(cnt.sum()))
+
+            def np_merge(keys, counts, first, kk):
+                kn, cn, fn = keys.numpy().view(np.uint64), counts.numpy().astype(np.int64), first.numpy().astype(np.int64)
+                order = np.lexsort((fn, kn))
+                kn, cn, fn = kn[order], cn[order], fn[order]
+                u, idx = np.unique(kn, return_index=True)
+                return (torch.from_numpy(u.view(np.int64).copy()), torch.from_numpy(np.add.reduceat(cn, idx).astype(np.int32)),
+                        torch.from_numpy(fn[idx].astype(np.int32)))
+
+            mk, mc, mf, windows = kdist.count_sparse_sharded(torch.from_numpy(np.frombuffer(fa, np.uint8).copy()), k,
+                                                             canonical=canonical, count_range=np_count_range, merge=np_merge)
+            u, cnt, fst = reduce_windows(wk, we)
+            ok &= windows == int(cnt.sum())
+            # this rank holds exactly the k-mers of its key range; the ranges tile the key space in rank order
+            top = (u >> np.uint64(2 * k - 16)) & np.uint64(0xFFFF)
+            mine = ((top * np.uint64(world)) >> np.uint64(16)) == rank
+            ok &= bool(np.array_equal(mk.numpy().view(np.uint64), u[mine]))
+            ok &= bool(np.array_equal(mc.numpy().astype(np.int64), cnt[mine]))
+            ok &= bool(np.array_equal(mf.numpy().astype(np.int64), fst[mine]))
         results[rank] = ok
     finally:
         dist.destroy_process_group()

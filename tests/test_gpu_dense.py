@@ -236,3 +236,47 @@ def test_run_end_tail_list_overflow_rescans():
         check_against_oracle([calm1, busy, calm2], ks)
     check_against_oracle([calm1, busy, calm2], [9, 12], canonical=True)
     check_against_oracle([busy], [7, 12], min_record_len=40)
+
+
+def test_sparse_byte_ranges_and_merge():
+    """The multi-GPU units of the sparse path in one process: windows ending in byte ranges
+    (kmerml_count_sparse_range), routed by key range and merged (kmerml_merge_sparse) == the whole genome."""
+    import torch
+    from helpers import reduce_windows, unwrapped_fasta_with_windows
+    from kmerml_b200 import dist as kdist
+    from kmerml_b200 import engine
+    rng = np.random.default_rng(123)
+    seqs = [np.frombuffer(b"ACGTN", np.uint8)[rng.choice(5, n, p=[.24, .25, .25, .24, .02])].tobytes()
+            for n in (700_000, 12, 400_000, 90_000)]
+    for k, canonical in ((21, True), (16, False), (32, False)):
+        fa, wk, we = unwrapped_fasta_with_windows(seqs, k, canonical)
+        dev = torch.from_numpy(np.frombuffer(fa, np.uint8).copy()).cuda()
+        whole = engine.count_sparse_device(dev, k, canonical=canonical)
+        u, cnt, fst = reduce_windows(wk, we)
+        assert np.array_equal(whole[0].cpu().numpy().view(np.uint64), u)
+        assert np.array_equal(whole[1].cpu().numpy().astype(np.int64), cnt)
+        assert np.array_equal(whole[2].cpu().numpy().view(np.uint32).astype(np.int64), fst)
+        assert whole[3] == int(cnt.sum())
+        world = 3
+        parts, windows = [], 0
+        for b, e in kdist.chunk_ranges(len(fa), world, tile=engine.SPARSE_RANGE_ALIGN):
+            pk, pc, pf, pw = engine.count_sparse_range_device(dev, b, e, k, canonical=canonical)
+            ru, rc, rf = reduce_windows(wk, we, b, e)
+            assert np.array_equal(pk.cpu().numpy().view(np.uint64), ru), (k, b, e)
+            assert np.array_equal(pc.cpu().numpy().astype(np.int64), rc)
+            assert np.array_equal(pf.cpu().numpy().view(np.uint32).astype(np.int64), rf)
+            parts.append((pk, pc, pf))
+            windows += pw
+        assert windows == whole[3]
+        # owner r receives every rank's k-mers of key range r
+        got = []
+        splits = [kdist.key_owner_splits(p[0], k, world) for p in parts]
+        for r in range(world):
+            ks_, cs_, fs_ = [], [], []
+            for p, sp in zip(parts, splits):
+                lo = sum(sp[:r])
+                ks_.append(p[0][lo:lo + sp[r]]); cs_.append(p[1][lo:lo + sp[r]]); fs_.append(p[2][lo:lo + sp[r]])
+            got.append(engine.merge_sparse_device(torch.cat(ks_), torch.cat(cs_), torch.cat(fs_), k))
+        assert torch.equal(torch.cat([g[0] for g in got]), whole[0])
+        assert torch.equal(torch.cat([g[1] for g in got]), whole[1])
+        assert torch.equal(torch.cat([g[2] for g in got]), whole[2])
