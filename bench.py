@@ -197,6 +197,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from kmerml_b200 import _lib, engine
+    from kmerml_b200 import dist as kdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -204,6 +205,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
+    numa_node = kdist.bind_to_gpu_numa_node(local) if world > 1 else None     # before any pinned allocation
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
@@ -407,10 +409,15 @@ def run_ours(args):
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
                 nb_e2e = float(t.item())
             same = torch.equal(hc, counts[:n_e2e].cpu())
+            io = torch.tensor([float(sum(sizes[:n_e2e])), float(n_e2e * (row_len * 4 + len(ks) * 8))],
+                              dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(io, op=dist.ReduceOp.SUM)          # whole job, like the value
             e2e = {"value": nb_e2e / dt / 1e9, "unit": UNIT,
-                   "h2d_bytes_per_step": int(sum(sizes[:n_e2e])),
-                   "d2h_bytes_per_step": int(n_e2e * (row_len * 4 + len(ks) * 8)),
+                   "h2d_bytes_per_step": int(io[0].item()),
+                   "d2h_bytes_per_step": int(io[1].item()),
                    "genomes": n_e2e, "ms_per_step": dt * 1e3, "matches_device_path": bool(same),
+                   "numa_node": numa_node,
                    "api": "kmerml_count_dense_host: pinned host FASTA -> H2D -> count + frequency rows -> D2H of the "
                           "uint32 count rows and totals (what the reference writes to disk); the float32 frequency "
                           "matrix is computed per step and left resident in HBM (KMERML_FLAG_FREQ_ON_DEVICE)"}

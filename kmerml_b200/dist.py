@@ -45,6 +45,35 @@ def chunk_ranges(nbytes, world_size, tile=TILE_BYTES):
     return out
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers it
+    allocates afterwards (first touch) and the copies to and from them stay on that socket.  With one process per
+    GPU on a two-socket host this is what keeps 8 ranks' PCIe streams from crossing the inter-socket link.
+    Returns the node number, or None when the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def _world():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
