@@ -361,7 +361,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     KM_CUDA(cudaEventRecord(ws.staging_free, s));
 
     {
-        Prof pr(ctx, s, 3, 2);
+        Prof pr(ctx, s, 3, 4);      // prologue + the three slice-table kernels
         rc = launch_prologue(d_fasta, d_offsets, d_genomes, d_stats, n_genomes, s);
         if (!rc) rc = launch_slice_headers(d_fasta, d_genomes, d_slices, (int)n_slices, s);
     }
