@@ -6,6 +6,7 @@
 // Round 1: the sort and the segmented reductions are CUB library calls (the toolkit's own headers);
 // the emitter is the shared carry-free walker with 64-bit state.
 #include <cub/cub.cuh>
+#include <thrust/iterator/constant_iterator.h>
 
 #include "fasta_walk.cuh"
 #include "internal.h"
@@ -181,8 +182,9 @@ size_t sparse_workspace(uint64_t cap, uint64_t nbytes, SparseWork* w, uint8_t* b
     cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
     cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
     cub::DeviceRadixSort::SortPairs(nullptr, t1, dk, dv, (uint64_t)cap, 0, 64);
-    cub::DeviceRunLengthEncode::Encode(nullptr, t2, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
-                                       (unsigned long long*)nullptr, (uint64_t)cap);
+    cub::DeviceReduce::ReduceByKey(nullptr, t2, (uint64_t*)nullptr, (uint64_t*)nullptr,
+                                   thrust::constant_iterator<uint32_t>(1u), (uint32_t*)nullptr,
+                                   (unsigned long long*)nullptr, cub::Sum(), (uint64_t)cap);
     cub::DeviceReduce::ReduceByKey(nullptr, t3, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
                                    (uint32_t*)nullptr, (unsigned long long*)nullptr, cub::Min(), (uint64_t)cap);
     local.temp_bytes = std::max(t1, std::max(t2, t3));
@@ -240,7 +242,10 @@ int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, ui
     uint64_t* uniq = dk.Alternate();                 // scratch for the unique keys
     uint32_t* runs = dv.Alternate();                 // scratch for counts, then first offsets
     tb = w.temp_bytes;
-    KM_CUDA(cub::DeviceRunLengthEncode::Encode(w.temp, tb, sorted_keys, uniq, runs, w.n_runs, (uint64_t)n, s));
+    // run lengths as a segmented sum of ones: DeviceRunLengthEncode takes an `int` item count, a human-sized
+    // genome has more than 2^31 windows
+    KM_CUDA(cub::DeviceReduce::ReduceByKey(w.temp, tb, sorted_keys, uniq, thrust::constant_iterator<uint32_t>(1u), runs,
+                                           w.n_runs, cub::Sum(), (uint64_t)n, s));
     unsigned long long nu = 0;
     KM_CUDA(cudaMemcpyAsync(&nu, w.n_runs, 8, cudaMemcpyDeviceToHost, s));
     KM_CUDA(cudaStreamSynchronize(s));
