@@ -538,8 +538,17 @@ constexpr int PART_BINS = 1 << (2 * PART_LOW);        // 16384 bins per bucket
 constexpr int PART_MAX_BUCKETS = 1024;                // k <= 12
 constexpr int STAGE_ENTRIES = 32768;                  // uint16 entries staged per tile = nb * slot
 
+// Rare for a genome of mixed sequence: the slot is full.  Tandem repeats make it common (every window of a
+// tile falls into a handful of buckets), so the lanes that arrive together reserve their entries with one
+// atomic on the genome's cursor instead of one each.
 __device__ __noinline__ void overflow_push(uint32_t* ov, unsigned int* ov_count, uint32_t idx) {
-    ov[atomicAdd(ov_count, 1u)] = idx;                // rare: the slot is full
+    const unsigned act = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(act) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(ov_count, (unsigned int)__popc(act));
+    base = __shfl_sync(act, base, leader);
+    ov[base + __popc(act & ((1u << lane) - 1u))] = idx;
 }
 
 template <int SLOT_SHIFT>
@@ -871,21 +880,30 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
 // The windows that found their slot full: add them to level k and to every level of the bucket
 // subtrees (the cascade below k_stop runs after this kernel), then refresh the touched
 // frequencies from the final counts (idempotent, so concurrent duplicates are harmless).
+// Slots run full where the sequence is repetitive, and then the list holds the same few k-mers over and
+// over: each CTA first folds its share of the list into a small shared-memory hash table (k-mer -> how
+// often), so that a tandem repeat costs a handful of global atomics per CTA instead of one per window.
+constexpr int OV_TABLE = 4096;
+constexpr uint32_t OV_EMPTY = 0xFFFFFFFFu;                 // not a valid k-mer index (k <= 14 here)
+
 __global__ void __launch_bounds__(256)
 overflow_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const GenomeDev* __restrict__ gds,
                 const uint32_t* __restrict__ overflow, const unsigned int* __restrict__ ov_counts, uint64_t batch_lo,
                 const GenomeStats* __restrict__ stats, float* freq, uint64_t freq_stride, uint32_t genome0, int pass) {
+    __shared__ uint32_t t_key[OV_TABLE];
+    __shared__ uint32_t t_cnt[OV_TABLE];
+    __shared__ unsigned int t_used;
     const uint32_t g = genome0 + blockIdx.y;
     const unsigned int n = ov_counts[g];
-    if (!n) return;
+    if (blockIdx.x * 256u >= n) return;
     const uint32_t* ov = overflow + (gds[g].file_lo - batch_lo);
-    for (unsigned int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-        const uint32_t idx = ov[i];
+    const int tid = threadIdx.x;
+    auto apply = [&](uint32_t idx, uint32_t cnt) {
         for (int level = k; level >= k_stop; level--) {
             const uint32_t x = idx >> (2 * (k - level));
             uint32_t* c = lm.ptr(g, level);
             if (pass == 0) {
-                atomicAdd(c + x, 1u);
+                atomicAdd(c + x, cnt);
             } else if (freq && li.ki[level] >= 0) {
                 const int ki = li.ki[level];
                 unsigned long long t = stats[g].total_top;
@@ -893,7 +911,47 @@ overflow_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const
                 freq[(uint64_t)g * freq_stride + row.off[ki] + x] = t ? (float)((double)c[x] * (1.0 / (double)t)) : 0.0f;
             }
         }
+    };
+    auto flush = [&]() {                                   // (whole CTA, between barriers)
+        for (int e = tid; e < OV_TABLE; e += 256) {
+            const uint32_t key = t_key[e];
+            if (key != OV_EMPTY) apply(key, t_cnt[e]);
+            t_key[e] = OV_EMPTY;
+            t_cnt[e] = 0;
+        }
+        if (tid == 0) t_used = 0;
+        __syncthreads();
+    };
+    if (n < 4096u) {                                       // the usual handful of entries: no table
+        for (unsigned int i = blockIdx.x * 256u + tid; i < n; i += gridDim.x * 256u) apply(ov[i], 1u);
+        return;
     }
+    for (int e = tid; e < OV_TABLE; e += 256) { t_key[e] = OV_EMPTY; t_cnt[e] = 0; }
+    if (tid == 0) t_used = 0;
+    __syncthreads();
+    for (unsigned int base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {
+        const unsigned int i = base + tid;
+        if (i < n) {
+            const uint32_t idx = ov[i];
+            uint32_t h = (idx * 2654435761u) >> 20;        // 12 bits
+            bool placed = false;
+            for (int probe = 0; probe < 8 && !placed; probe++) {
+                const uint32_t old = atomicCAS(&t_key[h], OV_EMPTY, idx);
+                if (old == OV_EMPTY) atomicAdd(&t_used, 1u);
+                if (old == OV_EMPTY || old == idx) {
+                    atomicAdd(&t_cnt[h], 1u);
+                    placed = true;
+                }
+                h = (h + 1) & (OV_TABLE - 1);
+            }
+            if (!placed) apply(idx, 1u);                   // crowded neighbourhood: straight to global memory
+        }
+        __syncthreads();
+        const bool crowded = t_used > OV_TABLE / 2;
+        __syncthreads();                                   // everybody has read it before flush() resets it
+        if (crowded) flush();
+    }
+    flush();
 }
 
 // One run-end tail of level j (>= k_stop) counts at level j and, through the marginal sums, at every
@@ -1239,7 +1297,7 @@ int launch_overflow(const LevelMap& lm, const RowSpec& row, int k, int k_bottom,
     if (n_genomes <= 0) return KMERML_OK;
     const LevelInfo li = make_level_info(row);
     const int k_stop = std::max(k - PART_LOW, k_bottom);
-    dim3 grid(32, (unsigned)n_genomes);
+    dim3 grid(64, (unsigned)n_genomes);
     for (int pass = 0; pass < (d_freq ? 2 : 1); pass++) {
         overflow_kernel<<<grid, 256, 0, s>>>(lm, row, li, k, k_stop, d_genomes, d_overflow, d_ov_counts, batch_lo,
                                              d_stats, d_freq, freq_stride, genome0, pass);
