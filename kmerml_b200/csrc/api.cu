@@ -105,6 +105,7 @@ struct kmerml_ctx {
     int device = 0;
     int sm_count = 148;
     km::Workspace ws[3];
+    uint64_t max_group_payload = 12ull << 30;     // partition path: payload bytes one group of genomes may take
     // measurement hooks
     bool profiling = false;
     uint64_t launches = 0, count_launches = 0;
@@ -337,7 +338,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     uint32_t* h_gtiles = (uint32_t*)(hs + off_bytes + sl_bytes);
     std::vector<int> group_end;                              // exclusive genome index per group
     if (use_part) {
-        const uint64_t max_tiles = (12ull << 30) / ((uint64_t)PART_STAGE_ENTRIES * 2);
+        const uint64_t max_tiles = std::max<uint64_t>(ctx->max_group_payload / ((uint64_t)PART_STAGE_ENTRIES * 2), 1);
         uint64_t in_group = 0;
         uint64_t group_tile0 = 0;
         for (int g = 0; g < n_genomes; g++) {
@@ -524,6 +525,10 @@ int kmerml_ctx_create(int device, kmerml_ctx** out) {
     if (!ctx) return fail(KMERML_ERR_NOMEM, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* mb = getenv("KMERML_GROUP_PAYLOAD_MB")) {      // smaller groups: less workspace (and a test hook)
+        const long long v = atoll(mb);
+        if (v > 0) ctx->max_group_payload = (uint64_t)v << 20;
+    }
     int rc = dense_setup_attributes();
     if (rc) { delete ctx; return rc; }
     *out = ctx;

@@ -280,3 +280,38 @@ def test_sparse_byte_ranges_and_merge():
         assert torch.equal(torch.cat([g[0] for g in got]), whole[0])
         assert torch.equal(torch.cat([g[1] for g in got]), whole[1])
         assert torch.equal(torch.cat([g[2] for g in got]), whole[2])
+
+
+def test_several_payload_groups():
+    """More genomes than one payload group holds: with KMERML_GROUP_PAYLOAD_MB=1 the 9 genomes below fall into several
+    groups (tail lists and overflow lists are addressed per group).  Runs in a fresh process because the limit is
+    read when the context is created."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import random, sys
+import numpy as np
+sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+import oracle
+from helpers import fuzz_fasta
+from test_gpu_dense import gpu_counts
+rng = random.Random(3)
+datas = []
+for i in range(9):
+    seq = ''.join(rng.choice('ACGT') for _ in range(rng.randint(60_000, 150_000)))
+    if i % 3 == 1:
+        seq = seq[:20_000] + 'ACGTTGCAAT' * 3000 + seq[20_000:] + 'N' + seq[:500]
+    datas.append(('>g%d\n' % i + '\n'.join(seq[j:j + 70] for j in range(0, len(seq), 70)) + '\n>tail\nACGTACGTACGTAC\n').encode())
+ks = [5, 9, 12]
+res = gpu_counts(datas, ks)
+for g, d in enumerate(datas):
+    for k in ks:
+        ref = oracle.count_dense(d, k, max(ks))
+        assert np.array_equal(ref, res.counts_numpy(g, k).astype(np.uint64)), (g, k)
+print('groups ok')
+"""
+    env = dict(os.environ, KMERML_GROUP_PAYLOAD_MB="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "groups ok" in out.stdout, out.stdout + out.stderr
