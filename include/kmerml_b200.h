@@ -47,8 +47,10 @@ typedef struct kmerml_ctx kmerml_ctx;
 int kmerml_version(void);
 const char *kmerml_last_error(void);
 
-/* One context per GPU per host thread.  Owns scratch/staging memory and streams.  * Environment: KMERML_GROUP_PAYLOAD_MB=<n> (read here) bounds the partition workspace one group of genomes
- * may take (default 12288); smaller values trade workspace for more kernel launches.
+/*
+ * One context per GPU per host thread.  Owns scratch/staging memory and streams.
+ * Environment: KMERML_GROUP_PAYLOAD_MB=<n> (read by kmerml_ctx_create) bounds the partition workspace one
+ * group of genomes may take (default 12288); smaller values trade workspace for more kernel launches.
  */
 int kmerml_ctx_create(int device, kmerml_ctx **out);
 int kmerml_ctx_destroy(kmerml_ctx *ctx);
