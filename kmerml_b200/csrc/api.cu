@@ -250,6 +250,12 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     // ---- slices
     const uint64_t total_bytes = h_offsets[n_genomes] - h_offsets[0];
     const uint64_t target = (uint64_t)ctx->sm_count * 8;
+    // partition path: long runs of tiles per CTA amortise its set-up (fill of the staging buffer, first load,
+    // final reduction), but a small batch needs enough CTAs to fill the GPU
+    int part_tiles_per_slice = 1;
+    while (part_tiles_per_slice < PART_MAX_TILES_PER_SLICE &&
+           total_bytes / TILE_BYTES / (2ull * part_tiles_per_slice) >= (uint64_t)ctx->sm_count * 8)
+        part_tiles_per_slice *= 2;
     std::vector<uint64_t> slice_bytes(n_genomes);
     std::vector<uint32_t> first_slice(n_genomes + 1);
     uint64_t n_slices = 0;
@@ -257,7 +263,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         uint64_t bytes = h_offsets[g + 1] - h_offsets[g];
         uint64_t sb;
         if (use_part) {
-            sb = (uint64_t)TILE_BYTES * PART_TILES_PER_SLICE;   // a CTA walks a run of consecutive tiles
+            sb = (uint64_t)TILE_BYTES * part_tiles_per_slice;   // a CTA walks a run of consecutive tiles
         } else if (use_smem) {
             if ((uint64_t)n_genomes >= target) sb = 1ull << 40;
             else sb = align_up(std::max<uint64_t>(total_bytes / target, 4ull * TILE_BYTES), TILE_BYTES);

@@ -88,7 +88,7 @@ int launch_finalize(const LevelMap& lm, const RowSpec& row, int k_top, bool cano
 // partition path (k = 9..12)
 constexpr int PART_MIN_K = 9, PART_MAX_K = 12, PART_LOW_BASES = 7;
 constexpr int PART_STAGE_ENTRIES = 32768;               // uint16 payload entries written per tile (64 KB)
-constexpr int PART_TILES_PER_SLICE = 16;                // consecutive tiles one partition CTA walks
+constexpr int PART_MAX_TILES_PER_SLICE = 32;            // consecutive tiles one partition CTA walks, at most
 int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles,
                      const void* d_genome_tiles, int k, int k_bottom, int min_rec, const LevelMap& lm,
                      GenomeStats* d_stats, uint16_t* d_payload, uint32_t* d_overflow, unsigned int* d_ov_counts,
