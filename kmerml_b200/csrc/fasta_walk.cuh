@@ -132,20 +132,6 @@ KM_HD_NOINLINE bool record_len_at_least(const Genome& g, uint64_t p, int need) {
     return total >= need;
 }
 
-// Is byte position p (> g.lo) inside a header line?  If so *until is the first
-// position after the header's terminator... precisely: the header occupies
-// [line start, *until).  Used once per slice start.
-KM_HD_NOINLINE bool pos_in_header(const Genome& g, uint64_t p, uint64_t* until) {
-    if (p <= g.lo || p >= g.hi) return false;
-    uint64_t ls = p;
-    while (ls > g.lo && !is_term(g.b[ls - 1])) ls--;
-    if (ls == p || g.b[ls] != (uint8_t)'>') return false;
-    uint64_t e = p;
-    while (e < g.hi && !is_term(g.b[e])) e++;
-    *until = e + 1;
-    return true;
-}
-
 // ---- slice starts: is the first byte of a slice inside a header line? ----------------------------
 // Looking back for the start of the line costs the line's length, and an unwrapped FASTA file holds a
 // whole chromosome on one line.  So the look-back is bounded; slices it leaves open are settled by a
