@@ -1283,10 +1283,13 @@ int launch_bucket(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, c
     const int nb = 1 << (2 * (k - PART_LOW));
     const LevelInfo li = make_level_info(row);
     const int k_stop = std::max(k - PART_LOW, k_bottom);
-    dim3 grid((unsigned)nb, (unsigned)n_genomes);
-    bucket_kernel<<<grid, BUCKET_THREADS, sizeof(BucketSmem), s>>>(lm, row, li, k, k_stop,
-        (const GenomeTiles*)d_genome_tiles, d_payload, part_slot_shift(k), d_stats, d_freq, freq_stride, d_totals, genome0);
-    KM_CUDA(cudaGetLastError());
+    for (int h0 = 0; h0 < n_genomes; h0 += 32768) {           // gridDim.y <= 65535
+        dim3 grid((unsigned)nb, (unsigned)std::min(32768, n_genomes - h0));
+        bucket_kernel<<<grid, BUCKET_THREADS, sizeof(BucketSmem), s>>>(lm, row, li, k, k_stop,
+            (const GenomeTiles*)d_genome_tiles, d_payload, part_slot_shift(k), d_stats, d_freq, freq_stride, d_totals,
+            genome0 + (uint32_t)h0);
+        KM_CUDA(cudaGetLastError());
+    }
     return KMERML_OK;
 }
 
