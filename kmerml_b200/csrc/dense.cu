@@ -118,47 +118,51 @@ struct SmemSink {
     }
 };
 
-// k = 8: 65536 bins as packed 16-bit halves of 32768 shared words (128 KB).  A bin that reaches
-// 0x4000 is spilled (0x4000 moved to the global row) by the thread that saw it cross; because the
-// CTA synchronises after every tile (<= 16384 windows) a half can never exceed 0x7FFF, so there is
-// no carry into its neighbour and the counts stay exact for any input.
+// k = 8: 65536 bins as packed 16-bit halves of 32768 shared words (128 KB), counted with non-returning
+// shared atomics like the 32-bit histograms of k <= 7.  Exactness: a tile has at most 16384 windows, and
+// every third tile the CTA sweeps the histogram and moves every half that has reached 0x4000 to the
+// global row (sweep_packed16), so a half never exceeds 0x3FFF + 3 * 16384 = 0xFFFF: no carry into its
+// neighbour for any input (tested with a homopolymer).
 struct Packed16Sink {
-    uint32_t* __restrict__ hist;       // shared, 32768 words
-    uint32_t* __restrict__ row;        // this genome's level-8 count row (global)
+    uint32_t sbase;                    // shared-window address of the 32768 words
     unsigned n;
     __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
-        const uint32_t sh = (idx & 1u) << 4;
-        const uint32_t old = atomicAdd(hist + (idx >> 1), 1u << sh);
+        // word (idx >> 1), half (idx & 1): add 1 or 0x10000
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sbase + ((idx & ~1u) << 1)), "r"(1u + (idx & 1u) * 0xFFFFu)
+                     : "memory");
         n++;
-        if (((old >> sh) & 0xFFFFu) == 0x3FFFu) spill(idx, sh);
     }
-    __device__ __noinline__ void spill(uint32_t idx, uint32_t sh) {
-        atomicAdd(row + idx, 0x4000u);
-        atomicAdd(hist + (idx >> 1), 0u - (0x4000u << sh));
+    __device__ __forceinline__ void count4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pa, uint64_t pb,
+                                           uint64_t pc, uint64_t pd) {
+        count(a, pa); count(b, pb); count(c, pc); count(d, pd);
     }
-    __device__ __forceinline__ void count4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t, uint64_t, uint64_t,
-                                           uint64_t) {
-        const uint32_t w[4] = {a, b, c, d};
-        place<4>(w);
-    }
-    __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t*) { place<8>(w); }
-    __device__ __forceinline__ void count8_tail(const uint32_t* w, const uint64_t*, bool last) {
-        place<7>(w);
-        if (last) count(w[7], 0);
-    }
-    template <int N>
-    __device__ __forceinline__ void place(const uint32_t* idx) {
-        uint32_t old[N];
+    __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t* p) {
 #pragma unroll
-        for (int u = 0; u < N; u++) old[u] = atomicAdd(hist + (idx[u] >> 1), 1u << ((idx[u] & 1u) << 4));
-        n += N;
+        for (int i = 0; i < 8; i++) count(w[i], p[i]);
+    }
+    __device__ __forceinline__ void count8_tail(const uint32_t* w, const uint64_t* p, bool last) {
 #pragma unroll
-        for (int u = 0; u < N; u++) {
-            const uint32_t sh = (idx[u] & 1u) << 4;
-            if (((old[u] >> sh) & 0xFFFFu) == 0x3FFFu) spill(idx[u], sh);
-        }
+        for (int i = 0; i < 7; i++) count(w[i], p[i]);
+        if (last) count(w[7], p[7]);
     }
 };
+
+// (whole CTA, between the barrier that ends a tile and the one that precedes the next tile's counting)
+__device__ __forceinline__ void sweep_packed16(uint32_t* hist, uint32_t* row) {
+    uint4* h4 = reinterpret_cast<uint4*>(hist);
+    for (int i = threadIdx.x; i < 32768 / 4; i += COUNT_THREADS) {
+        const uint4 v = h4[i];
+        if (((v.x | v.y | v.z | v.w) & 0xC000C000u) == 0u) continue;        // every half below 0x4000
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t lo = w[j] & 0xFFFFu, hi = w[j] >> 16;
+            if (lo >= 0x4000u) { atomicAdd(row + 2 * (4 * i + j), lo); w[j] &= 0xFFFF0000u; }
+            if (hi >= 0x4000u) { atomicAdd(row + 2 * (4 * i + j) + 1, hi); w[j] &= 0x0000FFFFu; }
+        }
+        h4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
 
 struct FirstSink {
     uint32_t* first;
@@ -488,8 +492,11 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
     } else if (MODE == 3) {
         for (int i = tid; i < 32768; i += COUNT_THREADS) sh_hist[i] = 0;
         Packed16Sink sink;
-        sink.hist = sh_hist; sink.row = lm.ptr(sl.genome, 8); sink.n = 0;
-        walk_slice<true>(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
+        sink.sbase = (uint32_t)__cvta_generic_to_shared(sh_hist); sink.n = 0;
+        uint32_t* row8 = lm.ptr(sl.genome, 8);
+        walk_slice<true>(buf, g, sl, P, sink, tails, tc, [&](uint32_t tile_no) {
+            if (tile_no % 3u == 2u) sweep_packed16(sh_hist, row8);
+        });
         n = sink.n;
     } else {
         SmemSink sink;
