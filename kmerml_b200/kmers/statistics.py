@@ -104,9 +104,17 @@ def features_from_digits(values, wanted):
         with np.errstate(divide="ignore", invalid="ignore"):
             cols["cpg_obs_exp"] = np.where(expected > 0, cpg / np.where(expected > 0, expected, 1.0), 0.0)
     if "entropy" in wanted:
-        key = np.stack([nd, n_a, n_c, n_g, n_t, n_n], axis=1)
-        uniq, inverse = np.unique(key, axis=0, return_inverse=True)
-        table = np.array([_entropy_of(row[1:], int(row[0])) for row in uniq.tolist()], dtype=np.float64)
+        # (counts are < 64: one packed integer per composition instead of a row-wise unique)
+        key = ((((nd * 64 + n_a) * 64 + n_c) * 64 + n_g) * 64 + n_t) * 64 + n_n
+        uniq, inverse = np.unique(key, return_inverse=True)
+        table = np.empty(uniq.size, dtype=np.float64)
+        for i, u in enumerate(uniq.tolist()):
+            parts = []
+            for _ in range(5):
+                parts.append(u % 64)
+                u //= 64
+            nn_, nt_, ng_, nc_, na_ = parts
+            table[i] = _entropy_of([na_, nc_, ng_, nt_, nn_], int(u))
         ent = table[inverse.ravel()]
         cols["shannon_entropy"] = ent
         cols["normalized_entropy"] = ent / 2.0
@@ -148,6 +156,46 @@ def _features_from_strings(kmers, wanted):
         if "repeats" in wanted:
             out["has_repeat"].append(1 if any(s[i:i + 2] == s[i + 2:i + 4] for i in range(n - 3)) else 0)
     return {k: np.asarray(v, dtype=object if k == "kmer" else None) for k, v in out.items()}
+
+
+def _fast_csv(frames, genome_size):
+    """The text DataFrame.to_csv(index=False) writes for the concatenated frames, built without formatting every
+    cell: all columns after 'count' are functions of the (shortened) k-mer, and only a few thousand distinct
+    combinations of them occur, so pandas formats one row per combination and the rest is string joining.
+    Returns None when a frame does not have the expected shape (the caller then lets pandas write it)."""
+    if not frames:
+        return None
+    columns = list(frames[0].columns)
+    if columns[:3] != ["kmer", "count", "k"] or any(list(f.columns) != columns for f in frames):
+        return None
+    header = ",".join(columns + (["genome_size"] if genome_size else []))
+    tail = f",{genome_size}" if genome_size else ""
+    out = [header]
+    for f in frames:
+        n = len(f)
+        if n == 0:
+            continue
+        rest = f.iloc[:, 2:]
+        if rest.shape[1] > 1:
+            # one small integer per row and distinct combination: factorise column by column
+            key = np.zeros(n, dtype=np.int64)
+            for name in rest.columns:
+                codes, uniques = pd.factorize(rest[name].to_numpy(), sort=False)
+                key, combos = pd.factorize(key * len(uniques) + codes, sort=False)
+                if len(combos) > (1 << 22):
+                    return None
+            uniq, first, inverse = np.unique(key, return_index=True, return_inverse=True)
+        else:
+            uniq, first, inverse = np.zeros(1, np.int64), np.zeros(1, np.int64), np.zeros(n, np.int64)
+        lines = rest.iloc[first].to_csv(index=False, header=False, lineterminator="\n").split("\n")[:len(first)]
+        suffix = [ln + tail for ln in lines]
+        kmers = f["kmer"].tolist()
+        if any(("," in str(x)) or ('"' in str(x)) or ("\n" in str(x)) for x in kmers[:1]):
+            return None
+        counts = f["count"].tolist()
+        inv = inverse.ravel().tolist()
+        out.extend(f"{a},{b},{suffix[i]}" for a, b, i in zip(kmers, counts, inv))
+    return "\n".join(out) + "\n"
 
 
 class KmerFeatureExtractor:
@@ -197,11 +245,16 @@ class KmerFeatureExtractor:
         if not frames:
             print(f"No features extracted for {organism}")
             return None
-        result = pd.concat(frames, ignore_index=True) if len(frames) > 1 else frames[0]
-        if genome_size:
-            result["genome_size"] = genome_size
         output_file = self.output_dir / f"{organism}_kmer_features.csv"
-        result.to_csv(output_file, index=False)
+        text = _fast_csv(frames, genome_size)
+        if text is not None:
+            with open(output_file, "w", newline="") as fh:
+                fh.write(text)
+        else:
+            result = pd.concat(frames, ignore_index=True) if len(frames) > 1 else frames[0]
+            if genome_size:
+                result["genome_size"] = genome_size
+            result.to_csv(output_file, index=False)
         print(f"Created feature CSV for {organism}: {output_file}")
         return output_file
 
