@@ -215,7 +215,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     // fit the shared histogram of count_kernel<1> (256 KB), so it is counted as 9-mers through the
     // partition path (level 9 is a pass-through scratch level) instead of with global atomics
     const bool part_ok = !(flags & KMERML_FLAG_NO_PARTITION);
-    // k = 8: packed 16-bit shared histogram (count_kernel<3>); KMERML_FLAG_K8_AS_9 counts 9-mers through
+    // k = 8: packed 16-bit shared histogram (count8_kernel); KMERML_FLAG_K8_AS_9 counts 9-mers through
     // the partition path instead (kept for comparison)
     const int kcount = (kmax == SMEM_MAX_K + 1 && part_ok && (flags & KMERML_FLAG_K8_AS_9)) ? PART_MIN_K : kmax;
     const bool use_smem = kcount <= SMEM_MAX_K + 1;

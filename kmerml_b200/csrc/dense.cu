@@ -119,9 +119,10 @@ struct SmemSink {
 };
 
 // k = 8: 65536 bins as packed 16-bit halves of 32768 shared words (128 KB), counted with non-returning
-// shared atomics like the 32-bit histograms of k <= 7.  Exactness: a tile has at most 16384 windows, and
-// every third tile the CTA sweeps the histogram and moves every half that has reached 0x4000 to the
-// global row (sweep_packed16), so a half never exceeds 0x3FFF + 3 * 16384 = 0xFFFF: no carry into its
+// shared atomics like the 32-bit histograms of k <= 7.  The histogram leaves room for one CTA per SM, so
+// that CTA has 1024 threads (count8_kernel: 32 KB tiles).  Exactness: a tile has at most 32768 windows,
+// and after every tile the CTA sweeps the histogram and moves every half that has reached 0x4000 to the
+// global row (sweep_packed16), so a half never exceeds 0x3FFF + 32768 = 0xBFFF: no carry into its
 // neighbour for any input (tested with a homopolymer).
 struct Packed16Sink {
     uint32_t sbase;                    // shared-window address of the 32768 words
@@ -148,9 +149,10 @@ struct Packed16Sink {
 };
 
 // (whole CTA, between the barrier that ends a tile and the one that precedes the next tile's counting)
+template <int NT>
 __device__ __forceinline__ void sweep_packed16(uint32_t* hist, uint32_t* row) {
     uint4* h4 = reinterpret_cast<uint4*>(hist);
-    for (int i = threadIdx.x; i < 32768 / 4; i += COUNT_THREADS) {
+    for (int i = threadIdx.x; i < 32768 / 4; i += NT) {
         const uint4 v = h4[i];
         if (((v.x | v.y | v.z | v.w) & 0xC000C000u) == 0u) continue;        // every half below 0x4000
         uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -197,10 +199,11 @@ struct TileCtx {                      // shared-memory state of the tile loop
     uint32_t* prev_tile;              // [2] {ok, last16} of the previous tile's last chunk
 };
 
-#define KM_TILE_SMEM(prefix)                                   \
-    __shared__ uint8_t prefix##_flags[2 * COUNT_THREADS];      \
-    __shared__ uint8_t prefix##_clean[COUNT_THREADS];          \
-    __shared__ uint32_t prefix##_last16[COUNT_THREADS];        \
+#define KM_TILE_SMEM(prefix) KM_TILE_SMEM_N(prefix, COUNT_THREADS)
+#define KM_TILE_SMEM_N(prefix, NT)                             \
+    __shared__ uint8_t prefix##_flags[2 * (NT)];               \
+    __shared__ uint8_t prefix##_clean[(NT)];                   \
+    __shared__ uint32_t prefix##_last16[(NT)];                 \
     __shared__ unsigned long long prefix##_carry[2];           \
     __shared__ uint32_t prefix##_prev[2];                      \
     TileCtx tc;                                                \
@@ -215,7 +218,7 @@ struct TileCtx {                      // shared-memory state of the tile loop
 // prefetch; needs 8 registers across the whole tile: the histogram kernels have them) or right before
 // the tile's closing barrier (the partition kernel, whose placement code needs every register: there
 // the early prefetch was spilled to local memory at once, measured).
-template <bool EARLY_LOAD, class Sink, class Tails, class PerTile>
+template <bool EARLY_LOAD, int NT = COUNT_THREADS, class Sink, class Tails, class PerTile>
 __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, const Genome& g, const Slice& sl,
                                            const DenseParams& P, Sink& sink, const Tails& tails, const TileCtx& tc,
                                            PerTile&& per_tile) {
@@ -228,7 +231,7 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
     //  * clean[] / last16[] are written in phase 1 and read by the right neighbour in phase 2.
     const int tid = threadIdx.x;
     tc.flags[tid] = 0;
-    tc.flags[COUNT_THREADS + tid] = 0;
+    tc.flags[NT + tid] = 0;
     if (tid == 0) {
         tc.carry[0] = 0;
         tc.carry[1] = 0;
@@ -240,7 +243,7 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
     const uint64_t end = sl.end < g.hi ? sl.end : g.hi;
     auto load_chunk = [&](uint64_t tbx, uint32_t* w) -> bool {
         const uint64_t cbx = tbx + (uint64_t)tid * CHUNK;
-        if (!(cbx >= g.lo && cbx + CHUNK <= g.hi && tbx < end)) return false;
+        if (!(cbx >= g.lo && cbx + CHUNK <= g.hi && cbx < end)) return false;
         const uint4* src = reinterpret_cast<const uint4*>(buf + cbx);
 #pragma unroll
         for (int i = 0; i < CHUNK / 16; i++) {
@@ -252,19 +255,19 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
     uint32_t w[CHUNK / 4], wn[CHUNK / 4];
     bool full = load_chunk(sl.begin, w);
     uint32_t tile_no = 0;
-    for (uint64_t tb = sl.begin; tb < end; tb += TILE_BYTES, tile_no++) {
-        uint8_t* flags = tc.flags + (tile_no & 1u) * COUNT_THREADS;
+    for (uint64_t tb = sl.begin; tb < end; tb += (NT * CHUNK), tile_no++) {
+        uint8_t* flags = tc.flags + (tile_no & 1u) * NT;
         bool full_next = false;
-        if (EARLY_LOAD) full_next = load_chunk(tb + TILE_BYTES, wn);
+        if (EARLY_LOAD) full_next = load_chunk(tb + (NT * CHUNK), wn);
         const uint64_t cb = tb + (uint64_t)tid * CHUNK;
         const uint64_t cs = cb > g.lo ? cb : g.lo;
         const uint64_t ce = cb + CHUNK < g.hi ? cb + CHUNK : g.hi;
-        const bool has = cs < ce;
+        const bool has = cs < ce && cb < end;                // (a slice need not be a whole number of tiles)
         CleanChunk cc;
         cc.hi = cc.lo = 0; cc.n = 0; cc.nl = 32; cc.last16 = 0;
         bool clean = false;
         auto on_header = [&](uint64_t, uint64_t until) {
-            for (int j = tid + 1; j < COUNT_THREADS && tb + (uint64_t)j * CHUNK < until; j++) flags[j] = 1;
+            for (int j = tid + 1; j < NT && tb + (uint64_t)j * CHUNK < until; j++) flags[j] = 1;
             atomicMax(&tc.carry[tile_no & 1u], (unsigned long long)until);
         };
         if (full) {
@@ -294,7 +297,7 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
             const unsigned long long seen = tc.carry[tile_no & 1u];
             hc = seen > hc ? seen : hc;                     // header lines that run into later tiles
         }
-        tc.flags[((tile_no & 1u) ^ 1u) * COUNT_THREADS + tid] = 0;
+        tc.flags[((tile_no & 1u) ^ 1u) * NT + tid] = 0;
         if (has) {
             if (clean && !in_hdr && prev_ok && P.min_rec <= P.k) {
                 emit_clean(cc, carry16, cs, P, sink);
@@ -303,9 +306,9 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
                 walk_chunk(g, cs, ce, in_hdr, P, sink, tails, [&](uint64_t pos) -> uint32_t { return g.b[pos]; });
             }
         }
-        if (!EARLY_LOAD) full_next = load_chunk(tb + TILE_BYTES, wn);    // in flight during the barrier and the hook
+        if (!EARLY_LOAD) full_next = load_chunk(tb + (NT * CHUNK), wn);    // in flight during the barrier and the hook
         __syncthreads();
-        if (tid == COUNT_THREADS - 1) {
+        if (tid == NT - 1) {
             tc.prev_tile[0] = (has && clean && !in_hdr) ? 1u : 0u;
             tc.prev_tile[1] = cc.last16;
         }
@@ -450,7 +453,7 @@ slice_long_resolve_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __re
     }
 }
 
-// MODE 0: global histogram, 1: shared histogram, 2: first occurrence, 3: packed 16-bit shared histogram (k = 8)
+// MODE 0: global histogram, 1: shared histogram, 2: first occurrence  (k = 8: count8_kernel below)
 template <int MODE>
 __global__ void __launch_bounds__(COUNT_THREADS)
 count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
@@ -489,15 +492,6 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
         sink.top = lm.ptr(sl.genome, P.k); sink.n = 0;
         walk_slice<true>(buf, g, sl, P, sink, tails, tc, [](uint32_t) {});
         n = sink.n;
-    } else if (MODE == 3) {
-        for (int i = tid; i < 32768; i += COUNT_THREADS) sh_hist[i] = 0;
-        Packed16Sink sink;
-        sink.sbase = (uint32_t)__cvta_generic_to_shared(sh_hist); sink.n = 0;
-        uint32_t* row8 = lm.ptr(sl.genome, 8);
-        walk_slice<true>(buf, g, sl, P, sink, tails, tc, [&](uint32_t tile_no) {
-            if (tile_no % 3u == 2u) sweep_packed16(sh_hist, row8);
-        });
-        n = sink.n;
     } else {
         SmemSink sink;
         sink.sbase = (uint32_t)__cvta_generic_to_shared(sh_hist); sink.n = 0;
@@ -513,13 +507,38 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
             if (v) atomicAdd(top + i, v);
         }
     }
-    if (MODE == 3) {
-        uint32_t* top = lm.ptr(sl.genome, 8);
-        for (int i = tid; i < 32768; i += COUNT_THREADS) {
-            const uint32_t v = sh_hist[i];
-            if (v & 0xFFFFu) atomicAdd(top + 2 * i, v & 0xFFFFu);
-            if (v >> 16) atomicAdd(top + 2 * i + 1, v >> 16);
-        }
+    if (tid == 0 && total) atomicAdd(&stats[sl.genome].total_top, total);
+}
+
+// k = 8 (see Packed16Sink): one CTA of 1024 threads per SM, 32 KB tiles.
+constexpr int COUNT8_THREADS = 1024;
+__global__ void __launch_bounds__(COUNT8_THREADS, 1)
+count8_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds, const Slice* __restrict__ slices,
+              DenseParams P, LevelMap lm, GenomeStats* stats) {
+    extern __shared__ __align__(16) uint32_t sh_hist[];
+    KM_TILE_SMEM_N(c8, COUNT8_THREADS)
+    __shared__ unsigned long long sh_total;
+    const int tid = threadIdx.x;
+    const Slice sl = slices[blockIdx.x];
+    const GenomeDev gd = gds[sl.genome];
+    Genome g;
+    g.b = buf;
+    g.lo = gd.lo;
+    g.hi = gd.hi;
+    for (int i = tid; i < 32768; i += COUNT8_THREADS) sh_hist[i] = 0;
+    if (tid == 0) sh_total = 0;
+    DevTails tails;
+    tails.lm = &lm; tails.st = stats + sl.genome; tails.genome = sl.genome;
+    Packed16Sink sink;
+    sink.sbase = (uint32_t)__cvta_generic_to_shared(sh_hist); sink.n = 0;
+    uint32_t* row8 = lm.ptr(sl.genome, 8);
+    walk_slice<true, COUNT8_THREADS>(buf, g, sl, P, sink, tails, tc,
+                                     [&](uint32_t) { sweep_packed16<COUNT8_THREADS>(sh_hist, row8); });
+    const unsigned long long total = block_sum_u32(sink.n, &sh_total);
+    for (int i = tid; i < 32768; i += COUNT8_THREADS) {
+        const uint32_t v = sh_hist[i];
+        if (v & 0xFFFFu) atomicAdd(row8 + 2 * i, v & 0xFFFFu);
+        if (v >> 16) atomicAdd(row8 + 2 * i + 1, v >> 16);
     }
     if (tid == 0 && total) atomicAdd(&stats[sl.genome].total_top, total);
 }
@@ -1189,7 +1208,7 @@ finalize_canonical_kernel(LevelMap lm, RowSpec row, int k_top, const GenomeStats
 int dense_setup_attributes() {
     KM_CUDA(cudaFuncSetAttribute(count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (1 << (2 * SMEM_MAX_K)) * 4));
-    KM_CUDA(cudaFuncSetAttribute(count_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+    KM_CUDA(cudaFuncSetAttribute(count8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
     KM_CUDA(cudaFuncSetAttribute(partition_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
     KM_CUDA(cudaFuncSetAttribute(partition_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
     KM_CUDA(cudaFuncSetAttribute(partition_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
@@ -1232,7 +1251,7 @@ int launch_count(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice
     if (n_slices <= 0) return KMERML_OK;
     DenseParams P = make_params(k, min_rec, k > k_bottom, k_bottom);
     if (use_smem && k == 8) {
-        count_kernel<3><<<n_slices, COUNT_THREADS, 32768 * 4, s>>>(d_fasta, d_genomes, d_slices, P, lm, d_stats, nullptr);
+        count8_kernel<<<n_slices, COUNT8_THREADS, 32768 * 4, s>>>(d_fasta, d_genomes, d_slices, P, lm, d_stats);
     } else if (use_smem) {
         size_t smem = (size_t)(1u << (2 * k)) * 4;
         count_kernel<1><<<n_slices, COUNT_THREADS, smem, s>>>(d_fasta, d_genomes, d_slices, P, lm, d_stats, nullptr);
