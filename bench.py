@@ -106,6 +106,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
+    def wait_ready(self, timeout=8.0):
+        """Block until nvidia-smi has printed its first sample (its start-up can take seconds on a cold box)."""
+        t = time.time()
+        while self.proc and not self.lines and time.time() - t < timeout and self.proc.poll() is None:
+            time.sleep(0.02)
+
+    def samples_between(self, t0, t1):
+        return sum(1 for ts, _ in self.lines if t0 - 0.05 <= ts <= t1 + 0.05)
+
     def stop(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -127,7 +136,8 @@ class ClockSampler:
                     if val.lower().startswith("active"):
                         reasons.add(name)
         if not sm:
-            sm = [float(x.split(",")[1]) for _, x in self.lines[-3:] if len(x.split(",")) > 2] or [0.0]
+            return {"sm_mhz": None, "sm_max_mhz": float(max(mx)) if mx else None,
+                    "reasons": ["no nvidia-smi sample fell into the loaded window"], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -241,7 +251,8 @@ def run_ours(args):
     # clocks / throttle reasons are sampled under load: from the first warm-up step to the end of the timed region
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.25)
+    sampler.wait_ready()
+    time.sleep(0.05)
     t_load = time.time()
     for _ in range(max(args.warmup, 0)):
         step()
@@ -260,7 +271,17 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     prof = ctx.profile_read(reset=True)
     ctx.profile_enable(False)
-    clocks = sampler.stop(t_load, t1)
+    t_clk = t1
+    if sampler.samples_between(t_load, t1) < 3:
+        # the warm-up + timed steps were over before nvidia-smi sampled three times: keep the same load running
+        # (untimed steps) until it has, so that the clocks are still read under this workload
+        t_more = time.time()
+        while sampler.samples_between(t_load, time.time()) < 3 and time.time() - t_more < 1.0:
+            step()
+            torch.cuda.synchronize()
+        t_clk = time.time()
+    clocks = sampler.stop(t_load, t_clk)
+    clocks["window"] = "warm-up + timed steps" + ("" if t_clk == t1 else " + untimed steps of the same load until 3 samples")
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -229,6 +229,8 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
     //  * carry[parity] only ever grows (atomicMax of header ends); every thread folds it into its own
     //    running maximum `hc` after the barrier that closes phase 1;
     //  * clean[] / last16[] are written in phase 1 and read by the right neighbour in phase 2.
+    // slices are whole numbers of 16 KB tiles; a CTA with larger tiles must clip its chunks to the slice end
+    constexpr bool CLIP = NT * CHUNK > TILE_BYTES;
     const int tid = threadIdx.x;
     tc.flags[tid] = 0;
     tc.flags[NT + tid] = 0;
@@ -243,7 +245,7 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
     const uint64_t end = sl.end < g.hi ? sl.end : g.hi;
     auto load_chunk = [&](uint64_t tbx, uint32_t* w) -> bool {
         const uint64_t cbx = tbx + (uint64_t)tid * CHUNK;
-        if (!(cbx >= g.lo && cbx + CHUNK <= g.hi && cbx < end)) return false;
+        if (!(cbx >= g.lo && cbx + CHUNK <= g.hi && (CLIP ? cbx : tbx) < end)) return false;
         const uint4* src = reinterpret_cast<const uint4*>(buf + cbx);
 #pragma unroll
         for (int i = 0; i < CHUNK / 16; i++) {
@@ -262,7 +264,7 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
         const uint64_t cb = tb + (uint64_t)tid * CHUNK;
         const uint64_t cs = cb > g.lo ? cb : g.lo;
         const uint64_t ce = cb + CHUNK < g.hi ? cb + CHUNK : g.hi;
-        const bool has = cs < ce && cb < end;                // (a slice need not be a whole number of tiles)
+        const bool has = cs < ce && (!CLIP || cb < end);
         CleanChunk cc;
         cc.hi = cc.lo = 0; cc.n = 0; cc.nl = 32; cc.last16 = 0;
         bool clean = false;
