@@ -172,3 +172,22 @@ def test_single_process_additivity_over_ranges():
             total = c.numpy().view(np.uint32).astype(np.uint64) if total is None else total + c.numpy().view(np.uint32)
         ref = np.concatenate([oracle.count_dense(genome.tobytes(), k, 9) for k in (2, 9)])
         assert np.array_equal(total, ref), world
+
+
+def test_key_owner_splits_tile_the_key_space():
+    """Owners are ascending along sorted keys, every key has exactly one owner, also for k = 32 (top bit set)."""
+    rng = np.random.default_rng(3)
+    for k in (5, 8, 21, 31, 32):
+        bits = 2 * k
+        keys = np.unique(rng.integers(0, 2 ** 63, 5000, dtype=np.uint64) >> np.uint64(64 - bits)) if bits < 64 else \
+            np.unique(rng.integers(0, 2 ** 63, 5000, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, 5000, dtype=np.uint64))
+        keys.sort()
+        t = torch.from_numpy(keys.view(np.int64).copy())
+        for world in (1, 2, 3, 8):
+            sp = kdist.key_owner_splits(t, k, world)
+            assert len(sp) == world and sum(sp) == keys.size
+            top = (keys >> np.uint64(bits - 16)) & np.uint64(0xFFFF) if bits >= 16 else (keys << np.uint64(16 - bits)) & np.uint64(0xFFFF)
+            owner = (top * np.uint64(world)) >> np.uint64(16)
+            assert np.all(np.diff(owner.astype(np.int64)) >= 0)
+            assert sp == np.bincount(owner.astype(np.int64), minlength=world).tolist()
+    assert kdist.key_owner_splits(torch.zeros(0, dtype=torch.int64), 21, 4) == [0, 0, 0, 0]

@@ -131,3 +131,26 @@ def test_install_as_kmerml():
         for k in [k for k in sys.modules if k == "kmerml" or k.startswith("kmerml.") or k == "scripts" or k.startswith("scripts.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_fast_csv_writer_equals_pandas(tmp_path):
+    """The feature CSV is assembled from one pandas-formatted row per distinct feature combination; the text must
+    be exactly what DataFrame.to_csv writes for the concatenated frames (with and without genome_size)."""
+    from kmerml_b200.kmers import statistics as st
+    rng = np.random.default_rng(12)
+    fx = KmerFeatureExtractor(output_dir=tmp_path / "o")
+    frames = []
+    for k in (3, 7, 11):
+        digits = rng.integers(0, 4, (4000, k))
+        vals = (digits * (10 ** np.arange(k - 1, -1, -1))).sum(1).astype(np.int64)      # leading zeros vanish, as in pandas
+        df = pd.DataFrame({"kmer": vals, "count": rng.integers(1, 10 ** rng.integers(1, 7), 4000)})
+        frames.append(fx._extract_kmer_features(df, k, "org", st.ALL_FEATURES))
+    for genome_size in (None, 12157105):
+        want = pd.concat(frames, ignore_index=True)
+        if genome_size:
+            want["genome_size"] = genome_size
+        assert st._fast_csv(frames, genome_size) == want.to_csv(index=False)
+    sub = [f[["kmer", "count", "k", "gc_percent"]] for f in frames]
+    assert st._fast_csv(sub, None) == pd.concat(sub, ignore_index=True).to_csv(index=False)
+    only = [f[["kmer", "count", "k"]] for f in frames]
+    assert st._fast_csv(only, None) == pd.concat(only, ignore_index=True).to_csv(index=False)
