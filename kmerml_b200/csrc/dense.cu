@@ -590,9 +590,11 @@ struct SlotSink {
     uint16_t* __restrict__ staged;     // staged[nb << slot_shift]
     uint32_t* ov;                      // this genome's overflow list
     unsigned int* ov_count;
+    unsigned n;                        // windows seen by this thread (placed or overflowed)
     __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
         const uint32_t b = idx >> (2 * PART_LOW);
         const uint32_t pos = atomicAdd(cnt + b, 1u);
+        n++;
         if (pos < slot_size) {
             // entry e of bucket b lives at position (e + 2b) mod slot: the order inside a slot is
             // irrelevant, and the rotation spreads the random buckets over all 32 banks
@@ -619,6 +621,7 @@ struct SlotSink {
         for (int u = 0; u < N; u++) b[u] = idx[u] >> (2 * PART_LOW);
 #pragma unroll
         for (int u = 0; u < N; u++) pos[u] = (u < N - 1 || last_live) ? atomicAdd(cnt + b[u], 1u) : 0u;
+        n += last_live ? N : N - 1;
 #pragma unroll
         for (int u = 0; u < N; u++) {
             worst = max(worst, pos[u]);
@@ -682,6 +685,7 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     sink.staged = sm.staged;
     sink.ov = overflow + (gd.file_lo - batch_lo);      // one possible window per byte of the genome
     sink.ov_count = ov_counts + sl.genome;
+    sink.n = 0;
     ListTails tails;
     tails.lm = &lm; tails.st = stats + sl.genome; tails.genome = sl.genome; tails.k_stop = k_stop;
     tails.list = tail_list_of(tl, gd, sl.genome, &tails.cap);
@@ -694,7 +698,6 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     uint16_t* pg = payload + (size_t)gt.tile0 * STAGE_ENTRIES;
     const uint32_t b0 = (uint32_t)tid >> vec_shift, o = (uint32_t)tid & ((1u << vec_shift) - 1u);
     const size_t stride = (((size_t)(COUNT_THREADS >> vec_shift) * gt.n_tiles) << slot_shift) / 8;
-    unsigned n = 0;
     // Unused slot entries hold a padding value >= PART_BINS that the bucket kernel counts into a dummy
     // bin, so it needs neither fill counts nor validity tests.  The padding of (tile t, vector o of the
     // slot, entry e) is PART_BINS + ((t * vectors_per_slot + o) & 31) + 32 e: the 32 lanes of a bucket-
@@ -716,10 +719,7 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
         // another one.)  Vector v = tid + 512 j belongs to bucket (tid >> vec_shift) + (512 >> vec_shift) j:
         // the destination advances by a constant stride, one add per 128-bit store.  Each vector is
         // replaced by the next tile's padding as soon as it has been read.
-        for (int b = tid; b < nb; b += COUNT_THREADS) {
-            n += sm.cnt[b];                                  // every window, also those that found the slot full
-            sm.cnt[b] = 0;
-        }
+        if (tid < nb / 4) reinterpret_cast<uint4*>(sm.cnt)[tid] = make_uint4(0, 0, 0, 0);    // nb <= 1024 counters
         const uint32_t t_local = sl.tile0 + tile_no - gt.tile0;
         const uint4 pad = padding(t_local + 1);
         uint4* st = reinterpret_cast<uint4*>(sm.staged);
@@ -731,7 +731,7 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
             dst[j * stride] = x;
         }
     });
-    const unsigned long long total = block_sum_u32(n, &sm.sh_total);
+    const unsigned long long total = block_sum_u32(sink.n, &sm.sh_total);
     if (tid == 0 && total) atomicAdd(&stats[sl.genome].total_top, total);
 }
 
