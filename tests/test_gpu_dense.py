@@ -164,7 +164,7 @@ def test_byte_ranges_are_additive():
     dev = torch.from_numpy(g).cuda()
     for ks, part in (([12, 5], True), ([10], True), ([12, 11], False), ([6, 2], True), ([8], True)):
         whole = engine.count_dense_device(dev, [0, g.size], ks, want_freq=False, partition=part)
-        for world in (2, 5):
+        for world in (2, 3, 5, 7):          # 3 and 7: ranges that start at odd tiles (k = 8 walks 32 KB tiles)
             acc = torch.zeros_like(whole.counts[0], dtype=torch.int64)
             tot = torch.zeros_like(whole.totals[0])
             for b, e in kdist.chunk_ranges(g.size, world):
