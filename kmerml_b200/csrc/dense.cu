@@ -2,16 +2,24 @@
 //
 // Replaces the window loop of kmerml/kmers/generate.py:49-58 (reference tree).
 // Kernels:
-//   prologue_kernel   per genome: skip text before the first header line, zero stats
-//   count_kernel<0>   k = 8..14: one RED.ADD per window into the L2-resident 4^k row
-//   count_kernel<1>   k <= 7   : CTA-private shared-memory histogram, flushed once
-//   count_kernel<2>   first-occurrence offsets (atomicMin), for the k{k}.txt writer
-//   cascade_kernel    c_{j}[p] = sum_b c_{j+1}[4p+b] + tails_j[p], 5 levels per launch
-//   finalize_kernel   optional canonical fold, frequency row, window totals
+//   prologue_kernel            per genome: skip text before the first header line, zero stats
+//   slice_header_kernel        per slice: does it start inside a header line? (bounded look-back) ...
+//   slice_long_scan/_resolve   ... and the same for lines too long for that (unwrapped FASTA)
+//   count_kernel<1>            k <= 7   : CTA-private shared-memory histogram, flushed once
+//   count8_kernel              k = 8    : packed 16-bit shared histogram, 1024 threads, swept every tile
+//   partition_kernel<S>        k = 9..12: every window into its bucket's slot (shared atomics), slots written
+//                                         bucket-major; run-end tails into per-genome lists
+//   bucket_kernel              k = 9..12: per (bucket, genome) a 16384-bin shared histogram of its slots ->
+//                                         count row, frequencies and the bucket's cascade subtree
+//   overflow_kernel, tails_apply_kernel, tails_rescan_kernel   what slots / lists could not hold
+//   count_kernel<0>            k = 13, 14: one RED.ADD per window into the L2-resident 4^k row
+//   count_kernel<2>            first-occurrence offsets (atomicMin), for the k{k}.txt writer
+//   cascade_kernel             c_{j}[p] = sum_b c_{j+1}[4p+b] + tails_j[p], 6 levels per launch
+//   finalize_kernel / _low / _canonical    canonical fold, frequency rows, window totals
 //
-// Work decomposition: a CTA owns a slice (a few tiles) of one genome; a thread owns
-// the windows that START in its 32-byte chunk of the tile (fasta_walk.cuh), so there
-// is no carry between threads and no compaction pass: the FASTA bytes are read once.
+// Work decomposition: a CTA owns a slice (a run of tiles) of one genome; a thread owns the windows whose
+// LAST base lies in its 32-byte chunk of the tile (fasta_walk.cuh), so there is no carry between threads
+// and no compaction pass: the FASTA bytes are read once.
 #include <algorithm>
 
 #include "fasta_walk.cuh"
