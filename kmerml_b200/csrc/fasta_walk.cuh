@@ -1,6 +1,6 @@
 // fasta_walk.cuh -- exact FASTA byte-stream semantics for carry-free k-mer walking.
 //
-// Shared between the sm_100a kernels (dense_kernels.cu, ...) and the CPU thread
+// Shared between the sm_100a kernels (dense.cu, sparse.cu, features.cu) and the CPU thread
 // emulator in tests/emu (same source compiled with g++), so the per-thread logic
 // that runs on the GPU is the logic the CPU tests exercise.
 //

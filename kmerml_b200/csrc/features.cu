@@ -1,9 +1,10 @@
-// features.cu -- record table, static per-k-mer features, row normalisation and the
+// features.cu -- record table, genome tallies, static per-k-mer features, row normalisation and the
 // genome x genome distance matrix.
 //
 // Reference points (paths relative to the reference tree):
 //   scan_records      the per-record bookkeeping of kmerml/kmers/generate.py:39-46,60
 //                     (record ids come from the header lines, "too short" from lengths)
+//   genome_stats      contigs / total size / G+C / N of kmerml/utils/genome_metadata.py:55-85
 //   static_features   kmerml/kmers/statistics.py:190-240 (_add_gc / _add_base_count /
 //                     _add_presence / _add_cpg / _add_entropy / _add_repeat): every one
 //                     of them is a function of the k-mer string only, so one table per k
