@@ -33,6 +33,8 @@ struct EmuSink {
 }  // namespace
 
 static uint64_t g_line_limit = km::LINE_SCAN_LIMIT;
+static uint64_t g_slice_bytes = 0;
+extern "C" void emu_set_slice_bytes(uint64_t v) { g_slice_bytes = v; }
 extern "C" void emu_set_line_limit(uint64_t v) { g_line_limit = v ? v : km::LINE_SCAN_LIMIT; }
 extern "C" {
 
@@ -68,7 +70,9 @@ static int64_t emu_core(const uint8_t* bytes, uint64_t n, uint64_t base_off, int
     sink.first = out_first ? &first : nullptr;
 
     const uint64_t tile_bytes = (uint64_t)threads_per_tile * CHUNK;
-    const uint64_t slice_bytes = tile_bytes * (uint64_t)tiles_per_slice;
+    // g_slice_bytes != 0: slices that are NOT a whole number of tiles (count8_kernel: 32 KB tiles over slices
+    // of 16 KB units); the chunks of the last tile are then clipped to the slice end (walk_slice's CLIP)
+    const uint64_t slice_bytes = g_slice_bytes ? g_slice_bytes : tile_bytes * (uint64_t)tiles_per_slice;
     // slices are aligned to absolute multiples of slice_bytes (as on the GPU)
     uint64_t first_slice = g.lo / slice_bytes;
     // slice table passes (slice_header_kernel, slice_long_scan_kernel, slice_long_resolve_kernel)
@@ -118,7 +122,7 @@ static int64_t emu_core(const uint8_t* bytes, uint64_t n, uint64_t base_off, int
             auto clip = [&](int t, uint64_t& cs, uint64_t& ce) {
                 cs = std::max<uint64_t>(tb + (uint64_t)t * CHUNK, g.lo);
                 ce = std::min<uint64_t>(tb + (uint64_t)(t + 1) * CHUNK, g.hi);
-                return cs < ce;
+                return cs < ce && tb + (uint64_t)t * CHUNK < sb + slice_bytes;
             };
             for (int t = 0; t < threads_per_tile; t++) {            // phase 1: classify, pack, find header lines
                 uint64_t cs, ce;

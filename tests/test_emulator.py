@@ -118,3 +118,22 @@ def test_long_lines_and_bounded_lookback(emu):
                 check(emu, data, kmax, kmax, rng.choice([1, 2, 4]), rng.choice([1, 2, 3]), rng.choice([0, 5, 32, 64]))
     finally:
         emu.emu_set_line_limit(0)
+
+
+def test_slices_that_are_not_whole_tiles(emu):
+    """count8_kernel walks 32 KB tiles over slices made of 16 KB units: the last tile of a slice is clipped to the
+    slice end.  Emulated with small numbers: tiles of 4 or 8 chunks, slices of 3, 5, 7 ... chunks."""
+    emu.emu_set_slice_bytes.argtypes = [ctypes.c_uint64]
+    rng = random.Random(44)
+    try:
+        for _ in range(250):
+            tpt = rng.choice([4, 8])
+            emu.emu_set_slice_bytes(32 * rng.choice([1, 3, 5, 6, 7, 9, 11, 13]))
+            data = fuzz_fasta(rng)
+            kmax = rng.choice([1, 3, 6, 8])
+            check(emu, data, kmax, kmax, tpt, 1, rng.choice([0, 3, 32, 64]))
+        for c in golden_extract_cases():
+            emu.emu_set_slice_bytes(32 * rng.choice([3, 5, 7]))
+            check(emu, c["fasta"], 8, 8, 4, 1, rng.choice([0, 17]))
+    finally:
+        emu.emu_set_slice_bytes(0)
