@@ -16,6 +16,8 @@ Outputs
   matrix_cases.json   - KmerFeatureBuilder matrices, from
                         kmerml/ml/features.py:28-117
   ref_timing.json     - single-core timings of the reference extractor here
+  extract_big_cases.json - inputs of a few 100 kb (unwrapped, long header, repeats, CRLF + N runs, many short
+                        records): gzip FASTA + SHA-256 / line count of every k{k}.txt the reference wrote
 """
 import base64
 import contextlib
@@ -191,6 +193,45 @@ def stats_and_matrix_cases(extract):
     return stats, matrices
 
 
+def big_cases():
+    """Inputs of a few hundred kilobases that cross slice boundaries of the GPU kernels in their awkward modes
+    (unwrapped lines, a very long header made of base letters, tandem repeats, CRLF with N runs, thousands of
+    short records).  The reference's output files are large, so only their SHA-256 and line counts are kept;
+    the FASTA text travels gzip-compressed."""
+    import gzip
+    import hashlib
+    rng = random.Random(77)
+    seq = lambda n, alphabet="ACGT": "".join(rng.choice(alphabet) for _ in range(n))       # noqa: E731
+    wrap = lambda s, w, eol="\n": eol.join(s[i:i + w] for i in range(0, len(s), w))           # noqa: E731
+    unit = seq(171)
+    short = []
+    for i in range(5000):
+        short.append(f">s{i}\n{seq(rng.randint(8, 70), 'ACGTACGTACGTN')}\n")
+    cases = [
+        ("big_unwrapped", f">chr1 one line\n{seq(260_000)}\n>chr2\n{seq(90_000)}\n", [8, 12]),
+        ("big_header_of_bases", f">{seq(150_000)} a header made of base letters\n{wrap(seq(120_000), 70)}\n>x\n{seq(40)}\n", [12]),
+        ("big_satellite", f">sat\n{wrap(unit * 1200 + seq(60_000) + unit[:100] * 300, 80)}\n", [9, 12]),
+        ("big_crlf_n_runs", ">c\r\n" + wrap(seq(100_000) + "N" * 3000 + seq(80_000, "ACGTN") + seq(20_000), 60, "\r\n") + "\r\n", [7, 11]),
+        ("big_many_short_records", "".join(short), [5, 12]),
+    ]
+    out = []
+    for name, text, ks in cases:
+        with tempfile.TemporaryDirectory() as td:
+            fa = Path(td) / "GCF_900000001_1.fa"
+            with open(fa, "w", newline="") as f:
+                f.write(text)
+            with contextlib.redirect_stdout(io.StringIO()):
+                org = KmerExtractor(output_dir=Path(td) / "out", compress=False).extract_kmers_from_fasta(fa, list(ks))
+            files = {}
+            for k in ks:
+                data = (Path(td) / "out" / org / f"k{k}.txt").read_bytes()
+                files[str(k)] = {"sha256": hashlib.sha256(data).hexdigest(), "lines": data.count(b"\n"), "bytes": len(data)}
+            out.append({"name": name, "k_values": list(ks),
+                        "fasta_gz_b64": base64.b64encode(gzip.compress(text.encode("latin-1"), 9, mtime=0)).decode(),
+                        "files": files})
+    return out
+
+
 def timing():
     rng = random.Random(0)
     seq = "".join(rng.choice("ACGT") for _ in range(200_000))
@@ -215,7 +256,9 @@ def main():
     (HERE / "stats_cases.json").write_text(json.dumps(st, indent=0))
     (HERE / "matrix_cases.json").write_text(json.dumps(mx, indent=0))
     (HERE / "ref_timing.json").write_text(json.dumps(timing(), indent=1))
-    print(f"{len(ext)} extract cases, {len(st)} stats cases, {len(mx)} matrix cases")
+    big = big_cases()
+    (HERE / "extract_big_cases.json").write_text(json.dumps(big, indent=0))
+    print(f"{len(ext)} extract cases, {len(st)} stats cases, {len(mx)} matrix cases, {len(big)} big cases")
 
 
 if __name__ == "__main__":

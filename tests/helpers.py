@@ -107,3 +107,14 @@ def reduce_windows(keys, ends, begin=0, end=None):
     k, e = k[order], e[order]
     uniq, idx, cnt = np.unique(k, return_index=True, return_counts=True)
     return uniq, cnt.astype(np.int64), e[idx]
+
+
+def golden_big_cases():
+    """Inputs of a few hundred kilobases run through the unmodified reference (tests/golden/make_golden.py:
+    big_cases): FASTA bytes + SHA-256 / line count of every k{k}.txt it wrote."""
+    import gzip
+    with open(os.path.join(GOLDEN, "extract_big_cases.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        c["fasta"] = gzip.decompress(base64.b64decode(c["fasta_gz_b64"]))
+    return cases

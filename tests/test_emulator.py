@@ -137,3 +137,12 @@ def test_slices_that_are_not_whole_tiles(emu):
             check(emu, c["fasta"], 8, 8, 4, 1, rng.choice([0, 17]))
     finally:
         emu.emu_set_slice_bytes(0)
+
+
+def test_emulator_on_big_reference_cases(emu):
+    """The GPU thread decomposition (real tile size: 512 chunks, 8 tiles per slice) on the big reference-pinned
+    inputs, against the oracle (which test_oracle_golden pins to the reference's own output)."""
+    from helpers import golden_big_cases
+    for c in golden_big_cases():
+        kmax = min(max(c["k_values"]), 9)
+        check(emu, c["fasta"], kmax, kmax, 512, 8, 0)

@@ -244,3 +244,24 @@ def test_gpu_formatter_matches_golden_text():
             obs = np.nonzero(counts)[0]
             obs = obs[np.argsort(f[obs], kind="stable")]
             assert got == bytes(format_kmer_lines(obs, counts[obs], k)), (canonical, k)
+
+
+def test_extractor_reproduces_big_reference_outputs(tmp_path):
+    """KmerExtractor on the GPU against the files the unmodified reference wrote for inputs of a few hundred
+    kilobases (SHA-256 of every k{k}.txt): unwrapped lines, a 150 kb header made of base letters, tandem repeats
+    (slot overflow), CRLF + N runs, thousands of short records (tail lists)."""
+    import contextlib
+    import hashlib
+    import io
+    from helpers import golden_big_cases
+    from kmerml_b200.kmers.generate import KmerExtractor
+    for case in golden_big_cases():
+        fa = tmp_path / f"{case['name']}.fa"
+        fa.write_bytes(case["fasta"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            org = KmerExtractor(output_dir=tmp_path / "out", compress=False).extract_kmers_from_fasta(fa, case["k_values"])
+        for k in case["k_values"]:
+            data = (tmp_path / "out" / org / f"k{k}.txt").read_bytes()
+            want = case["files"][str(k)]
+            assert data.count(b"\n") == want["lines"], (case["name"], k)
+            assert hashlib.sha256(data).hexdigest() == want["sha256"], (case["name"], k)

@@ -65,3 +65,17 @@ def test_sparse_matches_dense():
         codes, cnts = oracle.count_sparse(g0["fasta"], k, 12)
         assert list(codes) == list(order)
         assert list(cnts) == [counts[b] for b in order]
+
+
+def test_oracle_reproduces_big_reference_outputs():
+    """The oracle against what the unmodified reference wrote for inputs of a few hundred kilobases (unwrapped
+    lines, a long header of base letters, tandem repeats, CRLF + N runs, thousands of short records)."""
+    import hashlib
+    from helpers import golden_big_cases
+    for case in golden_big_cases():
+        ml = max(case["k_values"])
+        for k in case["k_values"]:
+            text = oracle.kmer_file_text(case["fasta"], k, ml).encode()
+            want = case["files"][str(k)]
+            assert text.count(b"\n") == want["lines"], (case["name"], k)
+            assert hashlib.sha256(text).hexdigest() == want["sha256"], (case["name"], k)
