@@ -208,11 +208,11 @@ def big_cases():
     for i in range(5000):
         short.append(f">s{i}\n{seq(rng.randint(8, 70), 'ACGTACGTACGTN')}\n")
     cases = [
-        ("big_unwrapped", f">chr1 one line\n{seq(260_000)}\n>chr2\n{seq(90_000)}\n", [8, 12]),
+        ("big_unwrapped", f">chr1 one line\n{seq(260_000)}\n>chr2\n{seq(90_000)}\n", [8, 12, 21]),
         ("big_header_of_bases", f">{seq(150_000)} a header made of base letters\n{wrap(seq(120_000), 70)}\n>x\n{seq(40)}\n", [12]),
         ("big_satellite", f">sat\n{wrap(unit * 1200 + seq(60_000) + unit[:100] * 300, 80)}\n", [9, 12]),
         ("big_crlf_n_runs", ">c\r\n" + wrap(seq(100_000) + "N" * 3000 + seq(80_000, "ACGTN") + seq(20_000), 60, "\r\n") + "\r\n", [7, 11]),
-        ("big_many_short_records", "".join(short), [5, 12]),
+        ("big_many_short_records", "".join(short), [5, 12, 17]),
     ]
     out = []
     for name, text, ks in cases:
