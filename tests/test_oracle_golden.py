@@ -1,10 +1,14 @@
 """The CPU oracle against the fixtures produced by the UNMODIFIED reference
 (tests/golden/make_golden.py).  No GPU."""
+import os
+
 import numpy as np
 import pytest
 
 import oracle
 from helpers import golden_extract_cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 CASES = golden_extract_cases()
 
@@ -79,3 +83,43 @@ def test_oracle_reproduces_big_reference_outputs():
             want = case["files"][str(k)]
             assert text.count(b"\n") == want["lines"], (case["name"], k)
             assert hashlib.sha256(text).hexdigest() == want["sha256"], (case["name"], k)
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "kmerml")), reason="the reference tree exists only in the build container")
+def test_oracle_against_the_live_reference(tmp_path):
+    """Where the reference tree is present (the build container, never the GPU box) the UNMODIFIED reference is
+    run under the Bio.SeqIO shim on fresh random FASTA files and the oracle must reproduce every k{k}.txt byte
+    for byte -- the same procedure that produced tests/golden, on inputs nobody has looked at."""
+    import contextlib
+    import io
+    import random
+    import subprocess
+    import sys
+    from helpers import fuzz_fasta
+    rng = random.Random(os.getpid())
+    cases = []
+    for i in range(40):
+        data = fuzz_fasta(rng)
+        ks = sorted(rng.sample(range(1, 13), rng.randint(1, 3))) + ([rng.randint(13, 32)] if i % 4 == 0 else [])
+        (tmp_path / f"c{i}.fa").write_bytes(data)
+        cases.append((i, data, ks))
+    # the reference runs in a child process so that its modules never enter this interpreter
+    script = (
+        "import sys, json, contextlib, io\n"
+        f"sys.path.insert(0, {os.path.join(HERE, '_ref')!r}); sys.path.insert(1, {REFERENCE!r})\n"
+        "from kmerml.kmers.generate import KmerExtractor\n"
+        "root, spec = sys.argv[1], json.loads(sys.argv[2])\n"
+        "for i, ks in spec:\n"
+        "    with contextlib.redirect_stdout(io.StringIO()):\n"
+        "        KmerExtractor(output_dir=f'{root}/o{i}', compress=False).extract_kmers_from_fasta(f'{root}/c{i}.fa', ks)\n"
+    )
+    import json
+    subprocess.run([sys.executable, "-c", script, str(tmp_path), json.dumps([(i, ks) for i, _, ks in cases])],
+                   check=True, timeout=600)
+    for i, data, ks in cases:
+        for k in ks:
+            want = (tmp_path / f"o{i}" / f"c{i}" / f"k{k}.txt").read_text()
+            assert oracle.kmer_file_text(data, k, max(ks)) == want, (i, k, ks, data[:200])
