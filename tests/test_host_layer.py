@@ -154,3 +154,57 @@ def test_fast_csv_writer_equals_pandas(tmp_path):
     assert st._fast_csv(sub, None) == pd.concat(sub, ignore_index=True).to_csv(index=False)
     only = [f[["kmer", "count", "k"]] for f in frames]
     assert st._fast_csv(only, None) == pd.concat(only, ignore_index=True).to_csv(index=False)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/kmerml"), reason="the reference tree exists only in the build container")
+def test_statistics_csv_against_the_live_reference(tmp_path):
+    """Build container only: the unmodified KmerFeatureExtractor (child process) and the drop-in write the feature
+    CSV for the same fresh random k-mer files; identical except for the last ulps of the entropy columns, which
+    the reference sums in set-iteration (hash) order."""
+    import random
+    import subprocess
+    import sys
+    import oracle
+    from helpers import fuzz_fasta
+    rng = random.Random(os.getpid())
+    specs = []
+    for i in range(12):
+        data = fuzz_fasta(rng)
+        ks = sorted(rng.sample(range(1, 9), rng.randint(1, 3)))
+        kdir = tmp_path / f"k{i}" / f"GCF_90000{i:04d}_1"
+        kdir.mkdir(parents=True)
+        wrote = False
+        for k in ks:
+            text = oracle.kmer_file_text(data, k, max(ks))
+            (kdir / f"k{k}.txt").write_text(text)
+            wrote |= bool(text)
+        fs = rng.choice([None, ["gc_content", "base_counts"], ["gc_content", "base_counts", "entropy", "cpg_sites", "repeats"]])
+        specs.append((i, fs, wrote))
+    script = (
+        "import sys, json, contextlib, io\n"
+        "sys.path.insert(0, '/root/reference')\n"
+        "from kmerml.kmers.statistics import KmerFeatureExtractor\n"
+        "root, spec = sys.argv[1], json.loads(sys.argv[2])\n"
+        "for i, fs, _ in spec:\n"
+        "    with contextlib.redirect_stdout(io.StringIO()):\n"
+        "        KmerFeatureExtractor(input_paths=[f'{root}/k{i}'], output_dir=f'{root}/ref{i}').extract_features(fs)\n"
+    )
+    subprocess.run([sys.executable, "-c", script, str(tmp_path), json.dumps(specs)], check=True, timeout=600)
+    for i, fs, wrote in specs:
+        with contextlib.redirect_stdout(io.StringIO()):
+            KmerFeatureExtractor(input_paths=[tmp_path / f"k{i}"], output_dir=tmp_path / f"new{i}").extract_features(fs)
+        name = f"GCF_90000{i:04d}_1_kmer_features.csv"
+        ref_file, new_file = tmp_path / f"ref{i}" / name, tmp_path / f"new{i}" / name
+        assert ref_file.exists() == new_file.exists(), i
+        if not ref_file.exists():
+            continue
+        got, want = new_file.read_text(), ref_file.read_text()
+        if got == want:
+            continue
+        a, b = pd.read_csv(io.StringIO(got)), pd.read_csv(io.StringIO(want))
+        assert list(a.columns) == list(b.columns) and a.shape == b.shape, i
+        for col in a.columns:
+            if a[col].dtype.kind == "f":
+                np.testing.assert_allclose(a[col].to_numpy(), b[col].to_numpy(), rtol=1e-12, atol=0)
+            else:
+                assert a[col].equals(b[col]), (i, col)
