@@ -253,7 +253,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     // partition path: long runs of tiles per CTA amortise its set-up (fill of the staging buffer, first load,
     // final reduction), but a small batch needs enough CTAs to fill the GPU
     int part_tiles_per_slice = 1;
-    while (part_tiles_per_slice < PART_MAX_TILES_PER_SLICE &&
+    while (part_tiles_per_slice < PART_MAX_TILES_PER_RUN &&
            total_bytes / TILE_BYTES / (2ull * part_tiles_per_slice) >= (uint64_t)ctx->sm_count * 8)
         part_tiles_per_slice *= 2;
     std::vector<uint64_t> slice_bytes(n_genomes);
@@ -281,20 +281,6 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
         if (n_slices > 0x7fffffffull) return fail(KMERML_ERR_RANGE, "too many slices");
     }
     first_slice[n_genomes] = (uint32_t)n_slices;
-    // tiles of every genome (partition path: payload slots are addressed by tile)
-    std::vector<uint64_t> first_tile_abs(n_genomes, 0), tile_start(n_genomes + 1, 0);
-    for (int g = 0; g < n_genomes; g++) {
-        uint64_t lo = h_offsets[g], hi = h_offsets[g + 1];
-        if (range_end) { lo = std::max(lo, range_begin); hi = std::min(hi, range_end); }
-        uint64_t nt = 0;
-        if (lo < hi) {
-            first_tile_abs[g] = lo / TILE_BYTES;
-            nt = (hi - 1) / TILE_BYTES - first_tile_abs[g] + 1;
-        }
-        tile_start[g + 1] = tile_start[g] + nt;
-    }
-    if (use_part && tile_start[n_genomes] > 0x7fffffffull) return fail(KMERML_ERR_RANGE, "too many tiles");
-
     // ---- tables: offsets | genomes | stats | slices
     const size_t off_bytes = align_up((size_t)(n_genomes + 1) * 8, 256);
     const size_t gen_bytes = align_up((size_t)n_genomes * sizeof(GenomeDev), 256);
@@ -330,41 +316,41 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
                 // a range cuts whole tiles: clip the slice to it (range_begin is tile-aligned)
                 h_slices[si].begin = range_end ? std::max(b * sb, range_begin) : b * sb;
                 h_slices[si].end = range_end ? std::min((b + 1) * sb, range_end) : (b + 1) * sb;
-                if (use_part)     // skip the empty tiles before the genome's first byte: tiles are numbered from there
-                    h_slices[si].begin = std::max<uint64_t>(h_slices[si].begin, first_tile_abs[g] * TILE_BYTES);
-                h_slices[si].tile0 = (uint32_t)(tile_start[g] + (h_slices[si].begin / TILE_BYTES - first_tile_abs[g]));
+                if (use_part)     // skip the empty tiles before the genome's first byte
+                    h_slices[si].begin = std::max<uint64_t>(h_slices[si].begin, lo / TILE_BYTES * TILE_BYTES);
+                h_slices[si].tile0 = 0;
                 h_slices[si].hdr_until = 0;
                 si++;
             }
         }
         h_slices[n_slices].genome = 0;                      // scratch entry of launch_slice_headers
     }
-    // partition path: genomes are processed in groups whose payload workspace is bounded
-    uint32_t* d_gtiles = (uint32_t*)(base + off_bytes + gen_bytes + st_bytes + sl_bytes);
-    uint32_t* h_gtiles = (uint32_t*)(hs + off_bytes + sl_bytes);
+    // partition path: genomes are processed in groups whose payload workspace is bounded; a slice is a run
+    // (the tiles one partition CTA walks), and a run's regions take tiles_per_run * 64 KB of payload
+    uint32_t* d_gruns = (uint32_t*)(base + off_bytes + gen_bytes + st_bytes + sl_bytes);
+    uint32_t* h_gruns = (uint32_t*)(hs + off_bytes + sl_bytes);
     std::vector<int> group_end;                              // exclusive genome index per group
+    const uint64_t run_payload_bytes = (uint64_t)part_tiles_per_slice * PART_STAGE_ENTRIES * 2;
     if (use_part) {
-        const uint64_t max_tiles = std::max<uint64_t>(ctx->max_group_payload / ((uint64_t)PART_STAGE_ENTRIES * 2), 1);
+        const uint64_t max_runs = std::max<uint64_t>(ctx->max_group_payload / run_payload_bytes, 1);
         uint64_t in_group = 0;
-        uint64_t group_tile0 = 0;
+        uint32_t group_run0 = 0;
         for (int g = 0; g < n_genomes; g++) {
-            const uint64_t nt = tile_start[g + 1] - tile_start[g];
-            if (in_group && in_group + nt > max_tiles) {
+            const uint64_t nr = first_slice[g + 1] - first_slice[g];
+            if (in_group && in_group + nr > max_runs) {
                 group_end.push_back(g);
                 in_group = 0;
-                group_tile0 = tile_start[g];
+                group_run0 = first_slice[g];
             }
-            h_gtiles[2 * g] = (uint32_t)(tile_start[g] - group_tile0);
-            h_gtiles[2 * g + 1] = (uint32_t)nt;
-            in_group += nt;
-            // tile numbers inside slices are relative to the group's first tile
-            for (uint32_t si = first_slice[g]; si < first_slice[g + 1]; si++) h_slices[si].tile0 -= (uint32_t)group_tile0;
+            h_gruns[2 * g] = first_slice[g] - group_run0;    // run numbers are relative to the group's first run
+            h_gruns[2 * g + 1] = (uint32_t)nr;
+            in_group += nr;
         }
         group_end.push_back(n_genomes);
     }
     KM_CUDA(cudaMemcpyAsync(d_offsets, hs, off_bytes, cudaMemcpyHostToDevice, s));
     KM_CUDA(cudaMemcpyAsync(d_slices, h_slices, sl_bytes, cudaMemcpyHostToDevice, s));
-    if (use_part) KM_CUDA(cudaMemcpyAsync(d_gtiles, h_gtiles, gt_bytes, cudaMemcpyHostToDevice, s));
+    if (use_part) KM_CUDA(cudaMemcpyAsync(d_gruns, h_gruns, gt_bytes, cudaMemcpyHostToDevice, s));
     KM_CUDA(cudaEventRecord(ws.staging_free, s));
 
     {
@@ -378,24 +364,29 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     const size_t row_bytes = (size_t)row.off[nk] * 4;
     if (use_part) {
         const int k_stop = std::max(kcount - PART_LOW_BASES, kmin);
-        uint64_t max_group_tiles = 0, max_group_bytes = 0, max_group_genomes = 0;
+        uint64_t max_group_runs = 0, max_group_bytes = 0, max_group_genomes = 0;
         for (size_t gi = 0, g0 = 0; gi < group_end.size(); g0 = group_end[gi], gi++) {
-            max_group_tiles = std::max<uint64_t>(max_group_tiles, tile_start[group_end[gi]] - tile_start[g0]);
+            max_group_runs = std::max<uint64_t>(max_group_runs, first_slice[group_end[gi]] - first_slice[g0]);
             max_group_bytes = std::max<uint64_t>(max_group_bytes, h_offsets[group_end[gi]] - h_offsets[g0]);
             max_group_genomes = std::max<uint64_t>(max_group_genomes, group_end[gi] - g0);
         }
-        // workspace: bucket-major payload slots | overflow lists (one entry per FASTA byte at most) | counters
-        const size_t payload_bytes = align_up((size_t)max_group_tiles * PART_STAGE_ENTRIES * 2, 256);
+        const int nb = 1 << (2 * (kcount - PART_LOW_BASES));
+        // workspace: payload regions [run][bucket][cap sectors] | sectors written per (run, bucket) |
+        // overflow lists (one entry per FASTA byte at most) | ...
+        const size_t payload_bytes = align_up((size_t)max_group_runs * run_payload_bytes, 256);
+        const size_t nsec_bytes = align_up((size_t)max_group_runs * nb * 2, 256);
         const size_t ov_bytes = align_up((size_t)max_group_bytes * 4 + 64, 256);
         // ... | run-end tail lists (one entry per 64 FASTA bytes + 1024 per genome) | counters (overflow, tails)
         const size_t ovc_bytes = align_up((size_t)n_genomes * 8 + 8, 256);
         const size_t tl_bytes = align_up((size_t)((max_group_bytes >> 6) + 1024 * (max_group_genomes + 1)) * 8, 256);
-        rc = ws.part.ensure(payload_bytes + ov_bytes + tl_bytes + ovc_bytes);
+        rc = ws.part.ensure(payload_bytes + nsec_bytes + ov_bytes + tl_bytes + ovc_bytes);
         if (rc) return rc;
-        uint16_t* d_payload = (uint16_t*)ws.part.p;
-        uint32_t* d_overflow = (uint32_t*)((uint8_t*)ws.part.p + payload_bytes);
-        unsigned long long* d_tail_list = (unsigned long long*)((uint8_t*)ws.part.p + payload_bytes + ov_bytes);
-        unsigned int* d_ov_counts = (unsigned int*)((uint8_t*)ws.part.p + payload_bytes + ov_bytes + tl_bytes);
+        uint8_t* pw = (uint8_t*)ws.part.p;
+        void* d_payload = pw;
+        uint16_t* d_nsec = (uint16_t*)(pw + payload_bytes);
+        uint32_t* d_overflow = (uint32_t*)(pw + payload_bytes + nsec_bytes);
+        unsigned long long* d_tail_list = (unsigned long long*)(pw + payload_bytes + nsec_bytes + ov_bytes);
+        unsigned int* d_ov_counts = (unsigned int*)(pw + payload_bytes + nsec_bytes + ov_bytes + tl_bytes);
         unsigned int* d_tail_counts = d_ov_counts + n_genomes;
         unsigned int* d_tail_any = d_tail_counts + n_genomes;
         KM_CUDA(cudaMemsetAsync(d_ov_counts, 0, (size_t)n_genomes * 8 + 8, s));
@@ -414,15 +405,15 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
             const uint64_t batch_lo = h_offsets[g0];
             {
                 Prof pr(ctx, s, 4, nt > 0 ? 1 : 0);
-                rc = launch_partition(d_fasta, d_genomes, d_slices + first_slice[g0], nt, d_gtiles, kcount, kmin, min_rec,
-                                      lm, d_stats, d_payload, d_overflow, d_ov_counts, batch_lo, d_tail_list, d_tail_counts,
-                                      d_tail_any, (uint32_t)g0, s);
+                rc = launch_partition(d_fasta, d_genomes, d_slices + first_slice[g0], nt, part_tiles_per_slice, kcount,
+                                      kmin, min_rec, lm, d_stats, d_payload, d_nsec, d_overflow, d_ov_counts, batch_lo,
+                                      d_tail_list, d_tail_counts, d_tail_any, (uint32_t)g0, s);
             }
             if (rc) return rc;
             {
                 Prof pr(ctx, s, 5, 1);
-                rc = launch_bucket(lm, row, kcount, kmin, d_gtiles, d_payload, d_stats, canonical ? nullptr : d_freq,
-                                   freq_stride, d_totals, (uint32_t)g0, ng, s);
+                rc = launch_bucket(lm, row, kcount, kmin, d_gruns, part_tiles_per_slice, d_payload, d_nsec, d_stats,
+                                   canonical ? nullptr : d_freq, freq_stride, d_totals, (uint32_t)g0, ng, s);
             }
             if (rc) return rc;
             if (kcount > kmin) {

@@ -557,22 +557,26 @@ count8_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds
 // k = 9..12: the 4^k histogram (up to 64 MB) is too big for shared memory, and L2 atomics top out
 // near 190 G/s (measured) and thrash the L2 next to the streamed input, so the windows are first
 // partitioned by their leading k-7 bases into nb = 4^(k-7) buckets of 16384 bins:
-//   partition_kernel  one CTA per 16 KB tile: every window is placed with ONE returning shared
-//                     atomic into its bucket's fixed-size slot of a 64 KB staging buffer
-//                     (slot = 32768/nb uint16: entry 0 = fill count, then 14-bit payloads); the
-//                     slots are then written bucket-major: [genome][bucket][tile][slot]
-//   bucket_kernel     one CTA per (bucket, genome): STREAMS its n_tiles contiguous slots with
-//                     coalesced 128-bit loads into a 16384-bin shared histogram, then writes that
-//                     64 KB slice of the count row, its frequencies and the bucket's whole
-//                     cascade subtree (levels k .. k-7)
-//   overflow_kernel   the rare windows that found their slot full (slot = 2 x the mean fill;
-//                     skewed genomes) are kept as plain k-mer indices and added afterwards
+//   partition_kernel  one CTA per RUN of consecutive 16 KB tiles of one genome: every window is placed
+//                     with ONE returning shared atomic into its bucket's slot of a 64 KB staging buffer
+//                     (slot = 32768/nb uint16 14-bit payloads).  After every tile the FULL 32-byte
+//                     sectors (16 payloads) of every slot are appended to the bucket's region of this
+//                     run in HBM and the < 16 left-over payloads move to the front of the slot, so only
+//                     live payloads travel: 2 bytes per window plus one padded sector per (bucket, run).
+//                     Regions: [run][bucket][cap sectors], cap = 2 x the mean; sectors written per
+//                     (run, bucket) go to a small table the bucket kernel reads.
+//   bucket_kernel     one CTA per (bucket, genome): streams the regions of its bucket (coalesced 128-bit
+//                     loads, one warp per region) into a 16384-bin shared histogram, then writes that
+//                     64 KB slice of the count row, its frequencies and the bucket's whole cascade
+//                     subtree (levels k .. k-7)
+//   overflow_kernel   the rare windows that found their slot or region full (skewed genomes) are kept
+//                     as plain k-mer indices and added afterwards
 // Only shared-memory atomics (2.5 T/s measured on B200) sit on the hot path and every global
 // access is a full-sector vector stream.
 constexpr int PART_LOW = 7;
 constexpr int PART_BINS = 1 << (2 * PART_LOW);        // 16384 bins per bucket
 constexpr int PART_MAX_BUCKETS = 1024;                // k <= 12
-constexpr int STAGE_ENTRIES = 32768;                  // uint16 entries staged per tile = nb * slot
+constexpr int PART_SECTOR = 16;                       // payloads per 32-byte sector
 
 // Rare for a genome of mixed sequence: the slot is full.  Tandem repeats make it common (every window of a
 // tile falls into a handful of buckets), so the lanes that arrive together reserve their entries with one
@@ -587,59 +591,92 @@ __device__ __noinline__ void overflow_push(uint32_t* ov, unsigned int* ov_count,
     ov[base + __popc(act & ((1u << lane) - 1u))] = idx;
 }
 
-template <int SLOT_SHIFT>
+// Payload = the low 16 bits of the k-mer index: its 14 low-order bits (the bin inside the bucket) and, in bits
+// 15:14, the two low-order bits of the bucket number.  The partition kernel stores it unmasked (one integer
+// op less per window); the bucket kernel, which knows its bucket, clears the two bits with one XOR per pair of
+// payloads.  A padding payload carries (bucket & 3) ^ 1 there, so that after the XOR it reads
+// PART_BINS + spread: a dummy bin behind the histogram.
+__device__ __forceinline__ uint32_t payload_fix(uint32_t bucket) { return ((bucket & 3u) << 14) * 0x00010001u; }
+__device__ __forceinline__ uint32_t payload_pad(uint32_t bucket, uint32_t spread) {
+    return (((bucket & 3u) ^ 1u) << 14) | (spread & 255u);
+}
+
+// (a whole sector whose region is full: sixteen payloads straight from the staging buffer)
+__device__ __noinline__ void overflow_push_sector(uint32_t* ov, unsigned int* ov_count, uint32_t bucket,
+                                                  const uint16_t* src) {
+    for (int i = 0; i < PART_SECTOR; i++)
+        overflow_push(ov, ov_count, (bucket << (2 * PART_LOW)) | (src[i] & (uint32_t)(PART_BINS - 1)));
+}
+
+// Slot geometry per bucket count: nb = 4^(k-7) buckets share the staging buffer.  For k <= 11 a slot is
+// 32768 / nb payloads (twice the mean of a tile).  For k = 12 (1024 buckets, 16 payloads per tile on
+// average) a slot also has to hold up to 15 payloads left over from the tile before, so it is 48 entries
+// (96 KB of staging: two CTAs still share an SM): P(15 + Poisson(16) > 48) < 1e-4, whereas 32-entry slots
+// overflowed in 7 % of all (bucket, tile) pairs (measured: the overflow path took 15 ms per C2 step).
+template <int NB_SHIFT>
+struct PartGeom {
+    static constexpr uint32_t nb = 1u << NB_SHIFT;
+    static constexpr uint32_t slot_size = NB_SHIFT == 10 ? 48u : (32768u >> NB_SHIFT);
+    static constexpr uint32_t stage_entries = nb * slot_size;
+    static constexpr bool owned = NB_SHIFT == 10;              // flush: one thread owns a whole slot
+};
+
+template <int NB_SHIFT>
 struct SlotSink {
-    static constexpr uint32_t slot_shift = SLOT_SHIFT;         // log2(slot entries)
-    static constexpr uint32_t slot_cap = (1u << SLOT_SHIFT) - 1u;   // slot entries - 1 (a mask)
-    static constexpr uint32_t slot_size = 1u << SLOT_SHIFT;
-    // typed shared-memory pointers (not inline asm): the compiler can then keep several windows'
-    // atomics in flight before the first returned position is consumed
-    uint32_t* __restrict__ cnt;        // cnt[nb]
-    uint16_t* __restrict__ staged;     // staged[nb << slot_shift]
+    static constexpr bool raw_windows = true;                  // emit_clean passes unmasked funnel words
+    static constexpr uint32_t slot_size = PartGeom<NB_SHIFT>::slot_size;
+    static constexpr uint32_t b4_mask = (PartGeom<NB_SHIFT>::nb - 1u) << 2;
+    uint32_t cnt_s;                    // shared-window byte address of cnt[nb]
+    uint32_t staged_s;                 //                            ... of staged[nb * slot_size]
     uint32_t* ov;                      // this genome's overflow list
     unsigned int* ov_count;
+    uint32_t kmask;                    // 4^k - 1
     unsigned n;                        // windows seen by this thread (placed or overflowed)
-    __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
-        const uint32_t b = idx >> (2 * PART_LOW);
-        const uint32_t pos = atomicAdd(cnt + b, 1u);
-        n++;
-        if (pos < slot_size) {
-            // entry e of bucket b lives at position (e + 2b) mod slot: the order inside a slot is
-            // irrelevant, and the rotation spreads the random buckets over all 32 banks
-            const uint32_t phys = (pos + 2u * b) & slot_cap;
-            staged[(b << slot_shift) + phys] = (uint16_t)(idx & (PART_BINS - 1));
-        } else {
-            overflow_push(ov, ov_count, idx);
-        }
+    __device__ __forceinline__ uint32_t atom_inc(uint32_t b4) {
+        uint32_t old;
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt_s + b4) : "memory");
+        return old;
     }
-    // four windows: all four atomics are issued before the first returned position is needed
+    __device__ __forceinline__ void store16(uint32_t b4, uint32_t pos, uint32_t x) {
+        // entry (b, pos) at byte 2 * (b * slot + pos) = 2 * (b4 * (slot / 4) + pos): one IMAD, one add
+        const uint32_t e = b4 * (slot_size / 4u) + pos;
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(staged_s + 2u * e), "h"((unsigned short)x) : "memory");
+    }
+    // (generic byte walker: idx is masked)
+    __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
+        const uint32_t b4 = (idx >> (2 * PART_LOW - 2)) & b4_mask;
+        const uint32_t pos = atom_inc(b4);
+        n++;
+        if (pos < slot_size) store16(b4, pos, idx);
+        else overflow_push(ov, ov_count, idx);
+    }
     __device__ __forceinline__ void count4(uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3, uint64_t, uint64_t,
                                            uint64_t, uint64_t) {
-        const uint32_t idx[4] = {i0, i1, i2, i3};
-        place<4>(idx);
+        count(i0, 0); count(i1, 0); count(i2, 0); count(i3, 0);
     }
     __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t*) { place<8>(w, true); }
     __device__ __forceinline__ void count8_tail(const uint32_t* w, const uint64_t*, bool last) { place<8>(w, last); }
-    // `last_live` = false: the N-th window does not exist (a chunk of 31 bases); its atomic is skipped
-    // and its returned position reads as 0 with the store predicated off
+    // N unmasked windows: all atomics are issued before the first returned position is needed.
+    // `last_live` = false: the N-th window does not exist (a chunk of 31 bases).
     template <int N>
-    __device__ __forceinline__ void place(const uint32_t* idx, bool last_live = true) {
-        uint32_t b[N], pos[N], worst = 0;
+    __device__ __forceinline__ void place(const uint32_t* x, bool last_live = true) {
+        uint32_t b4[N], pos[N];
+        bool full = false;
 #pragma unroll
-        for (int u = 0; u < N; u++) b[u] = idx[u] >> (2 * PART_LOW);
+        for (int u = 0; u < N; u++) b4[u] = (x[u] >> (2 * PART_LOW - 2)) & b4_mask;
 #pragma unroll
-        for (int u = 0; u < N; u++) pos[u] = (u < N - 1 || last_live) ? atomicAdd(cnt + b[u], 1u) : 0u;
+        for (int u = 0; u < N; u++) pos[u] = (u < N - 1 || last_live) ? atom_inc(b4[u]) : 0u;
         n += last_live ? N : N - 1;
 #pragma unroll
         for (int u = 0; u < N; u++) {
-            worst = max(worst, pos[u]);
-            if (pos[u] < slot_size && (u < N - 1 || last_live))
-                staged[(b[u] << slot_shift) + ((pos[u] + 2u * b[u]) & slot_cap)] = (uint16_t)(idx[u] & (PART_BINS - 1));
+            const bool fits = pos[u] < slot_size;
+            full |= !fits;
+            if (fits && (u < N - 1 || last_live)) store16(b4[u], pos[u], x[u]);
         }
-        if (worst >= slot_size) {                                                // rare: some slot is full
+        if (full) {                                                              // rare: some slot is full
 #pragma unroll
             for (int u = 0; u < N; u++)
-                if (pos[u] >= slot_size) overflow_push(ov, ov_count, idx[u]);
+                if (pos[u] >= slot_size) overflow_push(ov, ov_count, x[u] & kmask);
         }
     }
 };
@@ -650,34 +687,66 @@ struct PartWalkSmem {                           // only live during the walk ...
     uint8_t clean[COUNT_THREADS];
 };
 
+template <int NB_SHIFT>
 struct PartSmem {
-    uint16_t staged[STAGE_ENTRIES];             // 64 KB: nb slots
-    uint32_t cnt[PART_MAX_BUCKETS];             // windows per bucket in this tile
+    uint16_t staged[PartGeom<NB_SHIFT>::stage_entries];    // 64 KB (96 KB for k = 12): nb slots
+    uint32_t cnt[PART_MAX_BUCKETS];             // payloads in the slot (beyond the slot size: they overflowed)
+    uint16_t written[PART_MAX_BUCKETS];         // sectors of this run already appended to the bucket's region
     PartWalkSmem walk;
     unsigned long long carry[2];
     uint32_t prev_tile[2];
     unsigned long long sh_total;
 };
-static_assert(sizeof(PartSmem) <= 74 * 1024, "three partition CTAs must fit in one SM's shared memory");
+static_assert(sizeof(PartSmem<10>) <= 113 * 1024, "two partition CTAs must fit in one SM's shared memory");
 
-struct GenomeTiles {                   // tiles of one genome inside the group's tile list
-    uint32_t tile0, n_tiles;
+struct GenomeRuns {                    // runs (= partition CTAs) of one genome inside the group's run list
+    uint32_t run0, n_runs;
 };
 
-template <int SLOT_SHIFT>
+// k = 12, rare: the slot ran over, or the bucket's region is about to: sector by sector, with every check.
+template <int NB_SHIFT>
+__device__ __noinline__ void flush_slot_slow(PartSmem<NB_SHIFT>& sm, uint32_t b, uint4* region, uint32_t cap,
+                                             uint32_t* ov, unsigned int* ov_count) {
+    constexpr uint32_t slot_size = PartGeom<NB_SHIFT>::slot_size;
+    const uint32_t c = min(sm.cnt[b], slot_size);
+    const uint32_t nfull = c / PART_SECTOR, left = c % PART_SECTOR;
+    uint16_t* slot16 = sm.staged + (size_t)b * slot_size;
+    uint4* slot = reinterpret_cast<uint4*>(slot16);
+    uint32_t wr = sm.written[b];
+    for (uint32_t q = 0; q < nfull; q++) {
+        if (wr < cap) {
+            region[((size_t)b * cap + wr) * 2] = slot[2 * q];
+            region[((size_t)b * cap + wr) * 2 + 1] = slot[2 * q + 1];
+            wr++;
+        } else {
+            overflow_push_sector(ov, ov_count, b, slot16 + q * PART_SECTOR);
+        }
+    }
+    if (nfull && left) {
+        const uint4 a = slot[2 * nfull], d = slot[2 * nfull + 1];
+        slot[0] = a;
+        slot[1] = d;
+    }
+    sm.written[b] = (uint16_t)wr;
+    sm.cnt[b] = left;
+}
+
+template <int NB_SHIFT>
 __global__ void __launch_bounds__(COUNT_THREADS, 2)
 partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
-                 const Slice* __restrict__ tiles, const GenomeTiles* __restrict__ gts, DenseParams P, LevelMap lm,
-                 GenomeStats* stats, uint16_t* __restrict__ payload, uint32_t* __restrict__ overflow,
-                 unsigned int* __restrict__ ov_counts, uint64_t batch_lo, TailList tl, int k_stop) {
-    constexpr int slot_shift = SLOT_SHIFT;
-    constexpr int nb = STAGE_ENTRIES >> SLOT_SHIFT;
+                 const Slice* __restrict__ runs, DenseParams P, LevelMap lm,
+                 GenomeStats* stats, uint4* __restrict__ payload, uint16_t* __restrict__ nsec, uint32_t cap,
+                 uint32_t* __restrict__ overflow, unsigned int* __restrict__ ov_counts, uint64_t batch_lo,
+                 TailList tl, int k_stop) {
+    using G = PartGeom<NB_SHIFT>;
+    constexpr uint32_t slot_size = G::slot_size;
+    constexpr uint32_t nb = G::nb;
+    constexpr uint32_t VPB = slot_size / 8;                                 // uint4 vectors per slot
     extern __shared__ __align__(16) unsigned char part_smem_raw[];
-    PartSmem& sm = *reinterpret_cast<PartSmem*>(part_smem_raw);
+    PartSmem<NB_SHIFT>& sm = *reinterpret_cast<PartSmem<NB_SHIFT>*>(part_smem_raw);
     const int tid = threadIdx.x;
-    const Slice sl = tiles[blockIdx.x];
+    const Slice sl = runs[blockIdx.x];
     const GenomeDev gd = gds[sl.genome];
-    const GenomeTiles gt = gts[sl.genome];
     Genome g;
     g.b = buf;
     g.lo = gd.lo;
@@ -685,60 +754,119 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
     TileCtx tc;
     tc.flags = sm.walk.flags; tc.clean = sm.walk.clean; tc.last16 = sm.walk.last16;
     tc.carry = sm.carry; tc.prev_tile = sm.prev_tile;
-    for (int i = tid; i < nb; i += COUNT_THREADS) sm.cnt[i] = 0;
+    for (uint32_t i = tid; i < nb; i += COUNT_THREADS) { sm.cnt[i] = 0; sm.written[i] = 0; }
     if (tid == 0) sm.sh_total = 0;
 
-    SlotSink<SLOT_SHIFT> sink;
-    sink.cnt = sm.cnt;
-    sink.staged = sm.staged;
+    SlotSink<NB_SHIFT> sink;
+    sink.cnt_s = (uint32_t)__cvta_generic_to_shared(sm.cnt);
+    sink.staged_s = (uint32_t)__cvta_generic_to_shared(sm.staged);
     sink.ov = overflow + (gd.file_lo - batch_lo);      // one possible window per byte of the genome
     sink.ov_count = ov_counts + sl.genome;
+    sink.kmask = P.mask;
     sink.n = 0;
     ListTails tails;
     tails.lm = &lm; tails.st = stats + sl.genome; tails.genome = sl.genome; tails.k_stop = k_stop;
     tails.list = tail_list_of(tl, gd, sl.genome, &tails.cap);
     tails.count = tl.counts + sl.genome;
     tails.any_full = tl.any_full;
-    // a slice is a run of consecutive tiles of one genome: the CTA walks them one after the other,
-    // and after each tile writes its 64 KB of slots bucket-major: slot (b, t) of this genome at
-    // ((b * n_tiles + t) << slot_shift)
-    constexpr int vec_shift = slot_shift - 3;                               // uint4 vectors per slot
-    uint16_t* pg = payload + (size_t)gt.tile0 * STAGE_ENTRIES;
-    const uint32_t b0 = (uint32_t)tid >> vec_shift, o = (uint32_t)tid & ((1u << vec_shift) - 1u);
-    const size_t stride = (((size_t)(COUNT_THREADS >> vec_shift) * gt.n_tiles) << slot_shift) / 8;
-    // Unused slot entries hold a padding value >= PART_BINS that the bucket kernel counts into a dummy
-    // bin, so it needs neither fill counts nor validity tests.  The padding of (tile t, vector o of the
-    // slot, entry e) is PART_BINS + ((t * vectors_per_slot + o) & 31) + 32 e: the 32 lanes of a bucket-
-    // kernel warp read 32 consecutive vectors, and for every e their dummy bins fall into 32 banks.
-    auto padding = [&](uint32_t t_local) -> uint4 {
-        const uint32_t L = ((t_local << vec_shift) + o) & 31u;
-        const uint32_t w0 = ((uint32_t)PART_BINS | ((uint32_t)(PART_BINS + 32) << 16)) + L * 0x00010001u;
-        return make_uint4(w0, w0 + 0x00400040u, w0 + 0x00800080u, w0 + 0x00C000C0u);
-    };
-    {
-        const uint4 pad = padding(sl.tile0 - gt.tile0);
-        uint4* st = reinterpret_cast<uint4*>(sm.staged);
-#pragma unroll
-        for (int j = 0; j < STAGE_ENTRIES / 8 / COUNT_THREADS; j++) st[tid + j * COUNT_THREADS] = pad;
-        // (walk_slice starts with a __syncthreads)
-    }
-    walk_slice<false>(buf, g, sl, P, sink, tails, tc, [&](uint32_t tile_no) {
+    // this run's regions: bucket b at [(run * nb + b) * cap, ... + cap) sectors (two uint4 each);
+    // nb * cap * 2 <= 2^18 vectors per run, so offsets inside a run fit 32 bits
+    uint4* const region = payload + (size_t)blockIdx.x * nb * cap * 2;
+    // (walk_slice starts with a __syncthreads)
+    walk_slice<false>(buf, g, sl, P, sink, tails, tc, [&](uint32_t) {
         // (the walk of the tile ended with a __syncthreads; the next tile's placements start after
-        // another one.)  Vector v = tid + 512 j belongs to bucket (tid >> vec_shift) + (512 >> vec_shift) j:
-        // the destination advances by a constant stride, one add per 128-bit store.  Each vector is
-        // replaced by the next tile's padding as soon as it has been read.
-        if (tid < nb / 4) reinterpret_cast<uint4*>(sm.cnt)[tid] = make_uint4(0, 0, 0, 0);    // nb <= 1024 counters
-        const uint32_t t_local = sl.tile0 + tile_no - gt.tile0;
-        const uint4 pad = padding(t_local + 1);
+        // another one.)  Full sectors go to the bucket's region, the sector with the left-over payloads
+        // moves to the front of the slot.
         uint4* st = reinterpret_cast<uint4*>(sm.staged);
-        uint4* dst = reinterpret_cast<uint4*>(pg + (((size_t)b0 * gt.n_tiles + t_local) << slot_shift)) + o;
+        if (G::owned) {
+            // k = 12: thread t owns slots t and t + 512 (six vectors each).  Nearly always the slot holds
+            // 16..31 payloads: one sector out, the second one to the front.
 #pragma unroll
-        for (int j = 0; j < STAGE_ENTRIES / 8 / COUNT_THREADS; j++) {
-            const uint4 x = st[tid + j * COUNT_THREADS];
-            st[tid + j * COUNT_THREADS] = pad;
-            dst[j * stride] = x;
+            for (int h = 0; h < 2; h++) {
+                const uint32_t b = (uint32_t)tid + h * COUNT_THREADS;
+                const uint32_t c = sm.cnt[b];
+                if (c < PART_SECTOR) continue;
+                const uint32_t wr = sm.written[b];
+                if (c > slot_size || wr + 3u > cap) {
+                    flush_slot_slow<NB_SHIFT>(sm, b, region, cap, sink.ov, sink.ov_count);
+                    continue;
+                }
+                uint4* slot = st + b * VPB;
+                uint4* dst = region + (b * cap + wr) * 2u;
+                dst[0] = slot[0];
+                dst[1] = slot[1];
+                uint32_t mv = 2;                                   // vectors 2, 3 hold the left-over payloads ...
+                if (c >= 2 * PART_SECTOR) {
+                    dst[2] = slot[2];
+                    dst[3] = slot[3];
+                    mv = 4;                                        // ... or 4, 5 ...
+                    if (c == 3 * PART_SECTOR) {
+                        dst[4] = slot[4];
+                        dst[5] = slot[5];
+                        mv = 0;                                    // ... or nothing is left
+                    }
+                }
+                const uint4 m0 = slot[mv], m1 = slot[mv + 1];
+                slot[0] = m0;
+                slot[1] = m1;
+                sm.written[b] = (uint16_t)(wr + c / PART_SECTOR);
+                sm.cnt[b] = c % PART_SECTOR;
+            }
+        } else {
+            // k <= 11: vector v of the staging buffer belongs to bucket v / VPB; the lanes that hold one
+            // bucket's vectors sit in one warp (nb = 256) or in one round of the CTA
+#pragma unroll
+            for (int j = 0; j < (int)(G::stage_entries / 8 / COUNT_THREADS); j++) {
+                const uint32_t v = (uint32_t)tid + j * COUNT_THREADS;
+                const uint32_t b = v / VPB, jv = v % VPB, q = jv >> 1;
+                const uint32_t c = min(sm.cnt[b], slot_size);
+                const uint32_t nfull = c / PART_SECTOR;
+                const uint32_t wr = sm.written[b];
+                const uint4 x = st[v];
+                if (VPB <= 32) __syncwarp(); else __syncthreads();
+                if (q < nfull) {
+                    const uint32_t sec = wr + q;
+                    if (sec < cap) region[(b * cap + sec) * 2u + (jv & 1u)] = x;
+                    else if (!(jv & 1u)) overflow_push_sector(sink.ov, sink.ov_count, b, sm.staged + b * slot_size + q * PART_SECTOR);
+                }
+                if (VPB <= 32) __syncwarp(); else __syncthreads();     // (the overflow path reads the slot)
+                if (q == nfull && nfull && (c % PART_SECTOR)) st[b * VPB + (jv & 1u)] = x;
+                if (jv == 0) {
+                    sm.cnt[b] = c % PART_SECTOR;
+                    sm.written[b] = (uint16_t)min(wr + nfull, cap);
+                }
+            }
         }
     });
+    __syncthreads();
+    // end of the run: the left-over payloads of every slot, padded to one sector with dummy bins
+    for (uint32_t b = tid; b < nb; b += COUNT_THREADS) {
+        const uint32_t left = sm.cnt[b];
+        uint32_t wr = sm.written[b];
+        if (left) {
+            uint32_t e[PART_SECTOR / 2];
+            const uint16_t* src16 = sm.staged + (size_t)b * slot_size;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(src16);
+            if (wr < cap) {
+#pragma unroll
+                for (int i = 0; i < PART_SECTOR / 2; i++) {
+                    uint32_t w = src[i];
+                    const uint32_t pad = payload_pad(b, b * 16u + 2u * i);
+                    if (2u * i >= left) w = (w & 0xFFFF0000u) | pad;
+                    if (2u * i + 1u >= left) w = (w & 0x0000FFFFu) | ((pad ^ 1u) << 16);
+                    e[i] = w;
+                }
+                uint4* dst = region + (b * cap + wr) * 2u;
+                dst[0] = make_uint4(e[0], e[1], e[2], e[3]);
+                dst[1] = make_uint4(e[4], e[5], e[6], e[7]);
+                wr++;
+            } else {
+                for (uint32_t i = 0; i < left; i++)
+                    overflow_push(sink.ov, sink.ov_count, (b << (2 * PART_LOW)) | (src16[i] & (uint32_t)(PART_BINS - 1)));
+            }
+        }
+        nsec[(size_t)blockIdx.x * nb + b] = (uint16_t)wr;
+    }
     const unsigned long long total = block_sum_u32(sink.n, &sm.sh_total);
     if (tid == 0 && total) atomicAdd(&stats[sl.genome].total_top, total);
 }
@@ -749,8 +877,10 @@ struct LevelInfo {                     // per level: index into the caller's k_l
 
 constexpr int BUCKET_THREADS = 512;
 
+constexpr int BUCKET_NS_CHUNK = 1024;      // runs whose sector counts are staged at a time
 struct BucketSmem {
     uint32_t hist[PART_BINS + 256];    // 64 KB (reused in place by the in-bucket cascade) + the padding's dummy bins
+    uint16_t ns[BUCKET_NS_CHUNK];      // sectors in this bucket's region of every run of the genome
     unsigned long long tot[16];
     uint32_t* lvl_counts[16];          // per level: this bucket's slice of the count row
     float* lvl_freq[16];               //            ... of the frequency row (nullptr: not requested)
@@ -760,8 +890,8 @@ static_assert(sizeof(BucketSmem) <= 74 * 1024, "three bucket CTAs must fit in on
 
 // 8 payload entries of one 128-bit vector: live ones are bins of the bucket, padding goes to the
 // dummy bins behind them (see partition_kernel).
-__device__ __forceinline__ void hist_add8(uint32_t hbase, const uint4& x) {
-    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+__device__ __forceinline__ void hist_add8(uint32_t hbase, const uint4& x, uint32_t fix) {
+    const uint32_t w[4] = {x.x ^ fix, x.y ^ fix, x.z ^ fix, x.w ^ fix};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase + ((w[i] & 0xFFFFu) << 2)) : "memory");
@@ -770,16 +900,17 @@ __device__ __forceinline__ void hist_add8(uint32_t hbase, const uint4& x) {
 }
 
 __global__ void __launch_bounds__(BUCKET_THREADS, 3)
-bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const GenomeTiles* __restrict__ gts,
-              const uint16_t* __restrict__ payload, int slot_shift,
+bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const GenomeRuns* __restrict__ grs,
+              const uint4* __restrict__ payload, const uint16_t* __restrict__ nsec, uint32_t cap,
               const GenomeStats* __restrict__ stats, float* freq, uint64_t freq_stride, uint64_t* totals,
               uint32_t genome0) {
     extern __shared__ __align__(16) unsigned char bucket_smem_raw[];
     BucketSmem& sm = *reinterpret_cast<BucketSmem*>(bucket_smem_raw);
     const int tid = threadIdx.x;
     const uint32_t b = blockIdx.x;
+    const uint32_t nb = gridDim.x;
     const uint32_t g = genome0 + blockIdx.y;
-    const GenomeTiles gt = gts[g];
+    const GenomeRuns gr = grs[g];
     if (tid < row.nk) {
         const int j = row.k[tid];
         unsigned long long t = stats[g].total_top;
@@ -809,37 +940,57 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
     constexpr int PER1 = PART_BINS / 4 / BUCKET_THREADS;          // 8 level-(k-1) bins per thread
     constexpr int PER2 = PART_BINS / 16 / BUCKET_THREADS;         // 2 level-(k-2) bins per thread
     // (run-end tails of these levels are added afterwards from the genome's tail list)
-    // stream this bucket's slots: n_tiles * slot entries, contiguous, 128-bit coalesced loads
+    // stream this bucket's regions: run r of the genome holds ns[r] sectors at
+    // payload[((run0 + r) * nb + b) * cap ...]; one warp per region, 128-bit coalesced loads
     const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sm.hist);
-    const uint16_t* bp = payload + (size_t)gt.tile0 * STAGE_ENTRIES + (((size_t)b * gt.n_tiles) << slot_shift);
-    const uint4* bp4 = reinterpret_cast<const uint4*>(bp);
-    const int vec_shift = slot_shift - 3;
-    const uint64_t n_vec = (uint64_t)gt.n_tiles << vec_shift;
-    // Software pipeline: round r + 1 is in flight while round r goes into the histogram (round 0 is
-    // issued before the histogram is cleared).
-    constexpr int UNROLL = 4;
-    const uint32_t n_rounds = (uint32_t)((n_vec + (uint64_t)BUCKET_THREADS * UNROLL - 1) / ((uint64_t)BUCKET_THREADS * UNROLL));
-    auto load_round = [&](uint32_t r, uint4* x) {
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            const uint64_t v = (uint64_t)r * (BUCKET_THREADS * UNROLL) + (uint64_t)u * BUCKET_THREADS + tid;
-            // (beyond the end: eight times dummy bin 0)
-            x[u] = v < n_vec ? __ldg(bp4 + v) : make_uint4(0x40004000u, 0x40004000u, 0x40004000u, 0x40004000u);
-        }
-    };
-    uint4 x[UNROLL], xn[UNROLL];
-    if (n_rounds) load_round(0, x);
+    const uint32_t fix = payload_fix(b);
     {
         uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
-        for (int i = tid; i < PART_BINS / 4; i += BUCKET_THREADS) h4[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < (PART_BINS + 256) / 4; i += BUCKET_THREADS) h4[i] = make_uint4(0, 0, 0, 0);
     }
-    __syncthreads();
-    for (uint32_t r = 0; r < n_rounds; r++) {
-        if (r + 1 < n_rounds) load_round(r + 1, xn);
+    constexpr int UNROLL = 4;
+    constexpr int NWARP = BUCKET_THREADS / 32;
+    const int lane = tid & 31, wid = tid >> 5;
+    const size_t run_stride = (size_t)nb * cap * 2;                       // uint4 per run
+    for (uint32_t rb = 0; rb < gr.n_runs; rb += BUCKET_NS_CHUNK) {
+        const uint32_t nr = min(gr.n_runs - rb, (uint32_t)BUCKET_NS_CHUNK);
+        __syncthreads();                                                  // histogram cleared / previous chunk consumed
+        for (uint32_t i = tid; i < nr; i += BUCKET_THREADS)
+            sm.ns[i] = __ldg(nsec + (size_t)(gr.run0 + rb + i) * nb + b);
+        __syncthreads();
+        const uint4* base = payload + ((size_t)(gr.run0 + rb) * nb + b) * cap * 2;
+        // rounds of this warp: (run r, chunk c) = vectors [c * 32 * UNROLL, ...) of run r's region
+        auto valid = [&](uint32_t r, uint32_t c) -> bool { return r < nr && c * (32u * UNROLL) < 2u * sm.ns[r]; };
+        auto next = [&](uint32_t& r, uint32_t& c) {
+            c++;
+            while (r < nr && !valid(r, c)) { r += NWARP; c = 0; }
+        };
+        auto load = [&](uint32_t r, uint32_t c, uint4* x) {
+            const uint32_t nv = 2u * sm.ns[r];
+            const uint4* p = base + (size_t)r * run_stride;
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) hist_add8(hbase, x[u]);
+            for (int u = 0; u < UNROLL; u++) {
+                const uint32_t v = c * (32u * UNROLL) + u * 32u + lane;
+                if (v < nv) x[u] = __ldg(p + v);
+            }
+        };
+        auto add = [&](uint32_t r, uint32_t c, const uint4* x) {
+            const uint32_t nv = 2u * sm.ns[r];
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) x[u] = xn[u];
+            for (int u = 0; u < UNROLL; u++) {
+                const uint32_t v = c * (32u * UNROLL) + u * 32u + lane;
+                if (v < nv) hist_add8(hbase, x[u], fix);
+            }
+        };
+        // (no register look-ahead: 48 warps per SM with four 128-bit loads each in flight cover the latency)
+        uint4 x[UNROLL];
+        uint32_t r = wid, c = 0;
+        while (r < nr && !valid(r, c)) r += NWARP;
+        while (r < nr) {
+            load(r, c, x);
+            add(r, c, x);
+            next(r, c);
+        }
     }
     __syncthreads();
     // level k: this bucket's 16384 bins, and level k-1 on the way (kept in registers)
@@ -1219,10 +1370,10 @@ int dense_setup_attributes() {
     KM_CUDA(cudaFuncSetAttribute(count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (1 << (2 * SMEM_MAX_K)) * 4));
     KM_CUDA(cudaFuncSetAttribute(count8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
-    KM_CUDA(cudaFuncSetAttribute(partition_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
-    KM_CUDA(cudaFuncSetAttribute(partition_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
-    KM_CUDA(cudaFuncSetAttribute(partition_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
-    KM_CUDA(cudaFuncSetAttribute(partition_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
+    KM_CUDA(cudaFuncSetAttribute(partition_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem<10>)));
+    KM_CUDA(cudaFuncSetAttribute(partition_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem<8>)));
+    KM_CUDA(cudaFuncSetAttribute(partition_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem<6>)));
+    KM_CUDA(cudaFuncSetAttribute(partition_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem<4>)));
     KM_CUDA(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
     return KMERML_OK;
 }
@@ -1272,30 +1423,33 @@ int launch_count(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice
     return KMERML_OK;
 }
 
-int part_slot_shift(int k) {                  // log2 of the slot size: 32768 / 4^(k-7) entries
-    return 15 - 2 * (k - PART_LOW);
+// Sectors one (run, bucket) region can hold: twice the mean of a run of `tiles_per_run` tiles.
+uint32_t part_region_cap(int k, int tiles_per_run) {
+    const uint32_t nb = 1u << (2 * (k - PART_LOW));
+    return (uint32_t)tiles_per_run * (2u * TILE_BYTES / PART_SECTOR) / nb;
 }
 
-int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles,
-                     const void* d_genome_tiles, int k, int k_bottom, int min_rec, const LevelMap& lm,
-                     GenomeStats* d_stats, uint16_t* d_payload, uint32_t* d_overflow, unsigned int* d_ov_counts,
-                     uint64_t batch_lo, unsigned long long* d_tail_list, unsigned int* d_tail_counts, unsigned int* d_tail_any,
-                     uint32_t genome0, cudaStream_t s) {
-    if (n_tiles <= 0) return KMERML_OK;
+int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_runs, int n_runs,
+                     int tiles_per_run, int k, int k_bottom, int min_rec, const LevelMap& lm,
+                     GenomeStats* d_stats, void* d_payload, uint16_t* d_nsec, uint32_t* d_overflow,
+                     unsigned int* d_ov_counts, uint64_t batch_lo, unsigned long long* d_tail_list,
+                     unsigned int* d_tail_counts, unsigned int* d_tail_any, uint32_t genome0, cudaStream_t s) {
+    if (n_runs <= 0) return KMERML_OK;
     DenseParams P = make_params(k, min_rec, k > k_bottom, k_bottom);
     const int k_stop = std::max(k - PART_LOW, k_bottom);
+    const uint32_t cap = part_region_cap(k, tiles_per_run);
     TailList tl;
     tl.list = d_tail_list; tl.counts = d_tail_counts; tl.batch_lo = batch_lo; tl.genome0 = genome0;
     tl.any_full = d_tail_any;
-#define KM_LAUNCH_PART(SH)                                                                            \
-    partition_kernel<SH><<<n_tiles, COUNT_THREADS, sizeof(PartSmem), s>>>(                             \
-        d_fasta, d_genomes, d_tiles, (const GenomeTiles*)d_genome_tiles, P, lm, d_stats, d_payload, d_overflow, \
+#define KM_LAUNCH_PART(NBS)                                                                           \
+    partition_kernel<NBS><<<n_runs, COUNT_THREADS, sizeof(PartSmem<NBS>), s>>>(                       \
+        d_fasta, d_genomes, d_runs, P, lm, d_stats, (uint4*)d_payload, d_nsec, cap, d_overflow,       \
         d_ov_counts, batch_lo, tl, k_stop)
-    switch (part_slot_shift(k)) {
-        case 5: KM_LAUNCH_PART(5); break;        // k = 12
-        case 7: KM_LAUNCH_PART(7); break;        // k = 11
-        case 9: KM_LAUNCH_PART(9); break;        // k = 10
-        default: KM_LAUNCH_PART(11); break;      // k = 9
+    switch (2 * (k - PART_LOW)) {                // log2(buckets)
+        case 10: KM_LAUNCH_PART(10); break;      // k = 12
+        case 8: KM_LAUNCH_PART(8); break;        // k = 11
+        case 6: KM_LAUNCH_PART(6); break;        // k = 10
+        default: KM_LAUNCH_PART(4); break;       // k = 9
     }
 #undef KM_LAUNCH_PART
     KM_CUDA(cudaGetLastError());
@@ -1312,18 +1466,20 @@ static LevelInfo make_level_info(const RowSpec& row) {
     return li;
 }
 
-int launch_bucket(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, const void* d_genome_tiles,
-                  const uint16_t* d_payload, const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride,
-                  uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s) {
+int launch_bucket(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, const void* d_genome_runs,
+                  int tiles_per_run, const void* d_payload, const uint16_t* d_nsec, const GenomeStats* d_stats,
+                  float* d_freq, uint64_t freq_stride, uint64_t* d_totals, uint32_t genome0, int n_genomes,
+                  cudaStream_t s) {
     if (n_genomes <= 0) return KMERML_OK;
     const int nb = 1 << (2 * (k - PART_LOW));
     const LevelInfo li = make_level_info(row);
     const int k_stop = std::max(k - PART_LOW, k_bottom);
+    const uint32_t cap = part_region_cap(k, tiles_per_run);
     for (int h0 = 0; h0 < n_genomes; h0 += 32768) {           // gridDim.y <= 65535
         dim3 grid((unsigned)nb, (unsigned)std::min(32768, n_genomes - h0));
         bucket_kernel<<<grid, BUCKET_THREADS, sizeof(BucketSmem), s>>>(lm, row, li, k, k_stop,
-            (const GenomeTiles*)d_genome_tiles, d_payload, part_slot_shift(k), d_stats, d_freq, freq_stride, d_totals,
-            genome0 + (uint32_t)h0);
+            (const GenomeRuns*)d_genome_runs, (const uint4*)d_payload, d_nsec, cap, d_stats, d_freq, freq_stride,
+            d_totals, genome0 + (uint32_t)h0);
         KM_CUDA(cudaGetLastError());
     }
     return KMERML_OK;

@@ -25,6 +25,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <type_traits>
+
 #if defined(__CUDACC__)
 #define KM_HD __host__ __device__ __forceinline__
 #define KM_HD_NOINLINE static __host__ __device__ __noinline__
@@ -376,11 +378,18 @@ KM_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int s) {                 // bi
 #endif
 }
 
+// A sink that declares `static constexpr bool raw_windows = true` receives the windows of a clean chunk
+// UNMASKED (the k-mer in the low 2k bits, earlier bases above it) and masks what it needs itself.
+template <class S, class = void>
+struct sink_raw_windows : std::false_type {};
+template <class S>
+struct sink_raw_windows<S, std::void_t<decltype(S::raw_windows)>> : std::integral_constant<bool, S::raw_windows> {};
+
 // Every window that ends in a clean chunk whose predecessor chunk is clean too:
 // carry16 = the predecessor's last 16 bases (k <= 16).  Two integer ops per window.
 template <class Sink>
 KM_HD void emit_clean(const CleanChunk& c, uint32_t carry16, uint64_t cs, const DenseParams& P, Sink& sink) {
-    const uint32_t mask = P.mask;
+    const uint32_t mask = sink_raw_windows<Sink>::value ? 0xFFFFFFFFu : P.mask;
     auto window = [&](int j) -> uint32_t {
         const int sft = 62 - 2 * j;                                        // bit position of base j in hi:lo
         return (sft >= 32 ? funnel_r(c.hi, carry16, sft - 32) : funnel_r(c.lo, c.hi, sft)) & mask;

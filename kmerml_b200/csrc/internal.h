@@ -87,20 +87,22 @@ int launch_finalize(const LevelMap& lm, const RowSpec& row, int k_top, bool cano
                     uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s);
 // partition path (k = 9..12)
 constexpr int PART_MIN_K = 9, PART_MAX_K = 12, PART_LOW_BASES = 7;
-constexpr int PART_STAGE_ENTRIES = 32768;               // uint16 payload entries written per tile (64 KB)
-constexpr int PART_MAX_TILES_PER_SLICE = 32;            // consecutive tiles one partition CTA walks, at most
-int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles,
-                     const void* d_genome_tiles, int k, int k_bottom, int min_rec, const LevelMap& lm,
-                     GenomeStats* d_stats, uint16_t* d_payload, uint32_t* d_overflow, unsigned int* d_ov_counts,
-                     uint64_t batch_lo, unsigned long long* d_tail_list, unsigned int* d_tail_counts,
-                     unsigned int* d_tail_any, uint32_t genome0, cudaStream_t s);
+constexpr int PART_STAGE_ENTRIES = 32768;               // uint16 payload entries staged per partition CTA (64 KB)
+constexpr int PART_MAX_TILES_PER_RUN = 64;              // consecutive tiles one partition CTA walks, at most
+uint32_t part_region_cap(int k, int tiles_per_run);     // 32-byte sectors per (run, bucket) region
+int launch_partition(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_runs, int n_runs,
+                     int tiles_per_run, int k, int k_bottom, int min_rec, const LevelMap& lm,
+                     GenomeStats* d_stats, void* d_payload, uint16_t* d_nsec, uint32_t* d_overflow,
+                     unsigned int* d_ov_counts, uint64_t batch_lo, unsigned long long* d_tail_list,
+                     unsigned int* d_tail_counts, unsigned int* d_tail_any, uint32_t genome0, cudaStream_t s);
 int launch_tails(const uint8_t* d_fasta, const LevelMap& lm, const RowSpec& row, int k, int k_bottom, int min_rec,
                  const GenomeDev* d_genomes, const Slice* d_tiles, int n_tiles, unsigned long long* d_tail_list,
                  unsigned int* d_tail_counts, unsigned int* d_tail_any, uint64_t batch_lo, const GenomeStats* d_stats,
                  float* d_freq, uint64_t freq_stride, uint32_t genome0, int n_genomes, cudaStream_t s);
-int launch_bucket(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, const void* d_genome_tiles,
-                  const uint16_t* d_payload, const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride,
-                  uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s);
+int launch_bucket(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, const void* d_genome_runs,
+                  int tiles_per_run, const void* d_payload, const uint16_t* d_nsec, const GenomeStats* d_stats,
+                  float* d_freq, uint64_t freq_stride, uint64_t* d_totals, uint32_t genome0, int n_genomes,
+                  cudaStream_t s);
 int launch_overflow(const LevelMap& lm, const RowSpec& row, int k, int k_bottom, const GenomeDev* d_genomes,
                     const uint32_t* d_overflow, const unsigned int* d_ov_counts, uint64_t batch_lo,
                     const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride, uint32_t genome0, int n_genomes,
