@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkmerml_b200.so")
+LIB_PATH = os.environ.get("KMERML_LIB") or os.path.join(_HERE, "libkmerml_b200.so")    # KMERML_LIB: A/B builds
 
 OK = 0
 FLAG_CANONICAL = 1

@@ -256,6 +256,10 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     while (part_tiles_per_slice < PART_MAX_TILES_PER_RUN &&
            total_bytes / TILE_BYTES / (2ull * part_tiles_per_slice) >= (uint64_t)ctx->sm_count * 8)
         part_tiles_per_slice *= 2;
+    if (const char* e = getenv("KMERML_TILES_PER_RUN")) {      // profiling hook: the run length of a big batch on a small one
+        const int v = atoi(e);
+        if (v >= 1 && v <= PART_MAX_TILES_PER_RUN) part_tiles_per_slice = v;
+    }
     std::vector<uint64_t> slice_bytes(n_genomes);
     std::vector<uint32_t> first_slice(n_genomes + 1);
     uint64_t n_slices = 0;

@@ -703,6 +703,12 @@ struct GenomeRuns {                    // runs (= partition CTAs) of one genome 
     uint32_t run0, n_runs;
 };
 
+// One 32-byte sector with one 256-bit store (sm_100: STG.256; a lane writes a whole sector).
+__device__ __forceinline__ void store_sector(uint4* dst, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z),
+                 "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
 // k = 12, rare: the slot ran over, or the bucket's region is about to: sector by sector, with every check.
 template <int NB_SHIFT>
 __device__ __noinline__ void flush_slot_slow(PartSmem<NB_SHIFT>& sm, uint32_t b, uint4* region, uint32_t cap,
@@ -793,16 +799,13 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
                 }
                 uint4* slot = st + b * VPB;
                 uint4* dst = region + (b * cap + wr) * 2u;
-                dst[0] = slot[0];
-                dst[1] = slot[1];
+                store_sector(dst, slot[0], slot[1]);
                 uint32_t mv = 2;                                   // vectors 2, 3 hold the left-over payloads ...
                 if (c >= 2 * PART_SECTOR) {
-                    dst[2] = slot[2];
-                    dst[3] = slot[3];
+                    store_sector(dst + 2, slot[2], slot[3]);
                     mv = 4;                                        // ... or 4, 5 ...
                     if (c == 3 * PART_SECTOR) {
-                        dst[4] = slot[4];
-                        dst[5] = slot[5];
+                        store_sector(dst + 4, slot[4], slot[5]);
                         mv = 0;                                    // ... or nothing is left
                     }
                 }
@@ -878,6 +881,9 @@ struct LevelInfo {                     // per level: index into the caller's k_l
 constexpr int BUCKET_THREADS = 512;
 
 constexpr int BUCKET_NS_CHUNK = 1024;      // runs whose sector counts are staged at a time
+#ifndef KM_BUCKET_BULK_STORE
+#define KM_BUCKET_BULK_STORE 1           // 1: the level-k count slice leaves as one shared -> global bulk copy
+#endif
 struct BucketSmem {
     uint32_t hist[PART_BINS + 256];    // 64 KB (reused in place by the in-bucket cascade) + the padding's dummy bins
     uint16_t ns[BUCKET_NS_CHUNK];      // sectors in this bucket's region of every run of the genome
@@ -886,7 +892,16 @@ struct BucketSmem {
     float* lvl_freq[16];               //            ... of the frequency row (nullptr: not requested)
     double lvl_inv[16];                //            1 / windows of that level
 };
-static_assert(sizeof(BucketSmem) <= 74 * 1024, "three bucket CTAs must fit in one SM's shared memory");
+constexpr int BUCKET_CTAS_PER_SM = 3;
+static_assert(sizeof(BucketSmem) <= 75 * 1024, "three bucket CTAs must fit in one SM's shared memory");
+
+// ---- 1-D TMA bulk copy (no tensor map)
+// shared -> global, tracked by the thread's bulk group
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // 8 payload entries of one 128-bit vector: live ones are bins of the bucket, padding goes to the
 // dummy bins behind them (see partition_kernel).
@@ -899,7 +914,7 @@ __device__ __forceinline__ void hist_add8(uint32_t hbase, const uint4& x, uint32
     }
 }
 
-__global__ void __launch_bounds__(BUCKET_THREADS, 3)
+__global__ void __launch_bounds__(BUCKET_THREADS, BUCKET_CTAS_PER_SM)
 bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const GenomeRuns* __restrict__ grs,
               const uint4* __restrict__ payload, const uint16_t* __restrict__ nsec, uint32_t cap,
               const GenomeStats* __restrict__ stats, float* freq, uint64_t freq_stride, uint64_t* totals,
@@ -940,15 +955,15 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
     constexpr int PER1 = PART_BINS / 4 / BUCKET_THREADS;          // 8 level-(k-1) bins per thread
     constexpr int PER2 = PART_BINS / 16 / BUCKET_THREADS;         // 2 level-(k-2) bins per thread
     // (run-end tails of these levels are added afterwards from the genome's tail list)
-    // stream this bucket's regions: run r of the genome holds ns[r] sectors at
-    // payload[((run0 + r) * nb + b) * cap ...]; one warp per region, 128-bit coalesced loads
+    // Stream this bucket's regions: run r of the genome holds ns[r] sectors at
+    // payload[((run0 + r) * nb + b) * cap ...]; one warp per region, 128-bit coalesced loads in rounds of
+    // 32 vectors, four rounds in flight
     const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sm.hist);
     const uint32_t fix = payload_fix(b);
     {
         uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
         for (int i = tid; i < (PART_BINS + 256) / 4; i += BUCKET_THREADS) h4[i] = make_uint4(0, 0, 0, 0);
     }
-    constexpr int UNROLL = 4;
     constexpr int NWARP = BUCKET_THREADS / 32;
     const int lane = tid & 31, wid = tid >> 5;
     const size_t run_stride = (size_t)nb * cap * 2;                       // uint4 per run
@@ -959,44 +974,49 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
             sm.ns[i] = __ldg(nsec + (size_t)(gr.run0 + rb + i) * nb + b);
         __syncthreads();
         const uint4* base = payload + ((size_t)(gr.run0 + rb) * nb + b) * cap * 2;
-        // rounds of this warp: (run r, chunk c) = vectors [c * 32 * UNROLL, ...) of run r's region
-        auto valid = [&](uint32_t r, uint32_t c) -> bool { return r < nr && c * (32u * UNROLL) < 2u * sm.ns[r]; };
-        auto next = [&](uint32_t& r, uint32_t& c) {
+        // the warp's rounds: (run r, c) = vectors [32 c, 32 c + 32) of run r's region, r = wid, wid + 16, ...
+        uint32_t r = wid, c = 0, nv = 0;
+        auto settle = [&]() {                                             // skip runs that are used up
+            while (r < nr && 32u * c >= (nv = 2u * sm.ns[r])) { r += NWARP; c = 0; }
+        };
+        auto issue = [&](uint4& x, bool& live) -> bool {                  // next round: load; false when the warp is done
+            settle();
+            if (r >= nr) { live = false; return false; }
+            const uint32_t v = 32u * c + lane;
+            live = v < nv;
+            if (live) x = __ldg(base + (size_t)r * run_stride + v);
             c++;
-            while (r < nr && !valid(r, c)) { r += NWARP; c = 0; }
+            return true;
         };
-        auto load = [&](uint32_t r, uint32_t c, uint4* x) {
-            const uint32_t nv = 2u * sm.ns[r];
-            const uint4* p = base + (size_t)r * run_stride;
-#pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                const uint32_t v = c * (32u * UNROLL) + u * 32u + lane;
-                if (v < nv) x[u] = __ldg(p + v);
-            }
-        };
-        auto add = [&](uint32_t r, uint32_t c, const uint4* x) {
-            const uint32_t nv = 2u * sm.ns[r];
-#pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                const uint32_t v = c * (32u * UNROLL) + u * 32u + lane;
-                if (v < nv) hist_add8(hbase, x[u], fix);
-            }
-        };
-        // (no register look-ahead: 48 warps per SM with four 128-bit loads each in flight cover the latency)
-        uint4 x[UNROLL];
-        uint32_t r = wid, c = 0;
-        while (r < nr && !valid(r, c)) r += NWARP;
-        while (r < nr) {
-            load(r, c, x);
-            add(r, c, x);
-            next(r, c);
+        uint4 x0, x1, x2, x3;
+        bool l0, l1, l2, l3;
+        bool h0 = issue(x0, l0), h1 = issue(x1, l1), h2 = issue(x2, l2), h3 = issue(x3, l3);
+        while (h0) {
+            if (l0) hist_add8(hbase, x0, fix);
+            h0 = issue(x0, l0);
+            if (!h1) break;
+            if (l1) hist_add8(hbase, x1, fix);
+            h1 = issue(x1, l1);
+            if (!h2) break;
+            if (l2) hist_add8(hbase, x2, fix);
+            h2 = issue(x2, l2);
+            if (!h3) break;
+            if (l3) hist_add8(hbase, x3, fix);
+            h3 = issue(x3, l3);
         }
     }
+    // level k: this bucket's 16384 bins leave as ONE bulk copy shared -> global (the atomics above went through
+    // the generic proxy: fence, barrier, then one thread issues the copy) ...
+#if KM_BUCKET_BULK_STORE
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    // level k: this bucket's 16384 bins, and level k-1 on the way (kept in registers)
+    if (tid == 0) bulk_store(sm.lvl_counts[k], hbase, PART_BINS * 4);
+#else
+    __syncthreads();
+#endif
+    // ... while the threads turn them into frequencies and level k-1 (kept in registers)
     uint32_t v1r[PER1];
     {
-        uint32_t* ck = sm.lvl_counts[k];
         float* fk = sm.lvl_freq[k];
         const double inv = sm.lvl_inv[k];
         const bool down = k - 1 >= k_stop;
@@ -1007,7 +1027,9 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
         for (int u = 0; u < PER1; u++) {
             const int i = tid + u * BUCKET_THREADS;
             const uint4 c = reinterpret_cast<const uint4*>(sm.hist)[i];
-            reinterpret_cast<uint4*>(ck)[i] = c;
+#if !KM_BUCKET_BULK_STORE
+            reinterpret_cast<uint4*>(sm.lvl_counts[k])[i] = c;
+#endif
             if (fk) {
                 float4 f;
                 f.x = (float)((double)c.x * inv); f.y = (float)((double)c.y * inv);
@@ -1021,6 +1043,9 @@ bucket_kernel(LevelMap lm, RowSpec row, LevelInfo li, int k, int k_stop, const G
             }
         }
     }
+#if KM_BUCKET_BULK_STORE
+    if (tid == 0) bulk_store_wait_read();                             // the bulk copy has read hist[]
+#endif
     if (k - 2 < k_stop) return;
     __syncthreads();                                                  // everybody is done reading hist[]
 #pragma unroll
