@@ -46,6 +46,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-genomes", type=int, default=None)
+    ap.add_argument("--extras", default="on", choices=["on", "off"],
+                    help="also time the other BASELINE configs (c3, c4_strong, c5_sparse: bench_extras.py)")
+    ap.add_argument("--extra-scale", type=float, default=1.0, help="shrink the extras' genomes (debug only)")
+    ap.add_argument("--c5-single", action="store_true", help="run c5_sparse on one GPU too (> 100 GB of workspace)")
     return ap.parse_args()
 
 
@@ -445,6 +449,14 @@ def run_ours(args):
         except Exception as exc:                                  # report, never fake
             e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:300]}
 
+    extras = {}
+    if args.extras == "on":
+        import bench_extras
+        del counts, freq, totals, fasta
+        if not args.no_e2e:
+            host_bufs = hc = hf = ht = None
+        torch.cuda.empty_cache()
+        extras = bench_extras.run_extras(args, torch, dist, device, rank, world)
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -455,11 +467,12 @@ def run_ours(args):
             "config": {"workload": f"C2: {n_gen} synthetic fungal-sized genomes per GPU (12-40 Mbp x {args.scale:g}), "
                                    f"k={ks[0]}..{ks[-1]} dense histograms + frequency rows",
                        "genomes_per_gpu": n_gen, "k_list": ks, "bases_per_gpu": nbases,
-                       "fasta_bytes_per_gpu": int(fasta.numel()),
+                       "fasta_bytes_per_gpu": int(F),
                        "l2_policy": "inputs (GBs) and outputs far exceed the 126 MB L2; no explicit flush"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": int(prof["launches"]), "clocks": clocks, "parity": parity,
         }
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

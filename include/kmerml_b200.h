@@ -124,6 +124,14 @@ int kmerml_count_sparse(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbytes
                         uint64_t out_cap, uint64_t *h_unique, uint64_t *h_windows, void *stream);
 
 /*
+ * The result of the last kmerml_count_sparse / kmerml_count_sparse_range call of this context whose
+ * *h_unique exceeded out_cap, copied out of the workspace without counting again (out_cap >= that number;
+ * no other call may have used the context in between).  Synchronous.
+ */
+int kmerml_sparse_fetch(kmerml_ctx *ctx, uint64_t *d_keys, uint32_t *d_counts, uint32_t *d_first,
+                        uint64_t out_cap, void *stream);
+
+/*
  * Multi-GPU unit of the sparse path ("one large genome, sparse k"): the same as
  * kmerml_count_sparse for the windows whose last base lies in the byte range [range_begin, range_end) of
  * the file -- begin a multiple of KMERML_SPARSE_RANGE_ALIGN, end too or == nbytes.  The k-1 bases before
@@ -226,6 +234,17 @@ int kmerml_normalize_rows(kmerml_ctx *ctx, const uint32_t *d_counts, uint64_t co
 #define KMERML_METRIC_EUCLIDEAN 1
 int kmerml_pairwise_distance(kmerml_ctx *ctx, const void *d_x, int dtype, uint64_t stride, int n,
                              uint64_t m, int metric, float *d_out32, double *d_out64, void *stream);
+
+/*
+ * Rows [row_begin, row_end) of that matrix for uint32 count rows (m a multiple of 64): the block one
+ * GPU computes when the genomes were counted on several GPUs and the rows gathered (the reference has no
+ * distance code; nearest hooks are the stubs kmerml/ml/clustering.py:6-16).  All n rows must be resident;
+ * d_out32 / d_out64: (row_end - row_begin) x n.  The Gram entries are exact integers (tcgen05 kind::i8), so
+ * the block is bit-identical to the same rows of kmerml_pairwise_distance.
+ */
+int kmerml_pairwise_distance_rows(kmerml_ctx *ctx, const uint32_t *d_counts, uint64_t stride, int n,
+                                  uint64_t m, int row_begin, int row_end, int metric, float *d_out32,
+                                  double *d_out64, void *stream);
 
 /*
  * Measurement hooks (bench.py): with profiling enabled every kernel the library

@@ -105,6 +105,7 @@ struct kmerml_ctx {
     int device = 0;
     int sm_count = 148;
     km::Workspace ws[3];
+    km::SparsePending sparse_pending;             // kmerml_count_sparse -> kmerml_sparse_fetch
     uint64_t max_group_payload = 12ull << 30;     // partition path: payload bytes one group of genomes may take
     // measurement hooks
     bool profiling = false;
@@ -772,6 +773,23 @@ int kmerml_pairwise_distance(kmerml_ctx* ctx, const void* d_x, int dtype, uint64
     return launch_pairwise(d_x, dtype, stride, n, m, metric, d_gram, d_out32, d_out64, (cudaStream_t)stream);
 }
 
+int kmerml_pairwise_distance_rows(kmerml_ctx* ctx, const uint32_t* d_counts, uint64_t stride, int n, uint64_t m,
+                                  int row_begin, int row_end, int metric, float* d_out32, double* d_out64, void* stream) {
+    if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
+    if (metric < 0 || metric > 1 || n < 0 || row_begin < 0 || row_end > n || row_begin > row_end)
+        return fail(KMERML_ERR_ARG, "bad metric / row range");
+    if (row_begin == row_end) return KMERML_OK;
+    if (!d_counts || (!d_out32 && !d_out64)) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (m < 64 || m % 64) return fail(KMERML_ERR_ARG, "the row length must be a multiple of 64 (k >= 3)");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    Workspace& ws = ctx->ws[0];
+    int rc = ws.part.ensure(gram_rows_workspace(n, m));
+    if (rc) return rc;
+    return launch_distance_rows_tc(d_counts, stride, n, m, row_begin, row_end, metric, ws.part.p, d_out32, d_out64,
+                                   (cudaStream_t)stream);
+}
+
 static int count_sparse_core(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin,
                              uint64_t range_end, int k, int min_record_len, unsigned flags, uint64_t* d_keys,
                              uint32_t* d_counts, uint32_t* d_first, uint64_t out_cap, uint64_t* h_unique,
@@ -781,6 +799,7 @@ static int count_sparse_core(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t n
     if (nbytes && !d_fasta) return fail(KMERML_ERR_ARG, "d_fasta is null");
     if (out_cap && (!d_keys || !d_counts)) return fail(KMERML_ERR_ARG, "null output pointer");
     if (nbytes >= 0xFFFFFFFFull) return fail(KMERML_ERR_RANGE, "genome too large for 32-bit offsets");
+    if ((uintptr_t)d_fasta & 15) return fail(KMERML_ERR_ARG, "device pointers must be 16-byte aligned");
     if (range_begin > range_end || range_end > nbytes) return fail(KMERML_ERR_ARG, "byte range outside the file");
     if (range_begin % KMERML_SPARSE_RANGE_ALIGN || (range_end % KMERML_SPARSE_RANGE_ALIGN && range_end != nbytes))
         return fail(KMERML_ERR_ARG, "byte range must be aligned to KMERML_SPARSE_RANGE_ALIGN");
@@ -793,9 +812,25 @@ static int count_sparse_core(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t n
     const uint64_t cap = std::max<uint64_t>(range_end - range_begin, 1);
     int rc = ws.part.ensure(sparse_workspace_bytes(cap, nbytes));
     if (rc) return rc;
-    return run_sparse_in(ws.part.p, d_fasta, nbytes, range_begin, range_end, k, min_rec,
-                         (flags & KMERML_FLAG_CANONICAL) != 0, cap, d_keys, d_counts, d_first, out_cap, h_unique,
-                         h_windows, (cudaStream_t)stream);
+    rc = run_sparse_in(ws.part.p, d_fasta, nbytes, range_begin, range_end, k, min_rec,
+                       (flags & KMERML_FLAG_CANONICAL) != 0, cap, d_keys, d_counts, d_first, out_cap, h_unique,
+                       h_windows, &ctx->sparse_pending, (cudaStream_t)stream);
+    ctx->sparse_pending.cap = cap;
+    ctx->sparse_pending.nbytes = nbytes;
+    ctx->sparse_pending.workspace = ws.part.p;
+    return rc;
+}
+
+int kmerml_sparse_fetch(kmerml_ctx* ctx, uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_first, uint64_t out_cap,
+                        void* stream) {
+    if (!ctx || !d_keys || !d_counts) return fail(KMERML_ERR_ARG, "null pointer argument");
+    const SparsePending& p = ctx->sparse_pending;
+    if (!p.valid || p.workspace != ctx->ws[0].part.p)
+        return fail(KMERML_ERR_ARG, "no sparse result to fetch (another call has used the workspace since)");
+    if (out_cap < p.nu) return fail(KMERML_ERR_ARG, "outputs smaller than the number of distinct k-mers");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    return sparse_fetch(ctx->ws[0].part.p, p.cap, p.nbytes, p, d_keys, d_counts, d_first, (cudaStream_t)stream);
 }
 
 int kmerml_count_sparse(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, int k, int min_record_len,

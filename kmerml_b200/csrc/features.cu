@@ -91,26 +91,28 @@ __global__ void genome_stats_kernel(const uint8_t* __restrict__ buf, uint64_t nb
     const uint64_t cb = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 64;
     const uint64_t cs = cb > g.lo ? cb : g.lo;
     const uint64_t ce = cb + 64 < g.hi ? cb + 64 : g.hi;
-    unsigned contigs = 0, total = 0, gc = 0, nn = 0;     // wrap-around arithmetic (see above)
-    auto tally = [&](uint64_t pos, unsigned sign) -> bool {          // true: a header line starts at pos
+    // 64-bit wrap-around arithmetic all the way (a warp's net tally can be negative when a header line
+    // crosses its span: with 32-bit tallies zero-extended into the 64-bit sums that added 2^32)
+    unsigned long long contigs = 0, total = 0, gc = 0, nn = 0;
+    auto tally = [&](uint64_t pos, unsigned long long sign) -> bool {  // true: a header line starts at pos
         const uint32_t c = buf[pos];
         const int code = base_code(c);
         if (code >= 0) {
             total += sign;
-            gc += (code == 1 || code == 2) ? sign : 0u;
+            gc += (code == 1 || code == 2) ? sign : 0ull;
             return false;
         }
         const int kind = classify_nonbase(g, pos, c);
         if (kind == SYM_SKIP) return false;
         if (kind == SYM_HDR) return true;
         total += sign;
-        nn += ((c & 0xDFu) == (uint32_t)'N') ? sign : 0u;
+        nn += ((c & 0xDFu) == (uint32_t)'N') ? sign : 0ull;
         return false;
     };
     for (uint64_t pos = cs; pos < ce; pos++) {
-        if (!tally(pos, 1u)) continue;
+        if (!tally(pos, 1ull)) continue;
         contigs++;
-        for (uint64_t q = pos + 1; q < g.hi && !is_term(buf[q]); q++) tally(q, 0u - 1u);
+        for (uint64_t q = pos + 1; q < g.hi && !is_term(buf[q]); q++) tally(q, ~0ull);
     }
     // warp then global reduction
     for (int o = 16; o > 0; o >>= 1) {
@@ -120,10 +122,10 @@ __global__ void genome_stats_kernel(const uint8_t* __restrict__ buf, uint64_t nb
         nn += __shfl_xor_sync(0xffffffffu, nn, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        if (contigs) atomicAdd(out + 0, (unsigned long long)contigs);
-        if (total) atomicAdd(out + 1, (unsigned long long)total);
-        if (gc) atomicAdd(out + 2, (unsigned long long)gc);
-        if (nn) atomicAdd(out + 3, (unsigned long long)nn);
+        if (contigs) atomicAdd(out + 0, contigs);
+        if (total) atomicAdd(out + 1, total);
+        if (gc) atomicAdd(out + 2, gc);
+        if (nn) atomicAdd(out + 3, nn);
     }
 }
 

@@ -61,7 +61,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 __global__ void __launch_bounds__(GT_THREADS)
 gram_i8_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, int n, uint64_t m, int symmetric_pair,
-               unsigned long long scale, unsigned long long* __restrict__ G) {
+               unsigned long long scale, unsigned long long* __restrict__ G, int row_tile0, int rows_only) {
+    // rows_only (multi-GPU row block): tile rows row_tile0 .. row_tile0 + gridDim.y - 1 against ALL columns, every
+    // (a, b) digit pair launched separately, nothing mirrored: G holds rows [128 row_tile0, ...) only, at their
+    // global row index.
     // shared: A tile and B tile in core-matrix layout: [kg (4)][mg (16)][8 rows][16 B]
     __shared__ __align__(128) uint8_t sA[GT_M * GT_KB];
     __shared__ __align__(128) uint8_t sB[GT_N * GT_KB];
@@ -69,8 +72,8 @@ gram_i8_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, int
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = blockIdx.y * GT_M, col0 = blockIdx.x * GT_N;
-    if (symmetric_pair && col0 < row0) return;             // D_a D_a^T: the upper triangle is enough
+    const int row0 = (blockIdx.y + row_tile0) * GT_M, col0 = blockIdx.x * GT_N;
+    if (!rows_only && symmetric_pair && col0 < row0) return;   // D_a D_a^T: the upper triangle is enough
     const uint64_t k_begin = (uint64_t)blockIdx.z * GT_KSPLIT;
     const uint64_t k_end = min(m, k_begin + GT_KSPLIT);
 
@@ -171,7 +174,9 @@ gram_i8_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, int
                 const int gj = col0 + c0 + c;
                 if (gj >= n || !v[c]) continue;
                 const unsigned long long add = (unsigned long long)v[c] * scale;
-                if (symmetric_pair) {
+                if (rows_only) {
+                    atomicAdd(G + (uint64_t)gi * n + gj, add);
+                } else if (symmetric_pair) {
                     if (gj < gi) continue;                                    // upper triangle (tiles on the diagonal)
                     atomicAdd(G + (uint64_t)gi * n + gj, add);
                     if (gj != gi) atomicAdd(G + (uint64_t)gj * n + gi, add);
@@ -215,12 +220,88 @@ int launch_gram_tc(const uint32_t* d_counts, uint64_t stride, int n, uint64_t m,
             if (8 * (a + b) >= 64) continue;                 // would not fit 64 bits anyway (counts^2 sums < 2^63 assumed)
             const unsigned long long scale = 1ull << (8 * (a + b));
             gram_i8_kernel<<<dim3(tiles, tiles, ksplits), GT_THREADS, 0, s>>>(planes + a * plane, planes + b * plane, n, m,
-                                                                             a == b ? 1 : 0, scale, G);
+                                                                             a == b ? 1 : 0, scale, G, 0, 0);
             KM_CUDA(cudaGetLastError());
         }
     }
     const uint64_t nn = (uint64_t)n * n;
     gram_to_double_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(G, d_gram, nn);
+    KM_CUDA(cudaGetLastError());
+    return KMERML_OK;
+}
+
+// Exact squared norms of the count rows (uint64, then double): the Gram diagonal every rank of a row-block
+// distance needs for ALL genomes.  One warp per row.
+__global__ void row_sumsq_kernel(const uint32_t* __restrict__ counts, uint64_t stride, int n, uint64_t m, double* __restrict__ out) {
+    const int row = (int)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const uint32_t* c = counts + (uint64_t)row * stride;
+    unsigned long long acc = 0;
+    for (uint64_t i = lane; i < m; i += 32) {
+        const unsigned long long v = c[i];
+        acc += v * v;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[row] = (double)acc;
+}
+
+// rows [row_begin, row_end) of the distance matrix from the row block of G and the squared norms of all rows
+__global__ void distance_rows_kernel(const unsigned long long* __restrict__ G, const double* __restrict__ norm2, int n,
+                                     int row_begin, int row_end, int metric, float* D32, double* D64) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)(row_end - row_begin) * n) return;
+    const int i = row_begin + (int)(idx / n), j = (int)(idx % n);
+    const double gii = norm2[i], gjj = norm2[j], gij = (double)G[(uint64_t)i * n + j];
+    double d;
+    if (i == j) {
+        d = 0.0;
+    } else if (metric == 0) {
+        const double den = sqrt(gii) * sqrt(gjj);
+        d = den > 0.0 ? 1.0 - gij / den : nan("");
+    } else {
+        const double d2 = gii + gjj - 2.0 * gij;
+        d = d2 > 0.0 ? sqrt(d2) : 0.0;
+    }
+    if (D32) D32[idx] = (float)d;
+    if (D64) D64[idx] = d;
+}
+
+size_t gram_rows_workspace(int n, uint64_t m) { return gram_tc_workspace(n, m) + (size_t)n * 8 + 256; }
+
+// Rows [row_begin, row_end) of the n x n distance matrix of uint32 count rows (all n rows resident): the unit one
+// rank computes when the genomes were counted on several GPUs and the rows gathered.  The Gram
+// entries are exact (tcgen05 kind::i8), so the block is bit-identical to the same rows of the single-GPU matrix.
+int launch_distance_rows_tc(const uint32_t* d_counts, uint64_t stride, int n, uint64_t m, int row_begin, int row_end,
+                            int metric, void* workspace, float* d_out32, double* d_out64, cudaStream_t s) {
+    if (row_begin >= row_end) return KMERML_OK;
+    uint8_t* planes = (uint8_t*)workspace;
+    const size_t plane = (size_t)n * m;
+    unsigned long long* G = (unsigned long long*)(planes + ((4 * plane + 255) / 256) * 256);
+    unsigned int* d_max = (unsigned int*)(G + (size_t)n * n);
+    double* d_norm = (double*)((uint8_t*)workspace + gram_tc_workspace(n, m) / 256 * 256 + 256);
+    const int t0 = row_begin / GT_M, t1 = (row_end + GT_M - 1) / GT_M;
+    KM_CUDA(cudaMemsetAsync(G + (size_t)t0 * GT_M * n, 0, (size_t)(std::min(t1 * GT_M, n) - t0 * GT_M) * n * 8, s));
+    KM_CUDA(cudaMemsetAsync(d_max, 0, 8, s));
+    split_digits_kernel<<<148 * 8, 256, 0, s>>>(d_counts, stride, n, m, planes, d_max);
+    row_sumsq_kernel<<<(unsigned)(((uint64_t)n * 32 + 255) / 256), 256, 0, s>>>(d_counts, stride, n, m, d_norm);
+    KM_CUDA(cudaGetLastError());
+    unsigned int h_max = 0;
+    KM_CUDA(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, s));
+    KM_CUDA(cudaStreamSynchronize(s));
+    const int nd = h_max >= (1u << 24) ? 4 : h_max >= (1u << 16) ? 3 : h_max >= (1u << 8) ? 2 : 1;
+    const unsigned tiles = (unsigned)((n + GT_N - 1) / GT_N);
+    const unsigned ksplits = (unsigned)((m + GT_KSPLIT - 1) / GT_KSPLIT);
+    for (int a = 0; a < nd; a++) {
+        for (int b = 0; b < nd; b++) {
+            if (8 * (a + b) >= 64) continue;
+            gram_i8_kernel<<<dim3(tiles, (unsigned)(t1 - t0), ksplits), GT_THREADS, 0, s>>>(
+                planes + a * plane, planes + b * plane, n, m, 0, 1ull << (8 * (a + b)), G, t0, 1);
+            KM_CUDA(cudaGetLastError());
+        }
+    }
+    const uint64_t cells = (uint64_t)(row_end - row_begin) * n;
+    distance_rows_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(G, d_norm, n, row_begin, row_end, metric, d_out32, d_out64);
     KM_CUDA(cudaGetLastError());
     return KMERML_OK;
 }

@@ -116,10 +116,21 @@ int dense_setup_attributes();
 
 // ---- sparse path (sparse.cu) ---------------------------------------------------
 struct SparseWork;
+struct SparsePending {        // the reduced result of the last sparse count, still in the workspace (kmerml_sparse_fetch)
+    bool valid = false;
+    uint64_t* sorted_keys = nullptr;
+    uint32_t* sorted_ends = nullptr;
+    uint64_t* uniq = nullptr;
+    uint32_t* runs = nullptr;
+    uint64_t n = 0, nu = 0, cap = 0, nbytes = 0;
+    const void* workspace = nullptr;
+};
 size_t sparse_workspace_bytes(uint64_t cap, uint64_t nbytes);
+int sparse_fetch(void* workspace, uint64_t cap, uint64_t nbytes, const SparsePending& p, uint64_t* d_keys_out,
+                 uint32_t* d_counts_out, uint32_t* d_first_out, cudaStream_t s);
 int run_sparse_in(void* workspace, const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, uint64_t range_end,
                   int k, int min_rec, bool canonical, uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
-                  uint64_t* h_unique, uint64_t* h_windows, cudaStream_t s);
+                  uint64_t* h_unique, uint64_t* h_windows, SparsePending* pending, cudaStream_t s);
 
 size_t merge_workspace_bytes(uint64_t n);
 int run_merge_sparse(void* workspace, int k, const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_first,
@@ -146,6 +157,9 @@ int launch_normalize_rows(const uint32_t* d_counts, uint64_t counts_stride, cons
 size_t gram_tc_workspace(int n, uint64_t m);
 int launch_gram_tc(const uint32_t* d_counts, uint64_t stride, int n, uint64_t m, void* workspace, double* d_gram,
                    cudaStream_t s);
+size_t gram_rows_workspace(int n, uint64_t m);
+int launch_distance_rows_tc(const uint32_t* d_counts, uint64_t stride, int n, uint64_t m, int row_begin, int row_end,
+                            int metric, void* workspace, float* d_out32, double* d_out64, cudaStream_t s);
 int launch_distance_from_gram(const double* d_gram, int n, int metric, float* d_out32, double* d_out64, cudaStream_t s);
 int launch_pairwise(const void* d_x, int dtype, uint64_t stride, int n, uint64_t m, int metric, double* d_gram,
                     float* d_out32, double* d_out64, cudaStream_t s);

@@ -193,11 +193,29 @@ size_t sparse_workspace(uint64_t cap, uint64_t nbytes, SparseWork* w, uint8_t* b
     return off;
 }
 
+// The reduced result (distinct k-mers in `uniq`, their counts in `runs`) to the caller's buffers; the first
+// offsets are the minimum end offset of every run of the sorted windows.
+static int sparse_copy_out(const SparseWork& w, uint64_t* sorted_keys, uint32_t* sorted_ends, uint64_t* uniq, uint32_t* runs,
+                           uint64_t n, uint64_t nu, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out,
+                           cudaStream_t s) {
+    KM_CUDA(cudaMemcpyAsync(d_keys_out, uniq, nu * 8, cudaMemcpyDeviceToDevice, s));
+    gather_u32_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, s>>>(runs, d_counts_out, nu);
+    KM_CUDA(cudaGetLastError());
+    if (d_first_out) {
+        size_t tb = w.temp_bytes;
+        KM_CUDA(cub::DeviceReduce::ReduceByKey(w.temp, tb, sorted_keys, uniq, sorted_ends, d_first_out, w.n_runs,
+                                               cub::Min(), (uint64_t)n, s));
+    }
+    KM_CUDA(cudaStreamSynchronize(s));
+    return KMERML_OK;
+}
+
 // Emits, sorts and reduces.  On return (after a stream sync) *h_windows / *h_unique are valid; when
 // *h_unique > out_cap nothing was written to the outputs.
 int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, uint64_t range_end, int k, int min_rec,
                bool canonical, const SparseWork& w, uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
-               uint64_t* h_unique, uint64_t* h_windows, cudaStream_t s) {
+               uint64_t* h_unique, uint64_t* h_windows, SparsePending* pending, cudaStream_t s) {
+    if (pending) pending->valid = false;
     SparseParams P;
     P.k = k;
     P.min_rec = min_rec;
@@ -250,28 +268,31 @@ int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, ui
     KM_CUDA(cudaMemcpyAsync(&nu, w.n_runs, 8, cudaMemcpyDeviceToHost, s));
     KM_CUDA(cudaStreamSynchronize(s));
     *h_unique = nu;
-    if (nu > out_cap) return KMERML_OK;             // caller re-sizes and calls again
-    KM_CUDA(cudaMemcpyAsync(d_keys_out, uniq, nu * 8, cudaMemcpyDeviceToDevice, s));
-    gather_u32_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, s>>>(runs, d_counts_out, nu);
-    KM_CUDA(cudaGetLastError());
-    if (d_first_out) {
-        tb = w.temp_bytes;
-        KM_CUDA(cub::DeviceReduce::ReduceByKey(w.temp, tb, sorted_keys, uniq, sorted_ends, d_first_out, w.n_runs,
-                                               cub::Min(), (uint64_t)n, s));
+    if (pending) {
+        pending->sorted_keys = sorted_keys; pending->sorted_ends = sorted_ends; pending->uniq = uniq; pending->runs = runs;
+        pending->n = n; pending->nu = nu; pending->valid = true;
     }
-    KM_CUDA(cudaStreamSynchronize(s));
-    return KMERML_OK;
+    if (nu > out_cap) return KMERML_OK;             // caller sizes its outputs and fetches (kmerml_sparse_fetch)
+    return sparse_copy_out(w, sorted_keys, sorted_ends, uniq, runs, n, nu, d_keys_out, d_counts_out, d_first_out, s);
+}
+
+int sparse_fetch(void* workspace, uint64_t cap, uint64_t nbytes, const SparsePending& p, uint64_t* d_keys_out,
+                 uint32_t* d_counts_out, uint32_t* d_first_out, cudaStream_t s) {
+    SparseWork w;
+    sparse_workspace(cap, nbytes, &w, (uint8_t*)workspace);
+    return sparse_copy_out(w, p.sorted_keys, p.sorted_ends, p.uniq, p.runs, p.n, p.nu, d_keys_out, d_counts_out,
+                           d_first_out, s);
 }
 
 size_t sparse_workspace_bytes(uint64_t cap, uint64_t nbytes) { return sparse_workspace(cap, nbytes, nullptr, nullptr); }
 
 int run_sparse_in(void* workspace, const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, uint64_t range_end,
                   int k, int min_rec, bool canonical, uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
-                  uint64_t* h_unique, uint64_t* h_windows, cudaStream_t s) {
+                  uint64_t* h_unique, uint64_t* h_windows, SparsePending* pending, cudaStream_t s) {
     SparseWork w;
     sparse_workspace(cap, nbytes, &w, (uint8_t*)workspace);
     return run_sparse(d_fasta, nbytes, range_begin, range_end, k, min_rec, canonical, w, cap, d_keys_out, d_counts_out, d_first_out, out_cap,
-                      h_unique, h_windows, s);
+                      h_unique, h_windows, pending, s);
 }
 
 // ---- merge of partial results (multi-GPU: every rank receives the (k-mer, count, first) triples of its

@@ -130,6 +130,54 @@ def count_genome_chunked(fasta, k_values, *, min_record_len=None, canonical=Fals
     return counts, freq, totals
 
 
+def count_genome_chunked_scatter(fasta, k, *, min_record_len=None, canonical=False, count_range=None):
+    """Dense counts of ONE genome resident on every rank's device, result SHARDED: rank r counts byte range r
+    and ONE reduce-scatter (SUM) leaves it with slice r of the 4^k row, [r * 4^k / world, (r + 1) * 4^k / world).
+    The canonical fold is linear, so it is applied to every rank's partial row BEFORE the reduction
+    (kmerml_count_dense_range does it): no second exchange.  A reduce-scatter moves (world - 1) / world of a row
+    per rank, half of what the all-reduce of count_genome_chunked moves; gather the slices only if one rank needs
+    the whole row.  Returns (slice int32[4^k / world], slice offset, windows of the whole genome)."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    rank, world = _world()
+    k = int(k)
+    n_bins = 4 ** k
+    if n_bins % world:
+        raise ValueError("4^k must be divisible by the number of ranks")
+    begin, end = chunk_ranges(int(fasta.numel()), world)[rank]
+    fn = count_range if count_range is not None else engine.count_dense_range_device
+    counts, totals = fn(fasta, begin, end, [k], min_record_len, canonical)
+    if world == 1:
+        return counts, 0, int(totals[0])
+    part = torch.empty(n_bins // world, dtype=counts.dtype, device=counts.device)
+    dist.reduce_scatter_tensor(part, counts.contiguous(), op=dist.ReduceOp.SUM)
+    dist.all_reduce(totals, op=dist.ReduceOp.SUM)
+    return part, rank * (n_bins // world), int(totals[0])
+
+
+def distance_matrix_sharded(counts, metric="cosine", rows_fn=None):
+    """n x n distance matrix of count rows resident on every rank: rank r computes rows
+    [r * n / world, (r + 1) * n / world) (kmerml_pairwise_distance_rows, exact Gram entries on the tensor
+    cores) and one all_gather assembles the matrix everywhere."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    rank, world = _world()
+    n = counts.shape[0]
+    per = (n + world - 1) // world
+    r0, r1 = min(rank * per, n), min((rank + 1) * per, n)
+    fn = rows_fn if rows_fn is not None else engine.pairwise_distance_rows_device
+    block = fn(counts, r0, r1, metric)
+    if world == 1:
+        return block
+    pad = torch.zeros((per, n), dtype=block.dtype, device=block.device)
+    pad[:r1 - r0] = block
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return torch.cat(parts)[:n]
+
+
 def count_genomes_sharded(fasta_list, k_values, *, min_record_len=None, canonical=False, gather=True, count_batch=None):
     """Dense counts of many genomes: this rank counts its LPT shard; with gather=True the rows
     of all ranks are assembled (in input order) on every rank with one all_gather per tensor.

@@ -215,6 +215,28 @@ def pairwise_distance_device(x, metric="cosine", *, out_dtype=torch.float32):
     return out
 
 
+def pairwise_distance_rows_device(counts, row_begin, row_end, metric="cosine", *, out_dtype=torch.float32):
+    """Rows [row_begin, row_end) of the n x n distance matrix of uint32 count rows (int32 storage; the row length
+    a multiple of 64): one rank's block of a sharded distance computation, bit-identical to the same rows of
+    pairwise_distance_device."""
+    if metric not in _METRIC_CODE:
+        raise ValueError(f"metric must be one of {sorted(_METRIC_CODE)}")
+    if counts.dtype != torch.int32 or not counts.is_cuda or counts.dim() != 2 or counts.stride(1) != 1:
+        raise ValueError("counts must be a 2-D int32 CUDA tensor with contiguous rows")
+    ctx = _lib.context(counts.device.index)
+    n, m = counts.shape
+    out = torch.empty((max(row_end - row_begin, 0), n), dtype=out_dtype, device=counts.device)
+    if out.numel() == 0:
+        return out
+    stream = torch.cuda.current_stream(counts.device).cuda_stream
+    o32 = out.data_ptr() if out_dtype == torch.float32 else None
+    o64 = out.data_ptr() if out_dtype == torch.float64 else None
+    _lib.check(_lib.load().kmerml_pairwise_distance_rows(ctx.handle, counts.data_ptr(), counts.stride(0), n, m,
+                                                         int(row_begin), int(row_end), _METRIC_CODE[metric], o32, o64,
+                                                         ctypes.c_void_p(stream)))
+    return out
+
+
 def count_dense_range_device(fasta, begin, end, k_values, min_record_len=None, canonical=False, partition=True):
     """(counts int32[row_len], totals int64[nk]) of the windows of ONE genome whose last base
     lies in bytes [begin, end): the additive unit of intra-genome / multi-GPU parallelism."""
@@ -239,19 +261,29 @@ def count_sparse_device(fasta, k, *, min_record_len=None, canonical=False, want_
     L = _lib.load()
     stream = ctypes.c_void_p(torch.cuda.current_stream(fasta.device).cuda_stream)
     cap = max(1024, min(int(fasta.numel()), 1 << 22))
-    while True:
-        keys = torch.empty(cap, dtype=torch.int64, device=fasta.device)
-        counts = torch.empty(cap, dtype=torch.int32, device=fasta.device)
-        first = torch.empty(cap, dtype=torch.int32, device=fasta.device) if want_first else None
-        nu, nw = ctypes.c_uint64(0), ctypes.c_uint64(0)
-        _lib.check(L.kmerml_count_sparse(ctx.handle, fasta.data_ptr() if fasta.numel() else None, fasta.numel(), int(k),
-                                         int(min_record_len or 0), _lib.FLAG_CANONICAL if canonical else 0,
-                                         keys.data_ptr(), counts.data_ptr(), first.data_ptr() if want_first else None,
-                                         cap, ctypes.byref(nu), ctypes.byref(nw), stream))
-        if nu.value <= cap:
-            n = int(nu.value)
-            return keys[:n], counts[:n], (first[:n] if want_first else None), int(nw.value)
-        cap = int(nu.value)
+    keys = torch.empty(cap, dtype=torch.int64, device=fasta.device)
+    counts = torch.empty(cap, dtype=torch.int32, device=fasta.device)
+    first = torch.empty(cap, dtype=torch.int32, device=fasta.device) if want_first else None
+    nu, nw = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    _lib.check(L.kmerml_count_sparse(ctx.handle, fasta.data_ptr() if fasta.numel() else None, fasta.numel(), int(k),
+                                     int(min_record_len or 0), _lib.FLAG_CANONICAL if canonical else 0,
+                                     keys.data_ptr(), counts.data_ptr(), first.data_ptr() if want_first else None,
+                                     cap, ctypes.byref(nu), ctypes.byref(nw), stream))
+    n = int(nu.value)
+    if n > cap:
+        keys, counts, first = _sparse_fetch(ctx, L, n, fasta.device, want_first, stream)
+    return keys[:n], counts[:n], (first[:n] if want_first else None), int(nw.value)
+
+
+def _sparse_fetch(ctx, L, n, device, want_first, stream):
+    """More distinct k-mers than the first guess: the reduced result is still in the workspace; size the
+    outputs and copy it out (no second emit / sort / reduce)."""
+    keys = torch.empty(n, dtype=torch.int64, device=device)
+    counts = torch.empty(n, dtype=torch.int32, device=device)
+    first = torch.empty(n, dtype=torch.int32, device=device) if want_first else None
+    _lib.check(L.kmerml_sparse_fetch(ctx.handle, keys.data_ptr(), counts.data_ptr(),
+                                     first.data_ptr() if want_first else None, n, stream))
+    return keys, counts, first
 
 
 SPARSE_RANGE_ALIGN = 131072
@@ -264,19 +296,18 @@ def count_sparse_range_device(fasta, begin, end, k, *, min_record_len=None, cano
     L = _lib.load()
     stream = ctypes.c_void_p(torch.cuda.current_stream(fasta.device).cuda_stream)
     cap = max(1024, min(int(end) - int(begin), 1 << 22))
-    while True:
-        keys = torch.empty(cap, dtype=torch.int64, device=fasta.device)
-        counts = torch.empty(cap, dtype=torch.int32, device=fasta.device)
-        first = torch.empty(cap, dtype=torch.int32, device=fasta.device)
-        nu, nw = ctypes.c_uint64(0), ctypes.c_uint64(0)
-        _lib.check(L.kmerml_count_sparse_range(ctx.handle, fasta.data_ptr() if fasta.numel() else None, fasta.numel(),
-                                               int(begin), int(end), int(k), int(min_record_len or 0),
-                                               _lib.FLAG_CANONICAL if canonical else 0, keys.data_ptr(), counts.data_ptr(),
-                                               first.data_ptr(), cap, ctypes.byref(nu), ctypes.byref(nw), stream))
-        if nu.value <= cap:
-            n = int(nu.value)
-            return keys[:n], counts[:n], first[:n], int(nw.value)
-        cap = int(nu.value)
+    keys = torch.empty(cap, dtype=torch.int64, device=fasta.device)
+    counts = torch.empty(cap, dtype=torch.int32, device=fasta.device)
+    first = torch.empty(cap, dtype=torch.int32, device=fasta.device)
+    nu, nw = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    _lib.check(L.kmerml_count_sparse_range(ctx.handle, fasta.data_ptr() if fasta.numel() else None, fasta.numel(),
+                                           int(begin), int(end), int(k), int(min_record_len or 0),
+                                           _lib.FLAG_CANONICAL if canonical else 0, keys.data_ptr(), counts.data_ptr(),
+                                           first.data_ptr(), cap, ctypes.byref(nu), ctypes.byref(nw), stream))
+    n = int(nu.value)
+    if n > cap:
+        keys, counts, first = _sparse_fetch(ctx, L, n, fasta.device, True, stream)
+    return keys[:n], counts[:n], first[:n], int(nw.value)
 
 
 def merge_sparse_device(keys, counts, first, k):

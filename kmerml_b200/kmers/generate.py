@@ -98,7 +98,10 @@ class KmerExtractor:
         and write <output_dir>/<organism_id>/k{k}.txt[.gz]; returns the organism id."""
         if organism_id is None:
             organism_id = Path(fasta_file).stem
+        # one dict per DISTINCT k (generate.py:36), but `for k in k_values` (:49) runs once per entry: a k listed
+        # m times is counted m times.  Counted once here, multiplied when the file is written.
         ks = list(dict.fromkeys(int(k) for k in k_values))
+        mult = {k: sum(1 for v in k_values if int(v) == k) for k in ks}
         max_k = max(ks)
         if max_k > _lib.MAX_K or min(ks) < 1:
             raise _lib.KmermlError(f"k must be in 1..{_lib.MAX_K}")
@@ -119,13 +122,23 @@ class KmerExtractor:
             if k > _lib.MAX_DENSE_K:                     # sparse path: distinct k-mers, sorted by first occurrence
                 keys, cnts, first, _ = engine.count_sparse_device(dev, k, min_record_len=max_k, canonical=self.canonical)
                 order = torch.argsort(first.to(torch.int64) & 0xFFFFFFFF, stable=True)
-                text = engine.format_kmer_lines_device(keys[order].contiguous(), cnts[order].contiguous(), k)
+                text = engine.format_kmer_lines_device(keys[order].contiguous(), self._times(cnts[order], mult[k]), k)
             else:                                        # dense row + first-occurrence offsets -> text, on the GPU
-                row = res.counts_of(0, k)
+                row = self._times(res.counts_of(0, k), mult[k])
                 first = engine.first_occurrence_device(dev, k, min_record_len=max_k)
                 text = engine.format_kmer_file_device(row, first, k, canonical=self.canonical)
             self._write_lines(organism_id, k, text.cpu().numpy())
         return organism_id
+
+    @staticmethod
+    def _times(counts, m):
+        """uint32 counts (int32 storage) times the multiplicity of k in k_values."""
+        if m == 1:
+            return counts.contiguous()
+        wide = (counts.to(torch.int64) & 0xFFFFFFFF) * m
+        if wide.numel() and int(wide.max().item()) >= 1 << 32:
+            raise _lib.KmermlError("a k-mer count times the multiplicity of k in k_values exceeds 32 bits")
+        return wide.to(torch.int32).contiguous()           # (wraps: int32 storage of uint32 values)
 
     # ------------------------------------------------------------- file output
     def _target(self, organism_id, k):

@@ -153,13 +153,24 @@ def file_digits(code, k):
     return "".join(FILE_DIGIT[ch] for ch in code_to_kmer(code, k))
 
 
-def kmer_file_text(data, k, min_len):
-    """Exact text of k{k}.txt as generate.py:68-91 writes it."""
+def kmer_file_text(data, k, min_len, multiplicity=1):
+    """Exact text of k{k}.txt as generate.py:68-91 writes it.  `multiplicity`: how often k appears in
+    k_values -- `for k in k_values` (generate.py:49) counts into ONE dict per distinct k (:36) once per entry."""
     if k <= 12:
         counts, order = count_dense(data, k, min_len, want_order=True)
-        return "".join(f"{file_digits(b, k)}\t{int(counts[b])}\n" for b in order)
+        return "".join(f"{file_digits(b, k)}\t{int(counts[b]) * multiplicity}\n" for b in order)
     codes, counts = count_sparse(data, k, min_len)
-    return "".join(f"{file_digits(c, k)}\t{int(n)}\n" for c, n in zip(codes, counts))
+    return "".join(f"{file_digits(c, k)}\t{int(n) * multiplicity}\n" for c, n in zip(codes, counts))
+
+
+def kmer_file_stats(text, k):
+    """kmerml/utils/kmer_metadata.py:59-78 for the text of one k{k}.txt (numpy restatement of the pandas
+    reductions: mean = sum / n, median = middle element or the mean of the two middle ones)."""
+    counts = np.array([int(line.split("\t")[1]) for line in text.splitlines()], dtype=np.int64)
+    total = int(counts.sum())
+    return {"k_value": k, "total_kmers": total, "unique_kmers": int(counts.size), "max_count": int(counts.max()),
+            "min_count": int(counts.min()), "mean_count": float(counts.mean()), "median_count": float(np.median(counts)),
+            "estimated_genome_size": total + k - 1}
 
 
 def revcomp_code(code, k):

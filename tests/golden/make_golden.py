@@ -16,6 +16,11 @@ Outputs
   matrix_cases.json   - KmerFeatureBuilder matrices, from
                         kmerml/ml/features.py:28-117
   ref_timing.json     - single-core timings of the reference extractor here
+  extract_dupk_cases.json - k_values holding the same k more than once (the reference counts it as
+                        often, generate.py:36,49-58), same layout as extract_cases.json
+  metadata_cases.json - GenomeMetadataManager._extract_genome_metadata (utils/genome_metadata.py:55-85)
+                        and KmerMetadataManager._calculate_basic_stats (utils/kmer_metadata.py:59-78) on
+                        the extraction cases
   extract_big_cases.json - inputs of a few 100 kb (unwrapped, long header, repeats, CRLF + N runs, many short
                         records): gzip FASTA + SHA-256 / line count of every k{k}.txt the reference wrote
 """
@@ -37,6 +42,8 @@ sys.path.insert(1, "/root/reference")              # the unmodified reference
 from kmerml.kmers.generate import KmerExtractor              # noqa: E402
 from kmerml.kmers.statistics import KmerFeatureExtractor     # noqa: E402
 from kmerml.ml.features import KmerFeatureBuilder            # noqa: E402
+from kmerml.utils.genome_metadata import GenomeMetadataManager    # noqa: E402
+from kmerml.utils.kmer_metadata import KmerMetadataManager        # noqa: E402
 
 
 G0 = (">chr1 test contig\nAAAAAATCGGNACGTacgtAAAAAATC\nAAAC\n>short\nACGTA\n>chr2\nACGTRACGTACGT\n")
@@ -137,6 +144,92 @@ def extract_cases():
                 "files": files,
             })
     return out
+
+
+def run_extract(name, text, ks):
+    with tempfile.TemporaryDirectory() as td:
+        fa = Path(td) / "GCF_900000001_1.fa"
+        with open(fa, "w", newline="") as f:
+            f.write(text)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            ex = KmerExtractor(output_dir=Path(td) / "out", compress=False)
+            org = ex.extract_kmers_from_fasta(fa, list(ks))
+        files = {}
+        for k in dict.fromkeys(ks):
+            files[str(k)] = (Path(td) / "out" / org / f"k{k}.txt").read_text()
+        return {"name": name, "fasta_b64": base64.b64encode(text.encode("latin-1")).decode(),
+                "k_values": list(ks), "organism_id": org, "stdout": buf.getvalue().splitlines(), "files": files}
+
+
+def dupk_cases():
+    """k_values with repeated entries: `for k in k_values` (generate.py:49) runs once per entry over one dict
+    per distinct k (:36), so a k listed m times is counted m times."""
+    rng = random.Random(424242)
+    seq = lambda n, a="ACGT": "".join(rng.choice(a) for _ in range(n))       # noqa: E731
+    multi = ">r1 d\n" + "\n".join(seq(60, "ACGTN") for _ in range(12)) + "\n>tiny\nACG\n>r2\n" + seq(333, "ACGTacgt") + "\n"
+    cases = [
+        ("dup_22", ">r\nACGTACGT\n", [2, 2]),
+        ("dup_828", G0, [8, 2, 8]),
+        ("dup_333", G0, [3, 3, 3]),
+        ("dup_mixed_order", multi, [5, 12, 5, 1, 12, 12]),
+        ("dup_large_k", multi, [21, 4, 21]),
+        ("dup_short_skip", ">a\nACGTAC\n>b\nACGTACGTACGTACGT\n", [2, 9, 2]),
+    ]
+    return [run_extract(*c) for c in cases]
+
+
+def metadata_cases(extract):
+    """Genome tallies and k-mer count summaries as the reference's metadata managers compute them."""
+    out = []
+    picks = [c for c in extract if c["name"] in ("G0", "G0_k1to6", "crlf", "lone_cr", "lower", "all_n", "blank_lines",
+                                                 "spaces_tabs", "header_only_records", "junk_then_header", "empty_file",
+                                                 "gt_midline", "rand02", "rand05", "rand11", "rand17", "rand20", "largek01")]
+    for c in picks:
+        text = base64.b64decode(c["fasta_b64"]).decode("latin-1")
+        with tempfile.TemporaryDirectory() as td:
+            fa = Path(td) / "GCF_900000001_1.fa"
+            with open(fa, "w", newline="") as f:
+                f.write(text)
+            gm = GenomeMetadataManager(Path(td) / "meta" / "genome_metadata.json")
+            g = gm._extract_genome_metadata(fa)
+            genome = {key: g[key] for key in ("contigs", "total_size", "gc_content", "n_count")}
+            kdir = Path(td) / "kmers" / "GCF_900000001_1"
+            kdir.mkdir(parents=True)
+            km = KmerMetadataManager(Path(td) / "meta" / "genome_metadata.json")
+            kstats = {}
+            for k, txt in c["files"].items():
+                if not txt:
+                    continue                 # the manager fails on an empty file (max of an empty column)
+                p = kdir / f"k{k}.txt"
+                p.write_text(txt)
+                st = km._calculate_basic_stats(p, int(k))
+                kstats[k] = {key: st[key] for key in ("k_value", "total_kmers", "unique_kmers", "max_count", "min_count",
+                                                      "mean_count", "median_count", "estimated_genome_size")}
+            out.append({"name": c["name"], "genome": genome, "kmers": kstats})
+    return out
+
+
+def many_contig_metadata_case():
+    """Header lines that hold G / C / N letters and cross 2 KB boundaries (the genome-stats kernel subtracts
+    header bytes per warp span): hundreds of contigs with long descriptive headers."""
+    rng = random.Random(99)
+    parts = []
+    for i in range(400):
+        parts.append(f">contig{i} GC rich N unknown scaffold NNNN GGCC len={rng.randint(1, 10 ** rng.randint(1, 9))} {'CGN' * rng.randint(0, 40)}\n")
+        s = "".join(rng.choice("ACGTNacgtn") for _ in range(rng.choice([0, 1, 30, 61, 200, 2030, 2047, 2048, 2049, 5000])))
+        w = rng.choice([60, 80, 1000000])
+        parts.append("\n".join(s[j:j + w] for j in range(0, len(s), w)) + "\n")
+    text = "".join(parts)
+    import gzip
+    with tempfile.TemporaryDirectory() as td:
+        fa = Path(td) / "many.fa"
+        with open(fa, "w", newline="") as f:
+            f.write(text)
+        g = GenomeMetadataManager(Path(td) / "m" / "g.json")._extract_genome_metadata(fa)
+    return {"name": "many_contigs_long_headers",
+            "fasta_gz_b64": base64.b64encode(gzip.compress(text.encode("latin-1"), 9, mtime=0)).decode(),
+            "genome": {key: g[key] for key in ("contigs", "total_size", "gc_content", "n_count")}}
 
 
 def stats_and_matrix_cases(extract):
@@ -258,6 +351,11 @@ def main():
     (HERE / "ref_timing.json").write_text(json.dumps(timing(), indent=1))
     big = big_cases()
     (HERE / "extract_big_cases.json").write_text(json.dumps(big, indent=0))
+    dup = dupk_cases()
+    (HERE / "extract_dupk_cases.json").write_text(json.dumps(dup, indent=0))
+    meta = {"cases": metadata_cases(ext), "big": [many_contig_metadata_case()]}
+    (HERE / "metadata_cases.json").write_text(json.dumps(meta, indent=0))
+    print(f"{len(dup)} duplicate-k cases, {len(meta['cases'])} + {len(meta['big'])} metadata cases")
     print(f"{len(ext)} extract cases, {len(st)} stats cases, {len(mx)} matrix cases, {len(big)} big cases")
 
 

@@ -17,6 +17,29 @@ def golden_extract_cases():
     return cases
 
 
+def golden_dupk_cases():
+    """k_values that list a k more than once (tests/golden/make_golden.py: dupk_cases)."""
+    with open(os.path.join(GOLDEN, "extract_dupk_cases.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        c["fasta"] = base64.b64decode(c["fasta_b64"])
+    return cases
+
+
+def golden_metadata_cases():
+    """(cases, big): genome tallies and k-mer count summaries written by the reference's metadata managers."""
+    import gzip
+    with open(os.path.join(GOLDEN, "metadata_cases.json")) as f:
+        meta = json.load(f)
+    by_name = {c["name"]: c for c in golden_extract_cases()}
+    for c in meta["cases"]:
+        c["fasta"] = by_name[c["name"]]["fasta"]
+        c["files"] = by_name[c["name"]]["files"]
+    for c in meta["big"]:
+        c["fasta"] = gzip.decompress(base64.b64decode(c["fasta_gz_b64"]))
+    return meta["cases"], meta["big"]
+
+
 def parse_kmer_file(text):
     """k{k}.txt text -> list of (digits, count) in file order."""
     out = []

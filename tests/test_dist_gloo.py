@@ -119,6 +119,31 @@ def _worker(rank, world, port, results):
             ok &= bool(np.array_equal(mk.numpy().view(np.uint64), u[mine]))
             ok &= bool(np.array_equal(mc.numpy().astype(np.int64), cnt[mine]))
             ok &= bool(np.array_equal(mf.numpy().astype(np.int64), fst[mine]))
+        # (4) one genome, dense: byte ranges -> reduce-scatter to owner slices (canonical fold before the
+        # reduction: it is linear), the slices concatenated in rank order give the single-GPU row
+        def emu_canonical_range(fasta, begin, end, kk, ml, canonical):
+            c, t = emu_count_range(fasta, begin, end, kk, ml, False)
+            if canonical:
+                fwd = c.numpy().view(np.uint32).astype(np.uint64)
+                c = torch.from_numpy(oracle.canonical_from_forward(fwd, kk[0]).astype(np.uint32).view(np.int32).copy())
+            return c, t
+        for canonical in (False, True):
+            part, off, windows = kdist.count_genome_chunked_scatter(data, 6, canonical=canonical, count_range=emu_canonical_range)
+            ref = oracle.count_dense(genome.tobytes(), 6, 6)
+            if canonical:
+                ref = oracle.canonical_from_forward(ref, 6)
+            n = 4 ** 6 // world
+            ok &= off == rank * n and windows == int(ref.sum())
+            ok &= bool(np.array_equal(part.numpy().view(np.uint32).astype(np.uint64), ref[off:off + n]))
+        # (5) distance matrix in row blocks + all_gather
+        X = torch.from_numpy(np.random.default_rng(5).integers(0, 50, (7, 64)).astype(np.int32))
+
+        def np_rows(counts, r0, r1, metric):
+            D = oracle.pairwise_distance(counts.numpy().astype(np.float64), metric)
+            return torch.from_numpy(D[r0:r1].astype(np.float32))
+        for metric in ("cosine", "euclidean"):
+            D = kdist.distance_matrix_sharded(X, metric, rows_fn=np_rows)
+            ok &= bool(np.array_equal(D.numpy(), oracle.pairwise_distance(X.numpy().astype(np.float64), metric).astype(np.float32)))
         results[rank] = ok
     finally:
         dist.destroy_process_group()

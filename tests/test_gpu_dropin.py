@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import golden_extract_cases
+from helpers import golden_dupk_cases, golden_extract_cases, golden_metadata_cases
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-6
@@ -32,6 +32,22 @@ def test_extractor_files_and_messages_match_reference(tmp_path):
             assert got == text.encode(), (c["name"], k)
         n += 1
     assert n >= 49
+
+
+def test_duplicate_k_values_count_as_often(tmp_path):
+    """k_values = [8, 2, 8]: the reference counts k = 8 twice (generate.py:36,49-58); fixtures from the reference."""
+    from kmerml_b200.kmers.generate import KmerExtractor
+    for c in golden_dupk_cases():
+        fa = tmp_path / c["name"] / "GCF_900000001_1.fa"
+        fa.parent.mkdir()
+        fa.write_bytes(c["fasta"])
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            org = KmerExtractor(output_dir=tmp_path / c["name"] / "out", compress=False).extract_kmers_from_fasta(
+                fa, list(c["k_values"]))
+        assert buf.getvalue().splitlines() == c["stdout"], c["name"]
+        for k, text in c["files"].items():
+            assert (tmp_path / c["name"] / "out" / org / f"k{k}.txt").read_bytes() == text.encode(), (c["name"], k)
 
 
 def test_extractor_gzip_and_genome_list(tmp_path, capsys):
@@ -181,6 +197,26 @@ def test_tensor_core_gram_is_exact():
             assert np.allclose(got, alt, rtol=1e-12, atol=1e-12, equal_nan=True)
 
 
+def test_distance_row_blocks_match_full_matrix():
+    """kmerml_pairwise_distance_rows: the row blocks the ranks of a sharded distance computation own,
+    concatenated, are bit-identical to the single-call matrix (exact integer Gram entries)."""
+    import torch
+    from kmerml_b200 import engine
+    rng = np.random.default_rng(11)
+    for n, m, hi in ((5, 64, 300), (131, 4096, 70000), (300, 65536, 40)):
+        X = torch.from_numpy(rng.integers(0, hi, (n, m)).astype(np.int32)).cuda()
+        for metric in ("cosine", "euclidean"):
+            full = engine.pairwise_distance_device(X, metric, out_dtype=torch.float64)
+            for world in (1, 3, 8):
+                per = (n + world - 1) // world
+                blocks = [engine.pairwise_distance_rows_device(X, min(r * per, n), min((r + 1) * per, n), metric,
+                                                               out_dtype=torch.float64) for r in range(world)]
+                assert torch.equal(torch.cat(blocks), full), (n, m, metric, world)
+        want = oracle.pairwise_distance(X.cpu().numpy().astype(np.float64), "cosine")
+        got = engine.pairwise_distance_rows_device(X, 0, n, "cosine", out_dtype=torch.float64).cpu().numpy()
+        assert np.all(np.abs(got - want) <= RTOL * np.maximum(np.abs(want), 1e-30) + 1e-12)
+
+
 def test_genome_and_kmer_metadata():
     """Genome tallies (genome_metadata.py:55-85) and k-mer file summaries (kmer_metadata.py:59-78) from the GPU."""
     import torch
@@ -192,6 +228,24 @@ def test_genome_and_kmer_metadata():
         want = oracle.genome_stats(c["fasta"])
         assert got["contigs"] == want["contigs"] and got["total_size"] == want["total_size"], c["name"]
         assert got["n_count"] == want["n_count"] and got["gc_content"] == want["gc_content"], c["name"]
+    # ... and against what the reference's own managers wrote (tests/golden/metadata_cases.json), including
+    # 400 contigs whose long headers hold G / C / N letters and cross the kernel's warp spans
+    cases, big = golden_metadata_cases()
+    for c in cases + big:
+        a = np.frombuffer(c["fasta"], np.uint8) if len(c["fasta"]) else np.zeros(0, np.uint8)
+        dev = torch.from_numpy(a.copy()).cuda() if a.size else torch.zeros(0, dtype=torch.uint8, device="cuda")
+        got = engine.genome_stats_device(dev)
+        for key in ("contigs", "total_size", "n_count", "gc_content"):
+            assert got[key] == c["genome"][key], (c["name"], key)
+    for c in cases:
+        ks = [int(k) for k in c["kmers"] if int(k) <= 12]
+        if not ks:
+            continue
+        dev = torch.from_numpy(np.frombuffer(c["fasta"], np.uint8).copy()).cuda()
+        ml = max(int(k) for k in c["files"])
+        res = engine.count_dense_device(dev, [0, dev.numel()], ks, min_record_len=ml, want_freq=False)
+        for k in ks:
+            assert engine.kmer_count_stats_device(res.counts_of(0, k), k) == c["kmers"][str(k)], (c["name"], k)
     g0 = next(c for c in golden_extract_cases() if c["name"] == "rand07")
     ks = [k for k in g0["k_values"] if k <= 12]
     dev = torch.from_numpy(np.frombuffer(g0["fasta"], np.uint8).copy()).cuda()

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import golden_extract_cases
+from helpers import golden_dupk_cases, golden_extract_cases, golden_metadata_cases
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -32,6 +32,31 @@ def test_record_messages(case):
         else:
             got.append(f"Processed chromosome/contig: {rid}")
     assert got == want
+
+
+DUPK = golden_dupk_cases()
+
+
+@pytest.mark.parametrize("case", DUPK, ids=[c["name"] for c in DUPK])
+def test_duplicate_k_values_count_as_often(case):
+    """generate.py:36,49-58: one dict per distinct k, one counting pass per ENTRY of k_values."""
+    ks = case["k_values"]
+    ml = max(ks)
+    for k in dict.fromkeys(ks):
+        assert oracle.kmer_file_text(case["fasta"], k, ml, multiplicity=ks.count(k)) == case["files"][str(k)]
+
+
+def test_metadata_managers():
+    """genome_metadata.py:55-85 and kmer_metadata.py:59-78, fixtures written by the unmodified managers."""
+    cases, big = golden_metadata_cases()
+    assert len(cases) >= 18
+    for c in cases + big:
+        got = oracle.genome_stats(c["fasta"])
+        for key in ("contigs", "total_size", "n_count", "gc_content"):
+            assert got[key] == c["genome"][key], (c["name"], key)
+    for c in cases:
+        for k, want in c["kmers"].items():
+            assert oracle.kmer_file_stats(c["files"][k], int(k)) == want, (c["name"], k)
 
 
 def test_g0_survey_values():
