@@ -106,6 +106,10 @@ int kmerml_count_dense_range(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t n
  * Synchronous.
  */
 #define KMERML_FLAG_FREQ_ON_DEVICE 4u
+/* By default the count rows of k >= 10 cross PCIe as one byte per bin plus an exception list and are widened to
+ * uint32 in the caller's buffer by host threads (KMERML_HOST_THREADS, default half the cores, at most 16) while
+ * the next genomes are in flight; lossless.  This flag copies the uint32 rows as they are instead. */
+#define KMERML_FLAG_WIDE_D2H 16u
 int kmerml_count_dense_host(kmerml_ctx *ctx, const uint8_t *const *h_fasta, const uint64_t *h_sizes,
                             int n_genomes, const int *k_list, int nk, int min_record_len,
                             unsigned flags, uint32_t *h_counts, uint64_t counts_stride,

@@ -14,6 +14,7 @@ FLAG_CANONICAL = 1
 FLAG_NO_PARTITION = 2
 FLAG_FREQ_ON_DEVICE = 4
 FLAG_K8_AS_9 = 8
+FLAG_WIDE_D2H = 16
 MAX_DENSE_K = 14
 MAX_K = 32
 

@@ -12,12 +12,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkmerml_b200.so")
-SOURCES = ["api.cu", "dense.cu", "features.cu", "sparse.cu", "gram_tc.cu", "format.cu"]
+SOURCES = ["api.cu", "dense.cu", "features.cu", "sparse.cu", "gram_tc.cu", "format.cu", "hostpipe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
-    "-shared", "-cudart", "static",
+    "-shared", "-cudart", "static", "-Xcompiler", "-pthread",
 ]
 
 

@@ -1,11 +1,16 @@
 // api.cu -- the C-ABI of libkmerml_b200.so (include/kmerml_b200.h) and the host
 // orchestration of the dense counting path.  No torch types, no CPU fallback.
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "internal.h"
@@ -83,10 +88,12 @@ struct Workspace {
     cudaEvent_t staging_free = nullptr;
     // host-path slot buffers
     DevBuf fasta, counts, freq, totals;
+    DevBuf wire;        // narrow D2H: bytes of the levels k >= 10 | exception count | exception list
+    PinBuf wire_host;   // ... and its pinned host image
     cudaStream_t stream = nullptr;
     void release() {
         tables.release(); scratch.release(); part.release(); misc.release(); staging.release();
-        fasta.release(); counts.release(); freq.release(); totals.release();
+        fasta.release(); counts.release(); freq.release(); totals.release(); wire.release(); wire_host.release();
         if (staging_free) cudaEventDestroy(staging_free);
         if (stream) cudaStreamDestroy(stream);
         staging_free = nullptr;
@@ -106,6 +113,7 @@ struct kmerml_ctx {
     int sm_count = 148;
     km::Workspace ws[3];
     km::SparsePending sparse_pending;             // kmerml_count_sparse -> kmerml_sparse_fetch
+    km::HostPool* host_pool = nullptr;            // host threads that widen the narrow D2H format
     uint64_t max_group_payload = 12ull << 30;     // partition path: payload bytes one group of genomes may take
     // measurement hooks
     bool profiling = false;
@@ -542,6 +550,7 @@ int kmerml_ctx_destroy(kmerml_ctx* ctx) {
     DeviceGuard guard(ctx->device);
     cudaDeviceSynchronize();
     for (auto& w : ctx->ws) w.release();
+    if (ctx->host_pool) host_pool_destroy(ctx->host_pool);
     for (auto& r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->pool) cudaEventDestroy(e);
     delete ctx;
@@ -624,6 +633,65 @@ int kmerml_count_dense_range(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t n
                             range_end);
 }
 
+namespace {
+
+constexpr int NARROW_MIN_K = 10;                 // levels that cross the bus as one byte per bin
+constexpr uint32_t NARROW_EXC_CAP = 65536;       // exception list entries (bin, count) per genome
+constexpr size_t NARROW_CHUNK = 1u << 20;        // bins one host task widens
+
+struct HostSlot {                                // hand-over between the stream callback, the pool and the caller
+    std::mutex m;
+    std::condition_variable cv;
+    bool busy = false;                           // a genome's expansion is outstanding
+    bool overflow = false;                       // its exception list overflowed: the caller copies the row in full
+    std::atomic<int> remaining{0};
+    // the genome in the slot
+    const uint8_t* wire_host = nullptr;
+    uint32_t* row = nullptr;
+    km::NarrowSpec spec;
+    km::HostPool* pool = nullptr;
+};
+
+void slot_finish(HostSlot* sl) {                 // last task of a genome: exceptions, then the slot is free
+    const uint8_t* tail = sl->wire_host + sl->spec.total;
+    uint32_t n_exc;
+    memcpy(&n_exc, tail, 4);
+    bool over = n_exc > NARROW_EXC_CAP;
+    if (!over) {
+        const uint32_t* e = reinterpret_cast<const uint32_t*>(tail + 16);
+        for (uint32_t i = 0; i < n_exc; i++) sl->row[e[2 * i]] = e[2 * i + 1];
+    }
+    {
+        std::lock_guard<std::mutex> g(sl->m);
+        sl->overflow = over;
+        sl->busy = false;
+    }
+    sl->cv.notify_all();
+}
+
+void CUDART_CB slot_arrived(void* p) {           // stream callback: the genome's narrow block is in host memory
+    HostSlot* sl = static_cast<HostSlot*>(p);
+    int n_tasks = 0;
+    for (int i = 0; i < sl->spec.n; i++)
+        n_tasks += (int)((sl->spec.dst_off[i + 1] - sl->spec.dst_off[i] + NARROW_CHUNK - 1) / NARROW_CHUNK);
+    if (!n_tasks) { slot_finish(sl); return; }
+    sl->remaining.store(n_tasks);
+    for (int i = 0; i < sl->spec.n; i++) {
+        const size_t len = (size_t)(sl->spec.dst_off[i + 1] - sl->spec.dst_off[i]);
+        for (size_t c = 0; c < len; c += NARROW_CHUNK) {
+            const uint8_t* src = sl->wire_host + sl->spec.dst_off[i] + c;
+            uint32_t* dst = sl->row + sl->spec.src_off[i] + c;
+            const size_t n = std::min(NARROW_CHUNK, len - c);
+            km::host_pool_submit(sl->pool, [sl, src, dst, n] {
+                km::widen_u8_to_u32(src, dst, n);
+                if (sl->remaining.fetch_sub(1) == 1) slot_finish(sl);
+            });
+        }
+    }
+}
+
+}  // namespace
+
 int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, const uint64_t* h_sizes, int n_genomes,
                             const int* k_list, int nk, int min_record_len, unsigned flags, uint32_t* h_counts,
                             uint64_t counts_stride, float* freq, uint64_t freq_stride, uint64_t* h_totals) {
@@ -640,11 +708,36 @@ int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, cons
     const bool freq_dev = freq && (flags & KMERML_FLAG_FREQ_ON_DEVICE);
     const size_t row_len = (size_t)row.off[nk];
     const size_t row_stride = align_up(row_len, 4);
+    if (counts_stride < row_len) return fail(KMERML_ERR_ARG, "counts_stride must be >= row length");
     if (freq_dev && (((uintptr_t)freq & 15) || (freq_stride & 3) || freq_stride < row_len))
         return fail(KMERML_ERR_ARG, "device freq buffer must be 16-byte aligned with a stride multiple of 4");
+    // the levels k >= 10 cross the bus as bytes + exceptions (hostpipe.cu), the small ones as they are
+    NarrowSpec spec;
+    memset(&spec, 0, sizeof(spec));
+    if (!(flags & KMERML_FLAG_WIDE_D2H)) {
+        for (int i = 0; i < nk; i++) {
+            if (row.k[i] < NARROW_MIN_K) continue;
+            spec.src_off[spec.n] = row.off[i];
+            spec.dst_off[spec.n] = spec.total;
+            spec.total += 1ull << (2 * row.k[i]);
+            spec.n++;
+        }
+        spec.dst_off[spec.n] = spec.total;
+    }
+    const bool narrow = spec.n > 0;
+    const size_t wire_bytes = (size_t)spec.total + 16 + (size_t)NARROW_EXC_CAP * 8;
+    if (narrow && !ctx->host_pool) {
+        int n_thr = 0;
+        if (const char* e = getenv("KMERML_HOST_THREADS")) n_thr = atoi(e);
+        if (n_thr <= 0) n_thr = (int)std::min(16u, std::max(2u, std::thread::hardware_concurrency() / 2));
+        ctx->host_pool = host_pool_create(n_thr);
+        if (!ctx->host_pool) return fail(KMERML_ERR_NOMEM, "could not start the host thread pool");
+    }
     uint64_t max_bytes = 0;
     for (int g = 0; g < n_genomes; g++) max_bytes = std::max(max_bytes, h_sizes[g]);
     const int n_slots = std::min(3, n_genomes);
+    std::unique_ptr<HostSlot[]> slots(new (std::nothrow) HostSlot[3]);
+    if (!slots) return fail(KMERML_ERR_NOMEM, "out of host memory");
     for (int i = 0; i < n_slots; i++) {
         Workspace& w = ctx->ws[i];
         if (!w.stream) KM_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
@@ -652,24 +745,91 @@ int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, cons
         if ((rc = w.counts.ensure(row_stride * 4))) return rc;
         if (freq && !freq_dev && (rc = w.freq.ensure(row_stride * 4))) return rc;
         if ((rc = w.totals.ensure((size_t)nk * 8))) return rc;
+        if (narrow) {
+            if ((rc = w.wire.ensure(wire_bytes))) return rc;
+            if ((rc = w.wire_host.ensure(wire_bytes))) return rc;
+        }
     }
+    // every exit below first waits for the host tasks that still reference `slots`
+    auto wait_slot = [&](int si, int g_of_slot) -> int {
+        HostSlot& sl = slots[si];
+        std::unique_lock<std::mutex> lk(sl.m);
+        sl.cv.wait(lk, [&] { return !sl.busy; });
+        if (sl.overflow) {                       // more than NARROW_EXC_CAP bins >= 255: the row in full
+            sl.overflow = false;
+            lk.unlock();
+            KM_CUDA(cudaMemcpy(h_counts + (size_t)g_of_slot * counts_stride, ctx->ws[si].counts.p, row_len * 4,
+                               cudaMemcpyDeviceToHost));
+        }
+        return KMERML_OK;
+    };
+    auto drain = [&]() {
+        for (int i = 0; i < n_slots; i++) cudaStreamSynchronize(ctx->ws[i].stream);
+        for (int i = 0; i < n_slots; i++) {
+            std::unique_lock<std::mutex> lk(slots[i].m);
+            slots[i].cv.wait(lk, [&] { return !slots[i].busy; });
+        }
+    };
     for (int g = 0; g < n_genomes; g++) {
-        Workspace& w = ctx->ws[g % n_slots];
+        const int si = g % n_slots;
+        Workspace& w = ctx->ws[si];
         cudaStream_t s = w.stream;
-        if (h_sizes[g]) KM_CUDA(cudaMemcpyAsync(w.fasta.p, h_fasta[g], (size_t)h_sizes[g], cudaMemcpyHostToDevice, s));
+        if (narrow && g >= n_slots && (rc = wait_slot(si, g - n_slots))) { drain(); return rc; }
+        if (h_sizes[g]) {
+            cudaError_t e = cudaMemcpyAsync(w.fasta.p, h_fasta[g], (size_t)h_sizes[g], cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) { drain(); return cuda_fail(e, "cudaMemcpyAsync(fasta)"); }
+        }
         uint64_t offs[2] = {0, h_sizes[g]};
         float* d_f = !freq ? nullptr : (freq_dev ? freq + (size_t)g * freq_stride : (float*)w.freq.p);
         rc = count_dense_core(ctx, w, (const uint8_t*)w.fasta.p, offs, 1, k_list, nk, min_record_len,
-                              flags & ~KMERML_FLAG_FREQ_ON_DEVICE, (uint32_t*)w.counts.p, row_stride, d_f,
-                              freq_dev ? freq_stride : row_stride, (uint64_t*)w.totals.p, s);
-        if (rc) return rc;
-        KM_CUDA(cudaMemcpyAsync(h_counts + (size_t)g * counts_stride, w.counts.p, row_len * 4, cudaMemcpyDeviceToHost, s));
-        if (freq && !freq_dev)
-            KM_CUDA(cudaMemcpyAsync(freq + (size_t)g * freq_stride, w.freq.p, row_len * 4, cudaMemcpyDeviceToHost, s));
-        if (h_totals)
-            KM_CUDA(cudaMemcpyAsync(h_totals + (size_t)g * nk, w.totals.p, (size_t)nk * 8, cudaMemcpyDeviceToHost, s));
+                              flags & ~(KMERML_FLAG_FREQ_ON_DEVICE | KMERML_FLAG_WIDE_D2H), (uint32_t*)w.counts.p, row_stride,
+                              d_f, freq_dev ? freq_stride : row_stride, (uint64_t*)w.totals.p, s);
+        if (rc) { drain(); return rc; }
+        uint32_t* h_row = h_counts + (size_t)g * counts_stride;
+        cudaError_t e = cudaSuccess;
+        if (!narrow) {
+            e = cudaMemcpyAsync(h_row, w.counts.p, row_len * 4, cudaMemcpyDeviceToHost, s);
+        } else {
+            uint8_t* dw = (uint8_t*)w.wire.p;
+            rc = launch_narrow_levels((const uint32_t*)w.counts.p, spec, dw, dw + spec.total + 16,
+                                      (unsigned int*)(dw + spec.total), NARROW_EXC_CAP, s);
+            if (rc) { drain(); return rc; }
+            ctx->launches++;
+            for (int i = 0; i < nk && e == cudaSuccess; i++)
+                if (row.k[i] < NARROW_MIN_K)
+                    e = cudaMemcpyAsync(h_row + row.off[i], (uint32_t*)w.counts.p + row.off[i],
+                                        (size_t)(1ull << (2 * row.k[i])) * 4, cudaMemcpyDeviceToHost, s);
+            // bytes + exception count always; the list only as far as it is usually filled (a second copy
+            // would need the count first): 64 K entries = 512 KB
+            if (e == cudaSuccess) e = cudaMemcpyAsync(w.wire_host.p, dw, wire_bytes, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) {
+                HostSlot& sl = slots[si];
+                {
+                    std::lock_guard<std::mutex> lk(sl.m);
+                    sl.busy = true;
+                    sl.overflow = false;
+                }
+                sl.wire_host = (const uint8_t*)w.wire_host.p;
+                sl.row = h_row;
+                sl.spec = spec;
+                sl.pool = ctx->host_pool;
+                e = cudaLaunchHostFunc(s, slot_arrived, &sl);
+                if (e != cudaSuccess) {
+                    std::lock_guard<std::mutex> lk(sl.m);
+                    sl.busy = false;
+                }
+            }
+        }
+        if (e == cudaSuccess && freq && !freq_dev)
+            e = cudaMemcpyAsync(freq + (size_t)g * freq_stride, w.freq.p, row_len * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && h_totals)
+            e = cudaMemcpyAsync(h_totals + (size_t)g * nk, w.totals.p, (size_t)nk * 8, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) { drain(); return cuda_fail(e, "device -> host copy"); }
     }
     for (int i = 0; i < n_slots; i++) KM_CUDA(cudaStreamSynchronize(ctx->ws[i].stream));
+    if (narrow)
+        for (int g = std::max(0, n_genomes - n_slots); g < n_genomes; g++)
+            if ((rc = wait_slot(g % n_slots, g))) { drain(); return rc; }
     return KMERML_OK;
 }
 

@@ -1,0 +1,139 @@
+// hostpipe.cu -- the narrow device -> host wire format of kmerml_count_dense_host.
+//
+// The host-buffer call is bound by PCIe: a genome's k = 1..12 count row is 89.5 MB of uint32, of which the
+// 4^10 + 4^11 + 4^12 bins of k = 10..12 are 98 % -- and for a genome of a few ten megabases nearly all of those
+// counts fit one byte.  So the levels k >= 10 cross the bus as ONE BYTE per bin plus a short exception list
+// (bin, count) for the bins that reached 255 (narrow_levels_kernel); the small levels cross as they are.  A pool
+// of host threads widens the bytes into the caller's uint32 row (non-temporal stores) while the next genomes'
+// bytes and counts are on the bus.  Lossless: a genome whose exception list overflows is copied in full.
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
+#include "internal.h"
+
+namespace km {
+
+// ---------------------------------------------------------------- device side
+// 16 bins per thread: four 128-bit loads, one 128-bit store of the low bytes; bins >= 255 are written as 255
+// and listed (row-relative bin, count).
+__global__ void __launch_bounds__(256)
+narrow_levels_kernel(const uint32_t* __restrict__ counts, NarrowSpec spec, uint8_t* __restrict__ out,
+                     uint2* __restrict__ exc, unsigned int* __restrict__ exc_count, uint32_t exc_cap) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;        // 16-bin vector of the narrow part
+    if (v >= spec.total >> 4) return;
+    const uint64_t e = v << 4;
+    int seg = 0;
+    while (seg + 1 < spec.n && e >= spec.dst_off[seg + 1]) seg++;
+    const uint64_t src = spec.src_off[seg] + (e - spec.dst_off[seg]);
+    const uint4* p = reinterpret_cast<const uint4*>(counts + src);
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint4 c = __ldg(p + i);
+        const uint32_t x[4] = {c.x, c.y, c.z, c.w};
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t b = x[j];
+            if (b >= 255u) {
+                const unsigned int slot = atomicAdd(exc_count, 1u);
+                if (slot < exc_cap) exc[slot] = make_uint2((uint32_t)(src + 4 * i + j), b);
+                b = 255u;
+            }
+            packed |= b << (8 * j);
+        }
+        w[i] = packed;
+    }
+    *reinterpret_cast<uint4*>(out + e) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+int launch_narrow_levels(const uint32_t* d_counts, const NarrowSpec& spec, uint8_t* d_out, void* d_exc,
+                         unsigned int* d_exc_count, uint32_t exc_cap, cudaStream_t s) {
+    KM_CUDA(cudaMemsetAsync(d_exc_count, 0, 4, s));
+    if (!spec.total) return KMERML_OK;
+    const uint64_t vecs = spec.total >> 4;
+    narrow_levels_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, s>>>(d_counts, spec, d_out, (uint2*)d_exc, d_exc_count, exc_cap);
+    KM_CUDA(cudaGetLastError());
+    return KMERML_OK;
+}
+
+// ------------------------------------------------------------------ host side
+void widen_u8_to_u32(const uint8_t* src, uint32_t* dst, size_t n) {
+    size_t i = 0;
+#if defined(__x86_64__)
+    if ((((uintptr_t)dst) & 15) == 0) {
+        const __m128i zero = _mm_setzero_si128();
+        for (; i + 16 <= n; i += 16) {
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+            const __m128i lo = _mm_unpacklo_epi8(b, zero), hi = _mm_unpackhi_epi8(b, zero);
+            __m128i* d = reinterpret_cast<__m128i*>(dst + i);
+            _mm_stream_si128(d, _mm_unpacklo_epi16(lo, zero));          // non-temporal: the row is written once
+            _mm_stream_si128(d + 1, _mm_unpackhi_epi16(lo, zero));
+            _mm_stream_si128(d + 2, _mm_unpacklo_epi16(hi, zero));
+            _mm_stream_si128(d + 3, _mm_unpackhi_epi16(hi, zero));
+        }
+        _mm_sfence();
+    }
+#endif
+    for (; i < n; i++) dst[i] = src[i];
+}
+
+class HostPool {
+public:
+    explicit HostPool(int n) {
+        for (int i = 0; i < n; i++) workers_.emplace_back([this] { run(); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    void submit(std::function<void()> f) {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            q_.push_back(std::move(f));
+        }
+        cv_.notify_one();
+    }
+    int size() const { return (int)workers_.size(); }
+
+private:
+    void run() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                f = std::move(q_.front());
+                q_.pop_front();
+            }
+            f();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::deque<std::function<void()>> q_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
+HostPool* host_pool_create(int n_threads) { return new (std::nothrow) HostPool(n_threads); }
+void host_pool_destroy(HostPool* p) { delete p; }
+void host_pool_submit(HostPool* p, std::function<void()> f) { p->submit(std::move(f)); }
+int host_pool_size(const HostPool* p) { return p ? p->size() : 0; }
+
+}  // namespace km

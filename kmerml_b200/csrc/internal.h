@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <functional>
 #include <string>
 
 #include "../../include/kmerml_b200.h"
@@ -113,6 +114,22 @@ int launch_finalize_low(const LevelMap& lm, const RowSpec& row, int k_top, int l
 int launch_first_occurrence(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices,
                             int n_slices, int k, int min_rec, uint32_t* d_first, cudaStream_t s);
 int dense_setup_attributes();
+
+// ---- narrow device -> host wire format (hostpipe.cu) ---------------------------
+struct NarrowSpec {           // the levels that cross the bus as one byte per bin
+    int n;
+    unsigned long long src_off[16];   // element offset of the level inside the count row
+    unsigned long long dst_off[17];   // byte offset inside the narrow block; dst_off[n] = total
+    unsigned long long total;         // bins (= bytes) of the narrow block, a multiple of 16
+};
+int launch_narrow_levels(const uint32_t* d_counts, const NarrowSpec& spec, uint8_t* d_out, void* d_exc,
+                         unsigned int* d_exc_count, uint32_t exc_cap, cudaStream_t s);
+void widen_u8_to_u32(const uint8_t* src, uint32_t* dst, size_t n);
+class HostPool;
+HostPool* host_pool_create(int n_threads);
+void host_pool_destroy(HostPool* p);
+void host_pool_submit(HostPool* p, std::function<void()> f);
+int host_pool_size(const HostPool* p);
 
 // ---- sparse path (sparse.cu) ---------------------------------------------------
 struct SparseWork;

@@ -101,7 +101,7 @@ def count_dense_device(fasta, offsets, k_values, *, min_record_len=None, canonic
 
 def count_dense_host(buffers, k_values, *, min_record_len=None, canonical=False, want_freq=True,
                      device=None, out_counts=None, out_freq=None, out_totals=None, partition=True,
-                     freq_on_device=False):
+                     freq_on_device=False, wide_d2h=False):
     """End to end from host byte buffers (numpy uint8 arrays / pinned torch tensors): H2D,
     counting and D2H all inside libkmerml_b200.so.  Returns host (pinned) torch tensors; with
     freq_on_device the frequency rows stay in HBM (a CUDA tensor) for the distance / ML stage."""
@@ -140,6 +140,8 @@ def count_dense_host(buffers, k_values, *, min_record_len=None, canonical=False,
     totals = out_totals if out_totals is not None else torch.zeros((n, len(ks)), dtype=torch.int64, pin_memory=pin)
     karr = np.asarray(ks, dtype=np.int32)
     flags = _flags(canonical, partition) | (_lib.FLAG_FREQ_ON_DEVICE if (freq is not None and freq.is_cuda) else 0)
+    if wide_d2h:                     # uint32 rows over PCIe as they are (default: bytes + exceptions for k >= 10)
+        flags |= _lib.FLAG_WIDE_D2H
     _lib.check(L.kmerml_count_dense_host(
         ctx.handle, ptrs, sizes.ctypes.data, n, karr.ctypes.data, len(ks), int(min_record_len or 0),
         flags, counts.data_ptr(), counts.stride(0),

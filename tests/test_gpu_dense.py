@@ -141,6 +141,32 @@ def test_host_api_matches_device_api():
         assert torch.equal(dres.totals.cpu(), hres.totals)
 
 
+def test_host_api_narrow_wire_format():
+    """The count rows of k >= 10 cross PCIe as bytes + an exception list and are widened on the host: same rows
+    as the plain uint32 copy, also when the exception list overflows (> 65536 bins at or above 255) and for more
+    genomes than pipeline slots."""
+    torch = torch_mod()
+    from kmerml_b200 import engine
+    from kmerml_b200 import synth
+    rng = np.random.default_rng(8)
+    unit = "".join("ACGT"[i] for i in rng.integers(0, 4, 90_000))
+    body = unit * 260                                                         # ~86 000 distinct 10-mers, 260 times each
+    tandem = (">t\n" + body + "\n").encode()                                  # one unwrapped line, 23 Mbp
+    wrapped = (">w\n" + "\n".join(body[i:i + 80] for i in range(0, len(body), 80)) + "\n").encode()
+    mid = synth.fasta_bytes([400_000, 30], seed=21).tobytes()
+    datas = [mid, tandem, synth.fasta_bytes([150_000], seed=22).tobytes(), wrapped, b">e\n",
+             synth.fasta_bytes([90_000], seed=23).tobytes(), mid]
+    for ks in ([10], [12, 3, 10], [11, 8]):
+        narrow = engine.count_dense_host(datas, ks, want_freq=False)
+        wide = engine.count_dense_host(datas, ks, want_freq=False, wide_d2h=True)
+        dres = gpu_counts(datas, ks)
+        assert torch.equal(narrow.counts, wide.counts), ks
+        assert torch.equal(narrow.totals, wide.totals)
+        assert torch.equal(narrow.counts, dres.counts.cpu())
+    big = (narrow.counts.to(torch.int64) & 0xFFFFFFFF)
+    assert int((big[1] >= 255).sum()) > 65536            # the tandem genome did overflow the exception list
+
+
 def test_argument_errors():
     torch = torch_mod()
     from kmerml_b200 import _lib, engine
