@@ -110,10 +110,31 @@ int kmerml_count_dense_range(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t n
  * uint32 in the caller's buffer by host threads (KMERML_HOST_THREADS, default half the cores, at most 16) while
  * the next genomes are in flight; lossless.  This flag copies the uint32 rows as they are instead. */
 #define KMERML_FLAG_WIDE_D2H 16u
+/* Number of host threads that widen the narrow format (one process per GPU: cores / ranks on the host). */
+int kmerml_ctx_set_host_threads(kmerml_ctx *ctx, int n_threads);
 int kmerml_count_dense_host(kmerml_ctx *ctx, const uint8_t *const *h_fasta, const uint64_t *h_sizes,
                             int n_genomes, const int *k_list, int nk, int min_record_len,
                             unsigned flags, uint32_t *h_counts, uint64_t counts_stride,
                             float *freq, uint64_t freq_stride, uint64_t *h_totals);
+
+/*
+ * The same call with the result left in the form it crosses PCIe in: per genome one row of
+ * kmerml_compact_row_bytes(k_list, nk) bytes (stride a multiple of 16):
+ *     [ one byte per bin of every k >= 10, in k_list order | exception count (uint32, padded to 16 bytes) |
+ *       65536 x (row-relative bin, count) uint32 pairs for the bins that reached 255 |
+ *       the uint32 rows of every k < 10, in k_list order ]
+ * Lossless unless the exception count exceeds 65536 (a genome with that many k-mers seen 255+ times:
+ * kmerml_compact_expand reports it; count that genome with kmerml_count_dense_host).  Four times fewer bytes
+ * cross the bus and none is rewritten by the host; kmerml_compact_expand widens one k of one genome on demand
+ * (pure host code, no GPU).  The host memory of this pool's boxes takes writes at ~60 GB/s, which is what bounds
+ * the uint32 variant above.
+ */
+uint64_t kmerml_compact_row_bytes(const int *k_list, int nk);
+int kmerml_count_dense_host_compact(kmerml_ctx *ctx, const uint8_t *const *h_fasta, const uint64_t *h_sizes,
+                                    int n_genomes, const int *k_list, int nk, int min_record_len,
+                                    unsigned flags, uint8_t *h_rows, uint64_t row_stride_bytes, float *freq,
+                                    uint64_t freq_stride, uint64_t *h_totals);
+int kmerml_compact_expand(const int *k_list, int nk, const uint8_t *h_row, int ki, uint32_t *h_out);
 
 /*
  * Sparse counting for 15 <= k <= 32 (any k >= 1 is accepted): the distinct k-mers of ONE genome as
@@ -238,6 +259,23 @@ int kmerml_normalize_rows(kmerml_ctx *ctx, const uint32_t *d_counts, uint64_t co
 #define KMERML_METRIC_EUCLIDEAN 1
 int kmerml_pairwise_distance(kmerml_ctx *ctx, const void *d_x, int dtype, uint64_t stride, int n,
                              uint64_t m, int metric, float *d_out32, double *d_out64, void *stream);
+
+/*
+ * Summary of one k's count row as kmerml/utils/kmer_metadata.py:59-78 reports it for a k{k}.txt file (the
+ * OBSERVED k-mers only): d_out uint64[8] = total_kmers, unique_kmers, max_count, min_count, the lower and the
+ * upper middle count (their mean is the median; equal for an odd number), 0, 0.  No observed k-mer: total =
+ * unique = max = 0, min = 2^64 - 1.  The median is an exact three-pass radix select, not a sort.
+ */
+int kmerml_count_stats(kmerml_ctx *ctx, const uint32_t *d_counts, uint64_t n_bins, uint64_t *d_out, void *stream);
+
+/*
+ * Per column of an n_rows x m feature matrix (dtype as in kmerml_pairwise_distance): rows with a non-zero entry,
+ * mean and population variance in float64 -- the reductions behind filter_features(min_prevalence, min_variance)
+ * and get_top_features(n, "variance"), the calls tests/test_ml.py:9-12 of the reference makes to methods its
+ * kmerml/ml/features.py does not define.
+ */
+int kmerml_column_stats(kmerml_ctx *ctx, const void *d_x, int dtype, uint64_t stride, int n_rows, uint64_t m,
+                        uint32_t *d_nnz, double *d_mean, double *d_var, void *stream);
 
 /*
  * Rows [row_begin, row_end) of that matrix for uint32 count rows (m a multiple of 64): the block one

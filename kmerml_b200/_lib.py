@@ -48,10 +48,15 @@ def load():
     L.kmerml_ctx_create.argtypes = [i32, ctypes.POINTER(vp)]
     L.kmerml_ctx_destroy.argtypes = [vp]
     L.kmerml_ctx_sm_count.argtypes = [vp]
+    L.kmerml_ctx_set_host_threads.argtypes = [vp, i32]
     L.kmerml_row_len.restype = u64
     L.kmerml_row_len.argtypes = [vp, i32]
     L.kmerml_count_dense_batch.argtypes = [vp, vp, vp, i32, vp, i32, i32, u32, vp, u64, vp, u64, vp, vp]
     L.kmerml_count_dense_host.argtypes = [vp, vp, vp, i32, vp, i32, i32, u32, vp, u64, vp, u64, vp]
+    L.kmerml_compact_row_bytes.restype = u64
+    L.kmerml_compact_row_bytes.argtypes = [vp, i32]
+    L.kmerml_count_dense_host_compact.argtypes = [vp, vp, vp, i32, vp, i32, i32, u32, vp, u64, vp, u64, vp]
+    L.kmerml_compact_expand.argtypes = [vp, i32, vp, i32, vp]
     L.kmerml_count_dense_range.argtypes = [vp, vp, u64, u64, u64, vp, i32, i32, u32, vp, vp, vp]
     L.kmerml_count_sparse.argtypes = [vp, vp, u64, i32, i32, u32, vp, vp, vp, u64, ctypes.POINTER(ctypes.c_uint64),
                                       ctypes.POINTER(ctypes.c_uint64), vp]
@@ -66,6 +71,8 @@ def load():
     p64 = ctypes.POINTER(ctypes.c_uint64)
     L.kmerml_format_kmer_file.argtypes = [vp, i32, vp, vp, u32, u64, vp, u64, p64, p64, vp]
     L.kmerml_format_kmer_lines.argtypes = [vp, i32, vp, vp, u64, vp, u64, p64, vp]
+    L.kmerml_count_stats.argtypes = [vp, vp, u64, vp, vp]
+    L.kmerml_column_stats.argtypes = [vp, vp, i32, u64, i32, u64, vp, vp, vp, vp]
     L.kmerml_static_features.argtypes = [vp, i32, i32, vp, vp]
     L.kmerml_normalize_rows.argtypes = [vp, vp, u64, vp, i32, u64, vp, u64, vp]
     L.kmerml_pairwise_distance.argtypes = [vp, vp, i32, u64, i32, u64, i32, vp, vp, vp]
@@ -88,7 +95,8 @@ EXPORTS = [
     "kmerml_profile_read", "kmerml_find_records", "kmerml_records_short", "kmerml_static_features",
     "kmerml_normalize_rows", "kmerml_pairwise_distance", "kmerml_count_dense_range",
     "kmerml_count_sparse", "kmerml_genome_stats", "kmerml_format_kmer_file", "kmerml_format_kmer_lines",
-    "kmerml_count_sparse_range", "kmerml_merge_sparse", "kmerml_pairwise_distance_rows", "kmerml_sparse_fetch",
+    "kmerml_count_sparse_range", "kmerml_merge_sparse", "kmerml_pairwise_distance_rows", "kmerml_sparse_fetch", "kmerml_ctx_set_host_threads", "kmerml_count_stats", "kmerml_column_stats",
+    "kmerml_compact_row_bytes", "kmerml_count_dense_host_compact", "kmerml_compact_expand",
 ]
 
 
@@ -116,6 +124,10 @@ class Context:
     @property
     def sm_count(self):
         return self._lib.kmerml_ctx_sm_count(self.handle)
+
+    def set_host_threads(self, n):
+        """Host threads that widen the narrow D2H format of count_dense_host (default: half the cores, <= 16)."""
+        check(self._lib.kmerml_ctx_set_host_threads(self.handle, int(n)))
 
     def profile_enable(self, on=True):
         check(self._lib.kmerml_profile_enable(self.handle, 1 if on else 0))

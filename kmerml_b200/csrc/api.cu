@@ -559,6 +559,16 @@ int kmerml_ctx_destroy(kmerml_ctx* ctx) {
 
 int kmerml_ctx_sm_count(const kmerml_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
+int kmerml_ctx_set_host_threads(kmerml_ctx* ctx, int n_threads) {
+    if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
+    if (n_threads < 1 || n_threads > 256) return fail(KMERML_ERR_ARG, "n_threads must be in 1..256");
+    if (ctx->host_pool && host_pool_size(ctx->host_pool) == n_threads) return KMERML_OK;
+    if (ctx->host_pool) host_pool_destroy(ctx->host_pool);
+    ctx->host_pool = host_pool_create(n_threads);
+    if (!ctx->host_pool) return fail(KMERML_ERR_NOMEM, "could not start the host thread pool");
+    return KMERML_OK;
+}
+
 int kmerml_profile_enable(kmerml_ctx* ctx, int on) {
     if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
     ctx->profiling = on != 0;
@@ -692,13 +702,17 @@ void CUDART_CB slot_arrived(void* p) {           // stream callback: the genome'
 
 }  // namespace
 
-int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, const uint64_t* h_sizes, int n_genomes,
-                            const int* k_list, int nk, int min_record_len, unsigned flags, uint32_t* h_counts,
-                            uint64_t counts_stride, float* freq, uint64_t freq_stride, uint64_t* h_totals) {
+// compact_rows != nullptr: the narrow block, the exception count + list and the small levels are delivered as
+// they crossed the bus (kmerml_count_dense_host_compact), one row of `compact_stride` bytes per genome.
+static int count_dense_host_impl(kmerml_ctx* ctx, const uint8_t* const* h_fasta, const uint64_t* h_sizes, int n_genomes,
+                                 const int* k_list, int nk, int min_record_len, unsigned flags, uint32_t* h_counts,
+                                 uint64_t counts_stride, float* freq, uint64_t freq_stride, uint64_t* h_totals,
+                                 uint8_t* compact_rows, uint64_t compact_stride) {
     if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
     if (n_genomes < 0) return fail(KMERML_ERR_ARG, "n_genomes < 0");
     if (n_genomes == 0) return KMERML_OK;
-    if (!h_fasta || !h_sizes || !h_counts) return fail(KMERML_ERR_ARG, "null pointer argument");
+    const bool compact = compact_rows != nullptr;
+    if (!h_fasta || !h_sizes || (!h_counts && !compact)) return fail(KMERML_ERR_ARG, "null pointer argument");
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     RowSpec row;
@@ -708,13 +722,13 @@ int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, cons
     const bool freq_dev = freq && (flags & KMERML_FLAG_FREQ_ON_DEVICE);
     const size_t row_len = (size_t)row.off[nk];
     const size_t row_stride = align_up(row_len, 4);
-    if (counts_stride < row_len) return fail(KMERML_ERR_ARG, "counts_stride must be >= row length");
+    if (!compact && counts_stride < row_len) return fail(KMERML_ERR_ARG, "counts_stride must be >= row length");
     if (freq_dev && (((uintptr_t)freq & 15) || (freq_stride & 3) || freq_stride < row_len))
         return fail(KMERML_ERR_ARG, "device freq buffer must be 16-byte aligned with a stride multiple of 4");
     // the levels k >= 10 cross the bus as bytes + exceptions (hostpipe.cu), the small ones as they are
     NarrowSpec spec;
     memset(&spec, 0, sizeof(spec));
-    if (!(flags & KMERML_FLAG_WIDE_D2H)) {
+    if (compact || !(flags & KMERML_FLAG_WIDE_D2H)) {
         for (int i = 0; i < nk; i++) {
             if (row.k[i] < NARROW_MIN_K) continue;
             spec.src_off[spec.n] = row.off[i];
@@ -724,9 +738,11 @@ int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, cons
         }
         spec.dst_off[spec.n] = spec.total;
     }
-    const bool narrow = spec.n > 0;
+    const bool narrow = spec.n > 0 || compact;
     const size_t wire_bytes = (size_t)spec.total + 16 + (size_t)NARROW_EXC_CAP * 8;
-    if (narrow && !ctx->host_pool) {
+    if (compact && compact_stride < kmerml_compact_row_bytes(k_list, nk))
+        return fail(KMERML_ERR_ARG, "compact row stride smaller than kmerml_compact_row_bytes");
+    if (narrow && !compact && !ctx->host_pool) {
         int n_thr = 0;
         if (const char* e = getenv("KMERML_HOST_THREADS")) n_thr = atoi(e);
         if (n_thr <= 0) n_thr = (int)std::min(16u, std::max(2u, std::thread::hardware_concurrency() / 2));
@@ -747,7 +763,7 @@ int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, cons
         if ((rc = w.totals.ensure((size_t)nk * 8))) return rc;
         if (narrow) {
             if ((rc = w.wire.ensure(wire_bytes))) return rc;
-            if ((rc = w.wire_host.ensure(wire_bytes))) return rc;
+            if (!compact && (rc = w.wire_host.ensure(wire_bytes))) return rc;
         }
     }
     // every exit below first waits for the host tasks that still reference `slots`
@@ -774,7 +790,7 @@ int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, cons
         const int si = g % n_slots;
         Workspace& w = ctx->ws[si];
         cudaStream_t s = w.stream;
-        if (narrow && g >= n_slots && (rc = wait_slot(si, g - n_slots))) { drain(); return rc; }
+        if (narrow && !compact && g >= n_slots && (rc = wait_slot(si, g - n_slots))) { drain(); return rc; }
         if (h_sizes[g]) {
             cudaError_t e = cudaMemcpyAsync(w.fasta.p, h_fasta[g], (size_t)h_sizes[g], cudaMemcpyHostToDevice, s);
             if (e != cudaSuccess) { drain(); return cuda_fail(e, "cudaMemcpyAsync(fasta)"); }
@@ -785,9 +801,25 @@ int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, cons
                               flags & ~(KMERML_FLAG_FREQ_ON_DEVICE | KMERML_FLAG_WIDE_D2H), (uint32_t*)w.counts.p, row_stride,
                               d_f, freq_dev ? freq_stride : row_stride, (uint64_t*)w.totals.p, s);
         if (rc) { drain(); return rc; }
-        uint32_t* h_row = h_counts + (size_t)g * counts_stride;
+        uint32_t* h_row = compact ? nullptr : h_counts + (size_t)g * counts_stride;
         cudaError_t e = cudaSuccess;
-        if (!narrow) {
+        if (compact) {
+            // [narrow bytes | exception count (16 B) | exception list | the small levels, uint32, in k_list order]
+            uint8_t* dw = (uint8_t*)w.wire.p;
+            uint8_t* hrow = compact_rows + (size_t)g * compact_stride;
+            rc = launch_narrow_levels((const uint32_t*)w.counts.p, spec, dw, dw + spec.total + 16,
+                                      (unsigned int*)(dw + spec.total), NARROW_EXC_CAP, s);
+            if (rc) { drain(); return rc; }
+            ctx->launches++;
+            e = cudaMemcpyAsync(hrow, dw, wire_bytes, cudaMemcpyDeviceToHost, s);
+            size_t small = wire_bytes;
+            for (int i = 0; i < nk && e == cudaSuccess; i++) {
+                if (row.k[i] >= NARROW_MIN_K) continue;
+                const size_t nb = (size_t)(1ull << (2 * row.k[i])) * 4;
+                e = cudaMemcpyAsync(hrow + small, (uint32_t*)w.counts.p + row.off[i], nb, cudaMemcpyDeviceToHost, s);
+                small += nb;
+            }
+        } else if (!narrow) {
             e = cudaMemcpyAsync(h_row, w.counts.p, row_len * 4, cudaMemcpyDeviceToHost, s);
         } else {
             uint8_t* dw = (uint8_t*)w.wire.p;
@@ -827,9 +859,63 @@ int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, cons
         if (e != cudaSuccess) { drain(); return cuda_fail(e, "device -> host copy"); }
     }
     for (int i = 0; i < n_slots; i++) KM_CUDA(cudaStreamSynchronize(ctx->ws[i].stream));
-    if (narrow)
+    if (narrow && !compact)
         for (int g = std::max(0, n_genomes - n_slots); g < n_genomes; g++)
             if ((rc = wait_slot(g % n_slots, g))) { drain(); return rc; }
+    return KMERML_OK;
+}
+
+int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, const uint64_t* h_sizes, int n_genomes,
+                            const int* k_list, int nk, int min_record_len, unsigned flags, uint32_t* h_counts,
+                            uint64_t counts_stride, float* freq, uint64_t freq_stride, uint64_t* h_totals) {
+    return count_dense_host_impl(ctx, h_fasta, h_sizes, n_genomes, k_list, nk, min_record_len, flags, h_counts,
+                                 counts_stride, freq, freq_stride, h_totals, nullptr, 0);
+}
+
+uint64_t kmerml_compact_row_bytes(const int* k_list, int nk) {
+    uint64_t narrow = 0, small = 0;
+    for (int i = 0; k_list && i < nk; i++) {
+        if (k_list[i] < 1 || k_list[i] > KMERML_MAX_DENSE_K) return 0;
+        if (k_list[i] >= NARROW_MIN_K) narrow += 1ull << (2 * k_list[i]);
+        else small += (1ull << (2 * k_list[i])) * 4;
+    }
+    return narrow + 16 + (uint64_t)NARROW_EXC_CAP * 8 + small;
+}
+
+int kmerml_count_dense_host_compact(kmerml_ctx* ctx, const uint8_t* const* h_fasta, const uint64_t* h_sizes,
+                                    int n_genomes, const int* k_list, int nk, int min_record_len, unsigned flags,
+                                    uint8_t* h_rows, uint64_t row_stride_bytes, float* freq, uint64_t freq_stride,
+                                    uint64_t* h_totals) {
+    if (!h_rows) return fail(KMERML_ERR_ARG, "h_rows is null");
+    if (row_stride_bytes & 15) return fail(KMERML_ERR_ARG, "row_stride_bytes must be a multiple of 16");
+    return count_dense_host_impl(ctx, h_fasta, h_sizes, n_genomes, k_list, nk, min_record_len, flags, nullptr, 0, freq,
+                                 freq_stride, h_totals, h_rows, row_stride_bytes);
+}
+
+int kmerml_compact_expand(const int* k_list, int nk, const uint8_t* h_row, int ki, uint32_t* h_out) {
+    if (!k_list || !h_row || !h_out || ki < 0 || ki >= nk) return fail(KMERML_ERR_ARG, "bad argument");
+    if (!kmerml_compact_row_bytes(k_list, nk)) return fail(KMERML_ERR_ARG, "dense k out of range");
+    uint64_t narrow_total = 0, row_off = 0, my_row_off = 0, my_narrow_off = 0, my_small_off = 0, small = 0;
+    for (int i = 0; i < nk; i++) {
+        const uint64_t n = 1ull << (2 * k_list[i]);
+        if (i == ki) { my_row_off = row_off; my_narrow_off = narrow_total; my_small_off = small; }
+        if (k_list[i] >= NARROW_MIN_K) narrow_total += n; else small += n * 4;
+        row_off += n;
+    }
+    const uint64_t n = 1ull << (2 * k_list[ki]);
+    const uint8_t* tail = h_row + narrow_total;
+    if (k_list[ki] < NARROW_MIN_K) {
+        memcpy(h_out, tail + 16 + (size_t)NARROW_EXC_CAP * 8 + my_small_off, (size_t)n * 4);
+        return KMERML_OK;
+    }
+    uint32_t n_exc;
+    memcpy(&n_exc, tail, 4);
+    if (n_exc > NARROW_EXC_CAP)
+        return fail(KMERML_ERR_RANGE, "this genome's exception list overflowed: count it with kmerml_count_dense_host");
+    widen_u8_to_u32(h_row + my_narrow_off, h_out, (size_t)n);
+    const uint32_t* e = reinterpret_cast<const uint32_t*>(tail + 16);
+    for (uint32_t i = 0; i < n_exc; i++)
+        if (e[2 * i] >= my_row_off && e[2 * i] < my_row_off + n) h_out[e[2 * i] - my_row_off] = e[2 * i + 1];
     return KMERML_OK;
 }
 
@@ -894,6 +980,25 @@ int kmerml_genome_stats(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     return launch_genome_stats(d_fasta, nbytes, (unsigned long long*)d_out, (cudaStream_t)stream);
+}
+
+int kmerml_count_stats(kmerml_ctx* ctx, const uint32_t* d_counts, uint64_t n_bins, uint64_t* d_out, void* stream) {
+    if (!ctx || !d_out || (n_bins && !d_counts)) return fail(KMERML_ERR_ARG, "null pointer argument");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    Workspace& ws = ctx->ws[0];
+    int rc = ws.misc.ensure(count_stats_workspace());
+    if (rc) return rc;
+    return launch_count_stats(d_counts, n_bins, ws.misc.p, (unsigned long long*)d_out, (cudaStream_t)stream);
+}
+
+int kmerml_column_stats(kmerml_ctx* ctx, const void* d_x, int dtype, uint64_t stride, int n_rows, uint64_t m,
+                        uint32_t* d_nnz, double* d_mean, double* d_var, void* stream) {
+    if (!ctx || (m && (!d_x || !d_nnz || !d_mean || !d_var))) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (dtype < 0 || dtype > 2 || n_rows < 0 || stride < m) return fail(KMERML_ERR_ARG, "bad dtype / shape");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    return launch_column_stats(d_x, dtype, stride, n_rows, m, d_nnz, d_mean, d_var, (cudaStream_t)stream);
 }
 
 int kmerml_static_features(kmerml_ctx* ctx, int k, int compat, int32_t* d_out, void* stream) {

@@ -131,6 +131,12 @@ void host_pool_destroy(HostPool* p);
 void host_pool_submit(HostPool* p, std::function<void()> f);
 int host_pool_size(const HostPool* p);
 
+// ---- reductions (stats.cu) ------------------------------------------------------
+size_t count_stats_workspace();
+int launch_count_stats(const uint32_t* d_counts, uint64_t n_bins, void* workspace, unsigned long long* d_out, cudaStream_t s);
+int launch_column_stats(const void* d_x, int dtype, uint64_t stride, int n_rows, uint64_t m, uint32_t* d_nnz,
+                        double* d_mean, double* d_var, cudaStream_t s);
+
 // ---- sparse path (sparse.cu) ---------------------------------------------------
 struct SparseWork;
 struct SparsePending {        // the reduced result of the last sparse count, still in the workspace (kmerml_sparse_fetch)

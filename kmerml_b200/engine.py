@@ -99,9 +99,42 @@ def count_dense_device(fasta, offsets, k_values, *, min_record_len=None, canonic
     return DenseResult(ks, counts, freq, totals)
 
 
+class CompactDenseResult:
+    """Host result of count_dense_host(..., compact=True): the count rows as they crossed PCIe (one byte per bin
+    for k >= 10 plus an exception list, uint32 for k < 10; include/kmerml_b200.h, kmerml_count_dense_host_compact).
+    Lossless; counts_numpy(g, k) widens one k of one genome on demand (host code of the library)."""
+
+    def __init__(self, k_list, rows, freq, totals, overflow_rows):
+        self.k_list, self.rows, self.freq, self.totals = k_list, rows, freq, totals
+        self._wide = overflow_rows                       # {genome: uint32 row} for genomes whose exception list overflowed
+
+    def counts_numpy(self, g, k):
+        lay, _ = row_layout(self.k_list)
+        off, n = lay[k]
+        if g in self._wide:
+            return self._wide[g][off:off + n]
+        out = np.empty(n, dtype=np.uint32)
+        karr = np.asarray(self.k_list, dtype=np.int32)
+        row = self.rows[g]
+        _lib.check(_lib.load().kmerml_compact_expand(karr.ctypes.data, len(self.k_list), row.data_ptr(),
+                                                     self.k_list.index(k), out.ctypes.data))
+        return out
+
+    def counts_tensor(self):
+        """[n_genomes, row_len] int32 tensor (uint32 storage) of all rows, widened (what count_dense_host returns)."""
+        _, row_len = row_layout(self.k_list)
+        out = np.empty((self.rows.shape[0], row_len), dtype=np.uint32)
+        lay, _ = row_layout(self.k_list)
+        for g in range(self.rows.shape[0]):
+            for k in self.k_list:
+                off, n = lay[k]
+                out[g, off:off + n] = self.counts_numpy(g, k)
+        return torch.from_numpy(out.view(np.int32))
+
+
 def count_dense_host(buffers, k_values, *, min_record_len=None, canonical=False, want_freq=True,
                      device=None, out_counts=None, out_freq=None, out_totals=None, partition=True,
-                     freq_on_device=False, wide_d2h=False):
+                     freq_on_device=False, wide_d2h=False, compact=False, out_rows=None):
     """End to end from host byte buffers (numpy uint8 arrays / pinned torch tensors): H2D,
     counting and D2H all inside libkmerml_b200.so.  Returns host (pinned) torch tensors; with
     freq_on_device the frequency rows stay in HBM (a CUDA tensor) for the distance / ML stage."""
@@ -127,7 +160,12 @@ def count_dense_host(buffers, k_values, *, min_record_len=None, canonical=False,
             ptrs[i] = a.ctypes.data if a.size else None
             sizes[i] = a.size
     pin = True
-    counts = out_counts if out_counts is not None else torch.empty((n, row_len), dtype=torch.int32, pin_memory=pin)
+    karr = np.asarray(ks, dtype=np.int32)
+    if compact:
+        row_bytes = int(L.kmerml_compact_row_bytes(karr.ctypes.data, len(ks)))
+        counts = out_rows if out_rows is not None else torch.empty((n, row_bytes), dtype=torch.uint8, pin_memory=pin)
+    else:
+        counts = out_counts if out_counts is not None else torch.empty((n, row_len), dtype=torch.int32, pin_memory=pin)
     freq = None
     if want_freq:
         if out_freq is not None:
@@ -138,10 +176,26 @@ def count_dense_host(buffers, k_values, *, min_record_len=None, canonical=False,
         else:
             freq = torch.empty((n, row_len), dtype=torch.float32, pin_memory=pin)
     totals = out_totals if out_totals is not None else torch.zeros((n, len(ks)), dtype=torch.int64, pin_memory=pin)
-    karr = np.asarray(ks, dtype=np.int32)
     flags = _flags(canonical, partition) | (_lib.FLAG_FREQ_ON_DEVICE if (freq is not None and freq.is_cuda) else 0)
     if wide_d2h:                     # uint32 rows over PCIe as they are (default: bytes + exceptions for k >= 10)
         flags |= _lib.FLAG_WIDE_D2H
+    if compact:
+        _lib.check(L.kmerml_count_dense_host_compact(
+            ctx.handle, ptrs, sizes.ctypes.data, n, karr.ctypes.data, len(ks), int(min_record_len or 0),
+            flags, counts.data_ptr(), counts.stride(0),
+            freq.data_ptr() if freq is not None else None, freq.stride(0) if freq is not None else 0,
+            totals.data_ptr()))
+        # genomes whose exception list overflowed (> 65536 bins at 255 or more): counted again, uint32 rows
+        narrow_total = sum(4 ** k for k in ks if k >= 10)
+        n_exc = counts[:, narrow_total:narrow_total + 4].contiguous().view(torch.int32)[:, 0]
+        over = [g for g in range(n) if int(n_exc[g]) > 65536 or int(n_exc[g]) < 0]
+        wide = {}
+        if over:
+            sub = count_dense_host([buffers[g] for g in over], ks, min_record_len=min_record_len, canonical=canonical,
+                                   want_freq=False, device=device, partition=partition, wide_d2h=True)
+            for j, g in enumerate(over):
+                wide[g] = sub.counts[j].numpy().view(np.uint32)
+        return CompactDenseResult(ks, counts, freq, totals, wide)
     _lib.check(L.kmerml_count_dense_host(
         ctx.handle, ptrs, sizes.ctypes.data, n, karr.ctypes.data, len(ks), int(min_record_len or 0),
         flags, counts.data_ptr(), counts.stride(0),
@@ -347,19 +401,35 @@ def genome_stats_device(fasta):
 
 def kmer_count_stats_device(counts_row, k):
     """Summary of one k's count vector (int32 storage of uint32) as kmerml/utils/kmer_metadata.py:59-78 reports
-    it for a k{k}.txt file: totals over the OBSERVED k-mers."""
-    c = counts_row.to(torch.int64) & 0xFFFFFFFF
-    obs = c[c > 0]
-    if obs.numel() == 0:
+    it for a k{k}.txt file: totals over the OBSERVED k-mers.  Reduction + radix-select kernels
+    (kmerml_count_stats), one small device -> host read."""
+    ctx = _lib.context(counts_row.device.index)
+    row = counts_row.contiguous()
+    out = torch.empty(8, dtype=torch.int64, device=row.device)
+    stream = torch.cuda.current_stream(row.device).cuda_stream
+    _lib.check(_lib.load().kmerml_count_stats(ctx.handle, row.data_ptr(), row.numel(), out.data_ptr(), ctypes.c_void_p(stream)))
+    total, n, mx, mn, lo, hi = (int(v) for v in out[:6].cpu().tolist())
+    if n == 0:
         return {"k_value": k, "total_kmers": 0, "unique_kmers": 0, "max_count": 0, "min_count": 0,
                 "mean_count": float("nan"), "median_count": float("nan"), "estimated_genome_size": k - 1}
-    srt = torch.sort(obs).values
-    n = srt.numel()
-    median = float(srt[n // 2].item()) if n % 2 else (float(srt[n // 2 - 1].item()) + float(srt[n // 2].item())) / 2.0
-    total = int(obs.sum().item())
-    return {"k_value": k, "total_kmers": total, "unique_kmers": int(n), "max_count": int(srt[-1].item()),
-            "min_count": int(srt[0].item()), "mean_count": total / n, "median_count": median,
-            "estimated_genome_size": total + k - 1}
+    return {"k_value": k, "total_kmers": total, "unique_kmers": n, "max_count": mx, "min_count": mn,
+            "mean_count": total / n, "median_count": (float(lo) + float(hi)) / 2.0, "estimated_genome_size": total + k - 1}
+
+
+def column_stats_device(x):
+    """(rows with a non-zero entry int32[m], mean float64[m], population variance float64[m]) of the columns of a
+    2-D CUDA tensor (float32 / float64 / int32 storage of uint32 counts)."""
+    if x.dtype not in _DTYPE_CODE or not x.is_cuda or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be a 2-D CUDA tensor (float32 / float64 / int32) with contiguous rows")
+    ctx = _lib.context(x.device.index)
+    n, m = x.shape
+    nnz = torch.empty(m, dtype=torch.int32, device=x.device)
+    mean = torch.empty(m, dtype=torch.float64, device=x.device)
+    var = torch.empty(m, dtype=torch.float64, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(_lib.load().kmerml_column_stats(ctx.handle, x.data_ptr(), _DTYPE_CODE[x.dtype], x.stride(0), n, m,
+                                               nnz.data_ptr(), mean.data_ptr(), var.data_ptr(), ctypes.c_void_p(stream)))
+    return nnz, mean, var
 
 
 def format_kmer_file_device(counts_row, first, k, *, canonical=False):

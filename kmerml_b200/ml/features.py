@@ -126,19 +126,31 @@ class KmerFeatureBuilder:
         d = engine.pairwise_distance_device(x, metric, out_dtype=torch.float64)
         return pd.DataFrame(d.cpu().numpy(), index=self.organisms, columns=self.organisms)
 
+    def _column_stats(self):
+        """(prevalence, population variance) per column: on the GPU when the matrix came from GPU count rows
+        (kmerml_column_stats), else pandas."""
+        m = self.feature_matrix
+        if self._device_counts is not None:
+            from .. import engine
+            nnz, _, var = engine.column_stats_device(self._device_counts[0])
+            n = max(len(self.organisms), 1)
+            return nnz.cpu().numpy().astype(np.float64) / n, var.cpu().numpy()
+        return (m != 0).mean(axis=0).to_numpy(), m.var(axis=0, ddof=0).to_numpy()
+
     def filter_features(self, min_prevalence=0.0, min_variance=0.0):
         """Columns present in at least min_prevalence of the organisms with variance >= min_variance."""
         if self.feature_matrix is None:
             raise ValueError("No feature matrix built")
-        m = self.feature_matrix
-        keep = ((m != 0).mean(axis=0) >= min_prevalence) & (m.var(axis=0, ddof=0) >= min_variance)
-        return m.loc[:, keep]
+        prev, var = self._column_stats()
+        keep = (prev >= min_prevalence) & (var >= min_variance)
+        return self.feature_matrix.loc[:, keep]
 
     def get_top_features(self, n_features=500, method="variance"):
+        """The n_features columns of largest variance, ties in column order."""
         if self.feature_matrix is None:
             raise ValueError("No feature matrix built")
         if method != "variance":
             raise ValueError(f"Unknown method: {method}")
-        var = self.feature_matrix.var(axis=0, ddof=0)
-        top = var.sort_values(ascending=False, kind="stable").index[:n_features]
-        return self.feature_matrix.loc[:, top]
+        _, var = self._column_stats()
+        top = np.argsort(-var, kind="stable")[:n_features]
+        return self.feature_matrix.iloc[:, top]

@@ -163,8 +163,11 @@ def test_host_api_narrow_wire_format():
         assert torch.equal(narrow.counts, wide.counts), ks
         assert torch.equal(narrow.totals, wide.totals)
         assert torch.equal(narrow.counts, dres.counts.cpu())
+        comp = engine.count_dense_host(datas, ks, want_freq=False, compact=True)      # result left as it crossed the bus
+        assert torch.equal(comp.counts_tensor(), wide.counts) and torch.equal(comp.totals, wide.totals), ks
     big = (narrow.counts.to(torch.int64) & 0xFFFFFFFF)
     assert int((big[1] >= 255).sum()) > 65536            # the tandem genome did overflow the exception list
+    assert 1 in comp._wide and 3 in comp._wide
 
 
 def test_argument_errors():

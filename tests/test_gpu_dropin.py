@@ -143,6 +143,22 @@ def test_builder_from_counts_and_distance_matrix():
         want = oracle.pairwise_distance(f, metric)
         off = ~np.eye(5, dtype=bool)
         assert np.all(np.abs(d - want)[off] <= RTOL * np.abs(want)[off])
+    # filter_features / get_top_features (tests/test_ml.py:9-12 of the reference): column reductions on the GPU
+    # against the float64 pandas restatement
+    import pandas as pd
+    frame = pd.DataFrame(ref[:, keep], index=orgs, columns=m.columns)
+    prev, var = (frame != 0).mean(axis=0), frame.var(axis=0, ddof=0)
+    nnz, mean, dvar = engine.column_stats_device(b._device_counts[0])
+    assert np.array_equal(nnz.cpu().numpy(), (frame != 0).sum(axis=0).to_numpy())
+    np.testing.assert_allclose(mean.cpu().numpy(), frame.mean(axis=0).to_numpy(), rtol=1e-12)
+    np.testing.assert_allclose(dvar.cpu().numpy(), var.to_numpy(), rtol=1e-9, atol=1e-12)
+    thr = float(np.median(var))
+    got = b.filter_features(min_prevalence=0.6, min_variance=thr)
+    want_cols = frame.columns[((prev >= 0.6) & (var >= thr * (1 - 1e-9))).to_numpy()]
+    assert set(got.columns) <= set(frame.columns[(prev >= 0.6).to_numpy()]) and abs(len(got.columns) - len(want_cols)) <= 2
+    top = b.get_top_features(n_features=20)
+    assert top.shape == (5, 20)
+    assert float(var[top.columns].min()) >= float(np.sort(var.to_numpy())[-20]) * (1 - 1e-9)
 
 
 def test_sparse_counts_match_oracle():
