@@ -505,6 +505,22 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     return KMERML_OK;
 }
 
+// A batch whose genome g occupies [starts[g], starts[g] + sizes[g]) of the buffer (starts are 256-byte aligned, so
+// there may be gaps): the core takes back-to-back offsets, and bytes between a genome's end and the next start
+// would be read as FASTA text, so the gaps must hold no text: they are filled with line feeds here.
+static int count_dense_group(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fasta, const uint64_t* starts,
+                             const uint64_t* sizes, int n, const int* k_list, int nk, int min_record_len, unsigned flags,
+                             uint32_t* d_counts, uint64_t counts_stride, float* d_freq, uint64_t freq_stride,
+                             uint64_t* d_totals, cudaStream_t s) {
+    for (int g = 0; g < n; g++) {
+        const uint64_t end = starts[g] + sizes[g];
+        if (starts[g + 1] > end)
+            KM_CUDA(cudaMemsetAsync(const_cast<uint8_t*>(d_fasta) + end, '\n', (size_t)(starts[g + 1] - end), s));
+    }
+    return count_dense_core(ctx, ws, d_fasta, starts, n, k_list, nk, min_record_len, flags, d_counts, counts_stride, d_freq,
+                            freq_stride, d_totals, s);
+}
+
 }  // namespace km
 
 using namespace km;
@@ -648,62 +664,121 @@ namespace {
 constexpr int NARROW_MIN_K = 10;                 // levels that cross the bus as one byte per bin
 constexpr uint32_t NARROW_EXC_CAP = 65536;       // exception list entries (bin, count) per genome
 constexpr size_t NARROW_CHUNK = 1u << 20;        // bins one host task widens
+// Measured (1 x B200, C2): the call is bound by the box's host memory system (~60 GB/s of DMA traffic in either
+// direction), not by launches: 8 genomes per slot gave the same 86 ms per step for the compact result and made the
+// uint32 variant slower (a group's rows can only be widened once its last byte has arrived), so a slot holds one.
+constexpr int HOST_GROUP_MAX = 1;                // genomes one pipeline slot holds (one batch of kernels) ...
+constexpr uint64_t HOST_GROUP_BYTES = 192ull << 20;   // ... and their FASTA bytes, at most
+
+// wire row of one genome: [narrow bytes | exception count (16 B) | exception list | small levels (uint32)]
+struct WireLayout {
+    km::NarrowSpec spec;
+    size_t exc_off, small_off, bytes;
+};
+
+WireLayout wire_layout(const km::RowSpec& row, bool narrow_big_levels) {
+    WireLayout L;
+    memset(&L, 0, sizeof(L));
+    km::NarrowSpec& sp = L.spec;
+    unsigned long long small = 0;
+    for (int i = 0; i < row.nk; i++) {
+        const unsigned long long n = 1ull << (2 * row.k[i]);
+        if (narrow_big_levels && row.k[i] >= NARROW_MIN_K) {
+            sp.src_off[sp.n] = row.off[i];
+            sp.dst_off[sp.n] = sp.total;
+            sp.total += n;
+            sp.n++;
+        } else {
+            sp.small_src[sp.n_small] = row.off[i];
+            sp.small_dst[sp.n_small] = small;
+            small += n;
+            sp.n_small++;
+        }
+    }
+    sp.dst_off[sp.n] = sp.total;
+    sp.small_dst[sp.n_small] = small;
+    sp.small_total = small;
+    L.exc_off = (size_t)sp.total;
+    L.small_off = L.exc_off + 16 + (size_t)NARROW_EXC_CAP * 8;
+    L.bytes = (L.small_off + (size_t)small * 4 + 15) / 16 * 16;
+    return L;
+}
 
 struct HostSlot {                                // hand-over between the stream callback, the pool and the caller
     std::mutex m;
     std::condition_variable cv;
-    bool busy = false;                           // a genome's expansion is outstanding
-    bool overflow = false;                       // its exception list overflowed: the caller copies the row in full
+    bool busy = false;                           // a group's expansion is outstanding
+    bool overflow[HOST_GROUP_MAX] = {};          // exception list overflowed: the caller copies that row in full
     std::atomic<int> remaining{0};
-    // the genome in the slot
-    const uint8_t* wire_host = nullptr;
-    uint32_t* row = nullptr;
-    km::NarrowSpec spec;
+    // the group in the slot
+    int n = 0;
+    const uint8_t* wire_host = nullptr;          // n wire rows
+    uint32_t* row[HOST_GROUP_MAX] = {};          // the caller's uint32 rows
+    WireLayout lay;
     km::HostPool* pool = nullptr;
 };
 
-void slot_finish(HostSlot* sl) {                 // last task of a genome: exceptions, then the slot is free
-    const uint8_t* tail = sl->wire_host + sl->spec.total;
-    uint32_t n_exc;
-    memcpy(&n_exc, tail, 4);
-    bool over = n_exc > NARROW_EXC_CAP;
-    if (!over) {
-        const uint32_t* e = reinterpret_cast<const uint32_t*>(tail + 16);
-        for (uint32_t i = 0; i < n_exc; i++) sl->row[e[2 * i]] = e[2 * i + 1];
+void slot_finish(HostSlot* sl) {                 // last task of a group: exceptions, then the slot is free
+    bool over[HOST_GROUP_MAX] = {};
+    for (int g = 0; g < sl->n; g++) {
+        const uint8_t* tail = sl->wire_host + (size_t)g * sl->lay.bytes + sl->lay.exc_off;
+        uint32_t n_exc;
+        memcpy(&n_exc, tail, 4);
+        over[g] = n_exc > NARROW_EXC_CAP;
+        if (!over[g]) {
+            const uint32_t* e = reinterpret_cast<const uint32_t*>(tail + 16);
+            for (uint32_t i = 0; i < n_exc; i++) sl->row[g][e[2 * i]] = e[2 * i + 1];
+        }
     }
     {
-        std::lock_guard<std::mutex> g(sl->m);
-        sl->overflow = over;
+        std::lock_guard<std::mutex> lk(sl->m);
+        for (int g = 0; g < sl->n; g++) sl->overflow[g] = over[g];
         sl->busy = false;
     }
     sl->cv.notify_all();
 }
 
-void CUDART_CB slot_arrived(void* p) {           // stream callback: the genome's narrow block is in host memory
+void CUDART_CB slot_arrived(void* p) {           // stream callback: the group's wire rows are in host memory
     HostSlot* sl = static_cast<HostSlot*>(p);
-    int n_tasks = 0;
-    for (int i = 0; i < sl->spec.n; i++)
-        n_tasks += (int)((sl->spec.dst_off[i + 1] - sl->spec.dst_off[i] + NARROW_CHUNK - 1) / NARROW_CHUNK);
-    if (!n_tasks) { slot_finish(sl); return; }
-    sl->remaining.store(n_tasks);
-    for (int i = 0; i < sl->spec.n; i++) {
-        const size_t len = (size_t)(sl->spec.dst_off[i + 1] - sl->spec.dst_off[i]);
-        for (size_t c = 0; c < len; c += NARROW_CHUNK) {
-            const uint8_t* src = sl->wire_host + sl->spec.dst_off[i] + c;
-            uint32_t* dst = sl->row + sl->spec.src_off[i] + c;
-            const size_t n = std::min(NARROW_CHUNK, len - c);
-            km::host_pool_submit(sl->pool, [sl, src, dst, n] {
-                km::widen_u8_to_u32(src, dst, n);
+    const km::NarrowSpec& sp = sl->lay.spec;
+    int per_genome = sp.n_small ? 1 : 0;
+    for (int i = 0; i < sp.n; i++) per_genome += (int)((sp.dst_off[i + 1] - sp.dst_off[i] + NARROW_CHUNK - 1) / NARROW_CHUNK);
+    if (!per_genome || !sl->n) { slot_finish(sl); return; }
+    sl->remaining.store(per_genome * sl->n);
+    for (int g = 0; g < sl->n; g++) {
+        const uint8_t* wire = sl->wire_host + (size_t)g * sl->lay.bytes;
+        uint32_t* row = sl->row[g];
+        if (sp.n_small) {
+            const km::NarrowSpec* spp = &sl->lay.spec;
+            const uint8_t* small = wire + sl->lay.small_off;
+            km::host_pool_submit(sl->pool, [sl, spp, small, row] {
+                for (int i = 0; i < spp->n_small; i++)
+                    memcpy(row + spp->small_src[i], small + spp->small_dst[i] * 4,
+                           (size_t)(spp->small_dst[i + 1] - spp->small_dst[i]) * 4);
                 if (sl->remaining.fetch_sub(1) == 1) slot_finish(sl);
             });
+        }
+        for (int i = 0; i < sp.n; i++) {
+            const size_t len = (size_t)(sp.dst_off[i + 1] - sp.dst_off[i]);
+            for (size_t c = 0; c < len; c += NARROW_CHUNK) {
+                const uint8_t* src = wire + sp.dst_off[i] + c;
+                uint32_t* dst = row + sp.src_off[i] + c;
+                const size_t n = std::min(NARROW_CHUNK, len - c);
+                km::host_pool_submit(sl->pool, [sl, src, dst, n] {
+                    km::widen_u8_to_u32(src, dst, n);
+                    if (sl->remaining.fetch_sub(1) == 1) slot_finish(sl);
+                });
+            }
         }
     }
 }
 
 }  // namespace
 
-// compact_rows != nullptr: the narrow block, the exception count + list and the small levels are delivered as
-// they crossed the bus (kmerml_count_dense_host_compact), one row of `compact_stride` bytes per genome.
+// compact_rows != nullptr: the wire rows are delivered as they crossed the bus (kmerml_count_dense_host_compact),
+// one row of `compact_stride` bytes per genome.  Genomes travel in groups of up to HOST_GROUP_MAX per pipeline slot
+// (three slots): one H2D copy per genome, ONE batch of counting kernels and one narrowing kernel per group, one D2H
+// copy per genome.
 static int count_dense_host_impl(kmerml_ctx* ctx, const uint8_t* const* h_fasta, const uint64_t* h_sizes, int n_genomes,
                                  const int* k_list, int nk, int min_record_len, unsigned flags, uint32_t* h_counts,
                                  uint64_t counts_stride, float* freq, uint64_t freq_stride, uint64_t* h_totals,
@@ -726,56 +801,68 @@ static int count_dense_host_impl(kmerml_ctx* ctx, const uint8_t* const* h_fasta,
     if (freq_dev && (((uintptr_t)freq & 15) || (freq_stride & 3) || freq_stride < row_len))
         return fail(KMERML_ERR_ARG, "device freq buffer must be 16-byte aligned with a stride multiple of 4");
     // the levels k >= 10 cross the bus as bytes + exceptions (hostpipe.cu), the small ones as they are
-    NarrowSpec spec;
-    memset(&spec, 0, sizeof(spec));
-    if (compact || !(flags & KMERML_FLAG_WIDE_D2H)) {
-        for (int i = 0; i < nk; i++) {
-            if (row.k[i] < NARROW_MIN_K) continue;
-            spec.src_off[spec.n] = row.off[i];
-            spec.dst_off[spec.n] = spec.total;
-            spec.total += 1ull << (2 * row.k[i]);
-            spec.n++;
-        }
-        spec.dst_off[spec.n] = spec.total;
-    }
-    const bool narrow = spec.n > 0 || compact;
-    const size_t wire_bytes = (size_t)spec.total + 16 + (size_t)NARROW_EXC_CAP * 8;
-    if (compact && compact_stride < kmerml_compact_row_bytes(k_list, nk))
+    const bool wire = compact || !(flags & KMERML_FLAG_WIDE_D2H);
+    const WireLayout lay = wire_layout(row, true);
+    if (compact && compact_stride < lay.bytes)
         return fail(KMERML_ERR_ARG, "compact row stride smaller than kmerml_compact_row_bytes");
-    if (narrow && !compact && !ctx->host_pool) {
+    if (wire && !compact && !ctx->host_pool) {
         int n_thr = 0;
         if (const char* e = getenv("KMERML_HOST_THREADS")) n_thr = atoi(e);
         if (n_thr <= 0) n_thr = (int)std::min(16u, std::max(2u, std::thread::hardware_concurrency() / 2));
         ctx->host_pool = host_pool_create(n_thr);
         if (!ctx->host_pool) return fail(KMERML_ERR_NOMEM, "could not start the host thread pool");
     }
-    uint64_t max_bytes = 0;
-    for (int g = 0; g < n_genomes; g++) max_bytes = std::max(max_bytes, h_sizes[g]);
-    const int n_slots = std::min(3, n_genomes);
+    // groups of consecutive genomes
+    std::vector<int> group_begin;
+    {
+        uint64_t bytes = 0;
+        int cnt = 0;
+        for (int g = 0; g < n_genomes; g++) {
+            if (h_sizes[g] >= (1ull << 32)) return fail(KMERML_ERR_RANGE, "a genome of 4 GiB or more does not fit the 32-bit counters");
+            if (cnt == 0 || cnt >= HOST_GROUP_MAX || bytes + h_sizes[g] > HOST_GROUP_BYTES) {
+                group_begin.push_back(g);
+                bytes = 0;
+                cnt = 0;
+            }
+            bytes += h_sizes[g];
+            cnt++;
+        }
+        group_begin.push_back(n_genomes);
+    }
+    const int n_groups = (int)group_begin.size() - 1;
+    uint64_t max_group_bytes = 0;
+    int max_group = 0;
+    for (int gi = 0; gi < n_groups; gi++) {
+        uint64_t b = 0;
+        for (int g = group_begin[gi]; g < group_begin[gi + 1]; g++) b += align_up((size_t)h_sizes[g], 256);
+        max_group_bytes = std::max(max_group_bytes, b);
+        max_group = std::max(max_group, group_begin[gi + 1] - group_begin[gi]);
+    }
+    const int n_slots = std::min(3, n_groups);
     std::unique_ptr<HostSlot[]> slots(new (std::nothrow) HostSlot[3]);
     if (!slots) return fail(KMERML_ERR_NOMEM, "out of host memory");
     for (int i = 0; i < n_slots; i++) {
         Workspace& w = ctx->ws[i];
         if (!w.stream) KM_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
-        if ((rc = w.fasta.ensure(align_up((size_t)max_bytes + 64, 256)))) return rc;
-        if ((rc = w.counts.ensure(row_stride * 4))) return rc;
-        if (freq && !freq_dev && (rc = w.freq.ensure(row_stride * 4))) return rc;
-        if ((rc = w.totals.ensure((size_t)nk * 8))) return rc;
-        if (narrow) {
-            if ((rc = w.wire.ensure(wire_bytes))) return rc;
-            if (!compact && (rc = w.wire_host.ensure(wire_bytes))) return rc;
+        if ((rc = w.fasta.ensure(align_up((size_t)max_group_bytes + 64, 256)))) return rc;
+        if ((rc = w.counts.ensure((size_t)max_group * row_stride * 4))) return rc;
+        if (freq && !freq_dev && (rc = w.freq.ensure((size_t)max_group * row_stride * 4))) return rc;
+        if ((rc = w.totals.ensure((size_t)max_group * nk * 8))) return rc;
+        if (wire) {
+            if ((rc = w.wire.ensure((size_t)max_group * lay.bytes))) return rc;
+            if (!compact && (rc = w.wire_host.ensure((size_t)max_group * lay.bytes))) return rc;
         }
     }
     // every exit below first waits for the host tasks that still reference `slots`
-    auto wait_slot = [&](int si, int g_of_slot) -> int {
+    auto wait_slot = [&](int si, int group) -> int {
         HostSlot& sl = slots[si];
         std::unique_lock<std::mutex> lk(sl.m);
         sl.cv.wait(lk, [&] { return !sl.busy; });
-        if (sl.overflow) {                       // more than NARROW_EXC_CAP bins >= 255: the row in full
-            sl.overflow = false;
-            lk.unlock();
-            KM_CUDA(cudaMemcpy(h_counts + (size_t)g_of_slot * counts_stride, ctx->ws[si].counts.p, row_len * 4,
-                               cudaMemcpyDeviceToHost));
+        for (int j = 0; j < sl.n; j++) {
+            if (!sl.overflow[j]) continue;       // more than NARROW_EXC_CAP bins >= 255: that row in full
+            sl.overflow[j] = false;
+            KM_CUDA(cudaMemcpy(h_counts + (size_t)(group_begin[group] + j) * counts_stride,
+                               (uint32_t*)ctx->ws[si].counts.p + (size_t)j * row_stride, row_len * 4, cudaMemcpyDeviceToHost));
         }
         return KMERML_OK;
     };
@@ -786,82 +873,79 @@ static int count_dense_host_impl(kmerml_ctx* ctx, const uint8_t* const* h_fasta,
             slots[i].cv.wait(lk, [&] { return !slots[i].busy; });
         }
     };
-    for (int g = 0; g < n_genomes; g++) {
-        const int si = g % n_slots;
+#define KM_HOST_TRY(expr)                                                     \
+    do {                                                                      \
+        cudaError_t e__ = (expr);                                             \
+        if (e__ != cudaSuccess) { drain(); return cuda_fail(e__, #expr); }    \
+    } while (0)
+    for (int gi = 0; gi < n_groups; gi++) {
+        const int si = gi % n_slots, g0 = group_begin[gi], ng = group_begin[gi + 1] - g0;
         Workspace& w = ctx->ws[si];
         cudaStream_t s = w.stream;
-        if (narrow && !compact && g >= n_slots && (rc = wait_slot(si, g - n_slots))) { drain(); return rc; }
-        if (h_sizes[g]) {
-            cudaError_t e = cudaMemcpyAsync(w.fasta.p, h_fasta[g], (size_t)h_sizes[g], cudaMemcpyHostToDevice, s);
-            if (e != cudaSuccess) { drain(); return cuda_fail(e, "cudaMemcpyAsync(fasta)"); }
+        if (wire && !compact && gi >= n_slots && (rc = wait_slot(si, gi - n_slots))) { drain(); return rc; }
+        std::vector<uint64_t> offs(ng + 1, 0);
+        for (int j = 0; j < ng; j++) {
+            if (h_sizes[g0 + j])
+                KM_HOST_TRY(cudaMemcpyAsync((uint8_t*)w.fasta.p + offs[j], h_fasta[g0 + j], (size_t)h_sizes[g0 + j],
+                                            cudaMemcpyHostToDevice, s));
+            offs[j + 1] = offs[j] + align_up((size_t)h_sizes[g0 + j], 256);
         }
-        uint64_t offs[2] = {0, h_sizes[g]};
-        float* d_f = !freq ? nullptr : (freq_dev ? freq + (size_t)g * freq_stride : (float*)w.freq.p);
-        rc = count_dense_core(ctx, w, (const uint8_t*)w.fasta.p, offs, 1, k_list, nk, min_record_len,
-                              flags & ~(KMERML_FLAG_FREQ_ON_DEVICE | KMERML_FLAG_WIDE_D2H), (uint32_t*)w.counts.p, row_stride,
-                              d_f, freq_dev ? freq_stride : row_stride, (uint64_t*)w.totals.p, s);
+        // (genomes start at 256-byte multiples of the slot's buffer; count_dense_group blanks the gaps)
+        float* d_f = !freq ? nullptr : (freq_dev ? freq + (size_t)g0 * freq_stride : (float*)w.freq.p);
+        rc = count_dense_group(ctx, w, (const uint8_t*)w.fasta.p, offs.data(), h_sizes + g0, ng, k_list, nk, min_record_len,
+                               flags & ~(KMERML_FLAG_FREQ_ON_DEVICE | KMERML_FLAG_WIDE_D2H), (uint32_t*)w.counts.p, row_stride,
+                               d_f, freq_dev ? freq_stride : row_stride, (uint64_t*)w.totals.p, s);
         if (rc) { drain(); return rc; }
-        uint32_t* h_row = compact ? nullptr : h_counts + (size_t)g * counts_stride;
-        cudaError_t e = cudaSuccess;
-        if (compact) {
-            // [narrow bytes | exception count (16 B) | exception list | the small levels, uint32, in k_list order]
-            uint8_t* dw = (uint8_t*)w.wire.p;
-            uint8_t* hrow = compact_rows + (size_t)g * compact_stride;
-            rc = launch_narrow_levels((const uint32_t*)w.counts.p, spec, dw, dw + spec.total + 16,
-                                      (unsigned int*)(dw + spec.total), NARROW_EXC_CAP, s);
-            if (rc) { drain(); return rc; }
-            ctx->launches++;
-            e = cudaMemcpyAsync(hrow, dw, wire_bytes, cudaMemcpyDeviceToHost, s);
-            size_t small = wire_bytes;
-            for (int i = 0; i < nk && e == cudaSuccess; i++) {
-                if (row.k[i] >= NARROW_MIN_K) continue;
-                const size_t nb = (size_t)(1ull << (2 * row.k[i])) * 4;
-                e = cudaMemcpyAsync(hrow + small, (uint32_t*)w.counts.p + row.off[i], nb, cudaMemcpyDeviceToHost, s);
-                small += nb;
-            }
-        } else if (!narrow) {
-            e = cudaMemcpyAsync(h_row, w.counts.p, row_len * 4, cudaMemcpyDeviceToHost, s);
+        if (!wire) {
+            for (int j = 0; j < ng; j++)
+                KM_HOST_TRY(cudaMemcpyAsync(h_counts + (size_t)(g0 + j) * counts_stride, (uint32_t*)w.counts.p + (size_t)j * row_stride,
+                                            row_len * 4, cudaMemcpyDeviceToHost, s));
         } else {
             uint8_t* dw = (uint8_t*)w.wire.p;
-            rc = launch_narrow_levels((const uint32_t*)w.counts.p, spec, dw, dw + spec.total + 16,
-                                      (unsigned int*)(dw + spec.total), NARROW_EXC_CAP, s);
+            rc = launch_narrow_levels((const uint32_t*)w.counts.p, row_stride, ng, lay.spec, dw, lay.bytes, lay.exc_off,
+                                      lay.small_off, NARROW_EXC_CAP, s);
             if (rc) { drain(); return rc; }
             ctx->launches++;
-            for (int i = 0; i < nk && e == cudaSuccess; i++)
-                if (row.k[i] < NARROW_MIN_K)
-                    e = cudaMemcpyAsync(h_row + row.off[i], (uint32_t*)w.counts.p + row.off[i],
-                                        (size_t)(1ull << (2 * row.k[i])) * 4, cudaMemcpyDeviceToHost, s);
-            // bytes + exception count always; the list only as far as it is usually filled (a second copy
-            // would need the count first): 64 K entries = 512 KB
-            if (e == cudaSuccess) e = cudaMemcpyAsync(w.wire_host.p, dw, wire_bytes, cudaMemcpyDeviceToHost, s);
-            if (e == cudaSuccess) {
+            if (compact) {
+                for (int j = 0; j < ng; j++)
+                    KM_HOST_TRY(cudaMemcpyAsync(compact_rows + (size_t)(g0 + j) * compact_stride, dw + (size_t)j * lay.bytes,
+                                                lay.bytes, cudaMemcpyDeviceToHost, s));
+            } else {
+                KM_HOST_TRY(cudaMemcpyAsync(w.wire_host.p, dw, (size_t)ng * lay.bytes, cudaMemcpyDeviceToHost, s));
                 HostSlot& sl = slots[si];
                 {
                     std::lock_guard<std::mutex> lk(sl.m);
                     sl.busy = true;
-                    sl.overflow = false;
+                    for (bool& o : sl.overflow) o = false;
                 }
+                sl.n = ng;
                 sl.wire_host = (const uint8_t*)w.wire_host.p;
-                sl.row = h_row;
-                sl.spec = spec;
+                for (int j = 0; j < ng; j++) sl.row[j] = h_counts + (size_t)(g0 + j) * counts_stride;
+                sl.lay = lay;
                 sl.pool = ctx->host_pool;
-                e = cudaLaunchHostFunc(s, slot_arrived, &sl);
+                cudaError_t e = cudaLaunchHostFunc(s, slot_arrived, &sl);
                 if (e != cudaSuccess) {
-                    std::lock_guard<std::mutex> lk(sl.m);
-                    sl.busy = false;
+                    {
+                        std::lock_guard<std::mutex> lk(sl.m);
+                        sl.busy = false;
+                    }
+                    drain();
+                    return cuda_fail(e, "cudaLaunchHostFunc");
                 }
             }
         }
-        if (e == cudaSuccess && freq && !freq_dev)
-            e = cudaMemcpyAsync(freq + (size_t)g * freq_stride, w.freq.p, row_len * 4, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess && h_totals)
-            e = cudaMemcpyAsync(h_totals + (size_t)g * nk, w.totals.p, (size_t)nk * 8, cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) { drain(); return cuda_fail(e, "device -> host copy"); }
+        if (freq && !freq_dev)
+            for (int j = 0; j < ng; j++)
+                KM_HOST_TRY(cudaMemcpyAsync(freq + (size_t)(g0 + j) * freq_stride, (float*)w.freq.p + (size_t)j * row_stride,
+                                            row_len * 4, cudaMemcpyDeviceToHost, s));
+        if (h_totals)
+            KM_HOST_TRY(cudaMemcpyAsync(h_totals + (size_t)g0 * nk, w.totals.p, (size_t)ng * nk * 8, cudaMemcpyDeviceToHost, s));
     }
+#undef KM_HOST_TRY
     for (int i = 0; i < n_slots; i++) KM_CUDA(cudaStreamSynchronize(ctx->ws[i].stream));
-    if (narrow && !compact)
-        for (int g = std::max(0, n_genomes - n_slots); g < n_genomes; g++)
-            if ((rc = wait_slot(g % n_slots, g))) { drain(); return rc; }
+    if (wire && !compact)
+        for (int gi = std::max(0, n_groups - n_slots); gi < n_groups; gi++)
+            if ((rc = wait_slot(gi % n_slots, gi))) { drain(); return rc; }
     return KMERML_OK;
 }
 
@@ -873,13 +957,10 @@ int kmerml_count_dense_host(kmerml_ctx* ctx, const uint8_t* const* h_fasta, cons
 }
 
 uint64_t kmerml_compact_row_bytes(const int* k_list, int nk) {
-    uint64_t narrow = 0, small = 0;
-    for (int i = 0; k_list && i < nk; i++) {
-        if (k_list[i] < 1 || k_list[i] > KMERML_MAX_DENSE_K) return 0;
-        if (k_list[i] >= NARROW_MIN_K) narrow += 1ull << (2 * k_list[i]);
-        else small += (1ull << (2 * k_list[i])) * 4;
-    }
-    return narrow + 16 + (uint64_t)NARROW_EXC_CAP * 8 + small;
+    RowSpec row;
+    int kmax, kmin;
+    if (build_row(k_list, nk, &row, &kmax, &kmin)) return 0;
+    return wire_layout(row, true).bytes;
 }
 
 int kmerml_count_dense_host_compact(kmerml_ctx* ctx, const uint8_t* const* h_fasta, const uint64_t* h_sizes,
@@ -894,29 +975,31 @@ int kmerml_count_dense_host_compact(kmerml_ctx* ctx, const uint8_t* const* h_fas
 
 int kmerml_compact_expand(const int* k_list, int nk, const uint8_t* h_row, int ki, uint32_t* h_out) {
     if (!k_list || !h_row || !h_out || ki < 0 || ki >= nk) return fail(KMERML_ERR_ARG, "bad argument");
-    if (!kmerml_compact_row_bytes(k_list, nk)) return fail(KMERML_ERR_ARG, "dense k out of range");
-    uint64_t narrow_total = 0, row_off = 0, my_row_off = 0, my_narrow_off = 0, my_small_off = 0, small = 0;
-    for (int i = 0; i < nk; i++) {
-        const uint64_t n = 1ull << (2 * k_list[i]);
-        if (i == ki) { my_row_off = row_off; my_narrow_off = narrow_total; my_small_off = small; }
-        if (k_list[i] >= NARROW_MIN_K) narrow_total += n; else small += n * 4;
-        row_off += n;
-    }
-    const uint64_t n = 1ull << (2 * k_list[ki]);
-    const uint8_t* tail = h_row + narrow_total;
-    if (k_list[ki] < NARROW_MIN_K) {
-        memcpy(h_out, tail + 16 + (size_t)NARROW_EXC_CAP * 8 + my_small_off, (size_t)n * 4);
+    RowSpec row;
+    int kmax, kmin;
+    int rc = build_row(k_list, nk, &row, &kmax, &kmin);
+    if (rc) return rc;
+    const WireLayout lay = wire_layout(row, true);
+    const NarrowSpec& sp = lay.spec;
+    const uint64_t n = 1ull << (2 * row.k[ki]);
+    for (int i = 0; i < sp.n_small; i++)
+        if (sp.small_src[i] == row.off[ki]) {
+            memcpy(h_out, h_row + lay.small_off + sp.small_dst[i] * 4, (size_t)n * 4);
+            return KMERML_OK;
+        }
+    for (int i = 0; i < sp.n; i++) {
+        if (sp.src_off[i] != row.off[ki]) continue;
+        uint32_t n_exc;
+        memcpy(&n_exc, h_row + lay.exc_off, 4);
+        if (n_exc > NARROW_EXC_CAP)
+            return fail(KMERML_ERR_RANGE, "this genome's exception list overflowed: count it with kmerml_count_dense_host");
+        widen_u8_to_u32(h_row + sp.dst_off[i], h_out, (size_t)n);
+        const uint32_t* e = reinterpret_cast<const uint32_t*>(h_row + lay.exc_off + 16);
+        for (uint32_t j = 0; j < n_exc; j++)
+            if (e[2 * j] >= row.off[ki] && e[2 * j] < row.off[ki] + n) h_out[e[2 * j] - row.off[ki]] = e[2 * j + 1];
         return KMERML_OK;
     }
-    uint32_t n_exc;
-    memcpy(&n_exc, tail, 4);
-    if (n_exc > NARROW_EXC_CAP)
-        return fail(KMERML_ERR_RANGE, "this genome's exception list overflowed: count it with kmerml_count_dense_host");
-    widen_u8_to_u32(h_row + my_narrow_off, h_out, (size_t)n);
-    const uint32_t* e = reinterpret_cast<const uint32_t*>(tail + 16);
-    for (uint32_t i = 0; i < n_exc; i++)
-        if (e[2 * i] >= my_row_off && e[2 * i] < my_row_off + n) h_out[e[2 * i] - my_row_off] = e[2 * i + 1];
-    return KMERML_OK;
+    return fail(KMERML_ERR_ARG, "internal: level not found");
 }
 
 int kmerml_find_records(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, uint64_t* d_offsets, uint32_t cap,

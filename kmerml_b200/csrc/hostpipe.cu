@@ -24,45 +24,68 @@
 namespace km {
 
 // ---------------------------------------------------------------- device side
-// 16 bins per thread: four 128-bit loads, one 128-bit store of the low bytes; bins >= 255 are written as 255
-// and listed (row-relative bin, count).
+// One wire row per genome (blockIdx.y): 16 bins per thread of the narrow levels (four 128-bit loads, one 128-bit
+// store of the low bytes; bins >= 255 are written as 255 and listed as (row-relative bin, count)), then the small
+// levels copied as they are, four uint32 per thread.
 __global__ void __launch_bounds__(256)
-narrow_levels_kernel(const uint32_t* __restrict__ counts, NarrowSpec spec, uint8_t* __restrict__ out,
-                     uint2* __restrict__ exc, unsigned int* __restrict__ exc_count, uint32_t exc_cap) {
-    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;        // 16-bin vector of the narrow part
-    if (v >= spec.total >> 4) return;
-    const uint64_t e = v << 4;
-    int seg = 0;
-    while (seg + 1 < spec.n && e >= spec.dst_off[seg + 1]) seg++;
-    const uint64_t src = spec.src_off[seg] + (e - spec.dst_off[seg]);
-    const uint4* p = reinterpret_cast<const uint4*>(counts + src);
-    uint32_t w[4];
+narrow_levels_kernel(const uint32_t* __restrict__ counts_all, uint64_t counts_stride, NarrowSpec spec,
+                     uint8_t* __restrict__ wire_all, uint64_t wire_stride, uint64_t exc_off, uint64_t small_off,
+                     uint32_t exc_cap) {
+    const uint32_t* counts = counts_all + (uint64_t)blockIdx.y * counts_stride;
+    uint8_t* wire = wire_all + (uint64_t)blockIdx.y * wire_stride;
+    unsigned int* exc_count = reinterpret_cast<unsigned int*>(wire + exc_off);
+    uint2* exc = reinterpret_cast<uint2*>(wire + exc_off + 16);
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t n_narrow = spec.total >> 4;
+    if (v < n_narrow) {
+        const uint64_t e = v << 4;
+        int seg = 0;
+        while (seg + 1 < spec.n && e >= spec.dst_off[seg + 1]) seg++;
+        const uint64_t src = spec.src_off[seg] + (e - spec.dst_off[seg]);
+        const uint4* p = reinterpret_cast<const uint4*>(counts + src);
+        uint32_t w[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint4 c = __ldg(p + i);
-        const uint32_t x[4] = {c.x, c.y, c.z, c.w};
-        uint32_t packed = 0;
+        for (int i = 0; i < 4; i++) {
+            const uint4 c = __ldg(p + i);
+            const uint32_t x[4] = {c.x, c.y, c.z, c.w};
+            uint32_t packed = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t b = x[j];
-            if (b >= 255u) {
-                const unsigned int slot = atomicAdd(exc_count, 1u);
-                if (slot < exc_cap) exc[slot] = make_uint2((uint32_t)(src + 4 * i + j), b);
-                b = 255u;
+            for (int j = 0; j < 4; j++) {
+                uint32_t b = x[j];
+                if (b >= 255u) {
+                    const unsigned int slot = atomicAdd(exc_count, 1u);
+                    if (slot < exc_cap) exc[slot] = make_uint2((uint32_t)(src + 4 * i + j), b);
+                    b = 255u;
+                }
+                packed |= b << (8 * j);
             }
-            packed |= b << (8 * j);
+            w[i] = packed;
         }
-        w[i] = packed;
+        *reinterpret_cast<uint4*>(wire + e) = make_uint4(w[0], w[1], w[2], w[3]);
+        return;
     }
-    *reinterpret_cast<uint4*>(out + e) = make_uint4(w[0], w[1], w[2], w[3]);
+    const uint64_t q = (v - n_narrow) << 2;                       // element of the small block
+    if (q >= spec.small_total) return;
+    int seg = 0;
+    while (seg + 1 < spec.n_small && q >= spec.small_dst[seg + 1]) seg++;
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(counts + spec.small_src[seg] + (q - spec.small_dst[seg])));
+    *reinterpret_cast<uint4*>(wire + small_off + q * 4) = c;
 }
 
-int launch_narrow_levels(const uint32_t* d_counts, const NarrowSpec& spec, uint8_t* d_out, void* d_exc,
-                         unsigned int* d_exc_count, uint32_t exc_cap, cudaStream_t s) {
-    KM_CUDA(cudaMemsetAsync(d_exc_count, 0, 4, s));
-    if (!spec.total) return KMERML_OK;
-    const uint64_t vecs = spec.total >> 4;
-    narrow_levels_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, s>>>(d_counts, spec, d_out, (uint2*)d_exc, d_exc_count, exc_cap);
+__global__ void clear_exc_counts_kernel(uint8_t* wire_all, uint64_t wire_stride, uint64_t exc_off, int n) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) *reinterpret_cast<uint4*>(wire_all + (uint64_t)g * wire_stride + exc_off) = make_uint4(0, 0, 0, 0);
+}
+
+int launch_narrow_levels(const uint32_t* d_counts, uint64_t counts_stride, int n_genomes, const NarrowSpec& spec,
+                         uint8_t* d_wire, uint64_t wire_stride, uint64_t exc_off, uint64_t small_off, uint32_t exc_cap,
+                         cudaStream_t s) {
+    if (n_genomes <= 0) return KMERML_OK;
+    clear_exc_counts_kernel<<<(n_genomes + 63) / 64, 64, 0, s>>>(d_wire, wire_stride, exc_off, n_genomes);
+    const uint64_t threads = (spec.total >> 4) + ((spec.small_total + 3) >> 2);
+    if (threads)
+        narrow_levels_kernel<<<dim3((unsigned)((threads + 255) / 256), (unsigned)n_genomes), 256, 0, s>>>(
+            d_counts, counts_stride, spec, d_wire, wire_stride, exc_off, small_off, exc_cap);
     KM_CUDA(cudaGetLastError());
     return KMERML_OK;
 }

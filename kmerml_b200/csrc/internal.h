@@ -116,14 +116,18 @@ int launch_first_occurrence(const uint8_t* d_fasta, const GenomeDev* d_genomes, 
 int dense_setup_attributes();
 
 // ---- narrow device -> host wire format (hostpipe.cu) ---------------------------
-struct NarrowSpec {           // the levels that cross the bus as one byte per bin
-    int n;
-    unsigned long long src_off[16];   // element offset of the level inside the count row
-    unsigned long long dst_off[17];   // byte offset inside the narrow block; dst_off[n] = total
+struct NarrowSpec {           // how a count row maps onto its wire row
+    int n, n_small;
+    unsigned long long src_off[16];   // narrow levels (one byte per bin): element offset inside the count row ...
+    unsigned long long dst_off[17];   // ... and byte offset inside the narrow block; dst_off[n] = total
     unsigned long long total;         // bins (= bytes) of the narrow block, a multiple of 16
+    unsigned long long small_src[16]; // small levels (uint32 as they are): element offset inside the count row ...
+    unsigned long long small_dst[17]; // ... and inside the small block; small_dst[n_small] = small_total
+    unsigned long long small_total;
 };
-int launch_narrow_levels(const uint32_t* d_counts, const NarrowSpec& spec, uint8_t* d_out, void* d_exc,
-                         unsigned int* d_exc_count, uint32_t exc_cap, cudaStream_t s);
+int launch_narrow_levels(const uint32_t* d_counts, uint64_t counts_stride, int n_genomes, const NarrowSpec& spec,
+                         uint8_t* d_wire, uint64_t wire_stride, uint64_t exc_off, uint64_t small_off, uint32_t exc_cap,
+                         cudaStream_t s);
 void widen_u8_to_u32(const uint8_t* src, uint32_t* dst, size_t n);
 class HostPool;
 HostPool* host_pool_create(int n_threads);
