@@ -222,7 +222,9 @@ def run_ours(args):
     numa_node = kdist.bind_to_gpu_numa_node(local) if world > 1 else None     # before any pinned allocation
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        # (a rank that fails alone must not keep the others in a collective for NCCL's default ten minutes)
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=240))
     ks = [int(x) for x in args.k.split(",")] if args.k else K_LIST
     n_gen = args.genomes
 

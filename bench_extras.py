@@ -325,10 +325,21 @@ def run_extras(args, torch, dist, device, rank, world):
         out["c4_strong"] = {"error": repr(exc)[:300]}
     torch.cuda.empty_cache()
     if world > 1 or args.c5_single:
-        try:
-            out["c5_sparse"] = run_c5(torch, dist, device, rank, world, max(1, min(steps, 2)), 1, scale=sc)
-        except Exception as exc:
-            out["c5_sparse"] = {"error": repr(exc)[:300]}
+        # memory guard, agreed by all ranks BEFORE any collective of the section (a rank that runs out of memory
+        # alone would leave the others waiting in the all-to-all): per window of this rank's byte range the emit +
+        # sort workspace takes 24 B, the exchanged triples 2 x 16 B, the merge workspace 32-48 B, its outputs 16 B
+        need = 3.1e9 * sc / world * 128.0
+        free = torch.tensor([float(torch.cuda.mem_get_info(device)[0])], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(free, op=dist.ReduceOp.MIN)
+        if need > 0.6 * float(free.item()):
+            out["c5_sparse"] = {"skipped": f"needs ~{need / 1e9:.0f} GB per GPU at N={world} (sort + exchange + merge buffers of "
+                                           f"{3.1 * sc / world:.2f} G windows); {float(free.item()) / 1e9:.0f} GB free: run with more GPUs"}
+        else:
+            try:
+                out["c5_sparse"] = run_c5(torch, dist, device, rank, world, max(1, min(steps, 2)), 1, scale=sc)
+            except Exception as exc:
+                out["c5_sparse"] = {"error": repr(exc)[:300]}
         torch.cuda.empty_cache()
     out["extras_seconds"] = round(time.time() - t0, 1)
     return out

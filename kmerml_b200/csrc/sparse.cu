@@ -59,23 +59,34 @@ __global__ void sparse_setup_kernel(const uint8_t* __restrict__ buf, uint64_t nb
     }
 }
 
-// One thread per 32-byte chunk, owning the windows whose last base lies in it; the k-1 bases before
-// the chunk come from a backward walk over global memory (same rules as fasta_walk.cuh's generic
-// path).  Whether a chunk starts inside a header line is settled per tile: the slice table says so for
-// the slice's first byte, and header lines that start inside the tile flag the chunks they cover.
+// One thread per 32-byte chunk, owning the windows whose last base lies in it.
+//   * Clean chunk (only bases and at most one '\n') after a clean chunk -- nearly every chunk of a wrapped
+//     genome: two 128-bit loads, the SWAR classifier and bit-compaction of fasta_walk.cuh, the k-1 bases before
+//     the chunk from the neighbour thread's packed chunk (31 or 32 bases: enough for k <= 32) through shared
+//     memory, then a rolling 64-bit forward k-mer and reverse complement, one shift-or each per base.  The
+//     windows of a warp's 32 chunks are written window-index-major with ONE cursor reservation per warp and
+//     tile, so the 8-byte key stores and 4-byte offset stores are contiguous across the lanes.
+//   * Anything else (header lines, N runs, IUPAC, '\r', the first chunk of a slice ...): the byte walker whose
+//     start state comes from a backward walk over global memory (same rules as the dense generic path).
+// Whether a chunk starts inside a header line is settled per tile: the slice table says so for the slice's
+// first byte, and header lines that start inside the tile flag the chunks they cover.
 __global__ void __launch_bounds__(SPARSE_THREADS)
 sparse_emit_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds, const Slice* __restrict__ slices,
                    SparseParams P, uint64_t* keys, uint32_t* ends, unsigned long long* cursor, uint64_t cap) {
     __shared__ uint8_t s_flags[SPARSE_THREADS];
     __shared__ unsigned long long s_carry[2];
-    const int tid = threadIdx.x;
+    __shared__ uint2 s_packed[SPARSE_THREADS];              // the chunk's bases, top-aligned (hi, lo) ...
+    __shared__ uint8_t s_n[SPARSE_THREADS];                 // ... and how many: 31 / 32, 0 = not a clean chunk
+    __shared__ uint2 s_prev_packed;                          // the last chunk of the tile before
+    __shared__ uint32_t s_prev_n;
+    const int tid = threadIdx.x, lane = tid & 31;
     const Slice sl = slices[blockIdx.x];
     const GenomeDev gd = gds[0];
     Genome g;
     g.b = buf;
     g.lo = gd.lo;
     g.hi = gd.hi;
-    if (tid == 0) s_carry[0] = s_carry[1] = sl.hdr_until;
+    if (tid == 0) { s_carry[0] = s_carry[1] = sl.hdr_until; s_prev_n = 0; s_prev_packed = make_uint2(0, 0); }
     const int rcshift = 2 * (P.k - 1);
     const uint64_t end = sl.end < g.hi ? sl.end : g.hi;
     for (uint64_t tb = sl.begin; tb < end; tb += SPARSE_TILE) {
@@ -85,60 +96,132 @@ sparse_emit_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict_
         const uint64_t cs = cb > g.lo ? cb : g.lo;
         const uint64_t ce = cb + CHUNK < g.hi ? cb + CHUNK : g.hi;
         const bool has = cs < ce;
-        if (has) {
-            find_headers(g, cs, ce, [&](uint64_t, uint64_t until) {
-                for (int j = tid + 1; j < SPARSE_THREADS && tb + (uint64_t)j * CHUNK < until; j++) s_flags[j] = 1;
-                atomicMax(&s_carry[1], (unsigned long long)until);
-            });
+        CleanChunk cc;
+        cc.hi = cc.lo = 0; cc.n = 0; cc.nl = 32; cc.last16 = 0;
+        bool clean = false;
+        auto on_header = [&](uint64_t, uint64_t until) {
+            for (int j = tid + 1; j < SPARSE_THREADS && tb + (uint64_t)j * CHUNK < until; j++) s_flags[j] = 1;
+            atomicMax(&s_carry[1], (unsigned long long)until);
+        };
+        if (has && cb >= g.lo && cb + CHUNK <= g.hi) {
+            uint32_t w[CHUNK / 4], y[CHUNK / 4], bad[CHUNK / 4];
+            const uint4* src = reinterpret_cast<const uint4*>(buf + cb);
+#pragma unroll
+            for (int i = 0; i < CHUNK / 16; i++) {
+                const uint4 v = __ldg(src + i);
+                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+            const bool weird = classify_chunk(w, y, bad) != 0;
+            clean = !weird && pack_clean(y, bad, cc);
+            if (weird && any_byte_eq_chunk(w, 0x3E3E3E3Eu)) find_headers(g, cs, ce, on_header);
+        } else if (has) {
+            find_headers(g, cs, ce, on_header);
         }
+        s_packed[tid] = make_uint2(cc.hi, cc.lo);
+        s_n[tid] = clean ? (uint8_t)cc.n : 0;
         __syncthreads();
         int in_hdr = (s_flags[tid] || cs < s_carry[0]) ? 1 : 0;
-        uint64_t fwd = 0, rc = 0;
-        int run = 0, rec_known = 0;
-        if (has && !in_hdr && cs > g.lo) {
-            // the up to k-1 valid bases right before the chunk, oldest first
-            uint64_t q = cs;
-            uint32_t codes[32];
-            int cnt = 0;
-            while (cnt < P.k - 1) {
-                int kind = prev_symbol(g, q);
-                if (kind > 3) break;
-                codes[cnt++] = (uint32_t)kind;
-            }
-            for (int i = cnt - 1; i >= 0; i--) {
-                fwd = ((fwd << 2) | codes[i]) & P.mask;
-                rc = (rc >> 2) | ((uint64_t)(3u - codes[i]) << rcshift);
-            }
-            run = cnt;
+        const bool starts_in_hdr = in_hdr != 0;
+        // the chunk before: clean, in sequence, not shadowed by a header line
+        uint2 pv;
+        uint32_t pn;
+        if (tid > 0) {
+            pv = s_packed[tid - 1];
+            pn = (s_flags[tid - 1] || (cb - CHUNK) < s_carry[0]) ? 0u : s_n[tid - 1];
+        } else {
+            pv = s_prev_packed;
+            pn = s_prev_n;
         }
-        for (uint64_t pos = cs; pos < ce; pos++) {
-            const uint32_t c = buf[pos];
-            const int code = base_code(c);
-            if (code >= 0 && !in_hdr) {
-                fwd = ((fwd << 2) | (uint64_t)code) & P.mask;
-                rc = (rc >> 2) | ((uint64_t)(3 - code) << rcshift);
-                run++;
-                if (run >= P.k) {
-                    if (P.min_rec > P.k) {
-                        if (rec_known == 0) rec_known = (run >= P.min_rec || record_len_at_least(g, pos, P.min_rec)) ? 1 : 2;
-                        if (rec_known == 2) continue;
+        const bool fast = has && clean && !in_hdr && pn != 0 && P.min_rec <= P.k;
+        // ---- fast lanes: one reservation per warp, window-index-major slots
+        const unsigned fast_mask = __ballot_sync(0xffffffffu, fast);
+        if (fast_mask) {
+            const unsigned n31_mask = __ballot_sync(0xffffffffu, fast && cc.n == 31);
+            const unsigned total = 32u * __popc(fast_mask) - __popc(n31_mask);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (unsigned long long)total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (fast) {
+                // the k-1 bases before the chunk: the last ones of the neighbour's pn bases
+                const uint64_t prev = (((uint64_t)pv.x << 32) | pv.y) >> (64 - 2 * pn);
+                uint64_t fwd = prev & (P.mask >> 2);
+                uint64_t rc = 0;
+                for (int i = P.k - 2; i >= 0; i--)                   // oldest first
+                    rc = (rc >> 2) | ((uint64_t)(3u - (uint32_t)((prev >> (2 * i)) & 3u)) << rcshift);
+                const uint64_t own = ((uint64_t)cc.hi << 32) | cc.lo;
+                const unsigned below = fast_mask & ((1u << lane) - 1u);
+                const unsigned rank = __popc(below);
+                const unsigned n_fast = __popc(fast_mask);
+                const unsigned rank32 = __popc(below & ~n31_mask);
+#pragma unroll 4
+                for (int j = 0; j < 32; j++) {
+                    if (j >= cc.n) break;
+                    const uint32_t code = (uint32_t)(own >> (62 - 2 * j)) & 3u;
+                    fwd = ((fwd << 2) | code) & P.mask;
+                    rc = (rc >> 2) | ((uint64_t)(3u - code) << rcshift);
+                    const unsigned long long slot = base + (j < 31 ? (unsigned long long)j * n_fast + rank
+                                                                   : 31ull * n_fast + rank32);
+                    if (slot < cap) {
+                        keys[slot] = P.canonical ? (fwd < rc ? fwd : rc) : fwd;
+                        ends[slot] = (uint32_t)(cs + (uint64_t)(j + (j >= cc.nl ? 1 : 0)));
                     }
-                    sparse_push(fwd, rc, P, pos, keys, ends, cursor, cap);
                 }
-                continue;
             }
-            if (in_hdr) {
-                if (is_term(c)) in_hdr = 0;
-                continue;
+        }
+        // ---- everything else: the byte walker
+        if (has && !fast) {
+            uint64_t fwd = 0, rc = 0;
+            int run = 0, rec_known = 0;
+            if (!in_hdr && cs > g.lo) {
+                // the up to k-1 valid bases right before the chunk, oldest first
+                uint64_t q = cs;
+                uint32_t codes[32];
+                int cnt = 0;
+                while (cnt < P.k - 1) {
+                    int kind = prev_symbol(g, q);
+                    if (kind > 3) break;
+                    codes[cnt++] = (uint32_t)kind;
+                }
+                for (int i = cnt - 1; i >= 0; i--) {
+                    fwd = ((fwd << 2) | codes[i]) & P.mask;
+                    rc = (rc >> 2) | ((uint64_t)(3u - codes[i]) << rcshift);
+                }
+                run = cnt;
             }
-            const int kind = classify_nonbase(g, pos, c);
-            if (kind == SYM_SKIP) continue;
-            run = 0;
-            fwd = rc = 0;
-            if (kind == SYM_HDR) { in_hdr = 1; rec_known = 0; }
+            for (uint64_t pos = cs; pos < ce; pos++) {
+                const uint32_t c = buf[pos];
+                const int code = base_code(c);
+                if (code >= 0 && !in_hdr) {
+                    fwd = ((fwd << 2) | (uint64_t)code) & P.mask;
+                    rc = (rc >> 2) | ((uint64_t)(3 - code) << rcshift);
+                    run++;
+                    if (run >= P.k) {
+                        if (P.min_rec > P.k) {
+                            if (rec_known == 0) rec_known = (run >= P.min_rec || record_len_at_least(g, pos, P.min_rec)) ? 1 : 2;
+                            if (rec_known == 2) continue;
+                        }
+                        sparse_push(fwd, rc, P, pos, keys, ends, cursor, cap);
+                    }
+                    continue;
+                }
+                if (in_hdr) {
+                    if (is_term(c)) in_hdr = 0;
+                    continue;
+                }
+                const int kind = classify_nonbase(g, pos, c);
+                if (kind == SYM_SKIP) continue;
+                run = 0;
+                fwd = rc = 0;
+                if (kind == SYM_HDR) { in_hdr = 1; rec_known = 0; }
+            }
         }
         __syncthreads();
         if (tid == 0) s_carry[0] = s_carry[1];
+        if (tid == SPARSE_THREADS - 1) {
+            const bool ok = has && clean && !starts_in_hdr;
+            s_prev_packed = make_uint2(cc.hi, cc.lo);
+            s_prev_n = ok ? (uint32_t)cc.n : 0u;
+        }
     }
 }
 

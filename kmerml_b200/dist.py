@@ -273,11 +273,19 @@ def count_sparse_sharded(fasta, k, *, min_record_len=None, canonical=False, coun
     recv = recv_t.cpu().tolist()
     total = int(sum(recv))
     out = []
-    for t in (keys, counts, first):
-        r = torch.empty(total, dtype=t.dtype, device=t.device)
-        dist.all_to_all_single(r, t.contiguous(), output_split_sizes=recv, input_split_sizes=send)
+    dev = keys.device
+    parts = [keys, counts, first]
+    del keys, counts, first
+    for i in range(3):                                   # (each send buffer is released as soon as it has been exchanged)
+        t = parts[i].contiguous()
+        parts[i] = None
+        r = torch.empty(total, dtype=t.dtype, device=dev)
+        dist.all_to_all_single(r, t, output_split_sizes=recv, input_split_sizes=send)
+        del t
         out.append(r)
-    w = torch.tensor([windows], dtype=torch.int64, device=keys.device)
+    w = torch.tensor([windows], dtype=torch.int64, device=dev)
     dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
     mk, mc, mf = merge(out[0], out[1], out[2], int(k))
     return mk, mc, mf, int(w.item())
