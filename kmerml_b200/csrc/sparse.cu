@@ -230,6 +230,61 @@ __global__ void gather_u32_kernel(const uint32_t* __restrict__ src, uint32_t* ds
     if (i < n) dst[i] = src[i];
 }
 
+struct CountFirst {               // count in the high word, first (smallest) offset in the low word
+    __host__ __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const {
+        const unsigned long long cnt = (a >> 32) + (b >> 32);
+        const unsigned long long fa = a & 0xFFFFFFFFull, fb = b & 0xFFFFFFFFull;
+        return (cnt << 32) | (fa < fb ? fa : fb);
+    }
+};
+struct OneWindow {                // a sorted window's end offset -> (count 1, first = that offset)
+    __host__ __device__ __forceinline__ unsigned long long operator()(uint32_t end) const { return (1ull << 32) | end; }
+};
+
+__global__ void unpack_count_first_kernel(const unsigned long long* __restrict__ in, uint64_t n, uint32_t* counts,
+                                          uint32_t* first) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    counts[i] = (uint32_t)(in[i] >> 32);
+    if (first) first[i] = (uint32_t)in[i];
+}
+
+// Output iterator of the fused segmented reduction: a packed (count, first) aggregate goes straight into the
+// caller's two arrays.
+struct SplitCountFirst {
+    uint32_t* counts;
+    uint32_t* first;              // may be null
+    struct Ref {
+        uint32_t* c;
+        uint32_t* f;
+        __host__ __device__ __forceinline__ Ref& operator=(unsigned long long v) {
+            *c = (uint32_t)(v >> 32);
+            if (f) *f = (uint32_t)v;
+            return *this;
+        }
+    };
+    using iterator_category = std::random_access_iterator_tag;
+    using value_type = unsigned long long;
+    using difference_type = ptrdiff_t;
+    using pointer = void;
+    using reference = Ref;
+    __host__ __device__ __forceinline__ Ref operator*() const { return Ref{counts, first}; }
+    __host__ __device__ __forceinline__ Ref operator[](difference_type i) const { return Ref{counts + i, first ? first + i : nullptr}; }
+    __host__ __device__ __forceinline__ SplitCountFirst operator+(difference_type i) const {
+        return SplitCountFirst{counts + i, first ? first + i : nullptr};
+    }
+};
+
+// distinct keys of a sorted array = 1 + the positions whose key differs from the one before
+__global__ void __launch_bounds__(256)
+count_boundaries_kernel(const uint64_t* __restrict__ keys, uint64_t n, unsigned long long* out) {
+    unsigned long long mine = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        mine += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
+}
+
 struct SparseWork {
     uint64_t* keys_a;
     uint64_t* keys_b;
@@ -265,11 +320,13 @@ size_t sparse_workspace(uint64_t cap, uint64_t nbytes, SparseWork* w, uint8_t* b
     cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
     cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
     cub::DeviceRadixSort::SortPairs(nullptr, t1, dk, dv, (uint64_t)cap, 0, 64);
-    cub::DeviceReduce::ReduceByKey(nullptr, t2, (uint64_t*)nullptr, (uint64_t*)nullptr,
-                                   thrust::constant_iterator<uint32_t>(1u), (uint32_t*)nullptr,
-                                   (unsigned long long*)nullptr, cub::Sum(), (uint64_t)cap);
-    cub::DeviceReduce::ReduceByKey(nullptr, t3, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
-                                   (uint32_t*)nullptr, (unsigned long long*)nullptr, cub::Min(), (uint64_t)cap);
+    {
+        cub::TransformInputIterator<unsigned long long, OneWindow, const uint32_t*> vin((const uint32_t*)nullptr, OneWindow());
+        cub::DeviceReduce::ReduceByKey(nullptr, t2, (const uint64_t*)nullptr, (uint64_t*)nullptr, vin,
+                                       SplitCountFirst{nullptr, nullptr}, (unsigned long long*)nullptr, CountFirst(),
+                                       (uint64_t)cap);
+    }
+    (void)t3;
     local.temp_bytes = std::max(t1, std::max(t2, t3));
     local.temp = take(local.temp_bytes);
     if (w) *w = local;
@@ -281,14 +338,13 @@ size_t sparse_workspace(uint64_t cap, uint64_t nbytes, SparseWork* w, uint8_t* b
 static int sparse_copy_out(const SparseWork& w, uint64_t* sorted_keys, uint32_t* sorted_ends, uint64_t* uniq, uint32_t* runs,
                            uint64_t n, uint64_t nu, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out,
                            cudaStream_t s) {
-    KM_CUDA(cudaMemcpyAsync(d_keys_out, uniq, nu * 8, cudaMemcpyDeviceToDevice, s));
-    gather_u32_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, s>>>(runs, d_counts_out, nu);
-    KM_CUDA(cudaGetLastError());
-    if (d_first_out) {
-        size_t tb = w.temp_bytes;
-        KM_CUDA(cub::DeviceReduce::ReduceByKey(w.temp, tb, sorted_keys, uniq, sorted_ends, d_first_out, w.n_runs,
-                                               cub::Min(), (uint64_t)n, s));
-    }
+    // ONE segmented reduction over the sorted windows: distinct k-mers to the caller's key array, (run length, smallest
+    // end offset) through a splitting output iterator to its count / first-offset arrays
+    (void)uniq; (void)runs; (void)nu;
+    cub::TransformInputIterator<unsigned long long, OneWindow, const uint32_t*> vin(sorted_ends, OneWindow());
+    size_t tb = w.temp_bytes;
+    KM_CUDA(cub::DeviceReduce::ReduceByKey(w.temp, tb, (const uint64_t*)sorted_keys, d_keys_out, vin,
+                                           SplitCountFirst{d_counts_out, d_first_out}, w.n_runs, CountFirst(), (uint64_t)n, s));
     KM_CUDA(cudaStreamSynchronize(s));
     return KMERML_OK;
 }
@@ -340,13 +396,11 @@ int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, ui
     KM_CUDA(cub::DeviceRadixSort::SortPairs(w.temp, tb, dk, dv, (uint64_t)n, 0, 2 * k, s));
     uint64_t* sorted_keys = dk.Current();
     uint32_t* sorted_ends = dv.Current();
-    uint64_t* uniq = dk.Alternate();                 // scratch for the unique keys
-    uint32_t* runs = dv.Alternate();                 // scratch for counts, then first offsets
-    tb = w.temp_bytes;
-    // run lengths as a segmented sum of ones: DeviceRunLengthEncode takes an `int` item count, a human-sized
-    // genome has more than 2^31 windows
-    KM_CUDA(cub::DeviceReduce::ReduceByKey(w.temp, tb, sorted_keys, uniq, thrust::constant_iterator<uint32_t>(1u), runs,
-                                           w.n_runs, cub::Sum(), (uint64_t)n, s));
+    uint64_t* uniq = dk.Alternate();
+    uint32_t* runs = dv.Alternate();
+    // number of distinct k-mers first (one read of the sorted keys): the caller's buffers may be too small
+    count_boundaries_kernel<<<148 * 8, 256, 0, s>>>(sorted_keys, (uint64_t)n, w.n_runs);
+    KM_CUDA(cudaGetLastError());
     unsigned long long nu = 0;
     KM_CUDA(cudaMemcpyAsync(&nu, w.n_runs, 8, cudaMemcpyDeviceToHost, s));
     KM_CUDA(cudaStreamSynchronize(s));
@@ -380,26 +434,10 @@ int run_sparse_in(void* workspace, const uint8_t* d_fasta, uint64_t nbytes, uint
 
 // ---- merge of partial results (multi-GPU: every rank receives the (k-mer, count, first) triples of its
 // key range from all ranks): sort by k-mer, add the counts, keep the smallest first offset.
-struct CountFirst {               // count in the high word, first offset in the low word
-    __host__ __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const {
-        const unsigned long long cnt = (a >> 32) + (b >> 32);
-        const unsigned long long fa = a & 0xFFFFFFFFull, fb = b & 0xFFFFFFFFull;
-        return (cnt << 32) | (fa < fb ? fa : fb);
-    }
-};
-
 __global__ void pack_count_first_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ first,
                                         uint64_t n, unsigned long long* out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = ((unsigned long long)counts[i] << 32) | (first ? first[i] : 0xFFFFFFFFu);
-}
-
-__global__ void unpack_count_first_kernel(const unsigned long long* __restrict__ in, uint64_t n, uint32_t* counts,
-                                          uint32_t* first) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    counts[i] = (uint32_t)(in[i] >> 32);
-    if (first) first[i] = (uint32_t)in[i];
 }
 
 struct MergeWork {
