@@ -375,7 +375,7 @@ def run_ours(args):
     n_dom_launch = max(int(prof["count_launches"]) // max(args.steps, 1), 1) if dom and dom["kernel"] in ("partition_kernel", "count_kernel") else 1
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tj = json.load(f)
         if dom and dom["kernel"] in tj:
             # measured DRAM bytes per algorithmic byte (one ncu --set full capture on a 6-genome subset of this

@@ -261,6 +261,29 @@ int kmerml_pairwise_distance(kmerml_ctx *ctx, const void *d_x, int dtype, uint64
                              uint64_t m, int metric, float *d_out32, double *d_out64, void *stream);
 
 /*
+ * The per-k-mer feature CSV of kmerml/kmers/statistics.py:95-251 as text produced on the GPU (featcsv.cu).
+ *   kmerml_parse_kmer_lines      the lines "<digits>\t<count>" of a k{k}.txt image in HBM -> int64 value (leading
+ *                                zeros lost, as pandas reads the column, :261-271) and count; d_line_end[i] = byte
+ *                                offset of the terminator of line i; *h_bad != 0: some line is not of that form (or
+ *                                has more than 18 digits): the caller takes the reference's pandas path.  Synchronous.
+ *   kmerml_feature_keys          composition class of str(value) decoded 0 A 1 T 2 C 3 G else N (:248-251):
+ *                                length | A << 5 | C << 10 | G << 15 | T << 20 | N << 25 | CpG count << 30 | repeat << 35;
+ *                                every feature column of :149-240 is a function of it
+ *   kmerml_feature_line_lengths  bytes of "<letters>,<count>,<suffix>\n" per row (suffix = the class's formatted columns)
+ *   kmerml_feature_write_lines   those lines at the given offsets (exclusive prefix sums of the lengths)
+ */
+int kmerml_parse_kmer_lines(kmerml_ctx *ctx, const uint8_t *d_text, const int64_t *d_line_end, uint64_t n_lines,
+                            int64_t *d_value, int64_t *d_count, uint32_t *h_bad, void *stream);
+int kmerml_feature_keys(kmerml_ctx *ctx, const int64_t *d_value, uint64_t n_rows, int64_t *d_keys, void *stream);
+int kmerml_feature_line_lengths(kmerml_ctx *ctx, const int64_t *d_value, const int64_t *d_count,
+                                const int64_t *d_class, const int32_t *d_suffix_len, uint64_t n_rows,
+                                int64_t *d_len, void *stream);
+int kmerml_feature_write_lines(kmerml_ctx *ctx, const int64_t *d_value, const int64_t *d_count,
+                               const int64_t *d_class, const int64_t *d_suffix_off, const int32_t *d_suffix_len,
+                               const uint8_t *d_suffix_text, const int64_t *d_line_off, uint64_t n_rows,
+                               uint8_t *d_out, void *stream);
+
+/*
  * Summary of one k's count row as kmerml/utils/kmer_metadata.py:59-78 reports it for a k{k}.txt file (the
  * OBSERVED k-mers only): d_out uint64[8] = total_kmers, unique_kmers, max_count, min_count, the lower and the
  * upper middle count (their mean is the median; equal for an odd number), 0, 0.  No observed k-mer: total =

@@ -71,6 +71,10 @@ def load():
     p64 = ctypes.POINTER(ctypes.c_uint64)
     L.kmerml_format_kmer_file.argtypes = [vp, i32, vp, vp, u32, u64, vp, u64, p64, p64, vp]
     L.kmerml_format_kmer_lines.argtypes = [vp, i32, vp, vp, u64, vp, u64, p64, vp]
+    L.kmerml_parse_kmer_lines.argtypes = [vp, vp, vp, u64, vp, vp, ctypes.POINTER(ctypes.c_uint32), vp]
+    L.kmerml_feature_keys.argtypes = [vp, vp, u64, vp, vp]
+    L.kmerml_feature_line_lengths.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp]
+    L.kmerml_feature_write_lines.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u64, vp, vp]
     L.kmerml_count_stats.argtypes = [vp, vp, u64, vp, vp]
     L.kmerml_column_stats.argtypes = [vp, vp, i32, u64, i32, u64, vp, vp, vp, vp]
     L.kmerml_static_features.argtypes = [vp, i32, i32, vp, vp]
@@ -97,6 +101,7 @@ EXPORTS = [
     "kmerml_count_sparse", "kmerml_genome_stats", "kmerml_format_kmer_file", "kmerml_format_kmer_lines",
     "kmerml_count_sparse_range", "kmerml_merge_sparse", "kmerml_pairwise_distance_rows", "kmerml_sparse_fetch", "kmerml_ctx_set_host_threads", "kmerml_count_stats", "kmerml_column_stats",
     "kmerml_compact_row_bytes", "kmerml_count_dense_host_compact", "kmerml_compact_expand",
+    "kmerml_parse_kmer_lines", "kmerml_feature_keys", "kmerml_feature_line_lengths", "kmerml_feature_write_lines",
 ]
 
 
@@ -153,8 +158,11 @@ _contexts = {}
 
 
 def context(device=0):
-    """Process-wide context cache, one per device index."""
-    ctx = _contexts.get(device)
+    """Context cache: one per (device, host thread), as include/kmerml_b200.h asks (a context's workspaces are
+    not shared between threads)."""
+    import threading
+    key = (device, threading.get_ident())
+    ctx = _contexts.get(key)
     if ctx is None:
-        ctx = _contexts[device] = Context(device)
+        ctx = _contexts[key] = Context(device)
     return ctx

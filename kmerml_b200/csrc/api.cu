@@ -1065,6 +1065,51 @@ int kmerml_genome_stats(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes
     return launch_genome_stats(d_fasta, nbytes, (unsigned long long*)d_out, (cudaStream_t)stream);
 }
 
+int kmerml_parse_kmer_lines(kmerml_ctx* ctx, const uint8_t* d_text, const int64_t* d_line_end, uint64_t n_lines,
+                            int64_t* d_value, int64_t* d_count, uint32_t* h_bad, void* stream) {
+    if (!ctx || !h_bad || (n_lines && (!d_text || !d_line_end || !d_value || !d_count))) return fail(KMERML_ERR_ARG, "null pointer argument");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    Workspace& ws = ctx->ws[0];
+    int rc = ws.misc.ensure(256);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = launch_parse_kmer_lines(d_text, (const long long*)d_line_end, n_lines, (long long*)d_value, (long long*)d_count,
+                                 (unsigned int*)ws.misc.p, s);
+    if (rc) return rc;
+    KM_CUDA(cudaMemcpyAsync(h_bad, ws.misc.p, 4, cudaMemcpyDeviceToHost, s));
+    KM_CUDA(cudaStreamSynchronize(s));
+    return KMERML_OK;
+}
+
+int kmerml_feature_keys(kmerml_ctx* ctx, const int64_t* d_value, uint64_t n_rows, int64_t* d_keys, void* stream) {
+    if (!ctx || (n_rows && (!d_value || !d_keys))) return fail(KMERML_ERR_ARG, "null pointer argument");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    return launch_feature_keys((const long long*)d_value, n_rows, (long long*)d_keys, (cudaStream_t)stream);
+}
+
+int kmerml_feature_line_lengths(kmerml_ctx* ctx, const int64_t* d_value, const int64_t* d_count, const int64_t* d_class,
+                                const int32_t* d_suffix_len, uint64_t n_rows, int64_t* d_len, void* stream) {
+    if (!ctx || (n_rows && (!d_value || !d_count || !d_class || !d_suffix_len || !d_len))) return fail(KMERML_ERR_ARG, "null pointer argument");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    return launch_feature_line_len((const long long*)d_value, (const long long*)d_count, (const long long*)d_class,
+                                   (const int*)d_suffix_len, n_rows, (long long*)d_len, (cudaStream_t)stream);
+}
+
+int kmerml_feature_write_lines(kmerml_ctx* ctx, const int64_t* d_value, const int64_t* d_count, const int64_t* d_class,
+                               const int64_t* d_suffix_off, const int32_t* d_suffix_len, const uint8_t* d_suffix_text,
+                               const int64_t* d_line_off, uint64_t n_rows, uint8_t* d_out, void* stream) {
+    if (!ctx || (n_rows && (!d_value || !d_count || !d_class || !d_suffix_off || !d_suffix_len || !d_line_off || !d_out)))
+        return fail(KMERML_ERR_ARG, "null pointer argument");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    return launch_feature_write((const long long*)d_value, (const long long*)d_count, (const long long*)d_class,
+                                (const long long*)d_suffix_off, (const int*)d_suffix_len, d_suffix_text,
+                                (const long long*)d_line_off, n_rows, d_out, (cudaStream_t)stream);
+}
+
 int kmerml_count_stats(kmerml_ctx* ctx, const uint32_t* d_counts, uint64_t n_bins, uint64_t* d_out, void* stream) {
     if (!ctx || !d_out || (n_bins && !d_counts)) return fail(KMERML_ERR_ARG, "null pointer argument");
     DeviceGuard guard(ctx->device);

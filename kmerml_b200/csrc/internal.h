@@ -135,6 +135,16 @@ void host_pool_destroy(HostPool* p);
 void host_pool_submit(HostPool* p, std::function<void()> f);
 int host_pool_size(const HostPool* p);
 
+// ---- feature CSV text (featcsv.cu) ----------------------------------------------
+int launch_parse_kmer_lines(const uint8_t* d_text, const long long* d_line_end, uint64_t n_lines, long long* d_value,
+                            long long* d_count, unsigned int* d_bad, cudaStream_t s);
+int launch_feature_keys(const long long* d_value, uint64_t n_rows, long long* d_keys, cudaStream_t s);
+int launch_feature_line_len(const long long* d_value, const long long* d_count, const long long* d_cls,
+                            const int* d_suffix_len, uint64_t n_rows, long long* d_len, cudaStream_t s);
+int launch_feature_write(const long long* d_value, const long long* d_count, const long long* d_cls,
+                         const long long* d_suffix_off, const int* d_suffix_len, const uint8_t* d_suffix_text,
+                         const long long* d_line_off, uint64_t n_rows, uint8_t* d_out, cudaStream_t s);
+
 // ---- reductions (stats.cu) ------------------------------------------------------
 size_t count_stats_workspace();
 int launch_count_stats(const uint32_t* d_counts, uint64_t n_bins, void* workspace, unsigned long long* d_out, cudaStream_t s);

@@ -85,7 +85,7 @@ class KmerExtractor:
         for i, o in enumerate(offs_h):
             o = int(o)
             end = o
-            limit = min(len(raw), o + 65536)
+            limit = len(raw)
             while end < limit and raw[end] not in (10, 13):
                 end += 1
             title = bytes(raw[o + 1:end]).decode("utf-8", "replace").rstrip()

@@ -88,7 +88,25 @@ def features_from_digits(values, wanted):
     n_c = (digits == 2).sum(1)
     n_g = (digits == 3).sum(1)
     n_n = ((digits >= 4) & (digits != 255)).sum(1)
+    cpg = ((digits[:, :-1] == 2) & (digits[:, 1:] == 3)).sum(1) if width > 1 else np.zeros(rows, np.int64)
+    rep = np.zeros(rows, dtype=bool)
+    sym = np.where(digits == 255, 250, np.minimum(digits, 4))           # every non-ACGT digit decodes to 'N'
+    for i in range(width - 3):
+        both = (digits[:, i] != 255)
+        rep |= both & (sym[:, i] == sym[:, i + 2]) & (sym[:, i + 1] == sym[:, i + 3])
+    cols.update(columns_from_composition(nd, n_a, n_c, n_g, n_t, n_n, cpg, rep.astype(np.int64), wanted))
+    return cols
+
+
+def columns_from_composition(nd, n_a, n_c, n_g, n_t, n_n, cpg, rep, wanted):
+    """The feature columns of statistics.py:149-240 from a k-mer's composition (length, letter counts, CpG count,
+    repeat flag): all of them are functions of it.  Shared by the pandas path (per row) and the GPU text path (per
+    composition class, kmerml_feature_keys)."""
+    nd = np.asarray(nd, dtype=np.int64)
+    n_a, n_c, n_g, n_t, n_n = (np.asarray(x, dtype=np.int64) for x in (n_a, n_c, n_g, n_t, n_n))
+    cpg = np.asarray(cpg, dtype=np.int64)
     nf = nd.astype(np.float64)
+    cols = {}
     if "gc_content" in wanted:
         cols["gc_percent"] = ((n_g + n_c) / nf) * 100
     if "base_counts" in wanted:
@@ -97,7 +115,6 @@ def features_from_digits(values, wanted):
         for name, cnt in (("A", n_a), ("C", n_c), ("G", n_g), ("T", n_t)):
             cols[f"{name}_present"] = (cnt > 0).astype(np.int64)
     if "cpg_sites" in wanted:
-        cpg = ((digits[:, :-1] == 2) & (digits[:, 1:] == 3)).sum(1) if width > 1 else np.zeros(rows, np.int64)
         cols["cpg_count"] = cpg
         prod = (n_c / nf) * (n_g / nf)
         expected = np.where(prod > 0, prod * (nd - 1), 0.001)
@@ -115,16 +132,11 @@ def features_from_digits(values, wanted):
                 u //= 64
             nn_, nt_, ng_, nc_, na_ = parts
             table[i] = _entropy_of([na_, nc_, ng_, nt_, nn_], int(u))
-        ent = table[inverse.ravel()]
+        ent = table[inverse.ravel()] if key.size else np.zeros(0)
         cols["shannon_entropy"] = ent
         cols["normalized_entropy"] = ent / 2.0
     if "repeats" in wanted:
-        rep = np.zeros(rows, dtype=bool)
-        sym = np.where(digits == 255, 250, np.minimum(digits, 4))       # every non-ACGT digit decodes to 'N'
-        for i in range(width - 3):
-            both = (digits[:, i] != 255)
-            rep |= both & (sym[:, i] == sym[:, i + 2]) & (sym[:, i + 1] == sym[:, i + 3])
-        cols["has_repeat"] = rep.astype(np.int64)
+        cols["has_repeat"] = np.asarray(rep, dtype=np.int64)
     return cols
 
 
@@ -198,10 +210,76 @@ def _fast_csv(frames, genome_size):
     return "\n".join(out) + "\n"
 
 
+def _gpu_available():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def gpu_feature_text(kmer_file, k_val, wanted, tail, device=None):
+    """The CSV lines (no header) the reference writes for one k{k}.txt, produced on the GPU: the file's bytes are
+    parsed, classified by composition, sized and written by the kernels of csrc/featcsv.cu; the host formats ONE
+    suffix string per composition class that occurs (pandas' own formatting).  Returns bytes, or None when the file
+    is not of the plain "<digits>\t<count>" form (the caller then takes the pandas path)."""
+    import ctypes
+    import gzip
+    import torch
+    from .. import _lib
+    raw = gzip.open(kmer_file, "rb").read() if str(kmer_file).endswith(".gz") else Path(kmer_file).read_bytes()
+    if not raw:
+        return None
+    dev = torch.device(device if device is not None else "cuda")
+    L = _lib.load()
+    ctx = _lib.context(dev.index if dev.index is not None else torch.cuda.current_device())
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    text = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+    ends = torch.nonzero(text == 10).flatten()
+    if raw[-1] != 10:
+        ends = torch.cat([ends, torch.tensor([len(raw)], dtype=torch.int64, device=dev)])
+    n = int(ends.numel())
+    value = torch.empty(n, dtype=torch.int64, device=dev)
+    count = torch.empty(n, dtype=torch.int64, device=dev)
+    bad = ctypes.c_uint32(0)
+    _lib.check(L.kmerml_parse_kmer_lines(ctx.handle, text.data_ptr(), ends.data_ptr(), n, value.data_ptr(), count.data_ptr(),
+                                         ctypes.byref(bad), stream))
+    if bad.value or n == 0:
+        return None
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    _lib.check(L.kmerml_feature_keys(ctx.handle, value.data_ptr(), n, keys.data_ptr(), stream))
+    uniq, cls = torch.unique(keys, return_inverse=True)
+    u = uniq.cpu().numpy()
+    field = lambda shift, bits: (u >> shift) & ((1 << bits) - 1)                     # noqa: E731
+    cols = {"k": np.full(u.size, k_val)}
+    cols.update(columns_from_composition(field(0, 5), field(5, 5), field(10, 5), field(15, 5), field(20, 5), field(25, 5),
+                                         field(30, 5), field(35, 1), wanted))
+    lines = pd.DataFrame(cols).to_csv(index=False, header=False, lineterminator="\n").split("\n")[:u.size]
+    suffix = [(ln + tail).encode() for ln in lines]
+    lens = np.fromiter((len(x) for x in suffix), dtype=np.int32, count=len(suffix))
+    offs = np.concatenate(([0], np.cumsum(lens)[:-1])).astype(np.int64)
+    d_suffix = torch.frombuffer(bytearray(b"".join(suffix) or b"\0"), dtype=torch.uint8).to(dev)
+    d_lens, d_offs = torch.from_numpy(lens).to(dev), torch.from_numpy(offs).to(dev)
+    cls = cls.contiguous()
+    line_len = torch.empty(n, dtype=torch.int64, device=dev)
+    _lib.check(L.kmerml_feature_line_lengths(ctx.handle, value.data_ptr(), count.data_ptr(), cls.data_ptr(), d_lens.data_ptr(),
+                                             n, line_len.data_ptr(), stream))
+    line_off = torch.cumsum(line_len, 0) - line_len
+    total = int((line_off[-1] + line_len[-1]).item())
+    out = torch.empty(total, dtype=torch.uint8, device=dev)
+    _lib.check(L.kmerml_feature_write_lines(ctx.handle, value.data_ptr(), count.data_ptr(), cls.data_ptr(), d_offs.data_ptr(),
+                                            d_lens.data_ptr(), d_suffix.data_ptr(), line_off.data_ptr(), n, out.data_ptr(),
+                                            stream))
+    return out.cpu().numpy().tobytes()
+
+
 class KmerFeatureExtractor:
     """Extract machine-learning features from k-mer count files."""
 
-    def __init__(self, input_paths=None, output_dir=None, metadata_file=None):
+    def __init__(self, input_paths=None, output_dir=None, metadata_file=None, *, device="auto"):
+        # device: "auto" = the GPU text path when a CUDA device is there (byte-identical output), None / "cpu" = the
+        # vectorised pandas path only
+        self.device = device
         self.input_paths = [Path(p) for p in input_paths] if input_paths else []
         self.output_dir = Path(output_dir) if output_dir else Path("kmer_features")
         self.output_dir.mkdir(exist_ok=True, parents=True)
@@ -234,11 +312,19 @@ class KmerFeatureExtractor:
         if hasattr(self, "metadata_manager"):
             genome_size = self.metadata_manager.get_genome_size(organism)
         frames = []
+        use_gpu = self.device not in (None, "cpu") and _gpu_available()
+        tail = f",{genome_size}" if genome_size else ""
         for kmer_file in kmer_files:
             k_val = self._extract_k_from_filename(kmer_file.name)
             if k_val is None:
                 print(f"Warning: Could not extract k value from {kmer_file}")
                 continue
+            if use_gpu:
+                body = gpu_feature_text(kmer_file, k_val, required_features, tail,
+                                        None if self.device == "auto" else self.device)
+                if body is not None:
+                    frames.append(body)                  # (bytes: this file's CSV lines, already formatted)
+                    continue
             table = self._load_kmer_file(kmer_file)
             if len(table):
                 frames.append(self._extract_kmer_features(table, k_val, organism, required_features))
@@ -246,6 +332,26 @@ class KmerFeatureExtractor:
             print(f"No features extracted for {organism}")
             return None
         output_file = self.output_dir / f"{organism}_kmer_features.csv"
+        if any(isinstance(f, bytes) for f in frames):
+            # header as DataFrame.to_csv writes it: the columns of any frame (all files share them)
+            probe = self._extract_kmer_features(pd.DataFrame({"kmer": np.array([0], np.int64), "count": np.array([1], np.int64)}),
+                                                0, organism, required_features)
+            header = ",".join(list(probe.columns) + (["genome_size"] if genome_size else [])) + "\n"
+            with open(output_file, "wb") as fh:
+                fh.write(header.encode())
+                for f in frames:
+                    if isinstance(f, bytes):
+                        fh.write(f)
+                        continue
+                    t = _fast_csv([f], genome_size)
+                    if t is None:
+                        g = f.copy()
+                        if genome_size:
+                            g["genome_size"] = genome_size
+                        t = "\n" + g.to_csv(index=False, header=False)
+                    fh.write(t.split("\n", 1)[1].encode())
+            print(f"Created feature CSV for {organism}: {output_file}")
+            return output_file
         text = _fast_csv(frames, genome_size)
         if text is not None:
             with open(output_file, "w", newline="") as fh:
@@ -261,7 +367,9 @@ class KmerFeatureExtractor:
     def _extract_kmer_features(self, df, k_val, organism, required_features):
         """DataFrame of the feature columns for one k-mer file (all rows at once)."""
         col = df["kmer"]
-        if pd.api.types.is_integer_dtype(col.dtype):
+        # (a digit column whose values exceed int64 but fit uint64 -- k = 20 without a leading C / G -- goes through
+        # the string path like the reference's str(int))
+        if pd.api.types.is_integer_dtype(col.dtype) and col.dtype != np.uint64:
             cols = features_from_digits(col.to_numpy(), required_features)
         else:
             decoded = [self._decode_kmer(x) if str(x).isdigit() else x for x in col.tolist()]

@@ -213,6 +213,62 @@ def test_tensor_core_gram_is_exact():
             assert np.allclose(got, alt, rtol=1e-12, atol=1e-12, equal_nan=True)
 
 
+def test_feature_csv_text_from_the_gpu(tmp_path):
+    """KmerFeatureExtractor with the GPU text path (csrc/featcsv.cu: parse, classify by composition, size, write)
+    writes the same bytes as its pandas path -- which tests/test_host_layer.py pins on the reference's own CSVs
+    (statistics.py:95-251, leading-zero quirk included)."""
+    import gzip
+    import json
+    import os
+    from helpers import GOLDEN
+    from kmerml_b200.kmers.statistics import KmerFeatureExtractor
+    with open(os.path.join(GOLDEN, "stats_cases.json")) as f:
+        stats = json.load(f)
+    by_name = {c["name"]: c for c in golden_extract_cases()}
+    n = 0
+    for ci, case in enumerate(stats):
+        src = by_name[case["name"]]
+        kdir = tmp_path / f"c{ci}" / "kmers" / "GCF_900000001_1"
+        kdir.mkdir(parents=True)
+        paths = []
+        for k, text in src["files"].items():
+            p = kdir / f"k{k}.txt"
+            p.write_text(text)
+            paths.append(p)
+        outs = {}
+        for dev in ("auto", None):
+            with contextlib.redirect_stdout(io.StringIO()):
+                res = KmerFeatureExtractor(input_paths=paths, output_dir=tmp_path / f"c{ci}" / f"f_{dev}", device=dev
+                                           ).extract_features(case["feature_set"])
+            path = res["GCF_900000001_1"]
+            outs[dev] = path.read_bytes() if path is not None else None
+        assert outs["auto"] == outs[None], (case["name"], case["feature_set"])
+        if case["csv"] is not None and outs["auto"].decode() == case["csv"]:
+            n += 1
+    assert n >= 15                                             # byte-identical to the reference's CSV (entropy ulps aside)
+    # a larger file (every 8-mer, counts up to 10^6), gzip input, a genome_size column, and a file the GPU parser
+    # hands back to pandas (letters instead of digits)
+    rng = np.random.default_rng(5)
+    kdir = tmp_path / "big" / "kmers" / "GCF_900000002_1"
+    kdir.mkdir(parents=True)
+    digits = np.array(["".join("0231"[(i >> (2 * (7 - j))) & 3] for j in range(8)) for i in range(4 ** 8)])
+    order = rng.permutation(4 ** 8)
+    text = "".join(f"{digits[i]}\t{int(c)}\n" for i, c in zip(order, rng.integers(1, 10 ** 6, 4 ** 8)))
+    (kdir / "k8.txt").write_text(text)
+    with gzip.open(kdir / "k5.txt.gz", "wt") as f:
+        f.write("".join(f"{digits[i][:5]}\t{i + 1}\n" for i in order[:700]))
+    (kdir / "k3.txt").write_text("ACG\t5\nTTT\t2\n")
+    meta = tmp_path / "big" / "genome_metadata.json"
+    meta.write_text(json.dumps({"GCF_900000002_1": {"total_size": 12157105}}))
+    outs = {}
+    for dev in ("auto", None):
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = KmerFeatureExtractor(input_paths=[tmp_path / "big" / "kmers"], output_dir=tmp_path / "big" / f"f_{dev}",
+                                       metadata_file=meta, device=dev).extract_features()
+        outs[dev] = res["GCF_900000002_1"].read_bytes()
+    assert outs["auto"] == outs[None] and outs["auto"].count(b"\n") == 1 + 4 ** 8 + 700 + 2
+
+
 def test_distance_row_blocks_match_full_matrix():
     """kmerml_pairwise_distance_rows: the row blocks the ranks of a sharded distance computation own,
     concatenated, are bit-identical to the single-call matrix (exact integer Gram entries)."""
