@@ -280,6 +280,12 @@ def run_c5(torch, dist, device, rank, world, steps, warmup, scale=1.0, check_sca
 
     ms, (keys, counts, first, windows) = T.timed(step, steps, warmup)
     torch.cuda.synchronize()
+    # one more, untimed, step with a synchronisation after every phase: where the time goes
+    phases = {}
+    del keys, counts, first
+    keys, counts, first, windows = kdist.count_sparse_sharded(fasta, k, canonical=True, phase_ms=phases)
+    phases.pop("start", None)
+    phases = {name: T.max_over_ranks(v) for name, v in phases.items()}
     n_local = int(keys.numel())
     asc = bool((keys[1:] > keys[:-1]).all().item()) if n_local > 1 else True
     lo = int(keys[0].item()) if n_local else None
@@ -300,7 +306,7 @@ def run_c5(torch, dist, device, rank, world, steps, warmup, scale=1.0, check_sca
     return {"workload": f"C5: one {bases / 1e9:.2f} Gbp genome with N runs, k=21 canonical, per-range sort-reduce on {world} GPU(s) + "
                         f"all-to-all by key range + merge", "ms": ms, "Gbp/s": bases / (ms * 1e-3) / 1e9,
             "collective": "all_to_all_single x3 (k-mer u64, count u32, first offset u32) of pre-reduced triples" if world > 1 else None,
-            "windows": int(windows), "distinct_kmers": int(distinct),
+            "phase_ms_synchronised": phases, "windows": int(windows), "distinct_kmers": int(distinct),
             "nvlink_bytes": int(distinct * 16 * (world - 1) / world) if world > 1 else 0,
             "bit_exact_vs_single_gpu": {"genome_mbp": round(small_mbp, 1), "ok": T.all_true(small_ok)},
             "full_size_invariants": {"sum_counts_equals_windows": total_counts == float(windows),

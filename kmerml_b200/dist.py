@@ -245,7 +245,8 @@ def key_owner_splits(keys, k, world_size):
     return torch.bincount(owner, minlength=world_size).cpu().tolist()
 
 
-def count_sparse_sharded(fasta, k, *, min_record_len=None, canonical=False, count_range=None, merge=None):
+def count_sparse_sharded(fasta, k, *, min_record_len=None, canonical=False, count_range=None, merge=None,
+                         phase_ms=None):
     """Distinct k-mers (k <= 32) of ONE genome resident on every rank's device, counted cooperatively.
     Rank r counts byte range r, the partial results are exchanged with one all-to-all per tensor, and rank r
     returns the k-mers of key range r: (keys, counts, first, windows of the whole genome).  Concatenating the
@@ -263,7 +264,21 @@ def count_sparse_sharded(fasta, k, *, min_record_len=None, canonical=False, coun
         count_range = lambda f, b, e, kk, ml, c: engine.count_sparse_range_device(f, b, e, kk, min_record_len=ml, canonical=c)
     if merge is None:
         merge = engine.merge_sparse_device
+    import time as _time
+
+    def mark(name, t_prev):
+        """(diagnostic only: phase_ms = {} makes every phase end with a device synchronisation)"""
+        if phase_ms is None:
+            return t_prev
+        if fasta.is_cuda:
+            torch.cuda.synchronize()
+        now = _time.perf_counter()
+        phase_ms[name] = phase_ms.get(name, 0.0) + (now - t_prev) * 1e3
+        return now
+
+    tm = mark("start", _time.perf_counter())
     keys, counts, first, windows = count_range(fasta, begin, end, int(k), min_record_len, canonical)
+    tm = mark("range_sort_reduce", tm)
     if world == 1:
         return keys, counts, first, windows
     send = key_owner_splits(keys, k, world)
@@ -272,6 +287,7 @@ def count_sparse_sharded(fasta, k, *, min_record_len=None, canonical=False, coun
     dist.all_to_all_single(recv_t, send_t)
     recv = recv_t.cpu().tolist()
     total = int(sum(recv))
+    tm = mark("owner_splits", tm)
     out = []
     dev = keys.device
     parts = [keys, counts, first]
@@ -285,7 +301,9 @@ def count_sparse_sharded(fasta, k, *, min_record_len=None, canonical=False, coun
         out.append(r)
     w = torch.tensor([windows], dtype=torch.int64, device=dev)
     dist.all_reduce(w, op=dist.ReduceOp.SUM)
-    if dev.type == "cuda":
-        torch.cuda.empty_cache()
+    tm = mark("all_to_all", tm)
+    if dev.type == "cuda" and torch.cuda.mem_get_info(dev)[0] < 96 * total:
+        torch.cuda.empty_cache()                         # the merge workspace (library-owned) needs real free memory
     mk, mc, mf = merge(out[0], out[1], out[2], int(k))
+    tm = mark("merge", tm)
     return mk, mc, mf, int(w.item())
