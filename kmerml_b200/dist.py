@@ -232,11 +232,18 @@ SPARSE_RANGE_ALIGN = 131072
 def key_owner_splits(keys, k, world_size):
     """keys: int64 tensor holding ascending uint64 2-bit packed k-mers.  Rank r owns the k-mers whose top
     16 bits t satisfy (t * world_size) >> 16 == r, so owners are ascending along `keys`; returns the number
-    of keys per owner (list of world_size ints)."""
+    of keys per owner (list of world_size ints).  The keys are sorted, so the owner boundaries are found by a
+    binary search for the first key of every rank (no pass over the keys)."""
     import torch
     bits = 2 * int(k)
     if keys.numel() == 0:
         return [0] * world_size
+    if 16 <= bits < 64:
+        # owner(key) >= r  <=>  top16 >= ceil(r * 65536 / world)  <=>  key >= that << (bits - 16)
+        firsts = [((r * 65536 + world_size - 1) // world_size) << (bits - 16) for r in range(1, world_size)]
+        cut = torch.searchsorted(keys, torch.tensor(firsts, dtype=torch.int64, device=keys.device)).cpu().tolist() if firsts else []
+        edges = [0] + cut + [int(keys.numel())]
+        return [edges[i + 1] - edges[i] for i in range(world_size)]
     if bits >= 16:
         top = (keys >> (bits - 16)) & 0xFFFF
     else:
@@ -262,6 +269,7 @@ def count_sparse_sharded(fasta, k, *, min_record_len=None, canonical=False, coun
     begin, end = chunk_ranges(int(fasta.numel()), world, tile=SPARSE_RANGE_ALIGN)[rank]
     if count_range is None:
         count_range = lambda f, b, e, kk, ml, c: engine.count_sparse_range_device(f, b, e, kk, min_record_len=ml, canonical=c)
+    merge_takes_sort_k = merge is None                    # (the injected CPU stand-ins sort whole keys)
     if merge is None:
         merge = engine.merge_sparse_device
     import time as _time
@@ -302,8 +310,13 @@ def count_sparse_sharded(fasta, k, *, min_record_len=None, canonical=False, coun
     w = torch.tensor([windows], dtype=torch.int64, device=dev)
     dist.all_reduce(w, op=dist.ReduceOp.SUM)
     tm = mark("all_to_all", tm)
-    if dev.type == "cuda" and torch.cuda.mem_get_info(dev)[0] < 96 * total:
+    if dev.type == "cuda" and torch.cuda.mem_get_info(dev)[0] < 64 * total:
         torch.cuda.empty_cache()                         # the merge workspace (library-owned) needs real free memory
-    mk, mc, mf = merge(out[0], out[1], out[2], int(k))
+    # all keys a rank receives share the bits that select the rank (world a power of two: the top log2(world)
+    # bits), so the merge's radix sort can leave them out: 2 (k - 1) bits are 5 byte-passes instead of 6 at k = 21
+    k_sort = int(k)
+    if world & (world - 1) == 0 and 2 * int(k) >= 16 and merge_takes_sort_k:
+        k_sort = int(k) - (world.bit_length() - 1) // 2
+    mk, mc, mf = merge(out[0], out[1], out[2], k_sort)
     tm = mark("merge", tm)
     return mk, mc, mf, int(w.item())
