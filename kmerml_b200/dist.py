@@ -310,8 +310,6 @@ def count_sparse_sharded(fasta, k, *, min_record_len=None, canonical=False, coun
     w = torch.tensor([windows], dtype=torch.int64, device=dev)
     dist.all_reduce(w, op=dist.ReduceOp.SUM)
     tm = mark("all_to_all", tm)
-    if dev.type == "cuda" and torch.cuda.mem_get_info(dev)[0] < 64 * total:
-        torch.cuda.empty_cache()                         # the merge workspace (library-owned) needs real free memory
     # all keys a rank receives share the bits that select the rank (world a power of two: the top log2(world)
     # bits), so the merge's radix sort can leave them out: 2 (k - 1) bits are 5 byte-passes instead of 6 at k = 21
     k_sort = int(k)

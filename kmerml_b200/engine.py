@@ -310,6 +310,18 @@ def count_dense_range_device(fasta, begin, end, k_values, min_record_len=None, c
     return counts, totals
 
 
+def _retry_after_cache_release(call):
+    """The library's workspaces are its own device allocations: when one cannot grow because torch's caching
+    allocator sits on freed blocks, release them and try once more (the workspace persists afterwards)."""
+    try:
+        return call()
+    except _lib.KmermlError as exc:
+        if "allocation" not in str(exc):
+            raise
+        torch.cuda.empty_cache()
+        return call()
+
+
 def count_sparse_device(fasta, k, *, min_record_len=None, canonical=False, want_first=True):
     """Distinct k-mers of ONE genome for any k <= 32 (meant for k > 14): returns
     (keys int64[n] -- uint64 2-bit packed, sorted --, counts int32[n], first int32[n] or None, windows)."""
@@ -356,10 +368,10 @@ def count_sparse_range_device(fasta, begin, end, k, *, min_record_len=None, cano
     counts = torch.empty(cap, dtype=torch.int32, device=fasta.device)
     first = torch.empty(cap, dtype=torch.int32, device=fasta.device)
     nu, nw = ctypes.c_uint64(0), ctypes.c_uint64(0)
-    _lib.check(L.kmerml_count_sparse_range(ctx.handle, fasta.data_ptr() if fasta.numel() else None, fasta.numel(),
-                                           int(begin), int(end), int(k), int(min_record_len or 0),
-                                           _lib.FLAG_CANONICAL if canonical else 0, keys.data_ptr(), counts.data_ptr(),
-                                           first.data_ptr(), cap, ctypes.byref(nu), ctypes.byref(nw), stream))
+    _retry_after_cache_release(lambda: _lib.check(L.kmerml_count_sparse_range(
+        ctx.handle, fasta.data_ptr() if fasta.numel() else None, fasta.numel(), int(begin), int(end), int(k),
+        int(min_record_len or 0), _lib.FLAG_CANONICAL if canonical else 0, keys.data_ptr(), counts.data_ptr(),
+        first.data_ptr(), cap, ctypes.byref(nu), ctypes.byref(nw), stream)))
     n = int(nu.value)
     if n > cap:
         keys, counts, first = _sparse_fetch(ctx, L, n, fasta.device, True, stream)
@@ -380,8 +392,9 @@ def merge_sparse_device(keys, counts, first, k):
     oc = torch.empty(n, dtype=torch.int32, device=keys.device)
     of = torch.empty(n, dtype=torch.int32, device=keys.device)
     nu = ctypes.c_uint64(0)
-    _lib.check(L.kmerml_merge_sparse(ctx.handle, int(k), keys.data_ptr(), counts.data_ptr(), first.data_ptr(), n,
-                                     ok.data_ptr(), oc.data_ptr(), of.data_ptr(), n, ctypes.byref(nu), stream))
+    _retry_after_cache_release(lambda: _lib.check(L.kmerml_merge_sparse(
+        ctx.handle, int(k), keys.data_ptr(), counts.data_ptr(), first.data_ptr(), n,
+        ok.data_ptr(), oc.data_ptr(), of.data_ptr(), n, ctypes.byref(nu), stream)))
     m = int(nu.value)
     return ok[:m], oc[:m], of[:m]
 
