@@ -162,6 +162,45 @@ def oracle_seconds(data, ks):
     return time.perf_counter() - t0
 
 
+def _unmodified_reference_worker(job):
+    """(child process) the UNMODIFIED reference from baseline/_ref under the Bio.SeqIO shim: one genome, k list."""
+    fasta_path, out_dir, ks = job
+    sys.path.insert(0, os.path.join(ROOT, "tests", "_ref"))          # Bio.SeqIO shim (biopython is not installable offline)
+    sys.path.insert(1, os.path.join(ROOT, "baseline", "_ref"))
+    import contextlib
+    import io
+    from kmerml.kmers.generate import KmerExtractor
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        KmerExtractor(output_dir=out_dir, compress=False).extract_kmers_from_fasta(fasta_path, list(ks))
+    return time.perf_counter() - t0
+
+
+def time_unmodified_reference(ks, cores, bases_per_genome=60_000):
+    """The unmodified Python reference (pip-installed into baseline/_ref from the reference tree) on
+    `cores` processes, one small C2-shaped genome each; None when baseline/_ref is absent."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "kmerml")):
+        return None
+    import multiprocessing as mp
+    import tempfile
+    from kmerml_b200 import synth
+    with tempfile.TemporaryDirectory() as td:
+        jobs = []
+        for i in range(cores):
+            g = synth.fasta_bytes([bases_per_genome // 2, bases_per_genome - bases_per_genome // 2], seed=5000 + i)
+            path = os.path.join(td, f"GCF_90000{i:04d}_1.fa")
+            g.tofile(path)
+            jobs.append((path, os.path.join(td, f"out{i}"), ks))
+        t0 = time.perf_counter()
+        with mp.get_context("spawn").Pool(cores) as pool:
+            pool.map(_unmodified_reference_worker, jobs)
+        wall = time.perf_counter() - t0
+    total = cores * bases_per_genome
+    return {"value": total / wall / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{cores} genomes of {bases_per_genome} bp, k={ks[0]}..{ks[-1]}, KmerExtractor.extract_kmers_from_fasta of the "
+                      f"unmodified reference (baseline/_ref) in {cores} processes, wall {wall:.1f} s incl. process start-up"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port: the reference itself is
     pure Python + biopython and cannot travel to the GPU box) on all host cores."""
@@ -199,9 +238,14 @@ def run_reference(args):
         "config": {"workload": "C2 sample on host cores: " + sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "oracle C port of kmerml/kmers/generate.py:36-58; the unmodified Python reference measured "
-                "0.034 Mbp/s on one core for k=1..12 in the build container (tests/golden/ref_timing.json)",
+        "note": "oracle C port of kmerml/kmers/generate.py:36-58 (the conservative baseline: ~100x faster than the Python it "
+                "restates); the unmodified Python reference measured 0.034 Mbp/s on one core for k=1..12 in the build "
+                "container (tests/golden/ref_timing.json) and is timed on this box in `unmodified_reference`",
     }
+    try:
+        line["unmodified_reference"] = time_unmodified_reference(ks, cores)
+    except Exception as exc:                                      # report, never fake
+        line["unmodified_reference"] = {"error": repr(exc)[:200]}
     print(json.dumps(line))
     return 0
 
