@@ -181,6 +181,24 @@ int kmerml_merge_sparse(kmerml_ctx *ctx, int k, const uint64_t *d_keys, const ui
                         uint32_t *d_first_out, uint64_t out_cap, uint64_t *h_unique, void *stream);
 
 /*
+ * Multi-GPU units of the sparse path with RAW routing (each rank sorts once): kmerml_emit_sparse_range emits the windows
+ * of a byte range -- 2-bit packed k-mer (canonical with the flag) and the byte offset of its last base -- grouped by the
+ * rank that owns them: owner = the top owner_bits bits of the 2k-bit k-mer (2^owner_bits ranks; one radix pass);
+ * h_owner_counts[2^owner_bits] receives the group sizes, *h_windows their sum (nothing is written when it exceeds
+ * out_cap; at most one window ends at every byte of the range).  After the all-to-all every rank calls
+ * kmerml_reduce_sparse_windows on what it received: one radix sort over the low sort_bits bits (2k - owner_bits: the
+ * owner bits are equal on a rank) + one fused segmented reduction -> distinct k-mers ascending, counts, smallest
+ * offset; *h_unique > out_cap: fetch with kmerml_sparse_fetch.  Both synchronous.
+ */
+int kmerml_emit_sparse_range(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbytes, uint64_t range_begin,
+                             uint64_t range_end, int k, int min_record_len, unsigned flags, int owner_bits,
+                             uint64_t *d_keys, uint32_t *d_ends, uint64_t out_cap, uint64_t *h_windows,
+                             uint64_t *h_owner_counts, void *stream);
+int kmerml_reduce_sparse_windows(kmerml_ctx *ctx, int sort_bits, const uint64_t *d_keys, const uint32_t *d_ends,
+                                 uint64_t n, uint64_t *d_keys_out, uint32_t *d_counts_out, uint32_t *d_first_out,
+                                 uint64_t out_cap, uint64_t *h_unique, void *stream);
+
+/*
  * Byte offset (within the genome) of the last base of the first window of every
  * k-mer, UINT32_MAX where the k-mer never occurs: sorting the observed bins by
  * this value gives dict insertion order, i.e. the line order of k{k}.txt

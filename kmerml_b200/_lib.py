@@ -51,6 +51,7 @@ def load():
     L.kmerml_ctx_set_host_threads.argtypes = [vp, i32]
     L.kmerml_row_len.restype = u64
     L.kmerml_row_len.argtypes = [vp, i32]
+    p64 = ctypes.POINTER(ctypes.c_uint64)
     L.kmerml_count_dense_batch.argtypes = [vp, vp, vp, i32, vp, i32, i32, u32, vp, u64, vp, u64, vp, vp]
     L.kmerml_count_dense_host.argtypes = [vp, vp, vp, i32, vp, i32, i32, u32, vp, u64, vp, u64, vp]
     L.kmerml_compact_row_bytes.restype = u64
@@ -62,13 +63,14 @@ def load():
                                       ctypes.POINTER(ctypes.c_uint64), vp]
     L.kmerml_count_sparse_range.argtypes = [vp, vp, u64, u64, u64, i32, i32, u32, vp, vp, vp, u64,
                                             ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), vp]
+    L.kmerml_emit_sparse_range.argtypes = [vp, vp, u64, u64, u64, i32, i32, u32, i32, vp, vp, u64, p64, vp, vp]
+    L.kmerml_reduce_sparse_windows.argtypes = [vp, i32, vp, vp, u64, vp, vp, vp, u64, p64, vp]
     L.kmerml_sparse_fetch.argtypes = [vp, vp, vp, vp, u64, vp]
     L.kmerml_merge_sparse.argtypes = [vp, i32, vp, vp, vp, u64, vp, vp, vp, u64, ctypes.POINTER(ctypes.c_uint64), vp]
     L.kmerml_first_occurrence.argtypes = [vp, vp, u64, i32, i32, vp, vp]
     L.kmerml_find_records.argtypes = [vp, vp, u64, vp, u32, ctypes.POINTER(ctypes.c_uint32), vp]
     L.kmerml_records_short.argtypes = [vp, vp, u64, vp, u32, i32, vp, vp]
     L.kmerml_genome_stats.argtypes = [vp, vp, u64, vp, vp]
-    p64 = ctypes.POINTER(ctypes.c_uint64)
     L.kmerml_format_kmer_file.argtypes = [vp, i32, vp, vp, u32, u64, vp, u64, p64, p64, vp]
     L.kmerml_format_kmer_lines.argtypes = [vp, i32, vp, vp, u64, vp, u64, p64, vp]
     L.kmerml_parse_kmer_lines.argtypes = [vp, vp, vp, u64, vp, vp, ctypes.POINTER(ctypes.c_uint32), vp]
@@ -102,6 +104,7 @@ EXPORTS = [
     "kmerml_count_sparse_range", "kmerml_merge_sparse", "kmerml_pairwise_distance_rows", "kmerml_sparse_fetch", "kmerml_ctx_set_host_threads", "kmerml_count_stats", "kmerml_column_stats",
     "kmerml_compact_row_bytes", "kmerml_count_dense_host_compact", "kmerml_compact_expand",
     "kmerml_parse_kmer_lines", "kmerml_feature_keys", "kmerml_feature_line_lengths", "kmerml_feature_write_lines",
+    "kmerml_emit_sparse_range", "kmerml_reduce_sparse_windows",
 ]
 
 

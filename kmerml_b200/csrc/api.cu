@@ -1214,6 +1214,54 @@ static int count_sparse_core(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t n
     return rc;
 }
 
+int kmerml_emit_sparse_range(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin,
+                             uint64_t range_end, int k, int min_record_len, unsigned flags, int owner_bits, uint64_t* d_keys,
+                             uint32_t* d_ends, uint64_t out_cap, uint64_t* h_windows, uint64_t* h_owner_counts, void* stream) {
+    if (!ctx || !h_windows || !h_owner_counts) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (k < 1 || k > KMERML_MAX_K) return fail(KMERML_ERR_ARG, "k must be in 1..32");
+    if (owner_bits < 0 || owner_bits > 5 || owner_bits > 2 * k) return fail(KMERML_ERR_ARG, "owner_bits must be in 0..5");
+    if (nbytes && !d_fasta) return fail(KMERML_ERR_ARG, "d_fasta is null");
+    if (out_cap && (!d_keys || !d_ends)) return fail(KMERML_ERR_ARG, "null output pointer");
+    if (nbytes >= 0xFFFFFFFFull) return fail(KMERML_ERR_RANGE, "genome too large for 32-bit offsets");
+    if ((uintptr_t)d_fasta & 15) return fail(KMERML_ERR_ARG, "device pointers must be 16-byte aligned");
+    if (range_begin > range_end || range_end > nbytes) return fail(KMERML_ERR_ARG, "byte range outside the file");
+    if (range_begin % KMERML_SPARSE_RANGE_ALIGN || (range_end % KMERML_SPARSE_RANGE_ALIGN && range_end != nbytes))
+        return fail(KMERML_ERR_ARG, "byte range must be aligned to KMERML_SPARSE_RANGE_ALIGN");
+    int min_rec = min_record_len > 0 ? min_record_len : k;
+    if (min_rec < k) return fail(KMERML_ERR_ARG, "min_record_len must be >= k");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    Workspace& ws = ctx->ws[0];
+    const uint64_t cap = std::max<uint64_t>(range_end - range_begin, 1);
+    int rc = ws.part.ensure(sparse_workspace_bytes(cap, nbytes));
+    if (rc) return rc;
+    ctx->sparse_pending.valid = false;
+    return run_sparse_emit_by_owner(ws.part.p, d_fasta, nbytes, range_begin, range_end, k, min_rec,
+                                    (flags & KMERML_FLAG_CANONICAL) != 0, owner_bits, cap, d_keys, d_ends, out_cap, h_windows,
+                                    h_owner_counts, (cudaStream_t)stream);
+}
+
+int kmerml_reduce_sparse_windows(kmerml_ctx* ctx, int sort_bits, const uint64_t* d_keys, const uint32_t* d_ends, uint64_t n,
+                                 uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
+                                 uint64_t* h_unique, void* stream) {
+    if (!ctx || !h_unique) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (sort_bits < 1 || sort_bits > 64) return fail(KMERML_ERR_ARG, "sort_bits must be in 1..64");
+    if (n && (!d_keys || !d_ends)) return fail(KMERML_ERR_ARG, "null input pointer");
+    if (out_cap && (!d_keys_out || !d_counts_out)) return fail(KMERML_ERR_ARG, "null output pointer");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    Workspace& ws = ctx->ws[0];
+    const uint64_t cap = std::max<uint64_t>(n, 1);
+    int rc = ws.part.ensure(sparse_workspace_bytes(cap, 0));
+    if (rc) return rc;
+    rc = run_sparse_reduce_windows(ws.part.p, sort_bits, d_keys, d_ends, n, d_keys_out, d_counts_out, d_first_out, out_cap,
+                                   h_unique, &ctx->sparse_pending, (cudaStream_t)stream);
+    ctx->sparse_pending.cap = cap;
+    ctx->sparse_pending.nbytes = 0;
+    ctx->sparse_pending.workspace = ws.part.p;
+    return rc;
+}
+
 int kmerml_sparse_fetch(kmerml_ctx* ctx, uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_first, uint64_t out_cap,
                         void* stream) {
     if (!ctx || !d_keys || !d_counts) return fail(KMERML_ERR_ARG, "null pointer argument");

@@ -169,6 +169,14 @@ int run_sparse_in(void* workspace, const uint8_t* d_fasta, uint64_t nbytes, uint
                   int k, int min_rec, bool canonical, uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
                   uint64_t* h_unique, uint64_t* h_windows, SparsePending* pending, cudaStream_t s);
 
+int run_sparse_emit_by_owner(void* workspace, const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin,
+                             uint64_t range_end, int k, int min_rec, bool canonical, int owner_bits, uint64_t cap,
+                             uint64_t* d_keys_out, uint32_t* d_ends_out, uint64_t out_cap, uint64_t* h_windows,
+                             uint64_t* h_owner_counts, cudaStream_t s);
+int run_sparse_reduce_windows(void* workspace, int sort_bits, const uint64_t* d_keys, const uint32_t* d_ends, uint64_t n,
+                              uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
+                              uint64_t* h_unique, SparsePending* pending, cudaStream_t s);
+
 size_t merge_workspace_bytes(uint64_t n);
 int run_merge_sparse(void* workspace, int k, const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_first,
                      uint64_t n, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,

@@ -349,20 +349,16 @@ static int sparse_copy_out(const SparseWork& w, uint64_t* sorted_keys, uint32_t*
     return KMERML_OK;
 }
 
-// Emits, sorts and reduces.  On return (after a stream sync) *h_windows / *h_unique are valid; when
-// *h_unique > out_cap nothing was written to the outputs.
-int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, uint64_t range_end, int k, int min_rec,
-               bool canonical, const SparseWork& w, uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
-               uint64_t* h_unique, uint64_t* h_windows, SparsePending* pending, cudaStream_t s) {
-    if (pending) pending->valid = false;
+// Emit the windows of the byte range into w.keys_a / w.ends_a; *h_windows receives their number.
+static int sparse_emit_phase(const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, uint64_t range_end, int k,
+                             int min_rec, bool canonical, const SparseWork& w, uint64_t cap, uint64_t* h_windows,
+                             cudaStream_t s) {
     SparseParams P;
     P.k = k;
     P.min_rec = min_rec;
     P.canonical = canonical ? 1 : 0;
     P.mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
     KM_CUDA(cudaMemsetAsync(w.cursor, 0, 8, s));
-    KM_CUDA(cudaMemsetAsync(w.n_runs, 0, 8, s));
-    *h_unique = 0;
     *h_windows = 0;
     if (!nbytes) return KMERML_OK;
     const uint64_t slice_bytes = (uint64_t)SPARSE_TILE * SPARSE_TILES_PER_SLICE;
@@ -387,13 +383,22 @@ int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, ui
         set_error("internal: sparse window capacity exceeded");
         return KMERML_ERR_RANGE;
     }
+    return KMERML_OK;
+}
+
+// Sort the n windows in w.keys_a / w.ends_a by bits [0, sort_bits) of the key and reduce them.
+static int sparse_sort_reduce_phase(const SparseWork& w, uint64_t n, int sort_bits, uint64_t* d_keys_out, uint32_t* d_counts_out,
+                                    uint32_t* d_first_out, uint64_t out_cap, uint64_t* h_unique, SparsePending* pending,
+                                    cudaStream_t s) {
+    *h_unique = 0;
     if (!n) return KMERML_OK;
+    KM_CUDA(cudaMemsetAsync(w.n_runs, 0, 8, s));
     cub::DoubleBuffer<uint64_t> dk(w.keys_a, w.keys_b);
     cub::DoubleBuffer<uint32_t> dv(w.ends_a, w.ends_b);
     size_t tb = w.temp_bytes;
     // radix sort is stable and the emission order is arbitrary, so the first occurrence is the
     // MIN end offset of each run, not its first element
-    KM_CUDA(cub::DeviceRadixSort::SortPairs(w.temp, tb, dk, dv, (uint64_t)n, 0, 2 * k, s));
+    KM_CUDA(cub::DeviceRadixSort::SortPairs(w.temp, tb, dk, dv, (uint64_t)n, 0, sort_bits, s));
     uint64_t* sorted_keys = dk.Current();
     uint32_t* sorted_ends = dv.Current();
     uint64_t* uniq = dk.Alternate();
@@ -411,6 +416,79 @@ int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, ui
     }
     if (nu > out_cap) return KMERML_OK;             // caller sizes its outputs and fetches (kmerml_sparse_fetch)
     return sparse_copy_out(w, sorted_keys, sorted_ends, uniq, runs, n, nu, d_keys_out, d_counts_out, d_first_out, s);
+}
+
+// Emits, sorts and reduces.  On return (after a stream sync) *h_windows / *h_unique are valid; when
+// *h_unique > out_cap nothing was written to the outputs (kmerml_sparse_fetch copies them out later).
+int run_sparse(const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin, uint64_t range_end, int k, int min_rec,
+               bool canonical, const SparseWork& w, uint64_t cap, uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
+               uint64_t* h_unique, uint64_t* h_windows, SparsePending* pending, cudaStream_t s) {
+    if (pending) pending->valid = false;
+    *h_unique = 0;
+    if (int rc = sparse_emit_phase(d_fasta, nbytes, range_begin, range_end, k, min_rec, canonical, w, cap, h_windows, s)) return rc;
+    return sparse_sort_reduce_phase(w, *h_windows, 2 * k, d_keys_out, d_counts_out, d_first_out, out_cap, h_unique, pending, s);
+}
+
+// ---- multi-GPU, raw routing: a rank emits the windows of its byte range, groups them by the rank that owns
+// their key range (ONE radix pass over the top owner_bits of the k-mer) and reports how many each owner gets; after
+// the exchange every rank sorts and reduces what it received ONCE (kmerml_reduce_sparse_windows).
+__global__ void owner_bounds_kernel(const uint64_t* __restrict__ keys, uint64_t n, int shift, int n_owners,
+                                    unsigned long long* bounds /* n_owners + 1 */) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_owners) return;
+    // first index whose owner (key >> shift) is >= r: the keys are grouped by owner, ascending
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if ((keys[mid] >> shift) < (uint64_t)r) lo = mid + 1; else hi = mid;
+    }
+    bounds[r] = lo;
+}
+
+int run_sparse_emit_by_owner(void* workspace, const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin,
+                             uint64_t range_end, int k, int min_rec, bool canonical, int owner_bits, uint64_t cap,
+                             uint64_t* d_keys_out, uint32_t* d_ends_out, uint64_t out_cap, uint64_t* h_windows,
+                             uint64_t* h_owner_counts, cudaStream_t s) {
+    SparseWork w;
+    sparse_workspace(cap, nbytes, &w, (uint8_t*)workspace);
+    const int n_owners = 1 << owner_bits;
+    for (int r = 0; r < n_owners; r++) h_owner_counts[r] = 0;
+    if (int rc = sparse_emit_phase(d_fasta, nbytes, range_begin, range_end, k, min_rec, canonical, w, cap, h_windows, s)) return rc;
+    const uint64_t n = *h_windows;
+    if (!n || n > out_cap) return KMERML_OK;
+    uint64_t* keys = w.keys_a;
+    uint32_t* ends = w.ends_a;
+    if (owner_bits > 0) {
+        cub::DoubleBuffer<uint64_t> dk(w.keys_a, w.keys_b);
+        cub::DoubleBuffer<uint32_t> dv(w.ends_a, w.ends_b);
+        size_t tb = w.temp_bytes;
+        KM_CUDA(cub::DeviceRadixSort::SortPairs(w.temp, tb, dk, dv, n, 2 * k - owner_bits, 2 * k, s));
+        keys = dk.Current();
+        ends = dv.Current();
+    }
+    unsigned long long* d_bounds = w.n_runs;                      // (256 bytes: up to 31 owners + 1)
+    owner_bounds_kernel<<<1, 64, 0, s>>>(keys, n, 2 * k - owner_bits, n_owners, d_bounds);
+    KM_CUDA(cudaGetLastError());
+    unsigned long long h_bounds[33];
+    KM_CUDA(cudaMemcpyAsync(h_bounds, d_bounds, (size_t)(n_owners + 1) * 8, cudaMemcpyDeviceToHost, s));
+    KM_CUDA(cudaMemcpyAsync(d_keys_out, keys, n * 8, cudaMemcpyDeviceToDevice, s));
+    KM_CUDA(cudaMemcpyAsync(d_ends_out, ends, n * 4, cudaMemcpyDeviceToDevice, s));
+    KM_CUDA(cudaStreamSynchronize(s));
+    for (int r = 0; r < n_owners; r++) h_owner_counts[r] = h_bounds[r + 1] - h_bounds[r];
+    return KMERML_OK;
+}
+
+int run_sparse_reduce_windows(void* workspace, int sort_bits, const uint64_t* d_keys, const uint32_t* d_ends, uint64_t n,
+                              uint64_t* d_keys_out, uint32_t* d_counts_out, uint32_t* d_first_out, uint64_t out_cap,
+                              uint64_t* h_unique, SparsePending* pending, cudaStream_t s) {
+    if (pending) pending->valid = false;
+    *h_unique = 0;
+    if (!n) return KMERML_OK;
+    SparseWork w;
+    sparse_workspace(n, 0, &w, (uint8_t*)workspace);
+    KM_CUDA(cudaMemcpyAsync(w.keys_a, d_keys, n * 8, cudaMemcpyDeviceToDevice, s));
+    KM_CUDA(cudaMemcpyAsync(w.ends_a, d_ends, n * 4, cudaMemcpyDeviceToDevice, s));
+    return sparse_sort_reduce_phase(w, n, sort_bits, d_keys_out, d_counts_out, d_first_out, out_cap, h_unique, pending, s);
 }
 
 int sparse_fetch(void* workspace, uint64_t cap, uint64_t nbytes, const SparsePending& p, uint64_t* d_keys_out,

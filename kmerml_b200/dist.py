@@ -253,20 +253,29 @@ def key_owner_splits(keys, k, world_size):
 
 
 def count_sparse_sharded(fasta, k, *, min_record_len=None, canonical=False, count_range=None, merge=None,
-                         phase_ms=None):
+                         emit_range=None, reduce_windows=None, phase_ms=None):
     """Distinct k-mers (k <= 32) of ONE genome resident on every rank's device, counted cooperatively.
     Rank r counts byte range r, the partial results are exchanged with one all-to-all per tensor, and rank r
     returns the k-mers of key range r: (keys, counts, first, windows of the whole genome).  Concatenating the
     ranks' results in rank order gives exactly the single-GPU result.
 
+    Two routes.  RAW (the default when the number of ranks is a power of two): rank r emits the windows of its byte
+    range grouped by owner (kmerml_emit_sparse_range: the owner is the top log2(world) bits of the k-mer), ONE
+    all-to-all per tensor moves every window to its owner, and each rank sorts + reduces what it received once
+    (kmerml_reduce_sparse_windows, the owner bits left out of the sort).  PRE-REDUCED (any number of ranks): every rank
+    sort-reduces its range first, the distinct k-mers travel, the owner merges (a second sort).  RAW does one sort per
+    rank instead of two; PRE-REDUCED moves less when the ranges hold many repeats.
+
     `count_range(fasta, begin, end, k, min_record_len, canonical) -> (keys, counts, first, windows)` and
-    `merge(keys, counts, first, k) -> (keys, counts, first)` can be injected (CPU tests); by default they are
-    the CUDA entry points."""
+    `merge(keys, counts, first, k) -> (keys, counts, first)` (PRE-REDUCED) or `emit_range(fasta, begin, end, k,
+    owner_bits, min_record_len, canonical) -> (keys, ends, per-owner counts)` and `reduce_windows(keys, ends,
+    sort_bits) -> (keys, counts, first)` (RAW) can be injected (CPU tests); by default they are the CUDA entry points."""
     import torch
     import torch.distributed as dist
     from . import engine
     rank, world = _world()
     begin, end = chunk_ranges(int(fasta.numel()), world, tile=SPARSE_RANGE_ALIGN)[rank]
+    default_count = count_range is None
     if count_range is None:
         count_range = lambda f, b, e, kk, ml, c: engine.count_sparse_range_device(f, b, e, kk, min_record_len=ml, canonical=c)
     merge_takes_sort_k = merge is None                    # (the injected CPU stand-ins sort whole keys)
@@ -285,6 +294,38 @@ def count_sparse_sharded(fasta, k, *, min_record_len=None, canonical=False, coun
         return now
 
     tm = mark("start", _time.perf_counter())
+    raw = (emit_range is not None) or (merge_takes_sort_k and default_count and world > 1 and world & (world - 1) == 0
+                                       and 2 * int(k) > world.bit_length())
+    if raw:
+        owner_bits = world.bit_length() - 1
+        if emit_range is None:
+            emit_range = lambda f, b, e, kk, ob, ml, c: engine.emit_sparse_range_device(f, b, e, kk, ob, min_record_len=ml, canonical=c)
+        if reduce_windows is None:
+            reduce_windows = engine.reduce_sparse_windows_device
+        keys, ends, send = emit_range(fasta, begin, end, int(k), owner_bits, min_record_len, canonical)
+        tm = mark("emit_group_by_owner", tm)
+        dev = keys.device
+        send_t = torch.tensor(send, dtype=torch.int64, device=dev)
+        recv_t = torch.empty_like(send_t)
+        dist.all_to_all_single(recv_t, send_t)
+        recv = recv_t.cpu().tolist()
+        total = int(sum(recv))
+        w = torch.tensor([int(keys.numel())], dtype=torch.int64, device=dev)
+        got = []
+        parts = [keys, ends]
+        del keys, ends
+        for i in range(2):
+            t = parts[i].contiguous()
+            parts[i] = None
+            r = torch.empty(total, dtype=t.dtype, device=dev)
+            dist.all_to_all_single(r, t, output_split_sizes=recv, input_split_sizes=send)
+            del t
+            got.append(r)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        tm = mark("all_to_all", tm)
+        mk, mc, mf = reduce_windows(got[0], got[1], 2 * int(k) - owner_bits)
+        tm = mark("sort_reduce", tm)
+        return mk, mc, mf, int(w.item())
     keys, counts, first, windows = count_range(fasta, begin, end, int(k), min_record_len, canonical)
     tm = mark("range_sort_reduce", tm)
     if world == 1:

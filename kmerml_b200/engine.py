@@ -378,6 +378,48 @@ def count_sparse_range_device(fasta, begin, end, k, *, min_record_len=None, cano
     return keys[:n], counts[:n], first[:n], int(nw.value)
 
 
+def emit_sparse_range_device(fasta, begin, end, k, owner_bits, *, min_record_len=None, canonical=False):
+    """Windows (k-mer int64 storage of uint64, end offset int32) ending in the byte range [begin, end), grouped by
+    owner = the top owner_bits bits of the 2k-bit k-mer; returns (keys, ends, [windows per owner])."""
+    ctx = _lib.context(fasta.device.index)
+    L = _lib.load()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(fasta.device).cuda_stream)
+    cap = max(int(end) - int(begin), 1)
+    keys = torch.empty(cap, dtype=torch.int64, device=fasta.device)
+    ends = torch.empty(cap, dtype=torch.int32, device=fasta.device)
+    nw = ctypes.c_uint64(0)
+    owners = np.zeros(1 << int(owner_bits), dtype=np.uint64)
+    _retry_after_cache_release(lambda: _lib.check(L.kmerml_emit_sparse_range(
+        ctx.handle, fasta.data_ptr() if fasta.numel() else None, fasta.numel(), int(begin), int(end), int(k),
+        int(min_record_len or 0), _lib.FLAG_CANONICAL if canonical else 0, int(owner_bits), keys.data_ptr(), ends.data_ptr(),
+        cap, ctypes.byref(nw), owners.ctypes.data, stream)))
+    n = int(nw.value)
+    return keys[:n], ends[:n], [int(x) for x in owners]
+
+
+def reduce_sparse_windows_device(keys, ends, sort_bits):
+    """Windows in any order -> (distinct k-mers ascending in their low sort_bits bits, counts, smallest end offset)."""
+    ctx = _lib.context(keys.device.index)
+    L = _lib.load()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(keys.device).cuda_stream)
+    n = int(keys.numel())
+    if n == 0:
+        return keys, torch.zeros(0, dtype=torch.int32, device=keys.device), ends
+    keys, ends = keys.contiguous(), ends.contiguous()
+    cap = max(1024, min(n, 1 << 22))
+    ok = torch.empty(cap, dtype=torch.int64, device=keys.device)
+    oc = torch.empty(cap, dtype=torch.int32, device=keys.device)
+    of = torch.empty(cap, dtype=torch.int32, device=keys.device)
+    nu = ctypes.c_uint64(0)
+    _retry_after_cache_release(lambda: _lib.check(L.kmerml_reduce_sparse_windows(
+        ctx.handle, int(sort_bits), keys.data_ptr(), ends.data_ptr(), n, ok.data_ptr(), oc.data_ptr(), of.data_ptr(), cap,
+        ctypes.byref(nu), stream)))
+    m = int(nu.value)
+    if m > cap:
+        ok, oc, of = _sparse_fetch(ctx, L, m, keys.device, True, stream)
+    return ok[:m], oc[:m], of[:m]
+
+
 def merge_sparse_device(keys, counts, first, k):
     """(k-mer, count, first) triples in any order, duplicates allowed -> distinct k-mers ascending, counts added,
     smallest first offset kept (int64 / int32 / int32 storage of uint64 / uint32 / uint32)."""

@@ -111,6 +111,27 @@ def _worker(rank, world, port, results):
 
             mk, mc, mf, windows = kdist.count_sparse_sharded(torch.from_numpy(np.frombuffer(fa, np.uint8).copy()), k,
                                                              canonical=canonical, count_range=np_count_range, merge=np_merge)
+            # ... and the RAW route: windows grouped by owner, exchanged, sorted + reduced once
+            def np_emit_range(fasta, begin, end, kk, owner_bits, ml, c):
+                sel = (we >= begin) & (we < end)
+                kk_, ee_ = wk[sel], we[sel]
+                owner = (kk_ >> np.uint64(2 * kk - owner_bits)).astype(np.int64) if owner_bits else np.zeros(kk_.size, np.int64)
+                order = np.argsort(owner, kind="stable")
+                return (torch.from_numpy(kk_[order].view(np.int64).copy()), torch.from_numpy(ee_[order].astype(np.int32)),
+                        np.bincount(owner, minlength=1 << owner_bits).tolist())
+
+            def np_reduce_windows(keys, ends, sort_bits):
+                kn, en = keys.numpy().view(np.uint64), ends.numpy().astype(np.int64)
+                order = np.lexsort((en, kn))
+                kn, en = kn[order], en[order]
+                uu, idx, cc = np.unique(kn, return_index=True, return_counts=True)
+                return (torch.from_numpy(uu.view(np.int64).copy()), torch.from_numpy(cc.astype(np.int32)),
+                        torch.from_numpy(en[idx].astype(np.int32)))
+
+            rk, rc_, rf, rwin = kdist.count_sparse_sharded(torch.from_numpy(np.frombuffer(fa, np.uint8).copy()), k,
+                                                          canonical=canonical, emit_range=np_emit_range,
+                                                          reduce_windows=np_reduce_windows)
+            ok &= bool(torch.equal(rk, mk) and torch.equal(rc_, mc) and torch.equal(rf, mf)) and rwin == windows
             u, cnt, fst = reduce_windows(wk, we)
             ok &= windows == int(cnt.sum())
             # this rank holds exactly the k-mers of its key range; the ranges tile the key space in rank order

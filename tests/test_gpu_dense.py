@@ -309,6 +309,26 @@ def test_sparse_byte_ranges_and_merge():
         assert torch.equal(torch.cat([g[0] for g in got]), whole[0])
         assert torch.equal(torch.cat([g[1] for g in got]), whole[1])
         assert torch.equal(torch.cat([g[2] for g in got]), whole[2])
+        # RAW routing (kmerml_emit_sparse_range / kmerml_reduce_sparse_windows): windows grouped by owner = top bits
+        # of the k-mer, every owner sorts + reduces what all ranges sent it once; owners in order == the whole genome
+        for owner_bits, world in ((0, 1), (2, 4), (3, 8)):
+            sent = []
+            for b, e in kdist.chunk_ranges(len(fa), world, tile=engine.SPARSE_RANGE_ALIGN):
+                ek, ee, oc = engine.emit_sparse_range_device(dev, b, e, k, owner_bits, canonical=canonical)
+                sel = (we >= b) & (we < e)
+                assert sum(oc) == int(sel.sum()) == ek.numel(), (k, owner_bits, b, e)
+                own = (ek.cpu().numpy().view(np.uint64) >> np.uint64(2 * k - owner_bits)).astype(np.int64) if owner_bits else \
+                    np.zeros(ek.numel(), np.int64)
+                assert np.all(np.diff(own) >= 0) and np.bincount(own, minlength=1 << owner_bits).tolist() == oc
+                sent.append((ek, ee, oc))
+            outs = []
+            for r in range(world):
+                ks_ = torch.cat([p[0][sum(p[2][:r]):sum(p[2][:r + 1])] for p in sent])
+                es_ = torch.cat([p[1][sum(p[2][:r]):sum(p[2][:r + 1])] for p in sent])
+                outs.append(engine.reduce_sparse_windows_device(ks_, es_, 2 * k - owner_bits))
+            assert torch.equal(torch.cat([o[0] for o in outs]), whole[0]), (k, owner_bits)
+            assert torch.equal(torch.cat([o[1] for o in outs]), whole[1])
+            assert torch.equal(torch.cat([o[2] for o in outs]), whole[2])
 
 
 def test_several_payload_groups():
