@@ -4,7 +4,8 @@
               ranks, rows all-gathered, genome x genome cosine distances in row blocks (tensor cores), gathered
   c4_strong   ONE 3.1 Gbp genome, k = 12 canonical: byte ranges with k-1 look-back, one reduce-scatter of the
               dense rows to owner slices (strong scaling: the genome is the same at every N)
-  c5_sparse   the same genome with N runs, k = 21 canonical: per-range sort-reduce, all-to-all by key range, merge
+  c5_sparse   the same genome with N runs, k = 21 canonical: windows emitted per byte range and grouped by owner,
+              all-to-all by key range, one sort + reduce per rank
 
 Every section: W warm-up + K timed steps between barriers, CUDA events on the launching stream, MAX over ranks;
 bit-exactness against the single-GPU result (c4 at full size on every rank's slice, c5 on a bounded prefix plus
@@ -303,11 +304,15 @@ def run_c5(torch, dist, device, rank, world, steps, warmup, scale=1.0, check_sca
                 last = b
     total_counts = T.sum_over_ranks(float((counts.to(torch.int64) & 0xFFFFFFFF).sum().item()))
     distinct = T.sum_over_ranks(float(n_local))
-    return {"workload": f"C5: one {bases / 1e9:.2f} Gbp genome with N runs, k=21 canonical, per-range sort-reduce on {world} GPU(s) + "
-                        f"all-to-all by key range + merge", "ms": ms, "Gbp/s": bases / (ms * 1e-3) / 1e9,
-            "collective": "all_to_all_single x3 (k-mer u64, count u32, first offset u32) of pre-reduced triples" if world > 1 else None,
+    raw = world > 1 and world & (world - 1) == 0
+    return {"workload": f"C5: one {bases / 1e9:.2f} Gbp genome with N runs, k=21 canonical on {world} GPU(s): " +
+                        ("windows of a byte range emitted and grouped by owner, all-to-all by key range, ONE sort + reduce per rank"
+                         if raw else "per-range sort-reduce, all-to-all of the distinct k-mers by key range, merge"),
+            "ms": ms, "Gbp/s": bases / (ms * 1e-3) / 1e9,
+            "collective": ("all_to_all_single x2 (k-mer u64, end offset u32) of raw windows" if raw else
+                           "all_to_all_single x3 (k-mer u64, count u32, first offset u32) of pre-reduced triples") if world > 1 else None,
             "phase_ms_synchronised": phases, "windows": int(windows), "distinct_kmers": int(distinct),
-            "nvlink_bytes": int(distinct * 16 * (world - 1) / world) if world > 1 else 0,
+            "nvlink_bytes": int((float(windows) * 12 if raw else distinct * 16) * (world - 1) / world) if world > 1 else 0,
             "bit_exact_vs_single_gpu": {"genome_mbp": round(small_mbp, 1), "ok": T.all_true(small_ok)},
             "full_size_invariants": {"sum_counts_equals_windows": total_counts == float(windows),
                                      "keys_ascending_within_and_across_ranks": T.all_true(asc and ordered)}}
