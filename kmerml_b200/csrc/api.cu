@@ -261,9 +261,13 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     const uint64_t target = (uint64_t)ctx->sm_count * 8;
     // partition path: long runs of tiles per CTA amortise its set-up (fill of the staging buffer, first load,
     // final reduction), but a small batch needs enough CTAs to fill the GPU
+    // (a byte-range call -- one rank's share of a genome -- only walks the range: size the runs from it, or a rank
+    // of an 8-GPU job is left with 1.3 waves of CTAs)
+    uint64_t walked_bytes = total_bytes;
+    if (range_end) walked_bytes = std::min(total_bytes, range_end > range_begin ? range_end - range_begin : 0);
     int part_tiles_per_slice = 1;
     while (part_tiles_per_slice < PART_MAX_TILES_PER_RUN &&
-           total_bytes / TILE_BYTES / (2ull * part_tiles_per_slice) >= (uint64_t)ctx->sm_count * 8)
+           walked_bytes / TILE_BYTES / (2ull * part_tiles_per_slice) >= (uint64_t)ctx->sm_count * 8)
         part_tiles_per_slice *= 2;
     if (const char* e = getenv("KMERML_TILES_PER_RUN")) {      // profiling hook: the run length of a big batch on a small one
         const int v = atoi(e);
