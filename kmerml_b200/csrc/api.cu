@@ -265,10 +265,21 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
     // of an 8-GPU job is left with 1.3 waves of CTAs)
     uint64_t walked_bytes = total_bytes;
     if (range_end) walked_bytes = std::min(total_bytes, range_end > range_begin ? range_end - range_begin : 0);
+    // Run length T (tiles per partition CTA): the longest T <= 64 for which the runs fill a whole number of waves of
+    // the 2 CTAs per SM -- w waves of (2 x SMs) runs at 96 % fill, so that genome ends (partial runs) do not spill
+    // into one more wave.  (Powers of two left a rank of an 8-GPU job with 5.03 waves: six rounds for 84 % use.)
     int part_tiles_per_slice = 1;
-    while (part_tiles_per_slice < PART_MAX_TILES_PER_RUN &&
-           walked_bytes / TILE_BYTES / (2ull * part_tiles_per_slice) >= (uint64_t)ctx->sm_count * 8)
-        part_tiles_per_slice *= 2;
+    {
+        const uint64_t tiles = std::max<uint64_t>(walked_bytes / TILE_BYTES, 1);
+        const uint64_t slots = (uint64_t)ctx->sm_count * 2;
+        for (uint64_t w = 1;; w++) {
+            const uint64_t t = (tiles * 100 + slots * w * 96 - 1) / (slots * w * 96);
+            if (t <= (uint64_t)PART_MAX_TILES_PER_RUN) {
+                part_tiles_per_slice = (int)std::max<uint64_t>(t, 1);
+                break;
+            }
+        }
+    }
     if (const char* e = getenv("KMERML_TILES_PER_RUN")) {      // profiling hook: the run length of a big batch on a small one
         const int v = atoi(e);
         if (v >= 1 && v <= PART_MAX_TILES_PER_RUN) part_tiles_per_slice = v;
