@@ -133,11 +133,12 @@ struct SmemSink {
 // global row (sweep_packed16), so a half never exceeds 0x3FFF + 32768 = 0xBFFF: no carry into its
 // neighbour for any input (tested with a homopolymer).
 struct Packed16Sink {
+    static constexpr bool raw_windows = true;       // emit_clean passes unmasked funnel words: the masks below do it
     uint32_t sbase;                    // shared-window address of the 32768 words
     unsigned n;
     __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
-        // word (idx >> 1), half (idx & 1): add 1 or 0x10000
-        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sbase + ((idx & ~1u) << 1)), "r"(1u + (idx & 1u) * 0xFFFFu)
+        // word (idx >> 1) & 0x7FFF, half (idx & 1): add 1 or 0x10000 = 1 + (idx & 1) * 0xFFFF (one IMAD)
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sbase + ((idx << 1) & 0x1FFFCu)), "r"((idx & 1u) * 0xFFFFu + 1u)
                      : "memory");
         n++;
     }
@@ -160,7 +161,8 @@ struct Packed16Sink {
 template <int NT>
 __device__ __forceinline__ void sweep_packed16(uint32_t* hist, uint32_t* row) {
     uint4* h4 = reinterpret_cast<uint4*>(hist);
-    for (int i = threadIdx.x; i < 32768 / 4; i += NT) {
+#pragma unroll
+    for (int i = threadIdx.x; i < 32768 / 4; i += NT) {                     // (32768 / 4 / NT loads in flight together)
         const uint4 v = h4[i];
         if (((v.x | v.y | v.z | v.w) & 0xC000C000u) == 0u) continue;        // every half below 0x4000
         uint32_t w[4] = {v.x, v.y, v.z, v.w};
