@@ -21,7 +21,7 @@ def install_as_kmerml():
 
     from . import kmers, ml, utils
     from .kmers import generate, statistics
-    from .ml import features
+    from .ml import clustering, features
     from .utils import path_utils
     root = types.ModuleType("kmerml")
     root.__version__ = __version__
@@ -29,6 +29,7 @@ def install_as_kmerml():
     mapping = {
         "kmerml": root, "kmerml.kmers": kmers, "kmerml.kmers.generate": generate,
         "kmerml.kmers.statistics": statistics, "kmerml.ml": ml, "kmerml.ml.features": features,
+        "kmerml.ml.clustering": clustering,
         "kmerml.utils": utils, "kmerml.utils.path_utils": path_utils,
     }
     for name, mod in mapping.items():

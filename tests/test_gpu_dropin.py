@@ -158,6 +158,11 @@ def test_builder_from_counts_and_distance_matrix():
     assert set(got.columns) <= set(frame.columns[(prev >= 0.6).to_numpy()]) and abs(len(got.columns) - len(want_cols)) <= 2
     top = b.get_top_features(n_features=20)
     assert top.shape == (5, 20)
+    # the clustering entry points (stubs in the reference) on the GPU distance matrix
+    from kmerml_b200.ml import clustering
+    labels, z = clustering.hierarchical_clustering(m, n_clusters=2, method="average", metric="cosine")
+    assert z.shape == (4, 4) and set(labels) <= {0, 1} and len(labels) == 5
+    assert len(clustering.dbscan_clustering(m, eps=1.0, min_samples=2)) == 5
     assert float(var[top.columns].min()) >= float(np.sort(var.to_numpy())[-20]) * (1 - 1e-9)
 
 

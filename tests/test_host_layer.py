@@ -208,3 +208,23 @@ def test_statistics_csv_against_the_live_reference(tmp_path):
                 np.testing.assert_allclose(a[col].to_numpy(), b[col].to_numpy(), rtol=1e-12, atol=0)
             else:
                 assert a[col].equals(b[col]), (i, col)
+
+
+def test_clustering_entry_points_on_injected_distances():
+    """kmerml/ml/clustering.py:6-16 are `pass` stubs in the reference; here they run on the genome x genome distance
+    matrix (injected in this CPU test; the GPU produces it otherwise)."""
+    from kmerml_b200.ml import clustering
+    rng = np.random.default_rng(0)
+    a = rng.normal(0, 0.05, (6, 8)) + np.array([1, 0, 0, 0, 0, 0, 0, 0])
+    b = rng.normal(0, 0.05, (5, 8)) + np.array([0, 0, 0, 1, 0, 0, 0, 0])
+    x = np.abs(np.vstack([a, b]))
+    d = np.sqrt(((x[:, None, :] - x[None, :, :]) ** 2).sum(-1))
+    labels, z = clustering.hierarchical_clustering(pd.DataFrame(x), n_clusters=2, distances=d)
+    assert z.shape == (10, 4) and len(set(labels[:6])) == 1 and len(set(labels[6:])) == 1 and labels[0] != labels[6]
+    assert clustering.hierarchical_clustering(x, distances=d)[0] is None
+    km, centres = clustering.kmeans_clustering(x, n_clusters=2)
+    assert centres.shape == (2, 8) and len(set(km[:6])) == 1 and km[0] != km[6]
+    db = clustering.dbscan_clustering(x, eps=0.5, min_samples=3, distances=d)
+    assert set(db) == {0, 1}
+    with pytest.raises(ValueError):
+        clustering.hierarchical_clustering(x, distances=np.zeros((3, 4)))
