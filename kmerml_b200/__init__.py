@@ -22,7 +22,7 @@ def install_as_kmerml():
     from . import kmers, ml, utils
     from .kmers import generate, statistics
     from .ml import clustering, features
-    from .utils import path_utils
+    from .utils import genome_metadata, kmer_metadata, path_utils
     root = types.ModuleType("kmerml")
     root.__version__ = __version__
     root.__path__ = []
@@ -31,6 +31,7 @@ def install_as_kmerml():
         "kmerml.kmers.statistics": statistics, "kmerml.ml": ml, "kmerml.ml.features": features,
         "kmerml.ml.clustering": clustering,
         "kmerml.utils": utils, "kmerml.utils.path_utils": path_utils,
+        "kmerml.utils.genome_metadata": genome_metadata, "kmerml.utils.kmer_metadata": kmer_metadata,
     }
     for name, mod in mapping.items():
         sys.modules[name] = mod

@@ -323,6 +323,34 @@ def test_genome_and_kmer_metadata():
         res = engine.count_dense_device(dev, [0, dev.numel()], ks, min_record_len=ml, want_freq=False)
         for k in ks:
             assert engine.kmer_count_stats_device(res.counts_of(0, k), k) == c["kmers"][str(k)], (c["name"], k)
+    # the drop-in managers (same JSON layout as the reference's) give the same records from files
+    import tempfile
+    from pathlib import Path
+    from kmerml_b200.utils.genome_metadata import GenomeMetadataManager
+    from kmerml_b200.utils.kmer_metadata import KmerMetadataManager
+    with tempfile.TemporaryDirectory() as td:
+        raw = Path(td) / "raw"
+        raw.mkdir()
+        picks = [c for c in cases if c["genome"]["contigs"] > 0][:6]
+        for i, c in enumerate(picks):
+            (raw / f"GCF_90000000{i}_1.fa").write_bytes(c["fasta"])
+            kdir = Path(td) / "kmers" / f"GCF_90000000{i}_1"
+            kdir.mkdir(parents=True)
+            for k, text in c["files"].items():
+                if text:
+                    (kdir / f"k{k}.txt").write_text(text)
+        gm = GenomeMetadataManager(Path(td) / "meta" / "genome_metadata.json")
+        meta = gm.collect_metadata(raw)
+        km = KmerMetadataManager(Path(td) / "meta" / "genome_metadata.json")
+        km.add_kmer_metadata(sorted((Path(td) / "kmers").glob("*/k*.txt")))
+        for i, c in enumerate(picks):
+            org = f"GCF_90000000{i}_1"
+            for key in ("contigs", "total_size", "n_count", "gc_content"):
+                assert meta[org][key] == c["genome"][key], (c["name"], key)
+            assert gm.get_genome_size(org) == c["genome"]["total_size"]
+            for k, want in c["kmers"].items():
+                got = {key: km.metadata[org]["kmers"][k][key] for key in want}
+                assert got == want, (c["name"], k)
     g0 = next(c for c in golden_extract_cases() if c["name"] == "rand07")
     ks = [k for k in g0["k_values"] if k <= 12]
     dev = torch.from_numpy(np.frombuffer(g0["fasta"], np.uint8).copy()).cuda()
