@@ -176,7 +176,7 @@ def _unmodified_reference_worker(job):
     return time.perf_counter() - t0
 
 
-def time_unmodified_reference(ks, cores, bases_per_genome=60_000):
+def time_unmodified_reference(ks, cores, bases_per_genome=300_000):
     """The unmodified Python reference (pip-installed into baseline/_ref from the reference tree) on
     `cores` processes, one small C2-shaped genome each; None when baseline/_ref is absent."""
     if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "kmerml")):
