@@ -110,6 +110,9 @@ int kmerml_count_dense_range(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t n
  * uint32 in the caller's buffer by host threads (KMERML_HOST_THREADS, default half the cores, at most 16) while
  * the next genomes are in flight; lossless.  This flag copies the uint32 rows as they are instead. */
 #define KMERML_FLAG_WIDE_D2H 16u
+/* ... and a level of k >= 10 whose mean count is at most 5 (genome bytes <= 5 * 4^k) even as FOUR BITS per bin (bins
+ * that reached 15 go to the exception list).  This flag keeps every level at one byte per bin. */
+#define KMERML_FLAG_NO_NIBBLES 32u
 /* Number of host threads that widen the narrow format (one process per GPU: cores / ranks on the host). */
 int kmerml_ctx_set_host_threads(kmerml_ctx *ctx, int n_threads);
 int kmerml_count_dense_host(kmerml_ctx *ctx, const uint8_t *const *h_fasta, const uint64_t *h_sizes,
@@ -120,11 +123,12 @@ int kmerml_count_dense_host(kmerml_ctx *ctx, const uint8_t *const *h_fasta, cons
 /*
  * The same call with the result left in the form it crosses PCIe in: per genome one row of
  * kmerml_compact_row_bytes(k_list, nk) bytes (stride a multiple of 16):
- *     [ one byte per bin of every k >= 10, in k_list order | exception count (uint32, padded to 16 bytes) |
- *       65536 x (row-relative bin, count) uint32 pairs for the bins that reached 255 |
- *       the uint32 rows of every k < 10, in k_list order ]
- * Lossless unless the exception count exceeds 65536 (a genome with that many k-mers seen 255+ times:
- * kmerml_compact_expand reports it; count that genome with kmerml_count_dense_host).  Four times fewer bytes
+ *     [ header: "KMW2", bit mask of the k_list entries packed as nibbles, 8 bytes reserved |
+ *       one byte -- or one nibble, low one first -- per bin of every k >= 10, in k_list order |
+ *       exception count (uint32, padded to 16 bytes) | 32768 x (row-relative bin, count) uint32 pairs for the bins
+ *       that reached 255 (15 in a nibble level) | the uint32 rows of every k < 10, in k_list order ]
+ * Lossless unless the exception count exceeds 32768 (kmerml_compact_row_overflowed / kmerml_compact_expand report it;
+ * count that genome with kmerml_count_dense_host).  Four to six times fewer bytes
  * cross the bus and none is rewritten by the host; kmerml_compact_expand widens one k of one genome on demand
  * (pure host code, no GPU).  The host memory of this pool's boxes takes writes at ~60 GB/s, which is what bounds
  * the uint32 variant above.
@@ -135,6 +139,7 @@ int kmerml_count_dense_host_compact(kmerml_ctx *ctx, const uint8_t *const *h_fas
                                     unsigned flags, uint8_t *h_rows, uint64_t row_stride_bytes, float *freq,
                                     uint64_t freq_stride, uint64_t *h_totals);
 int kmerml_compact_expand(const int *k_list, int nk, const uint8_t *h_row, int ki, uint32_t *h_out);
+int kmerml_compact_row_overflowed(const int *k_list, int nk, const uint8_t *h_row);   /* 1 / 0, negative: error */
 
 /*
  * Sparse counting for 15 <= k <= 32 (any k >= 1 is accepted): the distinct k-mers of ONE genome as

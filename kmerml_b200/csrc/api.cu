@@ -676,8 +676,10 @@ int kmerml_count_dense_range(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t n
 
 namespace {
 
-constexpr int NARROW_MIN_K = 10;                 // levels that cross the bus as one byte per bin
-constexpr uint32_t NARROW_EXC_CAP = 65536;       // exception list entries (bin, count) per genome
+constexpr int NARROW_MIN_K = 10;                 // levels that cross the bus as one byte (or one nibble) per bin
+constexpr uint32_t NARROW_EXC_CAP = 32768;       // exception list entries (bin, count) per genome
+constexpr uint32_t WIRE_MAGIC = 0x32574D4Bu;     // "KMW2": header word 0 of a wire row; word 1 = nibble mask over k_list
+constexpr size_t WIRE_HEADER = 16;
 constexpr size_t NARROW_CHUNK = 1u << 20;        // bins one host task widens
 // Measured (1 x B200, C2): the call is bound by the box's host memory system (~60 GB/s of DMA traffic in either
 // direction), not by launches: 8 genomes per slot gave the same 86 ms per step for the compact result and made the
@@ -685,13 +687,16 @@ constexpr size_t NARROW_CHUNK = 1u << 20;        // bins one host task widens
 constexpr int HOST_GROUP_MAX = 1;                // genomes one pipeline slot holds (one batch of kernels) ...
 constexpr uint64_t HOST_GROUP_BYTES = 192ull << 20;   // ... and their FASTA bytes, at most
 
-// wire row of one genome: [narrow bytes | exception count (16 B) | exception list | small levels (uint32)]
+// wire row of one genome:
+//   [header 16 B | narrow block | exception count (16 B) | exception list | small levels (uint32)]
+// nibble_mask bit i: level i of k_list is packed two bins per byte
 struct WireLayout {
     km::NarrowSpec spec;
-    size_t exc_off, small_off, bytes;
+    uint32_t nibble_mask;
+    size_t narrow_off, exc_off, small_off, bytes;
 };
 
-WireLayout wire_layout(const km::RowSpec& row, bool narrow_big_levels) {
+WireLayout wire_layout(const km::RowSpec& row, bool narrow_big_levels, uint32_t nibble_mask) {
     WireLayout L;
     memset(&L, 0, sizeof(L));
     km::NarrowSpec& sp = L.spec;
@@ -699,9 +704,12 @@ WireLayout wire_layout(const km::RowSpec& row, bool narrow_big_levels) {
     for (int i = 0; i < row.nk; i++) {
         const unsigned long long n = 1ull << (2 * row.k[i]);
         if (narrow_big_levels && row.k[i] >= NARROW_MIN_K) {
+            const bool nib = (nibble_mask >> i) & 1u;
+            if (nib) L.nibble_mask |= 1u << i;
             sp.src_off[sp.n] = row.off[i];
             sp.dst_off[sp.n] = sp.total;
-            sp.total += n;
+            sp.nibble[sp.n] = nib ? 1 : 0;
+            sp.total += nib ? n / 2 : n;
             sp.n++;
         } else {
             sp.small_src[sp.n_small] = row.off[i];
@@ -713,10 +721,21 @@ WireLayout wire_layout(const km::RowSpec& row, bool narrow_big_levels) {
     sp.dst_off[sp.n] = sp.total;
     sp.small_dst[sp.n_small] = small;
     sp.small_total = small;
-    L.exc_off = (size_t)sp.total;
+    L.narrow_off = WIRE_HEADER;
+    L.exc_off = L.narrow_off + (size_t)sp.total;
     L.small_off = L.exc_off + 16 + (size_t)NARROW_EXC_CAP * 8;
     L.bytes = (L.small_off + (size_t)small * 4 + 15) / 16 * 16;
     return L;
+}
+
+// Which levels of a genome of `fasta_bytes` bytes go as nibbles: those with a mean count <= 5 (Poisson(5) reaches 15
+// with probability 7e-5: a few hundred exceptions per 4^12 bins); repeats beyond that land in the exception list, and
+// a list that overflows sends the genome again in full.
+uint32_t nibble_mask_for(const km::RowSpec& row, uint64_t fasta_bytes) {
+    uint32_t m = 0;
+    for (int i = 0; i < row.nk; i++)
+        if (row.k[i] >= NARROW_MIN_K && fasta_bytes <= 5ull << (2 * row.k[i])) m |= 1u << i;
+    return m;
 }
 
 struct HostSlot {                                // hand-over between the stream callback, the pool and the caller
@@ -727,7 +746,8 @@ struct HostSlot {                                // hand-over between the stream
     std::atomic<int> remaining{0};
     // the group in the slot
     int n = 0;
-    const uint8_t* wire_host = nullptr;          // n wire rows
+    const uint8_t* wire_host = nullptr;          // n wire rows, wire_stride bytes apart
+    size_t wire_stride = 0;
     uint32_t* row[HOST_GROUP_MAX] = {};          // the caller's uint32 rows
     WireLayout lay;
     km::HostPool* pool = nullptr;
@@ -736,7 +756,7 @@ struct HostSlot {                                // hand-over between the stream
 void slot_finish(HostSlot* sl) {                 // last task of a group: exceptions, then the slot is free
     bool over[HOST_GROUP_MAX] = {};
     for (int g = 0; g < sl->n; g++) {
-        const uint8_t* tail = sl->wire_host + (size_t)g * sl->lay.bytes + sl->lay.exc_off;
+        const uint8_t* tail = sl->wire_host + (size_t)g * sl->wire_stride + sl->lay.exc_off;
         uint32_t n_exc;
         memcpy(&n_exc, tail, 4);
         over[g] = n_exc > NARROW_EXC_CAP;
@@ -761,7 +781,7 @@ void CUDART_CB slot_arrived(void* p) {           // stream callback: the group's
     if (!per_genome || !sl->n) { slot_finish(sl); return; }
     sl->remaining.store(per_genome * sl->n);
     for (int g = 0; g < sl->n; g++) {
-        const uint8_t* wire = sl->wire_host + (size_t)g * sl->lay.bytes;
+        const uint8_t* wire = sl->wire_host + (size_t)g * sl->wire_stride;
         uint32_t* row = sl->row[g];
         if (sp.n_small) {
             const km::NarrowSpec* spp = &sl->lay.spec;
@@ -775,12 +795,14 @@ void CUDART_CB slot_arrived(void* p) {           // stream callback: the group's
         }
         for (int i = 0; i < sp.n; i++) {
             const size_t len = (size_t)(sp.dst_off[i + 1] - sp.dst_off[i]);
+            const bool nib = sp.nibble[i] != 0;
             for (size_t c = 0; c < len; c += NARROW_CHUNK) {
-                const uint8_t* src = wire + sp.dst_off[i] + c;
-                uint32_t* dst = row + sp.src_off[i] + c;
+                const uint8_t* src = wire + sl->lay.narrow_off + sp.dst_off[i] + c;
+                uint32_t* dst = row + sp.src_off[i] + (nib ? 2 * c : c);
                 const size_t n = std::min(NARROW_CHUNK, len - c);
-                km::host_pool_submit(sl->pool, [sl, src, dst, n] {
-                    km::widen_u8_to_u32(src, dst, n);
+                km::host_pool_submit(sl->pool, [sl, src, dst, n, nib] {
+                    if (nib) km::widen_u4_to_u32(src, dst, n);
+                    else km::widen_u8_to_u32(src, dst, n);
                     if (sl->remaining.fetch_sub(1) == 1) slot_finish(sl);
                 });
             }
@@ -817,8 +839,8 @@ static int count_dense_host_impl(kmerml_ctx* ctx, const uint8_t* const* h_fasta,
         return fail(KMERML_ERR_ARG, "device freq buffer must be 16-byte aligned with a stride multiple of 4");
     // the levels k >= 10 cross the bus as bytes + exceptions (hostpipe.cu), the small ones as they are
     const bool wire = compact || !(flags & KMERML_FLAG_WIDE_D2H);
-    const WireLayout lay = wire_layout(row, true);
-    if (compact && compact_stride < lay.bytes)
+    const WireLayout lay_max = wire_layout(row, true, 0);           // all levels as bytes: the largest row
+    if (compact && compact_stride < lay_max.bytes)
         return fail(KMERML_ERR_ARG, "compact row stride smaller than kmerml_compact_row_bytes");
     if (wire && !compact && !ctx->host_pool) {
         int n_thr = 0;
@@ -864,8 +886,8 @@ static int count_dense_host_impl(kmerml_ctx* ctx, const uint8_t* const* h_fasta,
         if (freq && !freq_dev && (rc = w.freq.ensure((size_t)max_group * row_stride * 4))) return rc;
         if ((rc = w.totals.ensure((size_t)max_group * nk * 8))) return rc;
         if (wire) {
-            if ((rc = w.wire.ensure((size_t)max_group * lay.bytes))) return rc;
-            if (!compact && (rc = w.wire_host.ensure((size_t)max_group * lay.bytes))) return rc;
+            if ((rc = w.wire.ensure((size_t)max_group * lay_max.bytes))) return rc;
+            if (!compact && (rc = w.wire_host.ensure((size_t)max_group * lay_max.bytes))) return rc;
         }
     }
     // every exit below first waits for the host tasks that still reference `slots`
@@ -908,7 +930,7 @@ static int count_dense_host_impl(kmerml_ctx* ctx, const uint8_t* const* h_fasta,
         // (genomes start at 256-byte multiples of the slot's buffer; count_dense_group blanks the gaps)
         float* d_f = !freq ? nullptr : (freq_dev ? freq + (size_t)g0 * freq_stride : (float*)w.freq.p);
         rc = count_dense_group(ctx, w, (const uint8_t*)w.fasta.p, offs.data(), h_sizes + g0, ng, k_list, nk, min_record_len,
-                               flags & ~(KMERML_FLAG_FREQ_ON_DEVICE | KMERML_FLAG_WIDE_D2H), (uint32_t*)w.counts.p, row_stride,
+                               flags & ~(KMERML_FLAG_FREQ_ON_DEVICE | KMERML_FLAG_WIDE_D2H | KMERML_FLAG_NO_NIBBLES), (uint32_t*)w.counts.p, row_stride,
                                d_f, freq_dev ? freq_stride : row_stride, (uint64_t*)w.totals.p, s);
         if (rc) { drain(); return rc; }
         if (!wire) {
@@ -916,17 +938,24 @@ static int count_dense_host_impl(kmerml_ctx* ctx, const uint8_t* const* h_fasta,
                 KM_HOST_TRY(cudaMemcpyAsync(h_counts + (size_t)(g0 + j) * counts_stride, (uint32_t*)w.counts.p + (size_t)j * row_stride,
                                             row_len * 4, cudaMemcpyDeviceToHost, s));
         } else {
+            // the group's wire layout: a level goes as nibbles when every genome of the group is small enough
+            uint32_t mask = ~0u;
+            for (int j = 0; j < ng; j++) mask &= nibble_mask_for(row, h_sizes[g0 + j]);
+            if (flags & KMERML_FLAG_NO_NIBBLES) mask = 0;
+            const WireLayout lay = wire_layout(row, true, mask);
             uint8_t* dw = (uint8_t*)w.wire.p;
-            rc = launch_narrow_levels((const uint32_t*)w.counts.p, row_stride, ng, lay.spec, dw, lay.bytes, lay.exc_off,
-                                      lay.small_off, NARROW_EXC_CAP, s);
+            rc = launch_narrow_levels((const uint32_t*)w.counts.p, row_stride, ng, lay.spec, dw, lay_max.bytes, lay.narrow_off,
+                                      lay.exc_off, lay.small_off, NARROW_EXC_CAP, WIRE_MAGIC, lay.nibble_mask, s);
             if (rc) { drain(); return rc; }
-            ctx->launches++;
+            ctx->launches += 2;
             if (compact) {
                 for (int j = 0; j < ng; j++)
-                    KM_HOST_TRY(cudaMemcpyAsync(compact_rows + (size_t)(g0 + j) * compact_stride, dw + (size_t)j * lay.bytes,
+                    KM_HOST_TRY(cudaMemcpyAsync(compact_rows + (size_t)(g0 + j) * compact_stride, dw + (size_t)j * lay_max.bytes,
                                                 lay.bytes, cudaMemcpyDeviceToHost, s));
             } else {
-                KM_HOST_TRY(cudaMemcpyAsync(w.wire_host.p, dw, (size_t)ng * lay.bytes, cudaMemcpyDeviceToHost, s));
+                for (int j = 0; j < ng; j++)
+                    KM_HOST_TRY(cudaMemcpyAsync((uint8_t*)w.wire_host.p + (size_t)j * lay_max.bytes, dw + (size_t)j * lay_max.bytes,
+                                                lay.bytes, cudaMemcpyDeviceToHost, s));
                 HostSlot& sl = slots[si];
                 {
                     std::lock_guard<std::mutex> lk(sl.m);
@@ -935,6 +964,7 @@ static int count_dense_host_impl(kmerml_ctx* ctx, const uint8_t* const* h_fasta,
                 }
                 sl.n = ng;
                 sl.wire_host = (const uint8_t*)w.wire_host.p;
+                sl.wire_stride = lay_max.bytes;
                 for (int j = 0; j < ng; j++) sl.row[j] = h_counts + (size_t)(g0 + j) * counts_stride;
                 sl.lay = lay;
                 sl.pool = ctx->host_pool;
@@ -975,7 +1005,7 @@ uint64_t kmerml_compact_row_bytes(const int* k_list, int nk) {
     RowSpec row;
     int kmax, kmin;
     if (build_row(k_list, nk, &row, &kmax, &kmin)) return 0;
-    return wire_layout(row, true).bytes;
+    return wire_layout(row, true, 0).bytes;
 }
 
 int kmerml_count_dense_host_compact(kmerml_ctx* ctx, const uint8_t* const* h_fasta, const uint64_t* h_sizes,
@@ -988,13 +1018,34 @@ int kmerml_count_dense_host_compact(kmerml_ctx* ctx, const uint8_t* const* h_fas
                                  freq_stride, h_totals, h_rows, row_stride_bytes);
 }
 
-int kmerml_compact_expand(const int* k_list, int nk, const uint8_t* h_row, int ki, uint32_t* h_out) {
-    if (!k_list || !h_row || !h_out || ki < 0 || ki >= nk) return fail(KMERML_ERR_ARG, "bad argument");
-    RowSpec row;
+static int compact_row_layout(const int* k_list, int nk, const uint8_t* h_row, RowSpec* row, WireLayout* lay) {
+    if (!k_list || !h_row) return fail(KMERML_ERR_ARG, "null pointer argument");
     int kmax, kmin;
-    int rc = build_row(k_list, nk, &row, &kmax, &kmin);
+    int rc = build_row(k_list, nk, row, &kmax, &kmin);
     if (rc) return rc;
-    const WireLayout lay = wire_layout(row, true);
+    uint32_t head[2];
+    memcpy(head, h_row, 8);
+    if (head[0] != WIRE_MAGIC) return fail(KMERML_ERR_ARG, "not a compact count row (bad header)");
+    *lay = wire_layout(*row, true, head[1]);
+    return KMERML_OK;
+}
+
+int kmerml_compact_row_overflowed(const int* k_list, int nk, const uint8_t* h_row) {
+    RowSpec row;
+    WireLayout lay;
+    int rc = compact_row_layout(k_list, nk, h_row, &row, &lay);
+    if (rc) return rc;
+    uint32_t n_exc;
+    memcpy(&n_exc, h_row + lay.exc_off, 4);
+    return n_exc > NARROW_EXC_CAP ? 1 : 0;
+}
+
+int kmerml_compact_expand(const int* k_list, int nk, const uint8_t* h_row, int ki, uint32_t* h_out) {
+    if (!h_out || ki < 0 || ki >= nk) return fail(KMERML_ERR_ARG, "bad argument");
+    RowSpec row;
+    WireLayout lay;
+    int rc = compact_row_layout(k_list, nk, h_row, &row, &lay);
+    if (rc) return rc;
     const NarrowSpec& sp = lay.spec;
     const uint64_t n = 1ull << (2 * row.k[ki]);
     for (int i = 0; i < sp.n_small; i++)
@@ -1008,7 +1059,8 @@ int kmerml_compact_expand(const int* k_list, int nk, const uint8_t* h_row, int k
         memcpy(&n_exc, h_row + lay.exc_off, 4);
         if (n_exc > NARROW_EXC_CAP)
             return fail(KMERML_ERR_RANGE, "this genome's exception list overflowed: count it with kmerml_count_dense_host");
-        widen_u8_to_u32(h_row + sp.dst_off[i], h_out, (size_t)n);
+        if (sp.nibble[i]) widen_u4_to_u32(h_row + lay.narrow_off + sp.dst_off[i], h_out, (size_t)(n / 2));
+        else widen_u8_to_u32(h_row + lay.narrow_off + sp.dst_off[i], h_out, (size_t)n);
         const uint32_t* e = reinterpret_cast<const uint32_t*>(h_row + lay.exc_off + 16);
         for (uint32_t j = 0; j < n_exc; j++)
             if (e[2 * j] >= row.off[ki] && e[2 * j] < row.off[ki] + n) h_out[e[2 * j] - row.off[ki]] = e[2 * j + 1];

@@ -118,17 +118,19 @@ int dense_setup_attributes();
 // ---- narrow device -> host wire format (hostpipe.cu) ---------------------------
 struct NarrowSpec {           // how a count row maps onto its wire row
     int n, n_small;
-    unsigned long long src_off[16];   // narrow levels (one byte per bin): element offset inside the count row ...
+    unsigned long long src_off[16];   // narrow levels: element offset inside the count row ...
     unsigned long long dst_off[17];   // ... and byte offset inside the narrow block; dst_off[n] = total
-    unsigned long long total;         // bins (= bytes) of the narrow block, a multiple of 16
+    unsigned char nibble[16];         // 1: two bins per byte (4 bits each, 15 = see the exception list), 0: one byte per bin
+    unsigned long long total;         // bytes of the narrow block, a multiple of 16
     unsigned long long small_src[16]; // small levels (uint32 as they are): element offset inside the count row ...
     unsigned long long small_dst[17]; // ... and inside the small block; small_dst[n_small] = small_total
     unsigned long long small_total;
 };
 int launch_narrow_levels(const uint32_t* d_counts, uint64_t counts_stride, int n_genomes, const NarrowSpec& spec,
-                         uint8_t* d_wire, uint64_t wire_stride, uint64_t exc_off, uint64_t small_off, uint32_t exc_cap,
-                         cudaStream_t s);
+                         uint8_t* d_wire, uint64_t wire_stride, uint64_t narrow_off, uint64_t exc_off, uint64_t small_off,
+                         uint32_t exc_cap, uint32_t header_magic, uint32_t header_mask, cudaStream_t s);
 void widen_u8_to_u32(const uint8_t* src, uint32_t* dst, size_t n);
+void widen_u4_to_u32(const uint8_t* src, uint32_t* dst, size_t n_bytes);
 class HostPool;
 HostPool* host_pool_create(int n_threads);
 void host_pool_destroy(HostPool* p);

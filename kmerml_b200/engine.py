@@ -134,7 +134,7 @@ class CompactDenseResult:
 
 def count_dense_host(buffers, k_values, *, min_record_len=None, canonical=False, want_freq=True,
                      device=None, out_counts=None, out_freq=None, out_totals=None, partition=True,
-                     freq_on_device=False, wide_d2h=False, compact=False, out_rows=None):
+                     freq_on_device=False, wide_d2h=False, compact=False, out_rows=None, nibbles=True):
     """End to end from host byte buffers (numpy uint8 arrays / pinned torch tensors): H2D,
     counting and D2H all inside libkmerml_b200.so.  Returns host (pinned) torch tensors; with
     freq_on_device the frequency rows stay in HBM (a CUDA tensor) for the distance / ML stage."""
@@ -177,18 +177,24 @@ def count_dense_host(buffers, k_values, *, min_record_len=None, canonical=False,
             freq = torch.empty((n, row_len), dtype=torch.float32, pin_memory=pin)
     totals = out_totals if out_totals is not None else torch.zeros((n, len(ks)), dtype=torch.int64, pin_memory=pin)
     flags = _flags(canonical, partition) | (_lib.FLAG_FREQ_ON_DEVICE if (freq is not None and freq.is_cuda) else 0)
-    if wide_d2h:                     # uint32 rows over PCIe as they are (default: bytes + exceptions for k >= 10)
+    if wide_d2h:                     # uint32 rows over PCIe as they are (default: bytes / nibbles + exceptions for k >= 10)
         flags |= _lib.FLAG_WIDE_D2H
+    if not nibbles:                  # keep every level of k >= 10 at one byte per bin
+        flags |= _lib.FLAG_NO_NIBBLES
     if compact:
         _lib.check(L.kmerml_count_dense_host_compact(
             ctx.handle, ptrs, sizes.ctypes.data, n, karr.ctypes.data, len(ks), int(min_record_len or 0),
             flags, counts.data_ptr(), counts.stride(0),
             freq.data_ptr() if freq is not None else None, freq.stride(0) if freq is not None else 0,
             totals.data_ptr()))
-        # genomes whose exception list overflowed (> 65536 bins at 255 or more): counted again, uint32 rows
-        narrow_total = sum(4 ** k for k in ks if k >= 10)
-        n_exc = counts[:, narrow_total:narrow_total + 4].contiguous().view(torch.int32)[:, 0]
-        over = [g for g in range(n) if int(n_exc[g]) > 65536 or int(n_exc[g]) < 0]
+        # genomes whose exception list overflowed (too many bins at 255 / 15 or more): counted again, uint32 rows
+        over = []
+        for g in range(n):
+            r = L.kmerml_compact_row_overflowed(karr.ctypes.data, len(ks), counts[g].data_ptr())
+            if r < 0:
+                _lib.check(r)
+            if r:
+                over.append(g)
         wide = {}
         if over:
             sub = count_dense_host([buffers[g] for g in over], ks, min_record_len=min_record_len, canonical=canonical,

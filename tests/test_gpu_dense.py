@@ -153,7 +153,10 @@ def test_host_api_narrow_wire_format():
     body = unit * 260                                                         # ~86 000 distinct 10-mers, 260 times each
     tandem = (">t\n" + body + "\n").encode()                                  # one unwrapped line, 23 Mbp
     mid = synth.fasta_bytes([400_000, 30], seed=21).tobytes()
-    datas = [mid, tandem, synth.fasta_bytes([150_000], seed=22).tobytes(), b">e\n",
+    # small enough for 4-bit bins at k = 10..12, with a short tandem array: ~2000 bins beyond 15 -> exception list
+    sat = "".join("ACGT"[i] for i in rng.integers(0, 4, 2_000)) * 40
+    mixed = synth.fasta_bytes([3_000_000], seed=24).tobytes() + (">sat\n" + sat + "\n").encode()
+    datas = [mid, tandem, synth.fasta_bytes([150_000], seed=22).tobytes(), b">e\n", mixed,
              synth.fasta_bytes([90_000], seed=23).tobytes(), mid]
     for ks in ([12, 3, 10], [11, 8]):
         narrow = engine.count_dense_host(datas, ks, want_freq=False)
@@ -164,6 +167,11 @@ def test_host_api_narrow_wire_format():
         assert torch.equal(narrow.counts, dres.counts.cpu())
         comp = engine.count_dense_host(datas, ks, want_freq=False, compact=True)      # result left as it crossed the bus
         assert torch.equal(comp.counts_tensor(), wide.counts) and torch.equal(comp.totals, wide.totals), ks
+        bytes_only = engine.count_dense_host(datas, ks, want_freq=False, compact=True, nibbles=False)
+        assert torch.equal(bytes_only.counts_tensor(), wide.counts), ks
+        assert torch.equal(engine.count_dense_host(datas, ks, want_freq=False, nibbles=False).counts, wide.counts)
+        head = comp.rows[:, :8].contiguous().view(torch.int32)
+        assert int(head[4, 1]) != 0 and int(bytes_only.rows[:, :8].contiguous().view(torch.int32)[4, 1]) == 0   # nibble mask
     big = (narrow.counts.to(torch.int64) & 0xFFFFFFFF)
     assert int((big[1] >= 255).sum()) > 65536            # the tandem genome did overflow the exception list
     assert 1 in comp._wide
