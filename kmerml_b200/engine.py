@@ -122,13 +122,18 @@ class CompactDenseResult:
 
     def counts_tensor(self):
         """[n_genomes, row_len] int32 tensor (uint32 storage) of all rows, widened (what count_dense_host returns)."""
-        _, row_len = row_layout(self.k_list)
+        lay, row_len = row_layout(self.k_list)
         out = np.empty((self.rows.shape[0], row_len), dtype=np.uint32)
-        lay, _ = row_layout(self.k_list)
+        karr = np.asarray(self.k_list, dtype=np.int32)
+        L = _lib.load()
         for g in range(self.rows.shape[0]):
-            for k in self.k_list:
+            if g in self._wide:
+                out[g] = self._wide[g]
+                continue
+            for ki, k in enumerate(self.k_list):
                 off, n = lay[k]
-                out[g, off:off + n] = self.counts_numpy(g, k)
+                _lib.check(L.kmerml_compact_expand(karr.ctypes.data, len(self.k_list), self.rows[g].data_ptr(), ki,
+                                                   out[g, off:off + n].ctypes.data))
         return torch.from_numpy(out.view(np.int32))
 
 
