@@ -512,12 +512,13 @@ def run_ours(args):
                        for g in gi_chk for k in ks)
             e2e = {"value": nb_e2e / dt / 1e9, "unit": UNIT,
                    "h2d_bytes_per_step": int(whole_job(sum(sizes[:n_e2e]))),
-                   "d2h_bytes_per_step": int(whole_job(n_e2e * (row_bytes + len(ks) * 8))),
+                   "d2h_bytes_per_step": int(whole_job(sum(int(_lib.load().kmerml_compact_row_used_bytes(
+                       karr.ctypes.data, len(ks), hrows[g].data_ptr())) for g in range(n_e2e)) + n_e2e * len(ks) * 8)),
                    "genomes": n_e2e, "ms_per_step": dt * 1e3, "matches_device_path": bool(same),
                    "matches_checked_genomes": gi_chk, "exception_list_overflows": len(comp._wide), "numa_node": numa_node,
                    "api": "kmerml_count_dense_host_compact (engine.count_dense_host(compact=True)): pinned host FASTA -> H2D -> "
                           "count + frequency rows -> D2H of the count rows in the compact lossless form (1 byte per bin for "
-                          "k >= 10 + exception list, uint32 for k < 10) and the window totals; rows are widened to uint32 per "
+                          "k >= 10 -- 4 bits where the genome's mean count is <= 5 -- + exception list, uint32 for k < 10) and the window totals; rows are widened to uint32 per "
                           "(genome, k) on access (kmerml_compact_expand); the float32 frequency matrix is computed per step "
                           "and left resident in HBM (KMERML_FLAG_FREQ_ON_DEVICE)"}
             del comp

@@ -140,6 +140,7 @@ int kmerml_count_dense_host_compact(kmerml_ctx *ctx, const uint8_t *const *h_fas
                                     uint64_t freq_stride, uint64_t *h_totals);
 int kmerml_compact_expand(const int *k_list, int nk, const uint8_t *h_row, int ki, uint32_t *h_out);
 int kmerml_compact_row_overflowed(const int *k_list, int nk, const uint8_t *h_row);   /* 1 / 0, negative: error */
+uint64_t kmerml_compact_row_used_bytes(const int *k_list, int nk, const uint8_t *h_row);   /* bytes that crossed the bus */
 
 /*
  * Sparse counting for 15 <= k <= 32 (any k >= 1 is accepted): the distinct k-mers of ONE genome as

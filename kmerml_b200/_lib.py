@@ -60,6 +60,8 @@ def load():
     L.kmerml_count_dense_host_compact.argtypes = [vp, vp, vp, i32, vp, i32, i32, u32, vp, u64, vp, u64, vp]
     L.kmerml_compact_expand.argtypes = [vp, i32, vp, i32, vp]
     L.kmerml_compact_row_overflowed.argtypes = [vp, i32, vp]
+    L.kmerml_compact_row_used_bytes.restype = u64
+    L.kmerml_compact_row_used_bytes.argtypes = [vp, i32, vp]
     L.kmerml_count_dense_range.argtypes = [vp, vp, u64, u64, u64, vp, i32, i32, u32, vp, vp, vp]
     L.kmerml_count_sparse.argtypes = [vp, vp, u64, i32, i32, u32, vp, vp, vp, u64, ctypes.POINTER(ctypes.c_uint64),
                                       ctypes.POINTER(ctypes.c_uint64), vp]
@@ -104,7 +106,7 @@ EXPORTS = [
     "kmerml_normalize_rows", "kmerml_pairwise_distance", "kmerml_count_dense_range",
     "kmerml_count_sparse", "kmerml_genome_stats", "kmerml_format_kmer_file", "kmerml_format_kmer_lines",
     "kmerml_count_sparse_range", "kmerml_merge_sparse", "kmerml_pairwise_distance_rows", "kmerml_sparse_fetch", "kmerml_ctx_set_host_threads", "kmerml_count_stats", "kmerml_column_stats",
-    "kmerml_compact_row_bytes", "kmerml_count_dense_host_compact", "kmerml_compact_expand", "kmerml_compact_row_overflowed",
+    "kmerml_compact_row_bytes", "kmerml_count_dense_host_compact", "kmerml_compact_expand", "kmerml_compact_row_overflowed", "kmerml_compact_row_used_bytes",
     "kmerml_parse_kmer_lines", "kmerml_feature_keys", "kmerml_feature_line_lengths", "kmerml_feature_write_lines",
     "kmerml_emit_sparse_range", "kmerml_reduce_sparse_windows",
 ]

@@ -1045,6 +1045,13 @@ int kmerml_compact_row_overflowed(const int* k_list, int nk, const uint8_t* h_ro
     return n_exc > NARROW_EXC_CAP ? 1 : 0;
 }
 
+uint64_t kmerml_compact_row_used_bytes(const int* k_list, int nk, const uint8_t* h_row) {
+    RowSpec row;
+    WireLayout lay;
+    if (compact_row_layout(k_list, nk, h_row, &row, &lay)) return 0;
+    return lay.bytes;
+}
+
 int kmerml_compact_expand(const int* k_list, int nk, const uint8_t* h_row, int ki, uint32_t* h_out) {
     if (!h_out || ki < 0 || ki >= nk) return fail(KMERML_ERR_ARG, "bad argument");
     RowSpec row;
