@@ -13,6 +13,8 @@
  *     GPU (16-byte aligned), "h_" pointers are host memory (pinned for full speed);
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
  *     device entry points are asynchronous on it, *_host entry points synchronise;
+ *     a context's scratch memory is shared by its calls, so a call on another stream than
+ *     the context's previous call first waits (on the device) for that call to finish;
  *   - k-mer index = lexicographic ACGT (A0 C1 G2 T3), first base most significant;
  *     the on-disk digit code A0 T1 C2 G3 (kmerml/kmers/generate.py:71) is applied
  *     only by the text writer;

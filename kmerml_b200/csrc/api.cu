@@ -115,6 +115,9 @@ struct kmerml_ctx {
     int host_slots = 6;                           // (measured: 2 slots 29.8, 3: 39.4, 4: 34.9, 6: 45.3, 8: 44.7 Gbp/s for the compact call, 60 C2 genomes)
     km::SparsePending sparse_pending;             // kmerml_count_sparse -> kmerml_sparse_fetch
     km::HostPool* host_pool = nullptr;            // host threads that widen the narrow D2H format
+    cudaStream_t last_stream = nullptr;           // ws[0] is scratch shared by every device-resident call: a call on
+    bool last_stream_valid = false;               // another stream than the one before waits for that one (order_stream)
+    cudaEvent_t order_ev = nullptr;
     uint64_t max_group_payload = 12ull << 30;     // partition path: payload bytes one group of genomes may take
     // measurement hooks
     bool profiling = false;
@@ -140,6 +143,23 @@ struct DeviceGuard {
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// The scratch buffers of ws[0] are reused from call to call.  Calls on ONE stream are ordered by the stream; a call on
+// another stream than the previous one first waits for what that one still has in flight.
+static int order_stream(kmerml_ctx* ctx, cudaStream_t s) {
+    if (ctx->last_stream_valid && ctx->last_stream != s) {
+        if (!ctx->order_ev) KM_CUDA(cudaEventCreateWithFlags(&ctx->order_ev, cudaEventDisableTiming));
+        if (cudaEventRecord(ctx->order_ev, ctx->last_stream) == cudaSuccess) {
+            KM_CUDA(cudaStreamWaitEvent(s, ctx->order_ev, 0));
+        } else {                                    // the caller destroyed that stream: its work is done or abandoned
+            (void)cudaGetLastError();
+            KM_CUDA(cudaDeviceSynchronize());
+        }
+    }
+    ctx->last_stream = s;
+    ctx->last_stream_valid = true;
+    return KMERML_OK;
+}
 
 // Brackets a group of launches with events when profiling is on; always counts launches.
 struct Prof {
@@ -586,6 +606,7 @@ int kmerml_ctx_destroy(kmerml_ctx* ctx) {
     DeviceGuard guard(ctx->device);
     cudaDeviceSynchronize();
     for (auto& w : ctx->ws) w.release();
+    if (ctx->order_ev) cudaEventDestroy(ctx->order_ev);
     if (ctx->host_pool) host_pool_destroy(ctx->host_pool);
     for (auto& r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->pool) cudaEventDestroy(e);
@@ -652,6 +673,7 @@ int kmerml_count_dense_batch(kmerml_ctx* ctx, const uint8_t* d_fasta, const uint
     if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     return count_dense_core(ctx, ctx->ws[0], d_fasta, h_offsets, n_genomes, k_list, nk, min_record_len, flags,
                             d_counts, counts_stride, d_freq, freq_stride, d_totals, (cudaStream_t)stream);
 }
@@ -674,6 +696,7 @@ int kmerml_count_dense_range(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t n
         if (d_totals) KM_CUDA(cudaMemsetAsync(d_totals, 0, (size_t)nk * 8, (cudaStream_t)stream));
         return KMERML_OK;
     }
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     return count_dense_core(ctx, ctx->ws[0], d_fasta, offs, 1, k_list, nk, min_record_len, flags, d_counts,
                             align_up((size_t)row.off[nk], 4), nullptr, 0, d_totals, (cudaStream_t)stream, range_begin,
                             range_end);
@@ -832,6 +855,15 @@ static int count_dense_host_impl(kmerml_ctx* ctx, const uint8_t* const* h_fasta,
     if (!h_fasta || !h_sizes || (!h_counts && !compact)) return fail(KMERML_ERR_ARG, "null pointer argument");
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    // slot 0 shares ws[0] with the device-resident calls: let what the last of them launched finish first
+    // (this call runs on its own streams and returns synchronised)
+    if (ctx->last_stream_valid) {
+        if (cudaStreamSynchronize(ctx->last_stream) != cudaSuccess) {
+            (void)cudaGetLastError();
+            KM_CUDA(cudaDeviceSynchronize());
+        }
+        ctx->last_stream_valid = false;
+    }
     RowSpec row;
     int kmax, kmin;
     int rc = build_row(k_list, nk, &row, &kmax, &kmin);
@@ -1088,6 +1120,7 @@ int kmerml_find_records(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t s = (cudaStream_t)stream;
     Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     int rc = ws.misc.ensure(256);
     if (rc) return rc;
     uint32_t* d_count = (uint32_t*)ws.misc.p;
@@ -1116,6 +1149,7 @@ int kmerml_format_kmer_file(kmerml_ctx* ctx, int k, const uint32_t* d_counts, co
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     max_lines = std::max<uint64_t>(max_lines, 1);
     int rc = ws.part.ensure(format_workspace_bytes(1ull << (2 * k), max_lines));
     if (rc) return rc;
@@ -1132,6 +1166,7 @@ int kmerml_format_kmer_lines(kmerml_ctx* ctx, int k, const uint64_t* d_codes, co
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     int rc = ws.part.ensure(format_workspace_bytes(1, std::max<uint64_t>(n, 1)));
     if (rc) return rc;
     return run_format_lines(ws.part.p, k, d_codes, d_counts, n, d_text, text_cap, h_text_len, (cudaStream_t)stream);
@@ -1150,6 +1185,7 @@ int kmerml_parse_kmer_lines(kmerml_ctx* ctx, const uint8_t* d_text, const int64_
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     int rc = ws.misc.ensure(256);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -1194,6 +1230,7 @@ int kmerml_count_stats(kmerml_ctx* ctx, const uint32_t* d_counts, uint64_t n_bin
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     int rc = ws.misc.ensure(count_stats_workspace());
     if (rc) return rc;
     return launch_count_stats(d_counts, n_bins, ws.misc.p, (unsigned long long*)d_out, (cudaStream_t)stream);
@@ -1231,6 +1268,7 @@ int kmerml_pairwise_distance(kmerml_ctx* ctx, const void* d_x, int dtype, uint64
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     int rc = ws.misc.ensure(256 + (size_t)n * n * sizeof(double));
     if (rc) return rc;
     double* d_gram = (double*)((uint8_t*)ws.misc.p + 256);
@@ -1256,6 +1294,7 @@ int kmerml_pairwise_distance_rows(kmerml_ctx* ctx, const uint32_t* d_counts, uin
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     int rc = ws.part.ensure(gram_rows_workspace(n, m));
     if (rc) return rc;
     return launch_distance_rows_tc(d_counts, stride, n, m, row_begin, row_end, metric, ws.part.p, d_out32, d_out64,
@@ -1280,6 +1319,7 @@ static int count_sparse_core(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t n
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     // at most one window ends at every byte of the range; the slice table covers the whole file
     const uint64_t cap = std::max<uint64_t>(range_end - range_begin, 1);
     int rc = ws.part.ensure(sparse_workspace_bytes(cap, nbytes));
@@ -1311,6 +1351,7 @@ int kmerml_emit_sparse_range(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t n
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     const uint64_t cap = std::max<uint64_t>(range_end - range_begin, 1);
     int rc = ws.part.ensure(sparse_workspace_bytes(cap, nbytes));
     if (rc) return rc;
@@ -1330,6 +1371,7 @@ int kmerml_reduce_sparse_windows(kmerml_ctx* ctx, int sort_bits, const uint64_t*
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     const uint64_t cap = std::max<uint64_t>(n, 1);
     int rc = ws.part.ensure(sparse_workspace_bytes(cap, 0));
     if (rc) return rc;
@@ -1350,6 +1392,7 @@ int kmerml_sparse_fetch(kmerml_ctx* ctx, uint64_t* d_keys, uint32_t* d_counts, u
     if (out_cap < p.nu) return fail(KMERML_ERR_ARG, "outputs smaller than the number of distinct k-mers");
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     return sparse_fetch(ctx->ws[0].part.p, p.cap, p.nbytes, p, d_keys, d_counts, d_first, (cudaStream_t)stream);
 }
 
@@ -1378,6 +1421,7 @@ int kmerml_merge_sparse(kmerml_ctx* ctx, int k, const uint64_t* d_keys, const ui
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     int rc = ws.part.ensure(merge_workspace_bytes(std::max<uint64_t>(n, 1)));
     if (rc) return rc;
     return run_merge_sparse(ws.part.p, k, d_keys, d_counts, d_first, n, d_keys_out, d_counts_out, d_first_out, out_cap,
@@ -1397,6 +1441,7 @@ int kmerml_first_occurrence(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nb
     if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t s = (cudaStream_t)stream;
     Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     KM_CUDA(cudaMemsetAsync(d_first, 0xFF, (size_t)(1ull << (2 * k)) * 4, s));
     if (!nbytes) return KMERML_OK;
     const uint64_t sb = align_up(std::min<uint64_t>(std::max<uint64_t>(nbytes / ((uint64_t)ctx->sm_count * 8), TILE_BYTES),

@@ -373,3 +373,28 @@ print('groups ok')
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "groups ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_calls_on_different_streams_are_ordered():
+    """The context's scratch buffers are shared by all device-resident calls: a call on another stream than the one
+    before must wait for it (kmerml_b200.h, "streams"), so back-to-back calls on two streams stay exact."""
+    torch = torch_mod()
+    from kmerml_b200 import engine, synth
+    ks = [12, 9]
+    datas = [synth.fasta_bytes([1_500_000 + 77 * i], seed=300 + i).tobytes() for i in range(2)]
+    devs = []
+    for d in datas:
+        buf, offs = synth.pack([np.frombuffer(d, np.uint8)])
+        devs.append((torch.from_numpy(np.concatenate([buf, np.zeros(64, np.uint8)])).cuda(), offs))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    results = []
+    for rep in range(3):
+        for i in (0, 1):
+            with torch.cuda.stream(streams[i]):
+                results.append((i, engine.count_dense_device(devs[i][0], devs[i][1], ks)))
+    torch.cuda.synchronize()
+    refs = [[oracle.count_dense(d, k, max(ks)) for k in ks] for d in datas]
+    for i, res in results:
+        for ki, k in enumerate(ks):
+            assert np.array_equal(refs[i][ki], res.counts_numpy(0, k).astype(np.uint64)), (i, k)
