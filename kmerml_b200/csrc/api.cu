@@ -485,7 +485,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
                     rc = launch_cascade(lm, k_stop, kmin, (uint32_t)h0, nh, s);
                     if (rc) return rc;
                 }
-                Prof pr(ctx, s, 2, 1);
+                Prof pr(ctx, s, 2, canonical ? finalize_launches(row, true) : 1);
                 if (canonical)
                     rc = launch_finalize(lm, row, kcount, true, d_stats, d_freq, freq_stride, d_totals, (uint32_t)h0, nh, s);
                 else
@@ -510,7 +510,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
             }
             if (rc) return rc;
             {
-                Prof pr(ctx, s, 2, 1);
+                Prof pr(ctx, s, 2, finalize_launches(row, canonical));
                 rc = launch_finalize(lm, row, kcount, canonical, d_stats, d_freq, freq_stride, d_totals, (uint32_t)g0, ng, s);
             }
             if (rc) return rc;
@@ -532,7 +532,7 @@ static int count_dense_core(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fas
             }
             if (rc) return rc;
             {
-                Prof pr(ctx, s, 2, 1);
+                Prof pr(ctx, s, 2, finalize_launches(row, canonical));
                 rc = launch_finalize(lm, row, kcount, canonical, d_stats, d_freq, freq_stride, d_totals, (uint32_t)g, 1, s);
             }
             if (rc) return rc;

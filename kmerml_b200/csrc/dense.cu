@@ -1361,8 +1361,9 @@ finalize_kernel(LevelMap lm, RowSpec row, int k_top, const GenomeStats* __restri
     *reinterpret_cast<float4*>(freq + (uint64_t)g * freq_stride + e) = f;
 }
 
-// Canonical mode: fold every requested level onto min(kmer, revcomp) in place, then
-// normalise.  The thread of the smaller index of each {x, rc(x)} pair owns both bins.
+// Canonical mode: fold every requested level onto min(kmer, revcomp) in place, then normalise.
+// Levels below CANON_TILED_MIN_K: the thread of the smaller index of each {x, rc(x)} pair owns both bins.
+constexpr int CANON_TILED_MIN_K = 7;
 __global__ void __launch_bounds__(256)
 finalize_canonical_kernel(LevelMap lm, RowSpec row, int k_top, const GenomeStats* __restrict__ stats,
                           float* freq, uint64_t freq_stride, uint64_t* totals, uint32_t genome0) {
@@ -1370,24 +1371,90 @@ finalize_canonical_kernel(LevelMap lm, RowSpec row, int k_top, const GenomeStats
     const int tid = threadIdx.x;
     const uint32_t g = genome0 + blockIdx.y;
     level_totals(row, k_top, stats, g, tot, totals, blockIdx.x == 0);
-    const unsigned long long n = row.off[row.nk];
-    for (unsigned long long e = (unsigned long long)blockIdx.x * 256 + tid; e < n;
-         e += (unsigned long long)gridDim.x * 256) {
-        int ki = 0;
-        while (ki + 1 < row.nk && e >= row.off[ki + 1]) ki++;
+    for (int ki = 0; ki < row.nk; ki++) {
         const int j = row.k[ki];
-        const uint32_t x = (uint32_t)(e - row.off[ki]);
+        if (j >= CANON_TILED_MIN_K) continue;                       // finalize_canonical_tiled_kernel
         uint32_t* c = lm.ptr(g, j);
         float* f = freq ? freq + (uint64_t)g * freq_stride + row.off[ki] : nullptr;
         const double inv = tot[ki] ? 1.0 / (double)tot[ki] : 0.0;
-        const uint32_t rc = revcomp_code(x, j);
-        if (x < rc) {
-            const uint32_t a = c[x] + c[rc];
-            c[x] = a;
-            c[rc] = 0;
-            if (f) { f[x] = (float)((double)a * inv); f[rc] = 0.0f; }
-        } else if (x == rc) {
-            if (f) f[x] = (float)((double)c[x] * inv);
+        for (uint32_t x = blockIdx.x * 256 + tid; x < (1u << (2 * j)); x += gridDim.x * 256) {
+            const uint32_t rc = revcomp_code(x, j);
+            if (x < rc) {
+                const uint32_t a = c[x] + c[rc];
+                c[x] = a;
+                c[rc] = 0;
+                if (f) { f[x] = (float)((double)a * inv); f[rc] = 0.0f; }
+            } else if (x == rc) {
+                if (f) f[x] = (float)((double)c[x] * inv);
+            }
+        }
+    }
+}
+
+// Levels j >= 7: rc(x) reverses the base order, so the partner of a run of consecutive bins is a column of stride
+// 4^(j-1) -- one 32-byte sector per bin for the pairwise kernel above (0.17 ms for the 64 MB row of k = 12, four times
+// what its bytes cost).  Tiles make both sides contiguous: with x = A | M | B (A, B three bases, M the middle j - 6),
+// rc(x) = rc(B) | rc(M) | rc(A), i.e. the 64 x 64 tile M maps onto the tile rc(M).  A CTA loads the tile pair
+// {M, rc(M)} (M <= rc(M)) as 64 rows of 256 contiguous bytes into shared memory, folds, and writes both back.
+__global__ void __launch_bounds__(256)
+finalize_canonical_tiled_kernel(LevelMap lm, RowSpec row, int ki, int k_top, const GenomeStats* __restrict__ stats,
+                                float* freq, uint64_t freq_stride, uint32_t genome0) {
+    __shared__ uint32_t tile[2][64][65];
+    __shared__ double s_inv;
+    const int j = row.k[ki];
+    const int mid = j - 6;
+    const uint32_t M = blockIdx.x;
+    const uint32_t Mr = revcomp_code(M, mid);
+    if (M > Mr) return;
+    const int tid = threadIdx.x;
+    const uint32_t g = genome0 + blockIdx.y;
+    const int n_tiles = M == Mr ? 1 : 2;
+    if (tid == 0) {
+        unsigned long long t = stats[g].total_top;
+        for (int i = j; i < k_top; i++) t += stats[g].n_tail[i];
+        s_inv = t ? 1.0 / (double)t : 0.0;
+    }
+    uint32_t* c = lm.ptr(g, j);
+    float* f = freq ? freq + (uint64_t)g * freq_stride + row.off[ki] : nullptr;
+    const uint32_t mids[2] = {M, Mr};
+    // a thread moves 4 consecutive bins (128 bits) of 4 rows per tile
+    const int q = tid & 15, r0 = tid >> 4;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        if (t >= n_tiles) break;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int A = r0 + 16 * i;
+            const uint32_t x = ((uint32_t)A << (2 * (j - 3))) | (mids[t] << 6) | (uint32_t)(4 * q);
+            const uint4 v = *reinterpret_cast<const uint4*>(c + x);
+            tile[t][A][4 * q] = v.x; tile[t][A][4 * q + 1] = v.y; tile[t][A][4 * q + 2] = v.z; tile[t][A][4 * q + 3] = v.w;
+        }
+    }
+    __syncthreads();
+    const double inv = s_inv;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        if (t >= n_tiles) break;
+        const int p = n_tiles == 1 ? 0 : (t ^ 1);                   // the tile that holds the partners
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int A = r0 + 16 * i;
+            const uint32_t Ar = revcomp_code((uint32_t)A, 3);
+            const uint32_t x0 = ((uint32_t)A << (2 * (j - 3))) | (mids[t] << 6) | (uint32_t)(4 * q);
+            uint32_t out[4];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t B = (uint32_t)(4 * q + b);
+                const uint32_t Br = revcomp_code(B, 3);
+                const uint32_t x = x0 + b;
+                const uint32_t rc = (Br << (2 * (j - 3))) | (mids[p] << 6) | Ar;
+                const uint32_t own = tile[t][A][B];
+                out[b] = x < rc ? own + tile[p][Br][Ar] : (x == rc ? own : 0u);
+            }
+            *reinterpret_cast<uint4*>(c + x0) = make_uint4(out[0], out[1], out[2], out[3]);
+            if (f)
+                *reinterpret_cast<float4*>(f + x0) = make_float4((float)((double)out[0] * inv), (float)((double)out[1] * inv),
+                                                                 (float)((double)out[2] * inv), (float)((double)out[3] * inv));
         }
     }
 }
@@ -1592,17 +1659,31 @@ int launch_cascade(const LevelMap& lm, int k_top, int k_bottom, uint32_t genome0
 
 int cascade_launches(int k_top, int k_bottom) { return (k_top - k_bottom + 5) / 6; }
 
+int finalize_launches(const RowSpec& row, bool canonical) {
+    int n = 1;
+    if (canonical)
+        for (int i = 0; i < row.nk; i++) n += row.k[i] >= CANON_TILED_MIN_K ? 1 : 0;
+    return n;
+}
+
 int launch_finalize(const LevelMap& lm, const RowSpec& row, int k_top, bool canonical,
                     const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride, uint64_t* d_totals,
                     uint32_t genome0, int n_genomes, cudaStream_t s) {
     if (n_genomes <= 0) return KMERML_OK;
     unsigned long long n = row.off[row.nk];
     if (canonical) {
-        unsigned gx = (unsigned)((n + 256ull * 8 - 1) / (256ull * 8));
-        if (gx < 1) gx = 1;
-        if (gx > 148u * 16u) gx = 148u * 16u;
+        unsigned long long n_small = 0;
+        for (int i = 0; i < row.nk; i++)
+            if (row.k[i] < CANON_TILED_MIN_K) n_small = std::max(n_small, 1ull << (2 * row.k[i]));
+        unsigned gx = (unsigned)((n_small + 256ull * 4 - 1) / (256ull * 4));
+        if (gx < 1) gx = 1;                                          // (always launched: it writes the totals)
         dim3 grid(gx, (unsigned)n_genomes);
         finalize_canonical_kernel<<<grid, 256, 0, s>>>(lm, row, k_top, d_stats, d_freq, freq_stride, d_totals, genome0);
+        for (int i = 0; i < row.nk; i++) {
+            if (row.k[i] < CANON_TILED_MIN_K) continue;
+            dim3 tg(1u << (2 * (row.k[i] - 6)), (unsigned)n_genomes);
+            finalize_canonical_tiled_kernel<<<tg, 256, 0, s>>>(lm, row, i, k_top, d_stats, d_freq, freq_stride, genome0);
+        }
     } else {
         unsigned gx = d_freq ? (unsigned)(((n >> 2) + 255) / 256) : 1u;
         dim3 grid(gx, (unsigned)n_genomes);

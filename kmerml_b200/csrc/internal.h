@@ -83,6 +83,7 @@ int launch_count(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice
 int launch_cascade(const LevelMap& lm, int k_top, int k_bottom, uint32_t genome0, int n_genomes,
                    cudaStream_t s);
 int cascade_launches(int k_top, int k_bottom);
+int finalize_launches(const RowSpec& row, bool canonical);
 int launch_finalize(const LevelMap& lm, const RowSpec& row, int k_top, bool canonical,
                     const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride,
                     uint64_t* d_totals, uint32_t genome0, int n_genomes, cudaStream_t s);

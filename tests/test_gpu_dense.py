@@ -95,6 +95,12 @@ def test_canonical_opt_in():
     check_against_oracle(datas, [4, 5, 6], canonical=True)
     check_against_oracle(datas, [12, 9], canonical=True)
     check_against_oracle(datas, [12, 9], canonical=True, partition=False)
+    # the tiled fold (k >= 7: odd and even k, palindromic middles) beside the pairwise one (k < 7)
+    check_against_oracle(datas, [7, 3, 8], canonical=True)
+    check_against_oracle(datas, [10, 6, 11, 1], canonical=True)
+    from kmerml_b200 import synth
+    big = [synth.fasta_bytes([300_000, 150_001], seed=77).tobytes()]
+    check_against_oracle(big, [7, 8, 9, 10, 11, 12, 2], canonical=True)
 
 
 def test_medium_genomes_multi_slice():
