@@ -128,18 +128,21 @@ struct SmemSink {
 
 // k = 8: 65536 bins as packed 16-bit halves of 32768 shared words (128 KB), counted with non-returning
 // shared atomics like the 32-bit histograms of k <= 7.  The histogram leaves room for one CTA per SM, so
-// that CTA has 1024 threads (count8_kernel: 32 KB tiles).  Exactness: a tile has at most 32768 windows,
-// and after every tile the CTA sweeps the histogram and moves every half that has reached 0x4000 to the
-// global row (sweep_packed16), so a half never exceeds 0x3FFF + 32768 = 0xBFFF: no carry into its
-// neighbour for any input (tested with a homopolymer).
+// that CTA has 1024 threads (count8_kernel: 32 KB tiles).  Word i serves the bins i and i + 32768: its LOW half
+// counts the windows of BOTH, its high half those of bin i + 32768 -- the addend is 1 + 0x10000 * (bit 15 of the
+// window), two instructions (AND, multiply-add) instead of the select a "1 or 0x10000" addend compiles to.
+// Exactness: a tile has at most 32768 windows, and after every tile the CTA sweeps the histogram and moves every
+// word whose low half has reached 0x4000 to the global row (sweep_packed16), so a low half never exceeds
+// 0x3FFF + 32768 = 0xBFFF and the high half never exceeds the low one: no carry for any input (tested with a
+// homopolymer).
 struct Packed16Sink {
     static constexpr bool raw_windows = true;       // emit_clean passes unmasked funnel words: the masks below do it
     uint32_t sbase;                    // shared-window address of the 32768 words
     unsigned n;
     __device__ __forceinline__ void count(uint32_t idx, uint64_t) {
-        // word (idx >> 1) & 0x7FFF, half (idx & 1): add 1 or 0x10000 = 1 + (idx & 1) * 0xFFFF (one IMAD)
-        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sbase + ((idx << 1) & 0x1FFFCu)), "r"((idx & 1u) * 0xFFFFu + 1u)
-                     : "memory");
+        uint32_t addend;
+        asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(addend) : "r"(idx & 0x8000u));
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sbase + ((idx & 0x7FFFu) << 2)), "r"(addend) : "memory");
         n++;
     }
     __device__ __forceinline__ void count4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pa, uint64_t pb,
@@ -157,6 +160,13 @@ struct Packed16Sink {
     }
 };
 
+// word -> the two bins it serves
+__device__ __forceinline__ void packed16_flush_word(uint32_t v, uint32_t i, uint32_t* row) {
+    const uint32_t hi = v >> 16, lo = (v & 0xFFFFu) - hi;
+    if (lo) atomicAdd(row + i, lo);
+    if (hi) atomicAdd(row + i + 32768u, hi);
+}
+
 // (whole CTA, between the barrier that ends a tile and the one that precedes the next tile's counting)
 template <int NT>
 __device__ __forceinline__ void sweep_packed16(uint32_t* hist, uint32_t* row) {
@@ -164,14 +174,11 @@ __device__ __forceinline__ void sweep_packed16(uint32_t* hist, uint32_t* row) {
 #pragma unroll
     for (int i = threadIdx.x; i < 32768 / 4; i += NT) {                     // (32768 / 4 / NT loads in flight together)
         const uint4 v = h4[i];
-        if (((v.x | v.y | v.z | v.w) & 0xC000C000u) == 0u) continue;        // every half below 0x4000
+        if (((v.x | v.y | v.z | v.w) & 0x0000C000u) == 0u) continue;        // every low half below 0x4000
         uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t lo = w[j] & 0xFFFFu, hi = w[j] >> 16;
-            if (lo >= 0x4000u) { atomicAdd(row + 2 * (4 * i + j), lo); w[j] &= 0xFFFF0000u; }
-            if (hi >= 0x4000u) { atomicAdd(row + 2 * (4 * i + j) + 1, hi); w[j] &= 0x0000FFFFu; }
-        }
+        for (int j = 0; j < 4; j++)
+            if (w[j] & 0xC000u) { packed16_flush_word(w[j], 4u * i + j, row); w[j] = 0; }
         h4[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
@@ -547,11 +554,7 @@ count8_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds
     walk_slice<true, COUNT8_THREADS>(buf, g, sl, P, sink, tails, tc,
                                      [&](uint32_t) { sweep_packed16<COUNT8_THREADS>(sh_hist, row8); });
     const unsigned long long total = block_sum_u32(sink.n, &sh_total);
-    for (int i = tid; i < 32768; i += COUNT8_THREADS) {
-        const uint32_t v = sh_hist[i];
-        if (v & 0xFFFFu) atomicAdd(row8 + 2 * i, v & 0xFFFFu);
-        if (v >> 16) atomicAdd(row8 + 2 * i + 1, v >> 16);
-    }
+    for (int i = tid; i < 32768; i += COUNT8_THREADS) packed16_flush_word(sh_hist[i], (uint32_t)i, row8);
     if (tid == 0 && total) atomicAdd(&stats[sl.genome].total_top, total);
 }
 
