@@ -290,11 +290,9 @@ __device__ __forceinline__ void walk_slice(const uint8_t* __restrict__ buf, cons
             atomicMax(&tc.carry[tile_no & 1u], (unsigned long long)until);
         };
         if (full) {
-            uint32_t y[CHUNK / 4], bad[CHUNK / 4];
-            const bool weird = classify_chunk(w, y, bad) != 0;      // anything besides bases and '\n' ?
-            clean = !weird && pack_clean(y, bad, cc);
+            clean = classify_pack(w, cc);                           // only bases and at most one '\n' ?
             // only chunks that hold a '>' can start a header line
-            if (weird && any_byte_eq_chunk(w, 0x3E3E3E3Eu)) find_headers(g, cs, ce, on_header);
+            if (!clean && any_byte_eq_chunk(w, 0x3E3E3E3Eu)) find_headers(g, cs, ce, on_header);
         } else if (has) {
             find_headers(g, cs, ce, on_header);
         }

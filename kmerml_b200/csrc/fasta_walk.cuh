@@ -370,6 +370,65 @@ KM_HD bool pack_clean(const uint32_t* y, const uint32_t* bad, CleanChunk& c) {
     return true;
 }
 
+// classify_chunk + pack_clean in one pass, for the counting kernels' hot loop: true when the chunk is clean (only
+// bases and at most one '\n'), with the chunk packed into `c`.  Cheaper than the pair above: the flags of the bytes
+// that are no bases are gathered into ONE word (bit 8 b + i <=> byte b of word i), so "how many, and where" is a
+// test on that word, and only a chunk with exactly one such byte looks at it again to see that it is the '\n'
+// (the pair above compares every byte with '\n' and builds a per-word nibble mask: ~9 more integer ops per word).
+KM_HD bool classify_pack(const uint32_t* w, CleanChunk& c) {
+    static_assert(CHUNK == 32, "classify_pack packs 32 bases into 64 bits");
+    uint32_t pk[8], acc = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 8; i++) {
+        const uint32_t u = w[i] & 0xDFDFDFDFu;                     // upper-case (generate.py:41)
+        const uint32_t y = ((u >> 1) ^ (u >> 2)) & 0x03030303u;    // A0 C1 G2 T3
+        const uint32_t t = y | (y >> 4);
+#if defined(__CUDA_ARCH__)
+        const uint32_t sel = __byte_perm(t, 0u, 0x4420u);          // the 4 codes as PRMT selector nibbles
+#else
+        const uint32_t sel = (t & 0xFFu) | ((t >> 8) & 0xFF00u);
+#endif
+        const uint32_t d = prmt4(0x54474341u, sel) ^ u;            // "ACGT"[code] == byte ?
+        const uint32_t bad = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+        acc |= bad >> (7 - i);
+        pk[i] = (y * 0x40100401u) >> 24;                           // 4 codes -> 8 bits, first base on top
+    }
+    uint64_t B = ((uint64_t)((pk[0] << 24) | (pk[1] << 16) | (pk[2] << 8) | pk[3]) << 32) |
+                 (uint64_t)((pk[4] << 24) | (pk[5] << 16) | (pk[6] << 8) | pk[7]);
+    if (acc == 0) {
+        c.n = 32;
+        c.nl = 32;
+        c.last16 = (uint32_t)B;
+    } else {
+        if (acc & (acc - 1)) return false;                         // two or more bytes that are no bases
+        int bit = 0;
+#if defined(__CUDA_ARCH__)
+        bit = __ffs((int)acc) - 1;
+#else
+        while (!((acc >> bit) & 1u)) bit++;
+#endif
+        const int i = bit & 7, b = bit >> 3;
+        const uint32_t a0 = (i & 1) ? w[1] : w[0], a1 = (i & 1) ? w[3] : w[2];
+        const uint32_t a2 = (i & 1) ? w[5] : w[4], a3 = (i & 1) ? w[7] : w[6];
+        const uint32_t b0 = (i & 2) ? a1 : a0, b1 = (i & 2) ? a3 : a2;
+        const uint32_t word = (i & 4) ? b1 : b0;
+        if (((word >> (8 * b)) & 0xFFu) != 0x0Au) return false;    // ... and that one must be the line feed
+        const int p = 4 * i + b;
+        const uint64_t upper = p ? (B >> (64 - 2 * p)) : 0ull;                            // bases 0 .. p-1
+        const uint64_t lower = p == 31 ? 0ull : (B & ((1ull << (62 - 2 * p)) - 1ull));     // bases p+1 .. 31
+        const uint64_t V = p == 31 ? upper : ((upper << (62 - 2 * p)) | lower);           // 31 bases, right-aligned
+        c.n = 31;
+        c.nl = p;
+        c.last16 = (uint32_t)V;
+        B = V << 2;
+    }
+    c.hi = (uint32_t)(B >> 32);
+    c.lo = (uint32_t)B;
+    return true;
+}
+
 KM_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int s) {                 // bits [s, s+32) of hi:lo, 0 <= s < 32
 #if defined(__CUDA_ARCH__)
     return __funnelshift_r(lo, hi, (unsigned)s);
@@ -462,7 +521,7 @@ KM_HD_NOINLINE void slice_head_quick(const Genome& g, uint64_t p, uint64_t limit
         w[j] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
     }
     CleanChunk pc;
-    if (classify_chunk(w, y, bad) != 0 || !pack_clean(y, bad, pc)) return;
+    if (!classify_pack(w, pc)) return;
     bool in_hdr;
     if (!known) {
         in_hdr = false;                   // same line as p (limit >= CHUNK): the table pass clears prev_ok if it is a header

@@ -104,16 +104,15 @@ sparse_emit_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict_
             atomicMax(&s_carry[1], (unsigned long long)until);
         };
         if (has && cb >= g.lo && cb + CHUNK <= g.hi) {
-            uint32_t w[CHUNK / 4], y[CHUNK / 4], bad[CHUNK / 4];
+            uint32_t w[CHUNK / 4];
             const uint4* src = reinterpret_cast<const uint4*>(buf + cb);
 #pragma unroll
             for (int i = 0; i < CHUNK / 16; i++) {
                 const uint4 v = __ldg(src + i);
                 w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
             }
-            const bool weird = classify_chunk(w, y, bad) != 0;
-            clean = !weird && pack_clean(y, bad, cc);
-            if (weird && any_byte_eq_chunk(w, 0x3E3E3E3Eu)) find_headers(g, cs, ce, on_header);
+            clean = classify_pack(w, cc);
+            if (!clean && any_byte_eq_chunk(w, 0x3E3E3E3Eu)) find_headers(g, cs, ce, on_header);
         } else if (has) {
             find_headers(g, cs, ce, on_header);
         }

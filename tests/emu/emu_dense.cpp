@@ -133,11 +133,10 @@ static int64_t emu_core(const uint8_t* bytes, uint64_t n, uint64_t base_off, int
                     next_carry = std::max(next_carry, until);
                 };
                 if (ce - cs == CHUNK) {
-                    uint32_t w[CHUNK / 4], y[CHUNK / 4], bad[CHUNK / 4];
+                    uint32_t w[CHUNK / 4];
                     memcpy(w, g.b + cs, CHUNK);
-                    const bool weird = classify_chunk(w, y, bad) != 0;
-                    clean[t] = !weird && pack_clean(y, bad, cc[t]);
-                    if (weird && any_byte_eq_chunk(w, 0x3E3E3E3Eu)) find_headers(g, cs, ce, on_header);
+                    clean[t] = classify_pack(w, cc[t]);
+                    if (!clean[t] && any_byte_eq_chunk(w, 0x3E3E3E3Eu)) find_headers(g, cs, ce, on_header);
                 } else {
                     find_headers(g, cs, ce, on_header);
                 }
