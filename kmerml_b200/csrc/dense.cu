@@ -800,21 +800,33 @@ partition_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ 
                     flush_slot_slow<NB_SHIFT>(sm, b, region, cap, sink.ov, sink.ov_count);
                     continue;
                 }
+                // Slots are 96 bytes apart, so the lanes of a quarter warp that all read vector 0 of their slot meet
+                // two by two in the same banks (6 t mod 8 is even).  Lanes 4..7 of every eight therefore take a
+                // sector's two vectors in the other order: (6 t + [t & 4 ? 1 : 0]) mod 8 is a permutation.
+                const uint32_t sw = ((uint32_t)tid >> 2) & 1u, sx = sw ^ 1u;
                 uint4* slot = st + b * VPB;
                 uint4* dst = region + (b * cap + wr) * 2u;
-                store_sector(dst, slot[0], slot[1]);
+                {
+                    const uint4 x0 = slot[sw], x1 = slot[sx];
+                    dst[sw] = x0;
+                    dst[sx] = x1;
+                }
                 uint32_t mv = 2;                                   // vectors 2, 3 hold the left-over payloads ...
                 if (c >= 2 * PART_SECTOR) {
-                    store_sector(dst + 2, slot[2], slot[3]);
+                    const uint4 x0 = slot[2 + sw], x1 = slot[2 + sx];
+                    dst[2 + sw] = x0;
+                    dst[2 + sx] = x1;
                     mv = 4;                                        // ... or 4, 5 ...
                     if (c == 3 * PART_SECTOR) {
-                        store_sector(dst + 4, slot[4], slot[5]);
+                        const uint4 y0 = slot[4 + sw], y1 = slot[4 + sx];
+                        dst[4 + sw] = y0;
+                        dst[4 + sx] = y1;
                         mv = 0;                                    // ... or nothing is left
                     }
                 }
-                const uint4 m0 = slot[mv], m1 = slot[mv + 1];
-                slot[0] = m0;
-                slot[1] = m1;
+                const uint4 m0 = slot[mv + sw], m1 = slot[mv + sx];
+                slot[sw] = m0;
+                slot[sx] = m1;
                 sm.written[b] = (uint16_t)(wr + c / PART_SECTOR);
                 sm.cnt[b] = c % PART_SECTOR;
             }
