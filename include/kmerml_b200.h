@@ -260,6 +260,17 @@ int kmerml_records_short(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbyte
 int kmerml_genome_stats(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbytes, uint64_t *d_out, void *stream);
 
 /*
+ * Stage 1 on its own (SURVEY 8b `kmerml_encode`): the symbols of one FASTA file resident in HBM, as the counting
+ * kernels see them after kmerml/kmers/generate.py:39-41,55-56 -- d_symbols[i] = 0..3 (A C G T, either case) when
+ * byte i is a base of a record, 0xFF for everything else (header lines, line ends, N / IUPAC codes, blanks, text
+ * before the first '>').  d_tallies (uint64[4], may be NULL) receives the tallies of kmerml_genome_stats.
+ * The counting entry points do NOT need this: they decode in registers; it is for callers that want the symbol
+ * stream itself.  Asynchronous on `stream`.
+ */
+int kmerml_encode(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbytes, uint8_t *d_symbols, uint64_t *d_tallies,
+                  void *stream);
+
+/*
  * Static per-k-mer features (functions of the k-mer string only): replaces the per-row
  * helpers of kmerml/kmers/statistics.py:190-240.  d_out: int32[4^k][8] =
  * {n, A_count, C_count, G_count, T_count, cpg_count, has_repeat, first base}, row index =

@@ -557,6 +557,50 @@ static int count_dense_group(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fa
                             freq_stride, d_totals, s);
 }
 
+// Slice table of ONE genome that fills the whole buffer (first occurrence, encode): prologue + header state.
+static int single_genome_tables(kmerml_ctx* ctx, Workspace& ws, const uint8_t* d_fasta, uint64_t nbytes, cudaStream_t s,
+                                const GenomeDev** d_genomes, const Slice** d_slices, int* n_slices_out) {
+    const uint64_t sb = align_up(std::min<uint64_t>(std::max<uint64_t>(nbytes / ((uint64_t)ctx->sm_count * 8), TILE_BYTES),
+                                                    64ull * TILE_BYTES), TILE_BYTES);
+    const uint64_t n_slices = (nbytes - 1) / sb + 1;
+    const size_t off_bytes = 256, gen_bytes = 256, st_bytes = 256;
+    const size_t sl_bytes = align_up((size_t)(n_slices + 1) * sizeof(Slice), 256);   // + 1 scratch entry
+    int rc = ws.tables.ensure(off_bytes + gen_bytes + st_bytes + sl_bytes);
+    if (rc) return rc;
+    if ((rc = ws.staging.ensure(off_bytes + sl_bytes))) return rc;
+    if (!ws.staging_free) KM_CUDA(cudaEventCreateWithFlags(&ws.staging_free, cudaEventDisableTiming));
+    KM_CUDA(cudaEventSynchronize(ws.staging_free));
+    uint8_t* base = (uint8_t*)ws.tables.p;
+    uint8_t* hs = (uint8_t*)ws.staging.p;
+    uint64_t* ho = (uint64_t*)hs;
+    ho[0] = 0;
+    ho[1] = nbytes;
+    Slice* h_slices = (Slice*)(hs + off_bytes);
+    for (uint64_t b = 0; b < n_slices; b++) {
+        h_slices[b].genome = 0;
+        h_slices[b].prev_ok = 0;
+        h_slices[b].prev16 = 0;
+        h_slices[b].tile0 = 0;
+        h_slices[b].begin = b * sb;
+        h_slices[b].end = (b + 1) * sb;
+        h_slices[b].hdr_until = 0;
+    }
+    h_slices[n_slices].genome = 0;                          // scratch entry of launch_slice_headers
+    KM_CUDA(cudaMemcpyAsync(base, hs, off_bytes, cudaMemcpyHostToDevice, s));
+    KM_CUDA(cudaMemcpyAsync(base + off_bytes + gen_bytes + st_bytes, h_slices, sl_bytes, cudaMemcpyHostToDevice, s));
+    KM_CUDA(cudaEventRecord(ws.staging_free, s));
+    rc = launch_prologue(d_fasta, (const uint64_t*)base, (GenomeDev*)(base + off_bytes),
+                         (GenomeStats*)(base + off_bytes + gen_bytes), 1, s);
+    if (rc) return rc;
+    rc = launch_slice_headers(d_fasta, (const GenomeDev*)(base + off_bytes),
+                              (Slice*)(base + off_bytes + gen_bytes + st_bytes), (int)n_slices, s);
+    if (rc) return rc;
+    *d_genomes = (const GenomeDev*)(base + off_bytes);
+    *d_slices = (const Slice*)(base + off_bytes + gen_bytes + st_bytes);
+    *n_slices_out = (int)n_slices;
+    return KMERML_OK;
+}
+
 }  // namespace km
 
 using namespace km;
@@ -1444,44 +1488,38 @@ int kmerml_first_occurrence(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nb
     if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     KM_CUDA(cudaMemsetAsync(d_first, 0xFF, (size_t)(1ull << (2 * k)) * 4, s));
     if (!nbytes) return KMERML_OK;
-    const uint64_t sb = align_up(std::min<uint64_t>(std::max<uint64_t>(nbytes / ((uint64_t)ctx->sm_count * 8), TILE_BYTES),
-                                                    64ull * TILE_BYTES), TILE_BYTES);
-    const uint64_t n_slices = (nbytes - 1) / sb + 1;
-    const size_t off_bytes = 256, gen_bytes = 256, st_bytes = 256;
-    const size_t sl_bytes = align_up((size_t)(n_slices + 1) * sizeof(Slice), 256);   // + 1 scratch entry
-    int rc = ws.tables.ensure(off_bytes + gen_bytes + st_bytes + sl_bytes);
+    const GenomeDev* d_genomes = nullptr;
+    const Slice* d_slices = nullptr;
+    int n_slices = 0;
+    int rc = single_genome_tables(ctx, ws, d_fasta, nbytes, s, &d_genomes, &d_slices, &n_slices);
     if (rc) return rc;
-    if ((rc = ws.staging.ensure(off_bytes + sl_bytes))) return rc;
-    if (!ws.staging_free) KM_CUDA(cudaEventCreateWithFlags(&ws.staging_free, cudaEventDisableTiming));
-    KM_CUDA(cudaEventSynchronize(ws.staging_free));
-    uint8_t* base = (uint8_t*)ws.tables.p;
-    uint8_t* hs = (uint8_t*)ws.staging.p;
-    uint64_t* ho = (uint64_t*)hs;
-    ho[0] = 0;
-    ho[1] = nbytes;
-    Slice* h_slices = (Slice*)(hs + off_bytes);
-    for (uint64_t b = 0; b < n_slices; b++) {
-        h_slices[b].genome = 0;
-        h_slices[b].prev_ok = 0;
-        h_slices[b].prev16 = 0;
-        h_slices[b].tile0 = 0;
-        h_slices[b].begin = b * sb;
-        h_slices[b].end = (b + 1) * sb;
-        h_slices[b].hdr_until = 0;
+    return launch_first_occurrence(d_fasta, d_genomes, d_slices, n_slices, k, min_rec, d_first, s);
+}
+
+int kmerml_encode(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, uint8_t* d_symbols, uint64_t* d_tallies,
+                  void* stream) {
+    if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
+    if (nbytes && (!d_fasta || !d_symbols)) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (((uintptr_t)d_fasta & 15)) return fail(KMERML_ERR_ARG, "device pointers must be 16-byte aligned");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t s = (cudaStream_t)stream;
+    Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
+    if (d_tallies) {
+        int rc = launch_genome_stats(d_fasta, nbytes, (unsigned long long*)d_tallies, s);
+        if (rc) return rc;
+        ctx->launches += 1;
     }
-    h_slices[n_slices].genome = 0;                          // scratch entry of launch_slice_headers
-    KM_CUDA(cudaMemcpyAsync(base, hs, off_bytes, cudaMemcpyHostToDevice, s));
-    KM_CUDA(cudaMemcpyAsync(base + off_bytes + gen_bytes + st_bytes, h_slices, sl_bytes, cudaMemcpyHostToDevice, s));
-    KM_CUDA(cudaEventRecord(ws.staging_free, s));
-    rc = launch_prologue(d_fasta, (const uint64_t*)base, (GenomeDev*)(base + off_bytes),
-                         (GenomeStats*)(base + off_bytes + gen_bytes), 1, s);
+    if (!nbytes) return KMERML_OK;
+    KM_CUDA(cudaMemsetAsync(d_symbols, 0xFF, (size_t)nbytes, s));
+    const GenomeDev* d_genomes = nullptr;
+    const Slice* d_slices = nullptr;
+    int n_slices = 0;
+    int rc = single_genome_tables(ctx, ws, d_fasta, nbytes, s, &d_genomes, &d_slices, &n_slices);
     if (rc) return rc;
-    rc = launch_slice_headers(d_fasta, (const GenomeDev*)(base + off_bytes),
-                              (Slice*)(base + off_bytes + gen_bytes + st_bytes), (int)n_slices, s);
-    if (rc) return rc;
-    return launch_first_occurrence(d_fasta, (const GenomeDev*)(base + off_bytes),
-                                   (const Slice*)(base + off_bytes + gen_bytes + st_bytes), (int)n_slices, k, min_rec,
-                                   d_first, s);
+    ctx->launches += 1;
+    return launch_encode(d_fasta, d_genomes, d_slices, n_slices, d_symbols, s);
 }
 
 }  // extern "C"

@@ -204,6 +204,26 @@ struct FirstSink {
     }
 };
 
+// kmerml_encode: the walk with k = 1 -- every base that counts writes its 2-bit code at its byte position
+struct EncodeSink {
+    uint8_t* sym;
+    uint64_t file_lo;
+    __device__ __forceinline__ void count(uint32_t idx, uint64_t pos) { sym[pos - file_lo] = (uint8_t)idx; }
+    __device__ __forceinline__ void count4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pa, uint64_t pb,
+                                           uint64_t pc, uint64_t pd) {
+        count(a, pa); count(b, pb); count(c, pc); count(d, pd);
+    }
+    __device__ __forceinline__ void count8(const uint32_t* w, const uint64_t* p) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) count(w[i], p[i]);
+    }
+    __device__ __forceinline__ void count8_tail(const uint32_t* w, const uint64_t* p, bool last) {
+#pragma unroll
+        for (int i = 0; i < 7; i++) count(w[i], p[i]);
+        if (last) count(w[7], p[7]);
+    }
+};
+
 // ------------------------------------------------------------------ helpers
 __device__ __forceinline__ void level_totals(const RowSpec& row, int k_top, const GenomeStats* stats, uint32_t g,
                                              unsigned long long* tot, uint64_t* totals, bool write);
@@ -470,7 +490,7 @@ slice_long_resolve_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __re
     }
 }
 
-// MODE 0: global histogram, 1: shared histogram, 2: first occurrence  (k = 8: count8_kernel below)
+// MODE 0: global histogram, 1: shared histogram, 2: first occurrence, 3: symbols (kmerml_encode)  (k = 8: count8_kernel below)
 template <int MODE>
 __global__ void __launch_bounds__(COUNT_THREADS)
 count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
@@ -498,6 +518,13 @@ count_kernel(const uint8_t* __restrict__ buf, const GenomeDev* __restrict__ gds,
     if (MODE == 2) {
         FirstSink sink;
         sink.first = first; sink.file_lo = gd.file_lo;
+        NoTails nt;
+        walk_slice<true>(buf, g, sl, P, sink, nt, tc, [](uint32_t) {});
+        return;
+    }
+    if (MODE == 3) {
+        EncodeSink sink;
+        sink.sym = reinterpret_cast<uint8_t*>(first); sink.file_lo = gd.file_lo;
         NoTails nt;
         walk_slice<true>(buf, g, sl, P, sink, nt, tc, [](uint32_t) {});
         return;
@@ -1652,6 +1679,17 @@ int launch_first_occurrence(const uint8_t* d_fasta, const GenomeDev* d_genomes, 
     DenseParams P = make_params(k, min_rec, false, k);
     LevelMap lm = {};
     count_kernel<2><<<n_slices, COUNT_THREADS, 0, s>>>(d_fasta, d_genomes, d_slices, P, lm, nullptr, d_first);
+    KM_CUDA(cudaGetLastError());
+    return KMERML_OK;
+}
+
+int launch_encode(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices, int n_slices,
+                  uint8_t* d_symbols, cudaStream_t s) {
+    if (n_slices <= 0) return KMERML_OK;
+    DenseParams P = make_params(1, 1, false, 1);
+    LevelMap lm = {};
+    count_kernel<3><<<n_slices, COUNT_THREADS, 0, s>>>(d_fasta, d_genomes, d_slices, P, lm, nullptr,
+                                                        reinterpret_cast<uint32_t*>(d_symbols));
     KM_CUDA(cudaGetLastError());
     return KMERML_OK;
 }

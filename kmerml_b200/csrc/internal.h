@@ -112,6 +112,8 @@ int launch_overflow(const LevelMap& lm, const RowSpec& row, int k, int k_bottom,
 int launch_finalize_low(const LevelMap& lm, const RowSpec& row, int k_top, int level_limit,
                         const GenomeStats* d_stats, float* d_freq, uint64_t freq_stride, uint32_t genome0,
                         int n_genomes, cudaStream_t s);
+int launch_encode(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices, int n_slices,
+                  uint8_t* d_symbols, cudaStream_t s);
 int launch_first_occurrence(const uint8_t* d_fasta, const GenomeDev* d_genomes, const Slice* d_slices,
                             int n_slices, int k, int min_rec, uint32_t* d_first, cudaStream_t s);
 int dense_setup_attributes();

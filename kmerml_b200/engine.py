@@ -465,6 +465,20 @@ def genome_stats_device(fasta):
             "gc_content": (gc / total) * 100 if total > 0 else 0}
 
 
+def encode_device(fasta, want_tallies=False):
+    """Stage 1 on its own: uint8 symbols of one FASTA file on the GPU -- 0..3 (A C G T) where the byte is a base of a
+    record, 255 elsewhere (kmerml/kmers/generate.py:39-41,55-56).  With want_tallies also the int64[4] device tensor
+    (contigs, total_size, G+C, N) of genome_stats_device."""
+    ctx = _lib.context(fasta.device.index)
+    sym = torch.empty(fasta.numel(), dtype=torch.uint8, device=fasta.device)
+    tallies = torch.zeros(4, dtype=torch.int64, device=fasta.device) if want_tallies else None
+    stream = torch.cuda.current_stream(fasta.device).cuda_stream
+    _lib.check(_lib.load().kmerml_encode(ctx.handle, fasta.data_ptr() if fasta.numel() else None, fasta.numel(),
+                                         sym.data_ptr() if sym.numel() else None,
+                                         tallies.data_ptr() if want_tallies else None, ctypes.c_void_p(stream)))
+    return (sym, tallies) if want_tallies else sym
+
+
 def kmer_count_stats_device(counts_row, k):
     """Summary of one k's count vector (int32 storage of uint32) as kmerml/utils/kmer_metadata.py:59-78 reports
     it for a k{k}.txt file: totals over the OBSERVED k-mers.  Reduction + radix-select kernels

@@ -141,3 +141,26 @@ def golden_big_cases():
     for c in cases:
         c["fasta"] = gzip.decompress(base64.b64decode(c["fasta_gz_b64"]))
     return cases
+
+
+def encode_reference(data):
+    """Plain restatement of stage 1 for kmerml_encode: 0..3 for A C G T (either case) inside records, 255 elsewhere
+    (header lines, line ends, other letters, text before the first '>' -- the SeqIO rule of SURVEY 8c).  Checked
+    against the oracle's k = 1 counts in test_host_layer.py."""
+    import numpy as np
+    out = np.full(len(data), 255, np.uint8)
+    code = {65: 0, 67: 1, 71: 2, 84: 3, 97: 0, 99: 1, 103: 2, 116: 3}
+    line_start, in_header, in_record = True, False, False
+    for i, ch in enumerate(data):
+        if ch in (10, 13):
+            line_start, in_header = True, False
+            continue
+        if line_start and ch == 62:
+            in_header = in_record = True
+        line_start = False
+        if in_header or not in_record:
+            continue
+        c = code.get(ch)
+        if c is not None:
+            out[i] = c
+    return out

@@ -404,3 +404,29 @@ def test_calls_on_different_streams_are_ordered():
     for i, res in results:
         for ki, k in enumerate(ks):
             assert np.array_equal(refs[i][ki], res.counts_numpy(0, k).astype(np.uint64)), (i, k)
+
+
+def test_encode_symbols():
+    """kmerml_encode (stage 1 on its own) against the byte-wise restatement in tests/helpers.py, itself pinned to the
+    oracle's k = 1 counts: fuzzed corner cases, a multi-slice genome with N runs, and the tallies."""
+    torch = torch_mod()
+    from helpers import encode_reference
+    from kmerml_b200 import engine, synth
+    rng = random.Random(21)
+    datas = [fuzz_fasta(rng) for _ in range(40)]
+    big = np.frombuffer(synth.fasta_bytes([300_000, 5, 120_000], seed=5).tobytes(), np.uint8).copy()
+    big[100_000:103_000][big[100_000:103_000] != 10] = ord("N")
+    datas.append(big.tobytes())
+    datas.append(b"")
+    for d in datas:
+        buf = np.concatenate([np.frombuffer(d, np.uint8), np.zeros(64, np.uint8)])
+        dev = torch.from_numpy(buf).cuda()[:len(d)]
+        sym, tallies = engine.encode_device(dev, want_tallies=True)
+        torch.cuda.synchronize()
+        want = encode_reference(d)
+        got = sym.cpu().numpy()
+        assert np.array_equal(got, want), (d[:60], np.nonzero(got != want)[0][:5])
+        assert int(tallies[1]) >= int((want < 4).sum())          # total_size counts N / IUPAC symbols too
+        st = engine.genome_stats_device(dev)
+        t = tallies.cpu().tolist()
+        assert (t[0], t[1], t[3]) == (st["contigs"], st["total_size"], st["n_count"])

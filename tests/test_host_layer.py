@@ -228,3 +228,17 @@ def test_clustering_entry_points_on_injected_distances():
     assert set(db) == {0, 1}
     with pytest.raises(ValueError):
         clustering.hierarchical_clustering(x, distances=np.zeros((3, 4)))
+
+
+def test_encode_restatement_agrees_with_the_oracle():
+    """tests/helpers.encode_reference (the checker of kmerml_encode) against the pinned oracle: the symbols it marks
+    are exactly the windows the oracle counts at k = 1."""
+    import random
+    import oracle
+    from helpers import encode_reference, fuzz_fasta, golden_extract_cases
+    rng = random.Random(11)
+    datas = [fuzz_fasta(rng) for _ in range(150)] + [c["fasta"] for c in golden_extract_cases()[:20]]
+    for d in datas:
+        sym = encode_reference(d)
+        hist = np.bincount(sym[sym < 4], minlength=4).astype(np.uint64)
+        assert np.array_equal(hist, oracle.count_dense(d, 1, 1)), d[:80]
