@@ -260,6 +260,20 @@ int kmerml_records_short(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbyte
 int kmerml_genome_stats(kmerml_ctx *ctx, const uint8_t *d_fasta, uint64_t nbytes, uint64_t *d_out, void *stream);
 
 /*
+ * The exchange step of the chunked single-genome path for hosts that drive NCCL themselves:
+ * sums a count row over the ranks of `nccl_comm` (a ncclComm_t passed as void*), in place, on `stream`.
+ *   reduce_scatter = 0: all-reduce -- every rank ends with the whole row;
+ *   reduce_scatter = 1: rank r ends with slice r, n / nranks elements at d_counts + r * (n / nranks)
+ *                       (n must divide evenly); the other slices of its buffer are left as they were.
+ * dtype: 0 = uint32, 1 = uint64.  Integer sums: bit-identical to counting the whole genome on one GPU.
+ * NCCL is taken from the calling process at run time (dlopen of libnccl.so.2 -- the one torch or the host
+ * application already loaded); this library does not link it, and the call fails with KMERML_ERR_ARG when there
+ * is none.  (kmerml_b200/dist.py makes the same exchange through torch.distributed.)
+ */
+int kmerml_allreduce_counts(kmerml_ctx *ctx, void *nccl_comm, void *d_counts, uint64_t n, int dtype,
+                            int reduce_scatter, void *stream);
+
+/*
  * Stage 1 on its own (SURVEY 8b `kmerml_encode`): the symbols of one FASTA file resident in HBM, as the counting
  * kernels see them after kmerml/kmers/generate.py:39-41,55-56 -- d_symbols[i] = 0..3 (A C G T, either case) when
  * byte i is a base of a record, 0xFF for everything else (header lines, line ends, N / IUPAC codes, blanks, text

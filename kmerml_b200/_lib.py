@@ -76,6 +76,7 @@ def load():
     L.kmerml_records_short.argtypes = [vp, vp, u64, vp, u32, i32, vp, vp]
     L.kmerml_genome_stats.argtypes = [vp, vp, u64, vp, vp]
     L.kmerml_encode.argtypes = [vp, vp, u64, vp, vp, vp]
+    L.kmerml_allreduce_counts.argtypes = [vp, vp, vp, u64, i32, i32, vp]
     L.kmerml_format_kmer_file.argtypes = [vp, i32, vp, vp, u32, u64, vp, u64, p64, p64, vp]
     L.kmerml_format_kmer_lines.argtypes = [vp, i32, vp, vp, u64, vp, u64, p64, vp]
     L.kmerml_parse_kmer_lines.argtypes = [vp, vp, vp, u64, vp, vp, ctypes.POINTER(ctypes.c_uint32), vp]
@@ -105,7 +106,7 @@ EXPORTS = [
     "kmerml_count_dense_host", "kmerml_first_occurrence", "kmerml_profile_enable",
     "kmerml_profile_read", "kmerml_find_records", "kmerml_records_short", "kmerml_static_features",
     "kmerml_normalize_rows", "kmerml_pairwise_distance", "kmerml_count_dense_range",
-    "kmerml_count_sparse", "kmerml_genome_stats", "kmerml_encode", "kmerml_format_kmer_file", "kmerml_format_kmer_lines",
+    "kmerml_count_sparse", "kmerml_genome_stats", "kmerml_encode", "kmerml_allreduce_counts", "kmerml_format_kmer_file", "kmerml_format_kmer_lines",
     "kmerml_count_sparse_range", "kmerml_merge_sparse", "kmerml_pairwise_distance_rows", "kmerml_sparse_fetch", "kmerml_ctx_set_host_threads", "kmerml_count_stats", "kmerml_column_stats",
     "kmerml_compact_row_bytes", "kmerml_count_dense_host_compact", "kmerml_compact_expand", "kmerml_compact_row_overflowed", "kmerml_compact_row_used_bytes",
     "kmerml_parse_kmer_lines", "kmerml_feature_keys", "kmerml_feature_line_lengths", "kmerml_feature_write_lines",

@@ -17,7 +17,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
-    "-shared", "-cudart", "static", "-Xcompiler", "-pthread",
+    "-shared", "-cudart", "static", "-Xcompiler", "-pthread", "-ldl",
 ]
 
 

@@ -1,5 +1,7 @@
 // api.cu -- the C-ABI of libkmerml_b200.so (include/kmerml_b200.h) and the host
 // orchestration of the dense counting path.  No torch types, no CPU fallback.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -1494,6 +1496,67 @@ int kmerml_first_occurrence(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nb
     int rc = single_genome_tables(ctx, ws, d_fasta, nbytes, s, &d_genomes, &d_slices, &n_slices);
     if (rc) return rc;
     return launch_first_occurrence(d_fasta, d_genomes, d_slices, n_slices, k, min_rec, d_first, s);
+}
+
+// NCCL through the process that called us (no link-time dependency): the four entry points the exchange needs.
+namespace {
+struct NcclApi {
+    int (*all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*reduce_scatter)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*comm_count)(void*, int*) = nullptr;
+    int (*comm_user_rank)(void*, int*) = nullptr;
+    const char* (*get_error_string)(int) = nullptr;
+    bool ok = false;
+};
+const NcclApi& nccl_api() {
+    static const NcclApi api = [] {
+        NcclApi a;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // the copy that is already in the process
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return a;
+        a.all_reduce = reinterpret_cast<decltype(a.all_reduce)>(dlsym(h, "ncclAllReduce"));
+        a.reduce_scatter = reinterpret_cast<decltype(a.reduce_scatter)>(dlsym(h, "ncclReduceScatter"));
+        a.comm_count = reinterpret_cast<decltype(a.comm_count)>(dlsym(h, "ncclCommCount"));
+        a.comm_user_rank = reinterpret_cast<decltype(a.comm_user_rank)>(dlsym(h, "ncclCommUserRank"));
+        a.get_error_string = reinterpret_cast<decltype(a.get_error_string)>(dlsym(h, "ncclGetErrorString"));
+        a.ok = a.all_reduce && a.reduce_scatter && a.comm_count && a.comm_user_rank;
+        return a;
+    }();
+    return api;
+}
+}  // namespace
+
+int kmerml_allreduce_counts(kmerml_ctx* ctx, void* nccl_comm, void* d_counts, uint64_t n, int dtype, int reduce_scatter,
+                            void* stream) {
+    if (!ctx || !nccl_comm || (n && !d_counts)) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (dtype < 0 || dtype > 1) return fail(KMERML_ERR_ARG, "dtype must be 0 (uint32) or 1 (uint64)");
+    const NcclApi& nccl = nccl_api();
+    if (!nccl.ok) return fail(KMERML_ERR_ARG, "no NCCL in this process (libnccl.so.2 could not be opened)");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    if (!n) return KMERML_OK;
+    constexpr int NCCL_UINT32 = 3, NCCL_UINT64 = 5, NCCL_SUM = 0;      // ncclDataType_t / ncclRedOp_t (nccl.h)
+    const int type = dtype == 0 ? NCCL_UINT32 : NCCL_UINT64;
+    const size_t elem = dtype == 0 ? 4 : 8;
+    auto nccl_fail = [&](int e, const char* what) {
+        return fail(KMERML_ERR_CUDA, std::string(what) + ": " + (nccl.get_error_string ? nccl.get_error_string(e) : "NCCL error"));
+    };
+    int e;
+    if (!reduce_scatter) {
+        if ((e = nccl.all_reduce(d_counts, d_counts, (size_t)n, type, NCCL_SUM, nccl_comm, (cudaStream_t)stream)))
+            return nccl_fail(e, "ncclAllReduce");
+        return KMERML_OK;
+    }
+    int ranks = 0, rank = 0;
+    if ((e = nccl.comm_count(nccl_comm, &ranks))) return nccl_fail(e, "ncclCommCount");
+    if ((e = nccl.comm_user_rank(nccl_comm, &rank))) return nccl_fail(e, "ncclCommUserRank");
+    if (ranks <= 0 || n % (uint64_t)ranks) return fail(KMERML_ERR_ARG, "the row length must be a multiple of the number of ranks");
+    const size_t per = (size_t)(n / (uint64_t)ranks);
+    if ((e = nccl.reduce_scatter(d_counts, (uint8_t*)d_counts + (size_t)rank * per * elem, per, type, NCCL_SUM, nccl_comm,
+                                 (cudaStream_t)stream)))
+        return nccl_fail(e, "ncclReduceScatter");
+    return KMERML_OK;
 }
 
 int kmerml_encode(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, uint8_t* d_symbols, uint64_t* d_tallies,

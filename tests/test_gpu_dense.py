@@ -430,3 +430,17 @@ def test_encode_symbols():
         st = engine.genome_stats_device(dev)
         t = tallies.cpu().tolist()
         assert (t[0], t[1], t[3]) == (st["contigs"], st["total_size"], st["n_count"])
+
+
+def test_allreduce_counts_entry_point():
+    """kmerml_allreduce_counts with a ncclComm_t made through NCCL's own API: a communicator of one rank
+    here; tools/nccl_abi_check.py under torchrun is the same check on N GPUs (run with 2 and 8, profiles/)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "nccl_abi_check.py")], capture_output=True, text=True,
+                       timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"ok"' in r.stdout
