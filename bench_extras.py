@@ -151,6 +151,7 @@ def run_c3(torch, dist, device, rank, world, steps, warmup, n_genomes=1000, mbp=
     counts = torch.zeros((max(len(mine), 1), M), dtype=torch.int32, device=device)
     totals = torch.zeros((max(len(mine), 1), 1), dtype=torch.int64, device=device)
     ev = {"count": [], "gather": [], "distance": []}
+    info = {"planes": 0}
 
     def mark():
         e = torch.cuda.Event(enable_timing=True)
@@ -164,24 +165,35 @@ def run_c3(torch, dist, device, rank, world, steps, warmup, n_genomes=1000, mbp=
                                       out_totals=totals[:len(mine)])
         b = mark()
         if world > 1:
-            pad = torch.zeros((n_max, M), dtype=torch.int32, device=device)
-            pad[:len(mine)] = counts[:len(mine)]
-            allc = torch.empty((world * n_max, M), dtype=torch.int32, device=device)
-            dist.all_gather_into_tensor(allc, pad)
-            rows = torch.empty((n_genomes, M), dtype=torch.int32, device=device)
-            for r, idxs in enumerate(shards):
-                if idxs:
-                    rows[torch.tensor(idxs, device=device)] = allc[r * n_max:r * n_max + len(idxs)]
+            # the rows travel as byte planes (2 of 4 for these counts), the norms and the largest count in one small
+            # all_gather before them; every rank then holds all rows in planar form and computes its genomes' block
+            got = []
+            D = kdist.distance_matrix_from_shards(counts[:len(mine)], shards, "cosine", info=info,
+                                                  on_gathered=lambda: got.append(mark()))
+            c = got[0]
         else:
-            rows = counts
-        c = mark()
-        D = kdist.distance_matrix_sharded(rows, "cosine")
+            c = mark()
+            D = kdist.distance_matrix_sharded(counts, "cosine")
         d = mark()
         ev["count"].append((a, b)); ev["gather"].append((b, c)); ev["distance"].append((c, d))
-        return rows, D
+        return D
 
-    ms, (rows, D) = T.timed(step, steps, warmup)
+    def gather_rows():                                   # (untimed: the uint32 matrix in genome order, for the checks)
+        if world == 1:
+            return counts
+        pad = torch.zeros((n_max, M), dtype=torch.int32, device=device)
+        pad[:len(mine)] = counts[:len(mine)]
+        allc = torch.empty((world * n_max, M), dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(allc, pad)
+        rows = torch.empty((n_genomes, M), dtype=torch.int32, device=device)
+        for r, idxs in enumerate(shards):
+            if idxs:
+                rows[torch.tensor(idxs, device=device)] = allc[r * n_max:r * n_max + len(idxs)]
+        return rows
+
+    ms, D = T.timed(step, steps, warmup)
     torch.cuda.synchronize()
+    rows = gather_rows()
     n_ev = len(ev["count"])
     parts_ms = {k: T.max_over_ranks(_event_ms(v[n_ev - steps:]) / steps) for k, v in ev.items()}
     # ---- checks
@@ -201,10 +213,11 @@ def run_c3(torch, dist, device, rank, world, steps, warmup, n_genomes=1000, mbp=
         dist_ok = bool(np.all(np.abs(got - want) <= 1e-6 * np.maximum(np.abs(want), 1e-30) + 1e-7))
     bases = float(n_genomes) * L
     return {"workload": f"C3: {n_genomes} genomes x {mbp:g} Mbp, k=8 count rows + cosine distance matrix, genomes sharded over "
-                        f"{world} GPU(s)", "ms": ms, "Gbp/s": bases / (ms * 1e-3) / 1e9,
+                        f"{world} GPU(s)" + (", rows all-gathered as byte planes, row-block distances, blocks gathered" if world > 1 else ""), "ms": ms, "Gbp/s": bases / (ms * 1e-3) / 1e9,
             "count_ms": parts_ms["count"], "gather_ms": parts_ms["gather"], "distance_ms": parts_ms["distance"],
             "count_Gbp/s_per_gpu": (len(mine) * L) / (parts_ms["count"] * 1e-3) / 1e9 if parts_ms["count"] > 0 else None,
-            "nvlink_bytes": int((world - 1) * n_max * M * 4 + (world - 1) * ((n_genomes + world - 1) // world) * n_genomes * 4) if world > 1 else 0,
+            "gathered_as": f"{info['planes']} byte plane(s) of the count rows + squared norms (not the uint32 rows)" if world > 1 else None,
+            "nvlink_bytes": int((world - 1) * n_max * (M * info["planes"] + 8) + (world - 1) * n_max * world * n_max * 4) if world > 1 else 0,
             "parity": {"sum_counts_equals_windows": T.all_true(ok_sum), "sharded_distance_bit_exact_vs_single_gpu": T.all_true(same_D),
                        "oracle_bit_exact_genome0": exact, "distance_within_1e-6_of_float64": dist_ok}}
 

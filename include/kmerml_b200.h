@@ -363,6 +363,22 @@ int kmerml_pairwise_distance_rows(kmerml_ctx *ctx, const uint32_t *d_counts, uin
                                   double *d_out64, void *stream);
 
 /*
+ * The same in two steps, for genomes counted on several GPUs: every rank turns ITS count rows into
+ * byte planes, the planes -- one byte per bin and plane, not the uint32 rows -- are gathered, and every rank computes
+ * its row block from the planes of all rows.
+ *   kmerml_count_planes: plane d (d = 0..3, at d_planes + d * plane_stride, n x m bytes) = byte d of every count;
+ *     d_sumsq[row] (may be NULL) = the row's exact squared norm; *d_max (device, zeroed by the caller) = atomicMax
+ *     of the counts: planes 0 .. (bytes needed for the largest count of ALL ranks) - 1 are the ones to gather.
+ *   kmerml_distance_rows_planes: rows [row_begin, row_end) of the n x n matrix from n_planes planes of all n rows
+ *     and their squared norms; rows of zeros (padding) are allowed.  Bit-identical to kmerml_pairwise_distance.
+ */
+int kmerml_count_planes(kmerml_ctx *ctx, const uint32_t *d_counts, uint64_t stride, int n, uint64_t m, uint8_t *d_planes,
+                        uint64_t plane_stride, double *d_sumsq, uint32_t *d_max, void *stream);
+int kmerml_distance_rows_planes(kmerml_ctx *ctx, const uint8_t *d_planes, uint64_t plane_stride, int n_planes, int n,
+                                uint64_t m, const double *d_sumsq, int row_begin, int row_end, int metric,
+                                float *d_out32, double *d_out64, void *stream);
+
+/*
  * Measurement hooks (bench.py): with profiling enabled every kernel the library
  * launches is bracketed by CUDA events on the launching stream.  kmerml_profile_read
  * synchronises those events and returns the accumulated device time per kernel family

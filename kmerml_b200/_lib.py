@@ -89,6 +89,8 @@ def load():
     L.kmerml_normalize_rows.argtypes = [vp, vp, u64, vp, i32, u64, vp, u64, vp]
     L.kmerml_pairwise_distance.argtypes = [vp, vp, i32, u64, i32, u64, i32, vp, vp, vp]
     L.kmerml_pairwise_distance_rows.argtypes = [vp, vp, u64, i32, u64, i32, i32, i32, vp, vp, vp]
+    L.kmerml_count_planes.argtypes = [vp, vp, u64, i32, u64, vp, u64, vp, vp, vp]
+    L.kmerml_distance_rows_planes.argtypes = [vp, vp, u64, i32, i32, u64, vp, i32, i32, i32, vp, vp, vp]
     L.kmerml_profile_enable.argtypes = [vp, i32]
     L.kmerml_profile_read.argtypes = [vp, ctypes.POINTER(Profile), i32]
     for name in EXPORTS:
@@ -107,7 +109,7 @@ EXPORTS = [
     "kmerml_profile_read", "kmerml_find_records", "kmerml_records_short", "kmerml_static_features",
     "kmerml_normalize_rows", "kmerml_pairwise_distance", "kmerml_count_dense_range",
     "kmerml_count_sparse", "kmerml_genome_stats", "kmerml_encode", "kmerml_allreduce_counts", "kmerml_format_kmer_file", "kmerml_format_kmer_lines",
-    "kmerml_count_sparse_range", "kmerml_merge_sparse", "kmerml_pairwise_distance_rows", "kmerml_sparse_fetch", "kmerml_ctx_set_host_threads", "kmerml_count_stats", "kmerml_column_stats",
+    "kmerml_count_sparse_range", "kmerml_merge_sparse", "kmerml_pairwise_distance_rows", "kmerml_count_planes", "kmerml_distance_rows_planes", "kmerml_sparse_fetch", "kmerml_ctx_set_host_threads", "kmerml_count_stats", "kmerml_column_stats",
     "kmerml_compact_row_bytes", "kmerml_count_dense_host_compact", "kmerml_compact_expand", "kmerml_compact_row_overflowed", "kmerml_compact_row_used_bytes",
     "kmerml_parse_kmer_lines", "kmerml_feature_keys", "kmerml_feature_line_lengths", "kmerml_feature_write_lines",
     "kmerml_emit_sparse_range", "kmerml_reduce_sparse_windows",

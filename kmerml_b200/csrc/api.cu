@@ -1347,6 +1347,40 @@ int kmerml_pairwise_distance_rows(kmerml_ctx* ctx, const uint32_t* d_counts, uin
                                    (cudaStream_t)stream);
 }
 
+int kmerml_count_planes(kmerml_ctx* ctx, const uint32_t* d_counts, uint64_t stride, int n, uint64_t m, uint8_t* d_planes,
+                        uint64_t plane_stride, double* d_sumsq, uint32_t* d_max, void* stream) {
+    if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
+    if (n < 0 || stride < m || plane_stride < (uint64_t)n * m) return fail(KMERML_ERR_ARG, "bad shape / stride");
+    if (n == 0) return KMERML_OK;
+    if (!d_counts || !d_planes || !d_max) return fail(KMERML_ERR_ARG, "null pointer argument");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    ctx->launches += 1;
+    return launch_count_planes(d_counts, stride, n, m, d_planes, plane_stride, d_sumsq, d_max, (cudaStream_t)stream);
+}
+
+int kmerml_distance_rows_planes(kmerml_ctx* ctx, const uint8_t* d_planes, uint64_t plane_stride, int n_planes, int n,
+                                uint64_t m, const double* d_sumsq, int row_begin, int row_end, int metric, float* d_out32,
+                                double* d_out64, void* stream) {
+    if (!ctx) return fail(KMERML_ERR_ARG, "ctx is null");
+    if (metric < 0 || metric > 1 || n < 0 || row_begin < 0 || row_end > n || row_begin > row_end)
+        return fail(KMERML_ERR_ARG, "bad metric / row range");
+    if (n_planes < 1 || n_planes > 4 || plane_stride < (uint64_t)n * m) return fail(KMERML_ERR_ARG, "bad planes");
+    if (row_begin == row_end) return KMERML_OK;
+    if (!d_planes || !d_sumsq || (!d_out32 && !d_out64)) return fail(KMERML_ERR_ARG, "null pointer argument");
+    if (m < 64 || m % 64) return fail(KMERML_ERR_ARG, "the row length must be a multiple of 64 (k >= 3)");
+    if (((uintptr_t)d_planes | plane_stride) & 15) return fail(KMERML_ERR_ARG, "planes must be 16-byte aligned");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(KMERML_ERR_CUDA, "cudaSetDevice failed");
+    Workspace& ws = ctx->ws[0];
+    if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
+    int rc = ws.part.ensure(distance_planes_workspace(n));
+    if (rc) return rc;
+    ctx->launches += (uint64_t)n_planes * n_planes + 1;
+    return launch_distance_rows_planes(d_planes, plane_stride, n_planes, n, m, d_sumsq, row_begin, row_end, metric, ws.part.p,
+                                       d_out32, d_out64, (cudaStream_t)stream);
+}
+
 static int count_sparse_core(kmerml_ctx* ctx, const uint8_t* d_fasta, uint64_t nbytes, uint64_t range_begin,
                              uint64_t range_end, int k, int min_record_len, unsigned flags, uint64_t* d_keys,
                              uint32_t* d_counts, uint32_t* d_first, uint64_t out_cap, uint64_t* h_unique,

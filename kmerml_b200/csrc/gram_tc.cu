@@ -23,22 +23,67 @@ constexpr int GT_M = 128, GT_N = 128, GT_KB = 64;       // tile and K block (byt
 constexpr int GT_KSPLIT = 8192;                         // features per accumulation: 255^2 * 8192 < 2^31
 constexpr int GT_THREADS = 128;
 
-__global__ void split_digits_kernel(const uint32_t* __restrict__ counts, uint64_t stride, int n, uint64_t m,
-                                    uint8_t* __restrict__ planes /* [4][n][m] */, unsigned int* max_count) {
-    const uint64_t total = (uint64_t)n * m;
+// One CTA per count row: its four byte planes (128-bit loads, one packed 32-bit store per plane and four bins), its
+// exact squared norm (uint64, then double -- the Gram diagonal a row-block distance needs for ALL genomes) and the
+// largest count (how many planes the Gram needs).  This is also what one rank of a sharded job runs on ITS rows
+// before the planes -- not the uint32 rows -- are gathered (kmerml_count_planes).
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const uint32_t* __restrict__ counts, uint64_t stride, uint64_t m, uint8_t* __restrict__ planes,
+                    uint64_t plane_stride, double* __restrict__ sumsq, unsigned int* __restrict__ max_count) {
+    const uint32_t row = blockIdx.x;
+    const uint32_t* c = counts + (uint64_t)row * stride;
+    uint8_t* out = planes + (uint64_t)row * m;
+    unsigned long long acc = 0;
     unsigned int mx = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t r = i / m, c = i % m;
-        const uint32_t v = counts[r * stride + c];
-        mx = max(mx, v);
-        planes[i] = (uint8_t)v;
-        planes[total + i] = (uint8_t)(v >> 8);
-        planes[2 * total + i] = (uint8_t)(v >> 16);
-        planes[3 * total + i] = (uint8_t)(v >> 24);
+    const bool vec = (reinterpret_cast<uintptr_t>(c) & 15) == 0 && ((reinterpret_cast<uintptr_t>(out) | plane_stride) & 3) == 0;
+    if (vec) {
+        for (uint64_t i = (uint64_t)threadIdx.x * 4; i < m; i += 256 * 4) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(c + i));
+            mx = max(max(mx, v.x), max(max(v.y, v.z), v.w));
+            acc += (unsigned long long)v.x * v.x + (unsigned long long)v.y * v.y + (unsigned long long)v.z * v.z +
+                   (unsigned long long)v.w * v.w;
+            // byte d of the four counts -> one word of plane d  (lo01 = x0 y0 x1 y1, hi01 = x2 y2 x3 y3, ...)
+            const uint32_t lo01 = __byte_perm(v.x, v.y, 0x5140), hi01 = __byte_perm(v.x, v.y, 0x7362);
+            const uint32_t lo23 = __byte_perm(v.z, v.w, 0x5140), hi23 = __byte_perm(v.z, v.w, 0x7362);
+            *reinterpret_cast<uint32_t*>(out + i) = __byte_perm(lo01, lo23, 0x5410);
+            *reinterpret_cast<uint32_t*>(out + plane_stride + i) = __byte_perm(lo01, lo23, 0x7632);
+            *reinterpret_cast<uint32_t*>(out + 2 * plane_stride + i) = __byte_perm(hi01, hi23, 0x5410);
+            *reinterpret_cast<uint32_t*>(out + 3 * plane_stride + i) = __byte_perm(hi01, hi23, 0x7632);
+        }
+    } else {
+        for (uint64_t i = threadIdx.x; i < m; i += 256) {
+            const uint32_t v = c[i];
+            mx = max(mx, v);
+            acc += (unsigned long long)v * v;
+            out[i] = (uint8_t)v;
+            out[plane_stride + i] = (uint8_t)(v >> 8);
+            out[2 * plane_stride + i] = (uint8_t)(v >> 16);
+            out[3 * plane_stride + i] = (uint8_t)(v >> 24);
+        }
     }
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_count, mx);
+    __shared__ unsigned long long s_acc[8];
+    __shared__ unsigned int s_mx[8];
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_acc[threadIdx.x >> 5] = acc; s_mx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { acc += s_acc[w]; mx = max(mx, s_mx[w]); }
+        if (sumsq) sumsq[row] = (double)acc;
+        if (mx) atomicMax(max_count, mx);
+    }
 }
+
+int launch_count_planes(const uint32_t* d_counts, uint64_t stride, int n, uint64_t m, uint8_t* d_planes,
+                        uint64_t plane_stride, double* d_sumsq, unsigned int* d_max, cudaStream_t s) {
+    if (n <= 0) return KMERML_OK;
+    split_planes_kernel<<<(unsigned)n, 256, 0, s>>>(d_counts, stride, m, d_planes, plane_stride, d_sumsq, d_max);
+    KM_CUDA(cudaGetLastError());
+    return KMERML_OK;
+}
+
 
 __device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     // cute::UMMA::SmemDescriptor: start >> 4 [0,14) | LBO >> 4 [16,30) | SBO >> 4 [32,46) | version 1 [46,48) | layout 0
@@ -207,8 +252,7 @@ int launch_gram_tc(const uint32_t* d_counts, uint64_t stride, int n, uint64_t m,
     unsigned long long* G = (unsigned long long*)(planes + ((4 * plane + 255) / 256) * 256);
     unsigned int* d_max = (unsigned int*)(G + (size_t)n * n);
     KM_CUDA(cudaMemsetAsync(G, 0, (size_t)n * n * 8 + 8, s));
-    split_digits_kernel<<<148 * 8, 256, 0, s>>>(d_counts, stride, n, m, planes, d_max);
-    KM_CUDA(cudaGetLastError());
+    if (int rc = launch_count_planes(d_counts, stride, n, m, planes, plane, nullptr, d_max, s)) return rc;
     unsigned int h_max = 0;
     KM_CUDA(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, s));
     KM_CUDA(cudaStreamSynchronize(s));
@@ -228,22 +272,6 @@ int launch_gram_tc(const uint32_t* d_counts, uint64_t stride, int n, uint64_t m,
     gram_to_double_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(G, d_gram, nn);
     KM_CUDA(cudaGetLastError());
     return KMERML_OK;
-}
-
-// Exact squared norms of the count rows (uint64, then double): the Gram diagonal every rank of a row-block
-// distance needs for ALL genomes.  One warp per row.
-__global__ void row_sumsq_kernel(const uint32_t* __restrict__ counts, uint64_t stride, int n, uint64_t m, double* __restrict__ out) {
-    const int row = (int)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= n) return;
-    const uint32_t* c = counts + (uint64_t)row * stride;
-    unsigned long long acc = 0;
-    for (uint64_t i = lane; i < m; i += 32) {
-        const unsigned long long v = c[i];
-        acc += v * v;
-    }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) out[row] = (double)acc;
 }
 
 // rows [row_begin, row_end) of the distance matrix from the row block of G and the squared norms of all rows
@@ -267,43 +295,58 @@ __global__ void distance_rows_kernel(const unsigned long long* __restrict__ G, c
     if (D64) D64[idx] = d;
 }
 
-size_t gram_rows_workspace(int n, uint64_t m) { return gram_tc_workspace(n, m) + (size_t)n * 8 + 256; }
 
-// Rows [row_begin, row_end) of the n x n distance matrix of uint32 count rows (all n rows resident): the unit one
-// rank computes when the genomes were counted on several GPUs and the rows gathered.  The Gram
-// entries are exact (tcgen05 kind::i8), so the block is bit-identical to the same rows of the single-GPU matrix.
+// Rows [row_begin, row_end) of the n x n distance matrix from the byte planes of ALL n count rows (plane d at
+// d_planes + d * plane_stride, n x m bytes) and their squared norms: the unit one rank computes when the genomes were
+// counted on several GPUs.  The Gram entries are exact (tcgen05 kind::i8), so the block is
+// bit-identical to the same rows of the single-GPU matrix.  workspace: n * n * 8 bytes.
+size_t distance_planes_workspace(int n) { return (size_t)n * n * 8 + 256; }
+
+int launch_distance_rows_planes(const uint8_t* d_planes, uint64_t plane_stride, int n_planes, int n, uint64_t m,
+                                const double* d_sumsq, int row_begin, int row_end, int metric, void* workspace,
+                                float* d_out32, double* d_out64, cudaStream_t s) {
+    if (row_begin >= row_end) return KMERML_OK;
+    unsigned long long* G = (unsigned long long*)workspace;
+    const int t0 = row_begin / GT_M, t1 = (row_end + GT_M - 1) / GT_M;
+    KM_CUDA(cudaMemsetAsync(G + (size_t)t0 * GT_M * n, 0, (size_t)(std::min(t1 * GT_M, n) - t0 * GT_M) * n * 8, s));
+    const unsigned tiles = (unsigned)((n + GT_N - 1) / GT_N);
+    const unsigned ksplits = (unsigned)((m + GT_KSPLIT - 1) / GT_KSPLIT);
+    for (int a = 0; a < n_planes; a++) {
+        for (int b = 0; b < n_planes; b++) {
+            if (8 * (a + b) >= 64) continue;
+            gram_i8_kernel<<<dim3(tiles, (unsigned)(t1 - t0), ksplits), GT_THREADS, 0, s>>>(
+                d_planes + a * plane_stride, d_planes + b * plane_stride, n, m, 0, 1ull << (8 * (a + b)), G, t0, 1);
+            KM_CUDA(cudaGetLastError());
+        }
+    }
+    const uint64_t cells = (uint64_t)(row_end - row_begin) * n;
+    distance_rows_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(G, d_sumsq, n, row_begin, row_end, metric, d_out32, d_out64);
+    KM_CUDA(cudaGetLastError());
+    return KMERML_OK;
+}
+
+int planes_needed(unsigned int max_count) {
+    return max_count >= (1u << 24) ? 4 : max_count >= (1u << 16) ? 3 : max_count >= (1u << 8) ? 2 : 1;
+}
+
+// The same from uint32 count rows resident on this GPU: planes + norms + largest count in one pass, then the above.
+size_t gram_rows_workspace(int n, uint64_t m) { return (size_t)4 * n * m + 256 + (size_t)n * 8 + 256 + distance_planes_workspace(n); }
+
 int launch_distance_rows_tc(const uint32_t* d_counts, uint64_t stride, int n, uint64_t m, int row_begin, int row_end,
                             int metric, void* workspace, float* d_out32, double* d_out64, cudaStream_t s) {
     if (row_begin >= row_end) return KMERML_OK;
     uint8_t* planes = (uint8_t*)workspace;
     const size_t plane = (size_t)n * m;
-    unsigned long long* G = (unsigned long long*)(planes + ((4 * plane + 255) / 256) * 256);
-    unsigned int* d_max = (unsigned int*)(G + (size_t)n * n);
-    double* d_norm = (double*)((uint8_t*)workspace + gram_tc_workspace(n, m) / 256 * 256 + 256);
-    const int t0 = row_begin / GT_M, t1 = (row_end + GT_M - 1) / GT_M;
-    KM_CUDA(cudaMemsetAsync(G + (size_t)t0 * GT_M * n, 0, (size_t)(std::min(t1 * GT_M, n) - t0 * GT_M) * n * 8, s));
+    double* d_norm = (double*)(planes + (4 * plane + 255) / 256 * 256);
+    unsigned int* d_max = (unsigned int*)(d_norm + n);
+    void* gws = (uint8_t*)d_norm + ((size_t)n * 8 + 8 + 255) / 256 * 256;
     KM_CUDA(cudaMemsetAsync(d_max, 0, 8, s));
-    split_digits_kernel<<<148 * 8, 256, 0, s>>>(d_counts, stride, n, m, planes, d_max);
-    row_sumsq_kernel<<<(unsigned)(((uint64_t)n * 32 + 255) / 256), 256, 0, s>>>(d_counts, stride, n, m, d_norm);
-    KM_CUDA(cudaGetLastError());
+    if (int rc = launch_count_planes(d_counts, stride, n, m, planes, plane, d_norm, d_max, s)) return rc;
     unsigned int h_max = 0;
     KM_CUDA(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, s));
     KM_CUDA(cudaStreamSynchronize(s));
-    const int nd = h_max >= (1u << 24) ? 4 : h_max >= (1u << 16) ? 3 : h_max >= (1u << 8) ? 2 : 1;
-    const unsigned tiles = (unsigned)((n + GT_N - 1) / GT_N);
-    const unsigned ksplits = (unsigned)((m + GT_KSPLIT - 1) / GT_KSPLIT);
-    for (int a = 0; a < nd; a++) {
-        for (int b = 0; b < nd; b++) {
-            if (8 * (a + b) >= 64) continue;
-            gram_i8_kernel<<<dim3(tiles, (unsigned)(t1 - t0), ksplits), GT_THREADS, 0, s>>>(
-                planes + a * plane, planes + b * plane, n, m, 0, 1ull << (8 * (a + b)), G, t0, 1);
-            KM_CUDA(cudaGetLastError());
-        }
-    }
-    const uint64_t cells = (uint64_t)(row_end - row_begin) * n;
-    distance_rows_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(G, d_norm, n, row_begin, row_end, metric, d_out32, d_out64);
-    KM_CUDA(cudaGetLastError());
-    return KMERML_OK;
+    return launch_distance_rows_planes(planes, plane, planes_needed(h_max), n, m, d_norm, row_begin, row_end, metric, gws,
+                                       d_out32, d_out64, s);
 }
 
 }  // namespace km

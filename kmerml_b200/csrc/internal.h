@@ -207,6 +207,12 @@ int launch_normalize_rows(const uint32_t* d_counts, uint64_t counts_stride, cons
 size_t gram_tc_workspace(int n, uint64_t m);
 int launch_gram_tc(const uint32_t* d_counts, uint64_t stride, int n, uint64_t m, void* workspace, double* d_gram,
                    cudaStream_t s);
+int launch_count_planes(const uint32_t* d_counts, uint64_t stride, int n, uint64_t m, uint8_t* d_planes,
+                        uint64_t plane_stride, double* d_sumsq, unsigned int* d_max, cudaStream_t s);
+size_t distance_planes_workspace(int n);
+int launch_distance_rows_planes(const uint8_t* d_planes, uint64_t plane_stride, int n_planes, int n, uint64_t m,
+                                const double* d_sumsq, int row_begin, int row_end, int metric, void* workspace,
+                                float* d_out32, double* d_out64, cudaStream_t s);
 size_t gram_rows_workspace(int n, uint64_t m);
 int launch_distance_rows_tc(const uint32_t* d_counts, uint64_t stride, int n, uint64_t m, int row_begin, int row_end,
                             int metric, void* workspace, float* d_out32, double* d_out64, cudaStream_t s);

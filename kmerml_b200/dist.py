@@ -178,6 +178,84 @@ def distance_matrix_sharded(counts, metric="cosine", rows_fn=None):
     return torch.cat(parts)[:n]
 
 
+def _all_gather_rows(out, block):
+    """out [world * b, ...] <- the ranks' equal blocks [b, ...], in rank order."""
+    import torch
+    import torch.distributed as dist
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(out, block)
+    else:
+        parts = [torch.empty_like(block) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, block)
+        b = block.shape[0]
+        for r, p in enumerate(parts):
+            out[r * b:(r + 1) * b] = p
+
+
+_POS_CACHE = {}
+
+
+def _gathered_positions(shards, device):
+    """Position of genome i in the gathered order (rank-major, every rank padded to the largest shard)."""
+    import torch
+    key = (tuple(tuple(s) for s in shards), str(device))
+    pos = _POS_CACHE.get(key)
+    if pos is None:
+        n_max = max(len(s) for s in shards)
+        n = sum(len(s) for s in shards)
+        host = np.zeros(n, dtype=np.int64)
+        for r, idxs in enumerate(shards):
+            for j, i in enumerate(idxs):
+                host[i] = r * n_max + j
+        pos = torch.from_numpy(host).to(device)
+        if len(_POS_CACHE) > 16:
+            _POS_CACHE.clear()
+        _POS_CACHE[key] = pos
+    return pos
+
+
+def distance_matrix_from_shards(counts, shards, metric="cosine", planes_fn=None, rows_fn=None, info=None, on_gathered=None):
+    """n x n distance matrix of genomes counted on several GPUs, WITHOUT gathering the uint32 rows: rank r holds the
+    count rows of the genomes shards[r] (in that order).  Every rank turns its rows into byte planes
+    (kmerml_count_planes), one small all_gather carries the squared norms and the largest count, the planes that
+    count needs -- one byte per bin and plane instead of four -- are all-gathered, every rank computes the row block of
+    its own genomes on the tensor cores (kmerml_distance_rows_planes) and one all_gather assembles the matrix, which
+    is then put into genome order.  Bit-identical to the single-GPU matrix of the gathered rows."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    rank, world = _world()
+    planes_fn = planes_fn if planes_fn is not None else engine.count_planes_device
+    rows_fn = rows_fn if rows_fn is not None else engine.distance_rows_planes_device
+    n = sum(len(s) for s in shards)
+    n_max = max(max(len(s) for s in shards), 1)
+    planes_l, sumsq_l, mx = planes_fn(counts[:len(shards[rank])], n_rows=n_max)
+    pos = _gathered_positions(shards, counts.device)
+    top = (mx.to(torch.int64) & 0xFFFFFFFF).to(torch.float64)
+    if world == 1:
+        nd = engine.planes_needed(int(top.item()))
+        block = rows_fn(planes_l, nd, sumsq_l, 0, n_max, metric)
+        return block[pos][:, pos]
+    meta = torch.cat([sumsq_l, top])
+    metas = torch.empty((world * (n_max + 1),), dtype=torch.float64, device=counts.device)
+    _all_gather_rows(metas, meta)
+    metas = metas.view(world, n_max + 1)
+    nd = engine.planes_needed(int(metas[:, -1].max().item()))
+    sumsq_all = metas[:, :n_max].reshape(-1).contiguous()
+    m = planes_l.shape[2]
+    planes_all = torch.empty((nd, world * n_max, m), dtype=torch.uint8, device=counts.device)
+    for p in range(nd):
+        _all_gather_rows(planes_all[p], planes_l[p])
+    if info is not None:
+        info["planes"] = nd
+    if on_gathered is not None:
+        on_gathered()
+    block = rows_fn(planes_all, nd, sumsq_all, rank * n_max, (rank + 1) * n_max, metric)
+    Dg = torch.empty((world * n_max, world * n_max), dtype=block.dtype, device=block.device)
+    _all_gather_rows(Dg, block)
+    return Dg[pos][:, pos]
+
+
 def count_genomes_sharded(fasta_list, k_values, *, min_record_len=None, canonical=False, gather=True, count_batch=None):
     """Dense counts of many genomes: this rank counts its LPT shard; with gather=True the rows
     of all ranks are assembled (in input order) on every rank with one all_gather per tensor.

@@ -304,6 +304,59 @@ def pairwise_distance_rows_device(counts, row_begin, row_end, metric="cosine", *
     return out
 
 
+def count_planes_device(counts, out_planes=None, n_rows=None):
+    """Byte planes of uint32 count rows (int32 storage): (planes uint8 [4, n_rows, m], squared norms float64 [n_rows],
+    largest count as a 1-element int32 device tensor).  n_rows >= counts.shape[0] pads with zero rows (equal blocks for
+    an all_gather).  What one rank of a sharded distance computation runs on ITS rows before the gather."""
+    if counts.dtype != torch.int32 or not counts.is_cuda or counts.dim() != 2 or counts.stride(1) != 1:
+        raise ValueError("counts must be a 2-D int32 CUDA tensor with contiguous rows")
+    n, m = counts.shape
+    rows = n if n_rows is None else int(n_rows)
+    if rows < n:
+        raise ValueError("n_rows smaller than the number of rows")
+    dev = counts.device
+    planes = out_planes if out_planes is not None else torch.empty((4, rows, m), dtype=torch.uint8, device=dev)
+    if planes.shape != (4, rows, m) or planes.dtype != torch.uint8 or not planes.is_contiguous():
+        raise ValueError("out_planes must be a contiguous uint8 [4, n_rows, m] tensor")
+    if rows > n:
+        planes[:, n:].zero_()
+    sumsq = torch.zeros(rows, dtype=torch.float64, device=dev)
+    mx = torch.zeros(2, dtype=torch.int32, device=dev)
+    if n:
+        ctx = _lib.context(dev.index)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.load().kmerml_count_planes(ctx.handle, counts.data_ptr(), counts.stride(0), n, m, planes.data_ptr(),
+                                                   rows * m, sumsq.data_ptr(), mx.data_ptr(), ctypes.c_void_p(stream)))
+    return planes, sumsq, mx[:1]
+
+
+def planes_needed(max_count):
+    """How many byte planes hold every count up to max_count (uint32)."""
+    max_count = int(max_count) & 0xFFFFFFFF
+    return 4 if max_count >= 1 << 24 else 3 if max_count >= 1 << 16 else 2 if max_count >= 1 << 8 else 1
+
+
+def distance_rows_planes_device(planes, n_planes, sumsq, row_begin, row_end, metric="cosine", *, out_dtype=torch.float32):
+    """Rows [row_begin, row_end) of the n x n distance matrix from the first n_planes byte planes of ALL n count rows
+    (uint8 [>= n_planes, n, m]) and their squared norms: bit-identical to pairwise_distance_device on the counts."""
+    if metric not in _METRIC_CODE:
+        raise ValueError(f"metric must be one of {sorted(_METRIC_CODE)}")
+    if planes.dtype != torch.uint8 or not planes.is_cuda or planes.dim() != 3 or not planes[0].is_contiguous():
+        raise ValueError("planes must be a uint8 CUDA tensor [planes, n, m] with contiguous planes")
+    _, n, m = planes.shape
+    out = torch.empty((max(row_end - row_begin, 0), n), dtype=out_dtype, device=planes.device)
+    if out.numel() == 0:
+        return out
+    ctx = _lib.context(planes.device.index)
+    stream = torch.cuda.current_stream(planes.device).cuda_stream
+    o32 = out.data_ptr() if out_dtype == torch.float32 else None
+    o64 = out.data_ptr() if out_dtype == torch.float64 else None
+    _lib.check(_lib.load().kmerml_distance_rows_planes(ctx.handle, planes.data_ptr(), planes.stride(0), int(n_planes), n, m,
+                                                       sumsq.data_ptr(), int(row_begin), int(row_end), _METRIC_CODE[metric],
+                                                       o32, o64, ctypes.c_void_p(stream)))
+    return out
+
+
 def count_dense_range_device(fasta, begin, end, k_values, min_record_len=None, canonical=False, partition=True):
     """(counts int32[row_len], totals int64[nk]) of the windows of ONE genome whose last base
     lies in bytes [begin, end): the additive unit of intra-genome / multi-GPU parallelism."""

@@ -165,6 +165,33 @@ def _worker(rank, world, port, results):
         for metric in ("cosine", "euclidean"):
             D = kdist.distance_matrix_sharded(X, metric, rows_fn=np_rows)
             ok &= bool(np.array_equal(D.numpy(), oracle.pairwise_distance(X.numpy().astype(np.float64), metric).astype(np.float32)))
+        # (6) the same from sharded rows, gathered as byte planes (uneven shards: 4 + 3 genomes, one count >= 256
+        # so that two planes travel); numpy stand-ins for the two kernels
+        shards = [[0, 2, 5, 6], [1, 3, 4]]
+        X2 = X.clone()
+        X2[3, 7] = 70000
+
+        def np_planes(counts, n_rows):
+            c = counts.numpy().view(np.uint32)
+            planes = np.zeros((4, n_rows, c.shape[1]), np.uint8)
+            for d in range(4):
+                planes[d, :c.shape[0]] = (c >> (8 * d)) & 0xFF
+            sumsq = np.zeros(n_rows)
+            sumsq[:c.shape[0]] = (c.astype(np.float64) ** 2).sum(axis=1)
+            return torch.from_numpy(planes), torch.from_numpy(sumsq), torch.tensor([int(c.max()) if c.size else 0], dtype=torch.int32)
+
+        def np_rows_planes(planes, nd, sumsq, r0, r1, metric):
+            p = planes.numpy().astype(np.float64)
+            full = sum(p[d] * 256.0 ** d for d in range(nd))
+            with np.errstate(invalid="ignore", divide="ignore"):
+                D = oracle.pairwise_distance(full, metric)
+            return torch.from_numpy(D[r0:r1].astype(np.float32))
+        for metric in ("cosine", "euclidean"):
+            info = {}
+            D = kdist.distance_matrix_from_shards(X2[shards[rank]], shards, metric, planes_fn=np_planes, rows_fn=np_rows_planes,
+                                                  info=info)
+            want = oracle.pairwise_distance(X2.numpy().astype(np.float64), metric).astype(np.float32)
+            ok &= info["planes"] == 3 and bool(np.array_equal(D.numpy(), want))
         results[rank] = ok
     finally:
         dist.destroy_process_group()

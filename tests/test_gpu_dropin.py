@@ -294,6 +294,35 @@ def test_distance_row_blocks_match_full_matrix():
         assert np.all(np.abs(got - want) <= RTOL * np.maximum(np.abs(want), 1e-30) + 1e-12)
 
 
+def test_distance_from_plane_shards_matches_full_matrix():
+    """kmerml_count_planes + kmerml_distance_rows_planes: the sharded C3 route (every rank splits ITS rows into byte
+    planes, the planes are gathered, row blocks from the planes) emulated on one GPU -- bit-identical to the single-call
+    matrix, for 1..4 planes, uneven shards with padding rows, strided input rows."""
+    import torch
+    from kmerml_b200 import engine
+    from kmerml_b200 import dist as kdist
+    rng = np.random.default_rng(12)
+    for n, m, hi, world in ((5, 64, 200, 2), (131, 4096, 70000, 3), (300, 65536, 900, 8), (40, 256, 2 ** 26, 4), (9, 128, 2 ** 20, 1)):
+        wide = torch.from_numpy(rng.integers(0, hi, (n, m + 8)).astype(np.int64).astype(np.uint32).view(np.int32)).cuda()
+        X = wide[:, :m]                                            # row stride m + 8: not contiguous
+        shards = kdist.shard_genomes([int(v) for v in rng.integers(1, 100, n)], world)
+        n_max = max(len(s) for s in shards)
+        for metric in ("cosine", "euclidean"):
+            full = engine.pairwise_distance_device(X.contiguous(), metric, out_dtype=torch.float64)
+            parts = [engine.count_planes_device(X[torch.tensor(s, dtype=torch.long, device="cuda")] if s else X[:0], n_rows=n_max)
+                     for s in shards]
+            top = max(int(p[2].item()) & 0xFFFFFFFF for p in parts)
+            nd = engine.planes_needed(top)
+            assert nd == engine.planes_needed(int(X.contiguous().view(-1).cpu().numpy().view(np.uint32).max()))
+            planes = torch.cat([p[0] for p in parts], dim=1)[:nd].contiguous()          # what the all_gathers assemble
+            sumsq = torch.cat([p[1] for p in parts])
+            blocks = [engine.distance_rows_planes_device(planes, nd, sumsq, r * n_max, (r + 1) * n_max, metric,
+                                                         out_dtype=torch.float64) for r in range(world)]
+            pos = kdist._gathered_positions(shards, X.device)
+            got = torch.cat(blocks)[pos][:, pos]
+            assert torch.equal(got, full), (n, m, hi, world, metric)
+
+
 def test_genome_and_kmer_metadata():
     """Genome tallies (genome_metadata.py:55-85) and k-mer file summaries (kmer_metadata.py:59-78) from the GPU."""
     import torch
