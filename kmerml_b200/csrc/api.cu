@@ -1376,7 +1376,7 @@ int kmerml_distance_rows_planes(kmerml_ctx* ctx, const uint8_t* d_planes, uint64
     if (int orc = order_stream(ctx, (cudaStream_t)stream)) return orc;
     int rc = ws.part.ensure(distance_planes_workspace(n));
     if (rc) return rc;
-    ctx->launches += (uint64_t)n_planes * n_planes + 1;
+    ctx->launches += 2;
     return launch_distance_rows_planes(d_planes, plane_stride, n_planes, n, m, d_sumsq, row_begin, row_end, metric, ws.part.p,
                                        d_out32, d_out64, (cudaStream_t)stream);
 }

@@ -106,7 +106,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 __global__ void __launch_bounds__(GT_THREADS)
 gram_i8_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, int n, uint64_t m, int symmetric_pair,
-               unsigned long long scale, unsigned long long* __restrict__ G, int row_tile0, int rows_only) {
+               unsigned long long scale, unsigned long long* __restrict__ G, int row_tile0, int rows_only,
+               uint32_t ksplit, int n_planes, uint64_t plane_stride) {
     // rows_only (multi-GPU row block): tile rows row_tile0 .. row_tile0 + gridDim.y - 1 against ALL columns, every
     // (a, b) digit pair launched separately, nothing mirrored: G holds rows [128 row_tile0, ...) only, at their
     // global row index.
@@ -119,8 +120,21 @@ gram_i8_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, int
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = (blockIdx.y + row_tile0) * GT_M, col0 = blockIdx.x * GT_N;
     if (!rows_only && symmetric_pair && col0 < row0) return;   // D_a D_a^T: the upper triangle is enough
-    const uint64_t k_begin = (uint64_t)blockIdx.z * GT_KSPLIT;
-    const uint64_t k_end = min(m, k_begin + GT_KSPLIT);
+    // n_planes > 0: ONE launch for every (a, b) digit pair -- blockIdx.z = pair * splits + split, A / B = the plane base
+    uint32_t zsplit = blockIdx.z;
+    if (n_planes > 0) {
+        const uint32_t splits = gridDim.z / (uint32_t)(n_planes * n_planes);
+        const uint32_t pair = blockIdx.z / splits;
+        zsplit = blockIdx.z % splits;
+        const uint32_t a = pair / (uint32_t)n_planes, b = pair % (uint32_t)n_planes;
+        if (8 * (a + b) >= 64) return;                      // a multiple of 2^64
+        A += (uint64_t)a * plane_stride;
+        B += (uint64_t)b * plane_stride;
+        scale = 1ull << (8 * (a + b));
+    }
+    const uint64_t k_begin = (uint64_t)zsplit * ksplit;
+    const uint64_t k_end = min(m, k_begin + ksplit);
+    if (k_begin >= k_end) return;
 
     const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
     if (tid == 0) {
@@ -264,7 +278,7 @@ int launch_gram_tc(const uint32_t* d_counts, uint64_t stride, int n, uint64_t m,
             if (8 * (a + b) >= 64) continue;                 // would not fit 64 bits anyway (counts^2 sums < 2^63 assumed)
             const unsigned long long scale = 1ull << (8 * (a + b));
             gram_i8_kernel<<<dim3(tiles, tiles, ksplits), GT_THREADS, 0, s>>>(planes + a * plane, planes + b * plane, n, m,
-                                                                             a == b ? 1 : 0, scale, G, 0, 0);
+                                                                             a == b ? 1 : 0, scale, G, 0, 0, GT_KSPLIT, 0, 0);
             KM_CUDA(cudaGetLastError());
         }
     }
@@ -309,16 +323,21 @@ int launch_distance_rows_planes(const uint8_t* d_planes, uint64_t plane_stride, 
     unsigned long long* G = (unsigned long long*)workspace;
     const int t0 = row_begin / GT_M, t1 = (row_end + GT_M - 1) / GT_M;
     KM_CUDA(cudaMemsetAsync(G + (size_t)t0 * GT_M * n, 0, (size_t)(std::min(t1 * GT_M, n) - t0 * GT_M) * n * 8, s));
+    // one launch for all digit pairs; the K range of a CTA shrinks (down to 1024 features) until the grid holds about
+    // four CTAs per SM: a row block of one rank of eight is 8 x 1 tiles, which at 8192 features per CTA and one
+    // launch per pair left 64 CTAs at a time on 148 SMs
     const unsigned tiles = (unsigned)((n + GT_N - 1) / GT_N);
-    const unsigned ksplits = (unsigned)((m + GT_KSPLIT - 1) / GT_KSPLIT);
-    for (int a = 0; a < n_planes; a++) {
-        for (int b = 0; b < n_planes; b++) {
-            if (8 * (a + b) >= 64) continue;
-            gram_i8_kernel<<<dim3(tiles, (unsigned)(t1 - t0), ksplits), GT_THREADS, 0, s>>>(
-                d_planes + a * plane_stride, d_planes + b * plane_stride, n, m, 0, 1ull << (8 * (a + b)), G, t0, 1);
-            KM_CUDA(cudaGetLastError());
-        }
-    }
+    const unsigned pairs = (unsigned)(n_planes * n_planes);
+    const uint64_t want_ctas = 148ull * 4;
+    const uint64_t base = (uint64_t)tiles * (unsigned)(t1 - t0) * pairs;
+    uint64_t splits = std::max<uint64_t>((m + GT_KSPLIT - 1) / GT_KSPLIT, (want_ctas + base - 1) / base);
+    splits = std::min<uint64_t>(splits, std::max<uint64_t>(m / 1024, 1));
+    uint32_t ksplit = (uint32_t)(((m + splits - 1) / splits + GT_KB - 1) / GT_KB * GT_KB);
+    if (ksplit > (uint32_t)GT_KSPLIT) ksplit = GT_KSPLIT;
+    const unsigned ksplits = (unsigned)((m + ksplit - 1) / ksplit);
+    gram_i8_kernel<<<dim3(tiles, (unsigned)(t1 - t0), ksplits * pairs), GT_THREADS, 0, s>>>(
+        d_planes, d_planes, n, m, 0, 1ull, G, t0, 1, ksplit, n_planes, plane_stride);
+    KM_CUDA(cudaGetLastError());
     const uint64_t cells = (uint64_t)(row_end - row_begin) * n;
     distance_rows_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(G, d_sumsq, n, row_begin, row_end, metric, d_out32, d_out64);
     KM_CUDA(cudaGetLastError());
