@@ -167,6 +167,8 @@ def distance_matrix_sharded(counts, metric="cosine", rows_fn=None):
     n = counts.shape[0]
     per = (n + world - 1) // world
     r0, r1 = min(rank * per, n), min((rank + 1) * per, n)
+    if world == 1 and rows_fn is None:
+        return engine.pairwise_distance_device(counts, metric)      # one GPU: the symmetric call (upper triangle only)
     fn = rows_fn if rows_fn is not None else engine.pairwise_distance_rows_device
     block = fn(counts, r0, r1, metric)
     if world == 1:
