@@ -433,7 +433,7 @@ def run_ours(args):
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tj = json.load(f)
         if dom and dom["kernel"] in tj:
-            # measured DRAM bytes per algorithmic byte (one ncu --set full capture on a 6-genome subset of this
+            # measured DRAM bytes per algorithmic byte (one ncu --set full capture on a 24-genome subset of this
             # workload), scaled to this launch
             traffic = tj[dom["kernel"]]["ratio"] * dom["alg_bytes_per_step"] / n_dom_launch
             traffic_src = tj["source"]
@@ -453,7 +453,7 @@ def run_ours(args):
         # the longest kernel of the step is not the HBM-bound one: say so, and put the HBM-bound kernel beside it
         bk = next((k for k in kernels if k["kernel"] == "bucket_kernel"), None)
         roofline["note"] = ("partition_kernel (the longest kernel) is bound by the shared-memory pipe, not by HBM (ncu r02: L1TEX "
-                            "82 % busy, DRAM 16 %): its algorithmic bytes are only the FASTA read.  The HBM-bound kernel of the "
+                            "76-82 % busy, DRAM 16 %): its algorithmic bytes are only the FASTA read.  The HBM-bound kernel of the "
                             "step is bucket_kernel (87 % of the step's algorithmic bytes); step_frac is the whole step")
         if bk:
             btr = None
